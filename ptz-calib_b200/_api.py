@@ -1,0 +1,204 @@
+"""Host-side mirror of the reference's solver interface for the hot path, over the C ABI.
+
+`PTZRayOptimizer` / `KRTOptimizer` keep the reference's names, argument meaning and error behaviour
+(src/core/ptzray_optimizer.h:112-177, src/core/krt_optimizer.h:108-145) on flat numpy inputs; the functions
+`ba_solve`, `ba_eval`, `reloc_solve_batch`, `reloc_eval` are the thin ctypes calls underneath.
+Everything here runs on the GPU through csrc/libptzcalib_b200.so; there is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi, lib, problem
+from .abi import as_ptr, f32, f64
+from .problem import BAProblem, BAResult, RelocBatch, RelocResult, default_options
+
+__all__ = ["abi", "problem", "BAProblem", "BAResult", "RelocBatch", "RelocResult", "default_options", "ba_solve", "ba_eval", "BAHandle",
+           "reloc_solve_batch", "reloc_eval", "PTZRayOptimizer", "KRTOptimizer", "device_count", "nccl_init_from_torch", "nccl_finalize"]
+
+
+def device_count() -> int:
+    return lib.load().ptz_device_count()
+
+
+# --------------------------------------------------------------------------------------------- BA
+def ba_solve(prob: BAProblem, opt=None, **kw) -> BAResult:
+    """ptzba_solve: one PTZRayOptimizer::Solve worth of work (ptzray_optimizer.cc:454-489) with host buffers."""
+    opt = opt or default_options(**kw)
+    c = prob.to_c()
+    r, arrs, log = problem.alloc_ba_result(prob)
+    rc = lib.load().ptzba_solve(C.byref(c), C.byref(opt), C.byref(r))
+    lib.check(rc, "ptzba_solve")
+    return problem.unpack_ba_result(prob, r, arrs, log)
+
+
+def ba_eval(prob: BAProblem, disp=None) -> problem.BAEval:
+    """ptzba_eval: residuals, analytic Jacobian, cost, gradient at the problem's parameters."""
+    c = prob.to_c()
+    e, (res, jo, jp, g) = problem.alloc_ba_eval(prob)
+    d = None if disp is None else f64(disp)
+    rc = lib.load().ptzba_eval(C.byref(c), as_ptr(d, C.c_double), C.byref(e))
+    lib.check(rc, "ptzba_eval")
+    return problem.BAEval(e.cost, res, jo, jp, g)
+
+
+class BAHandle:
+    """Resident problem (ptzba_create/run/destroy): upload + structure set-up once, LM iterations on demand."""
+
+    def __init__(self, prob: BAProblem, opt=None, **kw):
+        self.prob = prob
+        self.opt = opt or default_options(**kw)
+        self._c = prob.to_c()
+        self._h = C.c_void_p()
+        rc = lib.load().ptzba_create(C.byref(self._c), C.byref(self.opt), C.byref(self._h))
+        lib.check(rc, "ptzba_create")
+
+    def reset(self):
+        lib.check(lib.load().ptzba_reset(self._h), "ptzba_reset")
+
+    def run(self, max_new_iterations: int, want_outputs=True) -> BAResult:
+        r, arrs, log = problem.alloc_ba_result(self.prob)
+        if not want_outputs:
+            for k in arrs:
+                setattr(r, k, as_ptr(None, C.c_double))
+        rc = lib.load().ptzba_run(self._h, C.c_int(max_new_iterations), C.byref(r))
+        lib.check(rc, "ptzba_run")
+        return problem.unpack_ba_result(self.prob, r, arrs, log)
+
+    def stage_times(self) -> dict:
+        t = abi.StageTimesC()
+        lib.check(lib.load().ptzba_get_stage_times(self._h, C.byref(t)), "ptzba_get_stage_times")
+        return {k: getattr(t, k) for k, _ in abi.StageTimesC._fields_}
+
+    def close(self):
+        if self._h:
+            lib.load().ptzba_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------------------------------- reloc
+def reloc_solve_batch(batch: RelocBatch, opt=None, **kw) -> RelocResult:
+    """ptzreloc_solve_batch: B independent KRTOptimizer solves (krt_optimizer.cc:385-404), one CTA each."""
+    opt = opt or default_options(**kw)
+    c = batch.to_c()
+    r, arrs = problem.alloc_reloc_result(batch.B)
+    rc = lib.load().ptzreloc_solve_batch(C.byref(c), C.byref(opt), C.byref(r))
+    lib.check(rc, "ptzreloc_solve_batch")
+    return RelocResult(**arrs)
+
+
+def reloc_eval(ftype, uv_ref, uv_cur, ref21, local15):
+    uv_ref, uv_cur = f32(uv_ref).reshape(-1, 2), f32(uv_cur).reshape(-1, 2)
+    N = uv_ref.shape[0]
+    nf = len(abi.KRT_FREE[ftype])
+    res, jac, g, cost = np.zeros((N, 2)), np.zeros((N, 2, nf)), np.zeros(nf), C.c_double(0)
+    rc = lib.load().ptzreloc_eval(C.c_int(ftype), C.c_int(N), as_ptr(uv_ref, C.c_float), as_ptr(uv_cur, C.c_float), as_ptr(f64(ref21), C.c_double),
+                                  as_ptr(f64(local15), C.c_double), as_ptr(res, C.c_double), as_ptr(jac, C.c_double), C.byref(cost), as_ptr(g, C.c_double))
+    lib.check(rc, "ptzreloc_eval")
+    return res, jac, cost.value, g
+
+
+# --------------------------------------------------------------------------------------------- multi-GPU plumbing
+def nccl_init_from_torch():
+    """One process per GPU (torchrun).  Rank 0 makes the ncclUniqueId, torch.distributed broadcasts its 128 bytes,
+    every rank joins the library's own communicator (used only to all-reduce camera blocks)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        lib.check(lib.load().ptz_nccl_unique_id(buf), "ptz_nccl_unique_id")
+    t = torch.tensor(list(buf), dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.broadcast(t, src=0)
+    data = bytes(t.cpu().tolist())
+    buf2 = (C.c_ubyte * 128).from_buffer_copy(data)
+    lib.check(lib.load().ptz_nccl_init(buf2, C.c_int(rank), C.c_int(world)), "ptz_nccl_init")
+    return rank, world
+
+
+def nccl_finalize():
+    lib.check(lib.load().ptz_nccl_finalize(), "ptz_nccl_finalize")
+
+
+# --------------------------------------------------------------------------------------------- class mirrors
+class PTZRayOptimizer:
+    """Mirror of ptzcalib::PTZRayOptimizer (ptzray_optimizer.h:112-177) on flattened inputs.
+
+    Construct with a BAProblem (views = candidate cameras, observations = tracks after FindTracks) and `max_iter`;
+    `Solve()` returns True only on CONVERGENCE and only then exposes refined parameters (ptzray_optimizer.cc:482-487).
+    """
+
+    def __init__(self, prob: BAProblem, max_iter: int, factor_type=None):
+        self.prob = prob if factor_type is None else BAProblem(**{**prob.__dict__, "factor_type": factor_type})
+        self.max_iter = int(max_iter)
+        self.result = None
+        self._err = (0.0, 0.0, 0.0)
+
+    def CheckValid(self) -> bool:  # ptzray_optimizer.cc:515-535
+        p = self.prob
+        return p.V > 0 and self.max_iter > 0
+
+    def Solve(self):
+        """-> (ok, cams_world [V,21] or None, rays_world [P,3] or None)"""
+        if not self.CheckValid():
+            return False, None, None
+        self.result = ba_solve(self.prob, max_num_iterations=self.max_iter)
+        r = self.result
+        self._err = (r.final_reproj_error_all, r.final_reproj_error_2d2d, r.final_reproj_error_2d3d)
+        if r.converged:
+            return True, r.cams_world, r.rays_world
+        return False, None, None
+
+    def final_reproj_error_all(self):
+        return self._err[0]
+
+    def final_reproj_error_2d2d(self):
+        return self._err[1]
+
+    def final_reproj_error_2d3d(self):
+        return self._err[2]
+
+
+class KRTOptimizer:
+    """Mirror of ptzcalib::KRTOptimizer (krt_optimizer.h:108-145) for one query; the batched call is reloc_solve_batch."""
+
+    F, FDist, Fxfy, FxfyDist = abi.PTZ_KRT_F, abi.PTZ_KRT_FDIST, abi.PTZ_KRT_FXFY, abi.PTZ_KRT_FXFYDIST
+
+    def __init__(self, max_iter: int, max_reproj_error: float, factor_type: int):
+        self.max_iter, self.max_reproj_error, self.factor_type = int(max_iter), float(max_reproj_error), int(factor_type)
+        self.num_iter_ = 0
+        self._init = None
+        self._ref = None
+        self._uv = None
+
+    def SetInitParams(self, K, R, t, dist):  # krt_optimizer.cc:257-263
+        K, R = f64(K).reshape(3, 3), f64(R).reshape(3, 3)
+        self._init = np.concatenate([[K[0, 0], K[1, 1], K[0, 2], K[1, 2]], R.reshape(9), f64(t).reshape(3), f64(dist).reshape(5)])
+
+    def Add2d2dConstraints(self, cam_ref21, kpts_ref, kpts_curr, matches):  # krt_optimizer.cc:265-348
+        """cam_ref21: krt21 of the reference camera; kpts_*: [n,2] pixels; matches: [m,2] (queryIdx, trainIdx)"""
+        matches = np.asarray(matches, dtype=np.int64).reshape(-1, 2)
+        self._ref = f64(cam_ref21).reshape(21)
+        self._uv = (f32(kpts_ref).reshape(-1, 2)[matches[:, 0]], f32(kpts_curr).reshape(-1, 2)[matches[:, 1]])
+
+    def Solve(self):
+        """-> (ok, K, R, t, dist); outputs are None unless ok (krt_optimizer.cc:398-403)"""
+        uv1, uv2 = self._uv
+        batch = RelocBatch(self.factor_type, np.array([0, len(uv1)], np.int64), uv1, uv2, self._ref[None], self._init[None], self.max_iter,
+                           self.max_reproj_error)
+        res = reloc_solve_batch(batch)
+        self.num_iter_ = int(res.num_iter[0])
+        if not res.success[0]:
+            return False, None, None, None, None
+        c = res.cam[0]
+        K = np.array([[c[0], 0, c[2]], [0, c[1], c[3]], [0, 0, 1.0]])
+        return True, K, c[4:13].reshape(3, 3).copy(), c[13:16].copy(), c[16:21].copy()

@@ -1,0 +1,195 @@
+"""The oracle against the golden vectors (OpenCV-python, mpmath, scipy): this is what pins the checker.
+CPU only.  Tolerances: values 1e-9 px absolute (cv2 and the oracle round differently at the 1e-12 level on
+pixel magnitudes of 1e3); exact Jacobians 1e-9 relative to the row scale."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from ptz_calib_b200 import abi, problem
+
+
+def test_rodrigues_matches_opencv(orc, opencv_kat):
+    k = opencv_kat
+    for r, R in zip(k["rod_r"], k["rod_R"]):
+        assert np.abs(orc.rodrigues(r) - R).max() < 1e-14
+    for R, r in zip(k["rodinv_R"], k["rodinv_r"]):
+        got = orc.rodrigues_inv(R)
+        # near pi the two branches may return the antipodal representation of the same rotation
+        if np.abs(got - r).max() > 1e-9:
+            assert np.abs(orc.rodrigues(got) - R).max() < 1e-9 and np.linalg.norm(r) > 3.1
+        else:
+            assert np.abs(got - r).max() < 1e-9
+
+
+def test_undistort_matches_opencv(orc, opencv_kat):
+    k = opencv_kat
+    bad = 0
+    for K4, d, uv, out in zip(k["und_K4"], k["und_d"], k["und_uv"], k["und_out"]):
+        got = orc.undistort_point(uv, K4, d)
+        assert got.dtype == np.float32
+        # float32 rounding of a double that may differ in the last place between OpenCV builds
+        if not np.array_equal(got, out):
+            bad += 1
+            assert np.abs(got.astype(float) - out.astype(float)).max() <= 2.5e-4 * max(1.0, np.abs(out).max() / 1000)
+    assert bad <= 3, bad
+
+
+@pytest.mark.parametrize("t", [0, 1, 2, 3])
+def test_ba_ray_factor_values(orc, functor_kat, t):
+    k = functor_kat
+    n = len(k[f"ba{t}_uv"])
+    err = 0.0
+    for i in range(n):
+        got = orc.ba_ray_factor(t, k[f"ba{t}_intr"][i], k[f"ba{t}_ext"][i], k[f"ba{t}_ray"][i], k[f"ba{t}_uv"][i], k[f"ba{t}_disp"][i])
+        err = max(err, relerr(got, k[f"ba{t}_res_cv"][i], floor=1e3))
+    assert err < 1e-11, err
+    # 60-digit values
+    for j, i in enumerate(k[f"ba{t}_mp_idx"]):
+        got = orc.ba_ray_factor(t, k[f"ba{t}_intr"][i], k[f"ba{t}_ext"][i], k[f"ba{t}_ray"][i], k[f"ba{t}_uv"][i], k[f"ba{t}_disp"][i])
+        assert relerr(got, k[f"ba{t}_res_mp"][j], floor=1e3) < 1e-12
+
+
+@pytest.mark.parametrize("t", [0, 3])
+def test_ba_pt_factor_values(orc, functor_kat, t):
+    k = functor_kat
+    p = f"pt{t}"
+    for i in range(len(k[p + "_uv"])):
+        got = orc.ba_pt_factor(t, k[p + "_intr"][i], k[p + "_ext"][i], k[p + "_tlw"][i], k[p + "_uv"][i], k[p + "_xyz"][i], k[p + "_disp"][i])
+        assert relerr(got, k[p + "_res_cv"][i], floor=1e3) < 1e-10
+
+
+@pytest.mark.parametrize("t", [0, 1, 2, 3])
+def test_krt_2d2d_factor_values(orc, functor_kat, t):
+    k = functor_kat
+    p = f"krt{t}"
+    n_masked = 0
+    for i in range(len(k[p + "_uv1"])):
+        got = orc.krt_2d2d_factor(t, k[p + "_cam"][i], k[p + "_refK"][i], k[p + "_refd"][i], k[p + "_uv1"][i], k[p + "_uv2"][i])
+        want = k[p + "_res_cv"][i]
+        n_masked += int(np.all(want == 0))
+        # the undistorted reference pixel is float32: one ulp there moves the residual by ~1e-4 px * f2/f1
+        tol = 1e-11 if t in (0, 2) else 2e-7
+        assert relerr(got, want, floor=1e3) < tol, (i, got, want)
+    if t in (1, 3):
+        assert n_masked > 0  # the border mask branch (krt_optimizer.cc:95-101) is exercised
+
+
+@pytest.mark.parametrize("t", [0, 2])
+def test_krt_2d3d_factor_values_and_jacobian(orc, functor_kat, t):
+    k = functor_kat
+    p = f"krt3d{t}"
+    for i in range(len(k[p + "_uv"])):
+        cam = k[p + "_cam"][i]
+        got = orc.krt_2d3d_factor(t, cam, k[p + "_uv"][i], k[p + "_xyz"][i])
+        assert relerr(got, k[p + "_res_cv"][i], floor=1e3) < 1e-11
+        # cv2's analytic Jacobian of the projection: columns rvec, tvec, fx, fy, cx, cy, k1,k2,p1,p2,k3; residual = uv - proj
+        J = orc.krt_2d3d_jac(t, cam, k[p + "_uv"][i], k[p + "_xyz"][i])
+        Jcv = -k[p + "_jac_cv"][i]
+        scale = np.abs(Jcv).max()
+        assert np.abs(J[:, 4:7] - Jcv[:, 0:3]).max() < 1e-9 * scale
+        assert np.abs(J[:, 7:10] - Jcv[:, 3:6]).max() < 1e-9 * scale
+        assert np.abs(J[:, 10:15] - Jcv[:, 10:15]).max() < 1e-9 * scale
+        if t == 2:
+            assert np.abs(J[:, 0:2] - Jcv[:, 6:8]).max() < 1e-9 * scale
+        else:  # fy tied to fx: d/dfx is the sum of cv2's fx and fy columns
+            assert np.abs(J[:, 0] - (Jcv[:, 6] + Jcv[:, 7])).max() < 1e-9 * scale
+
+
+def _ba_single(t, k, i, uv):
+    """a one-observation BAProblem at KAT sample i, so that ba_eval returns that sample's Jacobian"""
+    return problem.BAProblem(factor_type=t, intr=k[f"ba{t}_intr"][i][None], ext=k[f"ba{t}_ext"][i][None], obs_uv=uv[None], obs_view=[0], obs_track=[0],
+                             track_weight=[1.0], ray0=k[f"ba{t}_ray"][i][None])
+
+
+@pytest.mark.parametrize("t", [0, 1, 2, 3])
+def test_ba_exact_jacobian_matches_mpmath(orc, functor_kat, t):
+    k = functor_kat
+    nci = 2 if t == 0 else 3
+    for j, i in enumerate(k[f"ba{t}_mp_idx"]):
+        p = _ba_single(t, k, i, k[f"ba{t}_uv"][i])
+        e = orc.ba_eval(p, disp=k[f"ba{t}_disp"][i] if t == 3 else None)
+        Jmp = k[f"ba{t}_jac_mp"][j]  # columns: intr(9) [disp(3)] ext(6) ray(3)
+        o = 12 if t == 3 else 9
+        cols = [0, 1] + ([4] if nci == 3 else []) + [o, o + 1, o + 2] + [o + 6, o + 7, o + 8] + ([9, 10, 11] if t == 3 else [])
+        want = Jmp[:, cols]
+        if t != 2:
+            want[:, 1] = 0.0  # fy is tied to fx: its own column is identically zero
+        got = e.jac_obs[0]
+        scale = np.abs(want).max(axis=1, keepdims=True)
+        assert np.abs(got - want).max() / scale.max() < 1e-10, (i, np.abs(got - want).max(), scale.max())
+        # Ceres CENTRAL numeric differentiation is within its own noise floor of the exact derivative
+        e1 = orc.ba_eval(p, disp=k[f"ba{t}_disp"][i] if t == 3 else None, jacobian_mode=1)
+        # (the disp columns are excluded: disp[2] multiplies f^2 ~ 1e7, so Ceres' minimum step sqrt(eps) is a
+        #  finite, non-infinitesimal perturbation there and its numeric column is not a derivative at all)
+        nd = want.shape[1] - (3 if t == 3 else 0)
+        assert np.abs(e1.jac_obs[0][:, :nd] - want[:, :nd]).max() / np.abs(want[:, :nd]).max() < 5e-7
+
+
+@pytest.mark.parametrize("t", [0, 3])
+def test_ba_pt_exact_jacobian_matches_mpmath(orc, functor_kat, t):
+    k = functor_kat
+    p_ = f"pt{t}"
+    nci = 2 if t == 0 else 3
+    for q in range(len(k[p_ + "_jac_mp"])):
+        prob = problem.BAProblem(factor_type=t, intr=k[p_ + "_intr"][q][None], ext=k[p_ + "_ext"][q][None], obs_uv=np.zeros((0, 2), np.float32), obs_view=[],
+                                 obs_track=[], track_weight=[], pt_uv=k[p_ + "_uv"][q][None], pt_xyz=k[p_ + "_xyz"][q][None], pt_view=[0], tlw0=k[p_ + "_tlw"][q])
+        e = orc.ba_eval(prob, disp=k[p_ + "_disp"][q] if t == 3 else None)
+        Jmp = k[p_ + "_jac_mp"][q]  # intr(9) [disp(3)] ext(6) tlw(6)
+        o = 12 if t == 3 else 9
+        cols = [0, 1] + ([4] if nci == 3 else []) + [o, o + 1, o + 2] + list(range(o + 6, o + 12)) + ([9, 10, 11] if t == 3 else [])
+        want = Jmp[:, cols]
+        assert np.abs(e.jac_pts[0] - want).max() / np.abs(want).max() < 1e-10
+
+
+@pytest.mark.parametrize("t", [0, 1, 2, 3])
+def test_krt_exact_jacobian_matches_mpmath(orc, functor_kat, t):
+    k = functor_kat
+    p = f"krt{t}"
+    free = abi.KRT_FREE[t]
+    for j, i in enumerate(k[p + "_mp_idx"]):
+        ref21 = np.zeros(21)
+        ref21[:4] = k[p + "_refK"][i]
+        ref21[4:13] = np.eye(3).ravel()
+        ref21[16:21] = k[p + "_refd"][i]
+        res, jac, cost, g = orc.reloc_eval(t, k[p + "_uv1"][i][None], k[p + "_uv2"][i][None], ref21, k[p + "_cam"][i])
+        want = k[p + "_jac_mp"][j][:, free].copy()
+        if t in (0, 1):  # fy tied: d/dfx picks up the fy column
+            want[:, 0] = k[p + "_jac_mp"][j][:, 0]
+        assert np.abs(jac[0] - want).max() / np.abs(want).max() < 1e-9, (i, jac[0], want)
+
+
+def test_reloc_minimum_matches_scipy(orc, lm_kat):
+    """gauge-fixed: the oracle's LM run to tight tolerances lands on scipy's minimiser"""
+    k = lm_kat
+    for t in (0, 1):
+        b = problem.RelocBatch(t, k[f"reloc{t}_offset"], k[f"reloc{t}_uv_ref"], k[f"reloc{t}_uv_cur"], k[f"reloc{t}_ref"], k[f"reloc{t}_init"])
+        r = orc.reloc_solve_batch(b, function_tolerance=1e-15, parameter_tolerance=1e-14, gradient_tolerance=1e-12, max_num_iterations=200)
+        sol = k[f"reloc{t}_sol"]
+        assert np.all(r.termination == abi.PTZ_CONVERGENCE)
+        assert relerr(r.final_cost, k[f"reloc{t}_cost"], floor=1e-30) < 1e-9
+        assert np.abs(r.local_cam15[:, 4:7] - sol[:, 4:7]).max() < 1e-8  # rad
+        assert np.abs(r.local_cam15[:, 0] - sol[:, 0]).max() < 1e-5  # px focal
+        if t == 1:
+            assert np.abs(r.local_cam15[:, 10] - sol[:, 10]).max() < 1e-7
+        # default (Ceres) tolerances: same minimum to the function-tolerance level
+        r2 = orc.reloc_solve_batch(b)
+        assert np.all(r2.success == 1)
+        assert relerr(r2.final_cost, k[f"reloc{t}_cost"], floor=1e-30) < 1e-5
+
+
+def test_ba_minimum_matches_scipy(orc, lm_kat):
+    """free gauge: compare cost, focals and relative rotations R_i R_0^T"""
+    k = lm_kat
+    for t in (0, 1):
+        p = problem.BAProblem(factor_type=t, intr=k[f"ba{t}_intr"], ext=k[f"ba{t}_ext"], obs_uv=k[f"ba{t}_obs_uv"], obs_view=k[f"ba{t}_obs_view"],
+                              obs_track=k[f"ba{t}_obs_track"], track_weight=k[f"ba{t}_track_weight"])
+        assert np.abs(orc.ba_init_rays(p) - k[f"ba{t}_ray0"]).max() < 1e-13  # Pix2Ray
+        rc, r = orc.ba_solve(p, function_tolerance=1e-16, parameter_tolerance=1e-15, gradient_tolerance=1e-12, max_num_iterations=300)
+        assert rc == 0
+        assert abs(r.final_cost - float(k[f"ba{t}_cost"])) / float(k[f"ba{t}_cost"]) < 1e-8
+        assert np.abs(r.intr[:, 0] - k[f"ba{t}_sol_intr"][:, 0]).max() < 1e-2  # weakly determined with 6 views; cost is flat there
+        Ra = np.array([orc.rodrigues(e[:3]) for e in r.ext])
+        Rb = np.array([orc.rodrigues(e[:3]) for e in k[f"ba{t}_sol_ext"]])
+        rel_a = Ra @ Ra[0].T
+        rel_b = Rb @ Rb[0].T
+        assert np.abs(rel_a - rel_b).max() < 1e-5

@@ -1,0 +1,742 @@
+// ba_kernels.cuh — the kernels of one Levenberg–Marquardt iteration of PTZ bundle adjustment (fp64, sm_100a).
+//
+// Stage 1  k_view_prep, k_resjac, k_view_finalize, k_track_accum      residual + analytic Jacobian, block reductions
+// Stage 2  k_track_solve, k_schur_diag, k_schur_offdiag, k_precond    ray elimination, Schur complement onto cameras
+// Stage 3  k_pcg                                                      block-Jacobi PCG on the reduced camera system
+// Stage 4  k_track_backsub, k_cam_update, k_cost, k_scalars           back-substitution, damping bookkeeping, cost
+//
+// They replace what ceres::Solve does per iteration behind ptzray_optimizer.cc:475.
+// Memory-bound small-block work: no tensor cores; layouts are chosen so that every pass streams contiguous,
+// 16-byte-aligned records and the per-view tables are CTA-uniform.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "ptz_math.cuh"
+
+namespace ptz {
+namespace cg = cooperative_groups;
+
+constexpr int kChunk = 128;      // observations per CTA in the streaming passes; chunks never straddle a view
+constexpr int kMaxBorder = 32;   // dense border (tlw + per-annotated-view fy): one warp owns it in the PCG
+
+template <int NCL>
+struct Dims {
+  static constexpr int RS = 8 + 2 * NCL;            // record: r(2) E(6) F(2*NCL)            [doubles]
+  static constexpr int WS = (3 * NCL + 1) & ~1;     // What record: NCL x 3, padded to even
+  static constexpr int NU = NCL * (NCL + 1) / 2;    // upper triangle of a camera block
+  static constexpr int NPART = NU + NCL + 1;        // chunk partial: U upper, g, cost
+};
+
+// per-track parameter record: ray(3), sqrt(weight), Jacobi scale(3), pad
+constexpr int kTrk = 8;
+
+// -------------------------------------------------------------------------------------------------------------
+// stage 1
+// -------------------------------------------------------------------------------------------------------------
+__global__ void k_view_prep(int V, const double* __restrict__ intr, const double* __restrict__ ext, ViewTab* __restrict__ vt, int with_jac) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  double in[9], ex[6];
+  for (int j = 0; j < 9; ++j) in[j] = intr[9 * i + j];
+  for (int j = 0; j < 6; ++j) ex[j] = ext[6 * i + j];
+  ViewTab t;
+  make_view_tab(in, ex, &t, with_jac != 0);
+  vt[i] = t;
+}
+
+// One CTA per chunk of one view.  Each thread: one observation -> weighted, Jacobi-scaled residual/Jacobian record,
+// plus the chunk's partial camera block (U upper, g) and cost by a fixed-order block reduction.
+template <int TYPE>
+__global__ void __launch_bounds__(kChunk) k_resjac(const int* __restrict__ chunk_view, const int* __restrict__ chunk_begin, const int* __restrict__ chunk_cnt,
+                                                   const float2* __restrict__ o_uv, const int* __restrict__ o_track, const ViewTab* __restrict__ vt,
+                                                   const double* __restrict__ trk, const double* __restrict__ scale_cam, const double* __restrict__ disp,
+                                                   int weighted, double* __restrict__ rec, double* __restrict__ part) {
+  constexpr int NCL = ba_ncl(TYPE);
+  typedef Dims<NCL> D;
+  __shared__ ViewTab svt;
+  __shared__ double ssc[NCL];
+  __shared__ double sred[D::NPART * (kChunk / 32)];
+  const int chunk = blockIdx.x;
+  const int view = chunk_view[chunk], begin = chunk_begin[chunk], cnt = chunk_cnt[chunk];
+  if (threadIdx.x < 48) reinterpret_cast<double*>(&svt)[threadIdx.x] = reinterpret_cast<const double*>(vt + view)[threadIdx.x];
+  if (threadIdx.x < NCL) ssc[threadIdx.x] = scale_cam[view * NCL + threadIdx.x];
+  __syncthreads();
+  double acc[D::NPART];
+#pragma unroll
+  for (int i = 0; i < D::NPART; ++i) acc[i] = 0.0;
+  if (threadIdx.x < cnt) {
+    const int o = begin + threadIdx.x;
+    const float2 uv = o_uv[o];
+    const int p = o_track[o];
+    const double4 t0 = *reinterpret_cast<const double4*>(trk + (size_t)p * kTrk);
+    const double4 t1 = *reinterpret_cast<const double4*>(trk + (size_t)p * kTrk + 4);
+    const double ray[3] = {t0.x, t0.y, t0.z};
+    double dz[3] = {0, 0, 0};
+    if (TYPE == BA_PTZRAY_DIST_DISP) { dz[0] = disp[0]; dz[1] = disp[1]; dz[2] = disp[2]; }
+    double r[2], F[2 * NCL], E[6];
+    ba_obs<TYPE, true>(svt, ray, dz, (double)uv.x, (double)uv.y, r, F, E, nullptr);
+    const double sw = weighted ? t0.w : 1.0;
+    r[0] *= sw; r[1] *= sw;
+    const double sr[3] = {t1.x * sw, t1.y * sw, t1.z * sw};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { E[j] *= sr[j]; E[3 + j] *= sr[j]; }
+#pragma unroll
+    for (int a = 0; a < NCL; ++a) { const double s = ssc[a] * sw; F[a] *= s; F[NCL + a] *= s; }
+    double* out = rec + (size_t)o * D::RS;
+    double2* o2 = reinterpret_cast<double2*>(out);
+    o2[0] = make_double2(r[0], r[1]);
+    o2[1] = make_double2(E[0], E[1]); o2[2] = make_double2(E[2], E[3]); o2[3] = make_double2(E[4], E[5]);
+#pragma unroll
+    for (int a = 0; a < NCL; ++a) o2[4 + a] = make_double2(F[2 * a], F[2 * a + 1]);  // F stored flat [2*NCL]
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < NCL; ++a)
+#pragma unroll
+      for (int b = a; b < NCL; ++b) acc[k++] = F[a] * F[b] + F[NCL + a] * F[NCL + b];
+#pragma unroll
+    for (int a = 0; a < NCL; ++a) acc[D::NU + a] = F[a] * r[0] + F[NCL + a] * r[1];
+    acc[D::NU + NCL] = 0.5 * (r[0] * r[0] + r[1] * r[1]);
+  }
+  block_sum<D::NPART>(acc, sred);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < D::NPART; ++i) part[(size_t)chunk * D::NPART + i] = acc[i];
+  }
+}
+
+// per view: sum the chunk partials in chunk order -> full symmetric U[NCL*NCL], g[NCL], cost; |g/s| for the gradient norm
+template <int NCL>
+__global__ void k_view_finalize(int V, const int* __restrict__ view_chunk_off, const double* __restrict__ part, const double* __restrict__ scale_cam,
+                                double* __restrict__ U, double* __restrict__ g, double* __restrict__ cost_view, double* __restrict__ gabs) {
+  typedef Dims<NCL> D;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = idx / D::NPART, e = idx % D::NPART;
+  if (v >= V) return;
+  double s = 0;
+  for (int c = view_chunk_off[v]; c < view_chunk_off[v + 1]; ++c) s += part[(size_t)c * D::NPART + e];
+  if (e < D::NU) {
+    int a = 0, rem = e;
+    while (rem >= NCL - a) { rem -= NCL - a; ++a; }
+    const int b = a + rem;
+    U[(size_t)v * NCL * NCL + a * NCL + b] = s;
+    U[(size_t)v * NCL * NCL + b * NCL + a] = s;
+  } else if (e < D::NU + NCL) {
+    const int a = e - D::NU;
+    g[v * NCL + a] = s;
+    gabs[v * NCL + a] = fabs(s / scale_cam[v * NCL + a]);
+  } else {
+    cost_view[v] = s;
+  }
+}
+
+// per track: V = sum E^T E (lower 6), h = sum E^T r.  Once per Jacobian evaluation (gradient, column norms, LM diagonal).
+__global__ void k_track_accum(int P, int RS, const int* __restrict__ t_off, const int* __restrict__ t_obs, const double* __restrict__ rec,
+                              const double* __restrict__ trk, double* __restrict__ Vh, double* __restrict__ gmax_part) {
+  __shared__ double sm[8];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double gm = 0;
+  if (p < P) {
+    double v00 = 0, v10 = 0, v11 = 0, v20 = 0, v21 = 0, v22 = 0, h0 = 0, h1 = 0, h2 = 0;
+    for (int i = t_off[p]; i < t_off[p + 1]; ++i) {
+      const double2* q = reinterpret_cast<const double2*>(rec + (size_t)t_obs[i] * RS);
+      const double2 r = q[0], e01 = q[1], e23 = q[2], e45 = q[3];
+      const double a0 = e01.x, a1 = e01.y, a2 = e23.x, b0 = e23.y, b1 = e45.x, b2 = e45.y;
+      v00 += a0 * a0 + b0 * b0; v10 += a1 * a0 + b1 * b0; v11 += a1 * a1 + b1 * b1;
+      v20 += a2 * a0 + b2 * b0; v21 += a2 * a1 + b2 * b1; v22 += a2 * a2 + b2 * b2;
+      h0 += a0 * r.x + b0 * r.y; h1 += a1 * r.x + b1 * r.y; h2 += a2 * r.x + b2 * r.y;
+    }
+    double* o = Vh + (size_t)p * 10;
+    o[0] = v00; o[1] = v10; o[2] = v11; o[3] = v20; o[4] = v21; o[5] = v22; o[6] = h0; o[7] = h1; o[8] = h2; o[9] = 0;
+    const double* t = trk + (size_t)p * kTrk;
+    gm = fmax(fabs(h0 / t[4]), fmax(fabs(h1 / t[5]), fabs(h2 / t[6])));
+  }
+  gm = warp_max(gm);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = gm;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sm[w]);
+    gmax_part[blockIdx.x] = m;
+  }
+}
+
+// Jacobi scaling, once at iteration 0: s = 1 / (1 + sqrt(column norm^2))      (TrustRegionMinimizer::EvaluateGradientAndJacobian)
+template <int NCL>
+__global__ void k_make_scales(int V, int P, const double* __restrict__ U, const double* __restrict__ Vh, double* __restrict__ scale_cam,
+                              double* __restrict__ trk0, double* __restrict__ trk1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < V * NCL) {
+    const int v = i / NCL, a = i % NCL;
+    scale_cam[i] = 1.0 / (1.0 + sqrt(U[(size_t)v * NCL * NCL + a * NCL + a]));
+  }
+  if (i < P) {
+    const double* vh = Vh + (size_t)i * 10;
+    const double s0 = 1.0 / (1.0 + sqrt(vh[0])), s1 = 1.0 / (1.0 + sqrt(vh[2])), s2 = 1.0 / (1.0 + sqrt(vh[5]));
+    trk0[(size_t)i * kTrk + 4] = s0; trk0[(size_t)i * kTrk + 5] = s1; trk0[(size_t)i * kTrk + 6] = s2;
+    trk1[(size_t)i * kTrk + 4] = s0; trk1[(size_t)i * kTrk + 5] = s1; trk1[(size_t)i * kTrk + 6] = s2;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// stage 2
+// -------------------------------------------------------------------------------------------------------------
+// per track: damp, factor (V + D^2) = L L^T, t = L^-1 h; per observation What = (F^T E) L^-T and q = What t.
+template <int NCL>
+__global__ void k_track_solve(int P, const int* __restrict__ t_off, const int* __restrict__ t_obs, const double* __restrict__ rec,
+                              const double* __restrict__ Vh, double mu, int refresh_diag, double min_diag, double max_diag, double* __restrict__ diag_ray,
+                              double* __restrict__ Lt, double* __restrict__ What, double* __restrict__ q, int* __restrict__ fail) {
+  typedef Dims<NCL> D;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const double* vh = Vh + (size_t)p * 10;
+  double d0, d1, d2;
+  if (refresh_diag) {
+    d0 = fmin(fmax(vh[0], min_diag), max_diag); d1 = fmin(fmax(vh[2], min_diag), max_diag); d2 = fmin(fmax(vh[5], min_diag), max_diag);
+    diag_ray[3 * (size_t)p] = d0; diag_ray[3 * (size_t)p + 1] = d1; diag_ray[3 * (size_t)p + 2] = d2;
+  } else {
+    d0 = diag_ray[3 * (size_t)p]; d1 = diag_ray[3 * (size_t)p + 1]; d2 = diag_ray[3 * (size_t)p + 2];
+  }
+  const double A6[6] = {vh[0] + d0 / mu, vh[1], vh[2] + d1 / mu, vh[3], vh[4], vh[5] + d2 / mu};
+  double L[6];
+  double* lt = Lt + (size_t)p * 10;
+  if (t_off[p] == t_off[p + 1]) {  // track without observations: not in the problem
+    for (int i = 0; i < 10; ++i) lt[i] = 0;
+    lt[0] = lt[2] = lt[5] = 1.0;
+    return;
+  }
+  if (!chol3(A6, L)) {
+    atomicExch(fail, 1);
+    for (int i = 0; i < 10; ++i) lt[i] = 0;
+    lt[0] = lt[2] = lt[5] = 1.0;
+    L[0] = L[2] = L[5] = 1.0; L[1] = L[3] = L[4] = 0.0;
+  }
+  const double i00 = 1.0 / L[0], i11 = 1.0 / L[2], i22 = 1.0 / L[5];
+  const double t0 = vh[6] * i00, t1 = (vh[7] - L[1] * t0) * i11, t2 = (vh[8] - L[3] * t0 - L[4] * t1) * i22;
+  lt[0] = L[0]; lt[1] = L[1]; lt[2] = L[2]; lt[3] = L[3]; lt[4] = L[4]; lt[5] = L[5]; lt[6] = t0; lt[7] = t1; lt[8] = t2; lt[9] = 0;
+  for (int i = t_off[p]; i < t_off[p + 1]; ++i) {
+    const int o = t_obs[i];
+    const double2* rp = reinterpret_cast<const double2*>(rec + (size_t)o * D::RS);
+    const double2 e01 = rp[1], e23 = rp[2], e45 = rp[3];
+    const double a0 = e01.x, a1 = e01.y, a2 = e23.x, b0 = e23.y, b1 = e45.x, b2 = e45.y;
+    double w[D::WS];
+    double qa[NCL];
+    const double* Fp = rec + (size_t)o * D::RS + 8;
+#pragma unroll
+    for (int a = 0; a < NCL; ++a) {
+      const double f0 = Fp[a], f1 = Fp[NCL + a];
+      const double w0 = f0 * a0 + f1 * b0, w1 = f0 * a1 + f1 * b1, w2 = f0 * a2 + f1 * b2;  // row a of F^T E
+      const double x0 = w0 * i00, x1 = (w1 - L[1] * x0) * i11, x2 = (w2 - L[3] * x0 - L[4] * x1) * i22;
+      w[3 * a] = x0; w[3 * a + 1] = x1; w[3 * a + 2] = x2;
+      qa[a] = x0 * t0 + x1 * t1 + x2 * t2;
+    }
+    if (D::WS > 3 * NCL) w[D::WS - 1] = 0.0;
+    double2* wo = reinterpret_cast<double2*>(What + (size_t)o * D::WS);
+#pragma unroll
+    for (int k = 0; k < D::WS / 2; ++k) wo[k] = make_double2(w[2 * k], w[2 * k + 1]);
+#pragma unroll
+    for (int a = 0; a < NCL; ++a) q[(size_t)o * NCL + a] = qa[a];
+  }
+}
+
+// per view (one CTA): S_cc = [U + D^2] - sum_o What What^T, rhs_c = [g] - sum_o q_o.  The bracketed terms are added by
+// the rank that owns the camera blocks (add_own); D^2 = clamp(diag U) / mu, refreshed after accepted steps only.
+template <int NCL>
+__global__ void __launch_bounds__(128) k_schur_diag(const int* __restrict__ view_off, const double* __restrict__ What, const double* __restrict__ q,
+                                                    const double* __restrict__ U, const double* __restrict__ g, double mu, int refresh_diag, double min_diag,
+                                                    double max_diag, int add_own, double* __restrict__ diag_cam, const int* __restrict__ diag_pos,
+                                                    double* __restrict__ Sval, double* __restrict__ rhs) {
+  typedef Dims<NCL> D;
+  constexpr int NV = D::NU + NCL;
+  __shared__ double sred[NV * 4];
+  const int v = blockIdx.x;
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+  for (int o = view_off[v] + threadIdx.x; o < view_off[v + 1]; o += blockDim.x) {
+    double w[D::WS];
+    const double2* wp = reinterpret_cast<const double2*>(What + (size_t)o * D::WS);
+#pragma unroll
+    for (int k = 0; k < D::WS / 2; ++k) { const double2 t = wp[k]; w[2 * k] = t.x; w[2 * k + 1] = t.y; }
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < NCL; ++a)
+#pragma unroll
+      for (int b = a; b < NCL; ++b) acc[k++] += w[3 * a] * w[3 * b] + w[3 * a + 1] * w[3 * b + 1] + w[3 * a + 2] * w[3 * b + 2];
+#pragma unroll
+    for (int a = 0; a < NCL; ++a) acc[D::NU + a] += q[(size_t)o * NCL + a];
+  }
+  block_sum<NV>(acc, sred);
+  if (threadIdx.x == 0) {
+    const double* Uv = U + (size_t)v * NCL * NCL;
+    double* S = Sval + (size_t)diag_pos[v] * NCL * NCL;
+    int k = 0;
+    for (int a = 0; a < NCL; ++a)
+      for (int b = a; b < NCL; ++b) {
+        double s = -acc[k++];
+        if (add_own) s += Uv[a * NCL + b];
+        if (a == b) {
+          double d;
+          if (refresh_diag) { d = fmin(fmax(Uv[a * NCL + a], min_diag), max_diag); diag_cam[v * NCL + a] = d; }
+          else d = diag_cam[v * NCL + a];
+          if (add_own) s += d / mu;
+        }
+        S[a * NCL + b] = s;
+        S[b * NCL + a] = s;
+      }
+    for (int a = 0; a < NCL; ++a) rhs[v * NCL + a] = (add_own ? g[v * NCL + a] : 0.0) - acc[D::NU + a];
+  }
+}
+
+// per upper off-diagonal block (one warp): S_rc = - sum over observation pairs What_o What_o'^T ; also writes S_cr = S_rc^T
+template <int NCL>
+__global__ void __launch_bounds__(256) k_schur_offdiag(int nub, const int64_t* __restrict__ pair_off, const int* __restrict__ pair_a,
+                                                       const int* __restrict__ pair_b, const double* __restrict__ What, const int* __restrict__ ub_pos,
+                                                       const int* __restrict__ ub_pos_t, double* __restrict__ Sval) {
+  typedef Dims<NCL> D;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= nub) return;
+  double acc[NCL * NCL];
+#pragma unroll
+  for (int i = 0; i < NCL * NCL; ++i) acc[i] = 0.0;
+  for (int64_t k = pair_off[b] + lane; k < pair_off[b + 1]; k += 32) {
+    const double2* wa = reinterpret_cast<const double2*>(What + (size_t)pair_a[k] * D::WS);
+    const double2* wb = reinterpret_cast<const double2*>(What + (size_t)pair_b[k] * D::WS);
+    double x[D::WS], y[D::WS];
+#pragma unroll
+    for (int i = 0; i < D::WS / 2; ++i) { const double2 t = wa[i]; x[2 * i] = t.x; x[2 * i + 1] = t.y; }
+#pragma unroll
+    for (int i = 0; i < D::WS / 2; ++i) { const double2 t = wb[i]; y[2 * i] = t.x; y[2 * i + 1] = t.y; }
+#pragma unroll
+    for (int a = 0; a < NCL; ++a)
+#pragma unroll
+      for (int c = 0; c < NCL; ++c) acc[a * NCL + c] += x[3 * a] * y[3 * c] + x[3 * a + 1] * y[3 * c + 1] + x[3 * a + 2] * y[3 * c + 2];
+  }
+#pragma unroll
+  for (int i = 0; i < NCL * NCL; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+    double* S = Sval + (size_t)ub_pos[b] * NCL * NCL;
+    double* St = Sval + (size_t)ub_pos_t[b] * NCL * NCL;
+#pragma unroll
+    for (int a = 0; a < NCL; ++a)
+#pragma unroll
+      for (int c = 0; c < NCL; ++c) { S[a * NCL + c] = -acc[a * NCL + c]; St[c * NCL + a] = -acc[a * NCL + c]; }
+  }
+}
+
+// block-Jacobi preconditioner: explicit inverse of every diagonal camera block (and of the dense border block)
+template <int NCL>
+__global__ void k_precond(int V, const int* __restrict__ diag_pos, const double* __restrict__ Sval, double* __restrict__ Minv, int* __restrict__ fail) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < V) {
+    double A[NCL * NCL];
+    const double* S = Sval + (size_t)diag_pos[v] * NCL * NCL;
+#pragma unroll
+    for (int i = 0; i < NCL * NCL; ++i) A[i] = S[i];
+    double* M = Minv + (size_t)v * NCL * NCL;
+    if (!chol_n(A, NCL, NCL)) {
+      atomicExch(fail, 2);
+      for (int i = 0; i < NCL * NCL; ++i) M[i] = (i / NCL == i % NCL) ? 1.0 : 0.0;
+    } else {
+      for (int c = 0; c < NCL; ++c) {
+        double e[NCL];
+        for (int i = 0; i < NCL; ++i) e[i] = (i == c) ? 1.0 : 0.0;
+        chol_solve_n(A, NCL, NCL, e);
+        for (int i = 0; i < NCL; ++i) M[i * NCL + c] = e[i];
+      }
+    }
+  }
+}
+
+// explicit inverse of the dense border block (nb <= 32): one warp, matrix in shared memory
+__global__ void __launch_bounds__(32) k_precond_border(int nb, const double* __restrict__ Sbb, double* __restrict__ Minv_b, int* __restrict__ fail) {
+  __shared__ double A[kMaxBorder * kMaxBorder];
+  __shared__ int ok;
+  for (int i = threadIdx.x; i < nb * nb; i += 32) A[i] = Sbb[i];
+  __syncwarp();
+  if (threadIdx.x == 0) { ok = chol_n(A, nb, nb) ? 1 : 0; if (!ok) atomicExch(fail, 3); }
+  __syncwarp();
+  const int c = threadIdx.x;  // one column of the inverse per lane
+  if (c < nb) {
+    if (!ok) {
+      for (int i = 0; i < nb; ++i) Minv_b[i * nb + c] = (i == c) ? 1.0 : 0.0;
+    } else {
+      double e[kMaxBorder];
+      for (int i = 0; i < nb; ++i) e[i] = (i == c) ? 1.0 : 0.0;
+      chol_solve_n(A, nb, nb, e);
+      for (int i = 0; i < nb; ++i) Minv_b[i * nb + c] = e[i];
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// stage 3: block-Jacobi preconditioned CG on  [S_cc C; C^T S_bb] y = rhs, one cooperative launch per linear solve
+// -------------------------------------------------------------------------------------------------------------
+struct PcgArgs {
+  int V, nb, n;            // n = V*NCL + nb
+  const int* rowptr; const int* col; const double* Sval; const double* Minv; const double* rhs;
+  // border: nav annotated views, strips C[k][NCL][nb], Sbb[nb][nb], Minv_b[nb][nb]
+  int nav; const int* ann_view; const int* ann_idx; const double* C; const double* Sbb; const double* Minv_b;
+  double *x, *r, *z, *p0, *p1, *Ap;
+  double* partial;         // [2][gridDim][2]
+  int max_iter; double tol;
+  int* out_info;           // [0] iterations, [1] status (0 ok, 1 hit cap, 2 breakdown)
+  double* out_res;         // [0] |r|/|b|
+};
+
+__device__ __forceinline__ void grid_reduce2(cg::grid_group& grid, double& a, double& b, double* partial, int& phase, double (*sred)[2], double* sbc) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  a = warp_sum(a); b = warp_sum(b);
+  if (lane == 0) { sred[wid][0] = a; sred[wid][1] = b; }
+  __syncthreads();
+  double* buf = partial + (size_t)(phase & 1) * gridDim.x * 2;
+  if (threadIdx.x == 0) {
+    double s0 = 0, s1 = 0;
+    for (int w = 0; w < nwarp; ++w) { s0 += sred[w][0]; s1 += sred[w][1]; }
+    buf[2 * blockIdx.x] = s0; buf[2 * blockIdx.x + 1] = s1;
+    __threadfence();
+  }
+  grid.sync();
+  if (wid == 0) {
+    double s0 = 0, s1 = 0;
+    for (int i = lane; i < (int)gridDim.x; i += 32) { s0 += __ldcg(buf + 2 * i); s1 += __ldcg(buf + 2 * i + 1); }
+    // fixed-order tree: identical on every CTA
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    if (lane == 0) { sbc[0] = s0; sbc[1] = s1; }
+  }
+  __syncthreads();
+  a = sbc[0]; b = sbc[1];
+  ++phase;
+  __syncthreads();
+}
+
+template <int NCL>
+__global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
+  cg::grid_group grid = cg::this_grid();
+  constexpr int SLOTS = 32 / NCL;
+  __shared__ double sred[8][2];
+  __shared__ double sbc[2];
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + (threadIdx.x >> 5), nw = gridDim.x * wpb;
+  const int la = lane % NCL, ls = lane / NCL;
+  const bool lact = lane < SLOTS * NCL;
+  const int V = A.V, nb = A.nb, nrows = V + (nb > 0 ? 1 : 0), boff = V * NCL;
+  int phase = 0;
+  // ---- init
+  double s0 = 0, s1 = 0;
+  for (int row = gw; row < nrows; row += nw) {
+    if (row < V) {
+      if (lane < NCL) {
+        const double* Mi = A.Minv + (size_t)row * NCL * NCL + lane * NCL;
+        double zz = 0;
+#pragma unroll
+        for (int j = 0; j < NCL; ++j) zz += Mi[j] * A.rhs[row * NCL + j];
+        const double rr = A.rhs[row * NCL + lane];
+        const int i = row * NCL + lane;
+        A.x[i] = 0; A.r[i] = rr; A.z[i] = zz; A.p0[i] = 0; A.p1[i] = 0;
+        s0 += rr * zz; s1 += rr * rr;
+      }
+    } else if (lane < nb) {
+      double zz = 0;
+      for (int j = 0; j < nb; ++j) zz += A.Minv_b[lane * nb + j] * A.rhs[boff + j];
+      const double rr = A.rhs[boff + lane];
+      const int i = boff + lane;
+      A.x[i] = 0; A.r[i] = rr; A.z[i] = zz; A.p0[i] = 0; A.p1[i] = 0;
+      s0 += rr * zz; s1 += rr * rr;
+    }
+  }
+  grid_reduce2(grid, s0, s1, A.partial, phase, sred, sbc);
+  double rz = s0;
+  const double bb = s1;
+  int it = 0, status = 1;
+  double rr_last = bb;
+  if (!(bb > 0)) { status = 0; }
+  else {
+    double beta = 0.0;
+    double* pold = A.p0;
+    double* pnew = A.p1;
+    for (it = 0; it < A.max_iter;) {
+      // ---- phase A: p_new = z + beta p_old (recomputed on the fly for neighbours), Ap = S p_new
+      double pAp = 0, dummy = 0;
+      for (int row = gw; row < nrows; row += nw) {
+        if (row < V) {
+          double sum = 0;
+          if (lact) {
+            for (int k = A.rowptr[row] + ls; k < A.rowptr[row + 1]; k += SLOTS) {
+              const int c = __ldg(A.col + k);
+              const double* B = A.Sval + (size_t)k * NCL * NCL + la * NCL;
+#pragma unroll
+              for (int j = 0; j < NCL; ++j) {
+                const double pj = __ldcg(A.z + c * NCL + j) + beta * __ldcg(pold + c * NCL + j);
+                sum += __ldg(B + j) * pj;
+              }
+            }
+          }
+          double tot = sum;
+#pragma unroll
+          for (int s = 1; s < SLOTS; ++s) tot += __shfl_down_sync(0xffffffffu, sum, s * NCL);
+          if (lane < NCL) {
+            if (nb > 0) {
+              const int k = A.ann_idx[row];
+              if (k >= 0) {
+                const double* strip = A.C + ((size_t)k * NCL + lane) * nb;
+                for (int j = 0; j < nb; ++j) tot += strip[j] * (__ldcg(A.z + boff + j) + beta * __ldcg(pold + boff + j));
+              }
+            }
+            const int i = row * NCL + lane;
+            const double pn = __ldcg(A.z + i) + beta * __ldcg(pold + i);
+            pnew[i] = pn; A.Ap[i] = tot;
+            pAp += pn * tot;
+          }
+        } else if (lane < nb) {
+          double tot = 0;
+          for (int k = 0; k < A.nav; ++k) {
+            const int c = A.ann_view[k];
+            for (int a = 0; a < NCL; ++a)
+              tot += A.C[((size_t)k * NCL + a) * nb + lane] * (__ldcg(A.z + c * NCL + a) + beta * __ldcg(pold + c * NCL + a));
+          }
+          for (int j = 0; j < nb; ++j) tot += A.Sbb[lane * nb + j] * (__ldcg(A.z + boff + j) + beta * __ldcg(pold + boff + j));
+          const int i = boff + lane;
+          const double pn = __ldcg(A.z + i) + beta * __ldcg(pold + i);
+          pnew[i] = pn; A.Ap[i] = tot;
+          pAp += pn * tot;
+        }
+      }
+      grid_reduce2(grid, pAp, dummy, A.partial, phase, sred, sbc);
+      if (!(pAp > 0) || !isfinite(pAp)) { status = 2; break; }
+      const double alpha = rz / pAp;
+      // ---- phase B: x += alpha p, r -= alpha Ap, z = Minv r
+      double rz_new = 0, rr = 0;
+      for (int row = gw; row < nrows; row += nw) {
+        if (row < V) {
+          double rv = 0;
+          const int i = row * NCL + (lane < NCL ? lane : 0);
+          if (lane < NCL) {
+            A.x[i] += alpha * pnew[i];
+            rv = A.r[i] - alpha * A.Ap[i];
+            A.r[i] = rv;
+          }
+          double zz = 0;
+#pragma unroll
+          for (int j = 0; j < NCL; ++j) {
+            const double rj = __shfl_sync(0xffffffffu, rv, j);
+            if (lane < NCL) zz += A.Minv[(size_t)row * NCL * NCL + lane * NCL + j] * rj;
+          }
+          if (lane < NCL) { A.z[i] = zz; rz_new += rv * zz; rr += rv * rv; }
+        } else {
+          double rv = 0;
+          const int i = boff + (lane < nb ? lane : 0);
+          if (lane < nb) {
+            A.x[i] += alpha * pnew[i];
+            rv = A.r[i] - alpha * A.Ap[i];
+            A.r[i] = rv;
+          }
+          double zz = 0;
+          for (int j = 0; j < nb; ++j) {
+            const double rj = __shfl_sync(0xffffffffu, rv, j);
+            if (lane < nb) zz += A.Minv_b[lane * nb + j] * rj;
+          }
+          if (lane < nb) { A.z[i] = zz; rz_new += rv * zz; rr += rv * rv; }
+        }
+      }
+      grid_reduce2(grid, rz_new, rr, A.partial, phase, sred, sbc);
+      ++it;
+      rr_last = rr;
+      if (sqrt(rr) <= A.tol * sqrt(bb)) { status = 0; break; }
+      if (!isfinite(rr)) { status = 2; break; }
+      beta = rz_new / rz;
+      rz = rz_new;
+      double* t = pold; pold = pnew; pnew = t;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    A.out_info[0] = it; A.out_info[1] = status;
+    A.out_res[0] = bb > 0 ? sqrt(rr_last / bb) : 0.0;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// stage 4
+// -------------------------------------------------------------------------------------------------------------
+// per track: y_p = L^-T (t - sum_o What_o^T y_c(o)); candidate ray = ray - s*y.  Partials (per CTA): model cost change,
+// |step|^2, |x_cand|^2.
+template <int NCL>
+__global__ void k_track_backsub(int P, const int* __restrict__ t_off, const int* __restrict__ t_obs, const int* __restrict__ o_view,
+                                const double* __restrict__ What, const double* __restrict__ y, const double* __restrict__ Lt, const double* __restrict__ Vh,
+                                const double* __restrict__ diag_ray, double mu, const double* __restrict__ trk, double* __restrict__ trk_cand,
+                                double* __restrict__ part3) {
+  typedef Dims<NCL> D;
+  __shared__ double sred[3 * 8];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[3] = {0, 0, 0};
+  if (p < P) {
+    const double* t = trk + (size_t)p * kTrk;
+    double* tc = trk_cand + (size_t)p * kTrk;
+    if (t_off[p] == t_off[p + 1]) {
+      tc[0] = t[0]; tc[1] = t[1]; tc[2] = t[2];
+    } else {
+      const double* lt = Lt + (size_t)p * 10;
+      double b0 = lt[6], b1 = lt[7], b2 = lt[8];
+      for (int i = t_off[p]; i < t_off[p + 1]; ++i) {
+        const int o = t_obs[i];
+        const double* w = What + (size_t)o * D::WS;
+        const double* yc = y + (size_t)o_view[o] * NCL;
+#pragma unroll
+        for (int a = 0; a < NCL; ++a) { const double ya = yc[a]; b0 -= w[3 * a] * ya; b1 -= w[3 * a + 1] * ya; b2 -= w[3 * a + 2] * ya; }
+      }
+      // L^T y = b
+      const double y2 = b2 / lt[5], y1 = (b1 - lt[4] * y2) / lt[2], y0 = (b0 - lt[1] * y1 - lt[3] * y2) / lt[0];
+      const double* vh = Vh + (size_t)p * 10;
+      const double* dg = diag_ray + 3 * (size_t)p;
+      acc[0] = 0.5 * (y0 * (vh[6] + dg[0] / mu * y0) + y1 * (vh[7] + dg[1] / mu * y1) + y2 * (vh[8] + dg[2] / mu * y2));
+      const double d0 = -t[4] * y0, d1 = -t[5] * y1, d2 = -t[6] * y2;
+      const double c0 = t[0] + d0, c1 = t[1] + d1, c2 = t[2] + d2;
+      tc[0] = c0; tc[1] = c1; tc[2] = c2;
+      acc[1] = (t[0] - c0) * (t[0] - c0) + (t[1] - c1) * (t[1] - c1) + (t[2] - c2) * (t[2] - c2);
+      acc[2] = c0 * c0 + c1 * c1 + c2 * c2;
+    }
+  }
+  block_sum<3>(acc, sred);
+  if (threadIdx.x == 0) { part3[3 * blockIdx.x] = acc[0]; part3[3 * blockIdx.x + 1] = acc[1]; part3[3 * blockIdx.x + 2] = acc[2]; }
+}
+
+// ambient index of live camera column a: into intr (0..8) or ext (9 + 0..5)
+template <int TYPE>
+__host__ __device__ constexpr int live_col_slot(int a) {
+  // PTZRay: fx,w | Dist, DistDisp: fx,k1,w | FxfyDist: fx,fy,k1,w
+  return TYPE == BA_PTZRAY ? (a == 0 ? 0 : 9 + (a - 1))
+       : TYPE == BA_PTZRAY_FXFY_DIST ? (a == 0 ? 0 : a == 1 ? 1 : a == 2 ? 4 : 9 + (a - 3))
+       : (a == 0 ? 0 : a == 1 ? 4 : 9 + (a - 2));
+}
+
+// per view: candidate camera = camera - s*y on the live columns; partials as above (one value triple per CTA)
+template <int TYPE>
+__global__ void k_cam_update(int V, const double* __restrict__ y, const double* __restrict__ scale_cam, const double* __restrict__ g,
+                             const double* __restrict__ diag_cam, double mu, const int* __restrict__ view_active, const double* __restrict__ intr,
+                             const double* __restrict__ ext, double* __restrict__ intr_c, double* __restrict__ ext_c, double* __restrict__ part3) {
+  constexpr int NCL = ba_ncl(TYPE);
+  __shared__ double sred[3 * 8];
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[3] = {0, 0, 0};
+  if (v < V) {
+    double x[15], c[15];
+    for (int j = 0; j < 9; ++j) x[j] = intr[9 * v + j];
+    for (int j = 0; j < 6; ++j) x[9 + j] = ext[6 * v + j];
+    for (int j = 0; j < 15; ++j) c[j] = x[j];
+#pragma unroll
+    for (int a = 0; a < NCL; ++a) {
+      const double ya = y[v * NCL + a];
+      acc[0] += 0.5 * ya * (g[v * NCL + a] + diag_cam[v * NCL + a] / mu * ya);
+      c[live_col_slot<TYPE>(a)] = x[live_col_slot<TYPE>(a)] + (-scale_cam[v * NCL + a] * ya);
+    }
+    for (int j = 0; j < 9; ++j) intr_c[9 * v + j] = c[j];
+    for (int j = 0; j < 6; ++j) ext_c[6 * v + j] = c[9 + j];
+    if (view_active[v]) {
+      for (int j = 0; j < 15; ++j) { acc[1] += (x[j] - c[j]) * (x[j] - c[j]); acc[2] += c[j] * c[j]; }
+    }
+  }
+  block_sum<3>(acc, sred);
+  if (threadIdx.x == 0) { part3[3 * blockIdx.x] = acc[0]; part3[3 * blockIdx.x + 1] = acc[1]; part3[3 * blockIdx.x + 2] = acc[2]; }
+}
+
+// cost-only pass at the candidate point; `raw` != 0 also accumulates the unweighted squared residual (CalReprojError2d2d)
+template <int TYPE>
+__global__ void __launch_bounds__(kChunk) k_cost(const int* __restrict__ chunk_view, const int* __restrict__ chunk_begin, const int* __restrict__ chunk_cnt,
+                                                 const float2* __restrict__ o_uv, const int* __restrict__ o_track, const ViewTab* __restrict__ vt,
+                                                 const double* __restrict__ trk, const double* __restrict__ disp, double* __restrict__ part2) {
+  __shared__ ViewTab svt;
+  __shared__ double sred[2 * (kChunk / 32)];
+  const int chunk = blockIdx.x;
+  const int view = chunk_view[chunk], begin = chunk_begin[chunk], cnt = chunk_cnt[chunk];
+  if (threadIdx.x < 48) reinterpret_cast<double*>(&svt)[threadIdx.x] = reinterpret_cast<const double*>(vt + view)[threadIdx.x];
+  __syncthreads();
+  double acc[2] = {0, 0};
+  if (threadIdx.x < cnt) {
+    const int o = begin + threadIdx.x;
+    const float2 uv = o_uv[o];
+    const int p = o_track[o];
+    const double4 t0 = *reinterpret_cast<const double4*>(trk + (size_t)p * kTrk);
+    const double ray[3] = {t0.x, t0.y, t0.z};
+    double dz[3] = {0, 0, 0};
+    if (TYPE == BA_PTZRAY_DIST_DISP) { dz[0] = disp[0]; dz[1] = disp[1]; dz[2] = disp[2]; }
+    double r[2];
+    ba_obs<TYPE, false>(svt, ray, dz, (double)uv.x, (double)uv.y, r, nullptr, nullptr, nullptr);
+    const double s = r[0] * r[0] + r[1] * r[1];
+    acc[0] = 0.5 * t0.w * t0.w * s;
+    acc[1] = s;
+  }
+  block_sum<2>(acc, sred);
+  if (threadIdx.x == 0) { part2[2 * (size_t)chunk] = acc[0]; part2[2 * (size_t)chunk + 1] = acc[1]; }
+}
+
+// fixed-order single-CTA reductions of the partial arrays into the scalar block the host reads once per iteration
+struct ScalarJobs {
+  // sums: (ptr, count, stride, offset) -> out slot ; maxes likewise
+  const double* sum_ptr[12]; int sum_n[12]; int sum_stride[12]; int sum_slot[12]; int nsum;
+  const double* max_ptr[4]; int max_n[4]; int max_slot[4]; int nmax;
+};
+__global__ void __launch_bounds__(256) k_scalars(ScalarJobs J, double* __restrict__ out) {
+  __shared__ double sred[8];
+  for (int j = 0; j < J.nsum; ++j) {
+    double s[1] = {0};
+    for (int i = threadIdx.x; i < J.sum_n[j]; i += blockDim.x) s[0] += J.sum_ptr[j][(size_t)i * J.sum_stride[j]];
+    block_sum<1>(s, sred);
+    if (threadIdx.x == 0) out[J.sum_slot[j]] = s[0];
+  }
+  for (int j = 0; j < J.nmax; ++j) {
+    double m = 0;
+    for (int i = threadIdx.x; i < J.max_n[j]; i += blockDim.x) m = fmax(m, J.max_ptr[j][i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double mm = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mm = fmax(mm, sred[w]);
+      out[J.max_slot[j]] = mm;
+    }
+    __syncthreads();
+  }
+}
+
+// initial rays (Pix2Ray, ptzray_optimizer.cc:768-797): mean over the track's views of normalise((R^-1 K^-1)[u,v,1]), normalised
+__global__ void k_init_rays(int P, const int* __restrict__ t_off, const int* __restrict__ t_obs, const int* __restrict__ o_view,
+                            const float2* __restrict__ o_uv, const double* __restrict__ RiKi, double* __restrict__ trk) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  double a0 = 0, a1 = 0, a2 = 0;
+  const int n = t_off[p + 1] - t_off[p];
+  for (int i = t_off[p]; i < t_off[p + 1]; ++i) {
+    const int o = t_obs[i];
+    const double* Mv = RiKi + 9 * (size_t)o_view[o];
+    const double u = o_uv[o].x, v = o_uv[o].y;
+    const double x = Mv[0] * u + Mv[1] * v + Mv[2], yv = Mv[3] * u + Mv[4] * v + Mv[5], z = Mv[6] * u + Mv[7] * v + Mv[8];
+    const double nn = sqrt(x * x + yv * yv + z * z);
+    a0 += x / nn; a1 += yv / nn; a2 += z / nn;
+  }
+  a0 /= n; a1 /= n; a2 /= n;
+  const double nn = sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+  trk[(size_t)p * kTrk] = a0 / nn; trk[(size_t)p * kTrk + 1] = a1 / nn; trk[(size_t)p * kTrk + 2] = a2 / nn;
+}
+// (R^-1 K^-1) per view with OpenCV's 3x3 cofactor inverse (cv::Mat::inv, ptzray_optimizer.cc:786)
+__global__ void k_rikI(int V, const double* __restrict__ intr, const double* __restrict__ ext, double* __restrict__ RiKi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  double w[3] = {ext[6 * i], ext[6 * i + 1], ext[6 * i + 2]}, R[9];
+  rodrigues_jac(w, R, nullptr);
+  double S[9], Ri[9], Ki[9];
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 0) for (int j = 0; j < 9; ++j) S[j] = R[j];
+    else { S[0] = intr[9 * i]; S[1] = 0; S[2] = intr[9 * i + 2]; S[3] = 0; S[4] = intr[9 * i + 1]; S[5] = intr[9 * i + 3]; S[6] = 0; S[7] = 0; S[8] = 1; }
+    double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+    d = 1.0 / d;
+    double* T = pass == 0 ? Ri : Ki;
+    T[0] = (S[4] * S[8] - S[5] * S[7]) * d; T[1] = (S[2] * S[7] - S[1] * S[8]) * d; T[2] = (S[1] * S[5] - S[2] * S[4]) * d;
+    T[3] = (S[5] * S[6] - S[3] * S[8]) * d; T[4] = (S[0] * S[8] - S[2] * S[6]) * d; T[5] = (S[2] * S[3] - S[0] * S[5]) * d;
+    T[6] = (S[3] * S[7] - S[4] * S[6]) * d; T[7] = (S[1] * S[6] - S[0] * S[7]) * d; T[8] = (S[0] * S[4] - S[1] * S[3]) * d;
+  }
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) RiKi[9 * (size_t)i + 3 * r + c] = Ri[3 * r] * Ki[c] + Ri[3 * r + 1] * Ki[3 + c] + Ri[3 * r + 2] * Ki[6 + c];
+}
+
+}  // namespace ptz

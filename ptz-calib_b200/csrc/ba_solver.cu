@@ -1,0 +1,952 @@
+// ba_solver.cu — host side of the PTZ-BA hot path: problem upload, the Levenberg–Marquardt loop that sequences the
+// stage kernels, and the extern "C" entry points of include/ptzcalib_b200.h.
+//
+// The loop restates Ceres 1.14's TrustRegionMinimizer + LevenbergMarquardtStrategy (what runs behind
+// ptzray_optimizer.cc:475) with the decisions taken on the host from ONE small device->host read per iteration;
+// every O(M), O(P) or O(V) piece of work is a kernel.  There is no CPU solver path in this library.
+#include <math.h>
+#include <nccl.h>
+#include <stdarg.h>
+
+#include <algorithm>
+#include <chrono>
+#include <memory>
+
+#include "ba_border.cuh"
+#include "ba_kernels.cuh"
+#include "ba_structure.hpp"
+
+namespace ptz {
+
+// --------------------------------------------------------------------------------------------------------------
+// errors, NCCL state
+// --------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct NcclState {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+};
+static NcclState g_nccl;
+
+#define PTZ_NCCL(expr)                                                                                       \
+  do {                                                                                                       \
+    ncclResult_t _r = (expr);                                                                                \
+    if (_r != ncclSuccess) {                                                                                 \
+      char _b[512];                                                                                          \
+      snprintf(_b, sizeof(_b), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, ncclGetErrorString(_r));        \
+      throw ::ptz::CudaError(PTZ_ERR_NCCL, _b);                                                              \
+    }                                                                                                        \
+  } while (0)
+
+static void allreduce_sum(double* buf, size_t n, cudaStream_t s) {
+  if (g_nccl.world > 1 && n) PTZ_NCCL(ncclAllReduce(buf, buf, n, ncclDouble, ncclSum, g_nccl.comm, s));
+}
+static void allreduce_max(double* buf, size_t n, cudaStream_t s) {
+  if (g_nccl.world > 1 && n) PTZ_NCCL(ncclAllReduce(buf, buf, n, ncclDouble, ncclMax, g_nccl.comm, s));
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// scalar slots read by the host once per LM iteration
+enum Slot {
+  // summed across ranks (local partial sums)
+  S_COST_CAND = 0, S_RAW2_CAND, S_DM_RAY, S_STEP2_RAY, S_XN2_RAY, S_SUM_END = 8,
+  // max across ranks
+  S_GMAX_RAY = 8, S_MAX_END = 10,
+  // replicated (computed from all-reduced data or from replicated camera parameters)
+  S_COST_X = 10, S_GMAX_CAM, S_GMAX_B, S_DM_CAM, S_STEP2_CAM, S_XN2_CAM, S_DM_B, S_STEP2_B, S_XN2_B, S_COSTPTS_X, S_RAWPTS_X, S_COSTPTS_CAND, S_RAWPTS_CAND,
+  S_COUNT = 32
+};
+
+struct StageClock {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> tag;  // stage of interval [2i, 2i+1]
+  size_t used = 0;
+  float ms[4] = {0, 0, 0, 0};
+  int launches[4] = {0, 0, 0, 0};
+  cudaStream_t stream = nullptr;
+  void init(cudaStream_t s) { stream = s; }
+  void begin(int stage) {
+    if (used + 2 > ev.size()) {
+      for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+    }
+    cudaEventRecord(ev[used], stream);
+    tag.push_back(stage);
+    ++used;
+  }
+  void end() { cudaEventRecord(ev[used], stream); ++used; }
+  void collect() {  // call after a stream synchronise
+    for (size_t i = 0; i + 1 < used; i += 2) {
+      float t = 0;
+      cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+      ms[tag[i / 2]] += t;
+    }
+    used = 0;
+    tag.clear();
+  }
+  void reset() { collect(); for (int i = 0; i < 4; ++i) { ms[i] = 0; launches[i] = 0; } }
+  ~StageClock() { for (auto e : ev) cudaEventDestroy(e); }
+};
+
+// --------------------------------------------------------------------------------------------------------------
+// the solver, specialised on the factor type
+// --------------------------------------------------------------------------------------------------------------
+struct BaSolverBase {
+  virtual ~BaSolverBase() {}
+  virtual void reset() = 0;
+  virtual void run(int max_new_iterations, ptzba_result* out) = 0;
+  virtual void eval(const double* disp, ptzba_eval_out* out) = 0;
+  virtual void stage_times(ptzba_stage_times* t) = 0;
+};
+
+template <int TYPE>
+struct BaSolver : BaSolverBase {
+  static constexpr int NCL = ba_ncl(TYPE);
+  typedef Dims<NCL> D;
+  static constexpr bool kFyBorder = (TYPE != BA_PTZRAY_FXFY_DIST);
+
+  int V, P, M, A, nb = 0, nav = 0, n = 0;
+  ptz_solver_options opt;
+  BaStructure st;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  StageClock clk;
+  double seconds_setup = 0;
+
+  // host copies of the inputs that outputs need
+  std::vector<double> h_intr0, h_ext0, h_weight, h_ray0, h_tlw0;
+  bool have_ray0 = false;
+  std::vector<int> h_view_active, h_ann_view, h_ann_off, h_ann_idx, h_pt_perm;
+
+  // device: structure
+  DevBuf<float2> d_uv;
+  DevBuf<int> d_otrack, d_oview, d_chunk_view, d_chunk_begin, d_chunk_cnt, d_view_chunk_off, d_view_off, d_toff, d_tobs;
+  DevBuf<int64_t> d_pair_off;
+  DevBuf<int> d_pair_a, d_pair_b, d_rowptr, d_col, d_diag_pos, d_ub_pos, d_ub_pos_t, d_view_active;
+  // device: parameters (two copies: current / candidate)
+  DevBuf<double> d_intr[2], d_ext[2], d_trk[2], d_tlw[2], d_intr_init, d_ext_init, d_trk_init, d_tlw_init;
+  int cur = 0;
+  // device: work
+  DevBuf<ViewTab> d_vt;
+  DevBuf<double> d_scale_cam, d_scale_b, d_rec, d_part, d_viewred, d_Vh, d_gmax_part, d_diag_ray, d_diag_cam, d_diag_b, d_Lt, d_What, d_q, d_sys, d_Minv,
+      d_Minv_b, d_Sbb, d_pcgvec, d_pcg_partial, d_pcg_res, d_part3_ray, d_part3_cam, d_part3_b, d_cost_part, d_scalars, d_RiKi, d_pts_scratch, d_pts_raw,
+      d_pts_xyz, d_disp;
+  DevBuf<float2> d_pts_uv;
+  DevBuf<int> d_pts_view, d_ann_view, d_ann_off, d_ann_idx, d_fail, d_pcg_info;
+  // views into d_viewred (all-reduced once per Jacobian evaluation): U | g | cost_view | C | Hbb | gb | cost_pts(2)
+  double *p_U, *p_g, *p_cost_view, *p_C, *p_Hbb, *p_gb, *p_cost_pts, *p_gabs, *p_gabs_b;
+  DevBuf<double> d_gabs;
+  size_t viewred_n = 0;
+  // views into d_sys (all-reduced once per linear solve): Sval | rhs(n)
+  double *p_Sval, *p_rhs;
+  size_t sys_n = 0;
+  double* h_scalars = nullptr;  // pinned
+  int* h_info = nullptr;        // pinned: pcg info(2), fail(1)
+  int nblk_ray = 0, nblk_cam = 0;
+
+  // LM state (names follow ceres::internal::TrustRegionMinimizer / LevenbergMarquardtStrategy)
+  double radius = 0, decrease_factor = 2.0, x_cost = 0, x_norm = 0, min_cost = 0, initial_cost = 0, grad_max = 0;
+  bool reuse_diagonal = false, last_successful = true, started = false, finished = false;
+  int iteration = 0, num_consecutive_invalid = 0, termination = PTZ_NO_CONVERGENCE;
+  int num_successful = 0, num_unsuccessful = 0, lin_iters_total = 0, jac_evals = 0, cost_evals = 0;
+  std::vector<ptz_iter_log> log;
+
+  BaSolver(const ptzba_problem* prob, const ptz_solver_options* o) {
+    auto t0 = std::chrono::steady_clock::now();
+    opt = *o;
+    V = prob->num_views; P = prob->num_tracks; M = prob->num_obs; A = prob->num_pts3d;
+    int dev = 0;
+    PTZ_CUDA(cudaGetDevice(&dev));
+    PTZ_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    PTZ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    clk.init(stream);
+    build_structure(V, P, M, prob->obs_uv, prob->obs_view, prob->obs_track, kChunk, st, nullptr);
+    if (g_nccl.world > 1) unify_pattern(prob);
+    // annotated points: sort by view, list annotated views
+    h_view_active.assign(V, 0);
+    for (int k = 0; k < M; ++k) h_view_active[prob->obs_view[k]] = 1;
+    h_ann_idx.assign(V, -1);
+    if (A > 0) {
+      h_pt_perm.resize(A);
+      std::iota(h_pt_perm.begin(), h_pt_perm.end(), 0);
+      std::stable_sort(h_pt_perm.begin(), h_pt_perm.end(), [&](int a, int b) { return prob->pt_view[a] < prob->pt_view[b]; });
+      for (int i = 0; i < A; ++i) {
+        int v = prob->pt_view[h_pt_perm[i]];
+        h_view_active[v] = 1;
+        if (h_ann_view.empty() || h_ann_view.back() != v) { h_ann_idx[v] = (int)h_ann_view.size(); h_ann_view.push_back(v); h_ann_off.push_back(i); }
+      }
+      h_ann_off.push_back(A);
+      nav = (int)h_ann_view.size();
+      nb = 6 + (kFyBorder ? nav : 0);
+      if (nb > kMaxBorder) throw CudaError(PTZ_ERR_UNSUPPORTED, "more than 26 annotated views");
+    }
+    if (g_nccl.world > 1 && A > 0) throw CudaError(PTZ_ERR_UNSUPPORTED, "2d-3d terms with a sharded problem");
+    n = V * NCL + nb;
+    upload(prob);
+    PTZ_CUDA(cudaStreamSynchronize(stream));
+    seconds_setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+
+  ~BaSolver() {
+    if (h_scalars) cudaFreeHost(h_scalars);
+    if (h_info) cudaFreeHost(h_info);
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  // every rank must hold the same block pattern of S: all-gather the local upper keys, take the union, rebuild
+  void unify_pattern(const ptzba_problem* prob) {
+    std::vector<int64_t> keys(st.nub());
+    for (int b = 0; b < st.nub(); ++b) keys[b] = ub_key(st.ub_row[b], st.ub_col[b]);
+    const int W = g_nccl.world;
+    DevBuf<int64_t> d_cnt, d_all;
+    d_cnt.alloc(W);
+    int64_t my = (int64_t)keys.size();
+    std::vector<int64_t> counts(W);
+    DevBuf<int64_t> d_my;
+    d_my.upload(&my, 1, stream);
+    PTZ_NCCL(ncclAllGather(d_my.p, d_cnt.p, 1, ncclInt64, g_nccl.comm, stream));
+    d_cnt.download(counts.data(), W, stream);
+    PTZ_CUDA(cudaStreamSynchronize(stream));
+    int64_t mx = *std::max_element(counts.begin(), counts.end());
+    if (mx == 0) return;
+    std::vector<int64_t> padded(mx, -1);
+    std::copy(keys.begin(), keys.end(), padded.begin());
+    DevBuf<int64_t> d_pad;
+    d_pad.upload(padded, stream);
+    d_all.alloc((size_t)mx * W);
+    PTZ_NCCL(ncclAllGather(d_pad.p, d_all.p, mx, ncclInt64, g_nccl.comm, stream));
+    std::vector<int64_t> all((size_t)mx * W);
+    d_all.download(all.data(), all.size(), stream);
+    PTZ_CUDA(cudaStreamSynchronize(stream));
+    all.erase(std::remove(all.begin(), all.end(), (int64_t)-1), all.end());
+    std::sort(all.begin(), all.end());
+    all.erase(std::unique(all.begin(), all.end()), all.end());
+    build_structure(V, P, M, prob->obs_uv, prob->obs_view, prob->obs_track, kChunk, st, &all);
+  }
+
+  void upload(const ptzba_problem* prob) {
+    cudaStream_t s = stream;
+    d_uv.upload(reinterpret_cast<const float2*>(st.o_uv.data()), M, s);
+    d_otrack.upload(st.o_track, s); d_oview.upload(st.o_view, s);
+    d_chunk_view.upload(st.chunk_view, s); d_chunk_begin.upload(st.chunk_begin, s); d_chunk_cnt.upload(st.chunk_cnt, s);
+    d_view_chunk_off.upload(st.view_chunk_off, s); d_view_off.upload(st.view_off, s);
+    d_toff.upload(st.t_off, s); d_tobs.upload(st.t_obs, s);
+    d_pair_off.upload(st.ub_pair_off, s); d_pair_a.upload(st.pair_a, s); d_pair_b.upload(st.pair_b, s);
+    d_rowptr.upload(st.s_rowptr, s); d_col.upload(st.s_col, s); d_diag_pos.upload(st.diag_pos, s);
+    d_ub_pos.upload(st.ub_pos, s); d_ub_pos_t.upload(st.ub_pos_t, s);
+    d_view_active.upload(h_view_active, s);
+    // parameters
+    h_intr0.assign(prob->intr, prob->intr + 9 * (size_t)V);
+    h_ext0.assign(prob->ext, prob->ext + 6 * (size_t)V);
+    h_weight.assign(prob->track_weight, prob->track_weight + (size_t)P);
+    h_tlw0.assign(6, 0.0);
+    if (prob->tlw0) h_tlw0.assign(prob->tlw0, prob->tlw0 + 6);
+    have_ray0 = prob->ray0 != nullptr;
+    std::vector<double> trk((size_t)std::max(P, 1) * kTrk, 0.0);
+    for (int p = 0; p < P; ++p) {
+      double* t = &trk[(size_t)p * kTrk];
+      if (have_ray0) { t[0] = prob->ray0[3 * (size_t)p]; t[1] = prob->ray0[3 * (size_t)p + 1]; t[2] = prob->ray0[3 * (size_t)p + 2]; }
+      t[3] = sqrt(h_weight[p]);
+      t[4] = t[5] = t[6] = 1.0;
+    }
+    d_intr_init.upload(h_intr0, s); d_ext_init.upload(h_ext0, s); d_tlw_init.upload(h_tlw0, s);
+    d_trk_init.upload(trk, s);
+    for (int i = 0; i < 2; ++i) { d_intr[i].alloc(9 * (size_t)V); d_ext[i].alloc(6 * (size_t)V); d_trk[i].alloc(trk.size()); d_tlw[i].alloc(6); }
+    d_vt.alloc(V);
+    d_RiKi.alloc(9 * (size_t)V);
+    if (!have_ray0 && P > 0) {  // Pix2Ray on the device, into the initial track records
+      k_rikI<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr_init.p, d_ext_init.p, d_RiKi.p);
+      k_init_rays<<<cdiv(P, 128), 128, 0, s>>>(P, d_toff.p, d_tobs.p, d_oview.p, d_uv.p, d_RiKi.p, d_trk_init.p);
+      PTZ_CUDA(cudaGetLastError());
+    }
+    // annotated points
+    if (A > 0) {
+      std::vector<float> puv(2 * (size_t)A);
+      std::vector<double> pxyz(3 * (size_t)A);
+      std::vector<int> pview(A);
+      for (int i = 0; i < A; ++i) {
+        int k = h_pt_perm[i];
+        puv[2 * i] = prob->pt_uv[2 * k]; puv[2 * i + 1] = prob->pt_uv[2 * k + 1];
+        for (int j = 0; j < 3; ++j) pxyz[3 * i + j] = prob->pt_xyz[3 * k + j];
+        pview[i] = prob->pt_view[k];
+      }
+      d_pts_uv.upload(reinterpret_cast<const float2*>(puv.data()), A, s);
+      d_pts_xyz.upload(pxyz, s); d_pts_view.upload(pview, s);
+      d_ann_view.upload(h_ann_view, s); d_ann_off.upload(h_ann_off, s);
+      d_pts_scratch.alloc((size_t)A * (2 + 2 * NCL + 2 * nb));
+      d_pts_raw.alloc((size_t)A * 26);
+    }
+    d_ann_idx.upload(h_ann_idx, s);
+    // work buffers
+    d_scale_cam.alloc((size_t)V * NCL); d_scale_b.alloc(kMaxBorder);
+    d_rec.alloc((size_t)std::max(M, 1) * D::RS);
+    d_part.alloc((size_t)std::max(st.nchunks(), 1) * D::NPART);
+    viewred_n = (size_t)V * NCL * NCL + (size_t)V * NCL + V + (size_t)nav * NCL * nb + (size_t)nb * nb + nb + 2;
+    d_viewred.alloc(viewred_n);
+    d_viewred.zero(s);
+    p_U = d_viewred.p; p_g = p_U + (size_t)V * NCL * NCL; p_cost_view = p_g + (size_t)V * NCL; p_C = p_cost_view + V;
+    p_Hbb = p_C + (size_t)nav * NCL * nb; p_gb = p_Hbb + (size_t)nb * nb; p_cost_pts = p_gb + nb;
+    d_gabs.alloc((size_t)V * NCL + kMaxBorder);
+    d_gabs.zero(s);
+    p_gabs = d_gabs.p; p_gabs_b = d_gabs.p + (size_t)V * NCL;
+    d_Vh.alloc((size_t)std::max(P, 1) * 10);
+    nblk_ray = std::max(cdiv(P, 128), 1); nblk_cam = std::max(cdiv(V, 128), 1);
+    d_gmax_part.alloc(nblk_ray); d_gmax_part.zero(s);
+    d_diag_ray.alloc(3 * (size_t)std::max(P, 1)); d_diag_cam.alloc((size_t)V * NCL); d_diag_b.alloc(kMaxBorder);
+    d_Lt.alloc((size_t)std::max(P, 1) * 10);
+    d_What.alloc((size_t)std::max(M, 1) * D::WS); d_What.zero(s);
+    d_q.alloc((size_t)std::max(M, 1) * NCL);
+    sys_n = (size_t)st.nnzb() * NCL * NCL + n;
+    d_sys.alloc(sys_n);
+    p_Sval = d_sys.p; p_rhs = p_Sval + (size_t)st.nnzb() * NCL * NCL;
+    d_Minv.alloc((size_t)V * NCL * NCL); d_Minv_b.alloc(kMaxBorder * kMaxBorder); d_Sbb.alloc(kMaxBorder * kMaxBorder);
+    d_pcgvec.alloc(6 * (size_t)n); d_pcgvec.zero(s);
+    d_pcg_partial.alloc(2 * 2 * (size_t)num_sms * 2);
+    d_pcg_res.alloc(2); d_pcg_info.alloc(2); d_fail.alloc(1); d_fail.zero(s);
+    d_part3_ray.alloc(3 * (size_t)nblk_ray); d_part3_ray.zero(s);
+    d_part3_cam.alloc(3 * (size_t)nblk_cam); d_part3_b.alloc(3); d_part3_b.zero(s);
+    d_cost_part.alloc(2 * (size_t)std::max(st.nchunks(), 1)); d_cost_part.zero(s);
+    d_scalars.alloc(S_COUNT); d_scalars.zero(s);
+    d_disp.alloc(3); d_disp.zero(s);
+    PTZ_CUDA(cudaMallocHost((void**)&h_scalars, S_COUNT * sizeof(double)));
+    PTZ_CUDA(cudaMallocHost((void**)&h_info, 4 * sizeof(int)));
+    reset();
+  }
+
+  void reset() override {
+    cudaStream_t s = stream;
+    PTZ_CUDA(cudaMemcpyAsync(d_intr[0].p, d_intr_init.p, 9 * (size_t)V * 8, cudaMemcpyDeviceToDevice, s));
+    PTZ_CUDA(cudaMemcpyAsync(d_ext[0].p, d_ext_init.p, 6 * (size_t)V * 8, cudaMemcpyDeviceToDevice, s));
+    PTZ_CUDA(cudaMemcpyAsync(d_tlw[0].p, d_tlw_init.p, 6 * 8, cudaMemcpyDeviceToDevice, s));
+    for (int i = 0; i < 2; ++i) PTZ_CUDA(cudaMemcpyAsync(d_trk[i].p, d_trk_init.p, d_trk_init.n * 8, cudaMemcpyDeviceToDevice, s));
+    cur = 0;
+    started = finished = false;
+    iteration = 0; num_consecutive_invalid = 0; num_successful = num_unsuccessful = lin_iters_total = jac_evals = cost_evals = 0;
+    radius = opt.initial_trust_region_radius; decrease_factor = 2.0; reuse_diagonal = false; last_successful = true;
+    termination = PTZ_NO_CONVERGENCE;
+    log.clear();
+    clk.reset();
+  }
+
+  // ---- stage 1 at the current point.  scale arrays must be valid (all ones on the very first pass).
+  void launch_resjac(int weighted) {
+    cudaStream_t s = stream;
+    k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[cur].p, d_ext[cur].p, d_vt.p, 1);
+    if (st.nchunks() > 0)
+      k_resjac<TYPE><<<st.nchunks(), kChunk, 0, s>>>(d_chunk_view.p, d_chunk_begin.p, d_chunk_cnt.p, d_uv.p, d_otrack.p, d_vt.p, d_trk[cur].p, d_scale_cam.p,
+                                                     d_disp.p, weighted, d_rec.p, d_part.p);
+    k_view_finalize<NCL><<<cdiv(V * D::NPART, 256), 256, 0, s>>>(V, d_view_chunk_off.p, d_part.p, d_scale_cam.p, p_U, p_g, p_cost_view, p_gabs);
+    if (P > 0) k_track_accum<<<nblk_ray, 128, 0, s>>>(P, D::RS, d_toff.p, d_tobs.p, d_rec.p, d_trk[cur].p, d_Vh.p, d_gmax_part.p);
+    clk.launches[0] += 4;
+    if (A > 0) {
+      PtsArgs a;
+      a.A = A; a.nav = nav; a.nb = nb; a.fy_in_border = kFyBorder ? 1 : 0;
+      a.uv = d_pts_uv.p; a.xyz = d_pts_xyz.p; a.view = d_pts_view.p; a.ann_view = d_ann_view.p; a.ann_off = d_ann_off.p;
+      a.vt = d_vt.p; a.tlw = d_tlw[cur].p; a.scale_cam = d_scale_cam.p; a.scale_b = d_scale_b.p; a.scratch = d_pts_scratch.p;
+      a.raw = weighted ? nullptr : d_pts_raw.p;
+      a.U = p_U; a.g = p_g; a.gabs = p_gabs; a.C = p_C; a.Hbb = p_Hbb; a.gb = p_gb; a.cost_pts = p_cost_pts; a.gabs_b = p_gabs_b;
+      k_pts<TYPE><<<1, 128, 0, s>>>(a);
+      ++clk.launches[0];
+    }
+    PTZ_CUDA(cudaGetLastError());
+    allreduce_sum(d_viewred.p, viewred_n, s);
+  }
+
+  void fill_ones(double* p, size_t count) {
+    std::vector<double> ones(count, 1.0);
+    PTZ_CUDA(cudaMemcpyAsync(p, ones.data(), count * 8, cudaMemcpyHostToDevice, stream));
+    PTZ_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  // EvaluateGradientAndJacobian: cost, scaled Jacobian records, gradient max-norm
+  void evaluate_jacobian(bool first) {
+    clk.begin(0);
+    if (first) {
+      fill_ones(d_scale_cam.p, (size_t)V * NCL);
+      fill_ones(d_scale_b.p, kMaxBorder);
+      if (opt.jacobi_scaling) {
+        launch_resjac(1);
+        k_make_scales<NCL><<<cdiv(std::max(V * NCL, P), 256), 256, 0, stream>>>(V, P, p_U, d_Vh.p, d_scale_cam.p, d_trk[0].p, d_trk[1].p);
+        if (nb > 0) k_border_scales<<<1, 32, 0, stream>>>(nb, p_Hbb, d_scale_b.p);
+        clk.launches[0] += 1 + (nb > 0);
+      }
+    }
+    launch_resjac(1);
+    ++jac_evals;
+    ScalarJobs J;
+    J.nsum = 0; J.nmax = 0;
+    auto add_sum = [&](const double* p, int cnt, int stride, int slot) { J.sum_ptr[J.nsum] = p; J.sum_n[J.nsum] = cnt; J.sum_stride[J.nsum] = stride; J.sum_slot[J.nsum] = slot; ++J.nsum; };
+    auto add_max = [&](const double* p, int cnt, int slot) { J.max_ptr[J.nmax] = p; J.max_n[J.nmax] = cnt; J.max_slot[J.nmax] = slot; ++J.nmax; };
+    add_sum(p_cost_view, V, 1, S_COST_X);
+    add_sum(p_cost_pts, A > 0 ? 1 : 0, 1, S_COSTPTS_X);
+    add_sum(p_cost_pts + 1, A > 0 ? 1 : 0, 1, S_RAWPTS_X);
+    add_max(p_gabs, V * NCL, S_GMAX_CAM);
+    add_max(d_gmax_part.p, P > 0 ? nblk_ray : 0, S_GMAX_RAY);
+    add_max(p_gabs_b, nb, S_GMAX_B);
+    k_scalars<<<1, 256, 0, stream>>>(J, d_scalars.p);
+    ++clk.launches[0];
+    PTZ_CUDA(cudaGetLastError());
+    allreduce_max(d_scalars.p + S_GMAX_RAY, S_MAX_END - S_GMAX_RAY, stream);
+    clk.end();
+    read_scalars();
+    x_cost = h_scalars[S_COST_X] + h_scalars[S_COSTPTS_X];
+    grad_max = std::max(h_scalars[S_GMAX_CAM], std::max(h_scalars[S_GMAX_RAY], h_scalars[S_GMAX_B]));
+  }
+
+  void read_scalars() {
+    d_scalars.download(h_scalars, S_COUNT, stream);
+    d_pcg_info.download(h_info, 2, stream);
+    d_fail.download(h_info + 2, 1, stream);
+    PTZ_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  // ---- stages 2-4: one trust-region step attempt at the current Jacobian.  Returns false on linear-solver failure.
+  bool compute_step_and_candidate(int* lin_iters) {
+    cudaStream_t s = stream;
+    const double mu = radius;
+    const int refresh = reuse_diagonal ? 0 : 1;
+    const int own = (g_nccl.rank == 0) ? 1 : 0;
+    PTZ_CUDA(cudaMemsetAsync(d_fail.p, 0, sizeof(int), s));
+    clk.begin(1);
+    if (P > 0)
+      k_track_solve<NCL><<<nblk_ray, 128, 0, s>>>(P, d_toff.p, d_tobs.p, d_rec.p, d_Vh.p, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_ray.p,
+                                                  d_Lt.p, d_What.p, d_q.p, d_fail.p);
+    k_schur_diag<NCL><<<V, 128, 0, s>>>(d_view_off.p, d_What.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, own, d_diag_cam.p,
+                                        d_diag_pos.p, p_Sval, p_rhs);
+    if (st.nub() > 0)
+      k_schur_offdiag<NCL><<<cdiv(st.nub(), 8), 256, 0, s>>>(st.nub(), d_pair_off.p, d_pair_a.p, d_pair_b.p, d_What.p, d_ub_pos.p, d_ub_pos_t.p, p_Sval);
+    if (nb > 0) k_border_system<<<1, 128, 0, s>>>(nb, p_Hbb, p_gb, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_b.p, d_Sbb.p, p_rhs + (size_t)V * NCL);
+    PTZ_CUDA(cudaGetLastError());
+    allreduce_sum(d_sys.p, sys_n, s);
+    k_precond<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, d_diag_pos.p, p_Sval, d_Minv.p, d_fail.p);
+    if (nb > 0) k_precond_border<<<1, 32, 0, s>>>(nb, d_Sbb.p, d_Minv_b.p, d_fail.p);
+    clk.launches[1] += 4 + 2 * (nb > 0);
+    clk.end();
+    // ---- stage 3
+    clk.begin(2);
+    PcgArgs a;
+    a.V = V; a.nb = nb; a.n = n;
+    a.rowptr = d_rowptr.p; a.col = d_col.p; a.Sval = p_Sval; a.Minv = d_Minv.p; a.rhs = p_rhs;
+    a.nav = nav; a.ann_view = d_ann_view.p; a.ann_idx = d_ann_idx.p; a.C = p_C; a.Sbb = d_Sbb.p; a.Minv_b = d_Minv_b.p;
+    a.x = d_pcgvec.p; a.r = a.x + n; a.z = a.r + n; a.p0 = a.z + n; a.p1 = a.p0 + n; a.Ap = a.p1 + n;
+    a.partial = d_pcg_partial.p; a.max_iter = opt.pcg_max_iterations; a.tol = opt.pcg_rel_tolerance;
+    a.out_info = d_pcg_info.p; a.out_res = d_pcg_res.p;
+    const int nrows = V + (nb > 0 ? 1 : 0);
+    int grid = std::min(num_sms, cdiv(nrows, 8));
+    void* args[] = {&a};
+    PTZ_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<NCL>, dim3(grid), dim3(256), args, 0, s));
+    ++clk.launches[2];
+    clk.end();
+    // ---- stage 4
+    clk.begin(3);
+    const int nxt = cur ^ 1;
+    const double* y = d_pcgvec.p;
+    if (P > 0)
+      k_track_backsub<NCL><<<nblk_ray, 128, 0, s>>>(P, d_toff.p, d_tobs.p, d_oview.p, d_What.p, y, d_Lt.p, d_Vh.p, d_diag_ray.p, mu, d_trk[cur].p, d_trk[nxt].p,
+                                                    d_part3_ray.p);
+    k_cam_update<TYPE><<<nblk_cam, 128, 0, s>>>(V, y, d_scale_cam.p, p_g, d_diag_cam.p, mu, d_view_active.p, d_intr[cur].p, d_ext[cur].p, d_intr[nxt].p,
+                                                d_ext[nxt].p, d_part3_cam.p);
+    if (nb > 0)
+      k_border_update<<<1, 32, 0, s>>>(nb, nav, kFyBorder ? 1 : 0, d_ann_view.p, y + (size_t)V * NCL, d_scale_b.p, p_gb, d_diag_b.p, mu, d_tlw[cur].p,
+                                       d_tlw[nxt].p, d_intr[cur].p, d_intr[nxt].p, d_part3_b.p);
+    launch_cost(nxt);
+    launch_step_scalars();
+    clk.launches[3] += 5 + (nb > 0) + (A > 0);
+    clk.end();
+    read_scalars();
+    ++cost_evals;
+    *lin_iters = h_info[0];
+    if (h_info[2] != 0) return false;          // a 3x3 / camera / border block was not positive definite
+    if (h_info[1] == 2) return false;          // PCG breakdown (non-finite or non-positive curvature)
+    return true;
+  }
+
+  void launch_cost(int which) {
+    cudaStream_t s = stream;
+    k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[which].p, d_ext[which].p, d_vt.p, 0);
+    if (st.nchunks() > 0)
+      k_cost<TYPE><<<st.nchunks(), kChunk, 0, s>>>(d_chunk_view.p, d_chunk_begin.p, d_chunk_cnt.p, d_uv.p, d_otrack.p, d_vt.p, d_trk[which].p, d_disp.p,
+                                                   d_cost_part.p);
+    if (A > 0) k_pts_cost<<<1, 32, 0, s>>>(A, d_pts_uv.p, d_pts_xyz.p, d_pts_view.p, d_vt.p, d_tlw[which].p, d_scalars.p + S_COSTPTS_CAND);
+    PTZ_CUDA(cudaGetLastError());
+  }
+
+  void launch_step_scalars() {
+    ScalarJobs J;
+    J.nsum = 0; J.nmax = 0;
+    auto add_sum = [&](const double* p, int cnt, int stride, int slot) { J.sum_ptr[J.nsum] = p; J.sum_n[J.nsum] = cnt; J.sum_stride[J.nsum] = stride; J.sum_slot[J.nsum] = slot; ++J.nsum; };
+    add_sum(d_cost_part.p, st.nchunks(), 2, S_COST_CAND);
+    add_sum(d_cost_part.p + 1, st.nchunks(), 2, S_RAW2_CAND);
+    add_sum(d_part3_ray.p, P > 0 ? nblk_ray : 0, 3, S_DM_RAY);
+    add_sum(d_part3_ray.p + 1, P > 0 ? nblk_ray : 0, 3, S_STEP2_RAY);
+    add_sum(d_part3_ray.p + 2, P > 0 ? nblk_ray : 0, 3, S_XN2_RAY);
+    add_sum(d_part3_cam.p, nblk_cam, 3, S_DM_CAM);
+    add_sum(d_part3_cam.p + 1, nblk_cam, 3, S_STEP2_CAM);
+    add_sum(d_part3_cam.p + 2, nblk_cam, 3, S_XN2_CAM);
+    add_sum(d_part3_b.p, 1, 3, S_DM_B);
+    add_sum(d_part3_b.p + 1, 1, 3, S_STEP2_B);
+    add_sum(d_part3_b.p + 2, 1, 3, S_XN2_B);
+    k_scalars<<<1, 256, 0, stream>>>(J, d_scalars.p);
+    PTZ_CUDA(cudaGetLastError());
+    allreduce_sum(d_scalars.p, S_SUM_END, stream);
+  }
+
+  // |x| of the current point over the coordinates that are in the Ceres problem
+  double current_x_norm() {
+    // candidate := current (y = 0 is not available before the first solve): sum squares directly on the host-visible copies
+    std::vector<double> intr(9 * (size_t)V), ext(6 * (size_t)V), trk((size_t)std::max(P, 1) * kTrk), tlw(6);
+    d_intr[cur].download(intr.data(), intr.size(), stream);
+    d_ext[cur].download(ext.data(), ext.size(), stream);
+    d_trk[cur].download(trk.data(), trk.size(), stream);
+    d_tlw[cur].download(tlw.data(), 6, stream);
+    PTZ_CUDA(cudaStreamSynchronize(stream));
+    double s = 0, sr = 0;
+    for (int v = 0; v < V; ++v)
+      if (h_view_active[v]) {
+        for (int j = 0; j < 9; ++j) s += intr[9 * (size_t)v + j] * intr[9 * (size_t)v + j];
+        for (int j = 0; j < 6; ++j) s += ext[6 * (size_t)v + j] * ext[6 * (size_t)v + j];
+      }
+    for (int p = 0; p < P; ++p)
+      if (st.t_off[p + 1] > st.t_off[p]) for (int j = 0; j < 3; ++j) sr += trk[(size_t)p * kTrk + j] * trk[(size_t)p * kTrk + j];
+    if (g_nccl.world > 1) {
+      DevBuf<double> d;
+      d.upload(&sr, 1, stream);
+      allreduce_sum(d.p, 1, stream);
+      d.download(&sr, 1, stream);
+      PTZ_CUDA(cudaStreamSynchronize(stream));
+    }
+    if (A > 0) for (int j = 0; j < 6; ++j) s += tlw[j] * tlw[j];
+    return sqrt(s + sr);
+  }
+
+  void push_log(double cost, double cost_change, double step_norm, double rho, int lin, int ok) {
+    ptz_iter_log l;
+    l.cost = cost; l.cost_change = cost_change; l.gradient_max_norm = grad_max; l.step_norm = step_norm; l.relative_decrease = rho;
+    l.trust_region_radius = radius; l.linear_solver_iterations = lin; l.step_is_successful = ok;
+    log.push_back(l);
+    if (opt.verbose)
+      printf("[ptzba] it %3d cost %.10e change %.3e |g| %.3e |step| %.3e rho %.3e radius %.3e pcg %d %s\n", (int)log.size() - 1, cost, cost_change, grad_max,
+             step_norm, rho, radius, lin, ok == 1 ? "ok" : ok == 0 ? "rej" : "invalid");
+  }
+
+  void run(int max_new_iterations, ptzba_result* out) override {
+    auto t0 = std::chrono::steady_clock::now();
+    if (!started) {
+      // IterationZero
+      x_norm = current_x_norm();
+      evaluate_jacobian(true);
+      initial_cost = x_cost; min_cost = x_cost;
+      last_successful = true;
+      ++num_successful;
+      push_log(x_cost, 0, 0, 0, 0, 1);
+      started = true;
+    }
+    const int iter_cap = iteration + max_new_iterations;
+    while (!finished) {
+      // FinalizeIterationAndCheckIfMinimizerCanContinue
+      if (iteration >= opt.max_num_iterations) { termination = PTZ_NO_CONVERGENCE; finished = true; break; }
+      if (last_successful && grad_max <= opt.gradient_tolerance) { termination = PTZ_CONVERGENCE; finished = true; break; }
+      if (radius <= opt.min_trust_region_radius) { termination = PTZ_CONVERGENCE; finished = true; break; }
+      if (iteration >= iter_cap) break;  // caller's slice is used up; not a termination
+      ++iteration;
+      int lin = 0;
+      bool ok = compute_step_and_candidate(&lin);
+      reuse_diagonal = true;
+      lin_iters_total += lin;
+      const double* S = h_scalars;
+      double model_cost_change = S[S_DM_RAY] + S[S_DM_CAM] + S[S_DM_B];
+      if (ok && !(std::isfinite(model_cost_change) && std::isfinite(S[S_STEP2_RAY]) && std::isfinite(S[S_STEP2_CAM]))) ok = false;
+      if (ok) ok = model_cost_change > 0.0;
+      if (!ok) {
+        // HandleInvalidStep
+        ++num_consecutive_invalid;
+        if (num_consecutive_invalid >= opt.max_num_consecutive_invalid_steps) { termination = PTZ_FAILURE; finished = true; break; }
+        radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+        last_successful = false;
+        ++num_unsuccessful;
+        push_log(x_cost, 0, 0, 0, lin, -1);
+        continue;
+      }
+      num_consecutive_invalid = 0;
+      double cand_cost = S[S_COST_CAND] + S[S_COSTPTS_CAND];
+      if (!std::isfinite(cand_cost)) cand_cost = 1.7976931348623157e308;
+      const double step_norm = sqrt(S[S_STEP2_RAY] + S[S_STEP2_CAM] + S[S_STEP2_B]);
+      const double cand_norm = sqrt(S[S_XN2_RAY] + S[S_XN2_CAM] + S[S_XN2_B]);
+      // ParameterToleranceReached
+      if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) { termination = PTZ_CONVERGENCE; finished = true; break; }
+      // FunctionToleranceReached
+      const double cost_change = x_cost - cand_cost;
+      if (fabs(cost_change) <= opt.function_tolerance * x_cost) { termination = PTZ_CONVERGENCE; finished = true; break; }
+      const double rho = cost_change / model_cost_change;
+      if (rho > opt.min_relative_decrease) {
+        // HandleSuccessfulStep
+        cur ^= 1;
+        x_norm = cand_norm;
+        evaluate_jacobian(false);
+        radius = radius / std::max(1.0 / 3.0, 1.0 - pow(2.0 * rho - 1.0, 3));
+        radius = std::min(opt.max_trust_region_radius, radius);
+        decrease_factor = 2.0;
+        reuse_diagonal = false;
+        last_successful = true;
+        ++num_successful;
+        if (x_cost < min_cost) min_cost = x_cost;
+        push_log(x_cost, cost_change, step_norm, rho, lin, 1);
+      } else {
+        // HandleUnsuccessfulStep
+        radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+        last_successful = false;
+        ++num_unsuccessful;
+        push_log(cand_cost, cost_change, step_norm, rho, lin, 0);
+      }
+    }
+    PTZ_CUDA(cudaStreamSynchronize(stream));
+    clk.collect();
+    double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (out) fill_result(out, seconds);
+  }
+
+  void fill_result(ptzba_result* out, double seconds_solve) {
+    out->termination = termination;
+    out->num_iterations = (int)log.size() - 1;
+    out->num_successful_steps = num_successful;
+    out->num_unsuccessful_steps = num_unsuccessful;
+    out->num_residuals = 2 * (M + A);
+    if (g_nccl.world > 1) {
+      // every rank reports the size of the whole problem
+      double m = (double)M;
+      DevBuf<double> d;
+      d.upload(&m, 1, stream);
+      allreduce_sum(d.p, 1, stream);
+      d.download(&m, 1, stream);
+      PTZ_CUDA(cudaStreamSynchronize(stream));
+      out->num_residuals = 2 * ((int)llround(m) + A);
+    }
+    out->linear_solver_iterations = lin_iters_total;
+    out->initial_cost = initial_cost;
+    out->final_cost = min_cost;
+    out->init_reproj_error_all = sqrt(2.0) * sqrt((2 * initial_cost) / out->num_residuals);
+    out->final_reproj_error_all = sqrt(2.0) * sqrt((2 * min_cost) / out->num_residuals);
+    // CalReprojError2d2d / 2d3d at the final parameters (unweighted)
+    launch_cost(cur);
+    ScalarJobs J;
+    J.nsum = 1; J.nmax = 0;
+    J.sum_ptr[0] = d_cost_part.p + 1; J.sum_n[0] = st.nchunks(); J.sum_stride[0] = 2; J.sum_slot[0] = S_RAW2_CAND;
+    k_scalars<<<1, 256, 0, stream>>>(J, d_scalars.p);
+    allreduce_sum(d_scalars.p + S_RAW2_CAND, 1, stream);
+    read_scalars();
+    const double n2 = (double)(out->num_residuals / 2 - A);
+    out->final_reproj_error_2d2d = sqrt(h_scalars[S_RAW2_CAND] / n2);
+    out->final_reproj_error_2d3d = A > 0 ? sqrt(h_scalars[S_RAWPTS_CAND] / A) : sqrt(0.0 / 0.0);
+    // parameters
+    std::vector<double> intr(9 * (size_t)V), ext(6 * (size_t)V), trk((size_t)std::max(P, 1) * kTrk), tlw(6, 0.0);
+    d_intr[cur].download(intr.data(), intr.size(), stream);
+    d_ext[cur].download(ext.data(), ext.size(), stream);
+    d_trk[cur].download(trk.data(), trk.size(), stream);
+    d_tlw[cur].download(tlw.data(), 6, stream);
+    PTZ_CUDA(cudaStreamSynchronize(stream));
+    if (out->intr) memcpy(out->intr, intr.data(), intr.size() * 8);
+    if (out->ext) memcpy(out->ext, ext.data(), ext.size() * 8);
+    if (out->ray) for (int p = 0; p < P; ++p) for (int j = 0; j < 3; ++j) out->ray[3 * (size_t)p + j] = trk[(size_t)p * kTrk + j];
+    if (out->disp) out->disp[0] = out->disp[1] = out->disp[2] = 0.0;
+    if (out->tlw) memcpy(out->tlw, tlw.data(), 48);
+    // ObtainRefinedCameraParams (ptzray_optimizer.cc:672-766)
+    double Rlw[9];
+    rodrigues_jac(tlw.data(), Rlw, nullptr);
+    if (out->cams_world)
+      for (int i = 0; i < V; ++i) {
+        const double* in = &intr[9 * (size_t)i];
+        const double* ex = &ext[6 * (size_t)i];
+        double* c = out->cams_world + 21 * (size_t)i;
+        c[0] = in[0]; c[1] = (TYPE == BA_PTZRAY_FXFY_DIST) ? in[1] : in[0]; c[2] = in[2]; c[3] = in[3];
+        double R[9];
+        rodrigues_jac(ex, R, nullptr);
+        for (int r = 0; r < 3; ++r) {
+          c[13 + r] = R[3 * r] * tlw[3] + R[3 * r + 1] * tlw[4] + R[3 * r + 2] * tlw[5] + ex[3 + r];
+          for (int q = 0; q < 3; ++q) c[4 + 3 * r + q] = R[3 * r] * Rlw[q] + R[3 * r + 1] * Rlw[3 + q] + R[3 * r + 2] * Rlw[6 + q];
+        }
+        for (int j = 0; j < 5; ++j) c[16 + j] = in[4 + j];
+      }
+    if (out->rays_world)
+      for (int p = 0; p < P; ++p) {
+        const double* r = &trk[(size_t)p * kTrk];
+        for (int j = 0; j < 3; ++j)
+          out->rays_world[3 * (size_t)p + j] = Rlw[j] * (r[0] - tlw[3]) + Rlw[3 + j] * (r[1] - tlw[4]) + Rlw[6 + j] * (r[2] - tlw[5]);
+      }
+    out->log_count = 0;
+    if (out->log)
+      for (size_t i = 0; i < log.size() && (int)i < out->log_capacity; ++i) out->log[out->log_count++] = log[i];
+    out->seconds_setup = seconds_setup;
+    out->seconds_solve = seconds_solve;
+  }
+
+  // ptzba_eval: raw residuals + analytic Jacobian in the caller's observation order, weighted cost and gradient
+  void eval(const double* disp, ptzba_eval_out* out) override {
+    (void)disp;
+    const int ncv = (TYPE == BA_PTZRAY) ? 5 : 6;
+    const int wo = ncv + 3, wp = ncv + 6;
+    fill_ones(d_scale_cam.p, (size_t)V * NCL);
+    fill_ones(d_scale_b.p, kMaxBorder);
+    // pass 1: unweighted, unscaled records
+    launch_resjac(0);
+    std::vector<double> rec((size_t)std::max(M, 1) * D::RS), raw((size_t)std::max(A, 1) * 26);
+    d_rec.download(rec.data(), (size_t)M * D::RS, stream);
+    if (A > 0) d_pts_raw.download(raw.data(), (size_t)A * 26, stream);
+    PTZ_CUDA(cudaStreamSynchronize(stream));
+    // live column a -> column of the documented layout [fx, fy, (k1), w(3)]
+    int live2col[NCL];
+    for (int a = 0; a < NCL; ++a) {
+      if (TYPE == BA_PTZRAY) live2col[a] = a == 0 ? 0 : 1 + a;              // fx, w -> 0, 2,3,4
+      else if (TYPE == BA_PTZRAY_FXFY_DIST) live2col[a] = a;                // fx, fy, k1, w
+      else live2col[a] = a == 0 ? 0 : 1 + a;                                // fx, k1, w -> 0, 2, 3,4,5
+    }
+    for (int i = 0; i < M; ++i) {
+      const double* r = &rec[(size_t)i * D::RS];
+      const int k = st.perm[i];
+      if (out->residuals) { out->residuals[2 * (size_t)k] = r[0]; out->residuals[2 * (size_t)k + 1] = r[1]; }
+      if (out->jac_obs)
+        for (int row = 0; row < 2; ++row) {
+          double* o = out->jac_obs + ((size_t)k * 2 + row) * wo;
+          for (int c = 0; c < wo; ++c) o[c] = 0.0;
+          for (int a = 0; a < NCL; ++a) o[live2col[a]] = r[8 + row * NCL + a];
+          for (int j = 0; j < 3; ++j) o[ncv + j] = r[2 + row * 3 + j];
+        }
+    }
+    for (int i = 0; i < A; ++i) {
+      const double* r = &raw[(size_t)i * 26];
+      const int k = h_pt_perm[i];
+      if (out->residuals) { out->residuals[2 * (size_t)(M + k)] = r[0]; out->residuals[2 * (size_t)(M + k) + 1] = r[1]; }
+      if (out->jac_pts)
+        for (int row = 0; row < 2; ++row) {
+          double* o = out->jac_pts + ((size_t)k * 2 + row) * wp;
+          const double* jc = r + 2 + 6 * row;
+          const double* jt = r + 14 + 6 * row;
+          o[0] = jc[0]; o[1] = jc[1];
+          if (ncv == 6) o[2] = jc[2];
+          for (int j = 0; j < 3; ++j) o[ncv - 3 + j] = jc[3 + j];
+          for (int j = 0; j < 6; ++j) o[ncv + j] = jt[j];
+        }
+    }
+    // pass 2: weighted (still unscaled) -> cost and gradient
+    launch_resjac(1);
+    std::vector<double> g((size_t)V * NCL), Vh((size_t)std::max(P, 1) * 10), gb(std::max(nb, 1)), cv(V), cp(2, 0.0);
+    PTZ_CUDA(cudaMemcpyAsync(g.data(), p_g, g.size() * 8, cudaMemcpyDeviceToHost, stream));
+    PTZ_CUDA(cudaMemcpyAsync(cv.data(), p_cost_view, cv.size() * 8, cudaMemcpyDeviceToHost, stream));
+    if (P > 0) d_Vh.download(Vh.data(), (size_t)P * 10, stream);
+    if (nb > 0) PTZ_CUDA(cudaMemcpyAsync(gb.data(), p_gb, nb * 8, cudaMemcpyDeviceToHost, stream));
+    if (A > 0) PTZ_CUDA(cudaMemcpyAsync(cp.data(), p_cost_pts, 16, cudaMemcpyDeviceToHost, stream));
+    PTZ_CUDA(cudaStreamSynchronize(stream));
+    double cost = cp[0];
+    for (int v = 0; v < V; ++v) cost += cv[v];
+    out->cost = cost;
+    out->num_tangent = V * ncv + 3 * P + (A > 0 ? 6 : 0);
+    if (out->gradient) {
+      for (int i = 0; i < out->num_tangent; ++i) out->gradient[i] = 0.0;
+      for (int v = 0; v < V; ++v)
+        for (int a = 0; a < NCL; ++a) out->gradient[(size_t)v * ncv + live2col[a]] = g[(size_t)v * NCL + a];
+      for (int p = 0; p < P; ++p)
+        for (int j = 0; j < 3; ++j) out->gradient[(size_t)V * ncv + 3 * (size_t)p + j] = Vh[(size_t)p * 10 + 6 + j];
+      if (A > 0) {
+        for (int j = 0; j < 6; ++j) out->gradient[(size_t)V * ncv + 3 * (size_t)P + j] = gb[j];
+        if (kFyBorder) for (int k = 0; k < nav; ++k) out->gradient[(size_t)h_ann_view[k] * ncv + 1] = gb[6 + k];
+      }
+    }
+  }
+
+  void stage_times(ptzba_stage_times* t) override {
+    t->ms_resjac = clk.ms[0]; t->ms_reduce_schur = clk.ms[1]; t->ms_pcg = clk.ms[2]; t->ms_update_cost = clk.ms[3];
+    t->ms_total = clk.ms[0] + clk.ms[1] + clk.ms[2] + clk.ms[3];
+    t->launches_resjac = clk.launches[0]; t->launches_reduce_schur = clk.launches[1]; t->launches_pcg = clk.launches[2];
+    t->launches_update_cost = clk.launches[3];
+    t->launches_total = clk.launches[0] + clk.launches[1] + clk.launches[2] + clk.launches[3];
+    t->lm_iterations = (int)log.size() - 1; t->pcg_iterations = lin_iters_total; t->jacobian_evals = jac_evals; t->cost_evals = cost_evals;
+  }
+};
+
+static int check_problem(const ptzba_problem* p) {
+  if (!p) return PTZ_ERR_INVALID;
+  if (p->num_views <= 0 || p->num_tracks < 0 || p->num_obs < 0 || p->num_pts3d < 0) return PTZ_ERR_INVALID;  // CheckValid (:515-535)
+  if (!p->intr || !p->ext) return PTZ_ERR_INVALID;
+  if (p->num_obs > 0 && (!p->obs_uv || !p->obs_view || !p->obs_track || !p->track_weight)) return PTZ_ERR_INVALID;
+  if (p->num_pts3d > 0 && (!p->pt_uv || !p->pt_xyz || !p->pt_view)) return PTZ_ERR_INVALID;
+  if (p->factor_type < 0 || p->factor_type > 3) return PTZ_ERR_INVALID;
+  for (int k = 0; k < p->num_obs; ++k)
+    if (p->obs_view[k] < 0 || p->obs_view[k] >= p->num_views || p->obs_track[k] < 0 || p->obs_track[k] >= p->num_tracks) return PTZ_ERR_INVALID;
+  for (int k = 0; k < p->num_pts3d; ++k)
+    if (p->pt_view[k] < 0 || p->pt_view[k] >= p->num_views) return PTZ_ERR_INVALID;
+  if (p->shared_ic_id)
+    for (int i = 0; i < p->num_views; ++i)
+      if (p->shared_ic_id[i] != i) { set_last_error("shared intrinsics (SetSharedIntrinsics) are not built"); return PTZ_ERR_UNSUPPORTED; }
+  if (p->factor_type == PTZ_BA_PTZRAY_DIST_DISP) { set_last_error("PTZRayDistDisp is not built on the GPU path yet"); return PTZ_ERR_UNSUPPORTED; }
+  return PTZ_OK;
+}
+
+static BaSolverBase* make_solver(const ptzba_problem* p, const ptz_solver_options* o) {
+  switch (p->factor_type) {
+    case PTZ_BA_PTZRAY: return new BaSolver<BA_PTZRAY>(p, o);
+    case PTZ_BA_PTZRAY_DIST: return new BaSolver<BA_PTZRAY_DIST>(p, o);
+    default: return new BaSolver<BA_PTZRAY_FXFY_DIST>(p, o);
+  }
+}
+
+static int ensure_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) { set_last_error("no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e)); return PTZ_ERR_NO_DEVICE; }
+  return PTZ_OK;
+}
+
+template <class F>
+static int guarded(F&& f) {
+  try {
+    return f();
+  } catch (const CudaError& e) {
+    set_last_error("%s", e.what());
+    return e.code;
+  } catch (const std::exception& e) {
+    set_last_error("%s", e.what());
+    return PTZ_ERR_CUDA;
+  }
+}
+
+}  // namespace ptz
+
+using namespace ptz;
+
+struct ptzba_handle {
+  std::unique_ptr<BaSolverBase> s;
+};
+
+extern "C" {
+
+void ptz_solver_options_default(ptz_solver_options* o) {
+  o->max_num_iterations = 50;
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->jacobi_scaling = 1;
+  o->pcg_max_iterations = 2000;
+  o->pcg_rel_tolerance = 1e-13;
+  o->jacobian_mode = 0;
+  o->linear_solver = 1;
+  o->num_threads = 1;
+  o->verbose = 0;
+}
+
+const char* ptz_last_error(void) { return g_err; }
+
+int ptz_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int ptzba_create(const ptzba_problem* prob, const ptz_solver_options* opt, ptzba_handle** h) {
+  if (!h || !opt) return PTZ_ERR_INVALID;
+  *h = nullptr;
+  int rc = check_problem(prob);
+  if (rc != PTZ_OK) return rc;
+  if (opt->max_num_iterations <= 0) return PTZ_ERR_INVALID;
+  rc = ensure_device();
+  if (rc != PTZ_OK) return rc;
+  return guarded([&]() {
+    ptzba_handle* hh = new ptzba_handle();
+    try {
+      hh->s.reset(make_solver(prob, opt));
+    } catch (...) {
+      delete hh;
+      throw;
+    }
+    *h = hh;
+    return (int)PTZ_OK;
+  });
+}
+
+int ptzba_reset(ptzba_handle* h) {
+  if (!h) return PTZ_ERR_INVALID;
+  return guarded([&]() { h->s->reset(); return (int)PTZ_OK; });
+}
+
+int ptzba_run(ptzba_handle* h, int max_new_iterations, ptzba_result* out) {
+  if (!h) return PTZ_ERR_INVALID;
+  return guarded([&]() { h->s->run(max_new_iterations, out); return (int)PTZ_OK; });
+}
+
+int ptzba_get_stage_times(ptzba_handle* h, ptzba_stage_times* t) {
+  if (!h || !t) return PTZ_ERR_INVALID;
+  h->s->stage_times(t);
+  return PTZ_OK;
+}
+
+int ptzba_destroy(ptzba_handle* h) {
+  delete h;
+  return PTZ_OK;
+}
+
+int ptzba_solve(const ptzba_problem* prob, const ptz_solver_options* opt, ptzba_result* out) {
+  if (!out) return PTZ_ERR_INVALID;
+  ptzba_handle* h = nullptr;
+  int rc = ptzba_create(prob, opt, &h);
+  if (rc != PTZ_OK) return rc;
+  rc = ptzba_run(h, opt->max_num_iterations + 1, out);
+  ptzba_destroy(h);
+  return rc;
+}
+
+int ptzba_eval(const ptzba_problem* prob, const double* disp, ptzba_eval_out* out) {
+  if (!out) return PTZ_ERR_INVALID;
+  ptz_solver_options o;
+  ptz_solver_options_default(&o);
+  ptzba_handle* h = nullptr;
+  int rc = ptzba_create(prob, &o, &h);
+  if (rc != PTZ_OK) return rc;
+  rc = guarded([&]() { h->s->eval(disp, out); return (int)PTZ_OK; });
+  ptzba_destroy(h);
+  return rc;
+}
+
+int ptz_nccl_unique_id(void* id_bytes128) {
+  if (!id_bytes128) return PTZ_ERR_INVALID;
+  return guarded([&]() {
+    ncclUniqueId id;
+    PTZ_NCCL(ncclGetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id_bytes128, &id, 128);
+    return (int)PTZ_OK;
+  });
+}
+
+int ptz_nccl_init(const void* id_bytes128, int rank, int world_size) {
+  if (!id_bytes128 || rank < 0 || world_size <= 0 || rank >= world_size) return PTZ_ERR_INVALID;
+  return guarded([&]() {
+    ncclUniqueId id;
+    memcpy(&id, id_bytes128, 128);
+    if (g_nccl.comm) { ncclCommDestroy(g_nccl.comm); g_nccl.comm = nullptr; }
+    PTZ_NCCL(ncclCommInitRank(&g_nccl.comm, world_size, id, rank));
+    g_nccl.rank = rank;
+    g_nccl.world = world_size;
+    return (int)PTZ_OK;
+  });
+}
+
+int ptz_nccl_finalize(void) {
+  if (g_nccl.comm) { ncclCommDestroy(g_nccl.comm); g_nccl.comm = nullptr; }
+  g_nccl.rank = 0;
+  g_nccl.world = 1;
+  return PTZ_OK;
+}
+
+}  // extern "C"

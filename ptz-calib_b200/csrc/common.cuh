@@ -1,0 +1,97 @@
+// common.cuh — error handling, device buffers and reduction helpers shared by the BA and reloc translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ptzcalib_b200.h"
+
+namespace ptz {
+
+void set_last_error(const char* fmt, ...);
+
+struct CudaError : std::runtime_error {
+  int code;
+  CudaError(int c, const std::string& s) : std::runtime_error(s), code(c) {}
+};
+
+#define PTZ_CUDA(expr)                                                                                        \
+  do {                                                                                                        \
+    cudaError_t _e = (expr);                                                                                  \
+    if (_e != cudaSuccess) {                                                                                  \
+      char _b[512];                                                                                           \
+      snprintf(_b, sizeof(_b), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));         \
+      throw ::ptz::CudaError(PTZ_ERR_CUDA, _b);                                                               \
+    }                                                                                                         \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) PTZ_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+  }
+  void zero(cudaStream_t s) {
+    if (n) PTZ_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+  }
+  void upload(const T* h, size_t count, cudaStream_t s) {
+    if (count > n) alloc(count);
+    if (count) PTZ_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+  void download(T* h, size_t count, cudaStream_t s) const {
+    if (count) PTZ_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;  // valid in lane 0
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum of NV values per thread; result valid in thread 0.  sm must hold NV * (blockDim/32) doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* sm) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double s = warp_sum(v[i]);
+    if (lane == 0) sm[wid * NV + i] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double s = 0;
+      for (int w = 0; w < nw; ++w) s += sm[w * NV + i];
+      v[i] = s;
+    }
+  }
+  __syncthreads();
+}
+#endif
+
+}  // namespace ptz

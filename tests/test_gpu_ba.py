@@ -1,0 +1,174 @@
+"""PTZ-BA on the GPU (through the C ABI) against the CPU oracle.  Run on the B200 box: pytest -m gpu.
+
+Tolerances are the north star's: residuals and gradients 1e-9 relative, final cost 1e-6 relative, refined
+parameters 1e-6 rad / 1e-4 px focal (BASELINE.json).  The oracle's Jacobian here is the exact (dual-number) one;
+the Ceres-CENTRAL emulation is compared separately with its documented noise floor."""
+import numpy as np
+import pytest
+
+import ptz_calib_b200 as ptz
+from conftest import relerr
+from ptz_calib_b200 import abi, synth
+
+pytestmark = pytest.mark.gpu
+
+TYPES = [abi.PTZ_BA_PTZRAY, abi.PTZ_BA_PTZRAY_DIST, abi.PTZ_BA_PTZRAY_FXFY_DIST]
+
+
+def small_scene(t, **kw):
+    if t == abi.PTZ_BA_PTZRAY_DIST:
+        return synth.make_config(2, scale=0.25, **kw)
+    return synth.make_config(1, scale=0.3, factor_type=t, **kw)
+
+
+@pytest.mark.parametrize("t", TYPES)
+def test_eval_matches_oracle(orc, t):
+    p = small_scene(t)
+    p = p.with_params(ray=orc.ba_init_rays(p))
+    got, want = ptz.ba_eval(p), orc.ba_eval(p)
+    assert np.abs(got.residuals - want.residuals).max() <= 1e-9 * max(1.0, np.abs(want.residuals).max())
+    assert np.abs(got.jac_obs - want.jac_obs).max() <= 1e-9 * np.abs(want.jac_obs).max()
+    assert abs(got.cost - want.cost) <= 1e-12 * want.cost
+    assert np.abs(got.gradient - want.gradient).max() <= 1e-9 * np.abs(want.gradient).max()
+    # against Ceres' own numeric Jacobian: at its noise floor (a few e-9 of the gradient scale)
+    num = orc.ba_eval(p, jacobian_mode=1)
+    assert np.abs(got.gradient - num.gradient).max() <= 2e-8 * np.abs(num.gradient).max()
+
+
+@pytest.mark.parametrize("t", TYPES)
+def test_eval_with_annotated_points(orc, t):
+    p = small_scene(t, num_pts3d=12)
+    p = p.with_params(ray=orc.ba_init_rays(p))
+    got, want = ptz.ba_eval(p), orc.ba_eval(p)
+    assert got.residuals.shape == (p.M + p.A, 2)
+    assert np.abs(got.residuals - want.residuals).max() <= 1e-9 * max(1.0, np.abs(want.residuals).max())
+    assert np.abs(got.jac_pts - want.jac_pts).max() <= 1e-9 * np.abs(want.jac_pts).max()
+    assert abs(got.cost - want.cost) <= 1e-12 * want.cost
+    assert np.abs(got.gradient - want.gradient).max() <= 1e-9 * np.abs(want.gradient).max()
+
+
+def test_init_rays_match_pix2ray(orc):
+    p = small_scene(abi.PTZ_BA_PTZRAY)
+    r = ptz.ba_solve(p, max_num_iterations=1, function_tolerance=0.0)  # rays after one step are not the initial ones; use eval instead
+    e = ptz.ba_eval(p)  # ray0 is None: the library computes Pix2Ray itself, the oracle too
+    w = orc.ba_eval(p)
+    assert np.abs(e.residuals - w.residuals).max() <= 1e-9 * np.abs(w.residuals).max()
+    assert r.num_iterations >= 1
+
+
+def rel_rot(ext, orc):
+    R = np.array([orc.rodrigues(e[:3]) for e in ext])
+    return R @ R[0].T
+
+
+def check_solve(orc, p, got, want, label=""):
+    assert got.termination == want.termination, (label, got.termination, want.termination)
+    assert got.num_iterations == want.num_iterations, (label, got.num_iterations, want.num_iterations)
+    assert got.num_successful_steps == want.num_successful_steps
+    assert abs(got.initial_cost - want.initial_cost) <= 1e-11 * want.initial_cost
+    assert abs(got.final_cost - want.final_cost) <= 1e-6 * want.final_cost, (label, got.final_cost, want.final_cost)
+    assert got.num_residuals == want.num_residuals
+    for a in ("init_reproj_error_all", "final_reproj_error_all", "final_reproj_error_2d2d"):
+        assert abs(getattr(got, a) - getattr(want, a)) <= 1e-6 * getattr(want, a), a
+    # per-iteration table (cost, radius, accept/reject decisions)
+    assert len(got.log) == len(want.log)
+    for lg, lw in zip(got.log, want.log):
+        assert lg["step_is_successful"] == lw["step_is_successful"]
+        assert abs(lg["cost"] - lw["cost"]) <= 1e-7 * lw["cost"]
+        assert abs(lg["trust_region_radius"] - lw["trust_region_radius"]) <= 1e-4 * lw["trust_region_radius"]
+    # refined parameters: 1e-4 px focal, 1e-6 rad on the gauge-invariant relative rotations and on the raw rvecs
+    assert np.abs(got.intr[:, 0] - want.intr[:, 0]).max() <= 1e-4, np.abs(got.intr[:, 0] - want.intr[:, 0]).max()
+    assert np.abs(got.intr[:, 4] - want.intr[:, 4]).max() <= 1e-7
+    assert np.abs(rel_rot(got.ext, orc) - rel_rot(want.ext, orc)).max() <= 1e-6
+    assert np.abs(got.ext - want.ext).max() <= 1e-6
+    assert np.abs(got.ray - want.ray).max() <= 1e-6
+    assert np.abs(got.cams_world - want.cams_world)[:, 4:13].max() <= 1e-6
+
+
+@pytest.mark.parametrize("t", TYPES)
+def test_solve_matches_oracle(orc, t):
+    p = small_scene(t)
+    got = ptz.ba_solve(p, max_num_iterations=200)
+    rc, want = orc.ba_solve(p, max_num_iterations=200)
+    assert rc == 0
+    check_solve(orc, p, got, want, f"type{t}")
+    assert got.converged  # PTZRayOptimizer::Solve returns true
+
+
+@pytest.mark.parametrize("t", [abi.PTZ_BA_PTZRAY, abi.PTZ_BA_PTZRAY_DIST])
+def test_georef_solve_matches_oracle(orc, t):
+    """RunGeoreferencing (run_ptz_ba.cc:131-155): ray terms + annotated 2d-3d points, free T_l_w"""
+    p = small_scene(t, num_pts3d=15)
+    got = ptz.ba_solve(p, max_num_iterations=200)
+    rc, want = orc.ba_solve(p, max_num_iterations=200)
+    assert rc == 0
+    check_solve(orc, p, got, want, f"georef{t}")
+    assert abs(got.final_reproj_error_2d3d - want.final_reproj_error_2d3d) <= 1e-6 * want.final_reproj_error_2d3d
+    assert np.abs(got.tlw - want.tlw).max() <= 1e-5
+    assert np.abs(got.intr[:, 1] - want.intr[:, 1]).max() <= 1e-4  # fy of the annotated views is driven by the 2d-3d terms only
+    assert np.abs(got.cams_world - want.cams_world).max() <= 1e-4
+
+
+def test_iteration_cap_reports_no_convergence(orc):
+    p = small_scene(abi.PTZ_BA_PTZRAY)
+    got = ptz.ba_solve(p, max_num_iterations=1)
+    rc, want = orc.ba_solve(p, max_num_iterations=1)
+    assert got.termination == want.termination == abi.PTZ_NO_CONVERGENCE
+    assert not got.converged
+    assert abs(got.final_cost - want.final_cost) <= 1e-8 * want.final_cost
+    ok, cams, rays = ptz.PTZRayOptimizer(p, 1).Solve()
+    assert ok is False and cams is None  # outputs untouched unless CONVERGENCE (ptzray_optimizer.cc:482-487)
+
+
+def test_edge_cases(orc):
+    # a view without observations, a track list in arbitrary order, arbitrary observation order
+    p = small_scene(abi.PTZ_BA_PTZRAY)
+    rng = np.random.default_rng(3)
+    keep = p.obs_view != 2
+    sh = rng.permutation(int(keep.sum()))
+    q = ptz.BAProblem(p.factor_type, p.intr, p.ext, p.obs_uv[keep][sh], p.obs_view[keep][sh], p.obs_track[keep][sh], p.track_weight)
+    got = ptz.ba_solve(q, max_num_iterations=100)
+    rc, want = orc.ba_solve(q, max_num_iterations=100)
+    assert got.termination == want.termination and got.num_iterations == want.num_iterations
+    assert abs(got.final_cost - want.final_cost) <= 1e-6 * want.final_cost
+    assert np.array_equal(got.intr[2], p.intr[2]) and np.array_equal(got.ext[2], p.ext[2])  # untouched view
+    # no observations at all: nothing to do, cost 0
+    e = ptz.BAProblem(0, p.intr, p.ext, np.zeros((0, 2), np.float32), [], [], [])
+    r = ptz.ba_solve(e)
+    assert r.initial_cost == 0.0 and r.num_iterations == 0
+
+
+def test_handle_reuse_and_stage_times():
+    p = small_scene(abi.PTZ_BA_PTZRAY)
+    h = ptz.BAHandle(p, max_num_iterations=200)
+    a = h.run(200)
+    h.reset()
+    b = h.run(3)
+    c = h.run(200)
+    assert a.termination == c.termination and a.num_iterations == c.num_iterations
+    assert a.final_cost == c.final_cost  # bit-reproducible: every reduction has a fixed order
+    assert b.num_iterations == 3
+    t = h.stage_times()
+    assert t["launches_total"] > 0 and t["ms_total"] > 0 and t["lm_iterations"] == c.num_iterations
+    h.close()
+
+
+@pytest.mark.parametrize("t", [abi.PTZ_BA_PTZRAY, abi.PTZ_BA_PTZRAY_DIST])
+def test_full_size_properties(t):
+    """BASELINE cfg 4 at 1/4 size (V=250, M~5e5): no oracle at this size; size-independent properties instead."""
+    p = synth.make_config(4, scale=0.25, factor_type=t)
+    r = ptz.ba_solve(p, max_num_iterations=50)
+    assert r.converged
+    acc = [l["cost"] for l in r.log if l["step_is_successful"] == 1]
+    assert all(b < a for a, b in zip(acc, acc[1:]))  # accepted steps strictly decrease the cost
+    assert r.final_cost == min(acc)
+    assert 0.5 < r.final_reproj_error_2d2d < 1.2  # sigma = 0.5 px per axis -> ~0.7 px RMS at the optimum
+    assert np.abs(r.intr[:, 0] - p.gt["f"]).max() < 5.0
+    # idempotence: restarting from the solution stops at once with the same cost
+    q = p.with_params(intr=r.intr, ext=r.ext, ray=r.ray)
+    r2 = ptz.ba_solve(q, max_num_iterations=50)
+    assert r2.num_iterations <= 2 and abs(r2.final_cost - r.final_cost) <= 1e-6 * r.final_cost
+    # gradient at the solution is small relative to the initial one
+    g0 = ptz.ba_eval(p).gradient
+    g1 = ptz.ba_eval(q).gradient
+    assert np.abs(g1).max() < 1e-3 * np.abs(g0).max()

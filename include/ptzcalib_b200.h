@@ -164,12 +164,19 @@ typedef struct ptzba_handle ptzba_handle;
 int ptzba_create(const ptzba_problem* prob, const ptz_solver_options* opt, ptzba_handle** h);
 int ptzba_reset(ptzba_handle* h);                               /* back to the initial parameters */
 int ptzba_run(ptzba_handle* h, int max_new_iterations, ptzba_result* out); /* out arrays may be NULL */
-/* device-time of the individual stages over the last ptzba_run, in ms, and launch counts */
+/* device time (CUDA events on the solver's stream) of every kernel of the LM loop since create/reset, by kernel id */
+enum {
+  PTZ_K_VIEW_PREP = 0, PTZ_K_RESJAC, PTZ_K_VIEW_FINALIZE, PTZ_K_TRACK_ACCUM, PTZ_K_PTS,       /* stage 1 */
+  PTZ_K_TRACK_SOLVE, PTZ_K_SCHUR_DIAG, PTZ_K_SCHUR_OFFDIAG, PTZ_K_PRECOND,                     /* stage 2 */
+  PTZ_K_PCG,                                                                                   /* stage 3 */
+  PTZ_K_TRACK_BACKSUB, PTZ_K_CAM_UPDATE, PTZ_K_COST, PTZ_K_SCALARS,                            /* stage 4 */
+  PTZ_K_ALLREDUCE, PTZ_K_COUNT = 16
+};
 typedef struct ptzba_stage_times {
-  float ms_resjac, ms_reduce_schur, ms_pcg, ms_update_cost, ms_total;
-  int launches_resjac, launches_reduce_schur, launches_pcg, launches_update_cost, launches_total;
-  int lm_iterations, pcg_iterations;
-  int jacobian_evals, cost_evals;
+  float ms_kernel[16];   /* summed device time per kernel id */
+  int launches[16];      /* launches per kernel id */
+  float ms_run;          /* device span of the ptzba_run calls (first launch to last completion, host gaps included) */
+  int lm_iterations, pcg_iterations, jacobian_evals, cost_evals;
 } ptzba_stage_times;
 int ptzba_get_stage_times(ptzba_handle* h, ptzba_stage_times* t);
 int ptzba_destroy(ptzba_handle* h);

@@ -397,6 +397,7 @@ struct Problem {
   virtual void eval_j(int k, const JetT* args, JetT* res) const = 0;
   // optional structure for the Schur path
   int ray_tan_begin = 0, ray_tan_end = 0;  // tangent range eliminated first (empty for KRT)
+  int cam_block = 0, num_cam_blocks = 0;   // reduced columns [0, cam_block*num_cam_blocks) come in per-view blocks; the rest is one border block
 };
 
 // evaluate one block: raw residual, raw Jacobian over ALL its global coordinates (mode 0 exact, 1 Ceres CENTRAL)
@@ -583,9 +584,29 @@ bool solve_schur(const Problem& P, const std::vector<BlockJ>& B, const double* D
     }
     W.built = true;
   }
-  std::vector<double> S((size_t)nC * nC, 0.0), rhs(nC, 0.0);
+  // reduced system storage: dense (exact Cholesky, small problems) or block-sparse by view (PCG, large problems)
+  const bool sparse = (linear_solver == 1);
+  const int bs = P.cam_block > 0 ? P.cam_block : 1, nvb = sparse ? P.num_cam_blocks : 0, nblk = nvb + 1, bbs = nC - nvb * bs;  // border block size
+  auto blk_of = [&](int c) { return c < nvb * bs ? c / bs : nvb; };
+  auto blk_off = [&](int c) { return c < nvb * bs ? c % bs : c - nvb * bs; };
+  auto blk_size = [&](int b) { return b < nvb ? bs : bbs; };
+  const int mbs = std::max(bs, bbs);
+  std::vector<double> S(sparse ? 0 : (size_t)nC * nC, 0.0), rhs(nC, 0.0);
+  std::vector<std::vector<std::pair<int, int>>> rows(sparse ? nblk : 0);  // per block row: (block col, slot)
+  std::vector<double> blocks;                                            // slot -> mbs*mbs values
+  auto slot_of = [&](int bi, int bj) {
+    for (auto& e : rows[bi]) if (e.first == bj) return e.second;
+    int sl = (int)(blocks.size() / ((size_t)mbs * mbs));
+    blocks.resize(blocks.size() + (size_t)mbs * mbs, 0.0);
+    rows[bi].push_back(std::make_pair(bj, sl));
+    return sl;
+  };
+  auto Sadd = [&](int i, int j, double v) {
+    if (!sparse) { S[(size_t)i * nC + j] += v; return; }
+    blocks[(size_t)slot_of(blk_of(i), blk_of(j)) * mbs * mbs + blk_off(i) * mbs + blk_off(j)] += v;
+  };
   for (int t = 0; t < nt; ++t)
-    if (t < rb || t >= re) S[(size_t)cidx(t) * nC + cidx(t)] = D[t] * D[t];
+    if (t < rb || t >= re) Sadd(cidx(t), cidx(t), D[t] * D[t]);
   auto add_FtF = [&](const BlockJ& b) {
     for (int a = 0; a < b.nc; ++a) {
       if (b.col[a] >= rb && b.col[a] < re) continue;
@@ -593,7 +614,7 @@ bool solve_schur(const Problem& P, const std::vector<BlockJ>& B, const double* D
       rhs[ia] += b.J[0][a] * b.r[0] + b.J[1][a] * b.r[1];
       for (int c = 0; c < b.nc; ++c) {
         if (b.col[c] >= rb && b.col[c] < re) continue;
-        S[(size_t)ia * nC + cidx(b.col[c])] += b.J[0][a] * b.J[0][c] + b.J[1][a] * b.J[1][c];
+        Sadd(ia, cidx(b.col[c]), b.J[0][a] * b.J[0][c] + b.J[1][a] * b.J[1][c]);
       }
     }
   };
@@ -647,41 +668,76 @@ bool solve_schur(const Problem& P, const std::vector<BlockJ>& B, const double* D
     for (size_t a = 0; a < cols.size(); ++a) {
       rhs[cols[a]] -= Wm[a * 3] * t0 + Wm[a * 3 + 1] * t1 + Wm[a * 3 + 2] * t2;
       for (size_t c = 0; c < cols.size(); ++c)
-        S[(size_t)cols[a] * nC + cols[c]] -= Wm[a * 3] * Wm[c * 3] + Wm[a * 3 + 1] * Wm[c * 3 + 1] + Wm[a * 3 + 2] * Wm[c * 3 + 2];
+        Sadd(cols[a], cols[c], -(Wm[a * 3] * Wm[c * 3] + Wm[a * 3 + 1] * Wm[c * 3 + 1] + Wm[a * 3 + 2] * Wm[c * 3 + 2]));
     }
   }
   std::vector<double> yc(rhs);
   *lin_iters = 0;
-  if (linear_solver == 0) {
+  if (!sparse) {
     std::vector<double> L(S);
     if (!cholesky_inplace(L, nC)) return false;
     cholesky_solve(L, nC, yc.data());
   } else {
-    // Jacobi-preconditioned CG (diagonal; the oracle's iterative option exists for the large CPU baseline only)
+    // block-Jacobi preconditioned CG on the block-sparse reduced system, run to opt.pcg_rel_tolerance ("exact" stand-in
+    // for the sparse Cholesky of SPARSE_SCHUR on problems where a dense factorisation would dominate the CPU baseline)
+    std::vector<std::vector<double>> Minv(nblk);
+    for (int b = 0; b < nblk; ++b) {
+      const int n = blk_size(b);
+      if (n == 0) continue;
+      std::vector<double> A((size_t)n * n);
+      const double* Bd = &blocks[(size_t)slot_of(b, b) * mbs * mbs];
+      for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) A[(size_t)i * n + j] = Bd[i * mbs + j];
+      if (!cholesky_inplace(A, n)) return false;
+      Minv[b].assign((size_t)n * n, 0.0);
+      for (int c = 0; c < n; ++c) {
+        std::vector<double> e(n, 0.0);
+        e[c] = 1.0;
+        cholesky_solve(A, n, e.data());
+        for (int i = 0; i < n; ++i) Minv[b][(size_t)i * n + c] = e[i];
+      }
+    }
+    auto boff = [&](int b) { return b < nvb ? b * bs : nvb * bs; };
+    auto apply_M = [&](const std::vector<double>& r, std::vector<double>& z) {
+      for (int b = 0; b < nblk; ++b) {
+        const int n = blk_size(b), o = boff(b);
+        for (int i = 0; i < n; ++i) { double sacc = 0; for (int j = 0; j < n; ++j) sacc += Minv[b][(size_t)i * n + j] * r[o + j]; z[o + i] = sacc; }
+      }
+    };
+    auto apply_S = [&](const std::vector<double>& x, std::vector<double>& out) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16)
+#endif
+      for (int bi = 0; bi < nblk; ++bi) {
+        const int ni = blk_size(bi), oi = boff(bi);
+        for (int i = 0; i < ni; ++i) out[oi + i] = 0;
+        for (auto& e : rows[bi]) {
+          const int nj = blk_size(e.first), oj = boff(e.first);
+          const double* Bd = &blocks[(size_t)e.second * mbs * mbs];
+          for (int i = 0; i < ni; ++i) { double sacc = 0; for (int j = 0; j < nj; ++j) sacc += Bd[i * mbs + j] * x[oj + j]; out[oi + i] += sacc; }
+        }
+      }
+    };
     std::vector<double> x(nC, 0.0), r(rhs), z(nC), p(nC), Ap(nC);
     double bn = 0;
     for (int i = 0; i < nC; ++i) bn += rhs[i] * rhs[i];
     bn = std::sqrt(bn);
+    apply_M(r, z);
+    p = z;
     double rz = 0;
-    for (int i = 0; i < nC; ++i) { z[i] = r[i] / S[(size_t)i * nC + i]; p[i] = z[i]; rz += r[i] * z[i]; }
+    for (int i = 0; i < nC; ++i) rz += r[i] * z[i];
     int it = 0;
-    for (; it < opt.pcg_max_iterations && bn > 0; ++it) {
-#ifdef _OPENMP
-#pragma omp parallel for schedule(static)
-#endif
-      for (int i = 0; i < nC; ++i) {
-        double s = 0;
-        const double* Si = &S[(size_t)i * nC];
-        for (int j = 0; j < nC; ++j) s += Si[j] * p[j];
-        Ap[i] = s;
-      }
+    for (; it < opt.pcg_max_iterations && bn > 0;) {
+      apply_S(p, Ap);
       double pAp = 0;
       for (int i = 0; i < nC; ++i) pAp += p[i] * Ap[i];
+      if (!(pAp > 0)) return false;
       double alpha = rz / pAp, rn = 0;
       for (int i = 0; i < nC; ++i) { x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; rn += r[i] * r[i]; }
-      if (std::sqrt(rn) <= opt.pcg_rel_tolerance * bn) { ++it; break; }
+      ++it;
+      if (std::sqrt(rn) <= opt.pcg_rel_tolerance * bn) break;
+      apply_M(r, z);
       double rz2 = 0;
-      for (int i = 0; i < nC; ++i) { z[i] = r[i] / S[(size_t)i * nC + i]; rz2 += r[i] * z[i]; }
+      for (int i = 0; i < nC; ++i) rz2 += r[i] * z[i];
       double beta = rz2 / rz;
       rz = rz2;
       for (int i = 0; i < nC; ++i) p[i] = z[i] + beta * p[i];
@@ -901,6 +957,7 @@ struct BaProblem : Problem {
     num_tangent = t;
     tan2amb.assign(t, 0);
     for (int i = 0; i < num_ambient; ++i) if (amb2tan[i] >= 0) tan2amb[amb2tan[i]] = i;
+    cam_block = ncv; num_cam_blocks = V;
   }
   // functor argument order: 2d-2d: intr(9) [disp(3)] ext(6) ray(3); 2d-3d: intr(9) [disp(3)] ext(6) tlw(6)
   int block_params(int k, int* amb) const override {

@@ -68,7 +68,14 @@ class BAHandle:
     def stage_times(self) -> dict:
         t = abi.StageTimesC()
         lib.check(lib.load().ptzba_get_stage_times(self._h, C.byref(t)), "ptzba_get_stage_times")
-        return {k: getattr(t, k) for k, _ in abi.StageTimesC._fields_}
+        out = dict(ms_run=t.ms_run, lm_iterations=t.lm_iterations, pcg_iterations=t.pcg_iterations, jacobian_evals=t.jacobian_evals,
+                   cost_evals=t.cost_evals, kernels={})
+        for i, name in enumerate(abi.KERNEL_NAMES[:15]):
+            if t.launches[i]:
+                out["kernels"][name] = dict(ms=float(t.ms_kernel[i]), launches=int(t.launches[i]), stage=abi.KERNEL_STAGE[name])
+        out["launches_total"] = sum(k["launches"] for k in out["kernels"].values())
+        out["ms_kernels_total"] = sum(k["ms"] for k in out["kernels"].values())
+        return out
 
     def close(self):
         if self._h:

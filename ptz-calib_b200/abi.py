@@ -117,18 +117,17 @@ class BAEvalOutC(C.Structure):
     ]
 
 
+KERNEL_NAMES = ["view_prep", "resjac", "view_finalize", "track_accum", "pts", "track_solve", "schur_diag", "schur_offdiag", "precond", "pcg",
+                "track_backsub", "cam_update", "cost", "scalars", "allreduce", "_"]
+KERNEL_STAGE = {"view_prep": 1, "resjac": 1, "view_finalize": 1, "track_accum": 1, "pts": 1, "track_solve": 2, "schur_diag": 2, "schur_offdiag": 2,
+                "precond": 2, "pcg": 3, "track_backsub": 4, "cam_update": 4, "cost": 4, "scalars": 4, "allreduce": 2}
+
+
 class StageTimesC(C.Structure):
     _fields_ = [
-        ("ms_resjac", C.c_float),
-        ("ms_reduce_schur", C.c_float),
-        ("ms_pcg", C.c_float),
-        ("ms_update_cost", C.c_float),
-        ("ms_total", C.c_float),
-        ("launches_resjac", C.c_int),
-        ("launches_reduce_schur", C.c_int),
-        ("launches_pcg", C.c_int),
-        ("launches_update_cost", C.c_int),
-        ("launches_total", C.c_int),
+        ("ms_kernel", C.c_float * 16),
+        ("launches", C.c_int * 16),
+        ("ms_run", C.c_float),
         ("lm_iterations", C.c_int),
         ("pcg_iterations", C.c_int),
         ("jacobian_evals", C.c_int),

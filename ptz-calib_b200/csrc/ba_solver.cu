@@ -67,18 +67,19 @@ enum Slot {
 
 struct StageClock {
   std::vector<cudaEvent_t> ev;
-  std::vector<int> tag;  // stage of interval [2i, 2i+1]
+  std::vector<int> tag;  // kernel id of interval [2i, 2i+1]; -1 = a whole ptzba_run
   size_t used = 0;
-  float ms[4] = {0, 0, 0, 0};
-  int launches[4] = {0, 0, 0, 0};
+  float ms[PTZ_K_COUNT] = {0};
+  int launches[PTZ_K_COUNT] = {0};
+  float ms_run = 0;
   cudaStream_t stream = nullptr;
   void init(cudaStream_t s) { stream = s; }
-  void begin(int stage) {
+  void begin(int id) {
     if (used + 2 > ev.size()) {
-      for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+      for (int i = 0; i < 256; ++i) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
     }
     cudaEventRecord(ev[used], stream);
-    tag.push_back(stage);
+    tag.push_back(id);
     ++used;
   }
   void end() { cudaEventRecord(ev[used], stream); ++used; }
@@ -86,14 +87,16 @@ struct StageClock {
     for (size_t i = 0; i + 1 < used; i += 2) {
       float t = 0;
       cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
-      ms[tag[i / 2]] += t;
+      if (tag[i / 2] < 0) ms_run += t; else ms[tag[i / 2]] += t;
     }
     used = 0;
     tag.clear();
   }
-  void reset() { collect(); for (int i = 0; i < 4; ++i) { ms[i] = 0; launches[i] = 0; } }
+  void reset() { collect(); for (int i = 0; i < PTZ_K_COUNT; ++i) { ms[i] = 0; launches[i] = 0; } ms_run = 0; }
   ~StageClock() { for (auto e : ev) cudaEventDestroy(e); }
 };
+// time one kernel launch (or one collective) under its id
+#define PTZ_TIMED(id, ...) do { clk.begin(id); __VA_ARGS__; clk.end(); ++clk.launches[id]; } while (0)
 
 // --------------------------------------------------------------------------------------------------------------
 // the solver, specialised on the factor type
@@ -338,13 +341,14 @@ struct BaSolver : BaSolverBase {
   // ---- stage 1 at the current point.  scale arrays must be valid (all ones on the very first pass).
   void launch_resjac(int weighted) {
     cudaStream_t s = stream;
-    k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[cur].p, d_ext[cur].p, d_vt.p, 1);
+    PTZ_TIMED(PTZ_K_VIEW_PREP, k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[cur].p, d_ext[cur].p, d_vt.p, 1));
     if (st.nchunks() > 0)
-      k_resjac<TYPE><<<st.nchunks(), kChunk, 0, s>>>(d_chunk_view.p, d_chunk_begin.p, d_chunk_cnt.p, d_uv.p, d_otrack.p, d_vt.p, d_trk[cur].p, d_scale_cam.p,
-                                                     d_disp.p, weighted, d_rec.p, d_part.p);
-    k_view_finalize<NCL><<<cdiv(V * D::NPART, 256), 256, 0, s>>>(V, d_view_chunk_off.p, d_part.p, d_scale_cam.p, p_U, p_g, p_cost_view, p_gabs);
-    if (P > 0) k_track_accum<<<nblk_ray, 128, 0, s>>>(P, D::RS, d_toff.p, d_tobs.p, d_rec.p, d_trk[cur].p, d_Vh.p, d_gmax_part.p);
-    clk.launches[0] += 4;
+      PTZ_TIMED(PTZ_K_RESJAC, k_resjac<TYPE><<<st.nchunks(), kChunk, 0, s>>>(d_chunk_view.p, d_chunk_begin.p, d_chunk_cnt.p, d_uv.p, d_otrack.p, d_vt.p,
+                                                                             d_trk[cur].p, d_scale_cam.p, d_disp.p, weighted, d_rec.p, d_part.p));
+    PTZ_TIMED(PTZ_K_VIEW_FINALIZE,
+              k_view_finalize<NCL><<<cdiv(V * D::NPART, 256), 256, 0, s>>>(V, d_view_chunk_off.p, d_part.p, d_scale_cam.p, p_U, p_g, p_cost_view, p_gabs));
+    if (P > 0)
+      PTZ_TIMED(PTZ_K_TRACK_ACCUM, k_track_accum<<<nblk_ray, 128, 0, s>>>(P, D::RS, d_toff.p, d_tobs.p, d_rec.p, d_trk[cur].p, d_Vh.p, d_gmax_part.p));
     if (A > 0) {
       PtsArgs a;
       a.A = A; a.nav = nav; a.nb = nb; a.fy_in_border = kFyBorder ? 1 : 0;
@@ -352,11 +356,10 @@ struct BaSolver : BaSolverBase {
       a.vt = d_vt.p; a.tlw = d_tlw[cur].p; a.scale_cam = d_scale_cam.p; a.scale_b = d_scale_b.p; a.scratch = d_pts_scratch.p;
       a.raw = weighted ? nullptr : d_pts_raw.p;
       a.U = p_U; a.g = p_g; a.gabs = p_gabs; a.C = p_C; a.Hbb = p_Hbb; a.gb = p_gb; a.cost_pts = p_cost_pts; a.gabs_b = p_gabs_b;
-      k_pts<TYPE><<<1, 128, 0, s>>>(a);
-      ++clk.launches[0];
+      PTZ_TIMED(PTZ_K_PTS, k_pts<TYPE><<<1, 128, 0, s>>>(a));
     }
     PTZ_CUDA(cudaGetLastError());
-    allreduce_sum(d_viewred.p, viewred_n, s);
+    if (g_nccl.world > 1) PTZ_TIMED(PTZ_K_ALLREDUCE, allreduce_sum(d_viewred.p, viewred_n, s));
   }
 
   void fill_ones(double* p, size_t count) {
@@ -367,7 +370,6 @@ struct BaSolver : BaSolverBase {
 
   // EvaluateGradientAndJacobian: cost, scaled Jacobian records, gradient max-norm
   void evaluate_jacobian(bool first) {
-    clk.begin(0);
     if (first) {
       fill_ones(d_scale_cam.p, (size_t)V * NCL);
       fill_ones(d_scale_b.p, kMaxBorder);
@@ -375,7 +377,6 @@ struct BaSolver : BaSolverBase {
         launch_resjac(1);
         k_make_scales<NCL><<<cdiv(std::max(V * NCL, P), 256), 256, 0, stream>>>(V, P, p_U, d_Vh.p, d_scale_cam.p, d_trk[0].p, d_trk[1].p);
         if (nb > 0) k_border_scales<<<1, 32, 0, stream>>>(nb, p_Hbb, d_scale_b.p);
-        clk.launches[0] += 1 + (nb > 0);
       }
     }
     launch_resjac(1);
@@ -390,11 +391,9 @@ struct BaSolver : BaSolverBase {
     add_max(p_gabs, V * NCL, S_GMAX_CAM);
     add_max(d_gmax_part.p, P > 0 ? nblk_ray : 0, S_GMAX_RAY);
     add_max(p_gabs_b, nb, S_GMAX_B);
-    k_scalars<<<1, 256, 0, stream>>>(J, d_scalars.p);
-    ++clk.launches[0];
+    PTZ_TIMED(PTZ_K_SCALARS, k_scalars<<<1, 256, 0, stream>>>(J, d_scalars.p));
     PTZ_CUDA(cudaGetLastError());
     allreduce_max(d_scalars.p + S_GMAX_RAY, S_MAX_END - S_GMAX_RAY, stream);
-    clk.end();
     read_scalars();
     x_cost = h_scalars[S_COST_X] + h_scalars[S_COSTPTS_X];
     grad_max = std::max(h_scalars[S_GMAX_CAM], std::max(h_scalars[S_GMAX_RAY], h_scalars[S_GMAX_B]));
@@ -414,23 +413,20 @@ struct BaSolver : BaSolverBase {
     const int refresh = reuse_diagonal ? 0 : 1;
     const int own = (g_nccl.rank == 0) ? 1 : 0;
     PTZ_CUDA(cudaMemsetAsync(d_fail.p, 0, sizeof(int), s));
-    clk.begin(1);
     if (P > 0)
-      k_track_solve<NCL><<<nblk_ray, 128, 0, s>>>(P, d_toff.p, d_tobs.p, d_rec.p, d_Vh.p, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_ray.p,
-                                                  d_Lt.p, d_What.p, d_q.p, d_fail.p);
-    k_schur_diag<NCL><<<V, 128, 0, s>>>(d_view_off.p, d_What.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, own, d_diag_cam.p,
-                                        d_diag_pos.p, p_Sval, p_rhs);
+      PTZ_TIMED(PTZ_K_TRACK_SOLVE, k_track_solve<NCL><<<nblk_ray, 128, 0, s>>>(P, d_toff.p, d_tobs.p, d_rec.p, d_Vh.p, mu, refresh, opt.min_lm_diagonal,
+                                                                               opt.max_lm_diagonal, d_diag_ray.p, d_Lt.p, d_What.p, d_q.p, d_fail.p));
+    PTZ_TIMED(PTZ_K_SCHUR_DIAG, k_schur_diag<NCL><<<V, 128, 0, s>>>(d_view_off.p, d_What.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal,
+                                                                    opt.max_lm_diagonal, own, d_diag_cam.p, d_diag_pos.p, p_Sval, p_rhs));
     if (st.nub() > 0)
-      k_schur_offdiag<NCL><<<cdiv(st.nub(), 8), 256, 0, s>>>(st.nub(), d_pair_off.p, d_pair_a.p, d_pair_b.p, d_What.p, d_ub_pos.p, d_ub_pos_t.p, p_Sval);
+      PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, k_schur_offdiag<NCL><<<cdiv(st.nub(), 8), 256, 0, s>>>(st.nub(), d_pair_off.p, d_pair_a.p, d_pair_b.p, d_What.p,
+                                                                                            d_ub_pos.p, d_ub_pos_t.p, p_Sval));
     if (nb > 0) k_border_system<<<1, 128, 0, s>>>(nb, p_Hbb, p_gb, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_b.p, d_Sbb.p, p_rhs + (size_t)V * NCL);
     PTZ_CUDA(cudaGetLastError());
-    allreduce_sum(d_sys.p, sys_n, s);
-    k_precond<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, d_diag_pos.p, p_Sval, d_Minv.p, d_fail.p);
+    if (g_nccl.world > 1) PTZ_TIMED(PTZ_K_ALLREDUCE, allreduce_sum(d_sys.p, sys_n, s));
+    PTZ_TIMED(PTZ_K_PRECOND, k_precond<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, d_diag_pos.p, p_Sval, d_Minv.p, d_fail.p));
     if (nb > 0) k_precond_border<<<1, 32, 0, s>>>(nb, d_Sbb.p, d_Minv_b.p, d_fail.p);
-    clk.launches[1] += 4 + 2 * (nb > 0);
-    clk.end();
     // ---- stage 3
-    clk.begin(2);
     PcgArgs a;
     a.V = V; a.nb = nb; a.n = n;
     a.rowptr = d_rowptr.p; a.col = d_col.p; a.Sval = p_Sval; a.Minv = d_Minv.p; a.rhs = p_rhs;
@@ -441,25 +437,20 @@ struct BaSolver : BaSolverBase {
     const int nrows = V + (nb > 0 ? 1 : 0);
     int grid = std::min(num_sms, cdiv(nrows, 8));
     void* args[] = {&a};
-    PTZ_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<NCL>, dim3(grid), dim3(256), args, 0, s));
-    ++clk.launches[2];
-    clk.end();
+    PTZ_TIMED(PTZ_K_PCG, PTZ_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<NCL>, dim3(grid), dim3(256), args, 0, s)));
     // ---- stage 4
-    clk.begin(3);
     const int nxt = cur ^ 1;
     const double* y = d_pcgvec.p;
     if (P > 0)
-      k_track_backsub<NCL><<<nblk_ray, 128, 0, s>>>(P, d_toff.p, d_tobs.p, d_oview.p, d_What.p, y, d_Lt.p, d_Vh.p, d_diag_ray.p, mu, d_trk[cur].p, d_trk[nxt].p,
-                                                    d_part3_ray.p);
-    k_cam_update<TYPE><<<nblk_cam, 128, 0, s>>>(V, y, d_scale_cam.p, p_g, d_diag_cam.p, mu, d_view_active.p, d_intr[cur].p, d_ext[cur].p, d_intr[nxt].p,
-                                                d_ext[nxt].p, d_part3_cam.p);
+      PTZ_TIMED(PTZ_K_TRACK_BACKSUB, k_track_backsub<NCL><<<nblk_ray, 128, 0, s>>>(P, d_toff.p, d_tobs.p, d_oview.p, d_What.p, y, d_Lt.p, d_Vh.p, d_diag_ray.p,
+                                                                                   mu, d_trk[cur].p, d_trk[nxt].p, d_part3_ray.p));
+    PTZ_TIMED(PTZ_K_CAM_UPDATE, k_cam_update<TYPE><<<nblk_cam, 128, 0, s>>>(V, y, d_scale_cam.p, p_g, d_diag_cam.p, mu, d_view_active.p, d_intr[cur].p,
+                                                                            d_ext[cur].p, d_intr[nxt].p, d_ext[nxt].p, d_part3_cam.p));
     if (nb > 0)
       k_border_update<<<1, 32, 0, s>>>(nb, nav, kFyBorder ? 1 : 0, d_ann_view.p, y + (size_t)V * NCL, d_scale_b.p, p_gb, d_diag_b.p, mu, d_tlw[cur].p,
                                        d_tlw[nxt].p, d_intr[cur].p, d_intr[nxt].p, d_part3_b.p);
     launch_cost(nxt);
     launch_step_scalars();
-    clk.launches[3] += 5 + (nb > 0) + (A > 0);
-    clk.end();
     read_scalars();
     ++cost_evals;
     *lin_iters = h_info[0];
@@ -470,10 +461,10 @@ struct BaSolver : BaSolverBase {
 
   void launch_cost(int which) {
     cudaStream_t s = stream;
-    k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[which].p, d_ext[which].p, d_vt.p, 0);
+    PTZ_TIMED(PTZ_K_VIEW_PREP, k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[which].p, d_ext[which].p, d_vt.p, 0));
     if (st.nchunks() > 0)
-      k_cost<TYPE><<<st.nchunks(), kChunk, 0, s>>>(d_chunk_view.p, d_chunk_begin.p, d_chunk_cnt.p, d_uv.p, d_otrack.p, d_vt.p, d_trk[which].p, d_disp.p,
-                                                   d_cost_part.p);
+      PTZ_TIMED(PTZ_K_COST, k_cost<TYPE><<<st.nchunks(), kChunk, 0, s>>>(d_chunk_view.p, d_chunk_begin.p, d_chunk_cnt.p, d_uv.p, d_otrack.p, d_vt.p,
+                                                                         d_trk[which].p, d_disp.p, d_cost_part.p));
     if (A > 0) k_pts_cost<<<1, 32, 0, s>>>(A, d_pts_uv.p, d_pts_xyz.p, d_pts_view.p, d_vt.p, d_tlw[which].p, d_scalars.p + S_COSTPTS_CAND);
     PTZ_CUDA(cudaGetLastError());
   }
@@ -493,7 +484,7 @@ struct BaSolver : BaSolverBase {
     add_sum(d_part3_b.p, 1, 3, S_DM_B);
     add_sum(d_part3_b.p + 1, 1, 3, S_STEP2_B);
     add_sum(d_part3_b.p + 2, 1, 3, S_XN2_B);
-    k_scalars<<<1, 256, 0, stream>>>(J, d_scalars.p);
+    PTZ_TIMED(PTZ_K_SCALARS, k_scalars<<<1, 256, 0, stream>>>(J, d_scalars.p));
     PTZ_CUDA(cudaGetLastError());
     allreduce_sum(d_scalars.p, S_SUM_END, stream);
   }
@@ -538,6 +529,9 @@ struct BaSolver : BaSolverBase {
 
   void run(int max_new_iterations, ptzba_result* out) override {
     auto t0 = std::chrono::steady_clock::now();
+    clk.begin(-1);
+    const size_t run_slot = clk.used;  // its end event is recorded below
+    clk.used += 1;
     if (!started) {
       // IterationZero
       x_norm = current_x_norm();
@@ -606,6 +600,7 @@ struct BaSolver : BaSolverBase {
         push_log(cand_cost, cost_change, step_norm, rho, lin, 0);
       }
     }
+    cudaEventRecord(clk.ev[run_slot], stream);
     PTZ_CUDA(cudaStreamSynchronize(stream));
     clk.collect();
     double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -760,11 +755,8 @@ struct BaSolver : BaSolverBase {
   }
 
   void stage_times(ptzba_stage_times* t) override {
-    t->ms_resjac = clk.ms[0]; t->ms_reduce_schur = clk.ms[1]; t->ms_pcg = clk.ms[2]; t->ms_update_cost = clk.ms[3];
-    t->ms_total = clk.ms[0] + clk.ms[1] + clk.ms[2] + clk.ms[3];
-    t->launches_resjac = clk.launches[0]; t->launches_reduce_schur = clk.launches[1]; t->launches_pcg = clk.launches[2];
-    t->launches_update_cost = clk.launches[3];
-    t->launches_total = clk.launches[0] + clk.launches[1] + clk.launches[2] + clk.launches[3];
+    for (int i = 0; i < PTZ_K_COUNT; ++i) { t->ms_kernel[i] = clk.ms[i]; t->launches[i] = clk.launches[i]; }
+    t->ms_run = clk.ms_run;
     t->lm_iterations = (int)log.size() - 1; t->pcg_iterations = lin_iters_total; t->jacobian_evals = jac_evals; t->cost_evals = cost_evals;
   }
 };

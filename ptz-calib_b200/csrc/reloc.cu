@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(32) k_reloc(RelocArgs a) {
   for (int i = 0; i < NF; ++i) grad_max = fmax(grad_max, fabs(g[i]));
   double radius = o.initial_trust_region_radius, decrease_factor = 2.0;
   bool reuse_diagonal = false, last_successful = true;
-  int iteration = 0, num_invalid = 0, num_successful = 1, termination = PTZ_NO_CONVERGENCE;
+  int iteration = 0, logged = 0, num_invalid = 0, num_successful = 1, termination = PTZ_NO_CONVERGENCE;
   const int max_iter = a.max_iter;
   while (true) {
     if (iteration >= max_iter) { termination = PTZ_NO_CONVERGENCE; break; }
@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(32) k_reloc(RelocArgs a) {
       if (num_invalid >= o.max_num_consecutive_invalid_steps) { termination = PTZ_FAILURE; break; }
       radius = radius / decrease_factor; decrease_factor *= 2.0;
       last_successful = false;
+      ++logged;
       continue;
     }
     num_invalid = 0;
@@ -235,6 +236,7 @@ __global__ void __launch_bounds__(32) k_reloc(RelocArgs a) {
       radius = radius / decrease_factor; decrease_factor *= 2.0;
       last_successful = false;
     }
+    ++logged;  // rows of Ceres' iteration table: the iteration that trips a tolerance is not recorded
   }
   // CheckResults (krt_optimizer.cc:504-533) and ObtainRefinedCameraParams (:535-567)
   if (lane == 0) {
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(32) k_reloc(RelocArgs a) {
     a.success[q] = ok;
     a.termination[q] = termination;
     a.num_iter[q] = num_successful;
-    if (a.iterations) a.iterations[q] = iteration;
+    if (a.iterations) a.iterations[q] = logged;
     if (a.initial_cost) a.initial_cost[q] = initial_cost;
     if (a.final_cost) a.final_cost[q] = min_cost;
     if (a.final_rms) a.final_rms[q] = final_rms;

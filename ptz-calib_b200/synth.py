@@ -225,7 +225,7 @@ def krt21(f, fy, c, R, t, dist):
 
 
 def make_reloc_batch(B, factor_type=abi.PTZ_KRT_F, seed=1003, n_min=64, n_max=512, width=1920, height=1080, sigma=0.5, outlier_frac=0.05,
-                     num_ref=36, dpan_deg=5.0, k1=-0.1, max_iter=200, max_reproj_error=100.0, query_seed=None):
+                     outlier_sigma=40.0, num_ref=36, dpan_deg=5.0, k1=-0.1, max_iter=200, max_reproj_error=100.0, query_seed=None):
     """cfg 3: B independent queries against a calibrated reference ring; init exactly as run_ptz_reloc.cc:97-104."""
     rng = np.random.default_rng(seed)
     Rref, fref, cref, _ = _views("ring", rng, num_ref, width, height)
@@ -265,7 +265,9 @@ def make_reloc_batch(B, factor_type=abi.PTZ_KRT_F, seed=1003, n_min=64, n_max=51
         uv_ref[todo] = uv_ref[off[qi[todo]]]
         uv_cur[todo] = uv_cur[off[qi[todo]]]
     out = q.random(N) < outlier_frac
-    uv_cur[out] = np.stack([q.uniform(0, width, int(out.sum())), q.uniform(0, height, int(out.sum()))], -1).astype(np.float32)
+    # gross outliers are mismatches displaced by N(0, outlier_sigma) px: kept, since the reference has no robust loss
+    # (krt_optimizer.cc:294); uniform-random ones would push most queries over the 100 px gate of CheckResults
+    uv_cur[out] = (uv_cur[out] + q.normal(0, outlier_sigma, (int(out.sum()), 2))).astype(np.float32)
     dist = np.zeros((B, 5))
     dist[:, 0] = k1v
     t0 = np.zeros((B, 3))

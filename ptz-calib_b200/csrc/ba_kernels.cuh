@@ -325,234 +325,312 @@ __global__ void __launch_bounds__(256) k_schur_offdiag(int nub, const int64_t* _
   }
 }
 
-// block-Jacobi preconditioner: explicit inverse of every diagonal camera block (and of the dense border block)
+// ---- block-Jacobi preconditioning applied as a SYMMETRIC SCALING of the reduced system --------------------------------
+// With S_cc = L_c L_c^T:  S~ = Linv S Linv^T (unit diagonal blocks), b~ = Linv b, y = Linv^T y~.  Plain CG on S~ has exactly
+// the iterates of block-Jacobi PCG on S, but no preconditioner application inside the iteration.
+//
+// k_precond: Linv_c (explicit inverse of the Cholesky factor of every diagonal block)
 template <int NCL>
-__global__ void k_precond(int V, const int* __restrict__ diag_pos, const double* __restrict__ Sval, double* __restrict__ Minv, int* __restrict__ fail) {
+__global__ void k_precond(int V, const int* __restrict__ diag_pos, const double* __restrict__ Sval, double* __restrict__ Linv, int* __restrict__ fail) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < V) {
-    double A[NCL * NCL];
-    const double* S = Sval + (size_t)diag_pos[v] * NCL * NCL;
+  if (v >= V) return;
+  double A[NCL * NCL];
+  const double* S = Sval + (size_t)diag_pos[v] * NCL * NCL;
 #pragma unroll
-    for (int i = 0; i < NCL * NCL; ++i) A[i] = S[i];
-    double* M = Minv + (size_t)v * NCL * NCL;
-    if (!chol_n(A, NCL, NCL)) {
-      atomicExch(fail, 2);
-      for (int i = 0; i < NCL * NCL; ++i) M[i] = (i / NCL == i % NCL) ? 1.0 : 0.0;
-    } else {
-      for (int c = 0; c < NCL; ++c) {
-        double e[NCL];
-        for (int i = 0; i < NCL; ++i) e[i] = (i == c) ? 1.0 : 0.0;
-        chol_solve_n(A, NCL, NCL, e);
-        for (int i = 0; i < NCL; ++i) M[i * NCL + c] = e[i];
-      }
+  for (int i = 0; i < NCL * NCL; ++i) A[i] = S[i];
+  double* M = Linv + (size_t)v * NCL * NCL;
+  if (!chol_n(A, NCL, NCL)) {
+    atomicExch(fail, 2);
+    for (int i = 0; i < NCL * NCL; ++i) M[i] = (i / NCL == i % NCL) ? 1.0 : 0.0;
+    return;
+  }
+  // X = L^-1 by forward substitution, column by column (lower triangular)
+  for (int c = 0; c < NCL; ++c) {
+    double x[NCL];
+    for (int i = 0; i < NCL; ++i) {
+      double sacc = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) sacc -= A[i * NCL + k] * x[k];
+      x[i] = (i < c) ? 0.0 : sacc / A[i * NCL + i];
     }
+    for (int i = 0; i < NCL; ++i) M[i * NCL + c] = x[i];
   }
 }
-
-// explicit inverse of the dense border block (nb <= 32): one warp, matrix in shared memory
-__global__ void __launch_bounds__(32) k_precond_border(int nb, const double* __restrict__ Sbb, double* __restrict__ Minv_b, int* __restrict__ fail) {
+// border block (nb <= 32): Cholesky in shared memory, one lane per column of L^-1
+__global__ void __launch_bounds__(32) k_precond_border(int nb, const double* __restrict__ Sbb, double* __restrict__ Linv_b, int* __restrict__ fail) {
   __shared__ double A[kMaxBorder * kMaxBorder];
   __shared__ int ok;
   for (int i = threadIdx.x; i < nb * nb; i += 32) A[i] = Sbb[i];
   __syncwarp();
   if (threadIdx.x == 0) { ok = chol_n(A, nb, nb) ? 1 : 0; if (!ok) atomicExch(fail, 3); }
   __syncwarp();
-  const int c = threadIdx.x;  // one column of the inverse per lane
+  const int c = threadIdx.x;
   if (c < nb) {
     if (!ok) {
-      for (int i = 0; i < nb; ++i) Minv_b[i * nb + c] = (i == c) ? 1.0 : 0.0;
+      for (int i = 0; i < nb; ++i) Linv_b[i * nb + c] = (i == c) ? 1.0 : 0.0;
     } else {
-      double e[kMaxBorder];
-      for (int i = 0; i < nb; ++i) e[i] = (i == c) ? 1.0 : 0.0;
-      chol_solve_n(A, nb, nb, e);
-      for (int i = 0; i < nb; ++i) Minv_b[i * nb + c] = e[i];
+      double x[kMaxBorder];
+      for (int i = 0; i < nb; ++i) {
+        double sacc = (i == c) ? 1.0 : 0.0;
+        for (int k = c; k < i; ++k) sacc -= A[i * nb + k] * x[k];
+        x[i] = (i < c) ? 0.0 : sacc / A[i * nb + i];
+      }
+      for (int i = 0; i < nb; ++i) Linv_b[i * nb + c] = x[i];
     }
   }
 }
 
+// CG state: per row three vectors (r, w = S~ r, s = S~ p), interleaved so that one neighbour is one contiguous gather:
+//   cams  : st[(c*3 + comp)*NCL + j]        border: st[3*V*NCL + comp*nb + j]
+// k_scale_system: one thread per block of S: B <- Linv_r B Linv_c^T (diagonal blocks become exactly I); the first V threads
+// also scale the right-hand side and write the initial CG state (r = b~, w = s = 0, x = p = 0).
+template <int NCL>
+__global__ void k_scale_system(int V, int nnzb, const int* __restrict__ blk_row, const int* __restrict__ col, const double* __restrict__ Linv,
+                               double* __restrict__ Sval, const double* __restrict__ rhs, double* __restrict__ st0, double* __restrict__ x,
+                               double* __restrict__ p) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nnzb) {
+    const int r = blk_row[k], c = col[k];
+    double* B = Sval + (size_t)k * NCL * NCL;
+    if (r == c) {
+#pragma unroll
+      for (int i = 0; i < NCL * NCL; ++i) B[i] = (i / NCL == i % NCL) ? 1.0 : 0.0;
+    } else {
+      double Lr[NCL * NCL], Lc[NCL * NCL], T[NCL * NCL], Bv[NCL * NCL];
+#pragma unroll
+      for (int i = 0; i < NCL * NCL; ++i) { Lr[i] = Linv[(size_t)r * NCL * NCL + i]; Lc[i] = Linv[(size_t)c * NCL * NCL + i]; Bv[i] = B[i]; }
+#pragma unroll
+      for (int i = 0; i < NCL; ++i)
+#pragma unroll
+        for (int j = 0; j < NCL; ++j) {
+          double sacc = 0;
+#pragma unroll
+          for (int q = 0; q <= i; ++q) sacc += Lr[i * NCL + q] * Bv[q * NCL + j];
+          T[i * NCL + j] = sacc;
+        }
+#pragma unroll
+      for (int i = 0; i < NCL; ++i)
+#pragma unroll
+        for (int j = 0; j < NCL; ++j) {
+          double sacc = 0;
+#pragma unroll
+          for (int q = 0; q <= j; ++q) sacc += T[i * NCL + q] * Lc[j * NCL + q];
+          B[i * NCL + j] = sacc;
+        }
+    }
+  }
+  if (k < V) {
+    double b[NCL];
+#pragma unroll
+    for (int i = 0; i < NCL; ++i) b[i] = rhs[k * NCL + i];
+#pragma unroll
+    for (int i = 0; i < NCL; ++i) {
+      double sacc = 0;
+#pragma unroll
+      for (int q = 0; q <= i; ++q) sacc += Linv[(size_t)k * NCL * NCL + i * NCL + q] * b[q];
+      st0[(k * 3 + 0) * NCL + i] = sacc; st0[(k * 3 + 1) * NCL + i] = 0.0; st0[(k * 3 + 2) * NCL + i] = 0.0;
+      x[k * NCL + i] = 0.0; p[k * NCL + i] = 0.0;
+    }
+  }
+}
+// border part of the scaling: strips C_k <- Linv_{c_k} C_k Linv_b^T, b_b <- Linv_b b_b, initial state of the border row
+template <int NCL>
+__global__ void __launch_bounds__(128) k_scale_border(int V, int nb, int nav, const int* __restrict__ ann_view, const double* __restrict__ Linv,
+                                                      const double* __restrict__ Linv_b, const double* __restrict__ C, double* __restrict__ Cs,
+                                                      const double* __restrict__ rhs, double* __restrict__ st0, double* __restrict__ x, double* __restrict__ p) {
+  for (int e = threadIdx.x; e < nav * NCL * nb; e += blockDim.x) {
+    const int k = e / (NCL * nb), i = (e / nb) % NCL, j = e % nb;
+    const double* Lr = Linv + (size_t)ann_view[k] * NCL * NCL;
+    const double* Ck = C + (size_t)k * NCL * nb;
+    double sacc = 0;
+    for (int q = 0; q <= i; ++q) {
+      double t = 0;
+      for (int m = 0; m <= j; ++m) t += Ck[q * nb + m] * Linv_b[j * nb + m];
+      sacc += Lr[i * NCL + q] * t;
+    }
+    Cs[e] = sacc;
+  }
+  const int boff = V * NCL;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    double sacc = 0;
+    for (int q = 0; q <= i; ++q) sacc += Linv_b[i * nb + q] * rhs[boff + q];
+    st0[3 * boff + 0 * nb + i] = sacc; st0[3 * boff + 1 * nb + i] = 0.0; st0[3 * boff + 2 * nb + i] = 0.0;
+    x[boff + i] = 0.0; p[boff + i] = 0.0;
+  }
+}
+// y = Linv^T y~ : back to the unscaled unknowns
+template <int NCL>
+__global__ void k_unscale(int V, int nb, const double* __restrict__ Linv, const double* __restrict__ Linv_b, const double* __restrict__ xs,
+                          double* __restrict__ y) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < V) {
+#pragma unroll
+    for (int i = 0; i < NCL; ++i) {
+      double sacc = 0;
+#pragma unroll
+      for (int q = i; q < NCL; ++q) sacc += Linv[(size_t)v * NCL * NCL + q * NCL + i] * xs[v * NCL + q];
+      y[v * NCL + i] = sacc;
+    }
+  } else if (v < V + nb) {
+    const int i = v - V, boff = V * NCL;
+    double sacc = 0;
+    for (int q = i; q < nb; ++q) sacc += Linv_b[q * nb + i] * xs[boff + q];
+    y[boff + i] = sacc;
+  }
+}
+
 // -------------------------------------------------------------------------------------------------------------
-// stage 3: block-Jacobi preconditioned CG on  [S_cc C; C^T S_bb] y = rhs, one cooperative launch per linear solve
+// stage 3: conjugate gradients on the scaled reduced system, ONE cooperative launch per linear solve and ONE grid-wide
+// barrier per iteration.  Chronopoulos-Gear recurrences (single fused reduction of (r,r) and (S~r, r)):
+//     p = r + beta p ; s = w + beta s ; x += alpha p ; r' = r - alpha s ; w' = S~ r' ; gamma' = (r',r') ; delta = (w',r')
+//     beta' = gamma'/gamma ; alpha' = gamma' / (delta - beta' gamma'/alpha)
+// A neighbour's r' is recomputed on the fly from its PREVIOUS (r, w, s) (one contiguous gather), so no barrier is needed
+// between the vector update and the sparse product; the state is ping-ponged so readers never race the owner.
 // -------------------------------------------------------------------------------------------------------------
-struct PcgArgs {
+struct CgArgs {
   int V, nb, n;            // n = V*NCL + nb
-  const int* rowptr; const int* col; const double* Sval; const double* Minv; const double* rhs;
-  // border: nav annotated views, strips C[k][NCL][nb], Sbb[nb][nb], Minv_b[nb][nb]
-  int nav; const int* ann_view; const int* ann_idx; const double* C; const double* Sbb; const double* Minv_b;
-  double *x, *r, *z, *p0, *p1, *Ap;
+  const int* rowptr; const int* col; const double* Sval;
+  int nav; const int* ann_view; const int* ann_idx; const double* C;   // scaled coupling strips [nav][NCL][nb]
+  double *st0, *st1;       // ping-pong state, 3*n doubles each
+  double *x, *p;
   double* partial;         // [2][gridDim][2]
+  unsigned int* bar;       // grid barrier counter, zeroed before the launch
   int max_iter; double tol;
-  int* out_info;           // [0] iterations, [1] status (0 ok, 1 hit cap, 2 breakdown)
-  double* out_res;         // [0] |r|/|b|
+  int* out_info;           // [0] iterations, [1] status (0 converged, 1 hit cap, 2 breakdown)
+  double* out_res;         // [0] |r~| / |b~|
 };
 
-__device__ __forceinline__ void grid_reduce2(cg::grid_group& grid, double& a, double& b, double* partial, int& phase, double (*sred)[2], double* sbc) {
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// block partial -> global slot, grid barrier, then every warp sums all slots in the same order (bitwise identical everywhere)
+__device__ __forceinline__ void grid_reduce2(double& a, double& b, double* partial, unsigned int* bar, unsigned int& epoch, double (*sred)[2]) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   a = warp_sum(a); b = warp_sum(b);
   if (lane == 0) { sred[wid][0] = a; sred[wid][1] = b; }
   __syncthreads();
-  double* buf = partial + (size_t)(phase & 1) * gridDim.x * 2;
+  double* buf = partial + (size_t)(epoch & 1) * gridDim.x * 2;
   if (threadIdx.x == 0) {
     double s0 = 0, s1 = 0;
     for (int w = 0; w < nwarp; ++w) { s0 += sred[w][0]; s1 += sred[w][1]; }
-    buf[2 * blockIdx.x] = s0; buf[2 * blockIdx.x + 1] = s1;
+    __stcg(buf + 2 * blockIdx.x, s0); __stcg(buf + 2 * blockIdx.x + 1, s1);
     __threadfence();
-  }
-  grid.sync();
-  if (wid == 0) {
-    double s0 = 0, s1 = 0;
-    for (int i = lane; i < (int)gridDim.x; i += 32) { s0 += __ldcg(buf + 2 * i); s1 += __ldcg(buf + 2 * i + 1); }
-    // fixed-order tree: identical on every CTA
-    s0 = warp_sum(s0); s1 = warp_sum(s1);
-    if (lane == 0) { sbc[0] = s0; sbc[1] = s1; }
+    atomicAdd(bar, 1u);
+    const unsigned int target = (epoch + 1u) * gridDim.x;
+    while (ld_acquire_u32(bar) < target) { }
   }
   __syncthreads();
-  a = sbc[0]; b = sbc[1];
-  ++phase;
-  __syncthreads();
+  double s0 = 0, s1 = 0;
+  for (int i = lane; i < (int)gridDim.x; i += 32) { s0 += __ldcg(buf + 2 * i); s1 += __ldcg(buf + 2 * i + 1); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+  a = s0; b = s1;
+  ++epoch;
 }
 
 template <int NCL>
-__global__ void __launch_bounds__(256) k_pcg(PcgArgs A) {
-  cg::grid_group grid = cg::this_grid();
+__global__ void __launch_bounds__(256) k_cg(CgArgs A) {
   constexpr int SLOTS = 32 / NCL;
   __shared__ double sred[8][2];
-  __shared__ double sbc[2];
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int gw = blockIdx.x * wpb + (threadIdx.x >> 5), nw = gridDim.x * wpb;
   const int la = lane % NCL, ls = lane / NCL;
   const bool lact = lane < SLOTS * NCL;
   const int V = A.V, nb = A.nb, nrows = V + (nb > 0 ? 1 : 0), boff = V * NCL;
-  int phase = 0;
-  // ---- init
-  double s0 = 0, s1 = 0;
-  for (int row = gw; row < nrows; row += nw) {
-    if (row < V) {
-      if (lane < NCL) {
-        const double* Mi = A.Minv + (size_t)row * NCL * NCL + lane * NCL;
-        double zz = 0;
-#pragma unroll
-        for (int j = 0; j < NCL; ++j) zz += Mi[j] * A.rhs[row * NCL + j];
-        const double rr = A.rhs[row * NCL + lane];
-        const int i = row * NCL + lane;
-        A.x[i] = 0; A.r[i] = rr; A.z[i] = zz; A.p0[i] = 0; A.p1[i] = 0;
-        s0 += rr * zz; s1 += rr * rr;
-      }
-    } else if (lane < nb) {
-      double zz = 0;
-      for (int j = 0; j < nb; ++j) zz += A.Minv_b[lane * nb + j] * A.rhs[boff + j];
-      const double rr = A.rhs[boff + lane];
-      const int i = boff + lane;
-      A.x[i] = 0; A.r[i] = rr; A.z[i] = zz; A.p0[i] = 0; A.p1[i] = 0;
-      s0 += rr * zz; s1 += rr * rr;
-    }
-  }
-  grid_reduce2(grid, s0, s1, A.partial, phase, sred, sbc);
-  double rz = s0;
-  const double bb = s1;
+  unsigned int epoch = 0;
+  double alpha = 0.0, beta = 0.0, gamma_old = 0.0, gamma0 = 0.0, gamma_last = 0.0;
+  double* so = A.st0;  // previous state (read by everyone)
+  double* sn = A.st1;  // next state (written by the owner only)
   int it = 0, status = 1;
-  double rr_last = bb;
-  if (!(bb > 0)) { status = 0; }
-  else {
-    double beta = 0.0;
-    double* pold = A.p0;
-    double* pnew = A.p1;
-    for (it = 0; it < A.max_iter;) {
-      // ---- phase A: p_new = z + beta p_old (recomputed on the fly for neighbours), Ap = S p_new
-      double pAp = 0, dummy = 0;
-      for (int row = gw; row < nrows; row += nw) {
-        if (row < V) {
-          double sum = 0;
-          if (lact) {
-            for (int k = A.rowptr[row] + ls; k < A.rowptr[row + 1]; k += SLOTS) {
-              const int c = __ldg(A.col + k);
-              const double* B = A.Sval + (size_t)k * NCL * NCL + la * NCL;
+  for (;; ++it) {
+    double g = 0, d = 0;
+    for (int row = gw; row < nrows; row += nw) {
+      if (row < V) {
+        double rn = 0;
+        if (lane < NCL) {
+          const int i = row * NCL + lane;
+          const double ro = __ldcg(so + (row * 3 + 0) * NCL + lane), wo = __ldcg(so + (row * 3 + 1) * NCL + lane), s_o = __ldcg(so + (row * 3 + 2) * NCL + lane);
+          const double pn = ro + beta * A.p[i];
+          const double s_n = wo + beta * s_o;
+          A.p[i] = pn;
+          A.x[i] += alpha * pn;
+          rn = ro - alpha * s_n;
+          sn[(row * 3 + 0) * NCL + lane] = rn;
+          sn[(row * 3 + 2) * NCL + lane] = s_n;
+        }
+        double sum = 0;
+        if (lact) {
+#pragma unroll 2
+          for (int k = A.rowptr[row] + ls; k < A.rowptr[row + 1]; k += SLOTS) {
+            const int c = __ldg(A.col + k);
+            const double* B = A.Sval + (size_t)k * NCL * NCL + la * NCL;
+            const double* q = so + (size_t)c * 3 * NCL;
 #pragma unroll
-              for (int j = 0; j < NCL; ++j) {
-                const double pj = __ldcg(A.z + c * NCL + j) + beta * __ldcg(pold + c * NCL + j);
-                sum += __ldg(B + j) * pj;
-              }
+            for (int j = 0; j < NCL; ++j) {
+              const double rj = __ldcg(q + j) - alpha * (__ldcg(q + NCL + j) + beta * __ldcg(q + 2 * NCL + j));
+              sum += __ldg(B + j) * rj;
             }
           }
-          double tot = sum;
+        }
+        double tot = sum;
 #pragma unroll
-          for (int s = 1; s < SLOTS; ++s) tot += __shfl_down_sync(0xffffffffu, sum, s * NCL);
-          if (lane < NCL) {
-            if (nb > 0) {
-              const int k = A.ann_idx[row];
-              if (k >= 0) {
-                const double* strip = A.C + ((size_t)k * NCL + lane) * nb;
-                for (int j = 0; j < nb; ++j) tot += strip[j] * (__ldcg(A.z + boff + j) + beta * __ldcg(pold + boff + j));
-              }
+        for (int sft = 1; sft < SLOTS; ++sft) tot += __shfl_down_sync(0xffffffffu, sum, sft * NCL);
+        if (lane < NCL) {
+          if (nb > 0) {
+            const int k = A.ann_idx[row];
+            if (k >= 0) {
+              const double* strip = A.C + ((size_t)k * NCL + lane) * nb;
+              const double* q = so + 3 * (size_t)boff;
+              for (int j = 0; j < nb; ++j) tot += strip[j] * (__ldcg(q + j) - alpha * (__ldcg(q + nb + j) + beta * __ldcg(q + 2 * nb + j)));
             }
-            const int i = row * NCL + lane;
-            const double pn = __ldcg(A.z + i) + beta * __ldcg(pold + i);
-            pnew[i] = pn; A.Ap[i] = tot;
-            pAp += pn * tot;
           }
-        } else if (lane < nb) {
-          double tot = 0;
-          for (int k = 0; k < A.nav; ++k) {
-            const int c = A.ann_view[k];
-            for (int a = 0; a < NCL; ++a)
-              tot += A.C[((size_t)k * NCL + a) * nb + lane] * (__ldcg(A.z + c * NCL + a) + beta * __ldcg(pold + c * NCL + a));
-          }
-          for (int j = 0; j < nb; ++j) tot += A.Sbb[lane * nb + j] * (__ldcg(A.z + boff + j) + beta * __ldcg(pold + boff + j));
-          const int i = boff + lane;
-          const double pn = __ldcg(A.z + i) + beta * __ldcg(pold + i);
-          pnew[i] = pn; A.Ap[i] = tot;
-          pAp += pn * tot;
+          sn[(row * 3 + 1) * NCL + lane] = tot;
+          g += rn * rn; d += tot * rn;
         }
-      }
-      grid_reduce2(grid, pAp, dummy, A.partial, phase, sred, sbc);
-      if (!(pAp > 0) || !isfinite(pAp)) { status = 2; break; }
-      const double alpha = rz / pAp;
-      // ---- phase B: x += alpha p, r -= alpha Ap, z = Minv r
-      double rz_new = 0, rr = 0;
-      for (int row = gw; row < nrows; row += nw) {
-        if (row < V) {
-          double rv = 0;
-          const int i = row * NCL + (lane < NCL ? lane : 0);
-          if (lane < NCL) {
-            A.x[i] += alpha * pnew[i];
-            rv = A.r[i] - alpha * A.Ap[i];
-            A.r[i] = rv;
-          }
-          double zz = 0;
-#pragma unroll
-          for (int j = 0; j < NCL; ++j) {
-            const double rj = __shfl_sync(0xffffffffu, rv, j);
-            if (lane < NCL) zz += A.Minv[(size_t)row * NCL * NCL + lane * NCL + j] * rj;
-          }
-          if (lane < NCL) { A.z[i] = zz; rz_new += rv * zz; rr += rv * rv; }
-        } else {
-          double rv = 0;
-          const int i = boff + (lane < nb ? lane : 0);
-          if (lane < nb) {
-            A.x[i] += alpha * pnew[i];
-            rv = A.r[i] - alpha * A.Ap[i];
-            A.r[i] = rv;
-          }
-          double zz = 0;
-          for (int j = 0; j < nb; ++j) {
-            const double rj = __shfl_sync(0xffffffffu, rv, j);
-            if (lane < nb) zz += A.Minv_b[lane * nb + j] * rj;
-          }
-          if (lane < nb) { A.z[i] = zz; rz_new += rv * zz; rr += rv * rv; }
+      } else if (lane < nb) {
+        const int i = boff + lane;
+        const double* q = so + 3 * (size_t)boff;
+        const double ro = __ldcg(q + lane), wo = __ldcg(q + nb + lane), s_o = __ldcg(q + 2 * nb + lane);
+        const double pn = ro + beta * A.p[i];
+        const double s_n = wo + beta * s_o;
+        A.p[i] = pn;
+        A.x[i] += alpha * pn;
+        const double rn = ro - alpha * s_n;
+        double* qn = sn + 3 * (size_t)boff;
+        qn[lane] = rn; qn[2 * nb + lane] = s_n;
+        double tot = rn;  // unit diagonal block
+        for (int k = 0; k < A.nav; ++k) {
+          const double* qc = so + (size_t)A.ann_view[k] * 3 * NCL;
+          for (int a = 0; a < NCL; ++a)
+            tot += A.C[((size_t)k * NCL + a) * nb + lane] * (__ldcg(qc + a) - alpha * (__ldcg(qc + NCL + a) + beta * __ldcg(qc + 2 * NCL + a)));
         }
+        qn[nb + lane] = tot;
+        g += rn * rn; d += tot * rn;
       }
-      grid_reduce2(grid, rz_new, rr, A.partial, phase, sred, sbc);
-      ++it;
-      rr_last = rr;
-      if (sqrt(rr) <= A.tol * sqrt(bb)) { status = 0; break; }
-      if (!isfinite(rr)) { status = 2; break; }
-      beta = rz_new / rz;
-      rz = rz_new;
-      double* t = pold; pold = pnew; pnew = t;
     }
+    grid_reduce2(g, d, A.partial, A.bar, epoch, sred);
+    gamma_last = g;
+    if (it == 0) {
+      gamma0 = g;
+      if (!(g > 0)) { status = 0; break; }          // zero right-hand side: x = 0
+      if (!(d > 0) || !isfinite(d)) { status = 2; break; }
+      beta = 0.0; alpha = g / d;
+    } else {
+      if (sqrt(g) <= A.tol * sqrt(gamma0)) { status = 0; break; }
+      if (!isfinite(g) || !isfinite(d)) { status = 2; break; }
+      if (it >= A.max_iter) { status = 1; break; }
+      beta = g / gamma_old;
+      const double den = d - beta * g / alpha;
+      if (!(den > 0)) { status = 2; break; }
+      alpha = g / den;
+    }
+    gamma_old = g;
+    double* t = so; so = sn; sn = t;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     A.out_info[0] = it; A.out_info[1] = status;
-    A.out_res[0] = bb > 0 ? sqrt(rr_last / bb) : 0.0;
+    A.out_res[0] = gamma0 > 0 ? sqrt(gamma_last / gamma0) : 0.0;
   }
 }
 
@@ -677,14 +755,17 @@ struct ScalarJobs {
   const double* max_ptr[4]; int max_n[4]; int max_slot[4]; int nmax;
 };
 __global__ void __launch_bounds__(256) k_scalars(ScalarJobs J, double* __restrict__ out) {
+  // one CTA per job (grid = nsum + nmax), fixed-order tree inside the CTA
   __shared__ double sred[8];
-  for (int j = 0; j < J.nsum; ++j) {
+  const int job = blockIdx.x;
+  if (job < J.nsum) {
+    const int j = job;
     double s[1] = {0};
     for (int i = threadIdx.x; i < J.sum_n[j]; i += blockDim.x) s[0] += J.sum_ptr[j][(size_t)i * J.sum_stride[j]];
     block_sum<1>(s, sred);
     if (threadIdx.x == 0) out[J.sum_slot[j]] = s[0];
-  }
-  for (int j = 0; j < J.nmax; ++j) {
+  } else if (job < J.nsum + J.nmax) {
+    const int j = job - J.nsum;
     double m = 0;
     for (int i = threadIdx.x; i < J.max_n[j]; i += blockDim.x) m = fmax(m, J.max_ptr[j][i]);
     m = warp_max(m);
@@ -695,7 +776,6 @@ __global__ void __launch_bounds__(256) k_scalars(ScalarJobs J, double* __restric
       for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mm = fmax(mm, sred[w]);
       out[J.max_slot[j]] = mm;
     }
-    __syncthreads();
   }
 }
 

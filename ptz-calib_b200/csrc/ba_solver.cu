@@ -138,11 +138,12 @@ struct BaSolver : BaSolverBase {
   int cur = 0;
   // device: work
   DevBuf<ViewTab> d_vt;
-  DevBuf<double> d_scale_cam, d_scale_b, d_rec, d_part, d_viewred, d_Vh, d_gmax_part, d_diag_ray, d_diag_cam, d_diag_b, d_Lt, d_What, d_q, d_sys, d_Minv,
-      d_Minv_b, d_Sbb, d_pcgvec, d_pcg_partial, d_pcg_res, d_part3_ray, d_part3_cam, d_part3_b, d_cost_part, d_scalars, d_RiKi, d_pts_scratch, d_pts_raw,
+  DevBuf<double> d_scale_cam, d_scale_b, d_rec, d_part, d_viewred, d_Vh, d_gmax_part, d_diag_ray, d_diag_cam, d_diag_b, d_Lt, d_What, d_q, d_sys, d_Linv,
+      d_Linv_b, d_Sbb, d_Cs, d_cgstate, d_cgxp, d_y, d_pcg_partial, d_pcg_res, d_part3_ray, d_part3_cam, d_part3_b, d_cost_part, d_scalars, d_RiKi, d_pts_scratch, d_pts_raw,
       d_pts_xyz, d_disp;
   DevBuf<float2> d_pts_uv;
-  DevBuf<int> d_pts_view, d_ann_view, d_ann_off, d_ann_idx, d_fail, d_pcg_info;
+  DevBuf<int> d_pts_view, d_ann_view, d_ann_off, d_ann_idx, d_fail, d_pcg_info, d_blk_row;
+  DevBuf<unsigned int> d_bar;
   // views into d_viewred (all-reduced once per Jacobian evaluation): U | g | cost_view | C | Hbb | gb | cost_pts(2)
   double *p_U, *p_g, *p_cost_view, *p_C, *p_Hbb, *p_gb, *p_cost_pts, *p_gabs, *p_gabs_b;
   DevBuf<double> d_gabs;
@@ -243,6 +244,11 @@ struct BaSolver : BaSolverBase {
     d_toff.upload(st.t_off, s); d_tobs.upload(st.t_obs, s);
     d_pair_off.upload(st.ub_pair_off, s); d_pair_a.upload(st.pair_a, s); d_pair_b.upload(st.pair_b, s);
     d_rowptr.upload(st.s_rowptr, s); d_col.upload(st.s_col, s); d_diag_pos.upload(st.diag_pos, s);
+    {
+      std::vector<int> blk_row(st.nnzb());
+      for (int v = 0; v < V; ++v) for (int k = st.s_rowptr[v]; k < st.s_rowptr[v + 1]; ++k) blk_row[k] = v;
+      d_blk_row.upload(blk_row, s);
+    }
     d_ub_pos.upload(st.ub_pos, s); d_ub_pos_t.upload(st.ub_pos_t, s);
     d_view_active.upload(h_view_active, s);
     // parameters
@@ -309,8 +315,12 @@ struct BaSolver : BaSolverBase {
     sys_n = (size_t)st.nnzb() * NCL * NCL + n;
     d_sys.alloc(sys_n);
     p_Sval = d_sys.p; p_rhs = p_Sval + (size_t)st.nnzb() * NCL * NCL;
-    d_Minv.alloc((size_t)V * NCL * NCL); d_Minv_b.alloc(kMaxBorder * kMaxBorder); d_Sbb.alloc(kMaxBorder * kMaxBorder);
-    d_pcgvec.alloc(6 * (size_t)n); d_pcgvec.zero(s);
+    d_Linv.alloc((size_t)V * NCL * NCL); d_Linv_b.alloc(kMaxBorder * kMaxBorder); d_Sbb.alloc(kMaxBorder * kMaxBorder);
+    d_Cs.alloc((size_t)std::max(nav, 1) * NCL * std::max(nb, 1));
+    d_cgstate.alloc(6 * (size_t)n); d_cgstate.zero(s);
+    d_cgxp.alloc(2 * (size_t)n); d_cgxp.zero(s);
+    d_y.alloc(n); d_y.zero(s);
+    d_bar.alloc(1);
     d_pcg_partial.alloc(2 * 2 * (size_t)num_sms * 2);
     d_pcg_res.alloc(2); d_pcg_info.alloc(2); d_fail.alloc(1); d_fail.zero(s);
     d_part3_ray.alloc(3 * (size_t)nblk_ray); d_part3_ray.zero(s);
@@ -335,7 +345,7 @@ struct BaSolver : BaSolverBase {
     radius = opt.initial_trust_region_radius; decrease_factor = 2.0; reuse_diagonal = false; last_successful = true;
     termination = PTZ_NO_CONVERGENCE;
     log.clear();
-    clk.reset();
+    // kernel timings keep accumulating across resets (bench.py times several solves); see ptzba_get_stage_times
   }
 
   // ---- stage 1 at the current point.  scale arrays must be valid (all ones on the very first pass).
@@ -391,7 +401,7 @@ struct BaSolver : BaSolverBase {
     add_max(p_gabs, V * NCL, S_GMAX_CAM);
     add_max(d_gmax_part.p, P > 0 ? nblk_ray : 0, S_GMAX_RAY);
     add_max(p_gabs_b, nb, S_GMAX_B);
-    PTZ_TIMED(PTZ_K_SCALARS, k_scalars<<<1, 256, 0, stream>>>(J, d_scalars.p));
+    PTZ_TIMED(PTZ_K_SCALARS, k_scalars<<<J.nsum + J.nmax, 256, 0, stream>>>(J, d_scalars.p));
     PTZ_CUDA(cudaGetLastError());
     allreduce_max(d_scalars.p + S_GMAX_RAY, S_MAX_END - S_GMAX_RAY, stream);
     read_scalars();
@@ -424,23 +434,33 @@ struct BaSolver : BaSolverBase {
     if (nb > 0) k_border_system<<<1, 128, 0, s>>>(nb, p_Hbb, p_gb, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_b.p, d_Sbb.p, p_rhs + (size_t)V * NCL);
     PTZ_CUDA(cudaGetLastError());
     if (g_nccl.world > 1) PTZ_TIMED(PTZ_K_ALLREDUCE, allreduce_sum(d_sys.p, sys_n, s));
-    PTZ_TIMED(PTZ_K_PRECOND, k_precond<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, d_diag_pos.p, p_Sval, d_Minv.p, d_fail.p));
-    if (nb > 0) k_precond_border<<<1, 32, 0, s>>>(nb, d_Sbb.p, d_Minv_b.p, d_fail.p);
+    PTZ_TIMED(PTZ_K_PRECOND, {
+      k_precond<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, d_diag_pos.p, p_Sval, d_Linv.p, d_fail.p);
+      if (nb > 0) k_precond_border<<<1, 32, 0, s>>>(nb, d_Sbb.p, d_Linv_b.p, d_fail.p);
+      k_scale_system<NCL><<<cdiv(std::max(st.nnzb(), V), 128), 128, 0, s>>>(V, st.nnzb(), d_blk_row.p, d_col.p, d_Linv.p, p_Sval, p_rhs, d_cgstate.p,
+                                                                            d_cgxp.p, d_cgxp.p + n);
+      if (nb > 0)
+        k_scale_border<NCL><<<1, 128, 0, s>>>(V, nb, nav, d_ann_view.p, d_Linv.p, d_Linv_b.p, p_C, d_Cs.p, p_rhs, d_cgstate.p, d_cgxp.p, d_cgxp.p + n);
+    });
     // ---- stage 3
-    PcgArgs a;
+    CgArgs a;
     a.V = V; a.nb = nb; a.n = n;
-    a.rowptr = d_rowptr.p; a.col = d_col.p; a.Sval = p_Sval; a.Minv = d_Minv.p; a.rhs = p_rhs;
-    a.nav = nav; a.ann_view = d_ann_view.p; a.ann_idx = d_ann_idx.p; a.C = p_C; a.Sbb = d_Sbb.p; a.Minv_b = d_Minv_b.p;
-    a.x = d_pcgvec.p; a.r = a.x + n; a.z = a.r + n; a.p0 = a.z + n; a.p1 = a.p0 + n; a.Ap = a.p1 + n;
-    a.partial = d_pcg_partial.p; a.max_iter = opt.pcg_max_iterations; a.tol = opt.pcg_rel_tolerance;
+    a.rowptr = d_rowptr.p; a.col = d_col.p; a.Sval = p_Sval;
+    a.nav = nav; a.ann_view = d_ann_view.p; a.ann_idx = d_ann_idx.p; a.C = d_Cs.p;
+    a.st0 = d_cgstate.p; a.st1 = d_cgstate.p + 3 * (size_t)n; a.x = d_cgxp.p; a.p = d_cgxp.p + n;
+    a.partial = d_pcg_partial.p; a.bar = d_bar.p; a.max_iter = opt.pcg_max_iterations; a.tol = opt.pcg_rel_tolerance;
     a.out_info = d_pcg_info.p; a.out_res = d_pcg_res.p;
     const int nrows = V + (nb > 0 ? 1 : 0);
     int grid = std::min(num_sms, cdiv(nrows, 8));
     void* args[] = {&a};
-    PTZ_TIMED(PTZ_K_PCG, PTZ_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<NCL>, dim3(grid), dim3(256), args, 0, s)));
+    PTZ_TIMED(PTZ_K_PCG, {
+      PTZ_CUDA(cudaMemsetAsync(d_bar.p, 0, sizeof(unsigned int), s));
+      PTZ_CUDA(cudaLaunchCooperativeKernel((void*)k_cg<NCL>, dim3(grid), dim3(256), args, 0, s));
+      k_unscale<NCL><<<cdiv(V + nb, 128), 128, 0, s>>>(V, nb, d_Linv.p, d_Linv_b.p, d_cgxp.p, d_y.p);
+    });
     // ---- stage 4
     const int nxt = cur ^ 1;
-    const double* y = d_pcgvec.p;
+    const double* y = d_y.p;
     if (P > 0)
       PTZ_TIMED(PTZ_K_TRACK_BACKSUB, k_track_backsub<NCL><<<nblk_ray, 128, 0, s>>>(P, d_toff.p, d_tobs.p, d_oview.p, d_What.p, y, d_Lt.p, d_Vh.p, d_diag_ray.p,
                                                                                    mu, d_trk[cur].p, d_trk[nxt].p, d_part3_ray.p));
@@ -484,7 +504,7 @@ struct BaSolver : BaSolverBase {
     add_sum(d_part3_b.p, 1, 3, S_DM_B);
     add_sum(d_part3_b.p + 1, 1, 3, S_STEP2_B);
     add_sum(d_part3_b.p + 2, 1, 3, S_XN2_B);
-    PTZ_TIMED(PTZ_K_SCALARS, k_scalars<<<1, 256, 0, stream>>>(J, d_scalars.p));
+    PTZ_TIMED(PTZ_K_SCALARS, k_scalars<<<J.nsum + J.nmax, 256, 0, stream>>>(J, d_scalars.p));
     PTZ_CUDA(cudaGetLastError());
     allreduce_sum(d_scalars.p, S_SUM_END, stream);
   }
@@ -633,7 +653,7 @@ struct BaSolver : BaSolverBase {
     ScalarJobs J;
     J.nsum = 1; J.nmax = 0;
     J.sum_ptr[0] = d_cost_part.p + 1; J.sum_n[0] = st.nchunks(); J.sum_stride[0] = 2; J.sum_slot[0] = S_RAW2_CAND;
-    k_scalars<<<1, 256, 0, stream>>>(J, d_scalars.p);
+    k_scalars<<<J.nsum + J.nmax, 256, 0, stream>>>(J, d_scalars.p);
     allreduce_sum(d_scalars.p + S_RAW2_CAND, 1, stream);
     read_scalars();
     const double n2 = (double)(out->num_residuals / 2 - A);

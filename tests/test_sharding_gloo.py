@@ -1,0 +1,66 @@
+"""The N>1 path on the CPU: two processes over gloo.  Each rank takes its shard of the tracks (BAProblem.shard_tracks,
+the partition bench.py and the library use), evaluates its part of the camera normal equations with the oracle and
+all-reduces it — the same exchange the CUDA path performs with NCCL.  The sum must equal the
+unsharded evaluation; reloc shards must tile the batch."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    from ptz_calib_b200 import synth
+
+    full = synth.make_config(1, scale=0.3)
+    full = full.with_params(ray=orc.ba_init_rays(full))
+    shard = full.shard_tracks(rank, world)
+    e = orc.ba_eval(shard)
+    ncv = full.ncv
+    # camera part of the gradient and the cost are additive over shards; rays are owned by one rank
+    cam = torch.from_numpy(np.concatenate([e.gradient[: full.V * ncv], [e.cost, float(shard.M), float(shard.P)]]))
+    dist.all_reduce(cam)
+    counts = np.bincount(full.obs_track, minlength=full.P)
+    cum = np.cumsum(counts)
+    lo = int(np.searchsorted(cum, cum[-1] * rank / world, side="left")) if rank > 0 else 0
+    ref = orc.ba_eval(full)
+    ok = np.abs(cam[: full.V * ncv].numpy() - ref.gradient[: full.V * ncv]).max() <= 1e-9 * np.abs(ref.gradient).max()
+    ok = ok and abs(cam[-3].item() - ref.cost) <= 1e-12 * ref.cost and int(cam[-2].item()) == full.M and int(cam[-1].item()) == full.P
+    ray_g = e.gradient[full.V * ncv :].reshape(-1, 3)
+    ok = ok and np.abs(ray_g - ref.gradient[full.V * ncv :].reshape(-1, 3)[lo : lo + shard.P]).max() <= 1e-9 * np.abs(ref.gradient).max()
+    # reloc batch: contiguous shards balanced by matches, no exchange
+    b = synth.make_reloc_batch(200, n_min=8, n_max=64)
+    mine = b.shard(rank, world)
+    sizes = torch.tensor([mine.B, mine.N], dtype=torch.int64)
+    dist.all_reduce(sizes)
+    ok = ok and sizes[0].item() == b.B and sizes[1].item() == b.N and abs(mine.N - b.N / world) <= 64
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out.put(int(flag.item()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_matches_unsharded():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) == 1

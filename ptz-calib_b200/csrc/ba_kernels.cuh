@@ -494,6 +494,7 @@ struct CgArgs {
   double *x, *p;
   double* partial;         // [2][gridDim][2]
   unsigned int* bar;       // grid barrier counter, zeroed before the launch
+  int smem_blocks;         // blocks of S (and their column indices) each warp keeps in shared memory for the whole solve
   int max_iter; double tol;
   int* out_info;           // [0] iterations, [1] status (0 converged, 1 hit cap, 2 breakdown)
   double* out_res;         // [0] |r~| / |b~|
@@ -514,7 +515,7 @@ __device__ __forceinline__ void grid_reduce2(double& a, double& b, double* parti
   if (threadIdx.x == 0) {
     double s0 = 0, s1 = 0;
     for (int w = 0; w < nwarp; ++w) { s0 += sred[w][0]; s1 += sred[w][1]; }
-    __stcg(buf + 2 * blockIdx.x, s0); __stcg(buf + 2 * blockIdx.x + 1, s1);
+    __stcg(reinterpret_cast<double2*>(buf) + blockIdx.x, make_double2(s0, s1));
     __threadfence();
     atomicAdd(bar, 1u);
     const unsigned int target = (epoch + 1u) * gridDim.x;
@@ -522,7 +523,7 @@ __device__ __forceinline__ void grid_reduce2(double& a, double& b, double* parti
   }
   __syncthreads();
   double s0 = 0, s1 = 0;
-  for (int i = lane; i < (int)gridDim.x; i += 32) { s0 += __ldcg(buf + 2 * i); s1 += __ldcg(buf + 2 * i + 1); }
+  for (int i = lane; i < (int)gridDim.x; i += 32) { const double2 v = __ldcg(reinterpret_cast<const double2*>(buf) + i); s0 += v.x; s1 += v.y; }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
   a = s0; b = s1;
@@ -531,13 +532,26 @@ __device__ __forceinline__ void grid_reduce2(double& a, double& b, double* parti
 
 template <int NCL>
 __global__ void __launch_bounds__(256) k_cg(CgArgs A) {
-  constexpr int SLOTS = 32 / NCL;
+  constexpr int SLOTS = 32 / NCL, NB = NCL * NCL;
+  extern __shared__ double cg_smem[];
   __shared__ double sred[8][2];
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  const int gw = blockIdx.x * wpb + (threadIdx.x >> 5), nw = gridDim.x * wpb;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;
+  const int gw = blockIdx.x * wpb + wid, nw = gridDim.x * wpb;
   const int la = lane % NCL, ls = lane / NCL;
   const bool lact = lane < SLOTS * NCL;
   const int V = A.V, nb = A.nb, nrows = V + (nb > 0 ? 1 : 0), boff = V * NCL;
+  // ---- the rows of a warp are the same in every iteration: keep (a prefix of) their S blocks and column indices on chip
+  const int cap = A.smem_blocks;
+  double* Bs = cg_smem + (size_t)wid * cap * NB;
+  int* cs = reinterpret_cast<int*>(cg_smem + (size_t)wpb * cap * NB) + (size_t)wid * cap;
+  int ncached = 0;
+  for (int row = gw; row < V && ncached < cap; row += nw) {
+    const int b0 = A.rowptr[row], take = min(A.rowptr[row + 1] - b0, cap - ncached);
+    for (int e = lane; e < take * NB; e += 32) Bs[(size_t)ncached * NB + e] = A.Sval[(size_t)b0 * NB + e];
+    for (int e = lane; e < take; e += 32) cs[ncached + e] = A.col[b0 + e];
+    ncached += take;
+  }
+  __syncwarp();
   unsigned int epoch = 0;
   double alpha = 0.0, beta = 0.0, gamma_old = 0.0, gamma0 = 0.0, gamma_last = 0.0;
   double* so = A.st0;  // previous state (read by everyone)
@@ -545,6 +559,7 @@ __global__ void __launch_bounds__(256) k_cg(CgArgs A) {
   int it = 0, status = 1;
   for (;; ++it) {
     double g = 0, d = 0;
+    int bi = 0;  // running index of this warp's blocks
     for (int row = gw; row < nrows; row += nw) {
       if (row < V) {
         double rn = 0;
@@ -559,20 +574,40 @@ __global__ void __launch_bounds__(256) k_cg(CgArgs A) {
           sn[(row * 3 + 0) * NCL + lane] = rn;
           sn[(row * 3 + 2) * NCL + lane] = s_n;
         }
+        const int b0 = A.rowptr[row], nblk = A.rowptr[row + 1] - b0;
         double sum = 0;
-        if (lact) {
-#pragma unroll 2
-          for (int k = A.rowptr[row] + ls; k < A.rowptr[row + 1]; k += SLOTS) {
-            const int c = __ldg(A.col + k);
-            const double* B = A.Sval + (size_t)k * NCL * NCL + la * NCL;
-            const double* q = so + (size_t)c * 3 * NCL;
+        {
+          // every lane of a slot fetches ONE entry of the neighbour's (r, w, s) -- 3 loads, each 32-byte sector requested once --
+          // forms its entry of r' and the NCL lanes exchange by shuffle; lanes beyond SLOTS*NCL idle along (uniform trip count)
+          const int nsteps = (nblk + SLOTS - 1) / SLOTS;
+          const int base = ls * NCL;
+#pragma unroll 4
+          for (int t = 0; t < nsteps; ++t) {
+            const int k = t * SLOTS + ls;
+            const bool on = lact && k < nblk;
+            const int idx = bi + k;
+            const bool hit = on && idx < ncached;
+            double mine = 0.0;
+            if (on) {
+              const int c = hit ? cs[idx] : __ldg(A.col + b0 + k);
+              const double* q = so + (size_t)c * 3 * NCL + la;
+              mine = __ldcg(q) - alpha * (__ldcg(q + NCL) + beta * __ldcg(q + 2 * NCL));
+            }
+            double rj[NCL];
 #pragma unroll
-            for (int j = 0; j < NCL; ++j) {
-              const double rj = __ldcg(q + j) - alpha * (__ldcg(q + NCL + j) + beta * __ldcg(q + 2 * NCL + j));
-              sum += __ldg(B + j) * rj;
+            for (int j = 0; j < NCL; ++j) rj[j] = __shfl_sync(0xffffffffu, mine, (base + j) & 31);
+            if (hit) {
+              const double* B = Bs + (size_t)idx * NB + la * NCL;
+#pragma unroll
+              for (int j = 0; j < NCL; ++j) sum += B[j] * rj[j];
+            } else if (on) {
+              const double* B = A.Sval + (size_t)(b0 + k) * NB + la * NCL;
+#pragma unroll
+              for (int j = 0; j < NCL; ++j) sum += __ldg(B + j) * rj[j];
             }
           }
         }
+        bi += nblk;
         double tot = sum;
 #pragma unroll
         for (int sft = 1; sft < SLOTS; ++sft) tot += __shfl_down_sync(0xffffffffu, sum, sft * NCL);

@@ -153,7 +153,7 @@ struct BaSolver : BaSolverBase {
   size_t sys_n = 0;
   double* h_scalars = nullptr;  // pinned
   int* h_info = nullptr;        // pinned: pcg info(2), fail(1)
-  int nblk_ray = 0, nblk_cam = 0;
+  int nblk_ray = 0, nblk_cam = 0, cg_cap = 1;
 
   // LM state (names follow ceres::internal::TrustRegionMinimizer / LevenbergMarquardtStrategy)
   double radius = 0, decrease_factor = 2.0, x_cost = 0, x_norm = 0, min_cost = 0, initial_cost = 0, grad_max = 0;
@@ -193,6 +193,21 @@ struct BaSolver : BaSolverBase {
     }
     if (g_nccl.world > 1 && A > 0) throw CudaError(PTZ_ERR_UNSUPPORTED, "2d-3d terms with a sharded problem");
     n = V * NCL + nb;
+    {
+      // blocks of S a warp of the CG kernel owns (rows gw, gw+nw, ...), and how many of them fit 200 KB of shared memory
+      const int nrows = V + (nb > 0 ? 1 : 0), grid = std::min(num_sms, cdiv(nrows, 8)), nw = grid * 8;
+      int worst = 0;
+      for (int w = 0; w < nw; ++w) {
+        int c = 0;
+        for (int r = w; r < V; r += nw) c += st.s_rowptr[r + 1] - st.s_rowptr[r];
+        worst = std::max(worst, c);
+      }
+      const size_t per_block = NCL * NCL * sizeof(double) + sizeof(int);
+      const int fit = (int)((200 * 1024) / (8 * per_block));
+      cg_cap = std::max(1, std::min(worst, fit));
+      const size_t cg_smem = (size_t)8 * cg_cap * per_block + 16;
+      PTZ_CUDA(cudaFuncSetAttribute((const void*)k_cg<NCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg_smem));
+    }
     upload(prob);
     PTZ_CUDA(cudaStreamSynchronize(stream));
     seconds_setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -452,10 +467,13 @@ struct BaSolver : BaSolverBase {
     a.out_info = d_pcg_info.p; a.out_res = d_pcg_res.p;
     const int nrows = V + (nb > 0 ? 1 : 0);
     int grid = std::min(num_sms, cdiv(nrows, 8));
+    // shared-memory residency of S: every warp keeps up to cg_cap blocks (+ column indices) of its rows for the whole solve
+    a.smem_blocks = cg_cap;
+    const size_t cg_smem = (size_t)8 * cg_cap * (NCL * NCL * sizeof(double) + sizeof(int)) + 16;
     void* args[] = {&a};
     PTZ_TIMED(PTZ_K_PCG, {
       PTZ_CUDA(cudaMemsetAsync(d_bar.p, 0, sizeof(unsigned int), s));
-      PTZ_CUDA(cudaLaunchCooperativeKernel((void*)k_cg<NCL>, dim3(grid), dim3(256), args, 0, s));
+      PTZ_CUDA(cudaLaunchCooperativeKernel((void*)k_cg<NCL>, dim3(grid), dim3(256), args, cg_smem, s));
       k_unscale<NCL><<<cdiv(V + nb, 128), 128, 0, s>>>(V, nb, d_Linv.p, d_Linv_b.p, d_cgxp.p, d_y.p);
     });
     // ---- stage 4

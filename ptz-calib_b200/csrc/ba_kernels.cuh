@@ -31,6 +31,11 @@ struct Dims {
 // per-track parameter record: ray(3), sqrt(weight), Jacobi scale(3), pad
 constexpr int kTrk = 8;
 
+// position of 16-byte chunk p of thread t's record inside its shared-memory slot.  Records of 8 chunks (NCL=4) would put
+// chunk p of every thread in the same bank group: rotate by the thread index.  9- and 10-chunk records spread by themselves.
+template <int NCL>
+__device__ __forceinline__ int rec_swz(int t, int p) { return NCL == 4 ? (p ^ (t & 7)) : p; }
+
 // -------------------------------------------------------------------------------------------------------------
 // stage 1
 // -------------------------------------------------------------------------------------------------------------
@@ -57,6 +62,7 @@ __global__ void __launch_bounds__(kChunk) k_resjac(const int* __restrict__ chunk
   __shared__ ViewTab svt;
   __shared__ double ssc[NCL];
   __shared__ double sred[D::NPART * (kChunk / 32)];
+  __shared__ double2 srec[kChunk * (D::RS / 2)];
   const int chunk = blockIdx.x;
   const int view = chunk_view[chunk], begin = chunk_begin[chunk], cnt = chunk_cnt[chunk];
   if (threadIdx.x < 48) reinterpret_cast<double*>(&svt)[threadIdx.x] = reinterpret_cast<const double*>(vt + view)[threadIdx.x];
@@ -83,12 +89,14 @@ __global__ void __launch_bounds__(kChunk) k_resjac(const int* __restrict__ chunk
     for (int j = 0; j < 3; ++j) { E[j] *= sr[j]; E[3 + j] *= sr[j]; }
 #pragma unroll
     for (int a = 0; a < NCL; ++a) { const double s = ssc[a] * sw; F[a] *= s; F[NCL + a] *= s; }
-    double* out = rec + (size_t)o * D::RS;
-    double2* o2 = reinterpret_cast<double2*>(out);
-    o2[0] = make_double2(r[0], r[1]);
-    o2[1] = make_double2(E[0], E[1]); o2[2] = make_double2(E[2], E[3]); o2[3] = make_double2(E[4], E[5]);
+    // record -> shared memory in 16-byte chunks; XOR swizzle so that neither these stores nor the coalesced read-out conflict
+    double2 rc[D::RS / 2];
+    rc[0] = make_double2(r[0], r[1]);
+    rc[1] = make_double2(E[0], E[1]); rc[2] = make_double2(E[2], E[3]); rc[3] = make_double2(E[4], E[5]);
 #pragma unroll
-    for (int a = 0; a < NCL; ++a) o2[4 + a] = make_double2(F[2 * a], F[2 * a + 1]);  // F stored flat [2*NCL]
+    for (int a = 0; a < NCL; ++a) rc[4 + a] = make_double2(F[2 * a], F[2 * a + 1]);  // F stored flat [2*NCL]
+#pragma unroll
+    for (int pch = 0; pch < D::RS / 2; ++pch) srec[threadIdx.x * (D::RS / 2) + rec_swz<NCL>(threadIdx.x, pch)] = rc[pch];
     int k = 0;
 #pragma unroll
     for (int a = 0; a < NCL; ++a)
@@ -98,10 +106,17 @@ __global__ void __launch_bounds__(kChunk) k_resjac(const int* __restrict__ chunk
     for (int a = 0; a < NCL; ++a) acc[D::NU + a] = F[a] * r[0] + F[NCL + a] * r[1];
     acc[D::NU + NCL] = 0.5 * (r[0] * r[0] + r[1] * r[1]);
   }
-  block_sum<D::NPART>(acc, sred);
+  block_sum<D::NPART>(acc, sred);  // (its barriers also publish srec)
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < D::NPART; ++i) part[(size_t)chunk * D::NPART + i] = acc[i];
+  }
+  // the chunk's records are contiguous in global memory: write them out as consecutive 16-byte chunks
+  double2* gout = reinterpret_cast<double2*>(rec + (size_t)begin * D::RS);
+  const int nch = cnt * (D::RS / 2);
+  for (int gch = threadIdx.x; gch < nch; gch += kChunk) {
+    const int t = gch / (D::RS / 2), pch = gch % (D::RS / 2);
+    gout[gch] = srec[t * (D::RS / 2) + rec_swz<NCL>(t, pch)];
   }
 }
 
@@ -181,12 +196,9 @@ __global__ void k_make_scales(int V, int P, const double* __restrict__ U, const 
 // -------------------------------------------------------------------------------------------------------------
 // stage 2
 // -------------------------------------------------------------------------------------------------------------
-// per track: damp, factor (V + D^2) = L L^T, t = L^-1 h; per observation What = (F^T E) L^-T and q = What t.
-template <int NCL>
-__global__ void k_track_solve(int P, const int* __restrict__ t_off, const int* __restrict__ t_obs, const double* __restrict__ rec,
-                              const double* __restrict__ Vh, double mu, int refresh_diag, double min_diag, double max_diag, double* __restrict__ diag_ray,
-                              double* __restrict__ Lt, double* __restrict__ What, double* __restrict__ q, int* __restrict__ fail) {
-  typedef Dims<NCL> D;
+// per track: damp and factor (V + D^2) = L L^T, t = L^-1 h
+__global__ void k_track_factor(int P, const int* __restrict__ t_off, const double* __restrict__ Vh, double mu, int refresh_diag, double min_diag,
+                               double max_diag, double* __restrict__ diag_ray, double* __restrict__ Lt, int* __restrict__ fail) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   const double* vh = Vh + (size_t)p * 10;
@@ -198,45 +210,50 @@ __global__ void k_track_solve(int P, const int* __restrict__ t_off, const int* _
     d0 = diag_ray[3 * (size_t)p]; d1 = diag_ray[3 * (size_t)p + 1]; d2 = diag_ray[3 * (size_t)p + 2];
   }
   const double A6[6] = {vh[0] + d0 / mu, vh[1], vh[2] + d1 / mu, vh[3], vh[4], vh[5] + d2 / mu};
-  double L[6];
+  double L[6] = {1, 0, 1, 0, 0, 1};
   double* lt = Lt + (size_t)p * 10;
-  if (t_off[p] == t_off[p + 1]) {  // track without observations: not in the problem
-    for (int i = 0; i < 10; ++i) lt[i] = 0;
-    lt[0] = lt[2] = lt[5] = 1.0;
-    return;
-  }
-  if (!chol3(A6, L)) {
+  const bool empty = t_off[p] == t_off[p + 1];  // track without observations: not in the problem
+  if (!empty && !chol3(A6, L)) {
     atomicExch(fail, 1);
-    for (int i = 0; i < 10; ++i) lt[i] = 0;
-    lt[0] = lt[2] = lt[5] = 1.0;
     L[0] = L[2] = L[5] = 1.0; L[1] = L[3] = L[4] = 0.0;
   }
-  const double i00 = 1.0 / L[0], i11 = 1.0 / L[2], i22 = 1.0 / L[5];
-  const double t0 = vh[6] * i00, t1 = (vh[7] - L[1] * t0) * i11, t2 = (vh[8] - L[3] * t0 - L[4] * t1) * i22;
-  lt[0] = L[0]; lt[1] = L[1]; lt[2] = L[2]; lt[3] = L[3]; lt[4] = L[4]; lt[5] = L[5]; lt[6] = t0; lt[7] = t1; lt[8] = t2; lt[9] = 0;
-  for (int i = t_off[p]; i < t_off[p + 1]; ++i) {
-    const int o = t_obs[i];
-    const double2* rp = reinterpret_cast<const double2*>(rec + (size_t)o * D::RS);
-    const double2 e01 = rp[1], e23 = rp[2], e45 = rp[3];
-    const double a0 = e01.x, a1 = e01.y, a2 = e23.x, b0 = e23.y, b1 = e45.x, b2 = e45.y;
-    double w[D::WS];
-    double qa[NCL];
-    const double* Fp = rec + (size_t)o * D::RS + 8;
+  const double t0 = vh[6] / L[0], t1 = (vh[7] - L[1] * t0) / L[2], t2 = (vh[8] - L[3] * t0 - L[4] * t1) / L[5];
+  lt[0] = L[0]; lt[1] = L[1]; lt[2] = L[2]; lt[3] = L[3]; lt[4] = L[4]; lt[5] = L[5];
+  lt[6] = empty ? 0.0 : t0; lt[7] = empty ? 0.0 : t1; lt[8] = empty ? 0.0 : t2; lt[9] = 0;
+}
+// per observation (one thread each, in view-major order so that records stream): What = (F^T E) L^-T, q = What t
+template <int NCL>
+__global__ void __launch_bounds__(256) k_obs_what(int M, const int* __restrict__ o_track, const double* __restrict__ rec, const double* __restrict__ Lt,
+                                                   double* __restrict__ What, double* __restrict__ q) {
+  typedef Dims<NCL> D;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= M) return;
+  const int p = o_track[o];
+  const double2* lp = reinterpret_cast<const double2*>(Lt + (size_t)p * 10);
+  const double2 l01 = lp[0], l23 = lp[1], l45 = lp[2], l67 = lp[3], l89 = lp[4];
+  const double L0 = l01.x, L1 = l01.y, L2 = l23.x, L3 = l23.y, L4 = l45.x, L5 = l45.y, t0 = l67.x, t1 = l67.y, t2 = l89.x;
+  const double i00 = 1.0 / L0, i11 = 1.0 / L2, i22 = 1.0 / L5;
+  const double2* rp = reinterpret_cast<const double2*>(rec + (size_t)o * D::RS);
+  const double2 e01 = rp[1], e23 = rp[2], e45 = rp[3];
+  const double a0 = e01.x, a1 = e01.y, a2 = e23.x, b0 = e23.y, b1 = e45.x, b2 = e45.y;
+  double Fv[2 * NCL];
 #pragma unroll
-    for (int a = 0; a < NCL; ++a) {
-      const double f0 = Fp[a], f1 = Fp[NCL + a];
-      const double w0 = f0 * a0 + f1 * b0, w1 = f0 * a1 + f1 * b1, w2 = f0 * a2 + f1 * b2;  // row a of F^T E
-      const double x0 = w0 * i00, x1 = (w1 - L[1] * x0) * i11, x2 = (w2 - L[3] * x0 - L[4] * x1) * i22;
-      w[3 * a] = x0; w[3 * a + 1] = x1; w[3 * a + 2] = x2;
-      qa[a] = x0 * t0 + x1 * t1 + x2 * t2;
-    }
-    if (D::WS > 3 * NCL) w[D::WS - 1] = 0.0;
-    double2* wo = reinterpret_cast<double2*>(What + (size_t)o * D::WS);
+  for (int a = 0; a < NCL; ++a) { const double2 f = rp[4 + a]; Fv[2 * a] = f.x; Fv[2 * a + 1] = f.y; }
+  double w[D::WS], qa[NCL];
 #pragma unroll
-    for (int k = 0; k < D::WS / 2; ++k) wo[k] = make_double2(w[2 * k], w[2 * k + 1]);
-#pragma unroll
-    for (int a = 0; a < NCL; ++a) q[(size_t)o * NCL + a] = qa[a];
+  for (int a = 0; a < NCL; ++a) {
+    const double f0 = Fv[a], f1 = Fv[NCL + a];
+    const double w0 = f0 * a0 + f1 * b0, w1 = f0 * a1 + f1 * b1, w2 = f0 * a2 + f1 * b2;  // row a of F^T E
+    const double x0 = w0 * i00, x1 = (w1 - L1 * x0) * i11, x2 = (w2 - L3 * x0 - L4 * x1) * i22;
+    w[3 * a] = x0; w[3 * a + 1] = x1; w[3 * a + 2] = x2;
+    qa[a] = x0 * t0 + x1 * t1 + x2 * t2;
   }
+  if (D::WS > 3 * NCL) w[D::WS - 1] = 0.0;
+  double2* wo = reinterpret_cast<double2*>(What + (size_t)o * D::WS);
+#pragma unroll
+  for (int k = 0; k < D::WS / 2; ++k) wo[k] = make_double2(w[2 * k], w[2 * k + 1]);
+#pragma unroll
+  for (int a = 0; a < NCL; ++a) q[(size_t)o * NCL + a] = qa[a];
 }
 
 // per view (one CTA): S_cc = [U + D^2] - sum_o What What^T, rhs_c = [g] - sum_o q_o.  The bracketed terms are added by
@@ -812,6 +829,35 @@ __global__ void __launch_bounds__(256) k_scalars(ScalarJobs J, double* __restric
       out[J.max_slot[j]] = mm;
     }
   }
+}
+
+// |x|^2 of the current point over the coordinates that are in the Ceres problem: partial sums per CTA
+__global__ void k_xnorm2(int V, int P, const int* __restrict__ view_active, const double* __restrict__ intr, const double* __restrict__ ext,
+                         const int* __restrict__ t_off, const double* __restrict__ trk, double* __restrict__ part2) {
+  __shared__ double sred[2 * 8];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[2] = {0, 0};
+  if (i < V && view_active[i]) {
+    for (int j = 0; j < 9; ++j) acc[0] += intr[9 * i + j] * intr[9 * i + j];
+    for (int j = 0; j < 6; ++j) acc[0] += ext[6 * i + j] * ext[6 * i + j];
+  }
+  if (i < P && t_off[i + 1] > t_off[i]) {
+    const double* t = trk + (size_t)i * kTrk;
+    acc[1] = t[0] * t[0] + t[1] * t[1] + t[2] * t[2];
+  }
+  block_sum<2>(acc, sred);
+  if (threadIdx.x == 0) { part2[2 * blockIdx.x] = acc[0]; part2[2 * blockIdx.x + 1] = acc[1]; }
+}
+// rays in the world frame (ptzray_optimizer.cc:748-754): R_lw^T (ray - t_lw), compact [P][3]
+__global__ void k_rays_out(int P, const double* __restrict__ trk, const double* __restrict__ tlw, double* __restrict__ ray, double* __restrict__ ray_w) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  double w[3] = {tlw[0], tlw[1], tlw[2]}, R[9];
+  rodrigues_jac(w, R, nullptr);
+  const double* t = trk + (size_t)p * kTrk;
+  const double r0 = t[0], r1 = t[1], r2 = t[2];
+  ray[3 * (size_t)p] = r0; ray[3 * (size_t)p + 1] = r1; ray[3 * (size_t)p + 2] = r2;
+  for (int j = 0; j < 3; ++j) ray_w[3 * (size_t)p + j] = R[j] * (r0 - tlw[3]) + R[3 + j] * (r1 - tlw[4]) + R[6 + j] * (r2 - tlw[5]);
 }
 
 // initial rays (Pix2Ray, ptzray_optimizer.cc:768-797): mean over the track's views of normalise((R^-1 K^-1)[u,v,1]), normalised

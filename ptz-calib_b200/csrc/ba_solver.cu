@@ -439,8 +439,10 @@ struct BaSolver : BaSolverBase {
     const int own = (g_nccl.rank == 0) ? 1 : 0;
     PTZ_CUDA(cudaMemsetAsync(d_fail.p, 0, sizeof(int), s));
     if (P > 0)
-      PTZ_TIMED(PTZ_K_TRACK_SOLVE, k_track_solve<NCL><<<nblk_ray, 128, 0, s>>>(P, d_toff.p, d_tobs.p, d_rec.p, d_Vh.p, mu, refresh, opt.min_lm_diagonal,
-                                                                               opt.max_lm_diagonal, d_diag_ray.p, d_Lt.p, d_What.p, d_q.p, d_fail.p));
+      PTZ_TIMED(PTZ_K_TRACK_SOLVE, {
+        k_track_factor<<<nblk_ray, 128, 0, s>>>(P, d_toff.p, d_Vh.p, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_ray.p, d_Lt.p, d_fail.p);
+        k_obs_what<NCL><<<cdiv(M, 256), 256, 0, s>>>(M, d_otrack.p, d_rec.p, d_Lt.p, d_What.p, d_q.p);
+      });
     PTZ_TIMED(PTZ_K_SCHUR_DIAG, k_schur_diag<NCL><<<V, 128, 0, s>>>(d_view_off.p, d_What.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal,
                                                                     opt.max_lm_diagonal, own, d_diag_cam.p, d_diag_pos.p, p_Sval, p_rhs));
     if (st.nub() > 0)
@@ -529,30 +531,23 @@ struct BaSolver : BaSolverBase {
 
   // |x| of the current point over the coordinates that are in the Ceres problem
   double current_x_norm() {
-    // candidate := current (y = 0 is not available before the first solve): sum squares directly on the host-visible copies
-    std::vector<double> intr(9 * (size_t)V), ext(6 * (size_t)V), trk((size_t)std::max(P, 1) * kTrk), tlw(6);
-    d_intr[cur].download(intr.data(), intr.size(), stream);
-    d_ext[cur].download(ext.data(), ext.size(), stream);
-    d_trk[cur].download(trk.data(), trk.size(), stream);
-    d_tlw[cur].download(tlw.data(), 6, stream);
-    PTZ_CUDA(cudaStreamSynchronize(stream));
-    double s = 0, sr = 0;
-    for (int v = 0; v < V; ++v)
-      if (h_view_active[v]) {
-        for (int j = 0; j < 9; ++j) s += intr[9 * (size_t)v + j] * intr[9 * (size_t)v + j];
-        for (int j = 0; j < 6; ++j) s += ext[6 * (size_t)v + j] * ext[6 * (size_t)v + j];
-      }
-    for (int p = 0; p < P; ++p)
-      if (st.t_off[p + 1] > st.t_off[p]) for (int j = 0; j < 3; ++j) sr += trk[(size_t)p * kTrk + j] * trk[(size_t)p * kTrk + j];
-    if (g_nccl.world > 1) {
-      DevBuf<double> d;
-      d.upload(&sr, 1, stream);
-      allreduce_sum(d.p, 1, stream);
-      d.download(&sr, 1, stream);
-      PTZ_CUDA(cudaStreamSynchronize(stream));
-    }
-    if (A > 0) for (int j = 0; j < 6; ++j) s += tlw[j] * tlw[j];
-    return sqrt(s + sr);
+    const int nblk = std::max(cdiv(std::max(V, P), 256), 1);
+    DevBuf<double> part;
+    part.alloc(2 * (size_t)nblk);
+    k_xnorm2<<<nblk, 256, 0, stream>>>(V, P, d_view_active.p, d_intr[cur].p, d_ext[cur].p, d_toff.p, d_trk[cur].p, part.p);
+    ScalarJobs J;
+    J.nsum = 2; J.nmax = 0;
+    J.sum_ptr[0] = part.p; J.sum_n[0] = nblk; J.sum_stride[0] = 2; J.sum_slot[0] = S_XN2_CAM;
+    J.sum_ptr[1] = part.p + 1; J.sum_n[1] = nblk; J.sum_stride[1] = 2; J.sum_slot[1] = S_XN2_RAY;
+    k_scalars<<<2, 256, 0, stream>>>(J, d_scalars.p);
+    PTZ_CUDA(cudaGetLastError());
+    allreduce_sum(d_scalars.p + S_XN2_RAY, 1, stream);
+    double tl[6] = {0, 0, 0, 0, 0, 0};
+    if (A > 0) d_tlw[cur].download(tl, 6, stream);
+    read_scalars();
+    double s = h_scalars[S_XN2_CAM] + h_scalars[S_XN2_RAY];
+    if (A > 0) for (int j = 0; j < 6; ++j) s += tl[j] * tl[j];
+    return sqrt(s);
   }
 
   void push_log(double cost, double cost_change, double step_norm, double rho, int lin, int ok) {
@@ -678,15 +673,22 @@ struct BaSolver : BaSolverBase {
     out->final_reproj_error_2d2d = sqrt(h_scalars[S_RAW2_CAND] / n2);
     out->final_reproj_error_2d3d = A > 0 ? sqrt(h_scalars[S_RAWPTS_CAND] / A) : sqrt(0.0 / 0.0);
     // parameters
-    std::vector<double> intr(9 * (size_t)V), ext(6 * (size_t)V), trk((size_t)std::max(P, 1) * kTrk), tlw(6, 0.0);
+    std::vector<double> intr(9 * (size_t)V), ext(6 * (size_t)V), tlw(6, 0.0);
     d_intr[cur].download(intr.data(), intr.size(), stream);
     d_ext[cur].download(ext.data(), ext.size(), stream);
-    d_trk[cur].download(trk.data(), trk.size(), stream);
     d_tlw[cur].download(tlw.data(), 6, stream);
+    if ((out->ray || out->rays_world) && P > 0) {
+      // compact rays (local and world frame) on the device, straight into the caller's buffers
+      DevBuf<double> d_ray, d_rayw;
+      d_ray.alloc(3 * (size_t)P); d_rayw.alloc(3 * (size_t)P);
+      k_rays_out<<<cdiv(P, 256), 256, 0, stream>>>(P, d_trk[cur].p, d_tlw[cur].p, d_ray.p, d_rayw.p);
+      if (out->ray) d_ray.download(out->ray, 3 * (size_t)P, stream);
+      if (out->rays_world) d_rayw.download(out->rays_world, 3 * (size_t)P, stream);
+      PTZ_CUDA(cudaStreamSynchronize(stream));
+    }
     PTZ_CUDA(cudaStreamSynchronize(stream));
     if (out->intr) memcpy(out->intr, intr.data(), intr.size() * 8);
     if (out->ext) memcpy(out->ext, ext.data(), ext.size() * 8);
-    if (out->ray) for (int p = 0; p < P; ++p) for (int j = 0; j < 3; ++j) out->ray[3 * (size_t)p + j] = trk[(size_t)p * kTrk + j];
     if (out->disp) out->disp[0] = out->disp[1] = out->disp[2] = 0.0;
     if (out->tlw) memcpy(out->tlw, tlw.data(), 48);
     // ObtainRefinedCameraParams (ptzray_optimizer.cc:672-766)
@@ -705,12 +707,6 @@ struct BaSolver : BaSolverBase {
           for (int q = 0; q < 3; ++q) c[4 + 3 * r + q] = R[3 * r] * Rlw[q] + R[3 * r + 1] * Rlw[3 + q] + R[3 * r + 2] * Rlw[6 + q];
         }
         for (int j = 0; j < 5; ++j) c[16 + j] = in[4 + j];
-      }
-    if (out->rays_world)
-      for (int p = 0; p < P; ++p) {
-        const double* r = &trk[(size_t)p * kTrk];
-        for (int j = 0; j < 3; ++j)
-          out->rays_world[3 * (size_t)p + j] = Rlw[j] * (r[0] - tlw[3]) + Rlw[3 + j] * (r[1] - tlw[4]) + Rlw[6 + j] * (r[2] - tlw[5]);
       }
     out->log_count = 0;
     if (out->log)

@@ -14,6 +14,7 @@
 
 #include "ba_border.cuh"
 #include "ba_kernels.cuh"
+#include "ba_setup.cuh"
 #include "ba_structure.hpp"
 
 namespace ptz {
@@ -117,7 +118,8 @@ struct BaSolver : BaSolverBase {
 
   int V, P, M, A, nb = 0, nav = 0, n = 0;
   ptz_solver_options opt;
-  BaStructure st;
+  DevStructure ds;       // orderings + block pattern, device-resident
+  std::vector<int> h_perm;  // view-major position -> caller's observation index (fetched lazily, ptzba_eval only)
   cudaStream_t stream = nullptr;
   int num_sms = 148;
   StageClock clk;
@@ -128,11 +130,7 @@ struct BaSolver : BaSolverBase {
   bool have_ray0 = false;
   std::vector<int> h_view_active, h_ann_view, h_ann_off, h_ann_idx, h_pt_perm;
 
-  // device: structure
-  DevBuf<float2> d_uv;
-  DevBuf<int> d_otrack, d_oview, d_chunk_view, d_chunk_begin, d_chunk_cnt, d_view_chunk_off, d_view_off, d_toff, d_tobs;
-  DevBuf<int64_t> d_pair_off;
-  DevBuf<int> d_pair_a, d_pair_b, d_rowptr, d_col, d_diag_pos, d_ub_pos, d_ub_pos_t, d_view_active;
+  // device: structure lives in `ds`; short aliases are set in upload()
   // device: parameters (two copies: current / candidate)
   DevBuf<double> d_intr[2], d_ext[2], d_trk[2], d_tlw[2], d_intr_init, d_ext_init, d_trk_init, d_tlw_init;
   int cur = 0;
@@ -142,7 +140,7 @@ struct BaSolver : BaSolverBase {
       d_Linv_b, d_Sbb, d_Cs, d_cgstate, d_cgxp, d_y, d_pcg_partial, d_pcg_res, d_part3_ray, d_part3_cam, d_part3_b, d_cost_part, d_scalars, d_RiKi, d_pts_scratch, d_pts_raw,
       d_pts_xyz, d_disp;
   DevBuf<float2> d_pts_uv;
-  DevBuf<int> d_pts_view, d_ann_view, d_ann_off, d_ann_idx, d_fail, d_pcg_info, d_blk_row;
+  DevBuf<int> d_pts_view, d_ann_view, d_ann_off, d_ann_idx, d_fail, d_pcg_info;
   DevBuf<unsigned int> d_bar;
   // views into d_viewred (all-reduced once per Jacobian evaluation): U | g | cost_view | C | Hbb | gb | cost_pts(2)
   double *p_U, *p_g, *p_cost_view, *p_C, *p_Hbb, *p_gb, *p_cost_pts, *p_gabs, *p_gabs_b;
@@ -171,11 +169,27 @@ struct BaSolver : BaSolverBase {
     PTZ_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     PTZ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     clk.init(stream);
-    build_structure(V, P, M, prob->obs_uv, prob->obs_view, prob->obs_track, kChunk, st, nullptr);
-    if (g_nccl.world > 1) unify_pattern(prob);
+    if (opt.verbose & 4) {
+      // reference path: the unit-tested host builder
+      BaStructure st;
+      build_structure(V, P, M, prob->obs_uv, prob->obs_view, prob->obs_track, kChunk, st, nullptr);
+      if (g_nccl.world > 1) {
+        std::vector<int64_t> keys(st.nub());
+        for (int b = 0; b < st.nub(); ++b) keys[b] = ub_key(st.ub_row[b], st.ub_col[b]);
+        std::vector<int64_t> all = union_of_keys(keys);
+        build_structure(V, P, M, prob->obs_uv, prob->obs_view, prob->obs_track, kChunk, st, &all);
+      }
+      upload_structure(st, ds, stream);
+    } else {
+      build_structure_device_obs(V, P, M, prob->obs_uv, prob->obs_view, prob->obs_track, kChunk, ds, stream);
+      if (g_nccl.world > 1) {
+        std::vector<int64_t> all = union_of_keys(ds.local_keys_host(stream));
+        build_structure_device_blocks(ds, &all, stream);
+      } else {
+        build_structure_device_blocks(ds, nullptr, stream);
+      }
+    }
     // annotated points: sort by view, list annotated views
-    h_view_active.assign(V, 0);
-    for (int k = 0; k < M; ++k) h_view_active[prob->obs_view[k]] = 1;
     h_ann_idx.assign(V, -1);
     if (A > 0) {
       h_pt_perm.resize(A);
@@ -183,7 +197,6 @@ struct BaSolver : BaSolverBase {
       std::stable_sort(h_pt_perm.begin(), h_pt_perm.end(), [&](int a, int b) { return prob->pt_view[a] < prob->pt_view[b]; });
       for (int i = 0; i < A; ++i) {
         int v = prob->pt_view[h_pt_perm[i]];
-        h_view_active[v] = 1;
         if (h_ann_view.empty() || h_ann_view.back() != v) { h_ann_idx[v] = (int)h_ann_view.size(); h_ann_view.push_back(v); h_ann_off.push_back(i); }
       }
       h_ann_off.push_back(A);
@@ -199,7 +212,7 @@ struct BaSolver : BaSolverBase {
       int worst = 0;
       for (int w = 0; w < nw; ++w) {
         int c = 0;
-        for (int r = w; r < V; r += nw) c += st.s_rowptr[r + 1] - st.s_rowptr[r];
+        for (int r = w; r < V; r += nw) c += ds.h_rowptr[r + 1] - ds.h_rowptr[r];
         worst = std::max(worst, c);
       }
       const size_t per_block = NCL * NCL * sizeof(double) + sizeof(int);
@@ -219,25 +232,21 @@ struct BaSolver : BaSolverBase {
     if (stream) cudaStreamDestroy(stream);
   }
 
-  // every rank must hold the same block pattern of S: all-gather the local upper keys, take the union, rebuild
-  void unify_pattern(const ptzba_problem* prob) {
-    std::vector<int64_t> keys(st.nub());
-    for (int b = 0; b < st.nub(); ++b) keys[b] = ub_key(st.ub_row[b], st.ub_col[b]);
+  // every rank must hold the same block pattern of S: all-gather the local upper block keys, return their sorted union
+  std::vector<int64_t> union_of_keys(const std::vector<int64_t>& keys) {
     const int W = g_nccl.world;
-    DevBuf<int64_t> d_cnt, d_all;
+    DevBuf<int64_t> d_cnt, d_all, d_my, d_pad;
     d_cnt.alloc(W);
     int64_t my = (int64_t)keys.size();
     std::vector<int64_t> counts(W);
-    DevBuf<int64_t> d_my;
     d_my.upload(&my, 1, stream);
     PTZ_NCCL(ncclAllGather(d_my.p, d_cnt.p, 1, ncclInt64, g_nccl.comm, stream));
     d_cnt.download(counts.data(), W, stream);
     PTZ_CUDA(cudaStreamSynchronize(stream));
     int64_t mx = *std::max_element(counts.begin(), counts.end());
-    if (mx == 0) return;
+    if (mx == 0) return std::vector<int64_t>();
     std::vector<int64_t> padded(mx, -1);
     std::copy(keys.begin(), keys.end(), padded.begin());
-    DevBuf<int64_t> d_pad;
     d_pad.upload(padded, stream);
     d_all.alloc((size_t)mx * W);
     PTZ_NCCL(ncclAllGather(d_pad.p, d_all.p, mx, ncclInt64, g_nccl.comm, stream));
@@ -247,25 +256,18 @@ struct BaSolver : BaSolverBase {
     all.erase(std::remove(all.begin(), all.end(), (int64_t)-1), all.end());
     std::sort(all.begin(), all.end());
     all.erase(std::unique(all.begin(), all.end()), all.end());
-    build_structure(V, P, M, prob->obs_uv, prob->obs_view, prob->obs_track, kChunk, st, &all);
+    return all;
   }
 
   void upload(const ptzba_problem* prob) {
     cudaStream_t s = stream;
-    d_uv.upload(reinterpret_cast<const float2*>(st.o_uv.data()), M, s);
-    d_otrack.upload(st.o_track, s); d_oview.upload(st.o_view, s);
-    d_chunk_view.upload(st.chunk_view, s); d_chunk_begin.upload(st.chunk_begin, s); d_chunk_cnt.upload(st.chunk_cnt, s);
-    d_view_chunk_off.upload(st.view_chunk_off, s); d_view_off.upload(st.view_off, s);
-    d_toff.upload(st.t_off, s); d_tobs.upload(st.t_obs, s);
-    d_pair_off.upload(st.ub_pair_off, s); d_pair_a.upload(st.pair_a, s); d_pair_b.upload(st.pair_b, s);
-    d_rowptr.upload(st.s_rowptr, s); d_col.upload(st.s_col, s); d_diag_pos.upload(st.diag_pos, s);
-    {
-      std::vector<int> blk_row(st.nnzb());
-      for (int v = 0; v < V; ++v) for (int k = st.s_rowptr[v]; k < st.s_rowptr[v + 1]; ++k) blk_row[k] = v;
-      d_blk_row.upload(blk_row, s);
+    if (A > 0) {  // views that carry only annotated points are active too
+      std::vector<int> act(V);
+      ds.view_active.download(act.data(), V, s);
+      PTZ_CUDA(cudaStreamSynchronize(s));
+      for (int v : h_ann_view) act[v] = 1;
+      ds.view_active.upload(act, s);
     }
-    d_ub_pos.upload(st.ub_pos, s); d_ub_pos_t.upload(st.ub_pos_t, s);
-    d_view_active.upload(h_view_active, s);
     // parameters
     h_intr0.assign(prob->intr, prob->intr + 9 * (size_t)V);
     h_ext0.assign(prob->ext, prob->ext + 6 * (size_t)V);
@@ -287,7 +289,7 @@ struct BaSolver : BaSolverBase {
     d_RiKi.alloc(9 * (size_t)V);
     if (!have_ray0 && P > 0) {  // Pix2Ray on the device, into the initial track records
       k_rikI<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr_init.p, d_ext_init.p, d_RiKi.p);
-      k_init_rays<<<cdiv(P, 128), 128, 0, s>>>(P, d_toff.p, d_tobs.p, d_oview.p, d_uv.p, d_RiKi.p, d_trk_init.p);
+      k_init_rays<<<cdiv(P, 128), 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, ds.o_view.p, ds.o_uv.p, d_RiKi.p, d_trk_init.p);
       PTZ_CUDA(cudaGetLastError());
     }
     // annotated points
@@ -311,7 +313,7 @@ struct BaSolver : BaSolverBase {
     // work buffers
     d_scale_cam.alloc((size_t)V * NCL); d_scale_b.alloc(kMaxBorder);
     d_rec.alloc((size_t)std::max(M, 1) * D::RS);
-    d_part.alloc((size_t)std::max(st.nchunks(), 1) * D::NPART);
+    d_part.alloc((size_t)std::max(ds.nchunks, 1) * D::NPART);
     viewred_n = (size_t)V * NCL * NCL + (size_t)V * NCL + V + (size_t)nav * NCL * nb + (size_t)nb * nb + nb + 2;
     d_viewred.alloc(viewred_n);
     d_viewred.zero(s);
@@ -327,9 +329,9 @@ struct BaSolver : BaSolverBase {
     d_Lt.alloc((size_t)std::max(P, 1) * 10);
     d_What.alloc((size_t)std::max(M, 1) * D::WS); d_What.zero(s);
     d_q.alloc((size_t)std::max(M, 1) * NCL);
-    sys_n = (size_t)st.nnzb() * NCL * NCL + n;
+    sys_n = (size_t)ds.nnzb * NCL * NCL + n;
     d_sys.alloc(sys_n);
-    p_Sval = d_sys.p; p_rhs = p_Sval + (size_t)st.nnzb() * NCL * NCL;
+    p_Sval = d_sys.p; p_rhs = p_Sval + (size_t)ds.nnzb * NCL * NCL;
     d_Linv.alloc((size_t)V * NCL * NCL); d_Linv_b.alloc(kMaxBorder * kMaxBorder); d_Sbb.alloc(kMaxBorder * kMaxBorder);
     d_Cs.alloc((size_t)std::max(nav, 1) * NCL * std::max(nb, 1));
     d_cgstate.alloc(6 * (size_t)n); d_cgstate.zero(s);
@@ -340,7 +342,7 @@ struct BaSolver : BaSolverBase {
     d_pcg_res.alloc(2); d_pcg_info.alloc(2); d_fail.alloc(1); d_fail.zero(s);
     d_part3_ray.alloc(3 * (size_t)nblk_ray); d_part3_ray.zero(s);
     d_part3_cam.alloc(3 * (size_t)nblk_cam); d_part3_b.alloc(3); d_part3_b.zero(s);
-    d_cost_part.alloc(2 * (size_t)std::max(st.nchunks(), 1)); d_cost_part.zero(s);
+    d_cost_part.alloc(2 * (size_t)std::max(ds.nchunks, 1)); d_cost_part.zero(s);
     d_scalars.alloc(S_COUNT); d_scalars.zero(s);
     d_disp.alloc(3); d_disp.zero(s);
     PTZ_CUDA(cudaMallocHost((void**)&h_scalars, S_COUNT * sizeof(double)));
@@ -367,13 +369,13 @@ struct BaSolver : BaSolverBase {
   void launch_resjac(int weighted) {
     cudaStream_t s = stream;
     PTZ_TIMED(PTZ_K_VIEW_PREP, k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[cur].p, d_ext[cur].p, d_vt.p, 1));
-    if (st.nchunks() > 0)
-      PTZ_TIMED(PTZ_K_RESJAC, k_resjac<TYPE><<<st.nchunks(), kChunk, 0, s>>>(d_chunk_view.p, d_chunk_begin.p, d_chunk_cnt.p, d_uv.p, d_otrack.p, d_vt.p,
+    if (ds.nchunks > 0)
+      PTZ_TIMED(PTZ_K_RESJAC, k_resjac<TYPE><<<ds.nchunks, kChunk, 0, s>>>(ds.chunk_view.p, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_uv.p, ds.o_track.p, d_vt.p,
                                                                              d_trk[cur].p, d_scale_cam.p, d_disp.p, weighted, d_rec.p, d_part.p));
     PTZ_TIMED(PTZ_K_VIEW_FINALIZE,
-              k_view_finalize<NCL><<<cdiv(V * D::NPART, 256), 256, 0, s>>>(V, d_view_chunk_off.p, d_part.p, d_scale_cam.p, p_U, p_g, p_cost_view, p_gabs));
+              k_view_finalize<NCL><<<cdiv(V * D::NPART, 256), 256, 0, s>>>(V, ds.view_chunk_off.p, d_part.p, d_scale_cam.p, p_U, p_g, p_cost_view, p_gabs));
     if (P > 0)
-      PTZ_TIMED(PTZ_K_TRACK_ACCUM, k_track_accum<<<nblk_ray, 128, 0, s>>>(P, D::RS, d_toff.p, d_tobs.p, d_rec.p, d_trk[cur].p, d_Vh.p, d_gmax_part.p));
+      PTZ_TIMED(PTZ_K_TRACK_ACCUM, k_track_accum<<<nblk_ray, 128, 0, s>>>(P, D::RS, ds.t_off.p, ds.t_obs.p, d_rec.p, d_trk[cur].p, d_Vh.p, d_gmax_part.p));
     if (A > 0) {
       PtsArgs a;
       a.A = A; a.nav = nav; a.nb = nb; a.fy_in_border = kFyBorder ? 1 : 0;
@@ -440,21 +442,21 @@ struct BaSolver : BaSolverBase {
     PTZ_CUDA(cudaMemsetAsync(d_fail.p, 0, sizeof(int), s));
     if (P > 0)
       PTZ_TIMED(PTZ_K_TRACK_SOLVE, {
-        k_track_factor<<<nblk_ray, 128, 0, s>>>(P, d_toff.p, d_Vh.p, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_ray.p, d_Lt.p, d_fail.p);
-        k_obs_what<NCL><<<cdiv(M, 256), 256, 0, s>>>(M, d_otrack.p, d_rec.p, d_Lt.p, d_What.p, d_q.p);
+        k_track_factor<<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, d_Vh.p, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_ray.p, d_Lt.p, d_fail.p);
+        k_obs_what<NCL><<<cdiv(M, 256), 256, 0, s>>>(M, ds.o_track.p, d_rec.p, d_Lt.p, d_What.p, d_q.p);
       });
-    PTZ_TIMED(PTZ_K_SCHUR_DIAG, k_schur_diag<NCL><<<V, 128, 0, s>>>(d_view_off.p, d_What.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal,
-                                                                    opt.max_lm_diagonal, own, d_diag_cam.p, d_diag_pos.p, p_Sval, p_rhs));
-    if (st.nub() > 0)
-      PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, k_schur_offdiag<NCL><<<cdiv(st.nub(), 8), 256, 0, s>>>(st.nub(), d_pair_off.p, d_pair_a.p, d_pair_b.p, d_What.p,
-                                                                                            d_ub_pos.p, d_ub_pos_t.p, p_Sval));
+    PTZ_TIMED(PTZ_K_SCHUR_DIAG, k_schur_diag<NCL><<<V, 128, 0, s>>>(ds.view_off.p, d_What.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal,
+                                                                    opt.max_lm_diagonal, own, d_diag_cam.p, ds.diag_pos.p, p_Sval, p_rhs));
+    if (ds.nub > 0)
+      PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, k_schur_offdiag<NCL><<<cdiv(ds.nub, 8), 256, 0, s>>>(ds.nub, ds.pair_off.p, ds.pair_a.p, ds.pair_b.p, d_What.p,
+                                                                                            ds.ub_pos.p, ds.ub_pos_t.p, p_Sval));
     if (nb > 0) k_border_system<<<1, 128, 0, s>>>(nb, p_Hbb, p_gb, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_b.p, d_Sbb.p, p_rhs + (size_t)V * NCL);
     PTZ_CUDA(cudaGetLastError());
     if (g_nccl.world > 1) PTZ_TIMED(PTZ_K_ALLREDUCE, allreduce_sum(d_sys.p, sys_n, s));
     PTZ_TIMED(PTZ_K_PRECOND, {
-      k_precond<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, d_diag_pos.p, p_Sval, d_Linv.p, d_fail.p);
+      k_precond<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, ds.diag_pos.p, p_Sval, d_Linv.p, d_fail.p);
       if (nb > 0) k_precond_border<<<1, 32, 0, s>>>(nb, d_Sbb.p, d_Linv_b.p, d_fail.p);
-      k_scale_system<NCL><<<cdiv(std::max(st.nnzb(), V), 128), 128, 0, s>>>(V, st.nnzb(), d_blk_row.p, d_col.p, d_Linv.p, p_Sval, p_rhs, d_cgstate.p,
+      k_scale_system<NCL><<<cdiv(std::max(ds.nnzb, V), 128), 128, 0, s>>>(V, ds.nnzb, ds.blk_row.p, ds.s_col.p, d_Linv.p, p_Sval, p_rhs, d_cgstate.p,
                                                                             d_cgxp.p, d_cgxp.p + n);
       if (nb > 0)
         k_scale_border<NCL><<<1, 128, 0, s>>>(V, nb, nav, d_ann_view.p, d_Linv.p, d_Linv_b.p, p_C, d_Cs.p, p_rhs, d_cgstate.p, d_cgxp.p, d_cgxp.p + n);
@@ -462,7 +464,7 @@ struct BaSolver : BaSolverBase {
     // ---- stage 3
     CgArgs a;
     a.V = V; a.nb = nb; a.n = n;
-    a.rowptr = d_rowptr.p; a.col = d_col.p; a.Sval = p_Sval;
+    a.rowptr = ds.s_rowptr.p; a.col = ds.s_col.p; a.Sval = p_Sval;
     a.nav = nav; a.ann_view = d_ann_view.p; a.ann_idx = d_ann_idx.p; a.C = d_Cs.p;
     a.st0 = d_cgstate.p; a.st1 = d_cgstate.p + 3 * (size_t)n; a.x = d_cgxp.p; a.p = d_cgxp.p + n;
     a.partial = d_pcg_partial.p; a.bar = d_bar.p; a.max_iter = opt.pcg_max_iterations; a.tol = opt.pcg_rel_tolerance;
@@ -482,9 +484,9 @@ struct BaSolver : BaSolverBase {
     const int nxt = cur ^ 1;
     const double* y = d_y.p;
     if (P > 0)
-      PTZ_TIMED(PTZ_K_TRACK_BACKSUB, k_track_backsub<NCL><<<nblk_ray, 128, 0, s>>>(P, d_toff.p, d_tobs.p, d_oview.p, d_What.p, y, d_Lt.p, d_Vh.p, d_diag_ray.p,
+      PTZ_TIMED(PTZ_K_TRACK_BACKSUB, k_track_backsub<NCL><<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, ds.o_view.p, d_What.p, y, d_Lt.p, d_Vh.p, d_diag_ray.p,
                                                                                    mu, d_trk[cur].p, d_trk[nxt].p, d_part3_ray.p));
-    PTZ_TIMED(PTZ_K_CAM_UPDATE, k_cam_update<TYPE><<<nblk_cam, 128, 0, s>>>(V, y, d_scale_cam.p, p_g, d_diag_cam.p, mu, d_view_active.p, d_intr[cur].p,
+    PTZ_TIMED(PTZ_K_CAM_UPDATE, k_cam_update<TYPE><<<nblk_cam, 128, 0, s>>>(V, y, d_scale_cam.p, p_g, d_diag_cam.p, mu, ds.view_active.p, d_intr[cur].p,
                                                                             d_ext[cur].p, d_intr[nxt].p, d_ext[nxt].p, d_part3_cam.p));
     if (nb > 0)
       k_border_update<<<1, 32, 0, s>>>(nb, nav, kFyBorder ? 1 : 0, d_ann_view.p, y + (size_t)V * NCL, d_scale_b.p, p_gb, d_diag_b.p, mu, d_tlw[cur].p,
@@ -502,8 +504,8 @@ struct BaSolver : BaSolverBase {
   void launch_cost(int which) {
     cudaStream_t s = stream;
     PTZ_TIMED(PTZ_K_VIEW_PREP, k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[which].p, d_ext[which].p, d_vt.p, 0));
-    if (st.nchunks() > 0)
-      PTZ_TIMED(PTZ_K_COST, k_cost<TYPE><<<st.nchunks(), kChunk, 0, s>>>(d_chunk_view.p, d_chunk_begin.p, d_chunk_cnt.p, d_uv.p, d_otrack.p, d_vt.p,
+    if (ds.nchunks > 0)
+      PTZ_TIMED(PTZ_K_COST, k_cost<TYPE><<<ds.nchunks, kChunk, 0, s>>>(ds.chunk_view.p, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_uv.p, ds.o_track.p, d_vt.p,
                                                                          d_trk[which].p, d_disp.p, d_cost_part.p));
     if (A > 0) k_pts_cost<<<1, 32, 0, s>>>(A, d_pts_uv.p, d_pts_xyz.p, d_pts_view.p, d_vt.p, d_tlw[which].p, d_scalars.p + S_COSTPTS_CAND);
     PTZ_CUDA(cudaGetLastError());
@@ -513,8 +515,8 @@ struct BaSolver : BaSolverBase {
     ScalarJobs J;
     J.nsum = 0; J.nmax = 0;
     auto add_sum = [&](const double* p, int cnt, int stride, int slot) { J.sum_ptr[J.nsum] = p; J.sum_n[J.nsum] = cnt; J.sum_stride[J.nsum] = stride; J.sum_slot[J.nsum] = slot; ++J.nsum; };
-    add_sum(d_cost_part.p, st.nchunks(), 2, S_COST_CAND);
-    add_sum(d_cost_part.p + 1, st.nchunks(), 2, S_RAW2_CAND);
+    add_sum(d_cost_part.p, ds.nchunks, 2, S_COST_CAND);
+    add_sum(d_cost_part.p + 1, ds.nchunks, 2, S_RAW2_CAND);
     add_sum(d_part3_ray.p, P > 0 ? nblk_ray : 0, 3, S_DM_RAY);
     add_sum(d_part3_ray.p + 1, P > 0 ? nblk_ray : 0, 3, S_STEP2_RAY);
     add_sum(d_part3_ray.p + 2, P > 0 ? nblk_ray : 0, 3, S_XN2_RAY);
@@ -534,7 +536,7 @@ struct BaSolver : BaSolverBase {
     const int nblk = std::max(cdiv(std::max(V, P), 256), 1);
     DevBuf<double> part;
     part.alloc(2 * (size_t)nblk);
-    k_xnorm2<<<nblk, 256, 0, stream>>>(V, P, d_view_active.p, d_intr[cur].p, d_ext[cur].p, d_toff.p, d_trk[cur].p, part.p);
+    k_xnorm2<<<nblk, 256, 0, stream>>>(V, P, ds.view_active.p, d_intr[cur].p, d_ext[cur].p, ds.t_off.p, d_trk[cur].p, part.p);
     ScalarJobs J;
     J.nsum = 2; J.nmax = 0;
     J.sum_ptr[0] = part.p; J.sum_n[0] = nblk; J.sum_stride[0] = 2; J.sum_slot[0] = S_XN2_CAM;
@@ -665,7 +667,7 @@ struct BaSolver : BaSolverBase {
     launch_cost(cur);
     ScalarJobs J;
     J.nsum = 1; J.nmax = 0;
-    J.sum_ptr[0] = d_cost_part.p + 1; J.sum_n[0] = st.nchunks(); J.sum_stride[0] = 2; J.sum_slot[0] = S_RAW2_CAND;
+    J.sum_ptr[0] = d_cost_part.p + 1; J.sum_n[0] = ds.nchunks; J.sum_stride[0] = 2; J.sum_slot[0] = S_RAW2_CAND;
     k_scalars<<<J.nsum + J.nmax, 256, 0, stream>>>(J, d_scalars.p);
     allreduce_sum(d_scalars.p + S_RAW2_CAND, 1, stream);
     read_scalars();
@@ -735,9 +737,11 @@ struct BaSolver : BaSolverBase {
       else if (TYPE == BA_PTZRAY_FXFY_DIST) live2col[a] = a;                // fx, fy, k1, w
       else live2col[a] = a == 0 ? 0 : 1 + a;                                // fx, k1, w -> 0, 2, 3,4,5
     }
+    h_perm.resize(std::max(M, 1));
+    if (M > 0) { ds.perm.download(h_perm.data(), M, stream); PTZ_CUDA(cudaStreamSynchronize(stream)); }
     for (int i = 0; i < M; ++i) {
       const double* r = &rec[(size_t)i * D::RS];
-      const int k = st.perm[i];
+      const int k = h_perm[i];
       if (out->residuals) { out->residuals[2 * (size_t)k] = r[0]; out->residuals[2 * (size_t)k + 1] = r[1]; }
       if (out->jac_obs)
         for (int row = 0; row < 2; ++row) {

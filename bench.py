@@ -204,6 +204,13 @@ def run_ours(args):
     # ---------------- end to end through the C ABI with host buffers: complete ptzba_solve calls ----------------
     e2e = None
     if not args.no_e2e:
+        # the contract's e2e leg copies from PINNED host memory: re-home the input arrays (same values)
+        def pin(a):
+            return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+        for name in ("intr", "ext", "obs_uv", "obs_view", "obs_track", "track_weight"):
+            setattr(prob, name, pin(getattr(prob, name)))
+        ptz.ba_solve(prob, opt)  # warm the memory pool / first-call costs outside the timed region
         barrier()
         n_e2e = max(1, args.e2e_solves)
         t0 = time.perf_counter()
@@ -294,7 +301,10 @@ def bench_reloc(args, rank, world, barrier, allmax, allsum):
     ms = allmax(e0.elapsed_time(e1) / reps)
     iters = float(o_i[3].double().mean().item())
     succ = allsum(float(o_i[0].sum().item())) / B
-    # end to end (host buffers in, host results out)
+    # end to end (pinned host buffers in, host results out)
+    for name in ("match_offset", "uv_ref", "uv_cur", "ref_cam", "init_cam"):
+        setattr(b, name, torch.from_numpy(np.ascontiguousarray(getattr(b, name))).pin_memory().numpy())
+    ptz.reloc_solve_batch(b, opt)  # warm-up
     barrier()
     t0 = time.perf_counter()
     r = ptz.reloc_solve_batch(b, opt)
@@ -376,7 +386,7 @@ def main():
     ap.add_argument("--factor-type", type=int, default=0)
     ap.add_argument("--pcg-tol", type=float, default=1e-13)
     ap.add_argument("--reloc-queries", type=int, default=100000)
-    ap.add_argument("--e2e-solves", type=int, default=2)
+    ap.add_argument("--e2e-solves", type=int, default=3)
     ap.add_argument("--cpu-tracks", type=int, default=40000)
     ap.add_argument("--cpu-iters", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")

@@ -154,8 +154,9 @@ __global__ void k_fill_csr(int V, int nub, const unsigned long long* __restrict_
 
 struct CubTemp {
   DevBuf<char> buf;
+  cudaStream_t s = nullptr;
   void* get(size_t bytes) {
-    if (bytes > buf.n) buf.alloc(bytes + bytes / 4 + 256);
+    if (bytes > buf.n) buf.alloc(bytes + bytes / 4 + 256, s);
     return buf.p;
   }
 };
@@ -184,6 +185,7 @@ inline void build_structure_device_obs(int V, int P, int M, const float* h_uv, c
   using namespace setup;
   d.V = V; d.P = P; d.M = M;
   CubTemp tmp;
+  tmp.s = s;
   auto grid = [](long long n, int b) { return (unsigned)std::max<long long>((n + b - 1) / b, 1); };
   // ---- raw inputs
   DevBuf<float2> uv_in;
@@ -193,9 +195,9 @@ inline void build_structure_device_obs(int V, int P, int M, const float* h_uv, c
   uv_in.upload(reinterpret_cast<const float2*>(h_uv), M, s);
   view_in.upload(h_view, M, s);
   track_in.upload(h_track, M, s);
-  k0.alloc(Mx); k1.alloc(Mx); idx0.alloc(Mx); idx1.alloc(Mx); pos0.alloc(Mx);
-  d.o_uv.alloc(Mx); d.o_view.alloc(Mx); d.o_track.alloc(Mx); d.perm.alloc(Mx);
-  d.view_off.alloc(V + 1); d.view_chunk_off.alloc(V + 1); d.t_off.alloc(P + 1); d.t_obs.alloc(Mx); d.view_active.alloc(V);
+  k0.alloc(Mx, s); k1.alloc(Mx, s); idx0.alloc(Mx, s); idx1.alloc(Mx, s); pos0.alloc(Mx, s);
+  d.o_uv.alloc(Mx, s); d.o_view.alloc(Mx, s); d.o_track.alloc(Mx, s); d.perm.alloc(Mx, s);
+  d.view_off.alloc(V + 1, s); d.view_chunk_off.alloc(V + 1, s); d.t_off.alloc(P + 1, s); d.t_obs.alloc(Mx, s); d.view_active.alloc(V, s);
   const int tbits = bits_for(std::max(P, 2)), vbits = bits_for(std::max(V, 2));
   // ---- view-major order: sort by (view, track)
   if (M > 0) {
@@ -206,13 +208,13 @@ inline void build_structure_device_obs(int V, int P, int M, const float* h_uv, c
   k_lower_bounds_int<<<grid(V + 1, 256), 256, 0, s>>>(V, M, d.o_view.p, d.view_off.p);
   // ---- chunks
   DevBuf<int> nch;
-  nch.alloc(V + 1);
+  nch.alloc(V + 1, s);
   nch.zero(s);
   k_chunk_counts<<<grid(V, 256), 256, 0, s>>>(V, chunk, d.view_off.p, nch.p, d.view_active.p);
   exclusive_scan(tmp, nch.p, d.view_chunk_off.p, V + 1, s);
   // ---- by-track lists: stable sort of positions by track
   DevBuf<int> tk0, tk1;
-  tk0.alloc(Mx); tk1.alloc(Mx);
+  tk0.alloc(Mx, s); tk1.alloc(Mx, s);
   if (M > 0) {
     PTZ_CUDA(cudaMemcpyAsync(tk0.p, d.o_track.p, (size_t)M * 4, cudaMemcpyDeviceToDevice, s));
     sort_pairs(tmp, tk0.p, tk1.p, pos0.p, d.t_obs.p, M, 0, tbits, s);
@@ -220,7 +222,7 @@ inline void build_structure_device_obs(int V, int P, int M, const float* h_uv, c
   k_lower_bounds_int<<<grid(P + 1, 256), 256, 0, s>>>(P, M, tk1.p, d.t_off.p);
   // ---- observation pairs
   DevBuf<long long> pcnt, pbase;
-  pcnt.alloc(P + 1); pbase.alloc(P + 1);
+  pcnt.alloc(P + 1, s); pbase.alloc(P + 1, s);
   pcnt.zero(s);
   if (P > 0) k_pair_counts<<<grid(P, 256), 256, 0, s>>>(P, d.t_off.p, pcnt.p);
   exclusive_scan(tmp, pcnt.p, pbase.p, P + 1, s);
@@ -230,17 +232,17 @@ inline void build_structure_device_obs(int V, int P, int M, const float* h_uv, c
   PTZ_CUDA(cudaMemcpyAsync(&h_npairs, pbase.p + P, 8, cudaMemcpyDeviceToHost, s));
   PTZ_CUDA(cudaStreamSynchronize(s));
   d.nchunks = h_nchunks; d.npairs = h_npairs;
-  d.chunk_view.alloc(std::max(h_nchunks, 1)); d.chunk_begin.alloc(std::max(h_nchunks, 1)); d.chunk_cnt.alloc(std::max(h_nchunks, 1));
+  d.chunk_view.alloc(std::max(h_nchunks, 1), s); d.chunk_begin.alloc(std::max(h_nchunks, 1), s); d.chunk_cnt.alloc(std::max(h_nchunks, 1), s);
   k_fill_chunks<<<grid(V, 128), 128, 0, s>>>(V, chunk, d.view_off.p, d.view_chunk_off.p, d.chunk_view.p, d.chunk_begin.p, d.chunk_cnt.p);
   const long long NPx = std::max<long long>(h_npairs, 1);
   DevBuf<unsigned long long> pk0, pv0, pv1;
   DevBuf<unsigned long long>& pk1 = d.pk_sorted;
   DevBuf<unsigned long long>& uniq = d.uniq_local;
-  pk0.alloc(NPx); pk1.alloc(NPx); pv0.alloc(NPx); pv1.alloc(NPx);
-  d.pair_a.alloc(NPx); d.pair_b.alloc(NPx);
-  uniq.alloc(NPx);
+  pk0.alloc(NPx, s); pk1.alloc(NPx, s); pv0.alloc(NPx, s); pv1.alloc(NPx, s);
+  d.pair_a.alloc(NPx, s); d.pair_b.alloc(NPx, s);
+  uniq.alloc(NPx, s);
   DevBuf<int> d_nuniq;
-  d_nuniq.alloc(1);
+  d_nuniq.alloc(1, s);
   int h_nuniq = 0;
   if (h_npairs > 0) {
     k_make_pairs<<<grid(P, 128), 128, 0, s>>>(P, d.t_off.p, d.t_obs.p, d.o_view.p, pbase.p, pk0.p, pv0.p);
@@ -260,6 +262,7 @@ inline void build_structure_device_obs(int V, int P, int M, const float* h_uv, c
 inline void build_structure_device_blocks(DevStructure& d, const std::vector<int64_t>* extra_upper_keys, cudaStream_t s) {
   using namespace setup;
   CubTemp tmp;
+  tmp.s = s;
   auto grid = [](long long n, int b) { return (unsigned)std::max<long long>((n + b - 1) / b, 1); };
   const int V = d.V;
   const long long h_npairs = d.npairs;
@@ -278,14 +281,14 @@ inline void build_structure_device_blocks(DevStructure& d, const std::vector<int
     d.nub = (int)merged.size();
   } else {
     d.nub = h_nuniq;
-    d.ub_keys.alloc(std::max(h_nuniq, 1));
+    d.ub_keys.alloc(std::max(h_nuniq, 1), s);
     if (h_nuniq) PTZ_CUDA(cudaMemcpyAsync(d.ub_keys.p, uniq.p, (size_t)h_nuniq * 8, cudaMemcpyDeviceToDevice, s));
   }
   const int nub = d.nub, nubx = std::max(nub, 1);
-  d.pair_off.alloc(nub + 1);
+  d.pair_off.alloc(nub + 1, s);
   {
     DevBuf<long long> off;
-    off.alloc(nub + 1);
+    off.alloc(nub + 1, s);
     k_lower_bounds_u64<<<grid(nub + 1, 256), 256, 0, s>>>(nub, h_npairs, pk1.p, d.ub_keys.p, off.p);
     PTZ_CUDA(cudaMemcpyAsync(d.pair_off.p, off.p, (size_t)(nub + 1) * 8, cudaMemcpyDeviceToDevice, s));
     PTZ_CUDA(cudaStreamSynchronize(s));
@@ -294,9 +297,9 @@ inline void build_structure_device_blocks(DevStructure& d, const std::vector<int
   d.nnzb = V + 2 * nub;
   DevBuf<unsigned long long> c0, c1;
   DevBuf<int> ci0, ci1, first_ub, first_lb, rowlen;
-  c0.alloc(nubx); c1.alloc(nubx); ci0.alloc(nubx); ci1.alloc(nubx); first_ub.alloc(V + 1); first_lb.alloc(V + 1); rowlen.alloc(V + 1);
+  c0.alloc(nubx, s); c1.alloc(nubx, s); ci0.alloc(nubx, s); ci1.alloc(nubx, s); first_ub.alloc(V + 1, s); first_lb.alloc(V + 1, s); rowlen.alloc(V + 1, s);
   rowlen.zero(s);
-  d.s_rowptr.alloc(V + 1); d.s_col.alloc(d.nnzb); d.blk_row.alloc(d.nnzb); d.diag_pos.alloc(V); d.ub_pos.alloc(nubx); d.ub_pos_t.alloc(nubx);
+  d.s_rowptr.alloc(V + 1, s); d.s_col.alloc(d.nnzb, s); d.blk_row.alloc(d.nnzb, s); d.diag_pos.alloc(V, s); d.ub_pos.alloc(nubx, s); d.ub_pos_t.alloc(nubx, s);
   if (nub > 0) {
     k_swap_keys<<<grid(nub, 256), 256, 0, s>>>(nub, d.ub_keys.p, c0.p, ci0.p);
     sort_pairs(tmp, c0.p, c1.p, ci0.p, ci1.p, nub, 0, 32 + vbits, s);
@@ -318,8 +321,8 @@ inline void build_structure_device_blocks(DevStructure& d, const std::vector<int
 inline void upload_structure(const BaStructure& st, DevStructure& d, cudaStream_t s) {
   d.V = st.V; d.P = st.P; d.M = st.M; d.nchunks = st.nchunks(); d.nub = st.nub(); d.nnzb = st.nnzb(); d.npairs = (int64_t)st.pair_a.size();
   d.o_uv.upload(reinterpret_cast<const float2*>(st.o_uv.data()), st.M, s);
-  if (st.M == 0) d.o_uv.alloc(1);
-  auto up = [&](DevBuf<int>& b, const std::vector<int>& v) { if (v.empty()) b.alloc(1); else b.upload(v, s); };
+  if (st.M == 0) d.o_uv.alloc(1, s);
+  auto up = [&](DevBuf<int>& b, const std::vector<int>& v) { if (v.empty()) b.alloc(1, s); else b.upload(v, s); };
   up(d.perm, st.perm); up(d.o_view, st.o_view); up(d.o_track, st.o_track); up(d.view_off, st.view_off);
   up(d.chunk_view, st.chunk_view); up(d.chunk_begin, st.chunk_begin); up(d.chunk_cnt, st.chunk_cnt); up(d.view_chunk_off, st.view_chunk_off);
   up(d.t_off, st.t_off); up(d.t_obs, st.t_obs); up(d.pair_a, st.pair_a); up(d.pair_b, st.pair_b);
@@ -333,7 +336,7 @@ inline void upload_structure(const BaStructure& st, DevStructure& d, cudaStream_
   up(d.blk_row, blk_row); up(d.view_active, active);
   std::vector<unsigned long long> keys(st.nub());
   for (int b = 0; b < st.nub(); ++b) keys[b] = ((unsigned long long)(unsigned)st.ub_row[b] << 32) | (unsigned)st.ub_col[b];
-  if (keys.empty()) d.ub_keys.alloc(1); else d.ub_keys.upload(keys, s);
+  if (keys.empty()) d.ub_keys.alloc(1, s); else d.ub_keys.upload(keys, s);
   d.h_rowptr = st.s_rowptr;
 }
 

@@ -116,6 +116,7 @@ struct BaSolver : BaSolverBase {
   typedef Dims<NCL> D;
   static constexpr bool kFyBorder = (TYPE != BA_PTZRAY_FXFY_DIST);
 
+  StreamHolder sh;       // first member: destroyed last, after every buffer allocated on its stream
   int V, P, M, A, nb = 0, nav = 0, n = 0;
   ptz_solver_options opt;
   DevStructure ds;       // orderings + block pattern, device-resident
@@ -167,7 +168,9 @@ struct BaSolver : BaSolverBase {
     int dev = 0;
     PTZ_CUDA(cudaGetDevice(&dev));
     PTZ_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    PTZ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    enable_memory_pool();
+    sh.create();
+    stream = sh.s;
     clk.init(stream);
     if (opt.verbose & 4) {
       // reference path: the unit-tested host builder
@@ -229,14 +232,13 @@ struct BaSolver : BaSolverBase {
   ~BaSolver() {
     if (h_scalars) cudaFreeHost(h_scalars);
     if (h_info) cudaFreeHost(h_info);
-    if (stream) cudaStreamDestroy(stream);
   }
 
   // every rank must hold the same block pattern of S: all-gather the local upper block keys, return their sorted union
   std::vector<int64_t> union_of_keys(const std::vector<int64_t>& keys) {
     const int W = g_nccl.world;
     DevBuf<int64_t> d_cnt, d_all, d_my, d_pad;
-    d_cnt.alloc(W);
+    d_cnt.alloc(W, stream);
     int64_t my = (int64_t)keys.size();
     std::vector<int64_t> counts(W);
     d_my.upload(&my, 1, stream);
@@ -248,7 +250,7 @@ struct BaSolver : BaSolverBase {
     std::vector<int64_t> padded(mx, -1);
     std::copy(keys.begin(), keys.end(), padded.begin());
     d_pad.upload(padded, stream);
-    d_all.alloc((size_t)mx * W);
+    d_all.alloc((size_t)mx * W, stream);
     PTZ_NCCL(ncclAllGather(d_pad.p, d_all.p, mx, ncclInt64, g_nccl.comm, stream));
     std::vector<int64_t> all((size_t)mx * W);
     d_all.download(all.data(), all.size(), stream);
@@ -284,9 +286,9 @@ struct BaSolver : BaSolverBase {
     }
     d_intr_init.upload(h_intr0, s); d_ext_init.upload(h_ext0, s); d_tlw_init.upload(h_tlw0, s);
     d_trk_init.upload(trk, s);
-    for (int i = 0; i < 2; ++i) { d_intr[i].alloc(9 * (size_t)V); d_ext[i].alloc(6 * (size_t)V); d_trk[i].alloc(trk.size()); d_tlw[i].alloc(6); }
-    d_vt.alloc(V);
-    d_RiKi.alloc(9 * (size_t)V);
+    for (int i = 0; i < 2; ++i) { d_intr[i].alloc(9 * (size_t)V, stream); d_ext[i].alloc(6 * (size_t)V, stream); d_trk[i].alloc(trk.size(), stream); d_tlw[i].alloc(6, stream); }
+    d_vt.alloc(V, stream);
+    d_RiKi.alloc(9 * (size_t)V, stream);
     if (!have_ray0 && P > 0) {  // Pix2Ray on the device, into the initial track records
       k_rikI<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr_init.p, d_ext_init.p, d_RiKi.p);
       k_init_rays<<<cdiv(P, 128), 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, ds.o_view.p, ds.o_uv.p, d_RiKi.p, d_trk_init.p);
@@ -306,45 +308,45 @@ struct BaSolver : BaSolverBase {
       d_pts_uv.upload(reinterpret_cast<const float2*>(puv.data()), A, s);
       d_pts_xyz.upload(pxyz, s); d_pts_view.upload(pview, s);
       d_ann_view.upload(h_ann_view, s); d_ann_off.upload(h_ann_off, s);
-      d_pts_scratch.alloc((size_t)A * (2 + 2 * NCL + 2 * nb));
-      d_pts_raw.alloc((size_t)A * 26);
+      d_pts_scratch.alloc((size_t)A * (2 + 2 * NCL + 2 * nb), stream);
+      d_pts_raw.alloc((size_t)A * 26, stream);
     }
     d_ann_idx.upload(h_ann_idx, s);
     // work buffers
-    d_scale_cam.alloc((size_t)V * NCL); d_scale_b.alloc(kMaxBorder);
-    d_rec.alloc((size_t)std::max(M, 1) * D::RS);
-    d_part.alloc((size_t)std::max(ds.nchunks, 1) * D::NPART);
+    d_scale_cam.alloc((size_t)V * NCL, stream); d_scale_b.alloc(kMaxBorder, stream);
+    d_rec.alloc((size_t)std::max(M, 1) * D::RS, stream);
+    d_part.alloc((size_t)std::max(ds.nchunks, 1) * D::NPART, stream);
     viewred_n = (size_t)V * NCL * NCL + (size_t)V * NCL + V + (size_t)nav * NCL * nb + (size_t)nb * nb + nb + 2;
-    d_viewred.alloc(viewred_n);
+    d_viewred.alloc(viewred_n, stream);
     d_viewred.zero(s);
     p_U = d_viewred.p; p_g = p_U + (size_t)V * NCL * NCL; p_cost_view = p_g + (size_t)V * NCL; p_C = p_cost_view + V;
     p_Hbb = p_C + (size_t)nav * NCL * nb; p_gb = p_Hbb + (size_t)nb * nb; p_cost_pts = p_gb + nb;
-    d_gabs.alloc((size_t)V * NCL + kMaxBorder);
+    d_gabs.alloc((size_t)V * NCL + kMaxBorder, stream);
     d_gabs.zero(s);
     p_gabs = d_gabs.p; p_gabs_b = d_gabs.p + (size_t)V * NCL;
-    d_Vh.alloc((size_t)std::max(P, 1) * 10);
+    d_Vh.alloc((size_t)std::max(P, 1) * 10, stream);
     nblk_ray = std::max(cdiv(P, 128), 1); nblk_cam = std::max(cdiv(V, 128), 1);
-    d_gmax_part.alloc(nblk_ray); d_gmax_part.zero(s);
-    d_diag_ray.alloc(3 * (size_t)std::max(P, 1)); d_diag_cam.alloc((size_t)V * NCL); d_diag_b.alloc(kMaxBorder);
-    d_Lt.alloc((size_t)std::max(P, 1) * 10);
-    d_What.alloc((size_t)std::max(M, 1) * D::WS); d_What.zero(s);
-    d_q.alloc((size_t)std::max(M, 1) * NCL);
+    d_gmax_part.alloc(nblk_ray, stream); d_gmax_part.zero(s);
+    d_diag_ray.alloc(3 * (size_t)std::max(P, 1), stream); d_diag_cam.alloc((size_t)V * NCL, stream); d_diag_b.alloc(kMaxBorder, stream);
+    d_Lt.alloc((size_t)std::max(P, 1) * 10, stream);
+    d_What.alloc((size_t)std::max(M, 1) * D::WS, stream); d_What.zero(s);
+    d_q.alloc((size_t)std::max(M, 1) * NCL, stream);
     sys_n = (size_t)ds.nnzb * NCL * NCL + n;
-    d_sys.alloc(sys_n);
+    d_sys.alloc(sys_n, stream);
     p_Sval = d_sys.p; p_rhs = p_Sval + (size_t)ds.nnzb * NCL * NCL;
-    d_Linv.alloc((size_t)V * NCL * NCL); d_Linv_b.alloc(kMaxBorder * kMaxBorder); d_Sbb.alloc(kMaxBorder * kMaxBorder);
-    d_Cs.alloc((size_t)std::max(nav, 1) * NCL * std::max(nb, 1));
-    d_cgstate.alloc(6 * (size_t)n); d_cgstate.zero(s);
-    d_cgxp.alloc(2 * (size_t)n); d_cgxp.zero(s);
-    d_y.alloc(n); d_y.zero(s);
-    d_bar.alloc(1);
-    d_pcg_partial.alloc(2 * 2 * (size_t)num_sms * 2);
-    d_pcg_res.alloc(2); d_pcg_info.alloc(2); d_fail.alloc(1); d_fail.zero(s);
-    d_part3_ray.alloc(3 * (size_t)nblk_ray); d_part3_ray.zero(s);
-    d_part3_cam.alloc(3 * (size_t)nblk_cam); d_part3_b.alloc(3); d_part3_b.zero(s);
-    d_cost_part.alloc(2 * (size_t)std::max(ds.nchunks, 1)); d_cost_part.zero(s);
-    d_scalars.alloc(S_COUNT); d_scalars.zero(s);
-    d_disp.alloc(3); d_disp.zero(s);
+    d_Linv.alloc((size_t)V * NCL * NCL, stream); d_Linv_b.alloc(kMaxBorder * kMaxBorder, stream); d_Sbb.alloc(kMaxBorder * kMaxBorder, stream);
+    d_Cs.alloc((size_t)std::max(nav, 1) * NCL * std::max(nb, 1), stream);
+    d_cgstate.alloc(6 * (size_t)n, stream); d_cgstate.zero(s);
+    d_cgxp.alloc(2 * (size_t)n, stream); d_cgxp.zero(s);
+    d_y.alloc(n, stream); d_y.zero(s);
+    d_bar.alloc(1, stream);
+    d_pcg_partial.alloc(2 * 2 * (size_t)num_sms * 2, stream);
+    d_pcg_res.alloc(2, stream); d_pcg_info.alloc(2, stream); d_fail.alloc(1, stream); d_fail.zero(s);
+    d_part3_ray.alloc(3 * (size_t)nblk_ray, stream); d_part3_ray.zero(s);
+    d_part3_cam.alloc(3 * (size_t)nblk_cam, stream); d_part3_b.alloc(3, stream); d_part3_b.zero(s);
+    d_cost_part.alloc(2 * (size_t)std::max(ds.nchunks, 1), stream); d_cost_part.zero(s);
+    d_scalars.alloc(S_COUNT, stream); d_scalars.zero(s);
+    d_disp.alloc(3, stream); d_disp.zero(s);
     PTZ_CUDA(cudaMallocHost((void**)&h_scalars, S_COUNT * sizeof(double)));
     PTZ_CUDA(cudaMallocHost((void**)&h_info, 4 * sizeof(int)));
     reset();
@@ -535,7 +537,7 @@ struct BaSolver : BaSolverBase {
   double current_x_norm() {
     const int nblk = std::max(cdiv(std::max(V, P), 256), 1);
     DevBuf<double> part;
-    part.alloc(2 * (size_t)nblk);
+    part.alloc(2 * (size_t)nblk, stream);
     k_xnorm2<<<nblk, 256, 0, stream>>>(V, P, ds.view_active.p, d_intr[cur].p, d_ext[cur].p, ds.t_off.p, d_trk[cur].p, part.p);
     ScalarJobs J;
     J.nsum = 2; J.nmax = 0;
@@ -682,7 +684,7 @@ struct BaSolver : BaSolverBase {
     if ((out->ray || out->rays_world) && P > 0) {
       // compact rays (local and world frame) on the device, straight into the caller's buffers
       DevBuf<double> d_ray, d_rayw;
-      d_ray.alloc(3 * (size_t)P); d_rayw.alloc(3 * (size_t)P);
+      d_ray.alloc(3 * (size_t)P, stream); d_rayw.alloc(3 * (size_t)P, stream);
       k_rays_out<<<cdiv(P, 256), 256, 0, stream>>>(P, d_trk[cur].p, d_tlw[cur].p, d_ray.p, d_rayw.p);
       if (out->ray) d_ray.download(out->ray, 3 * (size_t)P, stream);
       if (out->rays_world) d_rayw.download(out->rays_world, 3 * (size_t)P, stream);

@@ -30,29 +30,65 @@ struct CudaError : std::runtime_error {
     }                                                                                                         \
   } while (0)
 
+// Owns a stream; declare it BEFORE any DevBuf that allocates on it so that it is destroyed after them.
+struct StreamHolder {
+  cudaStream_t s = nullptr;
+  StreamHolder() {}
+  StreamHolder(const StreamHolder&) = delete;
+  StreamHolder& operator=(const StreamHolder&) = delete;
+  void create() { PTZ_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
+  ~StreamHolder() {
+    if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+  }
+};
+
+// keep freed device memory in the default pool: the many BA calls of one IBA run (and bench.py's repeated solves)
+// then allocate in microseconds instead of paying cudaMalloc/cudaFree every time
+inline void enable_memory_pool() {
+  static bool done = false;
+  if (done) return;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thresh = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+  }
+  done = true;
+}
+
+// Device buffer.  alloc(count, stream) with a non-null stream is stream-ordered (cudaMallocAsync / cudaFreeAsync on that
+// stream); without a stream it is a plain cudaMalloc.
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  cudaStream_t as = nullptr;
+  bool async = false;
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) { if (async) cudaFreeAsync(p, as); else cudaFree(p); }
     p = nullptr;
     n = 0;
   }
-  void alloc(size_t count) {
+  void alloc(size_t count, cudaStream_t s = nullptr) {
     release();
     n = count;
-    if (count) PTZ_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    as = s;
+    async = (s != nullptr);
+    if (count) {
+      if (async) PTZ_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), s));
+      else PTZ_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    }
   }
   void zero(cudaStream_t s) {
     if (n) PTZ_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
   }
   void upload(const T* h, size_t count, cudaStream_t s) {
-    if (count > n) alloc(count);
+    if (count > n) alloc(count, s);
     if (count) PTZ_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
   }
   void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }

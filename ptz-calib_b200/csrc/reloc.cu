@@ -353,8 +353,10 @@ int ptzreloc_solve_batch(const ptzreloc_batch* b, const ptz_solver_options* opt,
       if (n < 0) throw CudaError(PTZ_ERR_INVALID, "match_offset is not monotone");
       max_matches = std::max<int64_t>(max_matches, n);
     }
-    cudaStream_t s;
-    PTZ_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    enable_memory_pool();
+    StreamHolder sh;  // declared before the buffers: destroyed after them
+    sh.create();
+    cudaStream_t s = sh.s;
     DevBuf<int64_t> d_off;
     DevBuf<float2> d_ur, d_uc;
     DevBuf<double> d_ref, d_init, d_cam, d_ic, d_fc, d_rms, d_loc;
@@ -364,8 +366,8 @@ int ptzreloc_solve_batch(const ptzreloc_batch* b, const ptz_solver_options* opt,
     d_uc.upload(reinterpret_cast<const float2*>(b->uv_cur), N, s);
     d_ref.upload(b->ref_cam, 21 * (size_t)B, s);
     d_init.upload(b->init_cam, 21 * (size_t)B, s);
-    d_cam.alloc(21 * (size_t)B); d_ic.alloc(B); d_fc.alloc(B); d_rms.alloc(B); d_loc.alloc(15 * (size_t)B);
-    d_succ.alloc(B); d_term.alloc(B); d_ni.alloc(B); d_it.alloc(B);
+    d_cam.alloc(21 * (size_t)B, s); d_ic.alloc(B, s); d_fc.alloc(B, s); d_rms.alloc(B, s); d_loc.alloc(15 * (size_t)B, s);
+    d_succ.alloc(B, s); d_term.alloc(B, s); d_ni.alloc(B, s); d_it.alloc(B, s);
     RelocArgs a;
     a.B = B; a.off = d_off.p; a.uv_ref = d_ur.p; a.uv_cur = d_uc.p; a.ref_cam = d_ref.p; a.init_cam = d_init.p;
     a.max_iter = b->max_iter; a.max_reproj_error = b->max_reproj_error; a.opt = *opt;
@@ -381,9 +383,7 @@ int ptzreloc_solve_batch(const ptzreloc_batch* b, const ptz_solver_options* opt,
     if (out->final_cost) d_fc.download(out->final_cost, B, s);
     if (out->final_rms) d_rms.download(out->final_rms, B, s);
     if (out->local_cam15) d_loc.download(out->local_cam15, 15 * (size_t)B, s);
-    cudaError_t e = cudaStreamSynchronize(s);
-    cudaStreamDestroy(s);
-    PTZ_CUDA(e);
+    PTZ_CUDA(cudaStreamSynchronize(s));
     return (int)PTZ_OK;
   });
 }

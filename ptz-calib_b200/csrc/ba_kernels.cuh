@@ -153,13 +153,23 @@ __global__ void k_track_accum(int P, int RS, const int* __restrict__ t_off, cons
   double gm = 0;
   if (p < P) {
     double v00 = 0, v10 = 0, v11 = 0, v20 = 0, v21 = 0, v22 = 0, h0 = 0, h1 = 0, h2 = 0;
-    for (int i = t_off[p]; i < t_off[p + 1]; ++i) {
-      const double2* q = reinterpret_cast<const double2*>(rec + (size_t)t_obs[i] * RS);
-      const double2 r = q[0], e01 = q[1], e23 = q[2], e45 = q[3];
-      const double a0 = e01.x, a1 = e01.y, a2 = e23.x, b0 = e23.y, b1 = e45.x, b2 = e45.y;
-      v00 += a0 * a0 + b0 * b0; v10 += a1 * a0 + b1 * b0; v11 += a1 * a1 + b1 * b1;
-      v20 += a2 * a0 + b2 * b0; v21 += a2 * a1 + b2 * b1; v22 += a2 * a2 + b2 * b2;
-      h0 += a0 * r.x + b0 * r.y; h1 += a1 * r.x + b1 * r.y; h2 += a2 * r.x + b2 * r.y;
+    const int tb = t_off[p], te = t_off[p + 1];
+    for (int i = tb; i < te; i += 4) {
+      // four records in flight (indices clamped, extra ones weighted 0)
+      double2 rr[4], ea[4], eb[4], ec[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double2* q = reinterpret_cast<const double2*>(rec + (size_t)t_obs[min(i + u, te - 1)] * RS);
+        rr[u] = q[0]; ea[u] = q[1]; eb[u] = q[2]; ec[u] = q[3];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (i + u >= te) break;
+        const double a0 = ea[u].x, a1 = ea[u].y, a2 = eb[u].x, b0 = eb[u].y, b1 = ec[u].x, b2 = ec[u].y;
+        v00 += a0 * a0 + b0 * b0; v10 += a1 * a0 + b1 * b0; v11 += a1 * a1 + b1 * b1;
+        v20 += a2 * a0 + b2 * b0; v21 += a2 * a1 + b2 * b1; v22 += a2 * a2 + b2 * b2;
+        h0 += a0 * rr[u].x + b0 * rr[u].y; h1 += a1 * rr[u].x + b1 * rr[u].y; h2 += a2 * rr[u].x + b2 * rr[u].y;
+      }
     }
     double* o = Vh + (size_t)p * 10;
     o[0] = v00; o[1] = v10; o[2] = v11; o[3] = v20; o[4] = v21; o[5] = v22; o[6] = h0; o[7] = h1; o[8] = h2; o[9] = 0;
@@ -221,88 +231,96 @@ __global__ void k_track_factor(int P, const int* __restrict__ t_off, const doubl
   lt[0] = L[0]; lt[1] = L[1]; lt[2] = L[2]; lt[3] = L[3]; lt[4] = L[4]; lt[5] = L[5];
   lt[6] = empty ? 0.0 : t0; lt[7] = empty ? 0.0 : t1; lt[8] = empty ? 0.0 : t2; lt[9] = 0;
 }
-// per observation (one thread each, in view-major order so that records stream): What = (F^T E) L^-T, q = What t
+// per observation (one thread each; one CTA per chunk of one view, so records stream and the view's Schur terms reduce in
+// the CTA): What = (F^T E) L^-T, q = What t; chunk partials of sum What What^T (upper) and sum q for k_schur_diag
 template <int NCL>
-__global__ void __launch_bounds__(256) k_obs_what(int M, const int* __restrict__ o_track, const double* __restrict__ rec, const double* __restrict__ Lt,
-                                                   double* __restrict__ What, double* __restrict__ q) {
-  typedef Dims<NCL> D;
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= M) return;
-  const int p = o_track[o];
-  const double2* lp = reinterpret_cast<const double2*>(Lt + (size_t)p * 10);
-  const double2 l01 = lp[0], l23 = lp[1], l45 = lp[2], l67 = lp[3], l89 = lp[4];
-  const double L0 = l01.x, L1 = l01.y, L2 = l23.x, L3 = l23.y, L4 = l45.x, L5 = l45.y, t0 = l67.x, t1 = l67.y, t2 = l89.x;
-  const double i00 = 1.0 / L0, i11 = 1.0 / L2, i22 = 1.0 / L5;
-  const double2* rp = reinterpret_cast<const double2*>(rec + (size_t)o * D::RS);
-  const double2 e01 = rp[1], e23 = rp[2], e45 = rp[3];
-  const double a0 = e01.x, a1 = e01.y, a2 = e23.x, b0 = e23.y, b1 = e45.x, b2 = e45.y;
-  double Fv[2 * NCL];
-#pragma unroll
-  for (int a = 0; a < NCL; ++a) { const double2 f = rp[4 + a]; Fv[2 * a] = f.x; Fv[2 * a + 1] = f.y; }
-  double w[D::WS], qa[NCL];
-#pragma unroll
-  for (int a = 0; a < NCL; ++a) {
-    const double f0 = Fv[a], f1 = Fv[NCL + a];
-    const double w0 = f0 * a0 + f1 * b0, w1 = f0 * a1 + f1 * b1, w2 = f0 * a2 + f1 * b2;  // row a of F^T E
-    const double x0 = w0 * i00, x1 = (w1 - L1 * x0) * i11, x2 = (w2 - L3 * x0 - L4 * x1) * i22;
-    w[3 * a] = x0; w[3 * a + 1] = x1; w[3 * a + 2] = x2;
-    qa[a] = x0 * t0 + x1 * t1 + x2 * t2;
-  }
-  if (D::WS > 3 * NCL) w[D::WS - 1] = 0.0;
-  double2* wo = reinterpret_cast<double2*>(What + (size_t)o * D::WS);
-#pragma unroll
-  for (int k = 0; k < D::WS / 2; ++k) wo[k] = make_double2(w[2 * k], w[2 * k + 1]);
-#pragma unroll
-  for (int a = 0; a < NCL; ++a) q[(size_t)o * NCL + a] = qa[a];
-}
-
-// per view (one CTA): S_cc = [U + D^2] - sum_o What What^T, rhs_c = [g] - sum_o q_o.  The bracketed terms are added by
-// the rank that owns the camera blocks (add_own); D^2 = clamp(diag U) / mu, refreshed after accepted steps only.
-template <int NCL>
-__global__ void __launch_bounds__(128) k_schur_diag(const int* __restrict__ view_off, const double* __restrict__ What, const double* __restrict__ q,
-                                                    const double* __restrict__ U, const double* __restrict__ g, double mu, int refresh_diag, double min_diag,
-                                                    double max_diag, int add_own, double* __restrict__ diag_cam, const int* __restrict__ diag_pos,
-                                                    double* __restrict__ Sval, double* __restrict__ rhs) {
+__global__ void __launch_bounds__(kChunk) k_obs_what(const int* __restrict__ chunk_begin, const int* __restrict__ chunk_cnt, const int* __restrict__ o_track,
+                                                      const double* __restrict__ rec, const double* __restrict__ Lt, double* __restrict__ What,
+                                                      double* __restrict__ wpart) {
   typedef Dims<NCL> D;
   constexpr int NV = D::NU + NCL;
-  __shared__ double sred[NV * 4];
-  const int v = blockIdx.x;
+  __shared__ double sred[NV * (kChunk / 32)];
+  const int chunk = blockIdx.x, begin = chunk_begin[chunk], cnt = chunk_cnt[chunk];
   double acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-  for (int o = view_off[v] + threadIdx.x; o < view_off[v + 1]; o += blockDim.x) {
-    double w[D::WS];
-    const double2* wp = reinterpret_cast<const double2*>(What + (size_t)o * D::WS);
+  if (threadIdx.x < cnt) {
+    const int o = begin + threadIdx.x;
+    const int p = o_track[o];
+    const double2* lp = reinterpret_cast<const double2*>(Lt + (size_t)p * 10);
+    const double2 l01 = lp[0], l23 = lp[1], l45 = lp[2], l67 = lp[3], l89 = lp[4];
+    const double L0 = l01.x, L1 = l01.y, L2 = l23.x, L3 = l23.y, L4 = l45.x, L5 = l45.y, t0 = l67.x, t1 = l67.y, t2 = l89.x;
+    const double i00 = 1.0 / L0, i11 = 1.0 / L2, i22 = 1.0 / L5;
+    const double2* rp = reinterpret_cast<const double2*>(rec + (size_t)o * D::RS);
+    const double2 e01 = rp[1], e23 = rp[2], e45 = rp[3];
+    const double a0 = e01.x, a1 = e01.y, a2 = e23.x, b0 = e23.y, b1 = e45.x, b2 = e45.y;
+    double Fv[2 * NCL];
 #pragma unroll
-    for (int k = 0; k < D::WS / 2; ++k) { const double2 t = wp[k]; w[2 * k] = t.x; w[2 * k + 1] = t.y; }
+    for (int a = 0; a < NCL; ++a) { const double2 f = rp[4 + a]; Fv[2 * a] = f.x; Fv[2 * a + 1] = f.y; }
+    double w[D::WS];
+#pragma unroll
+    for (int a = 0; a < NCL; ++a) {
+      const double f0 = Fv[a], f1 = Fv[NCL + a];
+      const double w0 = f0 * a0 + f1 * b0, w1 = f0 * a1 + f1 * b1, w2 = f0 * a2 + f1 * b2;  // row a of F^T E
+      const double x0 = w0 * i00, x1 = (w1 - L1 * x0) * i11, x2 = (w2 - L3 * x0 - L4 * x1) * i22;
+      w[3 * a] = x0; w[3 * a + 1] = x1; w[3 * a + 2] = x2;
+      acc[D::NU + a] = x0 * t0 + x1 * t1 + x2 * t2;  // q_a
+    }
+    if (D::WS > 3 * NCL) w[D::WS - 1] = 0.0;
+    double2* wo = reinterpret_cast<double2*>(What + (size_t)o * D::WS);
+#pragma unroll
+    for (int k = 0; k < D::WS / 2; ++k) wo[k] = make_double2(w[2 * k], w[2 * k + 1]);
     int k = 0;
 #pragma unroll
     for (int a = 0; a < NCL; ++a)
 #pragma unroll
-      for (int b = a; b < NCL; ++b) acc[k++] += w[3 * a] * w[3 * b] + w[3 * a + 1] * w[3 * b + 1] + w[3 * a + 2] * w[3 * b + 2];
-#pragma unroll
-    for (int a = 0; a < NCL; ++a) acc[D::NU + a] += q[(size_t)o * NCL + a];
+      for (int b = a; b < NCL; ++b) acc[k++] = w[3 * a] * w[3 * b] + w[3 * a + 1] * w[3 * b + 1] + w[3 * a + 2] * w[3 * b + 2];
   }
   block_sum<NV>(acc, sred);
   if (threadIdx.x == 0) {
-    const double* Uv = U + (size_t)v * NCL * NCL;
-    double* S = Sval + (size_t)diag_pos[v] * NCL * NCL;
-    int k = 0;
-    for (int a = 0; a < NCL; ++a)
-      for (int b = a; b < NCL; ++b) {
-        double s = -acc[k++];
-        if (add_own) s += Uv[a * NCL + b];
-        if (a == b) {
-          double d;
-          if (refresh_diag) { d = fmin(fmax(Uv[a * NCL + a], min_diag), max_diag); diag_cam[v * NCL + a] = d; }
-          else d = diag_cam[v * NCL + a];
-          if (add_own) s += d / mu;
-        }
-        S[a * NCL + b] = s;
-        S[b * NCL + a] = s;
-      }
-    for (int a = 0; a < NCL; ++a) rhs[v * NCL + a] = (add_own ? g[v * NCL + a] : 0.0) - acc[D::NU + a];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) wpart[(size_t)chunk * NV + i] = acc[i];
   }
+}
+
+// per view (one thread): S_cc = [U + D^2] - sum_chunks(partial What What^T), rhs_c = [g] - sum_chunks(partial q), chunk order fixed.
+// The bracketed terms are added by the rank that owns the camera blocks (add_own); D^2 = clamp(diag U)/mu, refreshed after
+// accepted steps only.
+template <int NCL>
+__global__ void k_schur_diag(int V, const int* __restrict__ view_chunk_off, const double* __restrict__ wpart, const double* __restrict__ U,
+                             const double* __restrict__ g, double mu, int refresh_diag, double min_diag, double max_diag, int add_own,
+                             double* __restrict__ diag_cam, const int* __restrict__ diag_pos, double* __restrict__ Sval, double* __restrict__ rhs) {
+  typedef Dims<NCL> D;
+  constexpr int NV = D::NU + NCL;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+  for (int c = view_chunk_off[v]; c < view_chunk_off[v + 1]; ++c) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] += wpart[(size_t)c * NV + i];
+  }
+  const double* Uv = U + (size_t)v * NCL * NCL;
+  double* S = Sval + (size_t)diag_pos[v] * NCL * NCL;
+  int k = 0;
+#pragma unroll
+  for (int a = 0; a < NCL; ++a)
+#pragma unroll
+    for (int b = a; b < NCL; ++b) {
+      double sacc = -acc[k++];
+      if (add_own) sacc += Uv[a * NCL + b];
+      if (a == b) {
+        double d;
+        if (refresh_diag) { d = fmin(fmax(Uv[a * NCL + a], min_diag), max_diag); diag_cam[v * NCL + a] = d; }
+        else d = diag_cam[v * NCL + a];
+        if (add_own) sacc += d / mu;
+      }
+      S[a * NCL + b] = sacc;
+      S[b * NCL + a] = sacc;
+    }
+#pragma unroll
+  for (int a = 0; a < NCL; ++a) rhs[v * NCL + a] = (add_own ? g[v * NCL + a] : 0.0) - acc[D::NU + a];
 }
 
 // per upper off-diagonal block (one warp): S_rc = - sum over observation pairs What_o What_o'^T ; also writes S_cr = S_rc^T
@@ -533,8 +551,8 @@ __device__ __forceinline__ void grid_reduce2(double& a, double& b, double* parti
     double s0 = 0, s1 = 0;
     for (int w = 0; w < nwarp; ++w) { s0 += sred[w][0]; s1 += sred[w][1]; }
     __stcg(reinterpret_cast<double2*>(buf) + blockIdx.x, make_double2(s0, s1));
-    __threadfence();
-    atomicAdd(bar, 1u);
+    // release-increment: orders this CTA's writes (published to thread 0 by the barrier above) before the arrival
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
     const unsigned int target = (epoch + 1u) * gridDim.x;
     while (ld_acquire_u32(bar) < target) { }
   }
@@ -708,12 +726,30 @@ __global__ void k_track_backsub(int P, const int* __restrict__ t_off, const int*
     } else {
       const double* lt = Lt + (size_t)p * 10;
       double b0 = lt[6], b1 = lt[7], b2 = lt[8];
-      for (int i = t_off[p]; i < t_off[p + 1]; ++i) {
-        const int o = t_obs[i];
-        const double* w = What + (size_t)o * D::WS;
-        const double* yc = y + (size_t)o_view[o] * NCL;
+      const int tb = t_off[p], te = t_off[p + 1];
+      for (int i = tb; i < te; i += 4) {
+        int ob[4];
 #pragma unroll
-        for (int a = 0; a < NCL; ++a) { const double ya = yc[a]; b0 -= w[3 * a] * ya; b1 -= w[3 * a + 1] * ya; b2 -= w[3 * a + 2] * ya; }
+        for (int u = 0; u < 4; ++u) ob[u] = t_obs[min(i + u, te - 1)];
+        int vw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) vw[u] = o_view[ob[u]];
+        double wv[4][3 * NCL], yv[4][NCL];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double2* w2 = reinterpret_cast<const double2*>(What + (size_t)ob[u] * D::WS);
+#pragma unroll
+          for (int k = 0; k < (3 * NCL) / 2; ++k) { const double2 t2v = w2[k]; wv[u][2 * k] = t2v.x; wv[u][2 * k + 1] = t2v.y; }
+          if ((3 * NCL) & 1) wv[u][3 * NCL - 1] = What[(size_t)ob[u] * D::WS + 3 * NCL - 1];
+#pragma unroll
+          for (int a = 0; a < NCL; ++a) yv[u][a] = y[(size_t)vw[u] * NCL + a];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (i + u >= te) break;
+#pragma unroll
+          for (int a = 0; a < NCL; ++a) { const double ya = yv[u][a]; b0 -= wv[u][3 * a] * ya; b1 -= wv[u][3 * a + 1] * ya; b2 -= wv[u][3 * a + 2] * ya; }
+        }
       }
       // L^T y = b
       const double y2 = b2 / lt[5], y1 = (b1 - lt[4] * y2) / lt[2], y0 = (b0 - lt[1] * y1 - lt[3] * y2) / lt[0];
@@ -806,9 +842,9 @@ struct ScalarJobs {
   const double* sum_ptr[12]; int sum_n[12]; int sum_stride[12]; int sum_slot[12]; int nsum;
   const double* max_ptr[4]; int max_n[4]; int max_slot[4]; int nmax;
 };
-__global__ void __launch_bounds__(256) k_scalars(ScalarJobs J, double* __restrict__ out) {
+__global__ void __launch_bounds__(1024) k_scalars(ScalarJobs J, double* __restrict__ out) {
   // one CTA per job (grid = nsum + nmax), fixed-order tree inside the CTA
-  __shared__ double sred[8];
+  __shared__ double sred[32];
   const int job = blockIdx.x;
   if (job < J.nsum) {
     const int j = job;

@@ -330,7 +330,7 @@ struct BaSolver : BaSolverBase {
     d_diag_ray.alloc(3 * (size_t)std::max(P, 1), stream); d_diag_cam.alloc((size_t)V * NCL, stream); d_diag_b.alloc(kMaxBorder, stream);
     d_Lt.alloc((size_t)std::max(P, 1) * 10, stream);
     d_What.alloc((size_t)std::max(M, 1) * D::WS, stream); d_What.zero(s);
-    d_q.alloc((size_t)std::max(M, 1) * NCL, stream);
+    d_q.alloc((size_t)std::max(ds.nchunks, 1) * (D::NU + NCL), stream);  // chunk partials of sum What What^T, sum q
     sys_n = (size_t)ds.nnzb * NCL * NCL + n;
     d_sys.alloc(sys_n, stream);
     p_Sval = d_sys.p; p_rhs = p_Sval + (size_t)ds.nnzb * NCL * NCL;
@@ -420,7 +420,7 @@ struct BaSolver : BaSolverBase {
     add_max(p_gabs, V * NCL, S_GMAX_CAM);
     add_max(d_gmax_part.p, P > 0 ? nblk_ray : 0, S_GMAX_RAY);
     add_max(p_gabs_b, nb, S_GMAX_B);
-    PTZ_TIMED(PTZ_K_SCALARS, k_scalars<<<J.nsum + J.nmax, 256, 0, stream>>>(J, d_scalars.p));
+    PTZ_TIMED(PTZ_K_SCALARS, k_scalars<<<J.nsum + J.nmax, 1024, 0, stream>>>(J, d_scalars.p));
     PTZ_CUDA(cudaGetLastError());
     allreduce_max(d_scalars.p + S_GMAX_RAY, S_MAX_END - S_GMAX_RAY, stream);
     read_scalars();
@@ -445,10 +445,10 @@ struct BaSolver : BaSolverBase {
     if (P > 0)
       PTZ_TIMED(PTZ_K_TRACK_SOLVE, {
         k_track_factor<<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, d_Vh.p, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_ray.p, d_Lt.p, d_fail.p);
-        k_obs_what<NCL><<<cdiv(M, 256), 256, 0, s>>>(M, ds.o_track.p, d_rec.p, d_Lt.p, d_What.p, d_q.p);
+        if (ds.nchunks > 0) k_obs_what<NCL><<<ds.nchunks, kChunk, 0, s>>>(ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_track.p, d_rec.p, d_Lt.p, d_What.p, d_q.p);
       });
-    PTZ_TIMED(PTZ_K_SCHUR_DIAG, k_schur_diag<NCL><<<V, 128, 0, s>>>(ds.view_off.p, d_What.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal,
-                                                                    opt.max_lm_diagonal, own, d_diag_cam.p, ds.diag_pos.p, p_Sval, p_rhs));
+    PTZ_TIMED(PTZ_K_SCHUR_DIAG, k_schur_diag<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, ds.view_chunk_off.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal,
+                                                                               opt.max_lm_diagonal, own, d_diag_cam.p, ds.diag_pos.p, p_Sval, p_rhs));
     if (ds.nub > 0)
       PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, k_schur_offdiag<NCL><<<cdiv(ds.nub, 8), 256, 0, s>>>(ds.nub, ds.pair_off.p, ds.pair_a.p, ds.pair_b.p, d_What.p,
                                                                                             ds.ub_pos.p, ds.ub_pos_t.p, p_Sval));
@@ -528,7 +528,7 @@ struct BaSolver : BaSolverBase {
     add_sum(d_part3_b.p, 1, 3, S_DM_B);
     add_sum(d_part3_b.p + 1, 1, 3, S_STEP2_B);
     add_sum(d_part3_b.p + 2, 1, 3, S_XN2_B);
-    PTZ_TIMED(PTZ_K_SCALARS, k_scalars<<<J.nsum + J.nmax, 256, 0, stream>>>(J, d_scalars.p));
+    PTZ_TIMED(PTZ_K_SCALARS, k_scalars<<<J.nsum + J.nmax, 1024, 0, stream>>>(J, d_scalars.p));
     PTZ_CUDA(cudaGetLastError());
     allreduce_sum(d_scalars.p, S_SUM_END, stream);
   }
@@ -543,7 +543,7 @@ struct BaSolver : BaSolverBase {
     J.nsum = 2; J.nmax = 0;
     J.sum_ptr[0] = part.p; J.sum_n[0] = nblk; J.sum_stride[0] = 2; J.sum_slot[0] = S_XN2_CAM;
     J.sum_ptr[1] = part.p + 1; J.sum_n[1] = nblk; J.sum_stride[1] = 2; J.sum_slot[1] = S_XN2_RAY;
-    k_scalars<<<2, 256, 0, stream>>>(J, d_scalars.p);
+    k_scalars<<<2, 1024, 0, stream>>>(J, d_scalars.p);
     PTZ_CUDA(cudaGetLastError());
     allreduce_sum(d_scalars.p + S_XN2_RAY, 1, stream);
     double tl[6] = {0, 0, 0, 0, 0, 0};
@@ -670,7 +670,7 @@ struct BaSolver : BaSolverBase {
     ScalarJobs J;
     J.nsum = 1; J.nmax = 0;
     J.sum_ptr[0] = d_cost_part.p + 1; J.sum_n[0] = ds.nchunks; J.sum_stride[0] = 2; J.sum_slot[0] = S_RAW2_CAND;
-    k_scalars<<<J.nsum + J.nmax, 256, 0, stream>>>(J, d_scalars.p);
+    k_scalars<<<J.nsum + J.nmax, 1024, 0, stream>>>(J, d_scalars.p);
     allreduce_sum(d_scalars.p + S_RAW2_CAND, 1, stream);
     read_scalars();
     const double n2 = (double)(out->num_residuals / 2 - A);

@@ -1,0 +1,346 @@
+// ptzcalib_b200.hpp — header-only C++ adaptor: the reference's two solver classes on top of the C ABI.
+//
+// Same class names, constructor / method signatures, argument meaning and error behaviour as
+//   ptzcalib::PTZRayOptimizer   src/core/ptzray_optimizer.h:112-177, .cc:405-766
+//   ptzcalib::KRTOptimizer      src/core/krt_optimizer.h:108-145,    .cc:251-567
+// and the value types of src/core/types.h (Camera, ImageFeatures, MatchesInfo, Ray) and src/core/tracks.h (Tracks,
+// TracksBuilder) they take — with plain-array stand-ins for the OpenCV types (cv::Mat 3x3 -> Mat33, cv::KeyPoint ->
+// KeyPoint{pt}, cv::DMatch -> DMatch{queryIdx, trainIdx}), because OpenCV's C++ headers are not part of this build.
+// A caller of the reference switches by including this header instead of ptzray_optimizer.h / krt_optimizer.h and
+// linking libptzcalib_b200.so; all numerics run on the GPU behind ptzba_solve / ptzreloc_solve_batch.
+//
+// Deviation: PTZRayOptimizer::SetInitTransLocalToWorld uses cv::solvePnP(EPNP) in the reference (.cc:562-633); here the
+// caller supplies the initial T_l_w with SetInitTransLocalToWorld(const double[6]) (not built).
+#ifndef PTZCALIB_B200_HPP
+#define PTZCALIB_B200_HPP
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <limits>
+#include <map>
+#include <numeric>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../ptz-calib_b200/csrc/ptz_math.cuh"  // rodrigues_jac / rodrigues_inv / mul33 (plain C++ when not compiled by nvcc)
+#include "ptzcalib_b200.h"
+
+namespace ptzcalib {
+
+struct Point2f { float x = 0, y = 0; };
+struct Point3d { double x = 0, y = 0, z = 0; };
+struct Size { int width = 0, height = 0; };
+struct KeyPoint { Point2f pt; };
+struct DMatch { int queryIdx = 0, trainIdx = 0; };
+typedef std::array<double, 9> Mat33;  // row-major
+typedef std::array<double, 3> Vec3;
+typedef std::array<double, 5> Vec5;
+
+// types.h:17-45
+struct ImageFeatures { long img_idx = 0; Size img_size; std::vector<KeyPoint> keypoints; };
+struct MatchesInfo {
+  long src_img_idx = 0, dst_img_idx = 0;
+  std::vector<DMatch> matches;
+  std::vector<unsigned char> inliers_mask;
+  int num_inliers = 0;
+  Mat33 H{{1, 0, 0, 0, 1, 0, 0, 0, 1}};
+  double confidence = 0;
+};
+struct Ray {
+  int id_;
+  Point3d pt3d_;
+  Point2f uv_;
+  Ray(int id, const Vec3& p, const Point2f& uv) : id_(id), uv_(uv) { pt3d_.x = p[0]; pt3d_.y = p[1]; pt3d_.z = p[2]; }
+};
+
+// types.h:47-97, types.cc:16-73
+class Camera {
+ public:
+  Camera() : K_{{1, 0, 0, 0, 1, 0, 0, 0, 1}}, R_{{1, 0, 0, 0, 1, 0, 0, 0, 1}}, t_{{0, 0, 0}}, dist_{{0, 0, 0, 0, 0}} {}
+  Camera(const Mat33& K, const Mat33& R, const Vec3& t, const Vec5& dist) : K_(K), R_(R), t_(t), dist_(dist) {}
+  const Mat33& K() const { return K_; }
+  Mat33& K() { return K_; }
+  const Mat33& R() const { return R_; }
+  Mat33& R() { return R_; }
+  const Vec3& t() const { return t_; }
+  Vec3& t() { return t_; }
+  const Vec5& dist() const { return dist_; }
+  Vec5& dist() { return dist_; }
+  Vec3 rvec() const { Vec3 r; ptz::rodrigues_inv(R_.data(), r.data()); return r; }
+  std::vector<double> ToVector() const {  // fx, fy, cx, cy, rvec, t, dist
+    std::vector<double> v(15);
+    v[0] = K_[0]; v[1] = K_[4]; v[2] = K_[2]; v[3] = K_[5];
+    ptz::rodrigues_inv(R_.data(), &v[4]);
+    for (int i = 0; i < 3; ++i) v[7 + i] = t_[i];
+    for (int i = 0; i < 5; ++i) v[10 + i] = dist_[i];
+    return v;
+  }
+  void FromVector(const std::vector<double>& v) {
+    if (v.size() != 15) throw std::invalid_argument("Expected camera vector size: 15, actual size :" + std::to_string(v.size()));
+    K_ = Mat33{{v[0], 0, v[2], 0, v[1], v[3], 0, 0, 1}};
+    ptz::rodrigues_jac(&v[4], R_.data(), nullptr);
+    for (int i = 0; i < 3; ++i) t_[i] = v[7 + i];
+    for (int i = 0; i < 5; ++i) dist_[i] = v[10 + i];
+  }
+  void ToKrt21(double* o) const {
+    o[0] = K_[0]; o[1] = K_[4]; o[2] = K_[2]; o[3] = K_[5];
+    for (int i = 0; i < 9; ++i) o[4 + i] = R_[i];
+    for (int i = 0; i < 3; ++i) o[13 + i] = t_[i];
+    for (int i = 0; i < 5; ++i) o[16 + i] = dist_[i];
+  }
+  void FromKrt21(const double* c) {
+    K_ = Mat33{{c[0], 0, c[2], 0, c[1], c[3], 0, 0, 1}};
+    for (int i = 0; i < 9; ++i) R_[i] = c[4 + i];
+    for (int i = 0; i < 3; ++i) t_[i] = c[13 + i];
+    for (int i = 0; i < 5; ++i) dist_[i] = c[16 + i];
+  }
+
+ private:
+  Mat33 K_, R_;
+  Vec3 t_;
+  Vec5 dist_;
+};
+
+// tracks.h:24-60, tracks.cc:19-113 (openMVG-style union-find over (image, feature) nodes)
+typedef std::pair<int, int> IndexedFeaturePair;
+typedef std::map<int, int> Track;    // image id -> feature id
+typedef std::map<int, Track> Tracks;  // track id -> track
+
+class TracksBuilder {
+ public:
+  void Build(const std::vector<MatchesInfo>& matches_info) {
+    std::set<IndexedFeaturePair> all;
+    for (const auto& mi : matches_info)
+      for (const auto& m : mi.matches) { all.emplace((int)mi.src_img_idx, m.queryIdx); all.emplace((int)mi.dst_img_idx, m.trainIdx); }
+    nodes_.assign(all.begin(), all.end());  // sorted: node -> flat index by position
+    parent_.resize(nodes_.size());
+    std::iota(parent_.begin(), parent_.end(), 0);
+    rank_.assign(nodes_.size(), 0);
+    size_.assign(nodes_.size(), 1);
+    for (const auto& mi : matches_info)
+      for (const auto& m : mi.matches) Union(IndexOf({(int)mi.src_img_idx, m.queryIdx}), IndexOf({(int)mi.dst_img_idx, m.trainIdx}));
+  }
+  // remove tracks that list an image twice or are shorter than min_track_length
+  void Filter(int min_track_length = 2) {
+    std::map<int, std::set<int>> tracks;
+    std::set<int> bad;
+    for (int k = 0; k < (int)nodes_.size(); ++k) {
+      const int id = Find(k);
+      if (!tracks[id].insert(nodes_[k].first).second) bad.insert(id);
+    }
+    for (const auto& t : tracks) if ((int)t.second.size() < min_track_length) bad.insert(t.first);
+    for (int k = 0; k < (int)nodes_.size(); ++k) Find(k);  // full path compression: parent_ == root
+    for (int& root : parent_)
+      if (bad.count(root) > 0) { size_[root] = 1; root = std::numeric_limits<int>::max(); }
+  }
+  void ExportToSTL(Tracks& tracks) {
+    tracks.clear();
+    for (int k = 0; k < (int)nodes_.size(); ++k) {
+      const int id = parent_[k];
+      if (id != std::numeric_limits<int>::max() && size_[id] > 1) tracks[id].insert(nodes_[k]);
+    }
+  }
+
+ private:
+  int IndexOf(const IndexedFeaturePair& p) const { return (int)(std::lower_bound(nodes_.begin(), nodes_.end(), p) - nodes_.begin()); }
+  int Find(int i) {
+    while (parent_[i] != i) { parent_[i] = parent_[parent_[i]]; i = parent_[i]; }
+    return i;
+  }
+  void Union(int a, int b) {
+    a = Find(a); b = Find(b);
+    if (a == b) return;
+    if (rank_[a] < rank_[b]) std::swap(a, b);
+    parent_[b] = a; size_[a] += size_[b];
+    if (rank_[a] == rank_[b]) ++rank_[a];
+  }
+  std::vector<IndexedFeaturePair> nodes_;
+  std::vector<int> parent_, rank_, size_;
+};
+
+enum FACTOR_TYPE { PTZRay, PTZRayDist, PTZRayFxfyDist, PTZRayDistDisp };  // ptzray_optimizer.h:110
+
+class PTZRayOptimizer {
+ public:
+  PTZRayOptimizer(const std::vector<ImageFeatures>& features, const std::vector<MatchesInfo>& matches_info, const std::vector<Camera>& cameras,
+                  const std::vector<std::vector<Point2f>>& pixels, const std::vector<std::vector<Point3d>>& pts3d,
+                  const std::unordered_set<long>& cam_ids, int max_iter, FACTOR_TYPE type)
+      : cameras_(cameras), features_(features), matches_info_(matches_info), pixels_(pixels), pts3d_(pts3d), num_cams_(cameras.size()), type_(type),
+        max_iter_(max_iter) { InitIds(cam_ids); }
+  PTZRayOptimizer(const std::vector<ImageFeatures>& features, const std::vector<MatchesInfo>& matches_info, const std::vector<Camera>& cameras,
+                  const std::unordered_set<long>& cam_ids, int max_iter, FACTOR_TYPE type)
+      : cameras_(cameras), features_(features), matches_info_(matches_info), num_cams_(cameras.size()), type_(type), max_iter_(max_iter) { InitIds(cam_ids); }
+
+  bool Solve(std::vector<Camera>& cameras) { std::vector<std::vector<Ray>> rays; return Solve(cameras, rays); }
+
+  bool Solve(std::vector<Camera>& cameras, std::vector<std::vector<Ray>>& rays) {
+    if (!CheckValid()) return false;
+    FindTracks();
+    // flatten (AddConstraints2d2d / 2d3d, .cc:799-958): candidate views get dense ids, one row per (track, candidate view)
+    std::vector<long> view_of;
+    std::unordered_map<long, int> dense;
+    for (size_t i = 0; i < num_cams_; ++i) if (isCandidate((long)i)) { dense[(long)i] = (int)view_of.size(); view_of.push_back((long)i); }
+    std::vector<double> intr, ext, weight, pxyz;
+    std::vector<float> uv, puv;
+    std::vector<int32_t> oview, otrack, pview;
+    std::vector<int> track_ids;
+    for (long id : view_of) {
+      const std::vector<double> v = cameras_[id].ToVector();
+      const double in[9] = {v[0], v[1], v[2], v[3], v[10], v[11], v[12], v[13], v[14]};
+      intr.insert(intr.end(), in, in + 9);
+      ext.insert(ext.end(), v.begin() + 4, v.begin() + 10);
+    }
+    for (const auto& te : tracks_) {
+      int row = -1;
+      for (const auto& it : te.second) {
+        if (!isCandidate(it.first)) continue;
+        if (row < 0) { row = (int)track_ids.size(); track_ids.push_back(te.first); weight.push_back((double)te.second.size()); }
+        const Point2f pt = features_[it.first].keypoints[it.second].pt;
+        uv.push_back(pt.x); uv.push_back(pt.y); oview.push_back(dense[it.first]); otrack.push_back(row);
+      }
+    }
+    for (long id : view_of)
+      if (!pixels_.empty())
+        for (size_t j = 0; j < pixels_[id].size(); ++j) {
+          puv.push_back(pixels_[id][j].x); puv.push_back(pixels_[id][j].y); pview.push_back(dense[id]);
+          pxyz.push_back(pts3d_[id][j].x); pxyz.push_back(pts3d_[id][j].y); pxyz.push_back(pts3d_[id][j].z);
+        }
+    ptzba_problem p{};
+    p.factor_type = (int)type_;
+    p.num_views = (int)view_of.size(); p.num_tracks = (int)track_ids.size(); p.num_obs = (int)oview.size(); p.num_pts3d = (int)pview.size();
+    p.intr = intr.data(); p.ext = ext.data(); p.obs_uv = uv.data(); p.obs_view = oview.data(); p.obs_track = otrack.data(); p.track_weight = weight.data();
+    p.pt_uv = puv.data(); p.pt_xyz = pxyz.data(); p.pt_view = pview.data(); p.tlw0 = tlw_param_.data();
+    ptz_solver_options o;
+    ptz_solver_options_default(&o);
+    o.max_num_iterations = max_iter_;
+    std::vector<double> cams_w(21 * view_of.size()), rays_w(3 * std::max<size_t>(track_ids.size(), 1));
+    ptzba_result r{};
+    r.cams_world = cams_w.data(); r.rays_world = rays_w.data();
+    last_status_ = ptzba_solve(&p, &o, &r);
+    if (last_status_ != PTZ_OK) return false;
+    init_reproj_error_all_ = r.init_reproj_error_all; final_reproj_error_all_ = r.final_reproj_error_all;
+    final_reproj_error_2d2d_ = r.final_reproj_error_2d2d; final_reproj_error_2d3d_ = r.final_reproj_error_2d3d;
+    num_iterations_ = r.num_iterations;
+    if (r.termination != PTZ_CONVERGENCE) return false;  // .cc:482-487: outputs untouched
+    for (size_t k = 0; k < view_of.size(); ++k) cameras[view_of[k]].FromKrt21(&cams_w[21 * k]);
+    rays.clear();
+    rays.resize(num_cams_);
+    for (size_t t = 0; t < track_ids.size(); ++t) {
+      const Vec3 rw{{rays_w[3 * t], rays_w[3 * t + 1], rays_w[3 * t + 2]}};
+      for (const auto& it : tracks_.at(track_ids[t])) rays[it.first].emplace_back(track_ids[t], rw, features_[it.first].keypoints[it.second].pt);
+    }
+    return true;
+  }
+
+  double final_reproj_error_all() const { return final_reproj_error_all_; }
+  double final_reproj_error_2d2d() const { return final_reproj_error_2d2d_; }
+  double final_reproj_error_2d3d() const { return final_reproj_error_2d3d_; }
+  void SetSharedIntrinsics(const std::vector<long>& shared_ic_ids) {
+    if (shared_ic_ids.size() != cameras_.size()) return;  // .cc:499-502
+    shared_ic_ids_ = shared_ic_ids;
+  }
+  void SetInitTransLocalToWorld(const double tlw[6]) { tlw_param_.assign(tlw, tlw + 6); }  // see the header comment
+  static void T_l_w(const double* tlw, Mat33& R_l_w, Vec3& t_l_w) {                         // .cc:507-513
+    ptz::rodrigues_jac(tlw, R_l_w.data(), nullptr);
+    t_l_w = Vec3{{tlw[3], tlw[4], tlw[5]}};
+  }
+  const Tracks& tracks() const { return tracks_; }
+  int num_iterations() const { return num_iterations_; }
+  int last_status() const { return last_status_; }
+
+ private:
+  void InitIds(const std::unordered_set<long>& cam_ids) {
+    if (cam_ids.empty()) for (size_t i = 0; i < cameras_.size(); ++i) cam_ids_.insert((long)i);
+    else cam_ids_ = cam_ids;
+    shared_ic_ids_.resize(cameras_.size());
+    std::iota(shared_ic_ids_.begin(), shared_ic_ids_.end(), 0);
+  }
+  bool CheckValid() const {  // .cc:515-535
+    if (num_cams_ == 0 || features_.size() != num_cams_ || max_iter_ <= 0) return false;
+    if (!pixels_.empty()) {
+      if (pixels_.size() != num_cams_ || pts3d_.size() != num_cams_) return false;
+      for (size_t i = 0; i < num_cams_; ++i) if (pixels_[i].size() != pts3d_[i].size()) return false;
+    }
+    return true;
+  }
+  void FindTracks() {  // .cc:537-552
+    TracksBuilder b;
+    b.Build(matches_info_);
+    b.Filter(4);
+    b.ExportToSTL(tracks_);
+  }
+  bool isCandidate(long id) const { return cam_ids_.find(id) != cam_ids_.end(); }
+
+  std::vector<Camera> cameras_;
+  std::vector<ImageFeatures> features_;
+  std::vector<MatchesInfo> matches_info_;
+  std::vector<std::vector<Point2f>> pixels_;
+  std::vector<std::vector<Point3d>> pts3d_;
+  size_t num_cams_ = 0;
+  std::unordered_set<long> cam_ids_;
+  std::vector<long> shared_ic_ids_;
+  FACTOR_TYPE type_;
+  std::vector<double> tlw_param_ = std::vector<double>(6, 0.0);
+  Tracks tracks_;
+  int max_iter_ = 100, num_iterations_ = 0, last_status_ = 0;
+  double init_reproj_error_all_ = 0, final_reproj_error_all_ = 0, final_reproj_error_2d2d_ = 0, final_reproj_error_2d3d_ = 0;
+};
+
+class KRTOptimizer {
+ public:
+  enum FACTOR_TYPE { F, FDist, Fxfy, FxfyDist };  // krt_optimizer.h:110 (order differs from the C enum: mapped below)
+
+  KRTOptimizer(int max_iter, double max_reproj_error, FACTOR_TYPE factor_type)
+      : factor_type_(factor_type), max_iter_(max_iter), max_reproj_error_(max_reproj_error) {}
+
+  void SetInitParams(const Mat33& K, const Mat33& R, const Vec3& t, const Vec5& dist) { cam_curr_world_ = Camera(K, R, t, dist); }  // .cc:257-263
+  void Add2d2dConstraints(const Camera& cam_ref, const std::vector<KeyPoint>& kpts_ref, const std::vector<KeyPoint>& kpts_curr,
+                          const std::vector<DMatch>& matches) {  // .cc:265-348
+    cam_ref_ = cam_ref;
+    uv1_.clear(); uv2_.clear();
+    for (const auto& m : matches) {
+      uv1_.push_back(kpts_ref[m.queryIdx].pt.x); uv1_.push_back(kpts_ref[m.queryIdx].pt.y);
+      uv2_.push_back(kpts_curr[m.trainIdx].pt.x); uv2_.push_back(kpts_curr[m.trainIdx].pt.y);
+    }
+  }
+  bool Solve(Mat33& K, Mat33& R, Vec3& t, Vec5& dist) {  // .cc:385-404
+    double ref[21], init[21], out[21];
+    cam_ref_.ToKrt21(ref);
+    cam_curr_world_.ToKrt21(init);
+    const int64_t off[2] = {0, (int64_t)(uv1_.size() / 2)};
+    static const int kMap[4] = {PTZ_KRT_F, PTZ_KRT_FDIST, PTZ_KRT_FXFY, PTZ_KRT_FXFYDIST};
+    ptzreloc_batch b{};
+    b.factor_type = kMap[(int)factor_type_]; b.num_queries = 1; b.match_offset = off; b.uv_ref = uv1_.data(); b.uv_cur = uv2_.data();
+    b.ref_cam = ref; b.init_cam = init; b.max_iter = max_iter_; b.max_reproj_error = max_reproj_error_;
+    int32_t ok = 0, term = 0, nit = 0;
+    ptzreloc_result r{};
+    r.cam = out; r.success = &ok; r.termination = &term; r.num_iter = &nit;
+    ptz_solver_options o;
+    ptz_solver_options_default(&o);
+    if (ptzreloc_solve_batch(&b, &o, &r) != PTZ_OK) return false;
+    num_iter_ = nit;
+    if (!ok) return false;  // CheckResults (.cc:504-533) ran on the device
+    Camera c;
+    c.FromKrt21(out);
+    K = c.K(); R = c.R(); t = c.t(); dist = c.dist();
+    return true;
+  }
+  void SetFixedFocal() { set_fixed_focal_ = true; }  // a flag nothing reads, as in the reference (.cc:502)
+  int num_iter_ = 0;
+
+ private:
+  Camera cam_curr_world_, cam_ref_;
+  std::vector<float> uv1_, uv2_;
+  bool set_fixed_focal_ = false;
+  FACTOR_TYPE factor_type_ = F;
+  int max_iter_ = 100;
+  double max_reproj_error_ = 50;
+};
+
+}  // namespace ptzcalib
+#endif  // PTZCALIB_B200_HPP

@@ -35,6 +35,9 @@ constexpr int kTrk = 8;
 // chunk p of every thread in the same bank group: rotate by the thread index.  9- and 10-chunk records spread by themselves.
 template <int NCL>
 __device__ __forceinline__ int rec_swz(int t, int p) { return NCL == 4 ? (p ^ (t & 7)) : p; }
+// same rule keyed on the number C of 16-byte chunks per record
+template <int C>
+__device__ __forceinline__ int chunk_swz(int t, int p) { return C == 8 ? (p ^ (t & 7)) : p; }
 
 // -------------------------------------------------------------------------------------------------------------
 // stage 1
@@ -61,10 +64,23 @@ __global__ void __launch_bounds__(kChunk) k_resjac(const int* __restrict__ chunk
   typedef Dims<NCL> D;
   __shared__ ViewTab svt;
   __shared__ double ssc[NCL];
-  __shared__ double sred[D::NPART * (kChunk / 32)];
-  __shared__ double2 srec[kChunk * (D::RS / 2)];
+  // one buffer, used first to stage the records for the coalesced write-out, then as scratch of the block reduction
+  constexpr int kRecBytes = kChunk * D::RS * 8, kRedBytes = (D::NPART * (kChunk + 4) + D::NPART) * 8;
+  __shared__ __align__(16) unsigned char sbuf[kRecBytes > kRedBytes ? kRecBytes : kRedBytes];
+  double2* srec = reinterpret_cast<double2*>(sbuf);
+  double* sred = reinterpret_cast<double*>(sbuf);
   const int chunk = blockIdx.x;
   const int view = chunk_view[chunk], begin = chunk_begin[chunk], cnt = chunk_cnt[chunk];
+  // issue the per-observation gathers before waiting for the view table
+  float2 uv = make_float2(0.f, 0.f);
+  double4 t0 = make_double4(0, 0, 1, 0), t1 = make_double4(1, 1, 1, 0);
+  if (threadIdx.x < cnt) {
+    const int o = begin + threadIdx.x;
+    uv = o_uv[o];
+    const int p = o_track[o];
+    t0 = *reinterpret_cast<const double4*>(trk + (size_t)p * kTrk);
+    t1 = *reinterpret_cast<const double4*>(trk + (size_t)p * kTrk + 4);
+  }
   if (threadIdx.x < 48) reinterpret_cast<double*>(&svt)[threadIdx.x] = reinterpret_cast<const double*>(vt + view)[threadIdx.x];
   if (threadIdx.x < NCL) ssc[threadIdx.x] = scale_cam[view * NCL + threadIdx.x];
   __syncthreads();
@@ -72,11 +88,6 @@ __global__ void __launch_bounds__(kChunk) k_resjac(const int* __restrict__ chunk
 #pragma unroll
   for (int i = 0; i < D::NPART; ++i) acc[i] = 0.0;
   if (threadIdx.x < cnt) {
-    const int o = begin + threadIdx.x;
-    const float2 uv = o_uv[o];
-    const int p = o_track[o];
-    const double4 t0 = *reinterpret_cast<const double4*>(trk + (size_t)p * kTrk);
-    const double4 t1 = *reinterpret_cast<const double4*>(trk + (size_t)p * kTrk + 4);
     const double ray[3] = {t0.x, t0.y, t0.z};
     double dz[3] = {0, 0, 0};
     if (TYPE == BA_PTZRAY_DIST_DISP) { dz[0] = disp[0]; dz[1] = disp[1]; dz[2] = disp[2]; }
@@ -106,17 +117,19 @@ __global__ void __launch_bounds__(kChunk) k_resjac(const int* __restrict__ chunk
     for (int a = 0; a < NCL; ++a) acc[D::NU + a] = F[a] * r[0] + F[NCL + a] * r[1];
     acc[D::NU + NCL] = 0.5 * (r[0] * r[0] + r[1] * r[1]);
   }
-  block_sum<D::NPART>(acc, sred);  // (its barriers also publish srec)
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < D::NPART; ++i) part[(size_t)chunk * D::NPART + i] = acc[i];
-  }
+  __syncthreads();
   // the chunk's records are contiguous in global memory: write them out as consecutive 16-byte chunks
   double2* gout = reinterpret_cast<double2*>(rec + (size_t)begin * D::RS);
   const int nch = cnt * (D::RS / 2);
   for (int gch = threadIdx.x; gch < nch; gch += kChunk) {
     const int t = gch / (D::RS / 2), pch = gch % (D::RS / 2);
     gout[gch] = srec[t * (D::RS / 2) + rec_swz<NCL>(t, pch)];
+  }
+  __syncthreads();
+  block_sum_sm<D::NPART, kChunk>(acc, sred);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < D::NPART; ++i) part[(size_t)chunk * D::NPART + i] = acc[i];
   }
 }
 
@@ -234,29 +247,42 @@ __global__ void k_track_factor(int P, const int* __restrict__ t_off, const doubl
 // per observation (one thread each; one CTA per chunk of one view, so records stream and the view's Schur terms reduce in
 // the CTA): What = (F^T E) L^-T, q = What t; chunk partials of sum What What^T (upper) and sum q for k_schur_diag
 template <int NCL>
-__global__ void __launch_bounds__(kChunk) k_obs_what(const int* __restrict__ chunk_begin, const int* __restrict__ chunk_cnt, const int* __restrict__ o_track,
+__global__ void __launch_bounds__(kChunk, 4) k_obs_what(const int* __restrict__ chunk_begin, const int* __restrict__ chunk_cnt, const int* __restrict__ o_track,
                                                       const double* __restrict__ rec, const double* __restrict__ Lt, double* __restrict__ What,
                                                       double* __restrict__ wpart) {
   typedef Dims<NCL> D;
-  constexpr int NV = D::NU + NCL;
-  __shared__ double sred[NV * (kChunk / 32)];
+  constexpr int NV = D::NU + NCL, RC = D::RS / 2, WC = D::WS / 2;
+  constexpr int kStageBytes = kChunk * (RC + WC) * 16, kRedBytes = (NV * (kChunk + 4) + NV) * 8;
+  __shared__ __align__(16) unsigned char sbuf[kStageBytes > kRedBytes ? kStageBytes : kRedBytes];
+  double2* srec = reinterpret_cast<double2*>(sbuf);
+  double2* sw = srec + kChunk * RC;
+  double* sred = reinterpret_cast<double*>(sbuf);  // reused after the staged data has been written out
   const int chunk = blockIdx.x, begin = chunk_begin[chunk], cnt = chunk_cnt[chunk];
+  // the chunk's records are contiguous: coalesced 16-byte loads into (swizzled) shared memory
+  const double2* gin = reinterpret_cast<const double2*>(rec + (size_t)begin * D::RS);
+  for (int gch = threadIdx.x; gch < cnt * RC; gch += kChunk) {
+    const int t = gch / RC, pch = gch % RC;
+    srec[t * RC + chunk_swz<RC>(t, pch)] = gin[gch];
+  }
+  // per-track factor: gather while the records land
+  double2 l01 = make_double2(1, 0), l23 = make_double2(1, 0), l45 = make_double2(0, 1), l67 = make_double2(0, 0), l89 = make_double2(0, 0);
+  if (threadIdx.x < cnt) {
+    const double2* lp = reinterpret_cast<const double2*>(Lt + (size_t)o_track[begin + threadIdx.x] * 10);
+    l01 = lp[0]; l23 = lp[1]; l45 = lp[2]; l67 = lp[3]; l89 = lp[4];
+  }
+  __syncthreads();
   double acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = 0.0;
   if (threadIdx.x < cnt) {
-    const int o = begin + threadIdx.x;
-    const int p = o_track[o];
-    const double2* lp = reinterpret_cast<const double2*>(Lt + (size_t)p * 10);
-    const double2 l01 = lp[0], l23 = lp[1], l45 = lp[2], l67 = lp[3], l89 = lp[4];
-    const double L0 = l01.x, L1 = l01.y, L2 = l23.x, L3 = l23.y, L4 = l45.x, L5 = l45.y, t0 = l67.x, t1 = l67.y, t2 = l89.x;
-    const double i00 = 1.0 / L0, i11 = 1.0 / L2, i22 = 1.0 / L5;
-    const double2* rp = reinterpret_cast<const double2*>(rec + (size_t)o * D::RS);
-    const double2 e01 = rp[1], e23 = rp[2], e45 = rp[3];
+    const int t = threadIdx.x;
+    const double L1 = l01.y, L3 = l23.y, L4 = l45.x, t0 = l67.x, t1 = l67.y, t2 = l89.x;
+    const double i00 = 1.0 / l01.x, i11 = 1.0 / l23.x, i22 = 1.0 / l45.y;
+    const double2 e01 = srec[t * RC + chunk_swz<RC>(t, 1)], e23 = srec[t * RC + chunk_swz<RC>(t, 2)], e45 = srec[t * RC + chunk_swz<RC>(t, 3)];
     const double a0 = e01.x, a1 = e01.y, a2 = e23.x, b0 = e23.y, b1 = e45.x, b2 = e45.y;
     double Fv[2 * NCL];
 #pragma unroll
-    for (int a = 0; a < NCL; ++a) { const double2 f = rp[4 + a]; Fv[2 * a] = f.x; Fv[2 * a + 1] = f.y; }
+    for (int a = 0; a < NCL; ++a) { const double2 f = srec[t * RC + chunk_swz<RC>(t, 4 + a)]; Fv[2 * a] = f.x; Fv[2 * a + 1] = f.y; }
     double w[D::WS];
 #pragma unroll
     for (int a = 0; a < NCL; ++a) {
@@ -267,16 +293,22 @@ __global__ void __launch_bounds__(kChunk) k_obs_what(const int* __restrict__ chu
       acc[D::NU + a] = x0 * t0 + x1 * t1 + x2 * t2;  // q_a
     }
     if (D::WS > 3 * NCL) w[D::WS - 1] = 0.0;
-    double2* wo = reinterpret_cast<double2*>(What + (size_t)o * D::WS);
 #pragma unroll
-    for (int k = 0; k < D::WS / 2; ++k) wo[k] = make_double2(w[2 * k], w[2 * k + 1]);
+    for (int k = 0; k < WC; ++k) sw[t * WC + chunk_swz<WC>(t, k)] = make_double2(w[2 * k], w[2 * k + 1]);
     int k = 0;
 #pragma unroll
     for (int a = 0; a < NCL; ++a)
 #pragma unroll
       for (int b = a; b < NCL; ++b) acc[k++] = w[3 * a] * w[3 * b] + w[3 * a + 1] * w[3 * b + 1] + w[3 * a + 2] * w[3 * b + 2];
   }
-  block_sum<NV>(acc, sred);
+  __syncthreads();
+  double2* gout = reinterpret_cast<double2*>(What + (size_t)begin * D::WS);
+  for (int gch = threadIdx.x; gch < cnt * WC; gch += kChunk) {
+    const int t = gch / WC, pch = gch % WC;
+    gout[gch] = sw[t * WC + chunk_swz<WC>(t, pch)];
+  }
+  __syncthreads();
+  block_sum_sm<NV, kChunk>(acc, sred);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) wpart[(size_t)chunk * NV + i] = acc[i];

@@ -128,6 +128,37 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* sm) {
   }
   __syncthreads();
 }
+// block-wide sum of NV values per thread through shared memory (NT threads): NV stores, NT/8 loads per partial and 3 shuffle
+// steps instead of 10 shuffles per value.  Result valid in thread 0.  sm must hold NV*(NT+4)+NV doubles.  Fixed order.
+template <int NV, int NT>
+__device__ __forceinline__ void block_sum_sm(double (&v)[NV], double* sm) {
+  constexpr int LD = NT + 4;  // row padding: the four rows a warp sums at once fall into different banks
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) sm[i * LD + t] = v[i];
+  __syncthreads();
+  double* res = sm + NV * LD;
+  for (int u0 = 0; u0 < NV * 8; u0 += NT) {  // trip count uniform over the block: every lane reaches the shuffles
+    const int u = u0 + t;
+    const bool valid = u < NV * 8;
+    const int val = valid ? (u >> 3) : 0, seg = u & 7;
+    double sacc = 0;
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < NT / 8; ++k) sacc += sm[val * LD + k * 8 + seg];
+    }
+    sacc += __shfl_xor_sync(0xffffffffu, sacc, 4);
+    sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+    sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+    if (valid && seg == 0) res[val] = sacc;
+  }
+  __syncthreads();
+  if (t == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = res[i];
+  }
+  __syncthreads();
+}
 #endif
 
 }  // namespace ptz

@@ -163,7 +163,8 @@ def run_ours(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     # timings accumulate over the handle's life: the timed region is the difference
-    st = dict(ms_run=st_b["ms_run"] - st_a["ms_run"], pcg_iterations=st_b["pcg_iterations"], lm_iterations=max(st_b["lm_iterations"], 1), kernels={})
+    st = dict(ms_run=st_b["ms_run"] - st_a["ms_run"], pcg_iterations=st_b["pcg_iterations"] - st_a["pcg_iterations"],
+              lm_iterations=max(st_b["lm_iterations"] - st_a["lm_iterations"], 1), kernels={})
     for name, kb in st_b["kernels"].items():
         ka = st_a["kernels"].get(name, dict(ms=0.0, launches=0))
         if kb["launches"] > ka["launches"]:
@@ -245,7 +246,8 @@ def run_ours(args):
                                    f"tolerances, PCG tol {args.pcg_tol:g}; inputs larger than L2 (records {prob.M * 128 / 1e6:.0f} MB)",
                        "views": prob.V, "obs_per_gpu": prob.M, "parallelism": f"obs-sharded x{world}" if world > 1 else "single GPU"},
             "lm_iters_per_sec": round(done / (dev_ms * 1e-3), 2), "solves_in_timed_region": solves, "wall_seconds": round(wall, 4),
-            "pcg_iterations_per_step": round(last.linear_solver_iterations / max(last.num_iterations, 1), 1) if last else None,
+            "pcg_iterations_per_step": round(st["pcg_iterations"] / st["lm_iterations"], 1),
+            "us_per_pcg_iteration": round(1e3 * kernels["pcg"]["ms"] / max(st["pcg_iterations"], 1), 3) if "pcg" in kernels else None,
             "rj_mobs_per_sec": round(prob.M / (rj["avg_us"]) , 1) if rj else None,
             "gpu_launches": launches, "kernels": table, "roofline": roofline, "e2e": e2e, "reloc": reloc, "cpu_baseline": cpu, "clocks": clocks,
         }

@@ -562,6 +562,7 @@ struct CgArgs {
   double* partial;         // [2][gridDim][2]
   unsigned int* bar;       // grid barrier counter, zeroed before the launch
   int smem_blocks;         // blocks of S (and their column indices) each warp keeps in shared memory for the whole solve
+  int debug;               // timing experiments only (PTZ_CG_DEBUG): 1 = skip the sparse product, 2 = skip the grid barrier
   int max_iter; double tol;
   int* out_info;           // [0] iterations, [1] status (0 converged, 1 hit cap, 2 breakdown)
   double* out_res;         // [0] |r~| / |b~|
@@ -597,11 +598,12 @@ __device__ __forceinline__ void grid_reduce2(double& a, double& b, double* parti
   ++epoch;
 }
 
-template <int NCL>
-__global__ void __launch_bounds__(256) k_cg(CgArgs A) {
+// MAXT = CTA width (256 / 512 / 1024 threads): wide CTAs keep one row per warp on larger systems (one CTA per SM either way)
+template <int NCL, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
   constexpr int SLOTS = 32 / NCL, NB = NCL * NCL;
   extern __shared__ double cg_smem[];
-  __shared__ double sred[8][2];
+  __shared__ double sred[MAXT / 32][2];
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;
   const int gw = blockIdx.x * wpb + wid, nw = gridDim.x * wpb;
   const int la = lane % NCL, ls = lane / NCL;
@@ -644,33 +646,45 @@ __global__ void __launch_bounds__(256) k_cg(CgArgs A) {
         const int b0 = A.rowptr[row], nblk = A.rowptr[row + 1] - b0;
         double sum = 0;
         {
-          // every lane of a slot fetches ONE entry of the neighbour's (r, w, s) -- 3 loads, each 32-byte sector requested once --
-          // forms its entry of r' and the NCL lanes exchange by shuffle; lanes beyond SLOTS*NCL idle along (uniform trip count)
-          const int nsteps = (nblk + SLOTS - 1) / SLOTS;
+          // Every lane of a slot fetches ONE entry of the neighbour's (r, w, s) -- 3 loads, each 32-byte sector requested once --
+          // forms its entry of r' and the NCL lanes of the slot exchange by shuffle.  Branch-free: lanes without a block read
+          // their own row (valid memory) and discard; the raw loads of CH steps are issued before any is consumed.
+          constexpr int CH = 4;
+          const int nsteps = (A.debug & 1) ? 0 : (nblk + SLOTS - 1) / SLOTS;
+          const int lim = lact ? nblk : 0;
           const int base = ls * NCL;
-#pragma unroll 4
-          for (int t = 0; t < nsteps; ++t) {
-            const int k = t * SLOTS + ls;
-            const bool on = lact && k < nblk;
-            const int idx = bi + k;
-            const bool hit = on && idx < ncached;
-            double mine = 0.0;
-            if (on) {
-              const int c = hit ? cs[idx] : __ldg(A.col + b0 + k);
-              const double* q = so + (size_t)c * 3 * NCL + la;
-              mine = __ldcg(q) - alpha * (__ldcg(q + NCL) + beta * __ldcg(q + 2 * NCL));
+          const bool cached = bi + nblk <= ncached;  // uniform over the warp
+          const int* ci = cached ? (cs + bi) : nullptr;
+          for (int t0 = 0; t0 < nsteps; t0 += CH) {
+            int off[CH];
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+              const int k = (t0 + u) * SLOTS + ls;
+              int c = row;
+              if (k < lim) c = cached ? ci[k] : __ldg(A.col + b0 + k);
+              off[u] = c * (3 * NCL) + la;
             }
-            double rj[NCL];
+            double rr[CH], ww[CH], ss[CH];
 #pragma unroll
-            for (int j = 0; j < NCL; ++j) rj[j] = __shfl_sync(0xffffffffu, mine, (base + j) & 31);
-            if (hit) {
-              const double* B = Bs + (size_t)idx * NB + la * NCL;
+            for (int u = 0; u < CH; ++u) { rr[u] = __ldcg(so + off[u]); ww[u] = __ldcg(so + off[u] + NCL); ss[u] = __ldcg(so + off[u] + 2 * NCL); }
 #pragma unroll
-              for (int j = 0; j < NCL; ++j) sum += B[j] * rj[j];
-            } else if (on) {
-              const double* B = A.Sval + (size_t)(b0 + k) * NB + la * NCL;
+            for (int u = 0; u < CH; ++u) {
+              const int k = (t0 + u) * SLOTS + ls;
+              const double mine = rr[u] - alpha * (ww[u] + beta * ss[u]);
+              double rj[NCL];
 #pragma unroll
-              for (int j = 0; j < NCL; ++j) sum += __ldg(B + j) * rj[j];
+              for (int j = 0; j < NCL; ++j) rj[j] = __shfl_sync(0xffffffffu, mine, (base + j) & 31);
+              if (k < lim) {
+                if (cached) {
+                  const double* B = Bs + (size_t)(bi + k) * NB + la * NCL;
+#pragma unroll
+                  for (int j = 0; j < NCL; ++j) sum += B[j] * rj[j];
+                } else {
+                  const double* B = A.Sval + (size_t)(b0 + k) * NB + la * NCL;
+#pragma unroll
+                  for (int j = 0; j < NCL; ++j) sum += __ldg(B + j) * rj[j];
+                }
+              }
             }
           }
         }
@@ -711,7 +725,7 @@ __global__ void __launch_bounds__(256) k_cg(CgArgs A) {
         g += rn * rn; d += tot * rn;
       }
     }
-    grid_reduce2(g, d, A.partial, A.bar, epoch, sred);
+    if (A.debug & 2) { g = 1.0 / (it + 1.0); d = 1.0; __syncthreads(); } else grid_reduce2(g, d, A.partial, A.bar, epoch, sred);
     gamma_last = g;
     if (it == 0) {
       gamma0 = g;

@@ -7,6 +7,7 @@
 #include <math.h>
 #include <nccl.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <chrono>
@@ -152,13 +153,17 @@ struct BaSolver : BaSolverBase {
   size_t sys_n = 0;
   double* h_scalars = nullptr;  // pinned
   int* h_info = nullptr;        // pinned: pcg info(2), fail(1)
-  int nblk_ray = 0, nblk_cam = 0, cg_cap = 1;
+  int nblk_ray = 0, nblk_cam = 0, cg_cap = 1, cg_wpb = 8, cg_grid = 1;
+  const void* cg_kernel() const {
+    return cg_wpb == 8 ? (const void*)k_cg<NCL, 256> : cg_wpb == 16 ? (const void*)k_cg<NCL, 512> : (const void*)k_cg<NCL, 1024>;
+  }
 
   // LM state (names follow ceres::internal::TrustRegionMinimizer / LevenbergMarquardtStrategy)
   double radius = 0, decrease_factor = 2.0, x_cost = 0, x_norm = 0, min_cost = 0, initial_cost = 0, grad_max = 0;
   bool reuse_diagonal = false, last_successful = true, started = false, finished = false;
   int iteration = 0, num_consecutive_invalid = 0, termination = PTZ_NO_CONVERGENCE;
   int num_successful = 0, num_unsuccessful = 0, lin_iters_total = 0, jac_evals = 0, cost_evals = 0;
+  long long life_pcg = 0, life_lm = 0;  // since create, not cleared by reset (bench.py takes differences)
   std::vector<ptz_iter_log> log;
 
   BaSolver(const ptzba_problem* prob, const ptz_solver_options* o) {
@@ -210,8 +215,13 @@ struct BaSolver : BaSolverBase {
     if (g_nccl.world > 1 && A > 0) throw CudaError(PTZ_ERR_UNSUPPORTED, "2d-3d terms with a sharded problem");
     n = V * NCL + nb;
     {
-      // blocks of S a warp of the CG kernel owns (rows gw, gw+nw, ...), and how many of them fit 200 KB of shared memory
-      const int nrows = V + (nb > 0 ? 1 : 0), grid = std::min(num_sms, cdiv(nrows, 8)), nw = grid * 8;
+      // CG launch shape: one CTA per SM, as many warps per CTA (8/16/32) as it takes to give every warp at most one row
+      // where possible; then how many blocks of S each warp can keep in 200 KB of shared memory
+      const int nrows = V + (nb > 0 ? 1 : 0);
+      const int need = cdiv(nrows, num_sms);
+      cg_wpb = need <= 8 ? 8 : (need <= 16 ? 16 : 32);
+      cg_grid = std::min(num_sms, cdiv(nrows, cg_wpb));
+      const int nw = cg_grid * cg_wpb;
       int worst = 0;
       for (int w = 0; w < nw; ++w) {
         int c = 0;
@@ -219,10 +229,10 @@ struct BaSolver : BaSolverBase {
         worst = std::max(worst, c);
       }
       const size_t per_block = NCL * NCL * sizeof(double) + sizeof(int);
-      const int fit = (int)((200 * 1024) / (8 * per_block));
+      const int fit = (int)((200 * 1024) / (cg_wpb * per_block));
       cg_cap = std::max(1, std::min(worst, fit));
-      const size_t cg_smem = (size_t)8 * cg_cap * per_block + 16;
-      PTZ_CUDA(cudaFuncSetAttribute((const void*)k_cg<NCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg_smem));
+      const size_t cg_smem = (size_t)cg_wpb * cg_cap * per_block + 16;
+      PTZ_CUDA(cudaFuncSetAttribute(cg_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg_smem));
     }
     upload(prob);
     PTZ_CUDA(cudaStreamSynchronize(stream));
@@ -471,15 +481,14 @@ struct BaSolver : BaSolverBase {
     a.st0 = d_cgstate.p; a.st1 = d_cgstate.p + 3 * (size_t)n; a.x = d_cgxp.p; a.p = d_cgxp.p + n;
     a.partial = d_pcg_partial.p; a.bar = d_bar.p; a.max_iter = opt.pcg_max_iterations; a.tol = opt.pcg_rel_tolerance;
     a.out_info = d_pcg_info.p; a.out_res = d_pcg_res.p;
-    const int nrows = V + (nb > 0 ? 1 : 0);
-    int grid = std::min(num_sms, cdiv(nrows, 8));
     // shared-memory residency of S: every warp keeps up to cg_cap blocks (+ column indices) of its rows for the whole solve
     a.smem_blocks = cg_cap;
-    const size_t cg_smem = (size_t)8 * cg_cap * (NCL * NCL * sizeof(double) + sizeof(int)) + 16;
+    { const char* e = getenv("PTZ_CG_DEBUG"); a.debug = e ? atoi(e) : 0; }
+    const size_t cg_smem = (size_t)cg_wpb * cg_cap * (NCL * NCL * sizeof(double) + sizeof(int)) + 16;
     void* args[] = {&a};
     PTZ_TIMED(PTZ_K_PCG, {
       PTZ_CUDA(cudaMemsetAsync(d_bar.p, 0, sizeof(unsigned int), s));
-      PTZ_CUDA(cudaLaunchCooperativeKernel((void*)k_cg<NCL>, dim3(grid), dim3(256), args, cg_smem, s));
+      PTZ_CUDA(cudaLaunchCooperativeKernel(cg_kernel(), dim3(cg_grid), dim3(32 * cg_wpb), args, cg_smem, s));
       k_unscale<NCL><<<cdiv(V + nb, 128), 128, 0, s>>>(V, nb, d_Linv.p, d_Linv_b.p, d_cgxp.p, d_y.p);
     });
     // ---- stage 4
@@ -591,6 +600,7 @@ struct BaSolver : BaSolverBase {
       bool ok = compute_step_and_candidate(&lin);
       reuse_diagonal = true;
       lin_iters_total += lin;
+      life_pcg += lin; ++life_lm;
       const double* S = h_scalars;
       double model_cost_change = S[S_DM_RAY] + S[S_DM_CAM] + S[S_DM_B];
       if (ok && !(std::isfinite(model_cost_change) && std::isfinite(S[S_STEP2_RAY]) && std::isfinite(S[S_STEP2_CAM]))) ok = false;
@@ -797,7 +807,7 @@ struct BaSolver : BaSolverBase {
   void stage_times(ptzba_stage_times* t) override {
     for (int i = 0; i < PTZ_K_COUNT; ++i) { t->ms_kernel[i] = clk.ms[i]; t->launches[i] = clk.launches[i]; }
     t->ms_run = clk.ms_run;
-    t->lm_iterations = (int)log.size() - 1; t->pcg_iterations = lin_iters_total; t->jacobian_evals = jac_evals; t->cost_evals = cost_evals;
+    t->lm_iterations = (int)life_lm; t->pcg_iterations = (int)life_pcg; t->jacobian_evals = jac_evals; t->cost_evals = cost_evals;
   }
 };
 

@@ -149,7 +149,7 @@ def test_handle_reuse_and_stage_times():
     assert a.final_cost == c.final_cost  # bit-reproducible: every reduction has a fixed order
     assert b.num_iterations == 3
     t = h.stage_times()
-    assert t["launches_total"] > 0 and t["ms_run"] > 0 and t["ms_kernels_total"] <= t["ms_run"] and t["lm_iterations"] == c.num_iterations
+    assert t["launches_total"] > 0 and t["ms_run"] > 0 and t["ms_kernels_total"] <= t["ms_run"] and t["lm_iterations"] >= c.num_iterations
     assert {"resjac", "track_solve", "schur_diag", "schur_offdiag", "pcg", "track_backsub", "cost"} <= set(t["kernels"])
     h.close()
 

@@ -29,13 +29,13 @@ template <int TYPE>
 __global__ void __launch_bounds__(128) k_pts(PtsArgs a) {
   constexpr int NCL = ba_ncl(TYPE);
   const int nb = a.nb, RW = 2 + 2 * NCL + 2 * nb;
-  __shared__ double sR[9], sdR[27], st[3];
+  __shared__ double sR[9], sdR[9], st[3];
   if (threadIdx.x == 0) {
     double w[3] = {a.tlw[0], a.tlw[1], a.tlw[2]};
-    double R[9], dR[27];
-    rodrigues_jac(w, R, dR);
+    double R[9], Jl[9];
+    rodrigues_jl(w, R, Jl);
     for (int i = 0; i < 9; ++i) sR[i] = R[i];
-    for (int i = 0; i < 27; ++i) sdR[i] = dR[i];
+    for (int i = 0; i < 9; ++i) sdR[i] = Jl[i];
     st[0] = a.tlw[3]; st[1] = a.tlw[4]; st[2] = a.tlw[5];
   }
   __syncthreads();

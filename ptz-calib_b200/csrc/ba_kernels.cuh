@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kChunk) k_resjac(const int* __restrict__ chunk
     t0 = *reinterpret_cast<const double4*>(trk + (size_t)p * kTrk);
     t1 = *reinterpret_cast<const double4*>(trk + (size_t)p * kTrk + 4);
   }
-  if (threadIdx.x < 48) reinterpret_cast<double*>(&svt)[threadIdx.x] = reinterpret_cast<const double*>(vt + view)[threadIdx.x];
+  if (threadIdx.x < kViewTabDoubles) reinterpret_cast<double*>(&svt)[threadIdx.x] = reinterpret_cast<const double*>(vt + view)[threadIdx.x];
   if (threadIdx.x < NCL) ssc[threadIdx.x] = scale_cam[view * NCL + threadIdx.x];
   __syncthreads();
   double acc[D::NPART];
@@ -861,7 +861,7 @@ __global__ void __launch_bounds__(kChunk) k_cost(const int* __restrict__ chunk_v
   __shared__ double sred[2 * (kChunk / 32)];
   const int chunk = blockIdx.x;
   const int view = chunk_view[chunk], begin = chunk_begin[chunk], cnt = chunk_cnt[chunk];
-  if (threadIdx.x < 48) reinterpret_cast<double*>(&svt)[threadIdx.x] = reinterpret_cast<const double*>(vt + view)[threadIdx.x];
+  if (threadIdx.x < kViewTabDoubles) reinterpret_cast<double*>(&svt)[threadIdx.x] = reinterpret_cast<const double*>(vt + view)[threadIdx.x];
   __syncthreads();
   double acc[2] = {0, 0};
   if (threadIdx.x < cnt) {

@@ -25,12 +25,13 @@ PTZ_HD constexpr int ba_ncl(int type) { return type == BA_PTZRAY ? 4 : (type == 
 // per-view table: everything a thread needs about its view, computed once per evaluation
 struct ViewTab {
   double R[9];      // cv::Rodrigues(rvec)
-  double dR[27];    // dR/dw_k, k = 0..2, row-major 3x3 each
+  double Jl[9];     // left Jacobian of SO(3) at rvec, row-major: d(R n)/dw_k = (Jl e_k) x (R n)
   double fx, fy, cx, cy;
   double k1, k2, k3, p1, p2;  // hand-written factors read dist as (k1,k2,k3,p1,p2): ptzray_optimizer.cc:108-109
-  double pad[3];
+  double pad[5];
 };
-static_assert(sizeof(ViewTab) == 48 * 8, "ViewTab is 48 doubles");
+constexpr int kViewTabDoubles = 32;
+static_assert(sizeof(ViewTab) == kViewTabDoubles * 8, "ViewTab is 32 doubles");
 
 // R(w) = I + a[w]x + b[w]x^2 and its derivatives.  a = sin t/t, b = (1-cos t)/t^2; da = a'(t)/t, db = b'(t)/t.
 // Series below t^2 = 1e-2 (truncation < 3e-18), closed forms above.  Same function as cv::Rodrigues; OpenCV
@@ -73,12 +74,43 @@ PTZ_HD void rodrigues_jac(const double w[3], double R[9], double dR[27]) {
   }
 }
 
+// R(w) and the left Jacobian J_l(w) = I + b[w]x + c[w]x^2, b = (1-cos t)/t^2, c = (t - sin t)/t^3.  For any vector n,
+// d(R(w) n)/dw_k = (J_l e_k) x (R(w) n): the rotation-vector derivative without the 27-entry dR/dw table.
+PTZ_HD void rodrigues_jl(const double w[3], double R[9], double Jl[9]) {
+  const double x = w[0], y = w[1], z = w[2];
+  const double t2 = x * x + y * y + z * z;
+  double a, b, c;
+  if (t2 < 1e-2) {
+    a = 1.0 + t2 * (-1.0 / 6 + t2 * (1.0 / 120 + t2 * (-1.0 / 5040 + t2 * (1.0 / 362880))));
+    b = 0.5 + t2 * (-1.0 / 24 + t2 * (1.0 / 720 + t2 * (-1.0 / 40320 + t2 * (1.0 / 3628800))));
+    c = 1.0 / 6 + t2 * (-1.0 / 120 + t2 * (1.0 / 5040 + t2 * (-1.0 / 362880 + t2 * (1.0 / 39916800))));
+  } else {
+    const double t = sqrt(t2);
+    const double s = sin(t), co = cos(t);
+    a = s / t;
+    b = (1.0 - co) / t2;
+    c = (1.0 - a) / t2;
+  }
+  const double K[9] = {0, -z, y, z, 0, -x, -y, x, 0};
+  const double K2[9] = {x * x - t2, x * y, x * z, x * y, y * y - t2, y * z, x * z, y * z, z * z - t2};
+  for (int i = 0; i < 9; ++i) { R[i] = a * K[i] + b * K2[i]; if (Jl) Jl[i] = b * K[i] + c * K2[i]; }
+  R[0] += 1.0; R[4] += 1.0; R[8] += 1.0;
+  if (Jl) { Jl[0] += 1.0; Jl[4] += 1.0; Jl[8] += 1.0; }
+}
+// derivative of X = R n w.r.t. w_k from the k-th column of Jl:  (Jl e_k) x X
+PTZ_HD void dX_dw(const double Jl[9], int k, double X, double Y, double Z, double& dX, double& dY, double& dZ) {
+  const double j0 = Jl[k], j1 = Jl[3 + k], j2 = Jl[6 + k];
+  dX = j1 * Z - j2 * Y;
+  dY = j2 * X - j0 * Z;
+  dZ = j0 * Y - j1 * X;
+}
+
 PTZ_HD void make_view_tab(const double intr[9], const double ext[6], ViewTab* vt, bool with_jac) {
-  rodrigues_jac(ext, vt->R, with_jac ? vt->dR : nullptr);
-  if (!with_jac) for (int i = 0; i < 27; ++i) vt->dR[i] = 0.0;
+  rodrigues_jl(ext, vt->R, vt->Jl);
+  (void)with_jac;
   vt->fx = intr[0]; vt->fy = intr[1]; vt->cx = intr[2]; vt->cy = intr[3];
   vt->k1 = intr[4]; vt->k2 = intr[5]; vt->k3 = intr[6]; vt->p1 = intr[7]; vt->p2 = intr[8];
-  vt->pad[0] = vt->pad[1] = vt->pad[2] = 0.0;
+  for (int i = 0; i < 5; ++i) vt->pad[i] = 0.0;
 }
 
 // Brown model of the hand-written factors and its 2x2 Jacobian
@@ -139,7 +171,6 @@ PTZ_HD void ba_obs(const ViewTab& vt, const double ray[3], const double disp[3],
     Z = Z + (disp[0] + disp[1] * fx + disp[2] * fx * fx);
     dZ_df = disp[1] + 2.0 * disp[2] * fx;
   }
-  (void)Zr;
   const double iz = 1.0 / Z;
   const double x = X * iz, y = Y * iz;
   Brown bw;
@@ -161,12 +192,10 @@ PTZ_HD void ba_obs(const ViewTab& vt, const double ray[3], const double disp[3],
   ++c;
   if (TYPE == BA_PTZRAY_FXFY_DIST) { F[c] = 0.0; F[NCL + c] = -bw.yd; ++c; }
   if (TYPE != BA_PTZRAY) { F[c] = -(fx * x * bw.r2); F[NCL + c] = -(fy * y * bw.r2); ++c; }
-  // rotation: dX/dw_k = dR_k n
+  // rotation: dX/dw_k = (Jl e_k) x (R n)   (X, Y, Zr: before any displacement)
   for (int k = 0; k < 3; ++k) {
-    const double* D = vt.dR + 9 * k;
-    const double dX = D[0] * n[0] + D[1] * n[1] + D[2] * n[2];
-    const double dY = D[3] * n[0] + D[4] * n[1] + D[5] * n[2];
-    const double dZ = D[6] * n[0] + D[7] * n[1] + D[8] * n[2];
+    double dX, dY, dZ;
+    dX_dw(vt.Jl, k, X, Y, Zr, dX, dY, dZ);
     F[c + k] = -(ux * dX + uy * dY + uz * dZ);
     F[NCL + c + k] = -(vx * dX + vy * dY + vz * dZ);
   }
@@ -196,14 +225,15 @@ PTZ_HD void ba_obs(const ViewTab& vt, const double ray[3], const double disp[3],
 //   Jd[2][3]  d r / d disp (DISP only)
 // -----------------------------------------------------------------------------------------------------------
 template <bool DISP, bool JAC>
-PTZ_HD void ba_pt(const ViewTab& vt, const double Rl[9], const double dRl[27], const double tl[3], const double disp[3], const double Xw[3], double u,
-                  double v, double r[2], double* Jc, double* Jt, double* Jd) {
+PTZ_HD void ba_pt(const ViewTab& vt, const double Rl[9], const double Jll[9] /* left Jacobian at tlw rvec */, const double tl[3], const double disp[3],
+                  const double Xw[3], double u, double v, double r[2], double* Jc, double* Jt, double* Jd) {
   const double* R = vt.R;
   double Xl[3];
   for (int i = 0; i < 3; ++i) Xl[i] = Rl[3 * i] * Xw[0] + Rl[3 * i + 1] * Xw[1] + Rl[3 * i + 2] * Xw[2] + tl[i];
   const double X = R[0] * Xl[0] + R[1] * Xl[1] + R[2] * Xl[2];
   const double Y = R[3] * Xl[0] + R[4] * Xl[1] + R[5] * Xl[2];
   double Z = R[6] * Xl[0] + R[7] * Xl[1] + R[8] * Xl[2];
+  const double Zr = Z;
   const double fx = vt.fx, fy = vt.fy;
   double dZ_df = 0.0;
   if (DISP) { Z = Z + (disp[0] + disp[1] * fx + disp[2] * fx * fx); dZ_df = disp[1] + 2.0 * disp[2] * fx; }
@@ -218,17 +248,15 @@ PTZ_HD void ba_pt(const ViewTab& vt, const double Rl[9], const double dRl[27], c
   Jc[1] = 0.0;                   Jc[6 + 1] = -bw.yd;
   Jc[2] = -(fx * x * bw.r2);     Jc[6 + 2] = -(fy * y * bw.r2);
   for (int k = 0; k < 3; ++k) {
-    const double* D = vt.dR + 9 * k;
-    const double dX = D[0] * Xl[0] + D[1] * Xl[1] + D[2] * Xl[2];
-    const double dY = D[3] * Xl[0] + D[4] * Xl[1] + D[5] * Xl[2];
-    const double dZ = D[6] * Xl[0] + D[7] * Xl[1] + D[8] * Xl[2];
+    double dX, dY, dZ;
+    dX_dw(vt.Jl, k, X, Y, Zr, dX, dY, dZ);
     Jc[3 + k] = -(ux * dX + uy * dY + uz * dZ);
     Jc[6 + 3 + k] = -(vx * dX + vy * dY + vz * dZ);
   }
-  for (int k = 0; k < 3; ++k) {  // tlw rotation: dXl = dRl_k Xw, dXcam = R dXl
-    const double* D = dRl + 9 * k;
+  const double Rw[3] = {Xl[0] - tl[0], Xl[1] - tl[1], Xl[2] - tl[2]};  // R_lw X_w
+  for (int k = 0; k < 3; ++k) {  // tlw rotation: dXl = (Jll e_k) x (R_lw X_w), dXcam = R dXl
     double d[3];
-    for (int i = 0; i < 3; ++i) d[i] = D[3 * i] * Xw[0] + D[3 * i + 1] * Xw[1] + D[3 * i + 2] * Xw[2];
+    dX_dw(Jll, k, Rw[0], Rw[1], Rw[2], d[0], d[1], d[2]);
     const double dX = R[0] * d[0] + R[1] * d[1] + R[2] * d[2];
     const double dY = R[3] * d[0] + R[4] * d[1] + R[5] * d[2];
     const double dZ = R[6] * d[0] + R[7] * d[1] + R[8] * d[2];
@@ -302,12 +330,12 @@ PTZ_HD bool krt_precompute(int type, const double refK4[4], const double refd[5]
 
 // camera-side constants of one KRT evaluation
 struct KrtCam {
-  double R[9], dR[27];
+  double R[9], Jl[9];
   double fx, fy, cx, cy, k1, k2, k3, p1, p2;
 };
 template <int TYPE>
 PTZ_HD void krt_make_cam(const double cam[15], KrtCam* kc, bool with_jac) {
-  rodrigues_jac(cam + 4, kc->R, with_jac ? kc->dR : nullptr);
+  rodrigues_jl(cam + 4, kc->R, with_jac ? kc->Jl : nullptr);
   kc->fx = cam[0];
   kc->fy = (TYPE == KRT_FXFY || TYPE == KRT_FXFYDIST) ? cam[1] : cam[0];
   kc->cx = cam[2]; kc->cy = cam[3];
@@ -335,10 +363,8 @@ PTZ_HD void krt_obs(const KrtCam& kc, const double n[3], double u2, double v2, d
   J[c] = -bw.xd; J[NF + c] = FXFY ? 0.0 : -bw.yd; ++c;
   if (FXFY) { J[c] = 0.0; J[NF + c] = -bw.yd; ++c; }
   for (int k = 0; k < 3; ++k) {
-    const double* D = kc.dR + 9 * k;
-    const double dX = D[0] * n[0] + D[1] * n[1] + D[2] * n[2];
-    const double dY = D[3] * n[0] + D[4] * n[1] + D[5] * n[2];
-    const double dZ = D[6] * n[0] + D[7] * n[1] + D[8] * n[2];
+    double dX, dY, dZ;
+    dX_dw(kc.Jl, k, X, Y, Z, dX, dY, dZ);
     J[c + k] = -(ux * dX + uy * dY + uz * dZ);
     J[NF + c + k] = -(vx * dX + vy * dY + vz * dZ);
   }

@@ -32,8 +32,8 @@ void hm_ba_obs(int type, const double* intr, const double* ext, const double* ra
 void hm_ba_pt(int disp_on, const double* intr, const double* ext, const double* tlw, const double* disp, const float* uv, const double* xyz, double* r,
               double* Jc, double* Jt, double* Jd) {
   ViewTab vt; make_view_tab(intr, ext, &vt, true);
-  double Rl[9], dRl[27];
-  rodrigues_jac(tlw, Rl, dRl);
+  double Rl[9], dRl[9];
+  rodrigues_jl(tlw, Rl, dRl);
   if (disp_on) ba_pt<true, true>(vt, Rl, dRl, tlw + 3, disp, xyz, uv[0], uv[1], r, Jc, Jt, Jd);
   else ba_pt<false, true>(vt, Rl, dRl, tlw + 3, disp, xyz, uv[0], uv[1], r, Jc, Jt, Jd);
 }

@@ -10,13 +10,16 @@
 namespace ptz {
 
 struct PtsArgs {
-  int A, nav, nb, fy_in_border;     // fy_in_border = 1 for PTZRay / PTZRayDist
+  int A, nav, nb, fy_in_border;     // fy_in_border = 1 for the factor types that tie fy := fx in the ray terms
+  int bo_tlw, bo_fy, bo_disp;       // first border column of tlw(6) / fy(nav) / disp(3), or -1
+  const int* ann_strip;             // strip row of annotated view k inside C (k itself, or the view id when every view has a strip)
+  const double* disp;               // current disp[3] (PTZRayDistDisp) or nullptr
   const float2* uv; const double* xyz; const int* view;   // sorted by view
   const int* ann_view; const int* ann_off;                // [nav], [nav+1]
   const ViewTab* vt; const double* tlw;                   // current parameters
   const double* scale_cam; const double* scale_b;
   double* scratch;                  // [A][2 + 2*NCL + 2*nb] scaled rows
-  double* raw;                      // optional [A][2 + 12 + 12]: r, Jc(2x6), Jt(2x6) unscaled (ptzba_eval), or nullptr
+  double* raw;                      // optional [A][2 + 12 + 12 + 6]: r, Jc(2x6), Jt(2x6), Jd(2x3) unscaled (ptzba_eval), or nullptr
   // outputs
   double* U; double* g; double* gabs;   // += on the annotated views
   double* C;                        // [nav][NCL][nb]
@@ -46,13 +49,19 @@ __global__ void __launch_bounds__(128) k_pts(PtsArgs a) {
     while (a.ann_view[k] != v) ++k;
     const ViewTab vt = a.vt[v];
     const double Xw[3] = {a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]};
-    double r[2], Jc[12], Jt[12];
-    const double dz[3] = {0, 0, 0};
-    ba_pt<false, true>(vt, sR, sdR, st, dz, Xw, (double)a.uv[i].x, (double)a.uv[i].y, r, Jc, Jt, nullptr);
+    double r[2], Jc[12], Jt[12], Jd[6] = {0, 0, 0, 0, 0, 0};
+    double dz[3] = {0, 0, 0};
+    if (TYPE == BA_PTZRAY_DIST_DISP) {
+      dz[0] = a.disp[0]; dz[1] = a.disp[1]; dz[2] = a.disp[2];
+      ba_pt<true, true>(vt, sR, sdR, st, dz, Xw, (double)a.uv[i].x, (double)a.uv[i].y, r, Jc, Jt, Jd);
+    } else {
+      ba_pt<false, true>(vt, sR, sdR, st, dz, Xw, (double)a.uv[i].x, (double)a.uv[i].y, r, Jc, Jt, nullptr);
+    }
     if (a.raw) {
-      double* o = a.raw + (size_t)i * 26;
+      double* o = a.raw + (size_t)i * 32;
       o[0] = r[0]; o[1] = r[1];
       for (int j = 0; j < 12; ++j) { o[2 + j] = Jc[j]; o[14 + j] = Jt[j]; }
+      for (int j = 0; j < 6; ++j) o[26 + j] = Jd[j];
     }
     double* row = a.scratch + (size_t)i * RW;
     row[0] = r[0]; row[1] = r[1];
@@ -67,8 +76,9 @@ __global__ void __launch_bounds__(128) k_pts(PtsArgs a) {
       else if (TYPE == BA_PTZRAY_FXFY_DIST) { for (int j = 0; j < 6; ++j) live[n++] = jc[j]; }
       else { live[n++] = jc[0]; live[n++] = jc[2]; live[n++] = jc[3]; live[n++] = jc[4]; live[n++] = jc[5]; }
       for (int c = 0; c < NCL; ++c) Fc[rr * NCL + c] = live[c] * a.scale_cam[v * NCL + c];
-      for (int j = 0; j < 6; ++j) Bj[rr * nb + j] = Jt[6 * rr + j] * a.scale_b[j];
-      if (a.fy_in_border) Bj[rr * nb + 6 + k] = jc[1] * a.scale_b[6 + k];
+      for (int j = 0; j < 6; ++j) Bj[rr * nb + a.bo_tlw + j] = Jt[6 * rr + j] * a.scale_b[a.bo_tlw + j];
+      if (a.fy_in_border) Bj[rr * nb + a.bo_fy + k] = jc[1] * a.scale_b[a.bo_fy + k];
+      if (TYPE == BA_PTZRAY_DIST_DISP) for (int j = 0; j < 3; ++j) Bj[rr * nb + a.bo_disp + j] = Jd[3 * rr + j] * a.scale_b[a.bo_disp + j];
     }
   }
   __syncthreads();
@@ -78,8 +88,7 @@ __global__ void __launch_bounds__(128) k_pts(PtsArgs a) {
     double Uadd[NCL * NCL], gadd[NCL];
     for (int i = 0; i < NCL * NCL; ++i) Uadd[i] = 0;
     for (int i = 0; i < NCL; ++i) gadd[i] = 0;
-    double* Ck = a.C + (size_t)k * NCL * nb;
-    for (int i = 0; i < NCL * nb; ++i) Ck[i] = 0;
+    double* Ck = a.C + (size_t)a.ann_strip[k] * NCL * nb;  // zeroed by the caller; the disp kernels add to it as well
     for (int i = a.ann_off[k]; i < a.ann_off[k + 1]; ++i) {
       const double* row = a.scratch + (size_t)i * RW;
       const double* Fc = row + 2;
@@ -106,7 +115,7 @@ __global__ void __launch_bounds__(128) k_pts(PtsArgs a) {
         const double* Bj = a.scratch + (size_t)p * RW + 2 + 2 * NCL;
         s += Bj[i] * Bj[j] + Bj[nb + i] * Bj[nb + j];
       }
-      a.Hbb[e] = s;
+      a.Hbb[e] += s;
     } else {
       const int i = e - nb * nb;
       for (int p = 0; p < a.A; ++p) {
@@ -114,8 +123,8 @@ __global__ void __launch_bounds__(128) k_pts(PtsArgs a) {
         const double* Bj = row + 2 + 2 * NCL;
         s += Bj[i] * row[0] + Bj[nb + i] * row[1];
       }
-      a.gb[i] = s;
-      a.gabs_b[i] = fabs(s / a.scale_b[i]);
+      a.gb[i] += s;
+      a.gabs_b[i] = fabs(a.gb[i] / a.scale_b[i]);
     }
   }
   if (threadIdx.x == 0) {
@@ -128,7 +137,7 @@ __global__ void __launch_bounds__(128) k_pts(PtsArgs a) {
 
 // cost of the annotated points at the candidate parameters (one warp)
 __global__ void k_pts_cost(int A, const float2* __restrict__ uv, const double* __restrict__ xyz, const int* __restrict__ view, const ViewTab* __restrict__ vt,
-                           const double* __restrict__ tlw, double* __restrict__ out2) {
+                           const double* __restrict__ tlw, const double* __restrict__ disp /* or nullptr */, double* __restrict__ out2) {
   __shared__ double sR[9], st[3];
   if (threadIdx.x == 0) {
     double w[3] = {tlw[0], tlw[1], tlw[2]}, R[9];
@@ -141,9 +150,14 @@ __global__ void k_pts_cost(int A, const float2* __restrict__ uv, const double* _
   for (int i = threadIdx.x; i < A; i += 32) {
     const ViewTab t = vt[view[i]];
     const double Xw[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
-    const double dz[3] = {0, 0, 0};
     double r[2];
-    ba_pt<false, false>(t, sR, nullptr, st, dz, Xw, (double)uv[i].x, (double)uv[i].y, r, nullptr, nullptr, nullptr);
+    if (disp) {
+      const double dz[3] = {disp[0], disp[1], disp[2]};
+      ba_pt<true, false>(t, sR, nullptr, st, dz, Xw, (double)uv[i].x, (double)uv[i].y, r, nullptr, nullptr, nullptr);
+    } else {
+      const double dz[3] = {0, 0, 0};
+      ba_pt<false, false>(t, sR, nullptr, st, dz, Xw, (double)uv[i].x, (double)uv[i].y, r, nullptr, nullptr, nullptr);
+    }
     s += r[0] * r[0] + r[1] * r[1];
   }
   s = warp_sum(s);
@@ -174,28 +188,157 @@ __global__ void k_border_system(int nb, const double* __restrict__ Hbb, const do
 }
 
 // candidate border parameters; part3 = {model cost change, |step|^2, |x_cand|^2} contributions (fy corrections included)
-__global__ void k_border_update(int nb, int nav, int fy_in_border, const int* __restrict__ ann_view, const double* __restrict__ yb,
+__global__ void k_border_update(int nb, int nav, int bo_tlw, int bo_fy, int bo_disp, const int* __restrict__ ann_view, const double* __restrict__ yb,
                                 const double* __restrict__ scale_b, const double* __restrict__ gb, const double* __restrict__ diag_b, double mu,
                                 const double* __restrict__ tlw, double* __restrict__ tlw_c, const double* __restrict__ intr, double* __restrict__ intr_c,
-                                double* __restrict__ part3) {
+                                const double* __restrict__ disp, double* __restrict__ disp_c, double* __restrict__ part3) {
   if (threadIdx.x != 0) return;
   double dm = 0, st = 0, xn = 0;
   for (int j = 0; j < nb; ++j) dm += 0.5 * yb[j] * (gb[j] + diag_b[j] / mu * yb[j]);
-  for (int j = 0; j < 6; ++j) {
-    const double c = tlw[j] + (-scale_b[j] * yb[j]);
-    tlw_c[j] = c;
-    st += (tlw[j] - c) * (tlw[j] - c);
-    xn += c * c;
-  }
-  if (fy_in_border)
+  if (bo_tlw >= 0)
+    for (int j = 0; j < 6; ++j) {
+      const double c = tlw[j] + (-scale_b[bo_tlw + j] * yb[bo_tlw + j]);
+      tlw_c[j] = c;
+      st += (tlw[j] - c) * (tlw[j] - c);
+      xn += c * c;
+    }
+  if (bo_fy >= 0)
     for (int k = 0; k < nav; ++k) {
       const int v = ann_view[k];
-      const double x = intr[9 * v + 1], c = x + (-scale_b[6 + k] * yb[6 + k]);
+      const double x = intr[9 * v + 1], c = x + (-scale_b[bo_fy + k] * yb[bo_fy + k]);
       intr_c[9 * v + 1] = c;
       st += (x - c) * (x - c);
       xn += c * c - x * x;  // k_cam_update counted the unchanged fy
     }
+  if (bo_disp >= 0)
+    for (int j = 0; j < 3; ++j) {
+      const double c = disp[j] + (-scale_b[bo_disp + j] * yb[bo_disp + j]);
+      disp_c[j] = c;
+      st += (disp[j] - c) * (disp[j] - c);
+      xn += c * c;
+    }
   part3[0] = dm; part3[1] = st; part3[2] = xn;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PTZRayDistDisp (ptzray_optimizer.cc:202-264): the global disp[3] block is touched by EVERY ray observation.  It lives in
+// the border; its per-observation Jacobian Fd (2x3, sqrt(w)- and Jacobi-scaled) is kept in recd[M][6].  This factor type
+// is not selected by the reference's apps and only meets small scenes, so these kernels are plain (one thread per view or
+// per track, fixed-order loops), not tuned.
+// ---------------------------------------------------------------------------------------------------------------------
+// per view: coupling strip C[v][a][disp] += sum F^T Fd, per-view partials of Hdd = sum Fd^T Fd (6) and gd = sum Fd^T r (3)
+template <int NCL>
+__global__ void k_disp_view(int V, const int* __restrict__ view_off, const double* __restrict__ rec, const double* __restrict__ recd, int nb, int bo_disp,
+                            double* __restrict__ C, double* __restrict__ dpart) {
+  typedef Dims<NCL> D;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  double c[NCL * 3], h[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+  for (int i = 0; i < NCL * 3; ++i) c[i] = 0;
+  for (int o = view_off[v]; o < view_off[v + 1]; ++o) {
+    const double* rp = rec + (size_t)o * D::RS;
+    const double* fd = recd + (size_t)o * 6;
+    for (int a = 0; a < NCL; ++a)
+      for (int j = 0; j < 3; ++j) c[a * 3 + j] += rp[8 + a] * fd[j] + rp[8 + NCL + a] * fd[3 + j];
+    int k = 0;
+    for (int i = 0; i < 3; ++i) {
+      g[i] += fd[i] * rp[0] + fd[3 + i] * rp[1];
+      for (int j = i; j < 3; ++j) h[k++] += fd[i] * fd[j] + fd[3 + i] * fd[3 + j];
+    }
+  }
+  for (int a = 0; a < NCL; ++a)
+    for (int j = 0; j < 3; ++j) C[((size_t)v * NCL + a) * nb + bo_disp + j] += c[a * 3 + j];
+  for (int i = 0; i < 6; ++i) dpart[(size_t)v * 9 + i] = h[i];
+  for (int i = 0; i < 3; ++i) dpart[(size_t)v * 9 + 6 + i] = g[i];
+}
+// one thread: sums the per-view partials in view order into the disp block of Hbb and gb
+__global__ void k_disp_total(int V, const double* __restrict__ dpart, int nb, int bo_disp, const double* __restrict__ scale_b, double* __restrict__ Hbb,
+                             double* __restrict__ gb, double* __restrict__ gabs_b) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int v = 0; v < V; ++v)
+    for (int i = 0; i < 9; ++i) s[i] += dpart[(size_t)v * 9 + i];
+  int k = 0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = i; j < 3; ++j) {
+      Hbb[(bo_disp + i) * nb + bo_disp + j] += s[k];
+      if (j != i) Hbb[(bo_disp + j) * nb + bo_disp + i] += s[k];
+      ++k;
+    }
+  for (int i = 0; i < 3; ++i) {
+    gb[bo_disp + i] += s[6 + i];
+    gabs_b[bo_disp + i] = fabs(gb[bo_disp + i] / scale_b[bo_disp + i]);
+  }
+}
+// per track (after k_track_factor): Wd = sum Fd^T E, Wdh = Wd L^-T (3x3), qd = Wdh t; Wdh[P][12]
+template <int NCL>
+__global__ void k_disp_track(int P, const int* __restrict__ t_off, const int* __restrict__ t_obs, const double* __restrict__ rec,
+                             const double* __restrict__ recd, const double* __restrict__ Lt, double* __restrict__ Wdh) {
+  typedef Dims<NCL> D;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  double w[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = t_off[p]; i < t_off[p + 1]; ++i) {
+    const int o = t_obs[i];
+    const double* rp = rec + (size_t)o * D::RS;   // E at rp[2..7]: E0[3], E1[3]
+    const double* fd = recd + (size_t)o * 6;
+    for (int a = 0; a < 3; ++a)
+      for (int j = 0; j < 3; ++j) w[a * 3 + j] += fd[a] * rp[2 + j] + fd[3 + a] * rp[5 + j];
+  }
+  const double* lt = Lt + (size_t)p * 10;
+  double* out = Wdh + (size_t)p * 12;
+  for (int a = 0; a < 3; ++a) {
+    const double x0 = w[a * 3] / lt[0], x1 = (w[a * 3 + 1] - lt[1] * x0) / lt[2], x2 = (w[a * 3 + 2] - lt[3] * x0 - lt[4] * x1) / lt[5];
+    out[a * 3] = x0; out[a * 3 + 1] = x1; out[a * 3 + 2] = x2;
+    out[9 + a] = x0 * lt[6] + x1 * lt[7] + x2 * lt[8];
+  }
+}
+// per view: Schur term of the camera-disp coupling  sum_o What_o Wdh_{p(o)}^T  (NCL x 3), subtracted from the strip's disp columns
+// of the working copy Cw (= C at the last Jacobian evaluation)
+template <int NCL>
+__global__ void k_disp_schur_view(int V, const int* __restrict__ view_off, const int* __restrict__ o_track, const double* __restrict__ What,
+                                  const double* __restrict__ Wdh, int nb, int bo_disp, const double* __restrict__ C, double* __restrict__ Cw) {
+  typedef Dims<NCL> D;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  double c[NCL * 3];
+  for (int i = 0; i < NCL * 3; ++i) c[i] = 0;
+  for (int o = view_off[v]; o < view_off[v + 1]; ++o) {
+    const double* w = What + (size_t)o * D::WS;
+    const double* wd = Wdh + (size_t)o_track[o] * 12;
+    for (int a = 0; a < NCL; ++a)
+      for (int j = 0; j < 3; ++j) c[a * 3 + j] += w[3 * a] * wd[3 * j] + w[3 * a + 1] * wd[3 * j + 1] + w[3 * a + 2] * wd[3 * j + 2];
+  }
+  for (int a = 0; a < NCL; ++a)
+    for (int j = 0; j < nb; ++j) {
+      double val = C[((size_t)v * NCL + a) * nb + j];
+      if (j >= bo_disp && j < bo_disp + 3) val -= c[a * 3 + (j - bo_disp)];
+      Cw[((size_t)v * NCL + a) * nb + j] = val;
+    }
+}
+// one thread: disp block of S_bb -= sum_p Wdh Wdh^T, rhs_disp -= sum_p qd, in track order
+__global__ void k_disp_schur_border(int P, const int* __restrict__ t_off, const double* __restrict__ Wdh, int nb, int bo_disp, double* __restrict__ Sbb,
+                                    double* __restrict__ rhs_b) {
+  // 9 threads: entry (i, j) of the 3x3 block; 3 more for the right-hand side; every sum in track order
+  const int e = threadIdx.x;
+  if (blockIdx.x != 0 || e >= 12) return;
+  double sacc = 0;
+  if (e < 9) {
+    const int i = e / 3, j = e % 3;
+    for (int p = 0; p < P; ++p) {
+      if (t_off[p] == t_off[p + 1]) continue;
+      const double* w = Wdh + (size_t)p * 12;
+      sacc += w[3 * i] * w[3 * j] + w[3 * i + 1] * w[3 * j + 1] + w[3 * i + 2] * w[3 * j + 2];
+    }
+    Sbb[(bo_disp + i) * nb + bo_disp + j] -= sacc;
+  } else {
+    const int i = e - 9;
+    for (int p = 0; p < P; ++p) {
+      if (t_off[p] == t_off[p + 1]) continue;
+      sacc += Wdh[(size_t)p * 12 + 9 + i];
+    }
+    rhs_b[bo_disp + i] -= sacc;
+  }
 }
 
 }  // namespace ptz

@@ -59,7 +59,8 @@ template <int TYPE>
 __global__ void __launch_bounds__(kChunk) k_resjac(const int* __restrict__ chunk_view, const int* __restrict__ chunk_begin, const int* __restrict__ chunk_cnt,
                                                    const float2* __restrict__ o_uv, const int* __restrict__ o_track, const ViewTab* __restrict__ vt,
                                                    const double* __restrict__ trk, const double* __restrict__ scale_cam, const double* __restrict__ disp,
-                                                   int weighted, double* __restrict__ rec, double* __restrict__ part) {
+                                                   int weighted, double* __restrict__ rec, double* __restrict__ part,
+                                                   double* __restrict__ recd /* PTZRayDistDisp: [M][6] d r/d disp */, const double* __restrict__ scale_d) {
   constexpr int NCL = ba_ncl(TYPE);
   typedef Dims<NCL> D;
   __shared__ ViewTab svt;
@@ -91,9 +92,14 @@ __global__ void __launch_bounds__(kChunk) k_resjac(const int* __restrict__ chunk
     const double ray[3] = {t0.x, t0.y, t0.z};
     double dz[3] = {0, 0, 0};
     if (TYPE == BA_PTZRAY_DIST_DISP) { dz[0] = disp[0]; dz[1] = disp[1]; dz[2] = disp[2]; }
-    double r[2], F[2 * NCL], E[6];
-    ba_obs<TYPE, true>(svt, ray, dz, (double)uv.x, (double)uv.y, r, F, E, nullptr);
+    double r[2], F[2 * NCL], E[6], Fd[6];
+    ba_obs<TYPE, true>(svt, ray, dz, (double)uv.x, (double)uv.y, r, F, E, TYPE == BA_PTZRAY_DIST_DISP ? Fd : nullptr);
     const double sw = weighted ? t0.w : 1.0;
+    if (TYPE == BA_PTZRAY_DIST_DISP) {
+      double* fo = recd + (size_t)(begin + threadIdx.x) * 6;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { fo[j] = Fd[j] * sw * scale_d[j]; fo[3 + j] = Fd[3 + j] * sw * scale_d[j]; }
+    }
     r[0] *= sw; r[1] *= sw;
     const double sr[3] = {t1.x * sw, t1.y * sw, t1.z * sw};
 #pragma unroll
@@ -759,7 +765,7 @@ template <int NCL>
 __global__ void k_track_backsub(int P, const int* __restrict__ t_off, const int* __restrict__ t_obs, const int* __restrict__ o_view,
                                 const double* __restrict__ What, const double* __restrict__ y, const double* __restrict__ Lt, const double* __restrict__ Vh,
                                 const double* __restrict__ diag_ray, double mu, const double* __restrict__ trk, double* __restrict__ trk_cand,
-                                double* __restrict__ part3) {
+                                double* __restrict__ part3, const double* __restrict__ Wdh /* or nullptr */, const double* __restrict__ ydisp) {
   typedef Dims<NCL> D;
   __shared__ double sred[3 * 8];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -796,6 +802,11 @@ __global__ void k_track_backsub(int P, const int* __restrict__ t_off, const int*
 #pragma unroll
           for (int a = 0; a < NCL; ++a) { const double ya = yv[u][a]; b0 -= wv[u][3 * a] * ya; b1 -= wv[u][3 * a + 1] * ya; b2 -= wv[u][3 * a + 2] * ya; }
         }
+      }
+      if (Wdh) {  // PTZRayDistDisp: - Wdh^T y_disp
+        const double* wd = Wdh + (size_t)p * 12;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { const double ya = ydisp[a]; b0 -= wd[3 * a] * ya; b1 -= wd[3 * a + 1] * ya; b2 -= wd[3 * a + 2] * ya; }
       }
       // L^T y = b
       const double y2 = b2 / lt[5], y1 = (b1 - lt[4] * y2) / lt[2], y0 = (b0 - lt[1] * y1 - lt[3] * y2) / lt[0];

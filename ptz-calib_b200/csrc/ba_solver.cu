@@ -116,9 +116,13 @@ struct BaSolver : BaSolverBase {
   static constexpr int NCL = ba_ncl(TYPE);
   typedef Dims<NCL> D;
   static constexpr bool kFyBorder = (TYPE != BA_PTZRAY_FXFY_DIST);
+  static constexpr bool kDisp = (TYPE == BA_PTZRAY_DIST_DISP);
 
   StreamHolder sh;       // first member: destroyed last, after every buffer allocated on its stream
   int V, P, M, A, nb = 0, nav = 0, n = 0;
+  int bo_tlw = -1, bo_fy = -1, bo_disp = -1;  // first border column of tlw(6) / fy(nav) / disp(3)
+  int ncpl = 0;                               // views with a coupling strip to the border (annotated ones, or all of them with disp)
+  std::vector<int> h_cpl_view, h_cpl_idx, h_ann_strip;
   ptz_solver_options opt;
   DevStructure ds;       // orderings + block pattern, device-resident
   std::vector<int> h_perm;  // view-major position -> caller's observation index (fetched lazily, ptzba_eval only)
@@ -140,9 +144,10 @@ struct BaSolver : BaSolverBase {
   DevBuf<ViewTab> d_vt;
   DevBuf<double> d_scale_cam, d_scale_b, d_rec, d_part, d_viewred, d_Vh, d_gmax_part, d_diag_ray, d_diag_cam, d_diag_b, d_Lt, d_What, d_q, d_sys, d_Linv,
       d_Linv_b, d_Sbb, d_Cs, d_cgstate, d_cgxp, d_y, d_pcg_partial, d_pcg_res, d_part3_ray, d_part3_cam, d_part3_b, d_cost_part, d_scalars, d_RiKi, d_pts_scratch, d_pts_raw,
-      d_pts_xyz, d_disp;
+      d_pts_xyz;
   DevBuf<float2> d_pts_uv;
-  DevBuf<int> d_pts_view, d_ann_view, d_ann_off, d_ann_idx, d_fail, d_pcg_info;
+  DevBuf<int> d_pts_view, d_ann_view, d_ann_off, d_ann_idx, d_fail, d_pcg_info, d_cpl_view, d_cpl_idx, d_ann_strip;
+  DevBuf<double> d_recd, d_dpart, d_Wdh, d_Cw, d_dispp[2], d_disp_init;
   DevBuf<unsigned int> d_bar;
   // views into d_viewred (all-reduced once per Jacobian evaluation): U | g | cost_view | C | Hbb | gb | cost_pts(2)
   double *p_U, *p_g, *p_cost_view, *p_C, *p_Hbb, *p_gb, *p_cost_pts, *p_gabs, *p_gabs_b;
@@ -209,10 +214,24 @@ struct BaSolver : BaSolverBase {
       }
       h_ann_off.push_back(A);
       nav = (int)h_ann_view.size();
-      nb = 6 + (kFyBorder ? nav : 0);
-      if (nb > kMaxBorder) throw CudaError(PTZ_ERR_UNSUPPORTED, "more than 26 annotated views");
+      bo_tlw = 0; nb = 6;
+      if (kFyBorder) { bo_fy = nb; nb += nav; }
     }
-    if (g_nccl.world > 1 && A > 0) throw CudaError(PTZ_ERR_UNSUPPORTED, "2d-3d terms with a sharded problem");
+    if (kDisp) { bo_disp = nb; nb += 3; }
+    if (nb > kMaxBorder) throw CudaError(PTZ_ERR_UNSUPPORTED, "border larger than 32 unknowns (too many annotated views)");
+    if (g_nccl.world > 1 && nb > 0) throw CudaError(PTZ_ERR_UNSUPPORTED, "2d-3d terms / disp block with a sharded problem");
+    h_ann_strip.resize(nav);
+    if (kDisp) {
+      ncpl = V;
+      h_cpl_view.resize(V); std::iota(h_cpl_view.begin(), h_cpl_view.end(), 0);
+      h_cpl_idx = h_cpl_view;
+      for (int k = 0; k < nav; ++k) h_ann_strip[k] = h_ann_view[k];
+    } else {
+      ncpl = nav;
+      h_cpl_view = h_ann_view;
+      h_cpl_idx = h_ann_idx;
+      for (int k = 0; k < nav; ++k) h_ann_strip[k] = k;
+    }
     n = V * NCL + nb;
     {
       // CG launch shape: one CTA per SM, as many warps per CTA (8/16/32) as it takes to give every warp at most one row
@@ -319,18 +338,30 @@ struct BaSolver : BaSolverBase {
       d_pts_xyz.upload(pxyz, s); d_pts_view.upload(pview, s);
       d_ann_view.upload(h_ann_view, s); d_ann_off.upload(h_ann_off, s);
       d_pts_scratch.alloc((size_t)A * (2 + 2 * NCL + 2 * nb), stream);
-      d_pts_raw.alloc((size_t)A * 26, stream);
+      d_pts_raw.alloc((size_t)A * 32, stream);
     }
     d_ann_idx.upload(h_ann_idx, s);
+    if (h_cpl_view.empty()) d_cpl_view.alloc(1, s); else d_cpl_view.upload(h_cpl_view, s);
+    d_cpl_idx.upload(h_cpl_idx, s);
+    if (h_ann_strip.empty()) d_ann_strip.alloc(1, s); else d_ann_strip.upload(h_ann_strip, s);
+    {
+      std::vector<double> z3(3, 0.0);
+      d_disp_init.upload(z3, s);
+      d_dispp[0].alloc(3, s); d_dispp[1].alloc(3, s);
+    }
+    if (kDisp) {
+      d_recd.alloc((size_t)std::max(M, 1) * 6, s); d_dpart.alloc((size_t)V * 9, s); d_Wdh.alloc((size_t)std::max(P, 1) * 12, s);
+      d_Cw.alloc((size_t)V * NCL * nb, s);
+    }
     // work buffers
     d_scale_cam.alloc((size_t)V * NCL, stream); d_scale_b.alloc(kMaxBorder, stream);
     d_rec.alloc((size_t)std::max(M, 1) * D::RS, stream);
     d_part.alloc((size_t)std::max(ds.nchunks, 1) * D::NPART, stream);
-    viewred_n = (size_t)V * NCL * NCL + (size_t)V * NCL + V + (size_t)nav * NCL * nb + (size_t)nb * nb + nb + 2;
+    viewred_n = (size_t)V * NCL * NCL + (size_t)V * NCL + V + (size_t)ncpl * NCL * nb + (size_t)nb * nb + nb + 2;
     d_viewred.alloc(viewred_n, stream);
     d_viewred.zero(s);
     p_U = d_viewred.p; p_g = p_U + (size_t)V * NCL * NCL; p_cost_view = p_g + (size_t)V * NCL; p_C = p_cost_view + V;
-    p_Hbb = p_C + (size_t)nav * NCL * nb; p_gb = p_Hbb + (size_t)nb * nb; p_cost_pts = p_gb + nb;
+    p_Hbb = p_C + (size_t)ncpl * NCL * nb; p_gb = p_Hbb + (size_t)nb * nb; p_cost_pts = p_gb + nb;
     d_gabs.alloc((size_t)V * NCL + kMaxBorder, stream);
     d_gabs.zero(s);
     p_gabs = d_gabs.p; p_gabs_b = d_gabs.p + (size_t)V * NCL;
@@ -345,7 +376,7 @@ struct BaSolver : BaSolverBase {
     d_sys.alloc(sys_n, stream);
     p_Sval = d_sys.p; p_rhs = p_Sval + (size_t)ds.nnzb * NCL * NCL;
     d_Linv.alloc((size_t)V * NCL * NCL, stream); d_Linv_b.alloc(kMaxBorder * kMaxBorder, stream); d_Sbb.alloc(kMaxBorder * kMaxBorder, stream);
-    d_Cs.alloc((size_t)std::max(nav, 1) * NCL * std::max(nb, 1), stream);
+    d_Cs.alloc((size_t)std::max(ncpl, 1) * NCL * std::max(nb, 1), stream);
     d_cgstate.alloc(6 * (size_t)n, stream); d_cgstate.zero(s);
     d_cgxp.alloc(2 * (size_t)n, stream); d_cgxp.zero(s);
     d_y.alloc(n, stream); d_y.zero(s);
@@ -356,7 +387,7 @@ struct BaSolver : BaSolverBase {
     d_part3_cam.alloc(3 * (size_t)nblk_cam, stream); d_part3_b.alloc(3, stream); d_part3_b.zero(s);
     d_cost_part.alloc(2 * (size_t)std::max(ds.nchunks, 1), stream); d_cost_part.zero(s);
     d_scalars.alloc(S_COUNT, stream); d_scalars.zero(s);
-    d_disp.alloc(3, stream); d_disp.zero(s);
+
     PTZ_CUDA(cudaMallocHost((void**)&h_scalars, S_COUNT * sizeof(double)));
     PTZ_CUDA(cudaMallocHost((void**)&h_info, 4 * sizeof(int)));
     reset();
@@ -367,6 +398,7 @@ struct BaSolver : BaSolverBase {
     PTZ_CUDA(cudaMemcpyAsync(d_intr[0].p, d_intr_init.p, 9 * (size_t)V * 8, cudaMemcpyDeviceToDevice, s));
     PTZ_CUDA(cudaMemcpyAsync(d_ext[0].p, d_ext_init.p, 6 * (size_t)V * 8, cudaMemcpyDeviceToDevice, s));
     PTZ_CUDA(cudaMemcpyAsync(d_tlw[0].p, d_tlw_init.p, 6 * 8, cudaMemcpyDeviceToDevice, s));
+    PTZ_CUDA(cudaMemcpyAsync(d_dispp[0].p, d_disp_init.p, 3 * 8, cudaMemcpyDeviceToDevice, s));
     for (int i = 0; i < 2; ++i) PTZ_CUDA(cudaMemcpyAsync(d_trk[i].p, d_trk_init.p, d_trk_init.n * 8, cudaMemcpyDeviceToDevice, s));
     cur = 0;
     started = finished = false;
@@ -381,9 +413,11 @@ struct BaSolver : BaSolverBase {
   void launch_resjac(int weighted) {
     cudaStream_t s = stream;
     PTZ_TIMED(PTZ_K_VIEW_PREP, k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[cur].p, d_ext[cur].p, d_vt.p, 1));
+    if (nb > 0) PTZ_CUDA(cudaMemsetAsync(p_C, 0, (viewred_n - (size_t)(p_C - d_viewred.p)) * sizeof(double), s));  // C | Hbb | gb | cost_pts accumulate
     if (ds.nchunks > 0)
       PTZ_TIMED(PTZ_K_RESJAC, k_resjac<TYPE><<<ds.nchunks, kChunk, 0, s>>>(ds.chunk_view.p, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_uv.p, ds.o_track.p, d_vt.p,
-                                                                             d_trk[cur].p, d_scale_cam.p, d_disp.p, weighted, d_rec.p, d_part.p));
+                                                                             d_trk[cur].p, d_scale_cam.p, d_dispp[cur].p, weighted, d_rec.p, d_part.p,
+                                                                             d_recd.p, d_scale_b.p + (kDisp ? bo_disp : 0)));
     PTZ_TIMED(PTZ_K_VIEW_FINALIZE,
               k_view_finalize<NCL><<<cdiv(V * D::NPART, 256), 256, 0, s>>>(V, ds.view_chunk_off.p, d_part.p, d_scale_cam.p, p_U, p_g, p_cost_view, p_gabs));
     if (P > 0)
@@ -391,11 +425,16 @@ struct BaSolver : BaSolverBase {
     if (A > 0) {
       PtsArgs a;
       a.A = A; a.nav = nav; a.nb = nb; a.fy_in_border = kFyBorder ? 1 : 0;
+      a.bo_tlw = bo_tlw; a.bo_fy = bo_fy; a.bo_disp = bo_disp; a.ann_strip = d_ann_strip.p; a.disp = d_dispp[cur].p;
       a.uv = d_pts_uv.p; a.xyz = d_pts_xyz.p; a.view = d_pts_view.p; a.ann_view = d_ann_view.p; a.ann_off = d_ann_off.p;
       a.vt = d_vt.p; a.tlw = d_tlw[cur].p; a.scale_cam = d_scale_cam.p; a.scale_b = d_scale_b.p; a.scratch = d_pts_scratch.p;
       a.raw = weighted ? nullptr : d_pts_raw.p;
       a.U = p_U; a.g = p_g; a.gabs = p_gabs; a.C = p_C; a.Hbb = p_Hbb; a.gb = p_gb; a.cost_pts = p_cost_pts; a.gabs_b = p_gabs_b;
       PTZ_TIMED(PTZ_K_PTS, k_pts<TYPE><<<1, 128, 0, s>>>(a));
+    }
+    if (kDisp) {
+      k_disp_view<NCL><<<cdiv(V, 64), 64, 0, s>>>(V, ds.view_off.p, d_rec.p, d_recd.p, nb, bo_disp, p_C, d_dpart.p);
+      k_disp_total<<<1, 32, 0, s>>>(V, d_dpart.p, nb, bo_disp, d_scale_b.p, p_Hbb, p_gb, p_gabs_b);
     }
     PTZ_CUDA(cudaGetLastError());
     if (g_nccl.world > 1) PTZ_TIMED(PTZ_K_ALLREDUCE, allreduce_sum(d_viewred.p, viewred_n, s));
@@ -456,6 +495,7 @@ struct BaSolver : BaSolverBase {
       PTZ_TIMED(PTZ_K_TRACK_SOLVE, {
         k_track_factor<<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, d_Vh.p, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_ray.p, d_Lt.p, d_fail.p);
         if (ds.nchunks > 0) k_obs_what<NCL><<<ds.nchunks, kChunk, 0, s>>>(ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_track.p, d_rec.p, d_Lt.p, d_What.p, d_q.p);
+        if (kDisp) k_disp_track<NCL><<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_rec.p, d_recd.p, d_Lt.p, d_Wdh.p);
       });
     PTZ_TIMED(PTZ_K_SCHUR_DIAG, k_schur_diag<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, ds.view_chunk_off.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal,
                                                                                opt.max_lm_diagonal, own, d_diag_cam.p, ds.diag_pos.p, p_Sval, p_rhs));
@@ -463,6 +503,10 @@ struct BaSolver : BaSolverBase {
       PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, k_schur_offdiag<NCL><<<cdiv(ds.nub, 8), 256, 0, s>>>(ds.nub, ds.pair_off.p, ds.pair_a.p, ds.pair_b.p, d_What.p,
                                                                                             ds.ub_pos.p, ds.ub_pos_t.p, p_Sval));
     if (nb > 0) k_border_system<<<1, 128, 0, s>>>(nb, p_Hbb, p_gb, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_b.p, d_Sbb.p, p_rhs + (size_t)V * NCL);
+    if (kDisp) {
+      k_disp_schur_view<NCL><<<cdiv(V, 64), 64, 0, s>>>(V, ds.view_off.p, ds.o_track.p, d_What.p, d_Wdh.p, nb, bo_disp, p_C, d_Cw.p);
+      k_disp_schur_border<<<1, 32, 0, s>>>(P, ds.t_off.p, d_Wdh.p, nb, bo_disp, d_Sbb.p, p_rhs + (size_t)V * NCL);
+    }
     PTZ_CUDA(cudaGetLastError());
     if (g_nccl.world > 1) PTZ_TIMED(PTZ_K_ALLREDUCE, allreduce_sum(d_sys.p, sys_n, s));
     PTZ_TIMED(PTZ_K_PRECOND, {
@@ -471,13 +515,14 @@ struct BaSolver : BaSolverBase {
       k_scale_system<NCL><<<cdiv(std::max(ds.nnzb, V), 128), 128, 0, s>>>(V, ds.nnzb, ds.blk_row.p, ds.s_col.p, d_Linv.p, p_Sval, p_rhs, d_cgstate.p,
                                                                             d_cgxp.p, d_cgxp.p + n);
       if (nb > 0)
-        k_scale_border<NCL><<<1, 128, 0, s>>>(V, nb, nav, d_ann_view.p, d_Linv.p, d_Linv_b.p, p_C, d_Cs.p, p_rhs, d_cgstate.p, d_cgxp.p, d_cgxp.p + n);
+        k_scale_border<NCL><<<1, 128, 0, s>>>(V, nb, ncpl, d_cpl_view.p, d_Linv.p, d_Linv_b.p, kDisp ? d_Cw.p : p_C, d_Cs.p, p_rhs, d_cgstate.p, d_cgxp.p,
+                                              d_cgxp.p + n);
     });
     // ---- stage 3
     CgArgs a;
     a.V = V; a.nb = nb; a.n = n;
     a.rowptr = ds.s_rowptr.p; a.col = ds.s_col.p; a.Sval = p_Sval;
-    a.nav = nav; a.ann_view = d_ann_view.p; a.ann_idx = d_ann_idx.p; a.C = d_Cs.p;
+    a.nav = ncpl; a.ann_view = d_cpl_view.p; a.ann_idx = d_cpl_idx.p; a.C = d_Cs.p;
     a.st0 = d_cgstate.p; a.st1 = d_cgstate.p + 3 * (size_t)n; a.x = d_cgxp.p; a.p = d_cgxp.p + n;
     a.partial = d_pcg_partial.p; a.bar = d_bar.p; a.max_iter = opt.pcg_max_iterations; a.tol = opt.pcg_rel_tolerance;
     a.out_info = d_pcg_info.p; a.out_res = d_pcg_res.p;
@@ -496,12 +541,13 @@ struct BaSolver : BaSolverBase {
     const double* y = d_y.p;
     if (P > 0)
       PTZ_TIMED(PTZ_K_TRACK_BACKSUB, k_track_backsub<NCL><<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, ds.o_view.p, d_What.p, y, d_Lt.p, d_Vh.p, d_diag_ray.p,
-                                                                                   mu, d_trk[cur].p, d_trk[nxt].p, d_part3_ray.p));
+                                                                                   mu, d_trk[cur].p, d_trk[nxt].p, d_part3_ray.p, kDisp ? d_Wdh.p : nullptr,
+                                                                                   y + (size_t)V * NCL + (kDisp ? bo_disp : 0)));
     PTZ_TIMED(PTZ_K_CAM_UPDATE, k_cam_update<TYPE><<<nblk_cam, 128, 0, s>>>(V, y, d_scale_cam.p, p_g, d_diag_cam.p, mu, ds.view_active.p, d_intr[cur].p,
                                                                             d_ext[cur].p, d_intr[nxt].p, d_ext[nxt].p, d_part3_cam.p));
     if (nb > 0)
-      k_border_update<<<1, 32, 0, s>>>(nb, nav, kFyBorder ? 1 : 0, d_ann_view.p, y + (size_t)V * NCL, d_scale_b.p, p_gb, d_diag_b.p, mu, d_tlw[cur].p,
-                                       d_tlw[nxt].p, d_intr[cur].p, d_intr[nxt].p, d_part3_b.p);
+      k_border_update<<<1, 32, 0, s>>>(nb, nav, bo_tlw, bo_fy, bo_disp, d_ann_view.p, y + (size_t)V * NCL, d_scale_b.p, p_gb, d_diag_b.p, mu, d_tlw[cur].p,
+                                       d_tlw[nxt].p, d_intr[cur].p, d_intr[nxt].p, d_dispp[cur].p, d_dispp[nxt].p, d_part3_b.p);
     launch_cost(nxt);
     launch_step_scalars();
     read_scalars();
@@ -517,8 +563,10 @@ struct BaSolver : BaSolverBase {
     PTZ_TIMED(PTZ_K_VIEW_PREP, k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[which].p, d_ext[which].p, d_vt.p, 0));
     if (ds.nchunks > 0)
       PTZ_TIMED(PTZ_K_COST, k_cost<TYPE><<<ds.nchunks, kChunk, 0, s>>>(ds.chunk_view.p, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_uv.p, ds.o_track.p, d_vt.p,
-                                                                         d_trk[which].p, d_disp.p, d_cost_part.p));
-    if (A > 0) k_pts_cost<<<1, 32, 0, s>>>(A, d_pts_uv.p, d_pts_xyz.p, d_pts_view.p, d_vt.p, d_tlw[which].p, d_scalars.p + S_COSTPTS_CAND);
+                                                                         d_trk[which].p, d_dispp[which].p, d_cost_part.p));
+    if (A > 0)
+      k_pts_cost<<<1, 32, 0, s>>>(A, d_pts_uv.p, d_pts_xyz.p, d_pts_view.p, d_vt.p, d_tlw[which].p, kDisp ? d_dispp[which].p : nullptr,
+                                  d_scalars.p + S_COSTPTS_CAND);
     PTZ_CUDA(cudaGetLastError());
   }
 
@@ -555,11 +603,13 @@ struct BaSolver : BaSolverBase {
     k_scalars<<<2, 1024, 0, stream>>>(J, d_scalars.p);
     PTZ_CUDA(cudaGetLastError());
     allreduce_sum(d_scalars.p + S_XN2_RAY, 1, stream);
-    double tl[6] = {0, 0, 0, 0, 0, 0};
+    double tl[6] = {0, 0, 0, 0, 0, 0}, dd[3] = {0, 0, 0};
     if (A > 0) d_tlw[cur].download(tl, 6, stream);
+    if (kDisp) d_dispp[cur].download(dd, 3, stream);
     read_scalars();
     double s = h_scalars[S_XN2_CAM] + h_scalars[S_XN2_RAY];
     if (A > 0) for (int j = 0; j < 6; ++j) s += tl[j] * tl[j];
+    for (int j = 0; j < 3; ++j) s += dd[j] * dd[j];
     return sqrt(s);
   }
 
@@ -687,7 +737,8 @@ struct BaSolver : BaSolverBase {
     out->final_reproj_error_2d2d = sqrt(h_scalars[S_RAW2_CAND] / n2);
     out->final_reproj_error_2d3d = A > 0 ? sqrt(h_scalars[S_RAWPTS_CAND] / A) : sqrt(0.0 / 0.0);
     // parameters
-    std::vector<double> intr(9 * (size_t)V), ext(6 * (size_t)V), tlw(6, 0.0);
+    std::vector<double> intr(9 * (size_t)V), ext(6 * (size_t)V), tlw(6, 0.0), dsp(3, 0.0);
+    d_dispp[cur].download(dsp.data(), 3, stream);
     d_intr[cur].download(intr.data(), intr.size(), stream);
     d_ext[cur].download(ext.data(), ext.size(), stream);
     d_tlw[cur].download(tlw.data(), 6, stream);
@@ -703,7 +754,7 @@ struct BaSolver : BaSolverBase {
     PTZ_CUDA(cudaStreamSynchronize(stream));
     if (out->intr) memcpy(out->intr, intr.data(), intr.size() * 8);
     if (out->ext) memcpy(out->ext, ext.data(), ext.size() * 8);
-    if (out->disp) out->disp[0] = out->disp[1] = out->disp[2] = 0.0;
+    if (out->disp) memcpy(out->disp, dsp.data(), 24);
     if (out->tlw) memcpy(out->tlw, tlw.data(), 48);
     // ObtainRefinedCameraParams (ptzray_optimizer.cc:672-766)
     double Rlw[9];
@@ -717,7 +768,9 @@ struct BaSolver : BaSolverBase {
         double R[9];
         rodrigues_jac(ex, R, nullptr);
         for (int r = 0; r < 3; ++r) {
-          c[13 + r] = R[3 * r] * tlw[3] + R[3 * r + 1] * tlw[4] + R[3 * r + 2] * tlw[5] + ex[3 + r];
+          // t.z carries the displacement polynomial (ptzray_optimizer.cc:693-694,714-715)
+          const double tz = (r == 2) ? (dsp[0] + dsp[1] * in[0] + dsp[2] * in[0] * in[0]) : 0.0;
+          c[13 + r] = R[3 * r] * tlw[3] + R[3 * r + 1] * tlw[4] + R[3 * r + 2] * tlw[5] + ex[3 + r] + tz;
           for (int q = 0; q < 3; ++q) c[4 + 3 * r + q] = R[3 * r] * Rlw[q] + R[3 * r + 1] * Rlw[3 + q] + R[3 * r + 2] * Rlw[6 + q];
         }
         for (int j = 0; j < 5; ++j) c[16 + j] = in[4 + j];
@@ -731,16 +784,18 @@ struct BaSolver : BaSolverBase {
 
   // ptzba_eval: raw residuals + analytic Jacobian in the caller's observation order, weighted cost and gradient
   void eval(const double* disp, ptzba_eval_out* out) override {
-    (void)disp;
     const int ncv = (TYPE == BA_PTZRAY) ? 5 : 6;
-    const int wo = ncv + 3, wp = ncv + 6;
+    const int dd = kDisp ? 3 : 0;
+    const int wo = ncv + 3 + dd, wp = ncv + 6 + dd;
     fill_ones(d_scale_cam.p, (size_t)V * NCL);
     fill_ones(d_scale_b.p, kMaxBorder);
+    if (kDisp && disp) { PTZ_CUDA(cudaMemcpyAsync(d_dispp[cur].p, disp, 24, cudaMemcpyHostToDevice, stream)); PTZ_CUDA(cudaStreamSynchronize(stream)); }
     // pass 1: unweighted, unscaled records
     launch_resjac(0);
-    std::vector<double> rec((size_t)std::max(M, 1) * D::RS), raw((size_t)std::max(A, 1) * 26);
+    std::vector<double> rec((size_t)std::max(M, 1) * D::RS), raw((size_t)std::max(A, 1) * 32), recd((size_t)std::max(M, 1) * 6, 0.0);
     d_rec.download(rec.data(), (size_t)M * D::RS, stream);
-    if (A > 0) d_pts_raw.download(raw.data(), (size_t)A * 26, stream);
+    if (kDisp && M > 0) d_recd.download(recd.data(), (size_t)M * 6, stream);
+    if (A > 0) d_pts_raw.download(raw.data(), (size_t)A * 32, stream);
     PTZ_CUDA(cudaStreamSynchronize(stream));
     // live column a -> column of the documented layout [fx, fy, (k1), w(3)]
     int live2col[NCL];
@@ -761,10 +816,11 @@ struct BaSolver : BaSolverBase {
           for (int c = 0; c < wo; ++c) o[c] = 0.0;
           for (int a = 0; a < NCL; ++a) o[live2col[a]] = r[8 + row * NCL + a];
           for (int j = 0; j < 3; ++j) o[ncv + j] = r[2 + row * 3 + j];
+          for (int j = 0; j < dd; ++j) o[ncv + 3 + j] = recd[(size_t)i * 6 + row * 3 + j];
         }
     }
     for (int i = 0; i < A; ++i) {
-      const double* r = &raw[(size_t)i * 26];
+      const double* r = &raw[(size_t)i * 32];
       const int k = h_pt_perm[i];
       if (out->residuals) { out->residuals[2 * (size_t)(M + k)] = r[0]; out->residuals[2 * (size_t)(M + k) + 1] = r[1]; }
       if (out->jac_pts)
@@ -776,6 +832,7 @@ struct BaSolver : BaSolverBase {
           if (ncv == 6) o[2] = jc[2];
           for (int j = 0; j < 3; ++j) o[ncv - 3 + j] = jc[3 + j];
           for (int j = 0; j < 6; ++j) o[ncv + j] = jt[j];
+          for (int j = 0; j < dd; ++j) o[ncv + 6 + j] = r[26 + 3 * row + j];
         }
     }
     // pass 2: weighted (still unscaled) -> cost and gradient
@@ -790,16 +847,17 @@ struct BaSolver : BaSolverBase {
     double cost = cp[0];
     for (int v = 0; v < V; ++v) cost += cv[v];
     out->cost = cost;
-    out->num_tangent = V * ncv + 3 * P + (A > 0 ? 6 : 0);
+    out->num_tangent = V * ncv + 3 * P + dd + (A > 0 ? 6 : 0);
     if (out->gradient) {
       for (int i = 0; i < out->num_tangent; ++i) out->gradient[i] = 0.0;
       for (int v = 0; v < V; ++v)
         for (int a = 0; a < NCL; ++a) out->gradient[(size_t)v * ncv + live2col[a]] = g[(size_t)v * NCL + a];
       for (int p = 0; p < P; ++p)
         for (int j = 0; j < 3; ++j) out->gradient[(size_t)V * ncv + 3 * (size_t)p + j] = Vh[(size_t)p * 10 + 6 + j];
+      for (int j = 0; j < dd; ++j) out->gradient[(size_t)V * ncv + 3 * (size_t)P + j] = gb[bo_disp + j];
       if (A > 0) {
-        for (int j = 0; j < 6; ++j) out->gradient[(size_t)V * ncv + 3 * (size_t)P + j] = gb[j];
-        if (kFyBorder) for (int k = 0; k < nav; ++k) out->gradient[(size_t)h_ann_view[k] * ncv + 1] = gb[6 + k];
+        for (int j = 0; j < 6; ++j) out->gradient[(size_t)V * ncv + 3 * (size_t)P + dd + j] = gb[bo_tlw + j];
+        if (kFyBorder) for (int k = 0; k < nav; ++k) out->gradient[(size_t)h_ann_view[k] * ncv + 1] = gb[bo_fy + k];
       }
     }
   }
@@ -825,7 +883,6 @@ static int check_problem(const ptzba_problem* p) {
   if (p->shared_ic_id)
     for (int i = 0; i < p->num_views; ++i)
       if (p->shared_ic_id[i] != i) { set_last_error("shared intrinsics (SetSharedIntrinsics) are not built"); return PTZ_ERR_UNSUPPORTED; }
-  if (p->factor_type == PTZ_BA_PTZRAY_DIST_DISP) { set_last_error("PTZRayDistDisp is not built on the GPU path yet"); return PTZ_ERR_UNSUPPORTED; }
   return PTZ_OK;
 }
 
@@ -833,7 +890,8 @@ static BaSolverBase* make_solver(const ptzba_problem* p, const ptz_solver_option
   switch (p->factor_type) {
     case PTZ_BA_PTZRAY: return new BaSolver<BA_PTZRAY>(p, o);
     case PTZ_BA_PTZRAY_DIST: return new BaSolver<BA_PTZRAY_DIST>(p, o);
-    default: return new BaSolver<BA_PTZRAY_FXFY_DIST>(p, o);
+    case PTZ_BA_PTZRAY_FXFY_DIST: return new BaSolver<BA_PTZRAY_FXFY_DIST>(p, o);
+    default: return new BaSolver<BA_PTZRAY_DIST_DISP>(p, o);
   }
 }
 

@@ -60,8 +60,11 @@ def test_invalid_arguments_are_rejected_without_touching_the_gpu():
     c.obs_view = bad.ctypes.data_as(C.POINTER(C.c_int32))
     assert L.ptzba_solve(C.byref(c), C.byref(o), C.byref(r)) == abi.PTZ_ERR_INVALID
     c = p.to_c()
-    c.factor_type = abi.PTZ_BA_PTZRAY_DIST_DISP
+    ids = np.arange(p.V, dtype=np.int32)[::-1].copy()  # SetSharedIntrinsics with a non-identity map is not built
+    c.shared_ic_id = ids.ctypes.data_as(C.POINTER(C.c_int32))
     assert L.ptzba_solve(C.byref(c), C.byref(o), C.byref(r)) == abi.PTZ_ERR_UNSUPPORTED
+    c.factor_type = 7
+    assert L.ptzba_solve(C.byref(c), C.byref(o), C.byref(r)) == abi.PTZ_ERR_INVALID
 
 
 def test_no_cpu_fallback():

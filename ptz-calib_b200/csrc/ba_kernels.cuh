@@ -563,6 +563,7 @@ struct CgArgs {
   int V, nb, n;            // n = V*NCL + nb
   const int* rowptr; const int* col; const double* Sval;
   int nav; const int* ann_view; const int* ann_idx; const double* C;   // scaled coupling strips [nav][NCL][nb]
+  const int* order;        // slot -> row: consecutive slots are neighbouring views (Cuthill-McKee), one contiguous run per CTA
   double *st0, *st1;       // ping-pong state, 3*n doubles each
   double *x, *p;
   double* partial;         // [2][gridDim][2]
@@ -597,6 +598,8 @@ __device__ __forceinline__ void grid_reduce2(double& a, double& b, double* parti
   }
   __syncthreads();
   double s0 = 0, s1 = 0;
+  // every thread acquires: its later plain (L1-cached) loads must not be served from lines older than this barrier
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
   for (int i = lane; i < (int)gridDim.x; i += 32) { const double2 v = __ldcg(reinterpret_cast<const double2*>(buf) + i); s0 += v.x; s1 += v.y; }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
@@ -611,7 +614,6 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
   extern __shared__ double cg_smem[];
   __shared__ double sred[MAXT / 32][2];
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;
-  const int gw = blockIdx.x * wpb + wid, nw = gridDim.x * wpb;
   const int la = lane % NCL, ls = lane / NCL;
   const bool lact = lane < SLOTS * NCL;
   const int V = A.V, nb = A.nb, nrows = V + (nb > 0 ? 1 : 0), boff = V * NCL;
@@ -619,8 +621,13 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
   const int cap = A.smem_blocks;
   double* Bs = cg_smem + (size_t)wid * cap * NB;
   int* cs = reinterpret_cast<int*>(cg_smem + (size_t)wpb * cap * NB) + (size_t)wid * cap;
+  // slots [blockIdx*per, (blockIdx+1)*per) belong to this CTA; warp w takes every wpb-th of them
+  const int nslots = nrows, per = (nslots + gridDim.x - 1) / gridDim.x;
   int ncached = 0;
-  for (int row = gw; row < V && ncached < cap; row += nw) {
+  for (int sl = wid; sl < per && ncached < cap; sl += wpb) {
+    const int slot = blockIdx.x * per + sl;
+    if (slot >= V) break;
+    const int row = A.order[slot];
     const int b0 = A.rowptr[row], take = min(A.rowptr[row + 1] - b0, cap - ncached);
     for (int e = lane; e < take * NB; e += 32) Bs[(size_t)ncached * NB + e] = A.Sval[(size_t)b0 * NB + e];
     for (int e = lane; e < take; e += 32) cs[ncached + e] = A.col[b0 + e];
@@ -635,7 +642,10 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
   for (;; ++it) {
     double g = 0, d = 0;
     int bi = 0;  // running index of this warp's blocks
-    for (int row = gw; row < nrows; row += nw) {
+    for (int sl = wid; sl < per; sl += wpb) {
+      const int slot = blockIdx.x * per + sl;
+      if (slot >= nslots) break;
+      const int row = slot < V ? A.order[slot] : V;
       if (row < V) {
         double rn = 0;
         if (lane < NCL) {
@@ -672,7 +682,9 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
             }
             double rr[CH], ww[CH], ss[CH];
 #pragma unroll
-            for (int u = 0; u < CH; ++u) { rr[u] = __ldcg(so + off[u]); ww[u] = __ldcg(so + off[u] + NCL); ss[u] = __ldcg(so + off[u] + 2 * NCL); }
+            // plain (L1-cached) loads: the rows of a CTA are neighbours and share most of their gathers; the acquire in the grid
+            // barrier invalidates L1 every iteration, so a cached line is never older than the last barrier
+            for (int u = 0; u < CH; ++u) { rr[u] = so[off[u]]; ww[u] = so[off[u] + NCL]; ss[u] = so[off[u] + 2 * NCL]; }
 #pragma unroll
             for (int u = 0; u < CH; ++u) {
               const int k = (t0 + u) * SLOTS + ls;

@@ -149,6 +149,7 @@ struct BaSolver : BaSolverBase {
   DevBuf<int> d_pts_view, d_ann_view, d_ann_off, d_ann_idx, d_fail, d_pcg_info, d_cpl_view, d_cpl_idx, d_ann_strip;
   DevBuf<double> d_recd, d_dpart, d_Wdh, d_Cw, d_dispp[2], d_disp_init;
   DevBuf<unsigned int> d_bar;
+  DevBuf<int> d_cg_order;
   // views into d_viewred (all-reduced once per Jacobian evaluation): U | g | cost_view | C | Hbb | gb | cost_pts(2)
   double *p_U, *p_g, *p_cost_view, *p_C, *p_Hbb, *p_gb, *p_cost_pts, *p_gabs, *p_gabs_b;
   DevBuf<double> d_gabs;
@@ -235,20 +236,51 @@ struct BaSolver : BaSolverBase {
     n = V * NCL + nb;
     {
       // CG launch shape: one CTA per SM, as many warps per CTA (8/16/32) as it takes to give every warp at most one row
-      // where possible; then how many blocks of S each warp can keep in 200 KB of shared memory
+      // where possible.  Rows are handed out in Cuthill-McKee order of the view graph, a contiguous run per CTA, so that the
+      // rows of a CTA are neighbouring views whose gathers overlap (L1 hits).  Then: how many blocks of S fit 200 KB of smem.
       const int nrows = V + (nb > 0 ? 1 : 0);
       const int need = cdiv(nrows, num_sms);
       cg_wpb = need <= 8 ? 8 : (need <= 16 ? 16 : 32);
       cg_grid = std::min(num_sms, cdiv(nrows, cg_wpb));
-      const int nw = cg_grid * cg_wpb;
-      int worst = 0;
-      for (int w = 0; w < nw; ++w) {
-        int c = 0;
-        for (int r = w; r < V; r += nw) c += ds.h_rowptr[r + 1] - ds.h_rowptr[r];
-        worst = std::max(worst, c);
+      std::vector<int> h_col(ds.nnzb);
+      ds.s_col.download(h_col.data(), ds.nnzb, stream);
+      PTZ_CUDA(cudaStreamSynchronize(stream));
+      std::vector<int> order;
+      order.reserve(V);
+      {
+        std::vector<char> seen(V, 0);
+        std::vector<int> deg(V), byd(V);
+        for (int v = 0; v < V; ++v) { deg[v] = ds.h_rowptr[v + 1] - ds.h_rowptr[v]; byd[v] = v; }
+        std::stable_sort(byd.begin(), byd.end(), [&](int a, int b) { return deg[a] < deg[b]; });
+        std::vector<int> nbrs;
+        for (int start : byd) {
+          if (seen[start]) continue;
+          size_t head = order.size();
+          order.push_back(start); seen[start] = 1;
+          while (head < order.size()) {
+            const int v = order[head++];
+            nbrs.clear();
+            for (int k = ds.h_rowptr[v]; k < ds.h_rowptr[v + 1]; ++k) if (!seen[h_col[k]]) { nbrs.push_back(h_col[k]); seen[h_col[k]] = 1; }
+            std::stable_sort(nbrs.begin(), nbrs.end(), [&](int a, int b) { return deg[a] < deg[b]; });
+            order.insert(order.end(), nbrs.begin(), nbrs.end());
+          }
+        }
       }
+      d_cg_order.upload(order, stream);
+      const int per = cdiv(nrows, cg_grid);
+      int worst = 0;
+      for (int c = 0; c < cg_grid; ++c)
+        for (int w = 0; w < cg_wpb; ++w) {
+          int cnt = 0;
+          for (int sl = w; sl < per; sl += cg_wpb) {
+            const int slot = c * per + sl;
+            if (slot >= V) break;
+            cnt += ds.h_rowptr[order[slot] + 1] - ds.h_rowptr[order[slot]];
+          }
+          worst = std::max(worst, cnt);
+        }
       const size_t per_block = NCL * NCL * sizeof(double) + sizeof(int);
-      const int fit = (int)((200 * 1024) / (cg_wpb * per_block));
+      const int fit = (int)((160 * 1024) / (cg_wpb * per_block));  // leave >= 60 KB of the SM's 228 KB to the L1
       cg_cap = std::max(1, std::min(worst, fit));
       const size_t cg_smem = (size_t)cg_wpb * cg_cap * per_block + 16;
       PTZ_CUDA(cudaFuncSetAttribute(cg_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg_smem));
@@ -397,8 +429,12 @@ struct BaSolver : BaSolverBase {
     cudaStream_t s = stream;
     PTZ_CUDA(cudaMemcpyAsync(d_intr[0].p, d_intr_init.p, 9 * (size_t)V * 8, cudaMemcpyDeviceToDevice, s));
     PTZ_CUDA(cudaMemcpyAsync(d_ext[0].p, d_ext_init.p, 6 * (size_t)V * 8, cudaMemcpyDeviceToDevice, s));
-    PTZ_CUDA(cudaMemcpyAsync(d_tlw[0].p, d_tlw_init.p, 6 * 8, cudaMemcpyDeviceToDevice, s));
-    PTZ_CUDA(cudaMemcpyAsync(d_dispp[0].p, d_disp_init.p, 3 * 8, cudaMemcpyDeviceToDevice, s));
+    for (int i = 0; i < 2; ++i) {  // both copies: without a border the candidate copy is never written, yet `cur` flips to it
+      PTZ_CUDA(cudaMemcpyAsync(d_tlw[i].p, d_tlw_init.p, 6 * 8, cudaMemcpyDeviceToDevice, s));
+      PTZ_CUDA(cudaMemcpyAsync(d_dispp[i].p, d_disp_init.p, 3 * 8, cudaMemcpyDeviceToDevice, s));
+      PTZ_CUDA(cudaMemcpyAsync(d_intr[i].p, d_intr_init.p, 9 * (size_t)V * 8, cudaMemcpyDeviceToDevice, s));
+      PTZ_CUDA(cudaMemcpyAsync(d_ext[i].p, d_ext_init.p, 6 * (size_t)V * 8, cudaMemcpyDeviceToDevice, s));
+    }
     for (int i = 0; i < 2; ++i) PTZ_CUDA(cudaMemcpyAsync(d_trk[i].p, d_trk_init.p, d_trk_init.n * 8, cudaMemcpyDeviceToDevice, s));
     cur = 0;
     started = finished = false;
@@ -522,7 +558,7 @@ struct BaSolver : BaSolverBase {
     CgArgs a;
     a.V = V; a.nb = nb; a.n = n;
     a.rowptr = ds.s_rowptr.p; a.col = ds.s_col.p; a.Sval = p_Sval;
-    a.nav = ncpl; a.ann_view = d_cpl_view.p; a.ann_idx = d_cpl_idx.p; a.C = d_Cs.p;
+    a.nav = ncpl; a.ann_view = d_cpl_view.p; a.ann_idx = d_cpl_idx.p; a.C = d_Cs.p; a.order = d_cg_order.p;
     a.st0 = d_cgstate.p; a.st1 = d_cgstate.p + 3 * (size_t)n; a.x = d_cgxp.p; a.p = d_cgxp.p + n;
     a.partial = d_pcg_partial.p; a.bar = d_bar.p; a.max_iter = opt.pcg_max_iterations; a.tol = opt.pcg_rel_tolerance;
     a.out_info = d_pcg_info.p; a.out_res = d_pcg_res.p;

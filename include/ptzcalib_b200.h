@@ -202,6 +202,11 @@ typedef struct ptzreloc_batch {
   const double* init_cam;       /* [B*21] krt21 given to SetInitParams (:257-263) */
   int max_iter;                 /* KRTOptimizer ctor, :251 */
   double max_reproj_error;
+  /* optional 2d-3d terms, Add2d3dConstraints (:350-383): Factor2d3dDist / Factor2d3dFxfyDist through cv::projectPoints
+   * (uses the camera t and reads v[10..14] in OpenCV order k1,k2,p1,p2,k3).  All three NULL = none. */
+  const int64_t* pt_offset;     /* [B+1] */
+  const float* pt_uv;           /* [Np*2] pts2d */
+  const double* pt_xyz;         /* [Np*3] pts3d in the WORLD frame (moved to the reference-local frame as at :357-362) */
 } ptzreloc_batch;
 
 typedef struct ptzreloc_result {

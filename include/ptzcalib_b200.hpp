@@ -308,6 +308,14 @@ class KRTOptimizer {
       uv2_.push_back(kpts_curr[m.trainIdx].pt.x); uv2_.push_back(kpts_curr[m.trainIdx].pt.y);
     }
   }
+  // .cc:350-383; the world->local transform of the points (.cc:357-362) is applied on the device with cam_ref's R, t
+  void Add2d3dConstraints(const std::vector<Point2f>& pts2d, const std::vector<Point3d>& pts3d) {
+    if (pts2d.size() != pts3d.size() || pts2d.empty()) return;
+    for (size_t i = 0; i < pts2d.size(); ++i) {
+      puv_.push_back(pts2d[i].x); puv_.push_back(pts2d[i].y);
+      pxyz_.push_back(pts3d[i].x); pxyz_.push_back(pts3d[i].y); pxyz_.push_back(pts3d[i].z);
+    }
+  }
   bool Solve(Mat33& K, Mat33& R, Vec3& t, Vec5& dist) {  // .cc:385-404
     double ref[21], init[21], out[21];
     cam_ref_.ToKrt21(ref);
@@ -317,6 +325,8 @@ class KRTOptimizer {
     ptzreloc_batch b{};
     b.factor_type = kMap[(int)factor_type_]; b.num_queries = 1; b.match_offset = off; b.uv_ref = uv1_.data(); b.uv_cur = uv2_.data();
     b.ref_cam = ref; b.init_cam = init; b.max_iter = max_iter_; b.max_reproj_error = max_reproj_error_;
+    const int64_t poff[2] = {0, (int64_t)(puv_.size() / 2)};
+    if (!puv_.empty()) { b.pt_offset = poff; b.pt_uv = puv_.data(); b.pt_xyz = pxyz_.data(); }
     int32_t ok = 0, term = 0, nit = 0;
     ptzreloc_result r{};
     r.cam = out; r.success = &ok; r.termination = &term; r.num_iter = &nit;
@@ -335,7 +345,8 @@ class KRTOptimizer {
 
  private:
   Camera cam_curr_world_, cam_ref_;
-  std::vector<float> uv1_, uv2_;
+  std::vector<float> uv1_, uv2_, puv_;
+  std::vector<double> pxyz_;
   bool set_fixed_focal_ = false;
   FACTOR_TYPE factor_type_ = F;
   int max_iter_ = 100;

@@ -1075,9 +1075,21 @@ void ba_world_outputs(const BaProblem& bp, const std::vector<double>& x, ptzba_r
 // the KRT problem (KRTOptimizer), one query
 // =====================================================================================================
 struct KrtProblem : Problem {
-  int type, N;
+  int type, N, Np = 0;
   const float* uv2;
+  const float* puv = nullptr;
   std::vector<KrtPre> pre;
+  std::vector<double> plocal;  // 2d-3d points in the reference-local frame (Add2d3dConstraints, krt_optimizer.cc:357-362)
+  void add_points(int np, const float* pt_uv, const double* pt_xyz_world, const double* ref21) {
+    Np = np; puv = pt_uv;
+    plocal.resize(3 * (size_t)np);
+    for (int i = 0; i < np; ++i) {
+      double t[3];
+      mul31(ref21 + 4, pt_xyz_world + 3 * i, t);
+      for (int a = 0; a < 3; ++a) plocal[3 * (size_t)i + a] = t[a] + ref21[13 + a];
+    }
+    num_blocks = N + Np;
+  }
   KrtProblem(int type_, int n, const float* uv_ref, const float* uv_cur, const double refK4[4], const double refd[5]) : type(type_), N(n), uv2(uv_cur) {
     num_ambient = 15;
     num_blocks = N;
@@ -1099,8 +1111,14 @@ struct KrtProblem : Problem {
   }
   int block_params(int, int* amb) const override { for (int j = 0; j < 15; ++j) amb[j] = j; return 15; }
   double block_weight(int) const override { return 1.0; }  // nullptr loss (:294)
-  void eval_d(int k, const double* a, double* res) const override { krt_2d2d_factor<double>(type, a, pre[k], uv2[2 * k], uv2[2 * k + 1], res); }
-  void eval_j(int k, const JetT* a, JetT* res) const override { krt_2d2d_factor<JetT>(type, a, pre[k], uv2[2 * k], uv2[2 * k + 1], res); }
+  void eval_d(int k, const double* a, double* res) const override {
+    if (k < N) krt_2d2d_factor<double>(type, a, pre[k], uv2[2 * k], uv2[2 * k + 1], res);
+    else krt_2d3d_factor<double>(type, a, &plocal[3 * (size_t)(k - N)], puv[2 * (k - N)], puv[2 * (k - N) + 1], res);
+  }
+  void eval_j(int k, const JetT* a, JetT* res) const override {
+    if (k < N) krt_2d2d_factor<JetT>(type, a, pre[k], uv2[2 * k], uv2[2 * k + 1], res);
+    else krt_2d3d_factor<JetT>(type, a, &plocal[3 * (size_t)(k - N)], puv[2 * (k - N)], puv[2 * (k - N) + 1], res);
+  }
 };
 
 // Add2d2dConstraints frame change (krt_optimizer.cc:269-286): local = reference frame
@@ -1335,6 +1353,10 @@ int orc_ptzreloc_solve_batch(const ptzreloc_batch* b, const ptz_solver_options* 
     std::vector<double> x(15);
     krt_to_local(ref, b->init_cam + 21 * (size_t)q, x.data());
     KrtProblem kp(b->factor_type, N, b->uv_ref + 2 * o0, b->uv_cur + 2 * o0, ref, ref + 16);
+    if (b->pt_offset && b->pt_uv && b->pt_xyz) {
+      const int64_t p0 = b->pt_offset[q];
+      kp.add_points((int)(b->pt_offset[q + 1] - p0), b->pt_uv + 2 * p0, b->pt_xyz + 3 * p0, ref);
+    }
     ptz_solver_options o = *opt;
     o.max_num_iterations = b->max_iter;
     o.num_threads = 1;
@@ -1342,7 +1364,7 @@ int orc_ptzreloc_solve_batch(const ptzreloc_batch* b, const ptz_solver_options* 
     LmSummary sum;
     minimize(kp, x, o, false, sum);
     // CheckResults (krt_optimizer.cc:504-533)
-    const int nres = 2 * N;
+    const int nres = 2 * kp.num_blocks;
     double final_rms = std::sqrt(2.0) * std::sqrt((2 * sum.final_cost) / nres);
     int ok = 1;
     if (sum.termination != PTZ_CONVERGENCE) ok = 0;

@@ -186,6 +186,7 @@ class KRTOptimizer:
         self._init = None
         self._ref = None
         self._uv = None
+        self._pts = None
 
     def SetInitParams(self, K, R, t, dist):  # krt_optimizer.cc:257-263
         K, R = f64(K).reshape(3, 3), f64(R).reshape(3, 3)
@@ -197,11 +198,21 @@ class KRTOptimizer:
         self._ref = f64(cam_ref21).reshape(21)
         self._uv = (f32(kpts_ref).reshape(-1, 2)[matches[:, 0]], f32(kpts_curr).reshape(-1, 2)[matches[:, 1]])
 
+    def Add2d3dConstraints(self, pts2d, pts3d):  # krt_optimizer.cc:350-383
+        """pts2d: [n,2] pixels of the current image; pts3d: [n,3] world points"""
+        pts2d, pts3d = f32(pts2d).reshape(-1, 2), f64(pts3d).reshape(-1, 3)
+        if len(pts2d) != len(pts3d) or len(pts2d) == 0:
+            return
+        self._pts = (pts2d, pts3d)
+
     def Solve(self):
         """-> (ok, K, R, t, dist); outputs are None unless ok (krt_optimizer.cc:398-403)"""
         uv1, uv2 = self._uv
+        pts = {}
+        if self._pts is not None:
+            pts = dict(pt_offset=np.array([0, len(self._pts[0])], np.int64), pt_uv=self._pts[0], pt_xyz=self._pts[1])
         batch = RelocBatch(self.factor_type, np.array([0, len(uv1)], np.int64), uv1, uv2, self._ref[None], self._init[None], self.max_iter,
-                           self.max_reproj_error)
+                           self.max_reproj_error, **pts)
         res = reloc_solve_batch(batch)
         self.num_iter_ = int(res.num_iter[0])
         if not res.success[0]:

@@ -146,6 +146,9 @@ class RelocBatchC(C.Structure):
         ("init_cam", dp),
         ("max_iter", C.c_int),
         ("max_reproj_error", C.c_double),
+        ("pt_offset", lp),
+        ("pt_uv", fp),
+        ("pt_xyz", dp),
     ]
 
 

@@ -372,6 +372,40 @@ PTZ_HD void krt_obs(const KrtCam& kc, const double n[3], double u2, double v2, d
   if (DIST) { J[c] = -(kc.fx * x * bw.r2); J[NF + c] = -(kc.fy * y * bw.r2); }
 }
 
+// Factor2d3dDist / Factor2d3dFxfyDist (krt_optimizer.cc:201-248): cv::projectPoints(P; rvec, t, K, dist) with the stored
+// distortion vector read in OpenCV order (k1,k2,p1,p2,k3) = v[10..14] and the camera translation t = v[7..9] (not free).
+// Free columns as krt_obs.  P is the point in the reference-local frame.
+template <int TYPE, bool JAC>
+PTZ_HD void krt_obs3d(const KrtCam& kc, const double t[3], const double P[3], double u, double v, double r[2], double* J /*[2*NFREE]*/) {
+  constexpr int NF = krt_nfree(TYPE);
+  constexpr bool DIST = (TYPE == KRT_FDIST || TYPE == KRT_FXFYDIST);
+  constexpr bool FXFY = (TYPE == KRT_FXFY || TYPE == KRT_FXFYDIST);
+  const double* R = kc.R;
+  const double RX = R[0] * P[0] + R[1] * P[1] + R[2] * P[2];
+  const double RY = R[3] * P[0] + R[4] * P[1] + R[5] * P[2];
+  const double RZ = R[6] * P[0] + R[7] * P[1] + R[8] * P[2];
+  const double X = RX + t[0], Y = RY + t[1], Z = RZ + t[2];
+  const double iz = 1.0 / Z, x = X * iz, y = Y * iz;
+  // hand order (k1,k2,k3,p1,p2) <- OpenCV order (v10,v11,v14,v12,v13); kc holds v10..v14 as k1,k2,k3,p1,p2
+  const Brown bw = brown(x, y, kc.k1, kc.k2, kc.p2, kc.k3, kc.p1, JAC);
+  r[0] = u - (kc.fx * bw.xd + kc.cx);
+  r[1] = v - (kc.fy * bw.yd + kc.cy);
+  if (!JAC) return;
+  const double ux = kc.fx * bw.xd_x * iz, uy = kc.fx * bw.xd_y * iz, uz = -(ux * x + uy * y);
+  const double vx = kc.fy * bw.yd_x * iz, vy = kc.fy * bw.yd_y * iz, vz = -(vx * x + vy * y);
+  int c = 0;
+  J[c] = -bw.xd; J[NF + c] = FXFY ? 0.0 : -bw.yd; ++c;
+  if (FXFY) { J[c] = 0.0; J[NF + c] = -bw.yd; ++c; }
+  for (int k = 0; k < 3; ++k) {
+    double dX, dY, dZ;
+    dX_dw(kc.Jl, k, RX, RY, RZ, dX, dY, dZ);  // d(R P)/dw_k; t does not depend on w
+    J[c + k] = -(ux * dX + uy * dY + uz * dZ);
+    J[NF + c + k] = -(vx * dX + vy * dY + vz * dZ);
+  }
+  c += 3;
+  if (DIST) { J[c] = -(kc.fx * x * bw.r2); J[NF + c] = -(kc.fy * y * bw.r2); }
+}
+
 // -----------------------------------------------------------------------------------------------------------
 // frame changes of KRTOptimizer (krt_optimizer.cc:269-286, 535-567) with OpenCV's 3x3 inverse and cv::Rodrigues(R->r)
 // -----------------------------------------------------------------------------------------------------------

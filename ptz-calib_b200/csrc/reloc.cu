@@ -20,6 +20,7 @@ struct RelocArgs {
   const int64_t* off;
   const float2* uv_ref; const float2* uv_cur;
   const double* ref_cam; const double* init_cam;
+  const int64_t* pt_off; const float2* pt_uv; const double* pt_xyz;  // optional 2d-3d terms (Add2d3dConstraints)
   int max_iter; double max_reproj_error;
   ptz_solver_options opt;
   int smem_matches;  // matches that fit the dynamic shared memory of this launch; larger queries recompute from global
@@ -49,7 +50,8 @@ __device__ __forceinline__ int krt_free_index(int j) {
 // one pass over the query's matches at camera x: cost, and (when JAC) A = J^T J (upper, row-major), g = J^T r
 template <int TYPE, bool JAC>
 __device__ __forceinline__ void reloc_pass(const double x[15], int N, int lane, const double4* sm, int smem_matches, const float2* uv_ref,
-                                           const float2* uv_cur, const double* refK4, const double* refd, double* out /*[NA+NF+1]*/) {
+                                           const float2* uv_cur, const double* refK4, const double* refd, int npts, const float2* puv,
+                                           const double* pxyz, const double* ref21, double* out /*[NA+NF+1]*/) {
   constexpr int NF = krt_nfree(TYPE), NA = NF * (NF + 1) / 2, NV = NA + NF + 1;
   double acc[NV];
 #pragma unroll
@@ -84,6 +86,27 @@ __device__ __forceinline__ void reloc_pass(const double x[15], int N, int lane, 
       for (int a = 0; a < NF; ++a) acc[NA + a] += J[a] * r[0] + J[NF + a] * r[1];
     }
   }
+  // 2d-3d terms: the world point goes to the reference-local frame (R_ref X + t_ref, krt_optimizer.cc:357-362), then
+  // Factor2d3dDist / Factor2d3dFxfyDist with the camera's own t
+  for (int i = lane; i < npts; i += 32) {
+    const double* Rr = ref21 + 4;
+    const double Xw[3] = {pxyz[3 * i], pxyz[3 * i + 1], pxyz[3 * i + 2]};
+    double P[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) P[a] = Rr[3 * a] * Xw[0] + Rr[3 * a + 1] * Xw[1] + Rr[3 * a + 2] * Xw[2] + ref21[13 + a];
+    double r[2], J[2 * NF];
+    krt_obs3d<TYPE, JAC>(kc, x + 7, P, (double)puv[i].x, (double)puv[i].y, r, J);
+    acc[NA + NF] += 0.5 * (r[0] * r[0] + r[1] * r[1]);
+    if (JAC) {
+      int k = 0;
+#pragma unroll
+      for (int a = 0; a < NF; ++a)
+#pragma unroll
+        for (int b = a; b < NF; ++b) acc[k++] += J[a] * J[b] + J[NF + a] * J[NF + b];
+#pragma unroll
+      for (int a = 0; a < NF; ++a) acc[NA + a] += J[a] * r[0] + J[NF + a] * r[1];
+    }
+  }
   warp_allreduce<NV>(acc);
 #pragma unroll
   for (int i = 0; i < NV; ++i) out[i] = acc[i];
@@ -100,6 +123,10 @@ __global__ void __launch_bounds__(32) k_reloc(RelocArgs a) {
   const double* ref = a.ref_cam + 21 * (size_t)q;
   const float2* uv_ref = a.uv_ref + o0;
   const float2* uv_cur = a.uv_cur + o0;
+  const int64_t p0 = a.pt_off ? a.pt_off[q] : 0;
+  const int npts = a.pt_off ? (int)(a.pt_off[q + 1] - p0) : 0;
+  const float2* puv = a.pt_uv + p0;
+  const double* pxyz = a.pt_xyz + 3 * p0;
   double refK4[4], refd[5];
   for (int j = 0; j < 4; ++j) refK4[j] = ref[j];
   for (int j = 0; j < 5; ++j) refd[j] = ref[16 + j];
@@ -122,7 +149,7 @@ __global__ void __launch_bounds__(32) k_reloc(RelocArgs a) {
   const ptz_solver_options& o = a.opt;
   // ---- TrustRegionMinimizer (Ceres 1.14), dense normal equations
   double ev[NV], A[NA], g[NF], scale[NF], diag[NF], y[NF];
-  reloc_pass<TYPE, true>(x, N, lane, sm, a.smem_matches, uv_ref, uv_cur, refK4, refd, ev);
+  reloc_pass<TYPE, true>(x, N, lane, sm, a.smem_matches, uv_ref, uv_cur, refK4, refd, npts, puv, pxyz, ref, ev);
 #pragma unroll
   for (int i = 0; i < NA; ++i) A[i] = ev[i];
 #pragma unroll
@@ -205,7 +232,7 @@ __global__ void __launch_bounds__(32) k_reloc(RelocArgs a) {
       step2 += (x[idx] - cand[idx]) * (x[idx] - cand[idx]);
     }
     // candidate cost together with its normal equations (they are needed as soon as the step is accepted)
-    reloc_pass<TYPE, true>(cand, N, lane, sm, a.smem_matches, uv_ref, uv_cur, refK4, refd, ev);
+    reloc_pass<TYPE, true>(cand, N, lane, sm, a.smem_matches, uv_ref, uv_cur, refK4, refd, npts, puv, pxyz, ref, ev);
     double cand_cost = ev[NA + NF];
     if (!isfinite(cand_cost)) cand_cost = 1.7976931348623157e308;
     const double step_norm = sqrt(step2);
@@ -240,7 +267,7 @@ __global__ void __launch_bounds__(32) k_reloc(RelocArgs a) {
   }
   // CheckResults (krt_optimizer.cc:504-533) and ObtainRefinedCameraParams (:535-567)
   if (lane == 0) {
-    const double nres = 2.0 * N;
+    const double nres = 2.0 * (N + npts);
     const double final_rms = sqrt(2.0) * sqrt((2 * min_cost) / nres);
     int ok = 1;
     if (termination != PTZ_CONVERGENCE) ok = 0;
@@ -328,6 +355,7 @@ int ptzreloc_solve_batch_dev(const ptzreloc_batch* b, const ptz_solver_options* 
     a.B = b->num_queries; a.off = b->match_offset;
     a.uv_ref = reinterpret_cast<const float2*>(b->uv_ref); a.uv_cur = reinterpret_cast<const float2*>(b->uv_cur);
     a.ref_cam = b->ref_cam; a.init_cam = b->init_cam; a.max_iter = b->max_iter; a.max_reproj_error = b->max_reproj_error;
+    a.pt_off = b->pt_offset; a.pt_uv = reinterpret_cast<const float2*>(b->pt_uv); a.pt_xyz = b->pt_xyz;
     a.opt = *opt;
     a.cam = out->cam; a.success = out->success; a.termination = out->termination; a.num_iter = out->num_iter; a.iterations = out->iterations;
     a.initial_cost = out->initial_cost; a.final_cost = out->final_cost; a.final_rms = out->final_rms; a.local15 = out->local_cam15;
@@ -357,8 +385,17 @@ int ptzreloc_solve_batch(const ptzreloc_batch* b, const ptz_solver_options* opt,
     StreamHolder sh;  // declared before the buffers: destroyed after them
     sh.create();
     cudaStream_t s = sh.s;
-    DevBuf<int64_t> d_off;
-    DevBuf<float2> d_ur, d_uc;
+    DevBuf<int64_t> d_off, d_poff;
+    DevBuf<float2> d_ur, d_uc, d_puv;
+    DevBuf<double> d_pxyz;
+    const bool has_pts = b->pt_offset && b->pt_uv && b->pt_xyz;
+    if (has_pts) {
+      const int64_t Np = b->pt_offset[B];
+      d_poff.upload(b->pt_offset, B + 1, s);
+      d_puv.upload(reinterpret_cast<const float2*>(b->pt_uv), Np, s);
+      d_pxyz.upload(b->pt_xyz, 3 * (size_t)Np, s);
+      if (Np == 0) { d_puv.alloc(1, s); d_pxyz.alloc(1, s); }
+    }
     DevBuf<double> d_ref, d_init, d_cam, d_ic, d_fc, d_rms, d_loc;
     DevBuf<int> d_succ, d_term, d_ni, d_it;
     d_off.upload(b->match_offset, B + 1, s);
@@ -371,6 +408,7 @@ int ptzreloc_solve_batch(const ptzreloc_batch* b, const ptz_solver_options* opt,
     RelocArgs a;
     a.B = B; a.off = d_off.p; a.uv_ref = d_ur.p; a.uv_cur = d_uc.p; a.ref_cam = d_ref.p; a.init_cam = d_init.p;
     a.max_iter = b->max_iter; a.max_reproj_error = b->max_reproj_error; a.opt = *opt;
+    a.pt_off = has_pts ? d_poff.p : nullptr; a.pt_uv = d_puv.p; a.pt_xyz = d_pxyz.p;
     a.cam = d_cam.p; a.success = d_succ.p; a.termination = d_term.p; a.num_iter = d_ni.p; a.iterations = d_it.p;
     a.initial_cost = d_ic.p; a.final_cost = d_fc.p; a.final_rms = d_rms.p; a.local15 = d_loc.p;
     launch_reloc(b->factor_type, a, max_matches, s);

@@ -238,8 +238,15 @@ class RelocBatch:
     max_iter: int = 200  # run_ptz_reloc.cc:90
     max_reproj_error: float = 100.0  # run_ptz_reloc.cc:91
     gt: dict = field(default_factory=dict)
+    pt_offset: Optional[np.ndarray] = None  # [B+1] int64: optional 2d-3d terms (Add2d3dConstraints)
+    pt_uv: Optional[np.ndarray] = None  # [Np,2] float32
+    pt_xyz: Optional[np.ndarray] = None  # [Np,3] world frame
 
     def __post_init__(self):
+        if self.pt_offset is not None:
+            self.pt_offset = i64(self.pt_offset).reshape(-1)
+            self.pt_uv = f32(self.pt_uv).reshape(-1, 2)
+            self.pt_xyz = f64(self.pt_xyz).reshape(-1, 3)
         self.match_offset = i64(self.match_offset).reshape(-1)
         self.uv_ref = f32(self.uv_ref).reshape(-1, 2)
         self.uv_cur = f32(self.uv_cur).reshape(-1, 2)
@@ -265,14 +272,21 @@ class RelocBatch:
         c.init_cam = as_ptr(self.init_cam, C.c_double)
         c.max_iter = int(self.max_iter)
         c.max_reproj_error = float(self.max_reproj_error)
+        c.pt_offset = as_ptr(self.pt_offset, C.c_int64)
+        c.pt_uv = as_ptr(self.pt_uv, C.c_float)
+        c.pt_xyz = as_ptr(self.pt_xyz, C.c_double)
         return c
 
     def slice(self, lo: int, hi: int) -> "RelocBatch":
         """Queries [lo, hi): the unit of multi-GPU sharding (no collective)."""
         o0, o1 = int(self.match_offset[lo]), int(self.match_offset[hi])
         gt = {k: (v[lo:hi] if isinstance(v, np.ndarray) and len(v) == self.B else v) for k, v in self.gt.items()}
+        pts = {}
+        if self.pt_offset is not None:
+            p0, p1 = int(self.pt_offset[lo]), int(self.pt_offset[hi])
+            pts = dict(pt_offset=self.pt_offset[lo : hi + 1] - p0, pt_uv=self.pt_uv[p0:p1], pt_xyz=self.pt_xyz[p0:p1])
         return RelocBatch(self.factor_type, self.match_offset[lo : hi + 1] - o0, self.uv_ref[o0:o1], self.uv_cur[o0:o1], self.ref_cam[lo:hi],
-                          self.init_cam[lo:hi], self.max_iter, self.max_reproj_error, gt)
+                          self.init_cam[lo:hi], self.max_iter, self.max_reproj_error, gt, **pts)
 
     def shard(self, rank: int, world: int) -> "RelocBatch":
         """Contiguous split balanced by cumulative match count."""

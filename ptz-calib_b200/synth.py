@@ -225,7 +225,7 @@ def krt21(f, fy, c, R, t, dist):
 
 
 def make_reloc_batch(B, factor_type=abi.PTZ_KRT_F, seed=1003, n_min=64, n_max=512, width=1920, height=1080, sigma=0.5, outlier_frac=0.05,
-                     outlier_sigma=40.0, num_ref=36, dpan_deg=5.0, k1=-0.1, max_iter=200, max_reproj_error=100.0, query_seed=None):
+                     outlier_sigma=40.0, num_ref=36, dpan_deg=5.0, k1=-0.1, max_iter=200, max_reproj_error=100.0, query_seed=None, pts_per_query=0):
     """cfg 3: B independent queries against a calibrated reference ring; init exactly as run_ptz_reloc.cc:97-104."""
     rng = np.random.default_rng(seed)
     Rref, fref, cref, _ = _views("ring", rng, num_ref, width, height)
@@ -275,4 +275,16 @@ def make_reloc_batch(B, factor_type=abi.PTZ_KRT_F, seed=1003, n_min=64, n_max=51
     # SetInitParams: K = [f_ref, centre of the test image], R, t, dist of the reference camera
     init_cam = krt21(fref[ref_idx], fref[ref_idx], cq, Rref[ref_idx], t0, dist)
     gt = dict(R=Rq, f=fq, ref_idx=ref_idx)
-    return RelocBatch(factor_type, off, uv_ref, uv_cur, ref_cam, init_cam, max_iter, max_reproj_error, gt)
+    pts = {}
+    if pts_per_query > 0:
+        # optional 2d-3d terms (Add2d3dConstraints): world points in front of the query camera, seen with pixel noise
+        npq = np.full(B, pts_per_query, np.int64)
+        poff = np.zeros(B + 1, np.int64)
+        poff[1:] = np.cumsum(npq)
+        pb = np.repeat(np.arange(B), npq)
+        px = np.stack([q.uniform(0.1 * width, 0.9 * width, len(pb)), q.uniform(0.1 * height, 0.9 * height, len(pb))], -1)
+        dcam = np.stack([(px[:, 0] - cq[pb, 0]) / fq[pb], (px[:, 1] - cq[pb, 1]) / fq[pb], np.ones(len(pb))], -1) * q.uniform(10, 80, (len(pb), 1))
+        Xw = np.einsum("nji,nj->ni", Rq[pb], dcam)
+        uvp, _ = project(Rq[pb], fq[pb], cq[pb], k1v, Xw)
+        pts = dict(pt_offset=poff, pt_uv=(uvp + q.normal(0, sigma, uvp.shape)).astype(np.float32), pt_xyz=Xw)
+    return RelocBatch(factor_type, off, uv_ref, uv_cur, ref_cam, init_cam, max_iter, max_reproj_error, gt, **pts)

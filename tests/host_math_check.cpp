@@ -52,4 +52,13 @@ int hm_krt_obs(int type, const double* cam15, const double* refK4, const double*
   return 1;
 }
 void hm_rodrigues_jac(const double* w, double* R, double* dR) { rodrigues_jac(w, R, dR); }
+void hm_krt_obs3d(int type, const double* cam15, const float* uv, const double* P, double* r, double* J) {
+  KrtCam kc;
+  switch (type) {
+    case 0: krt_make_cam<0>(cam15, &kc, true); krt_obs3d<0, true>(kc, cam15 + 7, P, uv[0], uv[1], r, J); break;
+    case 1: krt_make_cam<1>(cam15, &kc, true); krt_obs3d<1, true>(kc, cam15 + 7, P, uv[0], uv[1], r, J); break;
+    case 2: krt_make_cam<2>(cam15, &kc, true); krt_obs3d<2, true>(kc, cam15 + 7, P, uv[0], uv[1], r, J); break;
+    default: krt_make_cam<3>(cam15, &kc, true); krt_obs3d<3, true>(kc, cam15 + 7, P, uv[0], uv[1], r, J); break;
+  }
+}
 }

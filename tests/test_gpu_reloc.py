@@ -96,3 +96,32 @@ def test_full_size_properties():
     # shards partition the batch
     parts = [b.shard(i, 4) for i in range(4)]
     assert sum(p.B for p in parts) == b.B and sum(p.N for p in parts) == b.N
+
+
+@pytest.mark.parametrize("t", TYPES)
+def test_batch_with_2d3d_constraints_matches_oracle(orc, t):
+    """Add2d3dConstraints (krt_optimizer.cc:350-383): Factor2d3dDist / Factor2d3dFxfyDist next to the 2d-2d terms"""
+    b = synth.make_reloc_batch(120, factor_type=t, n_min=16, n_max=120, pts_per_query=7)
+    got = ptz.reloc_solve_batch(b)
+    want = orc.reloc_solve_batch(b)
+    assert np.array_equal(got.termination, want.termination) and np.array_equal(got.success, want.success)
+    assert np.array_equal(got.iterations, want.iterations)
+    assert relerr(got.initial_cost, want.initial_cost, floor=1e-30) <= 1e-11
+    assert relerr(got.final_cost, want.final_cost, floor=1e-30) <= 1e-6
+    assert relerr(got.final_rms, want.final_rms, floor=1e-30) <= 1e-6
+    assert np.abs(got.local_cam15[:, 4:7] - want.local_cam15[:, 4:7]).max() <= 1e-6
+    assert np.abs(got.local_cam15[:, :2] - want.local_cam15[:, :2]).max() <= 1e-4
+    # the points do change the answer (they are not silently ignored)
+    plain = ptz.reloc_solve_batch(synth.make_reloc_batch(120, factor_type=t, n_min=16, n_max=120))
+    assert np.abs(plain.final_cost - got.final_cost).max() > 1e-3
+    # the class mirror: SetInitParams / Add2d2dConstraints / Add2d3dConstraints / Solve on query 3
+    q, k = 3, ptz.KRTOptimizer(200, 100.0, t)
+    c = b.init_cam[q]
+    k.SetInitParams(np.array([[c[0], 0, c[2]], [0, c[1], c[3]], [0, 0, 1]]), c[4:13].reshape(3, 3), c[13:16], c[16:21])
+    lo, hi = int(b.match_offset[q]), int(b.match_offset[q + 1])
+    k.Add2d2dConstraints(b.ref_cam[q], b.uv_ref[lo:hi], b.uv_cur[lo:hi], np.stack([np.arange(hi - lo)] * 2, 1))
+    k.Add2d3dConstraints(b.pt_uv[b.pt_offset[q]:b.pt_offset[q + 1]], b.pt_xyz[b.pt_offset[q]:b.pt_offset[q + 1]])
+    ok, K, R, tt, dist = k.Solve()
+    assert ok == bool(got.success[q]) and k.num_iter_ == got.num_iter[q]
+    if ok:
+        assert K[0, 0] == got.cam[q, 0] and np.array_equal(R.reshape(9), got.cam[q, 4:13])

@@ -95,3 +95,20 @@ def test_rodrigues_jac_small_angles(hm, orc):
             e[kk] = h
             num = (orc.rodrigues(w + e) - orc.rodrigues(w - e)) / (2 * h)
             assert np.abs(dR[9 * kk : 9 * kk + 9].reshape(3, 3) - num).max() < 1e-9
+
+
+@pytest.mark.parametrize("t", [0, 1, 2, 3])
+def test_krt_obs3d_matches_oracle(hm, orc, functor_kat, t):
+    """Factor2d3dDist / Factor2d3dFxfyDist (cv::projectPoints, OpenCV coefficient order, camera t): the oracle's values are
+    pinned to cv2.projectPoints by the golden vectors; here the kernel's closed form is checked against the oracle."""
+    k = functor_kat
+    src = "krt3d0" if t in (0, 1) else "krt3d2"
+    free = abi.KRT_FREE[t]
+    for i in range(0, len(k[src + "_uv"]), 2):
+        cam, uv, xyz = k[src + "_cam"][i], k[src + "_uv"][i], k[src + "_xyz"][i]
+        r, J = np.zeros(2), np.zeros((2, len(free)))
+        hm.hm_krt_obs3d(C.c_int(t), d(cam), as_ptr(f32(uv), C.c_float), d(xyz), d(r), as_ptr(J, C.c_double))
+        want_r = orc.krt_2d3d_factor(t, cam, uv, xyz)
+        want_J = orc.krt_2d3d_jac(t, cam, uv, xyz)[:, free]
+        assert np.abs(r - want_r).max() < 1e-9
+        assert np.abs(J - want_J).max() / np.abs(want_J).max() < 1e-10

@@ -386,15 +386,26 @@ __global__ void __launch_bounds__(256) k_schur_offdiag(int nub, const int64_t* _
 #pragma unroll
       for (int c = 0; c < NCL; ++c) acc[a * NCL + c] += x[3 * a] * y[3 * c] + x[3 * a + 1] * y[3 * c + 1] + x[3 * a + 2] * y[3 * c + 2];
   }
+  // reduce-scatter over the warp: element e of the block ends up in lane e * (32 / NP); those lanes store it (and its transpose)
+  constexpr int NN = NCL * NCL, NP = NN <= 16 ? 16 : 32, REST = NN > 32 ? NN - 32 : 0;
+  double* S = Sval + (size_t)ub_pos[b] * NN;
+  double* St = Sval + (size_t)ub_pos_t[b] * NN;
+  {
+    double v[NP];
 #pragma unroll
-  for (int i = 0; i < NCL * NCL; ++i) acc[i] = warp_sum(acc[i]);
-  if (lane == 0) {
-    double* S = Sval + (size_t)ub_pos[b] * NCL * NCL;
-    double* St = Sval + (size_t)ub_pos_t[b] * NCL * NCL;
+    for (int i = 0; i < NP; ++i) v[i] = i < NN ? acc[i] : 0.0;
+    const double tot = warp_reduce_scatter<NP>(v, lane);
+    const int e = lane / (32 / NP);
+    if (lane % (32 / NP) == 0 && e < NN) { S[e] = -tot; St[(e % NCL) * NCL + e / NCL] = -tot; }
+  }
+  if (REST > 0) {  // NCL = 6: elements 32..35
+    constexpr int RP = 4;
+    double v[RP];
 #pragma unroll
-    for (int a = 0; a < NCL; ++a)
-#pragma unroll
-      for (int c = 0; c < NCL; ++c) { S[a * NCL + c] = -acc[a * NCL + c]; St[c * NCL + a] = -acc[a * NCL + c]; }
+    for (int i = 0; i < RP; ++i) v[i] = (REST > 0 && 32 + i < NN) ? acc[(32 + i) < NN ? 32 + i : 0] : 0.0;
+    const double tot = warp_reduce_scatter<RP>(v, lane);
+    const int e = 32 + lane / (32 / RP);
+    if (lane % (32 / RP) == 0 && e < NN) { S[e] = -tot; St[(e % NCL) * NCL + e / NCL] = -tot; }
   }
 }
 

@@ -108,6 +108,39 @@ __device__ __forceinline__ double warp_max(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
   return v;
 }
+// Warp reduction of NP values per lane (NP a power of two <= 32) that SCATTERS the totals: at every step a lane keeps one
+// half of its values and adds the partner's copy of that half, so NP-1 (+ log2(32/NP)) shuffles do what 5*NP would in
+// NP separate butterflies.  Returns the warp total of element  lane / (32/NP)  (every element ends up in 32/NP lanes).
+// Fixed order -> bit-reproducible.
+template <int C, int O>
+struct WarpRS {
+  static __device__ __forceinline__ void run(double* v, int lane) {
+    if (C > 1) {
+      constexpr int H = C > 1 ? C / 2 : 1;
+      const bool up = (lane & O) != 0;
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const double send = up ? v[i] : v[i + H];
+        const double keep = up ? v[i + H] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+      }
+      WarpRS<H, O / 2>::run(v, lane);
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], O);
+      WarpRS<1, O / 2>::run(v, lane);
+    }
+  }
+};
+template <int C>
+struct WarpRS<C, 0> {
+  static __device__ __forceinline__ void run(double*, int) {}
+};
+template <int NP>
+__device__ __forceinline__ double warp_reduce_scatter(double (&v)[NP], int lane) {
+  static_assert(NP >= 1 && NP <= 32 && (NP & (NP - 1)) == 0, "NP must be a power of two <= 32");
+  WarpRS<NP, 16>::run(v, lane);
+  return v[0];
+}
 // block-wide sum of NV values per thread; result valid in thread 0.  sm must hold NV * (blockDim/32) doubles.
 template <int NV>
 __device__ __forceinline__ void block_sum(double (&v)[NV], double* sm) {

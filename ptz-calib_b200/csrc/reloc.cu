@@ -13,6 +13,9 @@
 #include "common.cuh"
 #include "ptz_math.cuh"
 
+#ifndef PTZ_RELOC_MINB
+#define PTZ_RELOC_MINB 12 // resident warps (= CTAs) per SM the register budget of k_reloc is sized for
+#endif
 namespace ptz {
 
 struct RelocArgs {
@@ -28,13 +31,18 @@ struct RelocArgs {
   double* local15;
 };
 
+// all lanes end with the same NV warp totals: reduce-scatter (NP-1 shuffles) + one broadcast per value, instead of NV
+// five-step butterflies; every lane receives the very same bits, which the lane-redundant LM logic below relies on
 template <int NV>
-__device__ __forceinline__ void warp_allreduce(double (&v)[NV]) {
+__device__ __forceinline__ void warp_allreduce(double (&v)[NV], int lane) {
+  constexpr int NP = NV <= 16 ? 16 : 32;
+  static_assert(NV <= 32, "at most 32 sums");
+  double t[NP];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
+  for (int i = 0; i < NP; ++i) t[i] = i < NV ? v[i] : 0.0;
+  const double tot = warp_reduce_scatter<NP>(t, lane);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
-  }
+  for (int i = 0; i < NV; ++i) v[i] = __shfl_sync(0xffffffffu, tot, i * (32 / NP));
 }
 
 template <int TYPE>
@@ -49,9 +57,9 @@ __device__ __forceinline__ int krt_free_index(int j) {
 
 // one pass over the query's matches at camera x: cost, and (when JAC) A = J^T J (upper, row-major), g = J^T r
 template <int TYPE, bool JAC>
-__device__ __forceinline__ void reloc_pass(const double x[15], int N, int lane, const double4* sm, int smem_matches, const float2* uv_ref,
-                                           const float2* uv_cur, const double* refK4, const double* refd, int npts, const float2* puv,
-                                           const double* pxyz, const double* ref21, double* out /*[NA+NF+1]*/) {
+__device__ __forceinline__ void reloc_pass(const double* x /*[15], shared*/, int N, int lane, const double4* sm, int smem_matches, const float2* uv_ref,
+                                           const float2* uv_cur, int npts, const float2* puv, const double* pxyz, const double* ref21,
+                                           double* out /*[NA+NF+1]*/) {
   constexpr int NF = krt_nfree(TYPE), NA = NF * (NF + 1) / 2, NV = NA + NF + 1;
   double acc[NV];
 #pragma unroll
@@ -68,6 +76,9 @@ __device__ __forceinline__ void reloc_pass(const double x[15], int N, int lane, 
       uv2 = *reinterpret_cast<const float2*>(&m.w);
       ok = !isnan(uv2.x);
     } else {
+      double refK4[4], refd[5];  // beyond the staging cap (rare): recompute from global
+      for (int j = 0; j < 4; ++j) refK4[j] = ref21[j];
+      for (int j = 0; j < 5; ++j) refd[j] = ref21[16 + j];
       const float2 u1 = uv_ref[i];
       ok = krt_precompute(TYPE, refK4, refd, u1.x, u1.y, n);
       uv2 = uv_cur[i];
@@ -107,13 +118,13 @@ __device__ __forceinline__ void reloc_pass(const double x[15], int N, int lane, 
       for (int a = 0; a < NF; ++a) acc[NA + a] += J[a] * r[0] + J[NF + a] * r[1];
     }
   }
-  warp_allreduce<NV>(acc);
+  warp_allreduce<NV>(acc, lane);
 #pragma unroll
   for (int i = 0; i < NV; ++i) out[i] = acc[i];
 }
 
 template <int TYPE>
-__global__ void __launch_bounds__(32) k_reloc(RelocArgs a) {
+__global__ void __launch_bounds__(32, PTZ_RELOC_MINB) k_reloc(RelocArgs a) {
   constexpr int NF = krt_nfree(TYPE), NA = NF * (NF + 1) / 2, NV = NA + NF + 1;
   extern __shared__ double4 sm[];
   const int q = blockIdx.x, lane = threadIdx.x;
@@ -127,41 +138,49 @@ __global__ void __launch_bounds__(32) k_reloc(RelocArgs a) {
   const int npts = a.pt_off ? (int)(a.pt_off[q + 1] - p0) : 0;
   const float2* puv = a.pt_uv + p0;
   const double* pxyz = a.pt_xyz + 3 * p0;
-  double refK4[4], refd[5];
-  for (int j = 0; j < 4; ++j) refK4[j] = ref[j];
-  for (int j = 0; j < 5; ++j) refd[j] = ref[16 + j];
   // stage the parameter-independent part of every match
-  for (int i = lane; i < N && i < a.smem_matches; i += 32) {
-    double n[3];
-    const float2 u1 = uv_ref[i];
-    const bool ok = krt_precompute(TYPE, refK4, refd, u1.x, u1.y, n);
-    float2 u2 = uv_cur[i];
-    if (!ok) u2.x = nanf("");
-    double4 m;
-    m.x = n[0]; m.y = n[1]; m.z = n[2];
-    *reinterpret_cast<float2*>(&m.w) = u2;
-    sm[i] = m;
+  {
+    double refK4[4], refd[5];
+    for (int j = 0; j < 4; ++j) refK4[j] = ref[j];
+    for (int j = 0; j < 5; ++j) refd[j] = ref[16 + j];
+    for (int i = lane; i < N && i < a.smem_matches; i += 32) {
+      double n[3];
+      const float2 u1 = uv_ref[i];
+      const bool ok = krt_precompute(TYPE, refK4, refd, u1.x, u1.y, n);
+      float2 u2 = uv_cur[i];
+      if (!ok) u2.x = nanf("");
+      double4 m;
+      m.x = n[0]; m.y = n[1]; m.z = n[2];
+      *reinterpret_cast<float2*>(&m.w) = u2;
+      sm[i] = m;
+    }
+  }
+  // The LM state is the same in every lane; it lives in shared memory (one copy per warp, broadcast reads) so that the
+  // registers of the match loop are not shared with it.  Every lane stores the same bits; __syncwarp orders them.
+  __shared__ double x[15], cand[15], A[NA], g[NF], scale[NF], diag[NF];
+  {
+    double x0[15];
+    krt_to_local(ref, a.init_cam + 21 * (size_t)q, x0);  // Add2d2dConstraints: reference-local frame
+    if (lane == 0) for (int j = 0; j < 15; ++j) x[j] = x0[j];
   }
   __syncwarp();
-  // Add2d2dConstraints: reference-local frame
-  double x[15], cand[15];
-  krt_to_local(ref, a.init_cam + 21 * (size_t)q, x);
   const ptz_solver_options& o = a.opt;
   // ---- TrustRegionMinimizer (Ceres 1.14), dense normal equations
-  double ev[NV], A[NA], g[NF], scale[NF], diag[NF], y[NF];
-  reloc_pass<TYPE, true>(x, N, lane, sm, a.smem_matches, uv_ref, uv_cur, refK4, refd, npts, puv, pxyz, ref, ev);
+  double ev[NV];
+  reloc_pass<TYPE, true>(x, N, lane, sm, a.smem_matches, uv_ref, uv_cur, npts, puv, pxyz, ref, ev);
+  if (lane == 0) {
 #pragma unroll
-  for (int i = 0; i < NA; ++i) A[i] = ev[i];
+    for (int i = 0; i < NA; ++i) A[i] = ev[i];
 #pragma unroll
-  for (int i = 0; i < NF; ++i) g[i] = ev[NA + i];
+    for (int i = 0; i < NF; ++i) g[i] = ev[NA + i];
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < NF; ++i) { scale[i] = o.jacobi_scaling ? 1.0 / (1.0 + sqrt(ev[k])) : 1.0; k += NF - i; }
+  }
+  __syncwarp();
   double x_cost = ev[NA + NF];
   const double initial_cost = x_cost;
   double min_cost = x_cost;
-  {
-    int k = 0;
-#pragma unroll
-    for (int i = 0; i < NF; ++i) { scale[i] = o.jacobi_scaling ? 1.0 / (1.0 + sqrt(A[k])) : 1.0; k += NF - i; }
-  }
   double x_norm = 0;
   for (int j = 0; j < 15; ++j) x_norm += x[j] * x[j];
   x_norm = sqrt(x_norm);
@@ -178,7 +197,7 @@ __global__ void __launch_bounds__(32) k_reloc(RelocArgs a) {
     if (radius <= o.min_trust_region_radius) { termination = PTZ_CONVERGENCE; break; }
     ++iteration;
     // scaled system  As = s A s,  gs = s g ; D^2 = clamp(diag As) / radius
-    double L[NF * NF];
+    double L[NF * NF], y[NF];
     {
       int k = 0;
 #pragma unroll
@@ -187,8 +206,12 @@ __global__ void __launch_bounds__(32) k_reloc(RelocArgs a) {
         for (int j = i; j < NF; ++j) { const double v = A[k++] * scale[i] * scale[j]; L[i * NF + j] = v; L[j * NF + i] = v; }
     }
     if (!reuse_diagonal) {
+      __syncwarp();
+      if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < NF; ++i) diag[i] = fmin(fmax(L[i * NF + i], o.min_lm_diagonal), o.max_lm_diagonal);
+        for (int i = 0; i < NF; ++i) diag[i] = fmin(fmax(L[i * NF + i], o.min_lm_diagonal), o.max_lm_diagonal);
+      }
+      __syncwarp();
     }
     double ytAy = 0, ygs = 0;
     double As[NF * NF];
@@ -222,17 +245,26 @@ __global__ void __launch_bounds__(32) k_reloc(RelocArgs a) {
       continue;
     }
     num_invalid = 0;
-#pragma unroll
-    for (int j = 0; j < 15; ++j) cand[j] = x[j];
     double step2 = 0;
+    {
+      double c[15];
 #pragma unroll
-    for (int i = 0; i < NF; ++i) {
-      const int idx = krt_free_index<TYPE>(i);
-      cand[idx] = x[idx] + (-y[i] * scale[i]);
-      step2 += (x[idx] - cand[idx]) * (x[idx] - cand[idx]);
+      for (int j = 0; j < 15; ++j) c[j] = x[j];
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const int idx = krt_free_index<TYPE>(i);
+        c[idx] = x[idx] + (-y[i] * scale[i]);
+        step2 += (x[idx] - c[idx]) * (x[idx] - c[idx]);
+      }
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 15; ++j) cand[j] = c[j];
+      }
+      __syncwarp();
     }
     // candidate cost together with its normal equations (they are needed as soon as the step is accepted)
-    reloc_pass<TYPE, true>(cand, N, lane, sm, a.smem_matches, uv_ref, uv_cur, refK4, refd, npts, puv, pxyz, ref, ev);
+    reloc_pass<TYPE, true>(cand, N, lane, sm, a.smem_matches, uv_ref, uv_cur, npts, puv, pxyz, ref, ev);
     double cand_cost = ev[NA + NF];
     if (!isfinite(cand_cost)) cand_cost = 1.7976931348623157e308;
     const double step_norm = sqrt(step2);
@@ -241,16 +273,22 @@ __global__ void __launch_bounds__(32) k_reloc(RelocArgs a) {
     if (fabs(cost_change) <= o.function_tolerance * x_cost) { termination = PTZ_CONVERGENCE; break; }
     const double rho = cost_change / model_cost_change;
     if (rho > o.min_relative_decrease) {
+      __syncwarp();
+      if (lane == 0) {
 #pragma unroll
-      for (int j = 0; j < 15; ++j) x[j] = cand[j];
+        for (int j = 0; j < 15; ++j) x[j] = cand[j];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) A[i] = ev[i];
+#pragma unroll
+        for (int i = 0; i < NF; ++i) g[i] = ev[NA + i];
+      }
+      __syncwarp();
       x_norm = 0;
       for (int j = 0; j < 15; ++j) x_norm += x[j] * x[j];
       x_norm = sqrt(x_norm);
-#pragma unroll
-      for (int i = 0; i < NA; ++i) A[i] = ev[i];
       grad_max = 0;
 #pragma unroll
-      for (int i = 0; i < NF; ++i) { g[i] = ev[NA + i]; grad_max = fmax(grad_max, fabs(g[i])); }
+      for (int i = 0; i < NF; ++i) grad_max = fmax(grad_max, fabs(g[i]));
       x_cost = cand_cost;
       radius = radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rho - 1.0, 3.0));
       radius = fmin(o.max_trust_region_radius, radius);

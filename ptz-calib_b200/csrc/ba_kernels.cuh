@@ -569,75 +569,124 @@ __global__ void k_unscale(int V, int nb, const double* __restrict__ Linv, const 
 //     beta' = gamma'/gamma ; alpha' = gamma' / (delta - beta' gamma'/alpha)
 // A neighbour's r' is recomputed on the fly from its PREVIOUS (r, w, s) (one contiguous gather), so no barrier is needed
 // between the vector update and the sparse product; the state is ping-ponged so readers never race the owner.
+//
+// Multi-GPU (MULTI): the ROWS are sharded across the ranks of one NVLink/NVSwitch box, W kernels (one per GPU) run the
+// same iteration in lock step.  Every rank keeps a full replica of the (r, w, s) state in a peer-mapped arena (CUDA IPC);
+// the owner of a row stores its new state into ALL replicas (plain stores over NVLink), every CTA stores its partial dot
+// products into all replicas, and the one barrier per iteration spans all CTAs of all GPUs: release-increment of a counter
+// in every replica (system scope), spin on the local one.  All ranks then sum the same partials in the same order, take
+// bit-identical decisions and leave together.  Sparse product, vector update, exchange and reduction are one kernel: there
+// is no NCCL call inside a linear solve.
 // -------------------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
 struct CgArgs {
   int V, nb, n;            // n = V*NCL + nb
   const int* rowptr; const int* col; const double* Sval;
   int nav; const int* ann_view; const int* ann_idx; const double* C;   // scaled coupling strips [nav][NCL][nb]
   const int* order;        // slot -> row: consecutive slots are neighbouring views (Cuthill-McKee), one contiguous run per CTA
-  double *st0, *st1;       // ping-pong state, 3*n doubles each
-  double *x, *p;
-  double* partial;         // [2][gridDim][2]
-  unsigned int* bar;       // grid barrier counter, zeroed before the launch
+  // arena replicas (index = rank; [rank] is local).  Same layout everywhere: ctrl | partial | st0 | st1 | x
+  char* arena[kMaxPeers];
+  size_t off_partial, off_st0, off_st1, off_x;
+  int W, rank;             // ranks sharing the rows; this rank owns slots [rank*slots_per_rank, (rank+1)*slots_per_rank)
+  int slots_per_rank;
+  double* p;               // search direction (owned rows only, local)
   int smem_blocks;         // blocks of S (and their column indices) each warp keeps in shared memory for the whole solve
   int debug;               // timing experiments only (PTZ_CG_DEBUG): 1 = skip the sparse product, 2 = skip the grid barrier
   int max_iter; double tol;
-  int* out_info;           // [0] iterations, [1] status (0 converged, 1 hit cap, 2 breakdown)
+  int* out_info;           // [0] iterations, [1] status (0 converged, 1 hit cap, 2 breakdown, 3 barrier timeout)
   double* out_res;         // [0] |r~| / |b~|
 };
+// arena control block: [0] barrier arrival counter (never reset), [1] arrivals consumed by the barriers passed so far (the same
+// on every rank; carried from solve to solve, so launches of different grid sizes can share the counter)
+constexpr size_t kArenaCtrlBytes = 256;
 
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+template <bool MULTI>
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  if (MULTI) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// block partial -> global slot, grid barrier, then every warp sums all slots in the same order (bitwise identical everywhere)
-__device__ __forceinline__ void grid_reduce2(double& a, double& b, double* partial, unsigned int* bar, unsigned int& epoch, double (*sred)[2]) {
+template <bool MULTI>
+__device__ __forceinline__ void red_release_inc_u64(unsigned long long* p) {
+  if (MULTI) asm volatile("red.release.sys.global.add.u64 [%0], 1;" :: "l"(p) : "memory");
+  else asm volatile("red.release.gpu.global.add.u64 [%0], 1;" :: "l"(p) : "memory");
+}
+// barrier over all CTAs of all ranks; returns false when a peer did not show up within ~20 s (never on a healthy run)
+template <bool MULTI>
+__device__ __forceinline__ bool cg_barrier(const CgArgs& A, unsigned long long& arrived, int* s_flag) {
+  if (threadIdx.x == 0) {
+    // release-increment: orders this CTA's writes (published to thread 0 by the __syncthreads before) before the arrival
+    for (int k = 0; k < A.W; ++k) red_release_inc_u64<MULTI>(reinterpret_cast<unsigned long long*>(A.arena[k]));
+    const unsigned long long target = arrived + (unsigned long long)(gridDim.x * A.W);
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(A.arena[A.rank]);
+    int ok = 1;
+    if (MULTI) {
+      const long long t0 = clock64();
+      while (ld_acquire_u64<true>(mine) < target) {
+        if (clock64() - t0 > 40000000000ll) { ok = 0; break; }
+      }
+    } else {
+      while (ld_acquire_u64<false>(mine) < target) { }
+    }
+    *s_flag = ok;
+  }
+  __syncthreads();
+  // every thread acquires: its later plain (L1-cached) loads must not be served from lines older than this barrier
+  if (MULTI) asm volatile("fence.acq_rel.sys;" ::: "memory");
+  else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  arrived += (unsigned long long)(gridDim.x * A.W);
+  return *s_flag != 0;
+}
+// block partial -> slot in every replica, barrier, then every warp sums all slots in the same order (bitwise identical
+// everywhere, on every rank)
+template <bool MULTI>
+__device__ __forceinline__ bool grid_reduce2(const CgArgs& A, double& a, double& b, int parity, unsigned long long& arrived, double (*sred)[2], int* s_flag) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   a = warp_sum(a); b = warp_sum(b);
   if (lane == 0) { sred[wid][0] = a; sred[wid][1] = b; }
   __syncthreads();
-  double* buf = partial + (size_t)(epoch & 1) * gridDim.x * 2;
+  const int nslot = gridDim.x * A.W;
+  const size_t boff = A.off_partial + (size_t)(parity & 1) * nslot * sizeof(double2);
   if (threadIdx.x == 0) {
     double s0 = 0, s1 = 0;
     for (int w = 0; w < nwarp; ++w) { s0 += sred[w][0]; s1 += sred[w][1]; }
-    __stcg(reinterpret_cast<double2*>(buf) + blockIdx.x, make_double2(s0, s1));
-    // release-increment: orders this CTA's writes (published to thread 0 by the barrier above) before the arrival
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
-    const unsigned int target = (epoch + 1u) * gridDim.x;
-    while (ld_acquire_u32(bar) < target) { }
+    for (int k = 0; k < A.W; ++k) __stcg(reinterpret_cast<double2*>(A.arena[k] + boff) + A.rank * gridDim.x + blockIdx.x, make_double2(s0, s1));
   }
-  __syncthreads();
+  const bool ok = cg_barrier<MULTI>(A, arrived, s_flag);
+  const double2* buf = reinterpret_cast<const double2*>(A.arena[A.rank] + boff);
   double s0 = 0, s1 = 0;
-  // every thread acquires: its later plain (L1-cached) loads must not be served from lines older than this barrier
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
-  for (int i = lane; i < (int)gridDim.x; i += 32) { const double2 v = __ldcg(reinterpret_cast<const double2*>(buf) + i); s0 += v.x; s1 += v.y; }
+  for (int i = lane; i < nslot; i += 32) { const double2 v = __ldcg(buf + i); s0 += v.x; s1 += v.y; }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
   a = s0; b = s1;
-  ++epoch;
+  return ok;
 }
 
 // MAXT = CTA width (256 / 512 / 1024 threads): wide CTAs keep one row per warp on larger systems (one CTA per SM either way)
-template <int NCL, int MAXT>
+template <int NCL, int MAXT, bool MULTI>
 __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
   constexpr int SLOTS = 32 / NCL, NB = NCL * NCL;
   extern __shared__ double cg_smem[];
   __shared__ double sred[MAXT / 32][2];
+  __shared__ int s_flag;
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;
   const int la = lane % NCL, ls = lane / NCL;
   const bool lact = lane < SLOTS * NCL;
   const int V = A.V, nb = A.nb, nrows = V + (nb > 0 ? 1 : 0), boff = V * NCL;
+  const int W = MULTI ? A.W : 1;
   // ---- the rows of a warp are the same in every iteration: keep (a prefix of) their S blocks and column indices on chip
   const int cap = A.smem_blocks;
   double* Bs = cg_smem + (size_t)wid * cap * NB;
   int* cs = reinterpret_cast<int*>(cg_smem + (size_t)wpb * cap * NB) + (size_t)wid * cap;
-  // slots [blockIdx*per, (blockIdx+1)*per) belong to this CTA; warp w takes every wpb-th of them
-  const int nslots = nrows, per = (nslots + gridDim.x - 1) / gridDim.x;
+  // this rank's slots [slot0, slot1); inside, slots [blockIdx*per, (blockIdx+1)*per) belong to this CTA; warp w takes every wpb-th
+  const int slot0 = A.rank * A.slots_per_rank, slot1 = min(nrows, slot0 + A.slots_per_rank);
+  const int per = (A.slots_per_rank + gridDim.x - 1) / gridDim.x;
+  const int cta0 = slot0 + blockIdx.x * per;
   int ncached = 0;
   for (int sl = wid; sl < per && ncached < cap; sl += wpb) {
-    const int slot = blockIdx.x * per + sl;
-    if (slot >= V) break;
+    const int slot = cta0 + sl;
+    if (slot >= min(V, slot1)) break;
     const int row = A.order[slot];
     const int b0 = A.rowptr[row], take = min(A.rowptr[row + 1] - b0, cap - ncached);
     for (int e = lane; e < take * NB; e += 32) Bs[(size_t)ncached * NB + e] = A.Sval[(size_t)b0 * NB + e];
@@ -645,30 +694,36 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
     ncached += take;
   }
   __syncwarp();
-  unsigned int epoch = 0;
+  unsigned long long* ctrl = reinterpret_cast<unsigned long long*>(A.arena[A.rank]);
+  unsigned long long arrived = ctrl[1];  // arrivals consumed so far on this arena (same on every rank)
   double alpha = 0.0, beta = 0.0, gamma_old = 0.0, gamma0 = 0.0, gamma_last = 0.0;
-  double* so = A.st0;  // previous state (read by everyone)
-  double* sn = A.st1;  // next state (written by the owner only)
+  size_t off_o = A.off_st0, off_n = A.off_st1;  // previous state (read by everyone) / next state (written by the owner only)
+  double* const xl = reinterpret_cast<double*>(A.arena[A.rank] + A.off_x);
   int it = 0, status = 1;
   for (;; ++it) {
+    const double* so = reinterpret_cast<const double*>(A.arena[A.rank] + off_o);
     double g = 0, d = 0;
     int bi = 0;  // running index of this warp's blocks
     for (int sl = wid; sl < per; sl += wpb) {
-      const int slot = blockIdx.x * per + sl;
-      if (slot >= nslots) break;
+      const int slot = cta0 + sl;
+      if (slot >= slot1) break;
       const int row = slot < V ? A.order[slot] : V;
       if (row < V) {
-        double rn = 0;
+        double rn = 0, s_n = 0;
         if (lane < NCL) {
           const int i = row * NCL + lane;
           const double ro = __ldcg(so + (row * 3 + 0) * NCL + lane), wo = __ldcg(so + (row * 3 + 1) * NCL + lane), s_o = __ldcg(so + (row * 3 + 2) * NCL + lane);
           const double pn = ro + beta * A.p[i];
-          const double s_n = wo + beta * s_o;
+          s_n = wo + beta * s_o;
           A.p[i] = pn;
-          A.x[i] += alpha * pn;
+          xl[i] += alpha * pn;
           rn = ro - alpha * s_n;
-          sn[(row * 3 + 0) * NCL + lane] = rn;
-          sn[(row * 3 + 2) * NCL + lane] = s_n;
+          // the row's new state goes into every replica; r and s now, so that the (remote) stores drain behind the product
+          for (int k = 0; k < W; ++k) {
+            double* sn = reinterpret_cast<double*>(A.arena[MULTI ? k : A.rank] + off_n);
+            sn[(row * 3 + 0) * NCL + lane] = rn;
+            sn[(row * 3 + 2) * NCL + lane] = s_n;
+          }
         }
         const int b0 = A.rowptr[row], nblk = A.rowptr[row + 1] - b0;
         double sum = 0;
@@ -730,19 +785,19 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
               for (int j = 0; j < nb; ++j) tot += strip[j] * (__ldcg(q + j) - alpha * (__ldcg(q + nb + j) + beta * __ldcg(q + 2 * nb + j)));
             }
           }
-          sn[(row * 3 + 1) * NCL + lane] = tot;
+          for (int k = 0; k < W; ++k) reinterpret_cast<double*>(A.arena[MULTI ? k : A.rank] + off_n)[(row * 3 + 1) * NCL + lane] = tot;
           g += rn * rn; d += tot * rn;
         }
-      } else if (lane < nb) {
+      } else if (lane < nb) {  // dense border row (single rank only)
         const int i = boff + lane;
         const double* q = so + 3 * (size_t)boff;
         const double ro = __ldcg(q + lane), wo = __ldcg(q + nb + lane), s_o = __ldcg(q + 2 * nb + lane);
         const double pn = ro + beta * A.p[i];
         const double s_n = wo + beta * s_o;
         A.p[i] = pn;
-        A.x[i] += alpha * pn;
+        xl[i] += alpha * pn;
         const double rn = ro - alpha * s_n;
-        double* qn = sn + 3 * (size_t)boff;
+        double* qn = reinterpret_cast<double*>(A.arena[A.rank] + off_n) + 3 * (size_t)boff;
         qn[lane] = rn; qn[2 * nb + lane] = s_n;
         double tot = rn;  // unit diagonal block
         for (int k = 0; k < A.nav; ++k) {
@@ -754,7 +809,8 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
         g += rn * rn; d += tot * rn;
       }
     }
-    if (A.debug & 2) { g = 1.0 / (it + 1.0); d = 1.0; __syncthreads(); } else grid_reduce2(g, d, A.partial, A.bar, epoch, sred);
+    if (A.debug & 2) { g = 1.0 / (it + 1.0); d = 1.0; __syncthreads(); }
+    else if (!grid_reduce2<MULTI>(A, g, d, it, arrived, sred, &s_flag)) { status = 3; break; }
     gamma_last = g;
     if (it == 0) {
       gamma0 = g;
@@ -771,9 +827,26 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
       alpha = g / den;
     }
     gamma_old = g;
-    double* t = so; so = sn; sn = t;
+    const size_t t = off_o; off_o = off_n; off_n = t;
+  }
+  if (MULTI && status != 3) {
+    // every rank needs the whole solution: push the owned rows of x into the other replicas, then meet once more so that
+    // nobody leaves (and lets later kernels read x) before all pushes have landed
+    for (int sl = wid; sl < per; sl += wpb) {
+      const int slot = cta0 + sl;
+      if (slot >= min(V, slot1)) break;
+      const int row = A.order[slot];
+      if (lane < NCL) {
+        const double v = xl[row * NCL + lane];
+        for (int k = 0; k < W; ++k)
+          if (k != A.rank) reinterpret_cast<double*>(A.arena[k] + A.off_x)[row * NCL + lane] = v;
+      }
+    }
+    __syncthreads();
+    if (!cg_barrier<true>(A, arrived, &s_flag)) status = 3;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctrl[1] = arrived;
     A.out_info[0] = it; A.out_info[1] = status;
     A.out_res[0] = gamma0 > 0 ? sqrt(gamma_last / gamma0) : 0.0;
   }

@@ -47,6 +47,70 @@ static NcclState g_nccl;
     }                                                                                                        \
   } while (0)
 
+// ---- peer arena of the row-sharded CG (k_cg): one cudaMalloc'ed block per rank, mapped into every other rank of the box
+// through CUDA IPC.  Persistent (grown on demand, collectively): its barrier counter and epoch carry over between solves.
+struct PeerArena {
+  char* base[kMaxPeers] = {nullptr};
+  size_t bytes = 0;
+  int world = 0;  // world size it was built for
+};
+static PeerArena g_arena;
+
+static void arena_release() {
+  if (!g_arena.bytes) return;
+  cudaDeviceSynchronize();
+  for (int k = 0; k < g_arena.world; ++k) {
+    if (!g_arena.base[k]) continue;
+    if (k == g_nccl.rank || g_arena.world == 1) cudaFree(g_arena.base[k]);
+    else cudaIpcCloseMemHandle(g_arena.base[k]);
+    g_arena.base[k] = nullptr;
+  }
+  g_arena.bytes = 0;
+  g_arena.world = 0;
+}
+
+// Collective over the ranks of the communicator (every rank asks for the same size: the reduced system is replicated).
+static void arena_ensure(size_t bytes, cudaStream_t s) {
+  const int W = g_nccl.world, R = g_nccl.rank;
+  if (g_arena.bytes >= bytes && g_arena.world == W) return;
+  if (W > kMaxPeers) throw CudaError(PTZ_ERR_UNSUPPORTED, "more than 8 ranks per box");
+  if (W > 1) {  // nobody may still be spinning on, or writing into, the old arena
+    PTZ_CUDA(cudaStreamSynchronize(s));
+    DevBuf<double> d_tok;
+    d_tok.alloc(1, nullptr);
+    PTZ_CUDA(cudaMemsetAsync(d_tok.p, 0, 8, s));
+    PTZ_NCCL(ncclAllReduce(d_tok.p, d_tok.p, 1, ncclDouble, ncclSum, g_nccl.comm, s));
+    PTZ_CUDA(cudaStreamSynchronize(s));
+  }
+  arena_release();
+  const size_t want = std::max(bytes + bytes / 2, (size_t)8 << 20);
+  char* mine = nullptr;
+  PTZ_CUDA(cudaMalloc((void**)&mine, want));
+  PTZ_CUDA(cudaMemset(mine, 0, want));
+  PTZ_CUDA(cudaDeviceSynchronize());
+  g_arena.base[R] = mine;
+  g_arena.world = W;
+  g_arena.bytes = want;
+  if (W > 1) {
+    cudaIpcMemHandle_t h;
+    PTZ_CUDA(cudaIpcGetMemHandle(&h, mine));
+    DevBuf<char> d_h, d_all;
+    d_h.alloc(sizeof(h), nullptr);
+    d_all.alloc(sizeof(h) * W, nullptr);
+    PTZ_CUDA(cudaMemcpyAsync(d_h.p, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    PTZ_NCCL(ncclAllGather(d_h.p, d_all.p, sizeof(h), ncclChar, g_nccl.comm, s));  // also the barrier after everybody's memset
+    std::vector<cudaIpcMemHandle_t> all(W);
+    PTZ_CUDA(cudaMemcpyAsync(all.data(), d_all.p, sizeof(h) * W, cudaMemcpyDeviceToHost, s));
+    PTZ_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < W; ++k) {
+      if (k == R) continue;
+      void* ptr = nullptr;
+      PTZ_CUDA(cudaIpcOpenMemHandle(&ptr, all[k], cudaIpcMemLazyEnablePeerAccess));
+      g_arena.base[k] = (char*)ptr;
+    }
+  }
+}
+
 static void allreduce_sum(double* buf, size_t n, cudaStream_t s) {
   if (g_nccl.world > 1 && n) PTZ_NCCL(ncclAllReduce(buf, buf, n, ncclDouble, ncclSum, g_nccl.comm, s));
 }
@@ -143,12 +207,11 @@ struct BaSolver : BaSolverBase {
   // device: work
   DevBuf<ViewTab> d_vt;
   DevBuf<double> d_scale_cam, d_scale_b, d_rec, d_part, d_viewred, d_Vh, d_gmax_part, d_diag_ray, d_diag_cam, d_diag_b, d_Lt, d_What, d_q, d_sys, d_Linv,
-      d_Linv_b, d_Sbb, d_Cs, d_cgstate, d_cgxp, d_y, d_pcg_partial, d_pcg_res, d_part3_ray, d_part3_cam, d_part3_b, d_cost_part, d_scalars, d_RiKi, d_pts_scratch, d_pts_raw,
+      d_Linv_b, d_Sbb, d_Cs, d_cgp, d_y, d_pcg_res, d_part3_ray, d_part3_cam, d_part3_b, d_cost_part, d_scalars, d_RiKi, d_pts_scratch, d_pts_raw,
       d_pts_xyz;
   DevBuf<float2> d_pts_uv;
   DevBuf<int> d_pts_view, d_ann_view, d_ann_off, d_ann_idx, d_fail, d_pcg_info, d_cpl_view, d_cpl_idx, d_ann_strip;
   DevBuf<double> d_recd, d_dpart, d_Wdh, d_Cw, d_dispp[2], d_disp_init;
-  DevBuf<unsigned int> d_bar;
   DevBuf<int> d_cg_order;
   // views into d_viewred (all-reduced once per Jacobian evaluation): U | g | cost_view | C | Hbb | gb | cost_pts(2)
   double *p_U, *p_g, *p_cost_view, *p_C, *p_Hbb, *p_gb, *p_cost_pts, *p_gabs, *p_gabs_b;
@@ -159,9 +222,13 @@ struct BaSolver : BaSolverBase {
   size_t sys_n = 0;
   double* h_scalars = nullptr;  // pinned
   int* h_info = nullptr;        // pinned: pcg info(2), fail(1)
-  int nblk_ray = 0, nblk_cam = 0, cg_cap = 1, cg_wpb = 8, cg_grid = 1;
+  int nblk_ray = 0, nblk_cam = 0, cg_cap = 1, cg_wpb = 8, cg_grid = 1, cg_slots_per_rank = 1;
+  size_t ar_partial = 0, ar_st0 = 0, ar_st1 = 0, ar_x = 0;  // arena offsets (bytes), identical on every rank
+  double* arena_ptr(size_t off) const { return reinterpret_cast<double*>(g_arena.base[g_nccl.rank] + off); }
   const void* cg_kernel() const {
-    return cg_wpb == 8 ? (const void*)k_cg<NCL, 256> : cg_wpb == 16 ? (const void*)k_cg<NCL, 512> : (const void*)k_cg<NCL, 1024>;
+    if (g_nccl.world > 1)
+      return cg_wpb == 8 ? (const void*)k_cg<NCL, 256, true> : cg_wpb == 16 ? (const void*)k_cg<NCL, 512, true> : (const void*)k_cg<NCL, 1024, true>;
+    return cg_wpb == 8 ? (const void*)k_cg<NCL, 256, false> : cg_wpb == 16 ? (const void*)k_cg<NCL, 512, false> : (const void*)k_cg<NCL, 1024, false>;
   }
 
   // LM state (names follow ceres::internal::TrustRegionMinimizer / LevenbergMarquardtStrategy)
@@ -238,10 +305,14 @@ struct BaSolver : BaSolverBase {
       // CG launch shape: one CTA per SM, as many warps per CTA (8/16/32) as it takes to give every warp at most one row
       // where possible.  Rows are handed out in Cuthill-McKee order of the view graph, a contiguous run per CTA, so that the
       // rows of a CTA are neighbouring views whose gathers overlap (L1 hits).  Then: how many blocks of S fit 200 KB of smem.
+      // Sharded problem: the rows are split across the ranks (a contiguous run of the ordering each), see k_cg.
       const int nrows = V + (nb > 0 ? 1 : 0);
-      const int need = cdiv(nrows, num_sms);
+      const int W = g_nccl.world, R = g_nccl.rank;
+      cg_slots_per_rank = cdiv(nrows, W);
+      const int my0 = R * cg_slots_per_rank, my1 = std::min(nrows, my0 + cg_slots_per_rank);
+      const int need = cdiv(cg_slots_per_rank, num_sms);
       cg_wpb = need <= 8 ? 8 : (need <= 16 ? 16 : 32);
-      cg_grid = std::min(num_sms, cdiv(nrows, cg_wpb));
+      cg_grid = std::min(num_sms, cdiv(cg_slots_per_rank, cg_wpb));
       std::vector<int> h_col(ds.nnzb);
       ds.s_col.download(h_col.data(), ds.nnzb, stream);
       PTZ_CUDA(cudaStreamSynchronize(stream));
@@ -267,14 +338,14 @@ struct BaSolver : BaSolverBase {
         }
       }
       d_cg_order.upload(order, stream);
-      const int per = cdiv(nrows, cg_grid);
+      const int per = cdiv(cg_slots_per_rank, cg_grid);
       int worst = 0;
       for (int c = 0; c < cg_grid; ++c)
         for (int w = 0; w < cg_wpb; ++w) {
           int cnt = 0;
           for (int sl = w; sl < per; sl += cg_wpb) {
-            const int slot = c * per + sl;
-            if (slot >= V) break;
+            const int slot = my0 + c * per + sl;
+            if (slot >= std::min(V, my1)) break;
             cnt += ds.h_rowptr[order[slot] + 1] - ds.h_rowptr[order[slot]];
           }
           worst = std::max(worst, cnt);
@@ -282,8 +353,24 @@ struct BaSolver : BaSolverBase {
       const size_t per_block = NCL * NCL * sizeof(double) + sizeof(int);
       const int fit = (int)((160 * 1024) / (cg_wpb * per_block));  // leave >= 60 KB of the SM's 228 KB to the L1
       cg_cap = std::max(1, std::min(worst, fit));
+      if (W > 1) {  // every rank launches the same shape (the slot of a CTA's partial sums is rank * grid + cta)
+        DevBuf<double> d_m;
+        double m[2] = {(double)cg_cap, 0.0};
+        d_m.upload(m, 2, stream);
+        PTZ_NCCL(ncclAllReduce(d_m.p, d_m.p, 2, ncclDouble, ncclMax, g_nccl.comm, stream));
+        d_m.download(m, 2, stream);
+        PTZ_CUDA(cudaStreamSynchronize(stream));
+        cg_cap = (int)m[0];
+      }
       const size_t cg_smem = (size_t)cg_wpb * cg_cap * per_block + 16;
       PTZ_CUDA(cudaFuncSetAttribute(cg_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg_smem));
+      // arena layout: ctrl | partial [2][W*grid] double2 | st0 [3n] | st1 [3n] | x [n]
+      auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+      ar_partial = kArenaCtrlBytes;
+      ar_st0 = al(ar_partial + 2 * (size_t)W * num_sms * sizeof(double2));
+      ar_st1 = al(ar_st0 + 3 * (size_t)n * sizeof(double));
+      ar_x = al(ar_st1 + 3 * (size_t)n * sizeof(double));
+      arena_ensure(al(ar_x + (size_t)n * sizeof(double)), stream);
     }
     upload(prob);
     PTZ_CUDA(cudaStreamSynchronize(stream));
@@ -409,11 +496,8 @@ struct BaSolver : BaSolverBase {
     p_Sval = d_sys.p; p_rhs = p_Sval + (size_t)ds.nnzb * NCL * NCL;
     d_Linv.alloc((size_t)V * NCL * NCL, stream); d_Linv_b.alloc(kMaxBorder * kMaxBorder, stream); d_Sbb.alloc(kMaxBorder * kMaxBorder, stream);
     d_Cs.alloc((size_t)std::max(ncpl, 1) * NCL * std::max(nb, 1), stream);
-    d_cgstate.alloc(6 * (size_t)n, stream); d_cgstate.zero(s);
-    d_cgxp.alloc(2 * (size_t)n, stream); d_cgxp.zero(s);
+    d_cgp.alloc((size_t)n, stream); d_cgp.zero(s);
     d_y.alloc(n, stream); d_y.zero(s);
-    d_bar.alloc(1, stream);
-    d_pcg_partial.alloc(2 * 2 * (size_t)num_sms * 2, stream);
     d_pcg_res.alloc(2, stream); d_pcg_info.alloc(2, stream); d_fail.alloc(1, stream); d_fail.zero(s);
     d_part3_ray.alloc(3 * (size_t)nblk_ray, stream); d_part3_ray.zero(s);
     d_part3_cam.alloc(3 * (size_t)nblk_cam, stream); d_part3_b.alloc(3, stream); d_part3_b.zero(s);
@@ -548,19 +632,21 @@ struct BaSolver : BaSolverBase {
     PTZ_TIMED(PTZ_K_PRECOND, {
       k_precond<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, ds.diag_pos.p, p_Sval, d_Linv.p, d_fail.p);
       if (nb > 0) k_precond_border<<<1, 32, 0, s>>>(nb, d_Sbb.p, d_Linv_b.p, d_fail.p);
-      k_scale_system<NCL><<<cdiv(std::max(ds.nnzb, V), 128), 128, 0, s>>>(V, ds.nnzb, ds.blk_row.p, ds.s_col.p, d_Linv.p, p_Sval, p_rhs, d_cgstate.p,
-                                                                            d_cgxp.p, d_cgxp.p + n);
+      k_scale_system<NCL><<<cdiv(std::max(ds.nnzb, V), 128), 128, 0, s>>>(V, ds.nnzb, ds.blk_row.p, ds.s_col.p, d_Linv.p, p_Sval, p_rhs, arena_ptr(ar_st0),
+                                                                            arena_ptr(ar_x), d_cgp.p);
       if (nb > 0)
-        k_scale_border<NCL><<<1, 128, 0, s>>>(V, nb, ncpl, d_cpl_view.p, d_Linv.p, d_Linv_b.p, kDisp ? d_Cw.p : p_C, d_Cs.p, p_rhs, d_cgstate.p, d_cgxp.p,
-                                              d_cgxp.p + n);
+        k_scale_border<NCL><<<1, 128, 0, s>>>(V, nb, ncpl, d_cpl_view.p, d_Linv.p, d_Linv_b.p, kDisp ? d_Cw.p : p_C, d_Cs.p, p_rhs, arena_ptr(ar_st0), arena_ptr(ar_x),
+                                              d_cgp.p);
     });
     // ---- stage 3
     CgArgs a;
     a.V = V; a.nb = nb; a.n = n;
     a.rowptr = ds.s_rowptr.p; a.col = ds.s_col.p; a.Sval = p_Sval;
     a.nav = ncpl; a.ann_view = d_cpl_view.p; a.ann_idx = d_cpl_idx.p; a.C = d_Cs.p; a.order = d_cg_order.p;
-    a.st0 = d_cgstate.p; a.st1 = d_cgstate.p + 3 * (size_t)n; a.x = d_cgxp.p; a.p = d_cgxp.p + n;
-    a.partial = d_pcg_partial.p; a.bar = d_bar.p; a.max_iter = opt.pcg_max_iterations; a.tol = opt.pcg_rel_tolerance;
+    for (int k = 0; k < kMaxPeers; ++k) a.arena[k] = g_arena.base[k];
+    a.off_partial = ar_partial; a.off_st0 = ar_st0; a.off_st1 = ar_st1; a.off_x = ar_x;
+    a.W = g_nccl.world; a.rank = g_nccl.rank; a.slots_per_rank = cg_slots_per_rank; a.p = d_cgp.p;
+    a.max_iter = opt.pcg_max_iterations; a.tol = opt.pcg_rel_tolerance;
     a.out_info = d_pcg_info.p; a.out_res = d_pcg_res.p;
     // shared-memory residency of S: every warp keeps up to cg_cap blocks (+ column indices) of its rows for the whole solve
     a.smem_blocks = cg_cap;
@@ -568,9 +654,8 @@ struct BaSolver : BaSolverBase {
     const size_t cg_smem = (size_t)cg_wpb * cg_cap * (NCL * NCL * sizeof(double) + sizeof(int)) + 16;
     void* args[] = {&a};
     PTZ_TIMED(PTZ_K_PCG, {
-      PTZ_CUDA(cudaMemsetAsync(d_bar.p, 0, sizeof(unsigned int), s));
       PTZ_CUDA(cudaLaunchCooperativeKernel(cg_kernel(), dim3(cg_grid), dim3(32 * cg_wpb), args, cg_smem, s));
-      k_unscale<NCL><<<cdiv(V + nb, 128), 128, 0, s>>>(V, nb, d_Linv.p, d_Linv_b.p, d_cgxp.p, d_y.p);
+      k_unscale<NCL><<<cdiv(V + nb, 128), 128, 0, s>>>(V, nb, d_Linv.p, d_Linv_b.p, arena_ptr(ar_x), d_y.p);
     });
     // ---- stage 4
     const int nxt = cur ^ 1;
@@ -590,6 +675,7 @@ struct BaSolver : BaSolverBase {
     ++cost_evals;
     *lin_iters = h_info[0];
     if (h_info[2] != 0) return false;          // a 3x3 / camera / border block was not positive definite
+    if (h_info[1] == 3) throw CudaError(PTZ_ERR_NCCL, "k_cg: a peer rank did not reach the cross-GPU barrier (timeout)");
     if (h_info[1] == 2) return false;          // PCG breakdown (non-finite or non-positive curvature)
     return true;
   }
@@ -1070,6 +1156,7 @@ int ptz_nccl_init(const void* id_bytes128, int rank, int world_size) {
   return guarded([&]() {
     ncclUniqueId id;
     memcpy(&id, id_bytes128, 128);
+    arena_release();
     if (g_nccl.comm) { ncclCommDestroy(g_nccl.comm); g_nccl.comm = nullptr; }
     PTZ_NCCL(ncclCommInitRank(&g_nccl.comm, world_size, id, rank));
     g_nccl.rank = rank;
@@ -1079,6 +1166,7 @@ int ptz_nccl_init(const void* id_bytes128, int rank, int world_size) {
 }
 
 int ptz_nccl_finalize(void) {
+  arena_release();
   if (g_nccl.comm) { ncclCommDestroy(g_nccl.comm); g_nccl.comm = nullptr; }
   g_nccl.rank = 0;
   g_nccl.world = 1;

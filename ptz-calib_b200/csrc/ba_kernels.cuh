@@ -570,97 +570,150 @@ __global__ void k_unscale(int V, int nb, const double* __restrict__ Linv, const 
 // A neighbour's r' is recomputed on the fly from its PREVIOUS (r, w, s) (one contiguous gather), so no barrier is needed
 // between the vector update and the sparse product; the state is ping-ponged so readers never race the owner.
 //
-// Multi-GPU (MULTI): the ROWS are sharded across the ranks of one NVLink/NVSwitch box, W kernels (one per GPU) run the
-// same iteration in lock step.  Every rank keeps a full replica of the (r, w, s) state in a peer-mapped arena (CUDA IPC);
-// the owner of a row stores its new state into ALL replicas (plain stores over NVLink), every CTA stores its partial dot
-// products into all replicas, and the one barrier per iteration spans all CTAs of all GPUs: release-increment of a counter
-// in every replica (system scope), spin on the local one.  All ranks then sum the same partials in the same order, take
-// bit-identical decisions and leave together.  Sparse product, vector update, exchange and reduction are one kernel: there
-// is no NCCL call inside a linear solve.
+// Multi-GPU (MULTI): the ROWS are sharded across the ranks of one NVLink/NVSwitch box; W kernels (one per GPU) run the same
+// iteration in lock step and exchange through peer-mapped arenas (CUDA IPC) -- sparse product, vector update, exchange and
+// reduction are ONE kernel, there is no NCCL call inside a linear solve.  The exchange is latency-bound (a few hundred
+// bytes per row), so it uses self-validating "LL" words instead of fence + flag: a double travels as two 8-byte words, each
+// holding 32 data bits and the 32-bit tag of the iteration it belongs to.  The receiver polls the DATA until both tags
+// match: one NVLink hop, no release fence waiting for write acknowledgements, no atomics.
+//   * state: the owner of a row keeps it in its local plain replica (read by the CTAs of the same GPU through L1) and
+//     pushes it as LL words into the inbox of every rank that owns a neighbouring row (peer_mask);
+//   * reduction + barrier: every CTA pushes its partial (r,r), (S~r,r) as LL words into its slot on every rank; warp 0 of
+//     every CTA polls all W x grid slots and sums them in slot order -- bit-identical totals on every rank, which therefore
+//     take the same decisions and leave together.  State and slots are double-buffered by iteration parity.
+// PTZ_CG_VRANKS=k (debug) runs the same protocol on ONE GPU with the grid split into k virtual ranks.
 // -------------------------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
 struct CgArgs {
   int V, nb, n;            // n = V*NCL + nb
-  const int* rowptr; const int* col; const double* Sval;
+  const int* rowptr; const int* col; const double* Sval;   // col: bit 31 set = the column is owned by another rank than the row
   int nav; const int* ann_view; const int* ann_idx; const double* C;   // scaled coupling strips [nav][NCL][nb]
   const int* order;        // slot -> row: consecutive slots are neighbouring views (Cuthill-McKee), one contiguous run per CTA
-  // arena replicas (index = rank; [rank] is local).  Same layout everywhere: ctrl | partial | st0 | st1 | x
+  const unsigned char* peer_mask;  // per row: ranks (bits) owning a neighbour of the row, i.e. that need its state
+  // arena replicas (index = rank; [rank] is local).  Same layout everywhere: ctrl | slots | st0 | st1 | x | ll0 | ll1
   char* arena[kMaxPeers];
-  size_t off_partial, off_st0, off_st1, off_x;
-  int W, rank;             // ranks sharing the rows; this rank owns slots [rank*slots_per_rank, (rank+1)*slots_per_rank)
+  size_t off_partial, off_st0, off_st1, off_x, off_ll0, off_ll1;
+  int W, rank;             // ranks sharing the rows; rank r owns slots [r*slots_per_rank, (r+1)*slots_per_rank)
+  int vranks;              // > 1: virtual ranks inside one launch (debug), rank = blockIdx / (gridDim / vranks)
   int slots_per_rank;
-  double* p;               // search direction (owned rows only, local)
+  double* p;               // search direction (every row has one owner)
   int smem_blocks;         // blocks of S (and their column indices) each warp keeps in shared memory for the whole solve
   int debug;               // timing experiments only (PTZ_CG_DEBUG): 1 = skip the sparse product, 2 = skip the grid barrier
   int max_iter; double tol;
-  int* out_info;           // [0] iterations, [1] status (0 converged, 1 hit cap, 2 breakdown, 3 barrier timeout)
+  int* out_info;           // [0] iterations, [1] status (0 converged, 1 hit cap, 2 breakdown, 3 peer timeout)
   double* out_res;         // [0] |r~| / |b~|
 };
-// arena control block: [0] barrier arrival counter (never reset), [1] arrivals consumed by the barriers passed so far (the same
-// on every rank; carried from solve to solve, so launches of different grid sizes can share the counter)
+// arena control block (u64 words): [0] barrier arrival counter of the single-GPU path (never reset), [1] arrivals consumed by
+// the barriers passed so far, [2] next unused LL tag (the same on every rank; carried from solve to solve)
 constexpr size_t kArenaCtrlBytes = 256;
+constexpr size_t kSlotBytes = 32;
+constexpr long long kPeerTimeoutCycles = 40000000000ll;  // ~20 s
 
-template <bool MULTI>
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
   unsigned long long v;
-  if (MULTI) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-template <bool MULTI>
-__device__ __forceinline__ void red_release_inc_u64(unsigned long long* p) {
-  if (MULTI) asm volatile("red.release.sys.global.add.u64 [%0], 1;" :: "l"(p) : "memory");
-  else asm volatile("red.release.gpu.global.add.u64 [%0], 1;" :: "l"(p) : "memory");
-}
-// barrier over all CTAs of all ranks; returns false when a peer did not show up within ~20 s (never on a healthy run)
-template <bool MULTI>
-__device__ __forceinline__ bool cg_barrier(const CgArgs& A, unsigned long long& arrived, int* s_flag) {
-  if (threadIdx.x == 0) {
-    // release-increment: orders this CTA's writes (published to thread 0 by the __syncthreads before) before the arrival
-    for (int k = 0; k < A.W; ++k) red_release_inc_u64<MULTI>(reinterpret_cast<unsigned long long*>(A.arena[k]));
-    const unsigned long long target = arrived + (unsigned long long)(gridDim.x * A.W);
-    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(A.arena[A.rank]);
-    int ok = 1;
-    if (MULTI) {
-      const long long t0 = clock64();
-      while (ld_acquire_u64<true>(mine) < target) {
-        if (clock64() - t0 > 40000000000ll) { ok = 0; break; }
-      }
-    } else {
-      while (ld_acquire_u64<false>(mine) < target) { }
-    }
-    *s_flag = ok;
-  }
-  __syncthreads();
-  // every thread acquires: its later plain (L1-cached) loads must not be served from lines older than this barrier
-  if (MULTI) asm volatile("fence.acq_rel.sys;" ::: "memory");
-  else asm volatile("fence.acq_rel.gpu;" ::: "memory");
-  arrived += (unsigned long long)(gridDim.x * A.W);
-  return *s_flag != 0;
-}
-// block partial -> slot in every replica, barrier, then every warp sums all slots in the same order (bitwise identical
-// everywhere, on every rank)
-template <bool MULTI>
-__device__ __forceinline__ bool grid_reduce2(const CgArgs& A, double& a, double& b, int parity, unsigned long long& arrived, double (*sred)[2], int* s_flag) {
+// single GPU: block partial -> slot, counter barrier, then every warp sums all slots in the same order
+__device__ __forceinline__ void grid_reduce2(const CgArgs& A, double& a, double& b, int parity, unsigned long long& arrived, double (*sred)[2]) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   a = warp_sum(a); b = warp_sum(b);
   if (lane == 0) { sred[wid][0] = a; sred[wid][1] = b; }
   __syncthreads();
-  const int nslot = gridDim.x * A.W;
-  const size_t boff = A.off_partial + (size_t)(parity & 1) * nslot * sizeof(double2);
+  double2* buf = reinterpret_cast<double2*>(A.arena[0] + A.off_partial) + (size_t)(parity & 1) * gridDim.x;
   if (threadIdx.x == 0) {
     double s0 = 0, s1 = 0;
     for (int w = 0; w < nwarp; ++w) { s0 += sred[w][0]; s1 += sred[w][1]; }
-    for (int k = 0; k < A.W; ++k) __stcg(reinterpret_cast<double2*>(A.arena[k] + boff) + A.rank * gridDim.x + blockIdx.x, make_double2(s0, s1));
+    __stcg(buf + blockIdx.x, make_double2(s0, s1));
+    // release-increment: orders this CTA's writes (published to thread 0 by the barrier above) before the arrival
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(A.arena[0]);
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" :: "l"(bar) : "memory");
+    const unsigned long long target = arrived + gridDim.x;
+    while (ld_acquire_u64(bar) < target) { }
   }
-  const bool ok = cg_barrier<MULTI>(A, arrived, s_flag);
-  const double2* buf = reinterpret_cast<const double2*>(A.arena[A.rank] + boff);
+  __syncthreads();
+  arrived += gridDim.x;
   double s0 = 0, s1 = 0;
-  for (int i = lane; i < nslot; i += 32) { const double2 v = __ldcg(buf + i); s0 += v.x; s1 += v.y; }
+  // every thread acquires: its later plain (L1-cached) loads must not be served from lines older than this barrier
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  for (int i = lane; i < (int)gridDim.x; i += 32) { const double2 v = __ldcg(buf + i); s0 += v.x; s1 += v.y; }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
   a = s0; b = s1;
-  return ok;
+}
+
+// ---- LL words
+__device__ __forceinline__ void ll_store(ulonglong2* dst, double v, unsigned int tag) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
+  const unsigned long long lo = t | (bits & 0xffffffffull), hi = t | (bits >> 32);
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" :: "l"(dst), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ bool ll_load(const ulonglong2* src, unsigned int tag, double& v) {
+  unsigned long long lo, hi;
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+  v = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+  return (unsigned int)(lo >> 32) == tag && (unsigned int)(hi >> 32) == tag;
+}
+// multi-rank reduction + barrier, two levels.  Inside a rank: plain partial + acq_rel arrival counter; the LAST CTA to arrive
+// sums the rank's partials in CTA order and pushes the rank total as LL words into the rank's slot on every rank (lane k ->
+// rank k).  Across ranks: every CTA polls the W local rank slots and adds them in rank order -- bit-identical totals on every
+// CTA of every rank.  sys_release: make this CTA's earlier PLAIN stores to peer memory visible first (end-of-solve push of
+// x).  Returns false on a peer timeout.
+__device__ __forceinline__ bool ll_reduce2(const CgArgs& A, double& a, double& b, int parity, unsigned int tag, int my_rank, int cta, int G, int W,
+                                           bool sys_release, unsigned long long& arrived, double (*sred)[2], double* s_tot) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  a = warp_sum(a); b = warp_sum(b);
+  if (lane == 0) { sred[wid][0] = a; sred[wid][1] = b; }
+  __syncthreads();
+  char* const mine = A.arena[my_rank];
+  // slots region: [2][G] plain CTA partials (double2), then [2][W] LL rank totals (2 x 16 bytes each)
+  double2* lbuf = reinterpret_cast<double2*>(mine + A.off_partial) + (size_t)(parity & 1) * G;
+  const size_t roff = A.off_partial + 2 * (size_t)G * sizeof(double2) + (size_t)(parity & 1) * W * kSlotBytes;
+  if (wid == 0) {
+    unsigned long long old = 0;
+    if (lane == 0) {
+      double s0 = 0, s1 = 0;
+      for (int w = 0; w < nwarp; ++w) { s0 += sred[w][0]; s1 += sred[w][1]; }
+      __stcg(lbuf + cta, make_double2(s0, s1));
+      if (sys_release) asm volatile("fence.acq_rel.sys;" ::: "memory");
+      // arrival: releases this CTA's writes (published to this thread by the barrier above), acquires those of earlier arrivers
+      asm volatile("atom.acq_rel.gpu.global.add.u64 %0, [%1], 1;" : "=l"(old) : "l"(reinterpret_cast<unsigned long long*>(mine)) : "memory");
+    }
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old + 1ull == arrived + (unsigned long long)G) {  // last CTA of this rank
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      double t0 = 0, t1 = 0;
+      for (int i = lane; i < G; i += 32) { const double2 v = __ldcg(lbuf + i); t0 += v.x; t1 += v.y; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); }
+      if (lane < W) {
+        ulonglong2* slot = reinterpret_cast<ulonglong2*>(A.arena[lane] + roff + (size_t)my_rank * kSlotBytes);
+        ll_store(slot, t0, tag);
+        ll_store(slot + 1, t1, tag);
+      }
+    }
+    // all CTAs: wait for the W rank totals
+    double v0 = 0, v1 = 0;
+    int ok = 1;
+    if (lane < W) {
+      const ulonglong2* slot = reinterpret_cast<const ulonglong2*>(mine + roff + (size_t)lane * kSlotBytes);
+      const long long t_begin = clock64();
+      while (!(ll_load(slot, tag, v0) & ll_load(slot + 1, tag, v1))) {
+        if (clock64() - t_begin > kPeerTimeoutCycles) { ok = 0; break; }
+      }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    double s0 = 0, s1 = 0;
+    for (int k = 0; k < W; ++k) { s0 += __shfl_sync(0xffffffffu, v0, k); s1 += __shfl_sync(0xffffffffu, v1, k); }
+    if (lane == 0) { s_tot[0] = s0; s_tot[1] = s1; s_tot[2] = ok ? 1.0 : 0.0; }
+  }
+  __syncthreads();
+  arrived += (unsigned long long)G;
+  // every thread acquires: its later plain (L1-cached) loads must not be served from lines older than this barrier
+  if (sys_release) asm volatile("fence.acq_rel.sys;" ::: "memory");
+  else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  a = s_tot[0]; b = s_tot[1];
+  return s_tot[2] != 0.0;
 }
 
 // MAXT = CTA width (256 / 512 / 1024 threads): wide CTAs keep one row per warp on larger systems (one CTA per SM either way)
@@ -669,20 +722,25 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
   constexpr int SLOTS = 32 / NCL, NB = NCL * NCL;
   extern __shared__ double cg_smem[];
   __shared__ double sred[MAXT / 32][2];
-  __shared__ int s_flag;
+  __shared__ double s_tot[3];
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;
   const int la = lane % NCL, ls = lane / NCL;
   const bool lact = lane < SLOTS * NCL;
   const int V = A.V, nb = A.nb, nrows = V + (nb > 0 ? 1 : 0), boff = V * NCL;
   const int W = MULTI ? A.W : 1;
+  // rank of this CTA, its index inside the rank and the CTAs per rank (virtual ranks split one launch)
+  const int G = (MULTI && A.vranks > 1) ? (int)gridDim.x / A.vranks : (int)gridDim.x;
+  const int my_rank = MULTI ? (A.vranks > 1 ? (int)blockIdx.x / G : A.rank) : 0;
+  const int cta = (MULTI && A.vranks > 1) ? (int)blockIdx.x % G : (int)blockIdx.x;
+  char* const mine = A.arena[my_rank];
   // ---- the rows of a warp are the same in every iteration: keep (a prefix of) their S blocks and column indices on chip
   const int cap = A.smem_blocks;
   double* Bs = cg_smem + (size_t)wid * cap * NB;
   int* cs = reinterpret_cast<int*>(cg_smem + (size_t)wpb * cap * NB) + (size_t)wid * cap;
-  // this rank's slots [slot0, slot1); inside, slots [blockIdx*per, (blockIdx+1)*per) belong to this CTA; warp w takes every wpb-th
-  const int slot0 = A.rank * A.slots_per_rank, slot1 = min(nrows, slot0 + A.slots_per_rank);
-  const int per = (A.slots_per_rank + gridDim.x - 1) / gridDim.x;
-  const int cta0 = slot0 + blockIdx.x * per;
+  // this rank's slots [slot0, slot1); inside, slots [cta*per, (cta+1)*per) belong to this CTA; warp w takes every wpb-th
+  const int slot0 = my_rank * A.slots_per_rank, slot1 = min(nrows, slot0 + A.slots_per_rank);
+  const int per = (A.slots_per_rank + G - 1) / G;
+  const int cta0 = slot0 + cta * per;
   int ncached = 0;
   for (int sl = wid; sl < per && ncached < cap; sl += wpb) {
     const int slot = cta0 + sl;
@@ -694,14 +752,22 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
     ncached += take;
   }
   __syncwarp();
-  unsigned long long* ctrl = reinterpret_cast<unsigned long long*>(A.arena[A.rank]);
-  unsigned long long arrived = ctrl[1];  // arrivals consumed so far on this arena (same on every rank)
+  unsigned long long* ctrl = reinterpret_cast<unsigned long long*>(mine);
+  unsigned long long arrived = ctrl[1];             // single GPU: arrivals consumed so far on this arena
+  const unsigned int tag0 = (unsigned int)ctrl[2];  // multi: first LL tag of this solve (same on every rank)
   double alpha = 0.0, beta = 0.0, gamma_old = 0.0, gamma0 = 0.0, gamma_last = 0.0;
   size_t off_o = A.off_st0, off_n = A.off_st1;  // previous state (read by everyone) / next state (written by the owner only)
-  double* const xl = reinterpret_cast<double*>(A.arena[A.rank] + A.off_x);
+  double* const xl = reinterpret_cast<double*>(mine + A.off_x);
   int it = 0, status = 1;
+  bool peers_ok = true;
   for (;; ++it) {
-    const double* so = reinterpret_cast<const double*>(A.arena[A.rank] + off_o);
+    const double* so = reinterpret_cast<const double*>(mine + off_o);
+    double* const sn = reinterpret_cast<double*>(mine + off_n);
+    // LL inboxes: state(it-1) was pushed with tag0 + it into buffer (it-1)&1; state(it) goes out with tag0 + it + 1 into it&1
+    const ulonglong2* llo = reinterpret_cast<const ulonglong2*>(mine + ((it & 1) ? A.off_ll0 : A.off_ll1));
+    const size_t off_lln = (it & 1) ? A.off_ll1 : A.off_ll0;
+    const unsigned int tag_rd = tag0 + (unsigned int)it, tag_wr = tag_rd + 1u;
+    const bool use_ll = MULTI && it > 0;  // iteration 0 reads the initial state, which every rank computed for all rows
     double g = 0, d = 0;
     int bi = 0;  // running index of this warp's blocks
     for (int sl = wid; sl < per; sl += wpb) {
@@ -710,6 +776,8 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
       const int row = slot < V ? A.order[slot] : V;
       if (row < V) {
         double rn = 0, s_n = 0;
+        unsigned int pmask = 0;
+        if (MULTI) pmask = A.peer_mask[row];
         if (lane < NCL) {
           const int i = row * NCL + lane;
           const double ro = __ldcg(so + (row * 3 + 0) * NCL + lane), wo = __ldcg(so + (row * 3 + 1) * NCL + lane), s_o = __ldcg(so + (row * 3 + 2) * NCL + lane);
@@ -718,11 +786,15 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
           A.p[i] = pn;
           xl[i] += alpha * pn;
           rn = ro - alpha * s_n;
-          // the row's new state goes into every replica; r and s now, so that the (remote) stores drain behind the product
-          for (int k = 0; k < W; ++k) {
-            double* sn = reinterpret_cast<double*>(A.arena[MULTI ? k : A.rank] + off_n);
-            sn[(row * 3 + 0) * NCL + lane] = rn;
-            sn[(row * 3 + 2) * NCL + lane] = s_n;
+          sn[(row * 3 + 0) * NCL + lane] = rn;
+          sn[(row * 3 + 2) * NCL + lane] = s_n;
+          if (MULTI) {  // r and s leave now, so that the remote stores drain behind the sparse product
+            for (int k = 0; k < W; ++k)
+              if ((pmask >> k) & 1u) {
+                ulonglong2* q = reinterpret_cast<ulonglong2*>(A.arena[k] + off_lln) + (size_t)row * (3 * NCL) + lane;
+                ll_store(q, rn, tag_wr);
+                ll_store(q + 2 * NCL, s_n, tag_wr);
+              }
           }
         }
         const int b0 = A.rowptr[row], nblk = A.rowptr[row + 1] - b0;
@@ -739,25 +811,52 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
           const int* ci = cached ? (cs + bi) : nullptr;
           for (int t0 = 0; t0 < nsteps; t0 += CH) {
             int off[CH];
+            bool rem[CH];
 #pragma unroll
             for (int u = 0; u < CH; ++u) {
               const int k = (t0 + u) * SLOTS + ls;
               int c = row;
               if (k < lim) c = cached ? ci[k] : __ldg(A.col + b0 + k);
-              off[u] = c * (3 * NCL) + la;
+              rem[u] = use_ll && c < 0;  // neighbour owned by another rank: its state arrives in the LL inbox
+              off[u] = (c & 0x7fffffff) * (3 * NCL) + la;
             }
             double rr[CH], ww[CH], ss[CH];
 #pragma unroll
             // plain (L1-cached) loads: the rows of a CTA are neighbours and share most of their gathers; the acquire in the grid
             // barrier invalidates L1 every iteration, so a cached line is never older than the last barrier
-            for (int u = 0; u < CH; ++u) { rr[u] = so[off[u]]; ww[u] = so[off[u] + NCL]; ss[u] = so[off[u] + 2 * NCL]; }
+            for (int u = 0; u < CH; ++u) {
+              if (!MULTI || !rem[u]) { rr[u] = so[off[u]]; ww[u] = so[off[u] + NCL]; ss[u] = so[off[u] + 2 * NCL]; }
+            }
+            if (MULTI) {
+              // remote neighbours: one batched attempt (the words normally arrived long ago), then poll the stragglers
+              unsigned int bad = 0;
+#pragma unroll
+              for (int u = 0; u < CH; ++u) {
+                if (rem[u]) {
+                  const ulonglong2* q = llo + off[u];
+                  if (!(ll_load(q, tag_rd, rr[u]) & ll_load(q + NCL, tag_rd, ww[u]) & ll_load(q + 2 * NCL, tag_rd, ss[u]))) bad |= 1u << u;
+                }
+              }
+              if (bad) {
+                const long long t_begin = clock64();
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                  if ((bad >> u) & 1u) {
+                    const ulonglong2* q = llo + off[u];
+                    while (!(ll_load(q, tag_rd, rr[u]) & ll_load(q + NCL, tag_rd, ww[u]) & ll_load(q + 2 * NCL, tag_rd, ss[u]))) {
+                      if (clock64() - t_begin > kPeerTimeoutCycles) { peers_ok = false; break; }
+                    }
+                  }
+                }
+              }
+            }
 #pragma unroll
             for (int u = 0; u < CH; ++u) {
               const int k = (t0 + u) * SLOTS + ls;
-              const double mine = rr[u] - alpha * (ww[u] + beta * ss[u]);
+              const double mine_r = rr[u] - alpha * (ww[u] + beta * ss[u]);
               double rj[NCL];
 #pragma unroll
-              for (int j = 0; j < NCL; ++j) rj[j] = __shfl_sync(0xffffffffu, mine, (base + j) & 31);
+              for (int j = 0; j < NCL; ++j) rj[j] = __shfl_sync(0xffffffffu, mine_r, (base + j) & 31);
               if (k < lim) {
                 if (cached) {
                   const double* B = Bs + (size_t)(bi + k) * NB + la * NCL;
@@ -785,7 +884,12 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
               for (int j = 0; j < nb; ++j) tot += strip[j] * (__ldcg(q + j) - alpha * (__ldcg(q + nb + j) + beta * __ldcg(q + 2 * nb + j)));
             }
           }
-          for (int k = 0; k < W; ++k) reinterpret_cast<double*>(A.arena[MULTI ? k : A.rank] + off_n)[(row * 3 + 1) * NCL + lane] = tot;
+          sn[(row * 3 + 1) * NCL + lane] = tot;
+          if (MULTI) {
+            for (int k = 0; k < W; ++k)
+              if ((pmask >> k) & 1u)
+                ll_store(reinterpret_cast<ulonglong2*>(A.arena[k] + off_lln) + (size_t)row * (3 * NCL) + NCL + lane, tot, tag_wr);
+          }
           g += rn * rn; d += tot * rn;
         }
       } else if (lane < nb) {  // dense border row (single rank only)
@@ -797,7 +901,7 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
         A.p[i] = pn;
         xl[i] += alpha * pn;
         const double rn = ro - alpha * s_n;
-        double* qn = reinterpret_cast<double*>(A.arena[A.rank] + off_n) + 3 * (size_t)boff;
+        double* qn = sn + 3 * (size_t)boff;
         qn[lane] = rn; qn[2 * nb + lane] = s_n;
         double tot = rn;  // unit diagonal block
         for (int k = 0; k < A.nav; ++k) {
@@ -810,7 +914,10 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
       }
     }
     if (A.debug & 2) { g = 1.0 / (it + 1.0); d = 1.0; __syncthreads(); }
-    else if (!grid_reduce2<MULTI>(A, g, d, it, arrived, sred, &s_flag)) { status = 3; break; }
+    else if (MULTI) {
+      if (!ll_reduce2(A, g, d, it, tag_wr, my_rank, cta, G, W, false, arrived, sred, s_tot)) peers_ok = false;
+      if (__syncthreads_or(peers_ok ? 0 : 1)) { status = 3; break; }
+    } else grid_reduce2(A, g, d, it, arrived, sred);
     gamma_last = g;
     if (it == 0) {
       gamma0 = g;
@@ -830,8 +937,8 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
     const size_t t = off_o; off_o = off_n; off_n = t;
   }
   if (MULTI && status != 3) {
-    // every rank needs the whole solution: push the owned rows of x into the other replicas, then meet once more so that
-    // nobody leaves (and lets later kernels read x) before all pushes have landed
+    // every rank needs the whole solution: push the owned rows of x (plain stores) into the other replicas, then meet once
+    // more -- this time behind a system-scope release -- so that nobody leaves before all pushes have landed
     for (int sl = wid; sl < per; sl += wpb) {
       const int slot = cta0 + sl;
       if (slot >= min(V, slot1)) break;
@@ -839,16 +946,19 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
       if (lane < NCL) {
         const double v = xl[row * NCL + lane];
         for (int k = 0; k < W; ++k)
-          if (k != A.rank) reinterpret_cast<double*>(A.arena[k] + A.off_x)[row * NCL + lane] = v;
+          if (k != my_rank) reinterpret_cast<double*>(A.arena[k] + A.off_x)[row * NCL + lane] = v;
       }
     }
-    __syncthreads();
-    if (!cg_barrier<true>(A, arrived, &s_flag)) status = 3;
+    double z0 = 0, z1 = 0;
+    if (!ll_reduce2(A, z0, z1, it + 1, tag0 + (unsigned int)it + 2u, my_rank, cta, G, W, true, arrived, sred, s_tot)) status = 3;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (cta == 0 && threadIdx.x == 0) {
     ctrl[1] = arrived;
-    A.out_info[0] = it; A.out_info[1] = status;
-    A.out_res[0] = gamma0 > 0 ? sqrt(gamma_last / gamma0) : 0.0;
+    ctrl[2] = (unsigned long long)(tag0 + (unsigned int)it + 3u);
+    if (my_rank == (MULTI ? A.rank : 0)) {
+      A.out_info[0] = it; A.out_info[1] = status;
+      A.out_res[0] = gamma0 > 0 ? sqrt(gamma_last / gamma0) : 0.0;
+    }
   }
 }
 

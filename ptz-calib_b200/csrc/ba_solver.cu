@@ -59,9 +59,9 @@ static PeerArena g_arena;
 static void arena_release() {
   if (!g_arena.bytes) return;
   cudaDeviceSynchronize();
-  for (int k = 0; k < g_arena.world; ++k) {
+  for (int k = 0; k < kMaxPeers; ++k) {
     if (!g_arena.base[k]) continue;
-    if (k == g_nccl.rank || g_arena.world == 1) cudaFree(g_arena.base[k]);
+    if (g_arena.world <= 1 || k == g_nccl.rank) cudaFree(g_arena.base[k]);  // own block, or local virtual replicas (world < 0)
     else cudaIpcCloseMemHandle(g_arena.base[k]);
     g_arena.base[k] = nullptr;
   }
@@ -70,8 +70,24 @@ static void arena_release() {
 }
 
 // Collective over the ranks of the communicator (every rank asks for the same size: the reduced system is replicated).
-static void arena_ensure(size_t bytes, cudaStream_t s) {
+// vranks > 1 (debug, single process): that many replicas on this device instead of peer mappings.
+static void arena_ensure(size_t bytes, cudaStream_t s, int vranks) {
   const int W = g_nccl.world, R = g_nccl.rank;
+  if (vranks > 1) {
+    if (g_arena.bytes >= bytes && g_arena.world == -vranks) return;
+    arena_release();
+    const size_t want = std::max(bytes + bytes / 2, (size_t)8 << 20);
+    for (int k = 0; k < vranks; ++k) {
+      PTZ_CUDA(cudaMalloc((void**)&g_arena.base[k], want));
+      PTZ_CUDA(cudaMemset(g_arena.base[k], 0, want));
+      const unsigned long long one = 1;
+      PTZ_CUDA(cudaMemcpy(g_arena.base[k] + 16, &one, 8, cudaMemcpyHostToDevice));
+    }
+    PTZ_CUDA(cudaDeviceSynchronize());
+    g_arena.world = -vranks;
+    g_arena.bytes = want;
+    return;
+  }
   if (g_arena.bytes >= bytes && g_arena.world == W) return;
   if (W > kMaxPeers) throw CudaError(PTZ_ERR_UNSUPPORTED, "more than 8 ranks per box");
   if (W > 1) {  // nobody may still be spinning on, or writing into, the old arena
@@ -87,6 +103,10 @@ static void arena_ensure(size_t bytes, cudaStream_t s) {
   char* mine = nullptr;
   PTZ_CUDA(cudaMalloc((void**)&mine, want));
   PTZ_CUDA(cudaMemset(mine, 0, want));
+  {
+    const unsigned long long one = 1;  // first LL tag: zero-filled memory must never look valid
+    PTZ_CUDA(cudaMemcpy(mine + 16, &one, 8, cudaMemcpyHostToDevice));
+  }
   PTZ_CUDA(cudaDeviceSynchronize());
   g_arena.base[R] = mine;
   g_arena.world = W;
@@ -223,10 +243,13 @@ struct BaSolver : BaSolverBase {
   double* h_scalars = nullptr;  // pinned
   int* h_info = nullptr;        // pinned: pcg info(2), fail(1)
   int nblk_ray = 0, nblk_cam = 0, cg_cap = 1, cg_wpb = 8, cg_grid = 1, cg_slots_per_rank = 1;
-  size_t ar_partial = 0, ar_st0 = 0, ar_st1 = 0, ar_x = 0;  // arena offsets (bytes), identical on every rank
-  double* arena_ptr(size_t off) const { return reinterpret_cast<double*>(g_arena.base[g_nccl.rank] + off); }
+  size_t ar_partial = 0, ar_st0 = 0, ar_st1 = 0, ar_x = 0, ar_ll0 = 0, ar_ll1 = 0;  // arena offsets (bytes), identical on every rank
+  int cgW = 1, cgR = 0, cg_vranks = 1;  // ranks sharing the rows of the CG, this rank; virtual ranks (debug: PTZ_CG_VRANKS)
+  DevBuf<int> d_cg_col;                 // column indices, bit 31 = owned by another rank than the row
+  DevBuf<unsigned char> d_cg_mask;      // per row: ranks that own one of its neighbours
+  double* arena_ptr(size_t off) const { return reinterpret_cast<double*>(g_arena.base[cgR] + off); }
   const void* cg_kernel() const {
-    if (g_nccl.world > 1)
+    if (cgW > 1)
       return cg_wpb == 8 ? (const void*)k_cg<NCL, 256, true> : cg_wpb == 16 ? (const void*)k_cg<NCL, 512, true> : (const void*)k_cg<NCL, 1024, true>;
     return cg_wpb == 8 ? (const void*)k_cg<NCL, 256, false> : cg_wpb == 16 ? (const void*)k_cg<NCL, 512, false> : (const void*)k_cg<NCL, 1024, false>;
   }
@@ -307,12 +330,19 @@ struct BaSolver : BaSolverBase {
       // rows of a CTA are neighbouring views whose gathers overlap (L1 hits).  Then: how many blocks of S fit 200 KB of smem.
       // Sharded problem: the rows are split across the ranks (a contiguous run of the ordering each), see k_cg.
       const int nrows = V + (nb > 0 ? 1 : 0);
-      const int W = g_nccl.world, R = g_nccl.rank;
+      cgW = g_nccl.world; cgR = g_nccl.rank; cg_vranks = 1;
+      if (cgW == 1 && nb == 0) {
+        const char* e = getenv("PTZ_CG_VRANKS");
+        const int vr = e ? atoi(e) : 1;
+        if (vr > 1 && vr <= kMaxPeers && V >= 4 * vr) { cg_vranks = vr; cgW = vr; }
+      }
+      const int W = cgW, R = cgR;
+      const int sms_per_rank = cg_vranks > 1 ? num_sms / cg_vranks : num_sms;
       cg_slots_per_rank = cdiv(nrows, W);
       const int my0 = R * cg_slots_per_rank, my1 = std::min(nrows, my0 + cg_slots_per_rank);
-      const int need = cdiv(cg_slots_per_rank, num_sms);
+      const int need = cdiv(cg_slots_per_rank, sms_per_rank);
       cg_wpb = need <= 8 ? 8 : (need <= 16 ? 16 : 32);
-      cg_grid = std::min(num_sms, cdiv(cg_slots_per_rank, cg_wpb));
+      cg_grid = std::min(sms_per_rank, cdiv(cg_slots_per_rank, cg_wpb));  // CTAs per rank
       std::vector<int> h_col(ds.nnzb);
       ds.s_col.download(h_col.data(), ds.nnzb, stream);
       PTZ_CUDA(cudaStreamSynchronize(stream));
@@ -340,20 +370,35 @@ struct BaSolver : BaSolverBase {
       d_cg_order.upload(order, stream);
       const int per = cdiv(cg_slots_per_rank, cg_grid);
       int worst = 0;
-      for (int c = 0; c < cg_grid; ++c)
-        for (int w = 0; w < cg_wpb; ++w) {
-          int cnt = 0;
-          for (int sl = w; sl < per; sl += cg_wpb) {
-            const int slot = my0 + c * per + sl;
-            if (slot >= std::min(V, my1)) break;
-            cnt += ds.h_rowptr[order[slot] + 1] - ds.h_rowptr[order[slot]];
+      for (int r = (cg_vranks > 1 ? 0 : R); r < (cg_vranks > 1 ? W : R + 1); ++r)
+        for (int c = 0; c < cg_grid; ++c)
+          for (int w = 0; w < cg_wpb; ++w) {
+            int cnt = 0;
+            for (int sl = w; sl < per; sl += cg_wpb) {
+              const int slot = r * cg_slots_per_rank + c * per + sl;
+              if (slot >= std::min(V, std::min(nrows, (r + 1) * cg_slots_per_rank))) break;
+              cnt += ds.h_rowptr[order[slot] + 1] - ds.h_rowptr[order[slot]];
+            }
+            worst = std::max(worst, cnt);
           }
-          worst = std::max(worst, cnt);
-        }
+      (void)my0; (void)my1;
+      {
+        // ownership marks for the sharded CG: which columns of a row live on another rank, which ranks need a row's state
+        std::vector<int> owner(V, 0), colx(h_col);
+        for (int sl = 0; sl < V; ++sl) owner[order[sl]] = sl / cg_slots_per_rank;
+        std::vector<unsigned char> mask(V, 0);
+        for (int r = 0; r < V; ++r)
+          for (int k = ds.h_rowptr[r]; k < ds.h_rowptr[r + 1]; ++k) {
+            const int c = h_col[k];
+            if (owner[c] != owner[r]) { colx[k] = c | (int)0x80000000; mask[c] |= (unsigned char)(1u << owner[r]); }
+          }
+        d_cg_col.upload(colx, stream);
+        d_cg_mask.upload(mask, stream);
+      }
       const size_t per_block = NCL * NCL * sizeof(double) + sizeof(int);
       const int fit = (int)((160 * 1024) / (cg_wpb * per_block));  // leave >= 60 KB of the SM's 228 KB to the L1
       cg_cap = std::max(1, std::min(worst, fit));
-      if (W > 1) {  // every rank launches the same shape (the slot of a CTA's partial sums is rank * grid + cta)
+      if (g_nccl.world > 1) {  // every rank launches the same shape (the slot of a CTA's partial sums is rank * grid + cta)
         DevBuf<double> d_m;
         double m[2] = {(double)cg_cap, 0.0};
         d_m.upload(m, 2, stream);
@@ -364,13 +409,16 @@ struct BaSolver : BaSolverBase {
       }
       const size_t cg_smem = (size_t)cg_wpb * cg_cap * per_block + 16;
       PTZ_CUDA(cudaFuncSetAttribute(cg_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg_smem));
-      // arena layout: ctrl | partial [2][W*grid] double2 | st0 [3n] | st1 [3n] | x [n]
+      // arena layout: ctrl | slots [2][W*grid] | st0 [3n] | st1 [3n] | x [n] | LL inboxes ll0, ll1 [V*3*NCL] 16-byte words
       auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
       ar_partial = kArenaCtrlBytes;
-      ar_st0 = al(ar_partial + 2 * (size_t)W * num_sms * sizeof(double2));
+      ar_st0 = al(ar_partial + 2 * (size_t)W * num_sms * kSlotBytes);
       ar_st1 = al(ar_st0 + 3 * (size_t)n * sizeof(double));
       ar_x = al(ar_st1 + 3 * (size_t)n * sizeof(double));
-      arena_ensure(al(ar_x + (size_t)n * sizeof(double)), stream);
+      ar_ll0 = al(ar_x + (size_t)n * sizeof(double));
+      const size_t ll_bytes = W > 1 ? (size_t)V * 3 * NCL * 16 : 0;
+      ar_ll1 = al(ar_ll0 + ll_bytes);
+      arena_ensure(al(ar_ll1 + ll_bytes), stream, cg_vranks);
     }
     upload(prob);
     PTZ_CUDA(cudaStreamSynchronize(stream));
@@ -641,11 +689,11 @@ struct BaSolver : BaSolverBase {
     // ---- stage 3
     CgArgs a;
     a.V = V; a.nb = nb; a.n = n;
-    a.rowptr = ds.s_rowptr.p; a.col = ds.s_col.p; a.Sval = p_Sval;
+    a.rowptr = ds.s_rowptr.p; a.col = d_cg_col.p; a.Sval = p_Sval; a.peer_mask = d_cg_mask.p;
     a.nav = ncpl; a.ann_view = d_cpl_view.p; a.ann_idx = d_cpl_idx.p; a.C = d_Cs.p; a.order = d_cg_order.p;
     for (int k = 0; k < kMaxPeers; ++k) a.arena[k] = g_arena.base[k];
-    a.off_partial = ar_partial; a.off_st0 = ar_st0; a.off_st1 = ar_st1; a.off_x = ar_x;
-    a.W = g_nccl.world; a.rank = g_nccl.rank; a.slots_per_rank = cg_slots_per_rank; a.p = d_cgp.p;
+    a.off_partial = ar_partial; a.off_st0 = ar_st0; a.off_st1 = ar_st1; a.off_x = ar_x; a.off_ll0 = ar_ll0; a.off_ll1 = ar_ll1;
+    a.W = cgW; a.rank = cgR; a.vranks = cg_vranks; a.slots_per_rank = cg_slots_per_rank; a.p = d_cgp.p;
     a.max_iter = opt.pcg_max_iterations; a.tol = opt.pcg_rel_tolerance;
     a.out_info = d_pcg_info.p; a.out_res = d_pcg_res.p;
     // shared-memory residency of S: every warp keeps up to cg_cap blocks (+ column indices) of its rows for the whole solve
@@ -654,7 +702,13 @@ struct BaSolver : BaSolverBase {
     const size_t cg_smem = (size_t)cg_wpb * cg_cap * (NCL * NCL * sizeof(double) + sizeof(int)) + 16;
     void* args[] = {&a};
     PTZ_TIMED(PTZ_K_PCG, {
-      PTZ_CUDA(cudaLaunchCooperativeKernel(cg_kernel(), dim3(cg_grid), dim3(32 * cg_wpb), args, cg_smem, s));
+      if (cg_vranks > 1) {  // debug: every virtual rank starts from the same initial state
+        for (int k = 1; k < cg_vranks; ++k) {
+          PTZ_CUDA(cudaMemcpyAsync(g_arena.base[k] + ar_st0, g_arena.base[0] + ar_st0, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+          PTZ_CUDA(cudaMemsetAsync(g_arena.base[k] + ar_x, 0, (size_t)n * sizeof(double), s));
+        }
+      }
+      PTZ_CUDA(cudaLaunchCooperativeKernel(cg_kernel(), dim3(cg_grid * cg_vranks), dim3(32 * cg_wpb), args, cg_smem, s));
       k_unscale<NCL><<<cdiv(V + nb, 128), 128, 0, s>>>(V, nb, d_Linv.p, d_Linv_b.p, arena_ptr(ar_x), d_y.p);
     });
     // ---- stage 4

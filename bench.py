@@ -76,6 +76,17 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
 
 
+def ncu_traffic(factor_type, M):
+    """DRAM bytes per launch of k_resjac from the committed ncu --set full capture (profiles/r1_dram_traffic.json), scaled by
+    the observation count when the launch differs from the profiled one; None when no capture covers this factor type."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_dram_traffic.json")) as f:
+            rec = json.load(f).get(f"k_resjac<{factor_type}>")
+        return None if rec is None else int(rec["dram_bytes_per_launch"] * (M / rec["obs"]))
+    except Exception:
+        return None
+
+
 def make_scene(args, rank, world):
     from ptz_calib_b200 import synth
 
@@ -196,7 +207,7 @@ def run_ours(args):
     roofline = None
     if rj:
         roofline = dict(kernel="k_resjac (stage 1: residual + analytic Jacobian)", bound="hbm", achieved=rj["alg_gbs"], peak=peak, unit="GB/s",
-                        frac=round(rj["alg_gbs"] / peak, 4), traffic=None, peak_source=peak_src,
+                        frac=round(rj["alg_gbs"] / peak, 4), traffic=ncu_traffic(args.factor_type, prob.M), peak_source=peak_src,
                         algorithmic_bytes_per_obs=RJ_BYTES_PER_OBS[args.factor_type], dominant_kernel_by_time=dom,
                         dominant_kernel_share=table[dom]["share"] if dom else None)
     launches = st["launches_total"]
@@ -246,7 +257,8 @@ def run_ours(args):
             "config": {"workload": f"cfg4_scaled_ba per GPU (V={prob.V}, P={prob.P} local tracks, M={prob.M} local obs, M_total={int(M_total)}); "
                                    f"factor {['PTZRay', 'PTZRayDist', 'PTZRayFxfyDist'][args.factor_type]}; LM iterations from complete solves at Ceres-default "
                                    f"tolerances, PCG tol {args.pcg_tol:g}; inputs larger than L2 (records {prob.M * 128 / 1e6:.0f} MB)",
-                       "views": prob.V, "obs_per_gpu": prob.M, "parallelism": f"obs-sharded x{world}" if world > 1 else "single GPU"},
+                       "views": prob.V, "obs_per_gpu": prob.M, "parallelism": (f"tracks/observations sharded x{world} (NCCL all-reduce of camera blocks), rows of the reduced system sharded x{world} "
+                                                                                       "(in-kernel NVLink peer exchange)") if world > 1 else "single GPU"},
             "lm_iters_per_sec": round(done / (dev_ms * 1e-3), 2), "solves_in_timed_region": solves, "wall_seconds": round(wall, 4),
             "pcg_iterations_per_step": round(st["pcg_iterations"] / st["lm_iterations"], 1),
             "us_per_pcg_iteration": round(1e3 * kernels["pcg"]["ms"] / max(st["pcg_iterations"], 1), 3) if "pcg" in kernels else None,

@@ -470,9 +470,10 @@ __global__ void __launch_bounds__(32) k_precond_border(int nb, const double* __r
 template <int NCL>
 __global__ void k_scale_system(int V, int nnzb, const int* __restrict__ blk_row, const int* __restrict__ col, const double* __restrict__ Linv,
                                double* __restrict__ Sval, const double* __restrict__ rhs, double* __restrict__ st0, double* __restrict__ x,
-                               double* __restrict__ p) {
+                               double* __restrict__ p, const unsigned char* __restrict__ row_owner, int my_rank) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < nnzb) {
+  // sharded CG: a rank only ever reads the rows of S~ it owns (my_rank < 0: all rows)
+  if (k < nnzb && (my_rank < 0 || row_owner[blk_row[k]] == my_rank)) {
     const int r = blk_row[k], c = col[k];
     double* B = Sval + (size_t)k * NCL * NCL;
     if (r == c) {

@@ -259,7 +259,39 @@ inline void build_structure_device_obs(int V, int P, int M, const float* h_uv, c
 }
 
 // phase B: block keys (local, or their union with the global ones on a sharded problem), pair ranges, block CSR
-inline void build_structure_device_blocks(DevStructure& d, const std::vector<int64_t>* extra_upper_keys, cudaStream_t s) {
+// sorted union of `count` keys that are already on the device (duplicates and the ~0 padding removed): radix sort + unique
+inline int union_keys_device(unsigned long long* keys, long long count, DevBuf<unsigned long long>& out, cudaStream_t s) {
+  using namespace setup;
+  CubTemp tmp;
+  tmp.s = s;
+  DevBuf<unsigned long long> sorted;
+  DevBuf<int> d_n;
+  sorted.alloc((size_t)count, s);
+  out.alloc((size_t)count, s);
+  d_n.alloc(1, s);
+  size_t bytes = 0;
+  PTZ_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, bytes, keys, sorted.p, count, 0, 64, s));
+  void* t = tmp.get(bytes);
+  PTZ_CUDA(cub::DeviceRadixSort::SortKeys(t, bytes, keys, sorted.p, count, 0, 64, s));
+  PTZ_CUDA(cub::DeviceSelect::Unique(nullptr, bytes, sorted.p, out.p, d_n.p, count, s));
+  t = tmp.get(bytes);
+  PTZ_CUDA(cub::DeviceSelect::Unique(t, bytes, sorted.p, out.p, d_n.p, count, s));
+  int n = 0;
+  unsigned long long last = 0;
+  d_n.download(&n, 1, s);
+  PTZ_CUDA(cudaStreamSynchronize(s));
+  if (n > 0) {
+    PTZ_CUDA(cudaMemcpyAsync(&last, out.p + (n - 1), 8, cudaMemcpyDeviceToHost, s));
+    PTZ_CUDA(cudaStreamSynchronize(s));
+    if (last == ~0ull) --n;  // the padding of the all-gather
+  }
+  return n;
+}
+
+// extra_upper_keys / dev_union: the block pattern every rank must share (sharded problems); dev_union is already the sorted
+// union INCLUDING the local keys.
+inline void build_structure_device_blocks(DevStructure& d, const std::vector<int64_t>* extra_upper_keys, cudaStream_t s,
+                                          const unsigned long long* dev_union = nullptr, int n_union = 0) {
   using namespace setup;
   CubTemp tmp;
   tmp.s = s;
@@ -270,7 +302,11 @@ inline void build_structure_device_blocks(DevStructure& d, const std::vector<int
   const int vbits = bits_for(std::max(V, 2));
   DevBuf<unsigned long long>& pk1 = d.pk_sorted;
   DevBuf<unsigned long long>& uniq = d.uniq_local;
-  if (extra_upper_keys && !extra_upper_keys->empty()) {
+  if (dev_union) {
+    d.nub = n_union;
+    d.ub_keys.alloc(std::max(n_union, 1), s);
+    if (n_union) PTZ_CUDA(cudaMemcpyAsync(d.ub_keys.p, dev_union, (size_t)n_union * 8, cudaMemcpyDeviceToDevice, s));
+  } else if (extra_upper_keys && !extra_upper_keys->empty()) {
     std::vector<unsigned long long> local(h_nuniq);
     if (h_nuniq) { uniq.download(local.data(), h_nuniq, s); PTZ_CUDA(cudaStreamSynchronize(s)); }
     std::vector<unsigned long long> merged(local.size() + extra_upper_keys->size());

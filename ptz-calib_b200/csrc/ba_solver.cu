@@ -247,6 +247,7 @@ struct BaSolver : BaSolverBase {
   int cgW = 1, cgR = 0, cg_vranks = 1;  // ranks sharing the rows of the CG, this rank; virtual ranks (debug: PTZ_CG_VRANKS)
   DevBuf<int> d_cg_col;                 // column indices, bit 31 = owned by another rank than the row
   DevBuf<unsigned char> d_cg_mask;      // per row: ranks that own one of its neighbours
+  DevBuf<unsigned char> d_cg_owner;     // per row: owning rank
   double* arena_ptr(size_t off) const { return reinterpret_cast<double*>(g_arena.base[cgR] + off); }
   const void* cg_kernel() const {
     if (cgW > 1)
@@ -287,8 +288,25 @@ struct BaSolver : BaSolverBase {
     } else {
       build_structure_device_obs(V, P, M, prob->obs_uv, prob->obs_view, prob->obs_track, kChunk, ds, stream);
       if (g_nccl.world > 1) {
-        std::vector<int64_t> all = union_of_keys(ds.local_keys_host(stream));
-        build_structure_device_blocks(ds, &all, stream);
+        // every rank must hold the same block pattern of S: all-gather the local upper-block keys, union on the device
+        const int W = g_nccl.world;
+        DevBuf<int64_t> d_cnt, d_my;
+        d_cnt.alloc(W, stream);
+        int64_t my = ds.n_local;
+        std::vector<int64_t> counts(W);
+        d_my.upload(&my, 1, stream);
+        PTZ_NCCL(ncclAllGather(d_my.p, d_cnt.p, 1, ncclInt64, g_nccl.comm, stream));
+        d_cnt.download(counts.data(), W, stream);
+        PTZ_CUDA(cudaStreamSynchronize(stream));
+        const int64_t mx = std::max<int64_t>(1, *std::max_element(counts.begin(), counts.end()));
+        DevBuf<unsigned long long> d_pad, d_all, d_union;
+        d_pad.alloc((size_t)mx, stream);
+        PTZ_CUDA(cudaMemsetAsync(d_pad.p, 0xff, (size_t)mx * 8, stream));
+        if (my) PTZ_CUDA(cudaMemcpyAsync(d_pad.p, ds.uniq_local.p, (size_t)my * 8, cudaMemcpyDeviceToDevice, stream));
+        d_all.alloc((size_t)mx * W, stream);
+        PTZ_NCCL(ncclAllGather(d_pad.p, d_all.p, mx, ncclUint64, g_nccl.comm, stream));
+        const int nun = union_keys_device(d_all.p, mx * W, d_union, stream);
+        build_structure_device_blocks(ds, nullptr, stream, d_union.p, nun);
       } else {
         build_structure_device_blocks(ds, nullptr, stream);
       }
@@ -334,7 +352,7 @@ struct BaSolver : BaSolverBase {
       if (cgW == 1 && nb == 0) {
         const char* e = getenv("PTZ_CG_VRANKS");
         const int vr = e ? atoi(e) : 1;
-        if (vr > 1 && vr <= kMaxPeers && V >= 4 * vr) { cg_vranks = vr; cgW = vr; }
+        if (vr > 1 && vr <= kMaxPeers && V >= 2 * vr) { cg_vranks = vr; cgW = vr; }
       }
       const int W = cgW, R = cgR;
       const int sms_per_rank = cg_vranks > 1 ? num_sms / cg_vranks : num_sms;
@@ -394,6 +412,8 @@ struct BaSolver : BaSolverBase {
           }
         d_cg_col.upload(colx, stream);
         d_cg_mask.upload(mask, stream);
+        std::vector<unsigned char> own8(owner.begin(), owner.end());
+        d_cg_owner.upload(own8, stream);
       }
       const size_t per_block = NCL * NCL * sizeof(double) + sizeof(int);
       const int fit = (int)((160 * 1024) / (cg_wpb * per_block));  // leave >= 60 KB of the SM's 228 KB to the L1
@@ -681,7 +701,8 @@ struct BaSolver : BaSolverBase {
       k_precond<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, ds.diag_pos.p, p_Sval, d_Linv.p, d_fail.p);
       if (nb > 0) k_precond_border<<<1, 32, 0, s>>>(nb, d_Sbb.p, d_Linv_b.p, d_fail.p);
       k_scale_system<NCL><<<cdiv(std::max(ds.nnzb, V), 128), 128, 0, s>>>(V, ds.nnzb, ds.blk_row.p, ds.s_col.p, d_Linv.p, p_Sval, p_rhs, arena_ptr(ar_st0),
-                                                                            arena_ptr(ar_x), d_cgp.p);
+                                                                            arena_ptr(ar_x), d_cgp.p, d_cg_owner.p,
+                                                                            (g_nccl.world > 1) ? cgR : -1);
       if (nb > 0)
         k_scale_border<NCL><<<1, 128, 0, s>>>(V, nb, ncpl, d_cpl_view.p, d_Linv.p, d_Linv_b.p, kDisp ? d_Cw.p : p_C, d_Cs.p, p_rhs, arena_ptr(ar_st0), arena_ptr(ar_x),
                                               d_cgp.p);
@@ -1175,10 +1196,17 @@ int ptzba_destroy(ptzba_handle* h) {
 int ptzba_solve(const ptzba_problem* prob, const ptz_solver_options* opt, ptzba_result* out) {
   if (!out) return PTZ_ERR_INVALID;
   ptzba_handle* h = nullptr;
+  const bool timing = getenv("PTZ_TIMING") != nullptr;  // phase wall-clock on stderr (diagnostics)
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
   int rc = ptzba_create(prob, opt, &h);
   if (rc != PTZ_OK) return rc;
+  const auto t1 = now();
   rc = ptzba_run(h, opt->max_num_iterations + 1, out);
+  const auto t2 = now();
   ptzba_destroy(h);
+  if (timing) fprintf(stderr, "[ptzba_solve rank %d] create %.2f ms  run %.2f ms  destroy %.2f ms\n", g_nccl.rank, ms(t0, t1), ms(t1, t2), ms(t2, now()));
   return rc;
 }
 

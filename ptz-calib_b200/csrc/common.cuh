@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -30,15 +31,34 @@ struct CudaError : std::runtime_error {
     }                                                                                                         \
   } while (0)
 
-// Owns a stream; declare it BEFORE any DevBuf that allocates on it so that it is destroyed after them.
+// Owns a stream; declare it BEFORE any DevBuf that allocates on it so that it is released after them.  Streams come from a
+// small per-device free list and go back to it: the many solver objects of one IBA run (and NCCL, which keeps per-stream
+// state) see the same few streams instead of a fresh one per call.
 struct StreamHolder {
   cudaStream_t s = nullptr;
+  int dev = 0;
   StreamHolder() {}
   StreamHolder(const StreamHolder&) = delete;
   StreamHolder& operator=(const StreamHolder&) = delete;
-  void create() { PTZ_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
+  static std::vector<cudaStream_t>& free_list(int device) {
+    static std::vector<cudaStream_t> lists[64];
+    return lists[device & 63];
+  }
+  static std::mutex& lock() { static std::mutex m; return m; }
+  void create() {
+    PTZ_CUDA(cudaGetDevice(&dev));
+    {
+      std::lock_guard<std::mutex> g(lock());
+      auto& fl = free_list(dev);
+      if (!fl.empty()) { s = fl.back(); fl.pop_back(); return; }
+    }
+    PTZ_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  }
   ~StreamHolder() {
-    if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    if (!s) return;
+    cudaStreamSynchronize(s);
+    std::lock_guard<std::mutex> g(lock());
+    free_list(dev).push_back(s);
   }
 };
 

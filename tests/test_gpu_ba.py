@@ -108,6 +108,28 @@ def test_solve_matches_oracle(orc, t):
     assert got.converged  # PTZRayOptimizer::Solve returns true
 
 
+@pytest.mark.parametrize("vranks", [2, 5, 8])
+def test_sharded_cg_protocol_with_virtual_ranks(orc, monkeypatch, vranks):
+    """The multi-GPU linear solver (rows of the reduced system sharded across ranks, LL words pushed into the other ranks'
+    inboxes, two-level reduction) run on ONE GPU with the grid split into virtual ranks: same answers as the oracle and as
+    the single-rank kernel."""
+    p = synth.make_config(4, scale=0.05)  # V = 50: every virtual rank owns a few rows
+    monkeypatch.setenv("PTZ_CG_VRANKS", str(vranks))
+    got = ptz.ba_solve(p, max_num_iterations=200)
+    monkeypatch.delenv("PTZ_CG_VRANKS")
+    rc, want = orc.ba_solve(p, max_num_iterations=200)
+    assert rc == 0
+    check_solve(orc, p, got, want, f"vranks{vranks}")
+    for t in TYPES[:3]:  # the three live-column layouts (4, 5, 6 per view), a fixed number of LM steps
+        q = synth.make_config(4, scale=0.05, factor_type=t)
+        monkeypatch.setenv("PTZ_CG_VRANKS", str(vranks))
+        a = ptz.ba_solve(q, max_num_iterations=8)
+        monkeypatch.delenv("PTZ_CG_VRANKS")
+        b = ptz.ba_solve(q, max_num_iterations=8)
+        assert a.num_iterations == b.num_iterations and abs(a.final_cost - b.final_cost) <= 1e-9 * b.final_cost
+        assert np.abs(a.ext - b.ext).max() <= 1e-8 and np.abs(a.intr - b.intr).max() <= 1e-6
+
+
 @pytest.mark.parametrize("t", [abi.PTZ_BA_PTZRAY, abi.PTZ_BA_PTZRAY_DIST])
 def test_georef_solve_matches_oracle(orc, t):
     """RunGeoreferencing (run_ptz_ba.cc:131-155): ray terms + annotated 2d-3d points, free T_l_w"""

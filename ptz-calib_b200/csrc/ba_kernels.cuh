@@ -1161,6 +1161,15 @@ __global__ void k_rays_out(int P, const double* __restrict__ trk, const double* 
 }
 
 // initial rays (Pix2Ray, ptzray_optimizer.cc:768-797): mean over the track's views of normalise((R^-1 K^-1)[u,v,1]), normalised
+// initial track records from the caller's arrays: ray0 (or zero, then k_init_rays), sqrt(ScaledLoss weight), unit Jacobi scales
+__global__ void k_trk_init(int P, const double* __restrict__ weight, const double* __restrict__ ray0, double* __restrict__ trk) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  double4 a = make_double4(0, 0, 0, sqrt(weight[p]));
+  if (ray0) { a.x = ray0[3 * (size_t)p]; a.y = ray0[3 * (size_t)p + 1]; a.z = ray0[3 * (size_t)p + 2]; }
+  reinterpret_cast<double4*>(trk + (size_t)p * kTrk)[0] = a;
+  reinterpret_cast<double4*>(trk + (size_t)p * kTrk)[1] = make_double4(1.0, 1.0, 1.0, 0.0);
+}
 __global__ void k_init_rays(int P, const int* __restrict__ t_off, const int* __restrict__ t_obs, const int* __restrict__ o_view,
                             const float2* __restrict__ o_uv, const double* __restrict__ RiKi, double* __restrict__ trk) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -216,7 +216,7 @@ struct BaSolver : BaSolverBase {
   double seconds_setup = 0;
 
   // host copies of the inputs that outputs need
-  std::vector<double> h_intr0, h_ext0, h_weight, h_ray0, h_tlw0;
+  std::vector<double> h_intr0, h_ext0, h_tlw0;
   bool have_ray0 = false;
   std::vector<int> h_view_active, h_ann_view, h_ann_off, h_ann_idx, h_pt_perm;
 
@@ -265,6 +265,12 @@ struct BaSolver : BaSolverBase {
 
   BaSolver(const ptzba_problem* prob, const ptz_solver_options* o) {
     auto t0 = std::chrono::steady_clock::now();
+    const bool dbg = getenv("PTZ_SETUP_DEBUG") != nullptr;  // prints where the set-up time goes (adds a stream sync per phase)
+    auto phase = [&](const char* what) {
+      if (!dbg) return;
+      cudaStreamSynchronize(stream);
+      fprintf(stderr, "[ptzba setup] %-28s %8.3f ms\n", what, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    };
     opt = *o;
     V = prob->num_views; P = prob->num_tracks; M = prob->num_obs; A = prob->num_pts3d;
     int dev = 0;
@@ -274,6 +280,7 @@ struct BaSolver : BaSolverBase {
     sh.create();
     stream = sh.s;
     clk.init(stream);
+    phase("stream + clock");
     if (opt.verbose & 4) {
       // reference path: the unit-tested host builder
       BaStructure st;
@@ -287,6 +294,7 @@ struct BaSolver : BaSolverBase {
       upload_structure(st, ds, stream);
     } else {
       build_structure_device_obs(V, P, M, prob->obs_uv, prob->obs_view, prob->obs_track, kChunk, ds, stream);
+      phase("orderings (obs)");
       if (g_nccl.world > 1) {
         // every rank must hold the same block pattern of S: all-gather the local upper-block keys, union on the device
         const int W = g_nccl.world;
@@ -311,6 +319,7 @@ struct BaSolver : BaSolverBase {
         build_structure_device_blocks(ds, nullptr, stream);
       }
     }
+    phase("block pattern + pair lists");
     // annotated points: sort by view, list annotated views
     h_ann_idx.assign(V, -1);
     if (A > 0) {
@@ -440,8 +449,10 @@ struct BaSolver : BaSolverBase {
       ar_ll1 = al(ar_ll0 + ll_bytes);
       arena_ensure(al(ar_ll1 + ll_bytes), stream, cg_vranks);
     }
+    phase("CG shape + arena");
     upload(prob);
     PTZ_CUDA(cudaStreamSynchronize(stream));
+    phase("parameters + work buffers");
     seconds_setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   }
 
@@ -489,20 +500,23 @@ struct BaSolver : BaSolverBase {
     // parameters
     h_intr0.assign(prob->intr, prob->intr + 9 * (size_t)V);
     h_ext0.assign(prob->ext, prob->ext + 6 * (size_t)V);
-    h_weight.assign(prob->track_weight, prob->track_weight + (size_t)P);
     h_tlw0.assign(6, 0.0);
     if (prob->tlw0) h_tlw0.assign(prob->tlw0, prob->tlw0 + 6);
     have_ray0 = prob->ray0 != nullptr;
-    std::vector<double> trk((size_t)std::max(P, 1) * kTrk, 0.0);
-    for (int p = 0; p < P; ++p) {
-      double* t = &trk[(size_t)p * kTrk];
-      if (have_ray0) { t[0] = prob->ray0[3 * (size_t)p]; t[1] = prob->ray0[3 * (size_t)p + 1]; t[2] = prob->ray0[3 * (size_t)p + 2]; }
-      t[3] = sqrt(h_weight[p]);
-      t[4] = t[5] = t[6] = 1.0;
-    }
     d_intr_init.upload(h_intr0, s); d_ext_init.upload(h_ext0, s); d_tlw_init.upload(h_tlw0, s);
-    d_trk_init.upload(trk, s);
-    for (int i = 0; i < 2; ++i) { d_intr[i].alloc(9 * (size_t)V, stream); d_ext[i].alloc(6 * (size_t)V, stream); d_trk[i].alloc(trk.size(), stream); d_tlw[i].alloc(6, stream); }
+    // track records [ray(3), sqrt(weight), Jacobi scale(3), pad] are laid out on the device from the caller's arrays
+    const size_t trk_n = (size_t)std::max(P, 1) * kTrk;
+    d_trk_init.alloc(trk_n, s);
+    if (P > 0) {
+      DevBuf<double> d_w, d_r0;
+      d_w.upload(prob->track_weight, (size_t)P, s);
+      if (have_ray0) d_r0.upload(prob->ray0, 3 * (size_t)P, s);
+      k_trk_init<<<cdiv(P, 256), 256, 0, s>>>(P, d_w.p, have_ray0 ? d_r0.p : nullptr, d_trk_init.p);
+      PTZ_CUDA(cudaGetLastError());
+    } else {
+      d_trk_init.zero(s);
+    }
+    for (int i = 0; i < 2; ++i) { d_intr[i].alloc(9 * (size_t)V, stream); d_ext[i].alloc(6 * (size_t)V, stream); d_trk[i].alloc(trk_n, stream); d_tlw[i].alloc(6, stream); }
     d_vt.alloc(V, stream);
     d_RiKi.alloc(9 * (size_t)V, stream);
     if (!have_ray0 && P > 0) {  // Pix2Ray on the device, into the initial track records

@@ -234,6 +234,68 @@ int ptzreloc_eval(int factor_type, int num_matches, const float* uv_ref, const f
 int ptzreloc_solve_batch_dev(const ptzreloc_batch* dev_batch, const ptz_solver_options* opt,
                              ptzreloc_result* dev_out, void* cuda_stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Track building: the step right before every BA, PTZRayOptimizer::FindTracks
+ * (ptzray_optimizer.cc:537-552) = TracksBuilder::Build / Filter(4) / ExportToSTL (src/core/tracks.cc:19-113), and the
+ * flattening of the tracks into the observation arrays of ptzba_problem (AddConstraints2d2d, ptzray_optimizer.cc:799-848).
+ * On the device: radix sort + unique of the (image, feature) nodes, lock-free union-find over the matches, one more sort
+ * by component, scans.  Integer work, results identical to the reference's as SETS; the reference's track ids are the
+ * union-by-rank roots of its sequential UnionFind (union_find.h:66-92), which only order the tracks — here a track's id is
+ * canonical: the flat index of its smallest (image, feature) node, and tracks come in ascending id.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ptztracks_matches {
+  int32_t num_pairs;            /* matches_info.size() (struct MatchesInfo, types.h:24-35) */
+  const int32_t* pair_src;      /* [num_pairs] MatchesInfo::src_img_idx */
+  const int32_t* pair_dst;      /* [num_pairs] MatchesInfo::dst_img_idx */
+  const int64_t* match_offset;  /* [num_pairs+1] rows of pair k are match_offset[k] .. match_offset[k+1]-1 */
+  const int32_t* query_idx;     /* [N] cv::DMatch::queryIdx: feature of the src image (tracks.cc:29) */
+  const int32_t* train_idx;     /* [N] cv::DMatch::trainIdx: feature of the dst image (tracks.cc:30) */
+  int32_t min_track_length;     /* TracksBuilder::Filter argument; FindTracks passes 4 (ptzray_optimizer.cc:541) */
+} ptztracks_matches;
+
+typedef struct ptztracks_result {
+  int32_t num_nodes;       /* out: distinct (image, feature) pairs = map_node_to_index_.size() (tracks.cc:35-43) */
+  int32_t num_components;  /* out: connected components before Filter */
+  int32_t num_tracks;      /* out: tracks ExportToSTL emits (no image listed twice, length >= min_track_length, > 1 node) */
+  int64_t num_elems;       /* out: sum of their lengths */
+  int64_t cap_tracks;      /* in: capacity of track_id (track_offset holds cap_tracks+1); N is always enough */
+  int64_t cap_elems;       /* in: capacity of elem_img / elem_feat; 2N is always enough */
+  int32_t* track_id;       /* [num_tracks] ascending */
+  int64_t* track_offset;   /* [num_tracks+1] */
+  int32_t* elem_img;       /* [num_elems] per track in ascending image id (Track = std::map<int,int>, tracks.h:31) */
+  int32_t* elem_feat;      /* [num_elems] */
+} ptztracks_result;
+
+/* PTZ_ERR_INVALID with the counts filled in when a capacity is too small, or for a negative image / feature index */
+int ptztracks_build(const ptztracks_matches* matches, ptztracks_result* out);
+/* all pointers (of both structs) are DEVICE pointers; counts come back in the struct (bench.py's kernel-only timing) */
+int ptztracks_build_dev(const ptztracks_matches* dev_matches, int64_t num_matches, ptztracks_result* dev_out, void* cuda_stream);
+
+/* tracks -> observation rows of ptzba_problem, as the loop at ptzray_optimizer.cc:801-848 adds residual blocks: tracks in
+ * ascending id, inside a track ascending image id, candidate views only (isCandidate, :554-560); a track without any
+ * candidate view gets no row; track_weight = number of images of the WHOLE track (:805); views are renumbered densely
+ * in ascending image id. */
+typedef struct ptztracks_views {
+  int32_t num_images;
+  const uint8_t* is_candidate;  /* [num_images] cam_ids_ membership */
+  const int64_t* kp_offset;     /* [num_images+1] keypoints of image i are rows kp_offset[i] .. kp_offset[i+1]-1 */
+  const float* kp_uv;           /* [.. * 2] features_[i].keypoints[j].pt (struct ImageFeatures, types.h:17-22) */
+} ptztracks_views;
+
+typedef struct ptztracks_obs {
+  int32_t num_rows;       /* out: tracks with at least one candidate view = ptzba_problem.num_tracks */
+  int32_t num_obs;        /* out: ptzba_problem.num_obs */
+  int64_t cap_rows, cap_obs; /* in: num_tracks and num_elems of the tracks are always enough */
+  int32_t* row_track;     /* [num_rows] index into the input tracks */
+  double* track_weight;   /* [num_rows] */
+  float* obs_uv;          /* [num_obs*2] */
+  int32_t* obs_view;      /* [num_obs] dense candidate-view index */
+  int32_t* obs_track;     /* [num_obs] row */
+} ptztracks_obs;
+
+int ptztracks_flatten(const ptztracks_result* tracks, const ptztracks_views* views, ptztracks_obs* out);
+
 #ifdef __cplusplus
 }
 #endif

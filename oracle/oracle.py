@@ -20,9 +20,8 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "libptz_oracle.so")
-    src = os.path.join(_HERE, "ptz_oracle.cpp")
-    hdr = os.path.join(_ROOT, "include", "ptzcalib_b200.h")
-    stale = (not os.path.exists(so)) or any(os.path.getmtime(so) < os.path.getmtime(p) for p in (src, hdr) if os.path.exists(p))
+    srcs = [os.path.join(_HERE, "ptz_oracle.cpp"), os.path.join(_HERE, "tracks_oracle.cpp"), os.path.join(_ROOT, "include", "ptzcalib_b200.h")]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(so) < os.path.getmtime(p) for p in srcs if os.path.exists(p))
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B", "libptz_oracle.so"], check=True, capture_output=True)
     return so
@@ -39,6 +38,8 @@ def lib():
         L.orc_ptzba_time_jacobian.restype = C.c_double
         L.orc_ptzba_time_jacobian.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.orc_num_threads.restype = C.c_int
+        L.orc_tracks_build.restype = C.c_int
+        L.orc_tracks_flatten.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -188,3 +189,21 @@ def reloc_solve_one(ftype, uv_ref, uv_cur, ref21, init21, opt=None, **kw):
     rows = [dict(cost=l.cost, cost_change=l.cost_change, gradient_max_norm=l.gradient_max_norm, step_norm=l.step_norm, relative_decrease=l.relative_decrease,
                  trust_region_radius=l.trust_region_radius, step_is_successful=l.step_is_successful) for l in log[: n.value]]
     return out, rows, term.value
+
+
+# ---------------------------------------------------------------------------------------- tracks (tracks_oracle.cpp)
+def tracks_build(matches, min_track_length=4):
+    """TracksBuilder::Build/Filter/ExportToSTL restated on the CPU; track ids are the reference's union-by-rank roots"""
+    from ptz_calib_b200 import tracks as T
+
+    rc, t = T.call_build(lib().orc_tracks_build, matches, min_track_length, "orc_tracks_build")
+    assert rc == 0, rc
+    return t
+
+
+def tracks_flatten(tracks, views):
+    from ptz_calib_b200 import tracks as T
+
+    rc, o = T.call_flatten(lib().orc_tracks_flatten, tracks, views)
+    assert rc == 0, rc
+    return o

@@ -9,12 +9,13 @@ import ctypes as C
 
 import numpy as np
 
-from . import abi, lib, problem
+from . import abi, lib, problem, tracks
 from .abi import as_ptr, f32, f64
 from .problem import BAProblem, BAResult, RelocBatch, RelocResult, default_options
+from .tracks import Matches, Tracks, Views, Observations, build_tracks, flatten_tracks
 
 __all__ = ["abi", "problem", "BAProblem", "BAResult", "RelocBatch", "RelocResult", "default_options", "ba_solve", "ba_eval", "BAHandle",
-           "reloc_solve_batch", "reloc_eval", "PTZRayOptimizer", "KRTOptimizer", "device_count", "nccl_init_from_torch", "nccl_finalize"]
+           "reloc_solve_batch", "reloc_eval", "tracks", "Matches", "Tracks", "Views", "Observations", "build_tracks", "flatten_tracks", "PTZRayOptimizer", "KRTOptimizer", "device_count", "nccl_init_from_torch", "nccl_finalize"]
 
 
 def device_count() -> int:

@@ -12,6 +12,7 @@ EXPORTS = [
     "ptzba_solve", "ptzba_eval", "ptzba_create", "ptzba_reset", "ptzba_run", "ptzba_get_stage_times", "ptzba_destroy",
     "ptz_nccl_unique_id", "ptz_nccl_init", "ptz_nccl_finalize",
     "ptzreloc_solve_batch", "ptzreloc_eval", "ptzreloc_solve_batch_dev",
+    "ptztracks_build", "ptztracks_build_dev", "ptztracks_flatten",
 ]
 
 

@@ -288,3 +288,103 @@ def make_reloc_batch(B, factor_type=abi.PTZ_KRT_F, seed=1003, n_min=64, n_max=51
         uvp, _ = project(Rq[pb], fq[pb], cq[pb], k1v, Xw)
         pts = dict(pt_offset=poff, pt_uv=(uvp + q.normal(0, sigma, uvp.shape)).astype(np.float32), pt_xyz=Xw)
     return RelocBatch(factor_type, off, uv_ref, uv_cur, ref_cam, init_cam, max_iter, max_reproj_error, gt, **pts)
+
+
+# ------------------------------------------------------------------------------------------ pairwise matches of a scene
+def make_matches_from_scene(prob, seed=11, edge_prob=1.0, n_collisions=0, n_short=0, extra_keypoints=0):
+    """What feature matching would hand to TracksBuilder for a synthetic scene: keypoints per image (a view's observations,
+    feature id = rank inside the view, plus `extra_keypoints` unmatched ones per image) and pairwise matches (every pair of a
+    track's observations with probability `edge_prob`, consecutive ones always, so the track stays connected).
+
+    n_collisions: extra matches that glue two tracks seen in a common image together -> that image is listed twice and
+    Filter rejects the merged set.  n_short: extra 2- and 3-image sets -> Filter(4) rejects them.
+
+    Returns (Matches, Views, expected) where expected = {frozenset((image, feature), ...)} of the tracks that must survive.
+    """
+    from .tracks import Matches, Views
+
+    rng = np.random.default_rng(seed)
+    V, M = prob.V, prob.M
+    order = np.lexsort((prob.obs_track, prob.obs_view))  # keypoints of an image in (view, track) order
+    view_s, track_s = prob.obs_view[order], prob.obs_track[order]
+    cnt = np.bincount(view_s, minlength=V).astype(np.int64)
+    nkp = cnt + extra_keypoints
+    kp_offset = np.concatenate([[0], np.cumsum(nkp)]).astype(np.int64)
+    first = np.concatenate([[0], np.cumsum(cnt)])[:-1]
+    feat = (np.arange(M) - first[view_s]).astype(np.int32)
+    kp_uv = np.zeros((int(kp_offset[-1]), 2), np.float32)
+    kp_uv[kp_offset[view_s] + feat] = prob.obs_uv[order]
+    if extra_keypoints:
+        for v in range(V):
+            kp_uv[kp_offset[v] + cnt[v]:kp_offset[v + 1]] = rng.uniform(0, 1000, (extra_keypoints, 2)).astype(np.float32)
+    # observations grouped by track (inside a track: ascending view)
+    g = np.lexsort((view_s, track_s))
+    tv, tf, tt = view_s[g], feat[g], track_s[g]
+    ea, eb = [], []
+    d = 1
+    while True:
+        same = tt[:-d] == tt[d:] if d < len(tt) else np.zeros(0, bool)
+        if not same.any():
+            break
+        idx = np.nonzero(same)[0]
+        if d > 1 and edge_prob < 1.0:
+            idx = idx[rng.random(len(idx)) < edge_prob]
+        ea.append(idx)
+        eb.append(idx + d)
+        d += 1
+    ea = np.concatenate(ea) if ea else np.zeros(0, np.int64)
+    eb = np.concatenate(eb) if eb else np.zeros(0, np.int64)
+    src, dst, q, t = tv[ea], tv[eb], tf[ea], tf[eb]  # ascending view inside a track: src < dst
+    dead = set()
+    if n_collisions:
+        # a match between a node of track A and a node of track B, A and B both seen in image v (as neighbours in (view, track) order)
+        start = np.concatenate([[0], np.nonzero(tt[1:] != tt[:-1])[0] + 1, [len(tt)]])
+        done = 0
+        for k in rng.permutation(M - 1):
+            if done >= n_collisions:
+                break
+            if view_s[k] != view_s[k + 1] or track_s[k] == track_s[k + 1]:
+                continue
+            A, B = int(track_s[k]), int(track_s[k + 1])
+            if A in dead or B in dead:
+                continue
+            ia = np.arange(start[A], start[A + 1])
+            ib = np.arange(start[B], start[B + 1])
+            ia, ib = ia[tv[ia] != view_s[k]], ib[tv[ib] != view_s[k]]
+            pairs = [(x, y) for x in ia for y in ib if tv[x] != tv[y]]
+            if not pairs:
+                continue
+            x, y = pairs[rng.integers(len(pairs))]
+            if tv[x] > tv[y]:
+                x, y = y, x
+            src, dst, q, t = np.append(src, tv[x]), np.append(dst, tv[y]), np.append(q, tf[x]), np.append(t, tf[y])
+            dead.update((A, B))
+            done += 1
+    if n_short:
+        assert extra_keypoints >= 1 and V >= 3
+        used = np.zeros(V, np.int64)
+        for _ in range(n_short):
+            L = int(rng.integers(2, 4))
+            vs = np.sort(rng.choice(V, L, replace=False))
+            if (used[vs] >= extra_keypoints).any():
+                continue
+            fs = cnt[vs] + used[vs]
+            used[vs] += 1
+            for a in range(L - 1):
+                src, dst, q, t = np.append(src, vs[a]), np.append(dst, vs[a + 1]), np.append(q, fs[a]), np.append(t, fs[a + 1])
+    # group by image pair, pairs in ascending (src, dst): the order of a vector<MatchesInfo> filled by two nested loops
+    o = np.lexsort((np.arange(len(src)), dst, src))
+    src, dst, q, t = src[o], dst[o], q[o], t[o]
+    key = src.astype(np.int64) * V + dst
+    pk, pstart = np.unique(key, return_index=True)
+    match_offset = np.concatenate([pstart, [len(key)]]).astype(np.int64)
+    matches = Matches((pk // V).astype(np.int32), (pk % V).astype(np.int32), match_offset, q.astype(np.int32), t.astype(np.int32))
+    views = Views(np.ones(V, np.uint8), kp_offset, kp_uv)
+    expected = set()
+    bounds = np.concatenate([[0], np.nonzero(tt[1:] != tt[:-1])[0] + 1, [len(tt)]])
+    for k in range(len(bounds) - 1):
+        b, e = bounds[k], bounds[k + 1]
+        if int(tt[b]) in dead:
+            continue
+        expected.add(frozenset(zip(tv[b:e].tolist(), tf[b:e].tolist())))
+    return matches, views, expected

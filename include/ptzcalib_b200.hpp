@@ -180,14 +180,15 @@ class PTZRayOptimizer {
 
   bool Solve(std::vector<Camera>& cameras, std::vector<std::vector<Ray>>& rays) {
     if (!CheckValid()) return false;
-    FindTracks();
-    // flatten (AddConstraints2d2d / 2d3d, .cc:799-958): candidate views get dense ids, one row per (track, candidate view)
+    if (!FindTracks()) return false;
+    // candidate views get dense ids in ascending image id; one row per (track, candidate view): AddConstraints2d2d, .cc:799-848,
+    // flattened on the device by ptztracks_flatten
     std::vector<long> view_of;
     std::unordered_map<long, int> dense;
     for (size_t i = 0; i < num_cams_; ++i) if (isCandidate((long)i)) { dense[(long)i] = (int)view_of.size(); view_of.push_back((long)i); }
     std::vector<double> intr, ext, weight, pxyz;
     std::vector<float> uv, puv;
-    std::vector<int32_t> oview, otrack, pview;
+    std::vector<int32_t> oview, otrack, pview, row_track;
     std::vector<int> track_ids;
     for (long id : view_of) {
       const std::vector<double> v = cameras_[id].ToVector();
@@ -195,14 +196,26 @@ class PTZRayOptimizer {
       intr.insert(intr.end(), in, in + 9);
       ext.insert(ext.end(), v.begin() + 4, v.begin() + 10);
     }
-    for (const auto& te : tracks_) {
-      int row = -1;
-      for (const auto& it : te.second) {
-        if (!isCandidate(it.first)) continue;
-        if (row < 0) { row = (int)track_ids.size(); track_ids.push_back(te.first); weight.push_back((double)te.second.size()); }
-        const Point2f pt = features_[it.first].keypoints[it.second].pt;
-        uv.push_back(pt.x); uv.push_back(pt.y); oview.push_back(dense[it.first]); otrack.push_back(row);
-      }
+    {
+      std::vector<uint8_t> cand(num_cams_, 0);
+      std::vector<int64_t> kp_off(num_cams_ + 1, 0);
+      for (size_t i = 0; i < num_cams_; ++i) { cand[i] = isCandidate((long)i) ? 1 : 0; kp_off[i + 1] = kp_off[i] + (int64_t)features_[i].keypoints.size(); }
+      std::vector<float> kp(2 * (size_t)kp_off[num_cams_] + 2);
+      for (size_t i = 0; i < num_cams_; ++i)
+        for (size_t j = 0; j < features_[i].keypoints.size(); ++j) { kp[2 * (kp_off[i] + j)] = features_[i].keypoints[j].pt.x; kp[2 * (kp_off[i] + j) + 1] = features_[i].keypoints[j].pt.y; }
+      ptztracks_views tv{(int32_t)num_cams_, cand.data(), kp_off.data(), kp.data()};
+      ptztracks_result tr{};
+      tr.num_tracks = (int32_t)flat_id_.size(); tr.num_elems = (int64_t)flat_img_.size();
+      tr.track_id = flat_id_.data(); tr.track_offset = flat_off_.data(); tr.elem_img = flat_img_.data(); tr.elem_feat = flat_feat_.data();
+      const size_t nt = std::max<size_t>(flat_id_.size(), 1), ne = std::max<size_t>(flat_img_.size(), 1);
+      row_track.resize(nt); weight.resize(nt); uv.resize(2 * ne); oview.resize(ne); otrack.resize(ne);
+      ptztracks_obs ob{};
+      ob.cap_rows = (int64_t)nt; ob.cap_obs = (int64_t)ne;
+      ob.row_track = row_track.data(); ob.track_weight = weight.data(); ob.obs_uv = uv.data(); ob.obs_view = oview.data(); ob.obs_track = otrack.data();
+      last_status_ = ptztracks_flatten(&tr, &tv, &ob);
+      if (last_status_ != PTZ_OK) return false;
+      row_track.resize(ob.num_rows); weight.resize(ob.num_rows); uv.resize(2 * (size_t)ob.num_obs); oview.resize(ob.num_obs); otrack.resize(ob.num_obs);
+      for (int32_t r : row_track) track_ids.push_back(flat_id_[r]);
     }
     for (long id : view_of)
       if (!pixels_.empty())
@@ -268,11 +281,32 @@ class PTZRayOptimizer {
     }
     return true;
   }
-  void FindTracks() {  // .cc:537-552
-    TracksBuilder b;
-    b.Build(matches_info_);
-    b.Filter(4);
-    b.ExportToSTL(tracks_);
+  // .cc:537-552: TracksBuilder::Build / Filter(4) / ExportToSTL, on the device (ptztracks_build); the class above stays as the
+  // host-side mirror of the reference's TracksBuilder API.  Track ids are canonical (smallest node), see ptzcalib_b200.h.
+  bool FindTracks() {
+    std::vector<int32_t> src, dst, q, t;
+    std::vector<int64_t> off(1, 0);
+    for (const auto& mi : matches_info_) {
+      src.push_back((int32_t)mi.src_img_idx); dst.push_back((int32_t)mi.dst_img_idx);
+      for (const auto& m : mi.matches) { q.push_back(m.queryIdx); t.push_back(m.trainIdx); }
+      off.push_back((int64_t)q.size());
+    }
+    const size_t N = q.size();
+    ptztracks_matches mm{(int32_t)src.size(), src.data(), dst.data(), off.data(), q.data(), t.data(), 4};
+    flat_id_.assign(std::max<size_t>(N, 1), 0); flat_off_.assign(std::max<size_t>(N, 1) + 1, 0);
+    flat_img_.assign(std::max<size_t>(2 * N, 1), 0); flat_feat_.assign(std::max<size_t>(2 * N, 1), 0);
+    ptztracks_result tr{};
+    tr.cap_tracks = (int64_t)N; tr.cap_elems = (int64_t)(2 * N);
+    tr.track_id = flat_id_.data(); tr.track_offset = flat_off_.data(); tr.elem_img = flat_img_.data(); tr.elem_feat = flat_feat_.data();
+    last_status_ = ptztracks_build(&mm, &tr);
+    if (last_status_ != PTZ_OK) return false;
+    flat_id_.resize(tr.num_tracks); flat_off_.resize((size_t)tr.num_tracks + 1); flat_img_.resize(tr.num_elems); flat_feat_.resize(tr.num_elems);
+    tracks_.clear();
+    for (int32_t k = 0; k < tr.num_tracks; ++k) {
+      Track& trk = tracks_[flat_id_[k]];
+      for (int64_t i = flat_off_[k]; i < flat_off_[k + 1]; ++i) trk.emplace_hint(trk.end(), flat_img_[i], flat_feat_[i]);
+    }
+    return true;
   }
   bool isCandidate(long id) const { return cam_ids_.find(id) != cam_ids_.end(); }
 
@@ -287,6 +321,8 @@ class PTZRayOptimizer {
   FACTOR_TYPE type_;
   std::vector<double> tlw_param_ = std::vector<double>(6, 0.0);
   Tracks tracks_;
+  std::vector<int32_t> flat_id_, flat_img_, flat_feat_;  // tracks_ as ptztracks_result arrays
+  std::vector<int64_t> flat_off_;
   int max_iter_ = 100, num_iterations_ = 0, last_status_ = 0;
   double init_reproj_error_all_ = 0, final_reproj_error_all_ = 0, final_reproj_error_2d2d_ = 0, final_reproj_error_2d3d_ = 0;
 };

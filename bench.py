@@ -243,6 +243,10 @@ def run_ours(args):
     if not args.no_reloc:
         reloc = bench_reloc(args, rank, world, barrier, allmax, allsum)
 
+    tracks = None
+    if rank == 0 and world == 1 and not args.no_tracks:
+        tracks = bench_tracks(args, prob)
+
     clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- CPU baseline (oracle port) on rank 0, bounded sample ----------------
@@ -263,7 +267,7 @@ def run_ours(args):
             "pcg_iterations_per_step": round(st["pcg_iterations"] / st["lm_iterations"], 1),
             "us_per_pcg_iteration": round(1e3 * kernels["pcg"]["ms"] / max(st["pcg_iterations"], 1), 3) if "pcg" in kernels else None,
             "rj_mobs_per_sec": round(prob.M / (rj["avg_us"]) , 1) if rj else None,
-            "gpu_launches": launches, "kernels": table, "roofline": roofline, "e2e": e2e, "reloc": reloc, "cpu_baseline": cpu, "clocks": clocks,
+            "gpu_launches": launches, "kernels": table, "roofline": roofline, "e2e": e2e, "reloc": reloc, "tracks": tracks, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -329,6 +333,72 @@ def bench_reloc(args, rank, world, barrier, allmax, allsum):
     return dict(workload=f"cfg3: {B} queries, {int(allsum(float(b.N)))} matches, factor F, 5% displaced outliers", solves_per_sec=round(B / (ms * 1e-3), 1),
                 ms_per_batch=round(ms, 3), mean_lm_iterations=round(iters, 2), success_rate=round(succ, 4), e2e_solves_per_sec=round(B / dt, 1),
                 e2e_seconds=round(dt, 4), h2d_bytes=int(b.N * 16 + b.B * (42 * 8 + 8)), d2h_bytes=int(b.B * (21 + 15 + 3) * 8 + b.B * 16))
+
+
+def bench_tracks(args, prob):
+    """Track building on the matches of the bench scene: device-resident (ptztracks_build_dev, CUDA events), end to
+    end through ptztracks_build with pinned host buffers, and the CPU restatement of TracksBuilder on a bounded sample of the pairs."""
+    import ctypes as C
+
+    import torch
+
+    import ptz_calib_b200 as ptz
+    from ptz_calib_b200 import abi, lib, synth
+    from ptz_calib_b200 import tracks as T
+
+    m, v, _ = synth.make_matches_from_scene(prob)
+    N = m.num_matches
+    dev = torch.device("cuda")
+    L = lib.load()
+    tens = [torch.from_numpy(a).to(dev) for a in (m.pair_src, m.pair_dst, m.match_offset, m.query_idx, m.train_idx)]
+    cm = T.MatchesC()
+    cm.num_pairs, cm.min_track_length = len(m.pair_src), 4
+    cm.pair_src, cm.pair_dst = C.cast(tens[0].data_ptr(), abi.ip), C.cast(tens[1].data_ptr(), abi.ip)
+    cm.match_offset = C.cast(tens[2].data_ptr(), abi.lp)
+    cm.query_idx, cm.train_idx = C.cast(tens[3].data_ptr(), abi.ip), C.cast(tens[4].data_ptr(), abi.ip)
+    o_tid, o_off = torch.zeros(N, dtype=torch.int32, device=dev), torch.zeros(N + 1, dtype=torch.int64, device=dev)
+    o_img, o_feat = torch.zeros(2 * N, dtype=torch.int32, device=dev), torch.zeros(2 * N, dtype=torch.int32, device=dev)
+    cr = T.TracksC()
+    cr.cap_tracks, cr.cap_elems = N, 2 * N
+    cr.track_id, cr.track_offset = C.cast(o_tid.data_ptr(), abi.ip), C.cast(o_off.data_ptr(), abi.lp)
+    cr.elem_img, cr.elem_feat = C.cast(o_img.data_ptr(), abi.ip), C.cast(o_feat.data_ptr(), abi.ip)
+    stream = torch.cuda.current_stream()
+
+    def run():
+        lib.check(L.ptztracks_build_dev(C.byref(cm), C.c_int64(N), C.byref(cr), C.c_void_p(stream.cuda_stream)), "tracks dev")
+
+    for _ in range(3):
+        run()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    ok = cr.num_tracks == prob.P and cr.num_elems == prob.M
+    # end to end with pinned host buffers
+    for name in ("pair_src", "pair_dst", "match_offset", "query_idx", "train_idx"):
+        setattr(m, name, torch.from_numpy(np.ascontiguousarray(getattr(m, name))).pin_memory().numpy())
+    ptz.build_tracks(m, 4)
+    t0 = time.perf_counter()
+    t = ptz.build_tracks(m, 4)
+    dt = time.perf_counter() - t0
+    # CPU restatement (std::set + union-by-rank, as the reference) on the first pairs holding ~1/8 of the matches
+    from oracle import oracle as orc
+
+    kp = int(np.searchsorted(m.match_offset, N // 8))
+    ms_ = T.Matches(m.pair_src[:kp], m.pair_dst[:kp], m.match_offset[:kp + 1], m.query_idx[:m.match_offset[kp]], m.train_idx[:m.match_offset[kp]])
+    t0 = time.perf_counter()
+    orc.tracks_build(ms_, 4)
+    dc = time.perf_counter() - t0
+    # algorithmic bytes: 16 B/match in (two indices + the pair's images), 8 B/track element out
+    return dict(workload=f"matches of the bench scene: {N} matches in {len(m.pair_src)} image pairs -> {t.num_tracks} tracks, {len(t.elem_img)} elements",
+                matches_per_sec=round(N / (ms * 1e-3), 1), ms_per_build=round(ms, 3), tracks_as_scene=bool(ok),
+                e2e_matches_per_sec=round(N / dt, 1), e2e_seconds=round(dt, 4), h2d_bytes=int(8 * N + 16 * len(m.pair_src)), d2h_bytes=int(8 * len(t.elem_img) + 12 * t.num_tracks),
+                cpu_matches_per_sec=round(ms_.num_matches / dc, 1), cpu_sample=f"first {kp} pairs ({ms_.num_matches} matches), 1 thread, {dc:.1f} s")
 
 
 def cpu_baseline(args, prob):
@@ -406,6 +476,7 @@ def main():
     ap.add_argument("--cpu-tracks", type=int, default=40000)
     ap.add_argument("--cpu-iters", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tracks", action="store_true")
     ap.add_argument("--no-reloc", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -49,6 +49,7 @@ struct MatchesInfo {
   std::vector<unsigned char> inliers_mask;
   int num_inliers = 0;
   Mat33 H{{1, 0, 0, 0, 1, 0, 0, 0, 1}};
+  bool has_H = false;  // stands for !H.empty() of the cv::Mat (data_io.cc fills H for image pairs that passed RANSAC)
   double confidence = 0;
 };
 struct Ray {
@@ -387,6 +388,238 @@ class KRTOptimizer {
   FACTOR_TYPE factor_type_ = F;
   int max_iter_ = 100;
   double max_reproj_error_ = 50;
+};
+
+// ptz_incremental_optimizer.h:24-124, .cc:39-441 — PTZ-IBA: greedy incremental registration around global bundle adjustments.
+// Same control flow, thresholds and state as the reference; the numerical work goes to the GPU: every global BA is one
+// ptztracks_build + ptztracks_flatten + ptzba_solve (through PTZRayOptimizer above), and RegisterNextImage solves ALL the
+// candidate (registered neighbour, new image) KRT problems of one image in ONE ptzreloc_solve_batch call — one CTA each —
+// then takes the first success in matches_info order, which is what the reference's sequential loop (.cc:384-415) returns.
+class PtzIncrementalOptimizer {
+ public:
+  PtzIncrementalOptimizer(const std::vector<ImageFeatures>& features, const std::vector<MatchesInfo>& matches_info, const std::vector<Camera>& cameras,
+                          int max_iter)
+      : cameras_(cameras), features_(features), matches_info_(matches_info), max_iter_(max_iter) {}
+  PtzIncrementalOptimizer(const std::vector<ImageFeatures>& features, const std::vector<MatchesInfo>& matches_info, const std::vector<Camera>& cameras,
+                          const std::vector<std::string>& names, int max_iter)
+      : cameras_(cameras), features_(features), matches_info_(matches_info), names_(names), max_iter_(max_iter) {}
+
+  static long& kMaxNumImages() { static long v = 100000; return v; }            // .cc:24
+  static float& kBaGlobalImagesRatio() { static float v = 1.1f; return v; }     // .cc:25
+
+  void SetSeedImageId(const std::vector<long>& image_ids) { seed_image_ids_ = image_ids; }  // .cc:127-132
+
+  bool Solve(std::vector<Camera>& cameras, std::unordered_set<long>& reg_image_ids) {  // .cc:39-125
+    if (features_.empty() || features_.size() != cameras_.size() || max_iter_ <= 0) return false;  // CheckValid, .cc:134-140
+    const int kInitNumTrials = 50;
+    for (int trial = 0; trial < kInitNumTrials; ++trial) {
+      long id1, id2;
+      if (!FindInitialImagePair(id1, id2)) return false;
+      if (!RegisterInitialImagePair(id1, id2)) continue;
+      AdjustGlobalBundle();
+      size_t ba_prev = reg_image_ids_.size();
+      bool reg_next = true;
+      while (reg_next) {
+        reg_next = false;
+        const std::vector<long> next = FindNextImages();
+        if (next.empty()) break;
+        for (size_t reg_trial = 0; reg_trial < next.size(); ++reg_trial) {
+          const long image_id = next[reg_trial];
+          reg_next = RegisterNextImage(image_id);
+          if (reg_next && reg_image_ids_.size() >= kBaGlobalImagesRatio() * ba_prev) {
+            if (AdjustGlobalBundle()) { ba_prev = reg_image_ids_.size(); break; }
+            reg_image_ids_.erase(image_id);
+            reg_next = false;
+          }
+          if (!reg_next) {
+            // an initial pair that cannot grow is abandoned for another one
+            const size_t kMinNumInitialRegTrials = 30, kMinModelSize = 3;
+            if (reg_trial >= kMinNumInitialRegTrials && reg_image_ids_.size() < kMinModelSize) break;
+          }
+        }
+      }
+      AdjustGlobalBundle();
+      reg_image_ids = reg_image_ids_;
+      cameras = cameras_;
+      return true;
+    }
+    return false;
+  }
+
+  // bookkeeping a caller may want to look at (not in the reference's public interface)
+  int num_global_bundles() const { return num_global_bundles_; }
+  int num_reloc_batches() const { return num_reloc_batches_; }
+  int num_reloc_queries() const { return num_reloc_queries_; }
+  double last_reproj_error() const { return last_reproj_error_; }
+
+ private:
+  bool isReg(long id) const { return reg_image_ids_.find(id) != reg_image_ids_.end(); }
+  static std::vector<long> RankedIds(const std::vector<float>& rank) {  // descending confidence, images without any dropped
+    std::vector<long> idx(rank.size());
+    std::iota(idx.begin(), idx.end(), 0);
+    std::sort(idx.begin(), idx.end(), [&](int A, int B) -> bool { return rank[A] > rank[B]; });
+    std::vector<long> out;
+    for (long i : idx) {
+      if (rank[i] <= 0.0f) break;
+      out.push_back(i);
+    }
+    return out;
+  }
+  long PairId(long a, long b) const { return a < b ? a * kMaxNumImages() + b : b * kMaxNumImages() + a; }  // .cc:306-312
+
+  bool FindInitialImagePair(long& id1, long& id2) {  // .cc:142-177
+    const std::vector<long> first = seed_image_ids_.empty() ? FindFirstInitialImage() : seed_image_ids_;
+    for (long a : first)
+      for (long b : FindSecondInitialImage(a)) {
+        const long pid = PairId(a, b);
+        if (init_image_pairs_.count(pid) > 0) continue;  // every pair is tried once
+        init_image_pairs_.insert(pid);
+        id1 = a; id2 = b;
+        return true;
+      }
+    id1 = id2 = std::numeric_limits<long>::max();
+    return false;
+  }
+  std::vector<long> FindFirstInitialImage() const {  // .cc:179-206
+    std::vector<float> rank(features_.size(), 0.0f);
+    for (const auto& mi : matches_info_) { rank[mi.src_img_idx] += (float)mi.confidence; rank[mi.dst_img_idx] += (float)mi.confidence; }
+    return RankedIds(rank);
+  }
+  std::vector<long> FindSecondInitialImage(long id1) const {  // .cc:208-247
+    std::vector<float> rank(features_.size(), 0.0f);
+    const float kMinPixelDiff = 50;
+    for (const auto& mi : matches_info_) {
+      const long s = mi.src_img_idx, d = mi.dst_img_idx;
+      if (mi.matches.empty() || (id1 != s && id1 != d) || (id1 == s && id1 == d)) continue;
+      if (CalPixelDiff(s, d, mi.matches) < kMinPixelDiff) continue;
+      rank[id1 == s ? d : s] += (float)mi.confidence;
+    }
+    return RankedIds(rank);
+  }
+  std::vector<long> FindNextImages() const {  // .cc:249-290
+    std::vector<float> rank(features_.size(), 0.0f);
+    const size_t kMaxRegTrials = 4;
+    auto tired = [&](long id) { auto it = num_reg_trials_.find(id); return it != num_reg_trials_.end() && it->second > kMaxRegTrials; };
+    for (const auto& mi : matches_info_) {
+      const long s = mi.src_img_idx, d = mi.dst_img_idx;
+      if (s == d || !mi.has_H || tired(s) || tired(d)) continue;
+      const bool rs = isReg(s), rd = isReg(d);
+      if (rs == rd) continue;  // both registered already, or neither a neighbour of the model
+      rank[rs ? d : s] += (float)mi.confidence;
+    }
+    return RankedIds(rank);
+  }
+  float CalPixelDiff(long id1, long id2, const std::vector<DMatch>& matches) const {  // .cc:292-304 (float accumulation as there)
+    float total = 0.0f;
+    for (const DMatch& m : matches) {
+      const Point2f a = features_[id1].keypoints[m.queryIdx].pt, b = features_[id2].keypoints[m.trainIdx].pt;
+      total += (float)std::sqrt((double)(a.x - b.x) * (a.x - b.x) + (double)(a.y - b.y) * (a.y - b.y));
+    }
+    return total * 1.0f / matches.size();
+  }
+  // R_j = K_j^-1 H_ji K_i R_i (.cc:343-346, 391-393)
+  static Mat33 RotationFromHomography(const Mat33& Kj, const Mat33& H, const Mat33& Ki, const Mat33& Ri) {
+    Mat33 Kinv, a, b, c;
+    ptz::inv3(Kj.data(), Kinv.data());
+    ptz::mul33(Kinv.data(), H.data(), a.data());
+    ptz::mul33(a.data(), Ki.data(), b.data());
+    ptz::mul33(b.data(), Ri.data(), c.data());
+    return c;
+  }
+  void SetInitialImagePairParameters(long id1, long id2) {  // .cc:314-350
+    const double ratio = 1.2;  // sets the initial field of view
+    for (long id : {id1, id2}) {
+      const double focal = ratio * std::max(features_[id].img_size.width, features_[id].img_size.height);
+      Mat33& K = cameras_[id].K();
+      K[0] = K[4] = focal; K[2] = 0.5 * features_[id].img_size.width; K[5] = 0.5 * features_[id].img_size.height;
+    }
+    cameras_[id1].R() = Mat33{{1, 0, 0, 0, 1, 0, 0, 0, 1}};
+    for (const auto& mi : matches_info_)
+      if (mi.src_img_idx == id1 && mi.dst_img_idx == id2) {
+        cameras_[id2].R() = RotationFromHomography(cameras_[id2].K(), mi.H, cameras_[id1].K(), cameras_[id1].R());
+        break;
+      }
+  }
+  bool RegisterInitialImagePair(long id1, long id2) {  // .cc:352-375
+    num_reg_trials_[id1] += 1; num_reg_trials_[id2] += 1;
+    init_image_pairs_.insert(PairId(id1, id2));
+    SetInitialImagePairParameters(id1, id2);
+    PTZRayOptimizer optimizer(features_, matches_info_, cameras_, std::unordered_set<long>{id1, id2}, max_iter_, PTZRay);
+    const bool ok = optimizer.Solve(cameras_);
+    if (ok) { reg_image_ids_.insert(id1); reg_image_ids_.insert(id2); }
+    return ok;
+  }
+  bool RegisterNextImage(long image_id) {  // .cc:377-419, batched
+    num_reg_trials_[image_id] += 1;
+    const long j = image_id;
+    std::vector<const MatchesInfo*> cand;
+    for (const auto& mi : matches_info_)
+      if (mi.has_H && isReg(mi.src_img_idx) && mi.dst_img_idx == j) cand.push_back(&mi);
+    if (cand.empty()) return false;
+    const int B = (int)cand.size();
+    std::vector<int64_t> off(1, 0);
+    std::vector<float> uv1, uv2;
+    std::vector<double> ref(21 * (size_t)B), init(21 * (size_t)B), out(21 * (size_t)B);
+    std::vector<Camera> init_cam(B);
+    for (int q = 0; q < B; ++q) {
+      const MatchesInfo& mi = *cand[q];
+      const long i = mi.src_img_idx;
+      Camera cj = cameras_[j];
+      cj.K() = cameras_[i].K();
+      cj.R() = RotationFromHomography(cj.K(), mi.H, cameras_[i].K(), cameras_[i].R());
+      init_cam[q] = cj;
+      cameras_[i].ToKrt21(&ref[21 * (size_t)q]);
+      cj.ToKrt21(&init[21 * (size_t)q]);
+      for (const DMatch& m : mi.matches) {
+        const Point2f a = features_[i].keypoints[m.queryIdx].pt, b = features_[j].keypoints[m.trainIdx].pt;
+        uv1.push_back(a.x); uv1.push_back(a.y); uv2.push_back(b.x); uv2.push_back(b.y);
+      }
+      off.push_back((int64_t)(uv1.size() / 2));
+    }
+    ptzreloc_batch b{};
+    b.factor_type = PTZ_KRT_F; b.num_queries = B; b.match_offset = off.data(); b.uv_ref = uv1.data(); b.uv_cur = uv2.data();
+    b.ref_cam = ref.data(); b.init_cam = init.data();
+    b.max_iter = 100; b.max_reproj_error = 100;  // .cc:395-396
+    std::vector<int32_t> ok(B, 0), term(B, 0), nit(B, 0);
+    ptzreloc_result r{};
+    r.cam = out.data(); r.success = ok.data(); r.termination = term.data(); r.num_iter = nit.data();
+    ptz_solver_options o;
+    ptz_solver_options_default(&o);
+    ++num_reloc_batches_; num_reloc_queries_ += B;
+    if (ptzreloc_solve_batch(&b, &o, &r) != PTZ_OK) return false;
+    for (int q = 0; q < B; ++q)
+      if (ok[q]) {
+        Camera c;
+        c.FromKrt21(&out[21 * (size_t)q]);
+        cameras_[j].K() = c.K();
+        cameras_[j].R() = c.R();
+        reg_image_ids_.insert(j);
+        return true;
+      }
+    // every trial failed: the reference leaves the last trial's initial K, R in cameras_[j]
+    cameras_[j].K() = init_cam[B - 1].K();
+    cameras_[j].R() = init_cam[B - 1].R();
+    return false;
+  }
+  bool AdjustGlobalBundle() {  // .cc:421-439
+    PTZRayOptimizer optimizer(features_, matches_info_, cameras_, reg_image_ids_, max_iter_, PTZRay);
+    const bool ok = optimizer.Solve(cameras_);
+    last_reproj_error_ = optimizer.final_reproj_error_all();
+    ++num_global_bundles_;
+    return ok;
+  }
+
+  std::vector<Camera> cameras_;
+  std::vector<ImageFeatures> features_;
+  std::vector<MatchesInfo> matches_info_;
+  std::vector<std::string> names_;
+  int max_iter_;
+  std::unordered_set<long> init_image_pairs_;            // image pairs already tried as the seed
+  std::unordered_map<long, size_t> num_reg_trials_;      // registration attempts per image (bounded by kMaxRegTrials)
+  std::unordered_set<long> reg_image_ids_;
+  std::vector<long> seed_image_ids_;
+  int num_global_bundles_ = 0, num_reloc_batches_ = 0, num_reloc_queries_ = 0;
+  double last_reproj_error_ = 0;
 };
 
 }  // namespace ptzcalib

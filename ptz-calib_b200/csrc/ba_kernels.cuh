@@ -53,89 +53,128 @@ __global__ void k_view_prep(int V, const double* __restrict__ intr, const double
   vt[i] = t;
 }
 
-// One CTA per chunk of one view.  Each thread: one observation -> weighted, Jacobi-scaled residual/Jacobian record,
-// plus the chunk's partial camera block (U upper, g) and cost by a fixed-order block reduction.
+// Each thread: one observation -> weighted, Jacobi-scaled residual/Jacobian record, plus the chunk's partial camera block
+// (U upper, g) and cost by a fixed-order block reduction.
+//
+// Persistent CTAs: CTA b owns the contiguous run of chunks [b*per, (b+1)*per) and walks it with a software pipeline, so that the
+// dependent gather chain  chunk -> o_track[o] -> trk[track]  (three DRAM/L2 latencies, which one-chunk-per-CTA launches exposed in
+// full at only 24 resident warps per SM) overlaps the record write-out and the block reduction of the previous chunk:
+//   iteration k:  compute chunk k from registers / shared memory, stage its records
+//                 ld.global  trk records of chunk k+1 (64 B per thread, index loaded one iteration earlier)  -> registers
+//                 ld.global  uv, track index of chunk k+2                                                    -> registers
+//                 cp.async   view table + camera scales of chunk k+1 (coalesced, 18 copies per CTA)          -> shared memory
+//                 coalesced write-out of the records, block reduction of the chunk partials
+// (A first pipelined version gathered the track records with per-thread cp.async: ncu showed each such copy costing ~30 shared-memory
+// wavefronts per warp — half of the kernel's shared-memory traffic — so the gather went back to registers, issued late.)
+constexpr int kResjacMaxPer = 64;  // chunks per CTA at most (their metadata sits in shared memory)
+#ifndef PTZ_RJ_MINB
+#define PTZ_RJ_MINB 5  // resident CTAs per SM the register budget of k_resjac is sized for
+#endif
 template <int TYPE>
-__global__ void __launch_bounds__(kChunk) k_resjac(const int* __restrict__ chunk_view, const int* __restrict__ chunk_begin, const int* __restrict__ chunk_cnt,
-                                                   const float2* __restrict__ o_uv, const int* __restrict__ o_track, const ViewTab* __restrict__ vt,
-                                                   const double* __restrict__ trk, const double* __restrict__ scale_cam, const double* __restrict__ disp,
-                                                   int weighted, double* __restrict__ rec, double* __restrict__ part,
-                                                   double* __restrict__ recd /* PTZRayDistDisp: [M][6] d r/d disp */, const double* __restrict__ scale_d) {
+__global__ void __launch_bounds__(kChunk, PTZ_RJ_MINB) k_resjac(int nchunks, int per, const int* __restrict__ chunk_view, const int* __restrict__ chunk_begin,
+                                                                const int* __restrict__ chunk_cnt, const float2* __restrict__ o_uv,
+                                                                const int* __restrict__ o_track, const ViewTab* __restrict__ vt,
+                                                                const double* __restrict__ trk, const double* __restrict__ scale_cam,
+                                                                const double* __restrict__ disp, int weighted, double* __restrict__ rec,
+                                                                double* __restrict__ part, double* __restrict__ recd /* PTZRayDistDisp: [M][6] d r/d disp */,
+                                                                const double* __restrict__ scale_d) {
   constexpr int NCL = ba_ncl(TYPE);
   typedef Dims<NCL> D;
-  __shared__ ViewTab svt;
-  __shared__ double ssc[NCL];
+  __shared__ __align__(16) ViewTab svt[2];
+  __shared__ __align__(16) double ssc[2][8];
+  __shared__ int s_view[kResjacMaxPer], s_begin[kResjacMaxPer], s_cnt[kResjacMaxPer];
   // one buffer, used first to stage the records for the coalesced write-out, then as scratch of the block reduction
   constexpr int kRecBytes = kChunk * D::RS * 8, kRedBytes = (D::NPART * (kChunk + 4) + D::NPART) * 8;
   __shared__ __align__(16) unsigned char sbuf[kRecBytes > kRedBytes ? kRecBytes : kRedBytes];
   double2* srec = reinterpret_cast<double2*>(sbuf);
   double* sred = reinterpret_cast<double*>(sbuf);
-  const int chunk = blockIdx.x;
-  const int view = chunk_view[chunk], begin = chunk_begin[chunk], cnt = chunk_cnt[chunk];
-  // issue the per-observation gathers before waiting for the view table
-  float2 uv = make_float2(0.f, 0.f);
+  const int t = threadIdx.x;
+  const int c0 = blockIdx.x * per, n = min(per, nchunks - c0);
+  if (n <= 0) return;
+  if (t < n) { s_view[t] = chunk_view[c0 + t]; s_begin[t] = chunk_begin[c0 + t]; s_cnt[t] = chunk_cnt[c0 + t]; }
+  __syncthreads();
+  auto stage_view = [&](int k) {  // asynchronous copies of chunk k's view table and camera scales into buffer k & 1
+    const int b = k & 1, view = s_view[k];
+    if (t < kViewTabDoubles / 2) cp_async16(reinterpret_cast<double2*>(&svt[b]) + t, reinterpret_cast<const double2*>(vt + view) + t);
+    else if (t >= 32 && t < 32 + NCL) cp_async8(&ssc[b][t - 32], scale_cam + view * NCL + (t - 32));
+    cp_async_commit();
+  };
+  float2 uv_a = make_float2(0.f, 0.f), uv_b = uv_a, uv_c = uv_a;
+  int p_b = -1, p_c = -1;
   double4 t0 = make_double4(0, 0, 1, 0), t1 = make_double4(1, 1, 1, 0);
-  if (threadIdx.x < cnt) {
-    const int o = begin + threadIdx.x;
-    uv = o_uv[o];
-    const int p = o_track[o];
-    t0 = *reinterpret_cast<const double4*>(trk + (size_t)p * kTrk);
-    t1 = *reinterpret_cast<const double4*>(trk + (size_t)p * kTrk + 4);
+  if (t < s_cnt[0]) {
+    uv_a = o_uv[s_begin[0] + t];
+    const int p_a = o_track[s_begin[0] + t];
+    t0 = *reinterpret_cast<const double4*>(trk + (size_t)p_a * kTrk);
+    t1 = *reinterpret_cast<const double4*>(trk + (size_t)p_a * kTrk + 4);
   }
-  if (threadIdx.x < kViewTabDoubles) reinterpret_cast<double*>(&svt)[threadIdx.x] = reinterpret_cast<const double*>(vt + view)[threadIdx.x];
-  if (threadIdx.x < NCL) ssc[threadIdx.x] = scale_cam[view * NCL + threadIdx.x];
-  __syncthreads();
-  double acc[D::NPART];
+  if (n > 1 && t < s_cnt[1]) { uv_b = o_uv[s_begin[1] + t]; p_b = o_track[s_begin[1] + t]; }
+  stage_view(0);
+  double dz[3] = {0, 0, 0};
+  if (TYPE == BA_PTZRAY_DIST_DISP) { dz[0] = disp[0]; dz[1] = disp[1]; dz[2] = disp[2]; }
+  for (int k = 0; k < n; ++k) {
+    cp_async_wait<0>();
+    __syncthreads();  // chunk k's view table is in svt[k & 1]; everybody is done with the previous chunk's buffers
+    if (k + 1 < n) stage_view(k + 1);
+    const int b = k & 1, chunk = c0 + k, begin = s_begin[k], cnt = s_cnt[k];
+    double acc[D::NPART];
 #pragma unroll
-  for (int i = 0; i < D::NPART; ++i) acc[i] = 0.0;
-  if (threadIdx.x < cnt) {
-    const double ray[3] = {t0.x, t0.y, t0.z};
-    double dz[3] = {0, 0, 0};
-    if (TYPE == BA_PTZRAY_DIST_DISP) { dz[0] = disp[0]; dz[1] = disp[1]; dz[2] = disp[2]; }
-    double r[2], F[2 * NCL], E[6], Fd[6];
-    ba_obs<TYPE, true>(svt, ray, dz, (double)uv.x, (double)uv.y, r, F, E, TYPE == BA_PTZRAY_DIST_DISP ? Fd : nullptr);
-    const double sw = weighted ? t0.w : 1.0;
-    if (TYPE == BA_PTZRAY_DIST_DISP) {
-      double* fo = recd + (size_t)(begin + threadIdx.x) * 6;
+    for (int i = 0; i < D::NPART; ++i) acc[i] = 0.0;
+    if (t < cnt) {
+      const double ray[3] = {t0.x, t0.y, t0.z};
+      double r[2], F[2 * NCL], E[6], Fd[6];
+      ba_obs<TYPE, true>(svt[b], ray, dz, (double)uv_a.x, (double)uv_a.y, r, F, E, TYPE == BA_PTZRAY_DIST_DISP ? Fd : nullptr);
+      const double sw = weighted ? t0.w : 1.0;
+      if (TYPE == BA_PTZRAY_DIST_DISP) {
+        double* fo = recd + (size_t)(begin + t) * 6;
 #pragma unroll
-      for (int j = 0; j < 3; ++j) { fo[j] = Fd[j] * sw * scale_d[j]; fo[3 + j] = Fd[3 + j] * sw * scale_d[j]; }
+        for (int j = 0; j < 3; ++j) { fo[j] = Fd[j] * sw * scale_d[j]; fo[3 + j] = Fd[3 + j] * sw * scale_d[j]; }
+      }
+      r[0] *= sw; r[1] *= sw;
+      const double sr[3] = {t1.x * sw, t1.y * sw, t1.z * sw};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { E[j] *= sr[j]; E[3 + j] *= sr[j]; }
+#pragma unroll
+      for (int a = 0; a < NCL; ++a) { const double s = ssc[b][a] * sw; F[a] *= s; F[NCL + a] *= s; }
+      // record -> shared memory in 16-byte chunks; XOR swizzle so that neither these stores nor the coalesced read-out conflict
+      double2 rc[D::RS / 2];
+      rc[0] = make_double2(r[0], r[1]);
+      rc[1] = make_double2(E[0], E[1]); rc[2] = make_double2(E[2], E[3]); rc[3] = make_double2(E[4], E[5]);
+#pragma unroll
+      for (int a = 0; a < NCL; ++a) rc[4 + a] = make_double2(F[2 * a], F[2 * a + 1]);  // F stored flat [2*NCL]
+#pragma unroll
+      for (int pch = 0; pch < D::RS / 2; ++pch) srec[t * (D::RS / 2) + rec_swz<NCL>(t, pch)] = rc[pch];
+      int kk = 0;
+#pragma unroll
+      for (int a = 0; a < NCL; ++a)
+#pragma unroll
+        for (int bb = a; bb < NCL; ++bb) acc[kk++] = F[a] * F[bb] + F[NCL + a] * F[NCL + bb];
+#pragma unroll
+      for (int a = 0; a < NCL; ++a) acc[D::NU + a] = F[a] * r[0] + F[NCL + a] * r[1];
+      acc[D::NU + NCL] = 0.5 * (r[0] * r[0] + r[1] * r[1]);
     }
-    r[0] *= sw; r[1] *= sw;
-    const double sr[3] = {t1.x * sw, t1.y * sw, t1.z * sw};
+    // gathers of the next two chunks: in flight during the write-out and the reduction below
+    if (p_b >= 0) {
+      t0 = *reinterpret_cast<const double4*>(trk + (size_t)p_b * kTrk);
+      t1 = *reinterpret_cast<const double4*>(trk + (size_t)p_b * kTrk + 4);
+    }
+    p_c = -1;
+    if (k + 2 < n && t < s_cnt[k + 2]) { uv_c = o_uv[s_begin[k + 2] + t]; p_c = o_track[s_begin[k + 2] + t]; }
+    __syncthreads();
+    // the chunk's records are contiguous in global memory: write them out as consecutive 16-byte chunks
+    double2* gout = reinterpret_cast<double2*>(rec + (size_t)begin * D::RS);
+    const int nch = cnt * (D::RS / 2);
+    for (int gch = t; gch < nch; gch += kChunk) {
+      const int tt = gch / (D::RS / 2), pch = gch % (D::RS / 2);
+      gout[gch] = srec[tt * (D::RS / 2) + rec_swz<NCL>(tt, pch)];
+    }
+    __syncthreads();
+    block_sum_sm<D::NPART, kChunk>(acc, sred);
+    if (t == 0) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { E[j] *= sr[j]; E[3 + j] *= sr[j]; }
-#pragma unroll
-    for (int a = 0; a < NCL; ++a) { const double s = ssc[a] * sw; F[a] *= s; F[NCL + a] *= s; }
-    // record -> shared memory in 16-byte chunks; XOR swizzle so that neither these stores nor the coalesced read-out conflict
-    double2 rc[D::RS / 2];
-    rc[0] = make_double2(r[0], r[1]);
-    rc[1] = make_double2(E[0], E[1]); rc[2] = make_double2(E[2], E[3]); rc[3] = make_double2(E[4], E[5]);
-#pragma unroll
-    for (int a = 0; a < NCL; ++a) rc[4 + a] = make_double2(F[2 * a], F[2 * a + 1]);  // F stored flat [2*NCL]
-#pragma unroll
-    for (int pch = 0; pch < D::RS / 2; ++pch) srec[threadIdx.x * (D::RS / 2) + rec_swz<NCL>(threadIdx.x, pch)] = rc[pch];
-    int k = 0;
-#pragma unroll
-    for (int a = 0; a < NCL; ++a)
-#pragma unroll
-      for (int b = a; b < NCL; ++b) acc[k++] = F[a] * F[b] + F[NCL + a] * F[NCL + b];
-#pragma unroll
-    for (int a = 0; a < NCL; ++a) acc[D::NU + a] = F[a] * r[0] + F[NCL + a] * r[1];
-    acc[D::NU + NCL] = 0.5 * (r[0] * r[0] + r[1] * r[1]);
-  }
-  __syncthreads();
-  // the chunk's records are contiguous in global memory: write them out as consecutive 16-byte chunks
-  double2* gout = reinterpret_cast<double2*>(rec + (size_t)begin * D::RS);
-  const int nch = cnt * (D::RS / 2);
-  for (int gch = threadIdx.x; gch < nch; gch += kChunk) {
-    const int t = gch / (D::RS / 2), pch = gch % (D::RS / 2);
-    gout[gch] = srec[t * (D::RS / 2) + rec_swz<NCL>(t, pch)];
-  }
-  __syncthreads();
-  block_sum_sm<D::NPART, kChunk>(acc, sred);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < D::NPART; ++i) part[(size_t)chunk * D::NPART + i] = acc[i];
+      for (int i = 0; i < D::NPART; ++i) part[(size_t)chunk * D::NPART + i] = acc[i];
+    }
+    uv_a = uv_b; uv_b = uv_c; p_b = p_c;
   }
 }
 
@@ -250,74 +289,111 @@ __global__ void k_track_factor(int P, const int* __restrict__ t_off, const doubl
   lt[0] = L[0]; lt[1] = L[1]; lt[2] = L[2]; lt[3] = L[3]; lt[4] = L[4]; lt[5] = L[5];
   lt[6] = empty ? 0.0 : t0; lt[7] = empty ? 0.0 : t1; lt[8] = empty ? 0.0 : t2; lt[9] = 0;
 }
-// per observation (one thread each; one CTA per chunk of one view, so records stream and the view's Schur terms reduce in
-// the CTA): What = (F^T E) L^-T, q = What t; chunk partials of sum What What^T (upper) and sum q for k_schur_diag
+// per observation (one thread each; a chunk of one view per step, so records stream and the view's Schur terms reduce in the
+// CTA): What = (F^T E) L^-T, q = What t; chunk partials of sum What What^T (upper) and sum q for k_schur_diag.
+//
+// Persistent CTAs over contiguous runs of chunks, as k_resjac.  The records of chunk k+1 stream into a second shared-memory
+// buffer with coalesced 16-byte cp.async (no register staging) while chunk k computes; the per-track Cholesky factors of
+// chunk k+1 are gathered into registers after the arithmetic of chunk k, so they fly during its write-out and reduction.
+#ifndef PTZ_OW_MINB
+#define PTZ_OW_MINB 4
+#endif
 template <int NCL>
-__global__ void __launch_bounds__(kChunk, 4) k_obs_what(const int* __restrict__ chunk_begin, const int* __restrict__ chunk_cnt, const int* __restrict__ o_track,
-                                                      const double* __restrict__ rec, const double* __restrict__ Lt, double* __restrict__ What,
-                                                      double* __restrict__ wpart) {
+struct ObsWhatSmem {
   typedef Dims<NCL> D;
-  constexpr int NV = D::NU + NCL, RC = D::RS / 2, WC = D::WS / 2;
-  constexpr int kStageBytes = kChunk * (RC + WC) * 16, kRedBytes = (NV * (kChunk + 4) + NV) * 8;
-  __shared__ __align__(16) unsigned char sbuf[kStageBytes > kRedBytes ? kStageBytes : kRedBytes];
-  double2* srec = reinterpret_cast<double2*>(sbuf);
-  double2* sw = srec + kChunk * RC;
-  double* sred = reinterpret_cast<double*>(sbuf);  // reused after the staged data has been written out
-  const int chunk = blockIdx.x, begin = chunk_begin[chunk], cnt = chunk_cnt[chunk];
-  // the chunk's records are contiguous: coalesced 16-byte loads into (swizzled) shared memory
-  const double2* gin = reinterpret_cast<const double2*>(rec + (size_t)begin * D::RS);
-  for (int gch = threadIdx.x; gch < cnt * RC; gch += kChunk) {
-    const int t = gch / RC, pch = gch % RC;
-    srec[t * RC + chunk_swz<RC>(t, pch)] = gin[gch];
-  }
-  // per-track factor: gather while the records land
+  static constexpr int NV = D::NU + NCL, RC = D::RS / 2, WC = D::WS / 2;
+  static constexpr int kRecBytes = kChunk * RC * 16, kWBytes = kChunk * WC * 16, kRedBytes = (NV * (kChunk + 4) + NV) * 8;
+  static constexpr int kBytes = 2 * kRecBytes + (kWBytes > kRedBytes ? kWBytes : kRedBytes);
+};
+template <int NCL>
+__global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, int per, const int* __restrict__ chunk_begin, const int* __restrict__ chunk_cnt,
+                                                                  const int* __restrict__ o_track, const double* __restrict__ rec,
+                                                                  const double* __restrict__ Lt, double* __restrict__ What, double* __restrict__ wpart) {
+  typedef Dims<NCL> D;
+  typedef ObsWhatSmem<NCL> SM;
+  constexpr int NV = SM::NV, RC = SM::RC, WC = SM::WC;
+  extern __shared__ __align__(16) unsigned char dsm[];
+  __shared__ int s_begin[kResjacMaxPer], s_cnt[kResjacMaxPer];
+  double2* sw = reinterpret_cast<double2*>(dsm + 2 * SM::kRecBytes);
+  double* sred = reinterpret_cast<double*>(dsm + 2 * SM::kRecBytes);  // reused after the staged What has been written out
+  const int t = threadIdx.x;
+  const int c0 = blockIdx.x * per, n = min(per, nchunks - c0);
+  if (n <= 0) return;
+  if (t < n) { s_begin[t] = chunk_begin[c0 + t]; s_cnt[t] = chunk_cnt[c0 + t]; }
+  __syncthreads();
+  auto stage_rec = [&](int k) {  // the chunk's records are contiguous: coalesced 16-byte copies into (swizzled) shared memory
+    double2* dst = reinterpret_cast<double2*>(dsm + (k & 1) * SM::kRecBytes);
+    const double2* gin = reinterpret_cast<const double2*>(rec + (size_t)s_begin[k] * D::RS);
+    const int nch = s_cnt[k] * RC;
+    for (int gch = t; gch < nch; gch += kChunk) {
+      const int tt = gch / RC, pch = gch % RC;
+      cp_async16(&dst[tt * RC + chunk_swz<RC>(tt, pch)], gin + gch);
+    }
+    cp_async_commit();
+  };
   double2 l01 = make_double2(1, 0), l23 = make_double2(1, 0), l45 = make_double2(0, 1), l67 = make_double2(0, 0), l89 = make_double2(0, 0);
-  if (threadIdx.x < cnt) {
-    const double2* lp = reinterpret_cast<const double2*>(Lt + (size_t)o_track[begin + threadIdx.x] * 10);
+  int p_b = -1, p_c = -1;
+  stage_rec(0);
+  if (t < s_cnt[0]) {
+    const double2* lp = reinterpret_cast<const double2*>(Lt + (size_t)o_track[s_begin[0] + t] * 10);
     l01 = lp[0]; l23 = lp[1]; l45 = lp[2]; l67 = lp[3]; l89 = lp[4];
   }
-  __syncthreads();
-  double acc[NV];
+  if (n > 1 && t < s_cnt[1]) p_b = o_track[s_begin[1] + t];
+  for (int k = 0; k < n; ++k) {
+    if (k + 1 < n) stage_rec(k + 1); else cp_async_commit();  // (an empty group keeps the wait below uniform)
+    cp_async_wait<1>();
+    __syncthreads();
+    const double2* srec = reinterpret_cast<const double2*>(dsm + (k & 1) * SM::kRecBytes);
+    const int chunk = c0 + k, begin = s_begin[k], cnt = s_cnt[k];
+    double acc[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-  if (threadIdx.x < cnt) {
-    const int t = threadIdx.x;
-    const double L1 = l01.y, L3 = l23.y, L4 = l45.x, t0 = l67.x, t1 = l67.y, t2 = l89.x;
-    const double i00 = 1.0 / l01.x, i11 = 1.0 / l23.x, i22 = 1.0 / l45.y;
-    const double2 e01 = srec[t * RC + chunk_swz<RC>(t, 1)], e23 = srec[t * RC + chunk_swz<RC>(t, 2)], e45 = srec[t * RC + chunk_swz<RC>(t, 3)];
-    const double a0 = e01.x, a1 = e01.y, a2 = e23.x, b0 = e23.y, b1 = e45.x, b2 = e45.y;
-    double Fv[2 * NCL];
+    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+    if (t < cnt) {
+      const double L1 = l01.y, L3 = l23.y, L4 = l45.x, t0 = l67.x, t1 = l67.y, t2 = l89.x;
+      const double i00 = 1.0 / l01.x, i11 = 1.0 / l23.x, i22 = 1.0 / l45.y;
+      const double2 e01 = srec[t * RC + chunk_swz<RC>(t, 1)], e23 = srec[t * RC + chunk_swz<RC>(t, 2)], e45 = srec[t * RC + chunk_swz<RC>(t, 3)];
+      const double a0 = e01.x, a1 = e01.y, a2 = e23.x, b0 = e23.y, b1 = e45.x, b2 = e45.y;
+      double Fv[2 * NCL];
 #pragma unroll
-    for (int a = 0; a < NCL; ++a) { const double2 f = srec[t * RC + chunk_swz<RC>(t, 4 + a)]; Fv[2 * a] = f.x; Fv[2 * a + 1] = f.y; }
-    double w[D::WS];
+      for (int a = 0; a < NCL; ++a) { const double2 f = srec[t * RC + chunk_swz<RC>(t, 4 + a)]; Fv[2 * a] = f.x; Fv[2 * a + 1] = f.y; }
+      double w[D::WS];
 #pragma unroll
-    for (int a = 0; a < NCL; ++a) {
-      const double f0 = Fv[a], f1 = Fv[NCL + a];
-      const double w0 = f0 * a0 + f1 * b0, w1 = f0 * a1 + f1 * b1, w2 = f0 * a2 + f1 * b2;  // row a of F^T E
-      const double x0 = w0 * i00, x1 = (w1 - L1 * x0) * i11, x2 = (w2 - L3 * x0 - L4 * x1) * i22;
-      w[3 * a] = x0; w[3 * a + 1] = x1; w[3 * a + 2] = x2;
-      acc[D::NU + a] = x0 * t0 + x1 * t1 + x2 * t2;  // q_a
+      for (int a = 0; a < NCL; ++a) {
+        const double f0 = Fv[a], f1 = Fv[NCL + a];
+        const double w0 = f0 * a0 + f1 * b0, w1 = f0 * a1 + f1 * b1, w2 = f0 * a2 + f1 * b2;  // row a of F^T E
+        const double x0 = w0 * i00, x1 = (w1 - L1 * x0) * i11, x2 = (w2 - L3 * x0 - L4 * x1) * i22;
+        w[3 * a] = x0; w[3 * a + 1] = x1; w[3 * a + 2] = x2;
+        acc[D::NU + a] = x0 * t0 + x1 * t1 + x2 * t2;  // q_a
+      }
+      if (D::WS > 3 * NCL) w[D::WS - 1] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < WC; ++kk) sw[t * WC + chunk_swz<WC>(t, kk)] = make_double2(w[2 * kk], w[2 * kk + 1]);
+      int kk = 0;
+#pragma unroll
+      for (int a = 0; a < NCL; ++a)
+#pragma unroll
+        for (int bb = a; bb < NCL; ++bb) acc[kk++] = w[3 * a] * w[3 * bb] + w[3 * a + 1] * w[3 * bb + 1] + w[3 * a + 2] * w[3 * bb + 2];
     }
-    if (D::WS > 3 * NCL) w[D::WS - 1] = 0.0;
+    // gathers for the next two chunks: in flight during the write-out and the reduction below
+    if (p_b >= 0) {
+      const double2* lp = reinterpret_cast<const double2*>(Lt + (size_t)p_b * 10);
+      l01 = lp[0]; l23 = lp[1]; l45 = lp[2]; l67 = lp[3]; l89 = lp[4];
+    }
+    p_c = -1;
+    if (k + 2 < n && t < s_cnt[k + 2]) p_c = o_track[s_begin[k + 2] + t];
+    __syncthreads();
+    double2* gout = reinterpret_cast<double2*>(What + (size_t)begin * D::WS);
+    for (int gch = t; gch < cnt * WC; gch += kChunk) {
+      const int tt = gch / WC, pch = gch % WC;
+      gout[gch] = sw[tt * WC + chunk_swz<WC>(tt, pch)];
+    }
+    __syncthreads();
+    block_sum_sm<NV, kChunk>(acc, sred);
+    if (t == 0) {
 #pragma unroll
-    for (int k = 0; k < WC; ++k) sw[t * WC + chunk_swz<WC>(t, k)] = make_double2(w[2 * k], w[2 * k + 1]);
-    int k = 0;
-#pragma unroll
-    for (int a = 0; a < NCL; ++a)
-#pragma unroll
-      for (int b = a; b < NCL; ++b) acc[k++] = w[3 * a] * w[3 * b] + w[3 * a + 1] * w[3 * b + 1] + w[3 * a + 2] * w[3 * b + 2];
-  }
-  __syncthreads();
-  double2* gout = reinterpret_cast<double2*>(What + (size_t)begin * D::WS);
-  for (int gch = threadIdx.x; gch < cnt * WC; gch += kChunk) {
-    const int t = gch / WC, pch = gch % WC;
-    gout[gch] = sw[t * WC + chunk_swz<WC>(t, pch)];
-  }
-  __syncthreads();
-  block_sum_sm<NV, kChunk>(acc, sred);
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) wpart[(size_t)chunk * NV + i] = acc[i];
+      for (int i = 0; i < NV; ++i) wpart[(size_t)chunk * NV + i] = acc[i];
+    }
+    p_b = p_c;
   }
 }
 

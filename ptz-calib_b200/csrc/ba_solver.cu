@@ -242,6 +242,7 @@ struct BaSolver : BaSolverBase {
   size_t sys_n = 0;
   double* h_scalars = nullptr;  // pinned
   int* h_info = nullptr;        // pinned: pcg info(2), fail(1)
+  int rj_per = 1, rj_grid = 1, ow_per = 1, ow_grid = 1;  // k_resjac / k_obs_what launch shapes (persistent CTAs)
   int nblk_ray = 0, nblk_cam = 0, cg_cap = 1, cg_wpb = 8, cg_grid = 1, cg_slots_per_rank = 1;
   size_t ar_partial = 0, ar_st0 = 0, ar_st1 = 0, ar_x = 0, ar_ll0 = 0, ar_ll1 = 0;  // arena offsets (bytes), identical on every rank
   int cgW = 1, cgR = 0, cg_vranks = 1;  // ranks sharing the rows of the CG, this rank; virtual ranks (debug: PTZ_CG_VRANKS)
@@ -557,6 +558,22 @@ struct BaSolver : BaSolverBase {
     // work buffers
     d_scale_cam.alloc((size_t)V * NCL, stream); d_scale_b.alloc(kMaxBorder, stream);
     d_rec.alloc((size_t)std::max(M, 1) * D::RS, stream);
+    {
+      // k_resjac runs persistent CTAs, one resident wave, each over a contiguous run of chunks (<= kResjacMaxPer of them)
+      int occ = 1;
+      PTZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resjac<TYPE>, kChunk, 0));
+      const int wave = std::max(1, num_sms * std::max(occ, 1));
+      rj_per = std::min(kResjacMaxPer, std::max(1, cdiv(ds.nchunks, wave)));
+      if (const char* e = getenv("PTZ_RJ_PER")) rj_per = std::min(kResjacMaxPer, std::max(1, atoi(e)));  // tuning hook
+      rj_grid = std::max(1, cdiv(ds.nchunks, rj_per));
+      // k_obs_what likewise (dynamic shared memory: two record buffers + staging)
+      PTZ_CUDA(cudaFuncSetAttribute(k_obs_what<NCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, ObsWhatSmem<NCL>::kBytes));
+      PTZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_obs_what<NCL>, kChunk, ObsWhatSmem<NCL>::kBytes));
+      const int wave2 = std::max(1, num_sms * std::max(occ, 1));
+      ow_per = std::min(kResjacMaxPer, std::max(1, cdiv(ds.nchunks, wave2)));
+      if (const char* e = getenv("PTZ_OW_PER")) ow_per = std::min(kResjacMaxPer, std::max(1, atoi(e)));
+      ow_grid = std::max(1, cdiv(ds.nchunks, ow_per));
+    }
     d_part.alloc((size_t)std::max(ds.nchunks, 1) * D::NPART, stream);
     viewred_n = (size_t)V * NCL * NCL + (size_t)V * NCL + V + (size_t)ncpl * NCL * nb + (size_t)nb * nb + nb + 2;
     d_viewred.alloc(viewred_n, stream);
@@ -617,7 +634,7 @@ struct BaSolver : BaSolverBase {
     PTZ_TIMED(PTZ_K_VIEW_PREP, k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[cur].p, d_ext[cur].p, d_vt.p, 1));
     if (nb > 0) PTZ_CUDA(cudaMemsetAsync(p_C, 0, (viewred_n - (size_t)(p_C - d_viewred.p)) * sizeof(double), s));  // C | Hbb | gb | cost_pts accumulate
     if (ds.nchunks > 0)
-      PTZ_TIMED(PTZ_K_RESJAC, k_resjac<TYPE><<<ds.nchunks, kChunk, 0, s>>>(ds.chunk_view.p, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_uv.p, ds.o_track.p, d_vt.p,
+      PTZ_TIMED(PTZ_K_RESJAC, k_resjac<TYPE><<<rj_grid, kChunk, 0, s>>>(ds.nchunks, rj_per, ds.chunk_view.p, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_uv.p, ds.o_track.p, d_vt.p,
                                                                              d_trk[cur].p, d_scale_cam.p, d_dispp[cur].p, weighted, d_rec.p, d_part.p,
                                                                              d_recd.p, d_scale_b.p + (kDisp ? bo_disp : 0)));
     PTZ_TIMED(PTZ_K_VIEW_FINALIZE,
@@ -696,7 +713,9 @@ struct BaSolver : BaSolverBase {
     if (P > 0)
       PTZ_TIMED(PTZ_K_TRACK_SOLVE, {
         k_track_factor<<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, d_Vh.p, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_ray.p, d_Lt.p, d_fail.p);
-        if (ds.nchunks > 0) k_obs_what<NCL><<<ds.nchunks, kChunk, 0, s>>>(ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_track.p, d_rec.p, d_Lt.p, d_What.p, d_q.p);
+        if (ds.nchunks > 0)
+          k_obs_what<NCL><<<ow_grid, kChunk, ObsWhatSmem<NCL>::kBytes, s>>>(ds.nchunks, ow_per, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_track.p, d_rec.p, d_Lt.p,
+                                                                          d_What.p, d_q.p);
         if (kDisp) k_disp_track<NCL><<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_rec.p, d_recd.p, d_Lt.p, d_Wdh.p);
       });
     PTZ_TIMED(PTZ_K_SCHUR_DIAG, k_schur_diag<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, ds.view_chunk_off.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal,

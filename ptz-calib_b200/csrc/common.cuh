@@ -181,6 +181,19 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* sm) {
   }
   __syncthreads();
 }
+// Ampere-style asynchronous copies global -> shared (LDGSTS): no register staging, completion tracked per thread in groups
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {  // 16 bytes, L2 only (streamed / gathered once)
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 // block-wide sum of NV values per thread through shared memory (NT threads): NV stores, NT/8 loads per partial and 3 shuffle
 // steps instead of 10 shuffles per value.  Result valid in thread 0.  sm must hold NV*(NT+4)+NV doubles.  Fixed order.
 template <int NV, int NT>

@@ -9,8 +9,8 @@
 // A caller of the reference switches by including this header instead of ptzray_optimizer.h / krt_optimizer.h and
 // linking libptzcalib_b200.so; all numerics run on the GPU behind ptzba_solve / ptzreloc_solve_batch.
 //
-// Deviation: PTZRayOptimizer::SetInitTransLocalToWorld uses cv::solvePnP(EPNP) in the reference (.cc:562-633); here the
-// caller supplies the initial T_l_w with SetInitTransLocalToWorld(const double[6]) (not built).
+// PTZRayOptimizer::SetInitTransLocalToWorld (.cc:562-633) runs on the host as in the reference; its cv::solvePnP(EPNP) is restated in
+// ptzcalib_epnp.hpp.  SetInitTransLocalToWorld(const double[6]) is an extra overload for callers that already know T_l_w.
 #ifndef PTZCALIB_B200_HPP
 #define PTZCALIB_B200_HPP
 
@@ -29,6 +29,7 @@
 
 #include "../ptz-calib_b200/csrc/ptz_math.cuh"  // rodrigues_jac / rodrigues_inv / mul33 (plain C++ when not compiled by nvcc)
 #include "ptzcalib_b200.h"
+#include "ptzcalib_epnp.hpp"
 
 namespace ptzcalib {
 
@@ -182,6 +183,7 @@ class PTZRayOptimizer {
   bool Solve(std::vector<Camera>& cameras, std::vector<std::vector<Ray>>& rays) {
     if (!CheckValid()) return false;
     if (!FindTracks()) return false;
+    if (!tlw_given_) SetInitTransLocalToWorld();
     // candidate views get dense ids in ascending image id; one row per (track, candidate view): AddConstraints2d2d, .cc:799-848,
     // flattened on the device by ptztracks_flatten
     std::vector<long> view_of;
@@ -258,12 +260,61 @@ class PTZRayOptimizer {
     if (shared_ic_ids.size() != cameras_.size()) return;  // .cc:499-502
     shared_ic_ids_ = shared_ic_ids;
   }
-  void SetInitTransLocalToWorld(const double tlw[6]) { tlw_param_.assign(tlw, tlw + 6); }  // see the header comment
+  void SetInitTransLocalToWorld(const double tlw[6]) { tlw_param_.assign(tlw, tlw + 6); tlw_given_ = true; }  // see the header comment
+  // .cc:562-633: T_l_w from EPnP on the first annotated candidate view that passes the gates; zeros and false when none does
+  bool SetInitTransLocalToWorld() {
+    for (size_t i = 0; i < num_cams_; ++i) {
+      if (!isCandidate((long)i) || pixels_.empty() || pixels_[i].empty()) continue;
+      const size_t n = pts3d_[i].size();
+      std::vector<double> obj(3 * n);
+      std::vector<float> pix(2 * n);
+      for (size_t j = 0; j < n; ++j) {
+        obj[3 * j] = pts3d_[i][j].x; obj[3 * j + 1] = pts3d_[i][j].y; obj[3 * j + 2] = pts3d_[i][j].z;
+        pix[2 * j] = pixels_[i][j].x; pix[2 * j + 1] = pixels_[i][j].y;
+      }
+      Mat33 R;
+      Vec3 tv;
+      if (!epnp::solve_pnp_epnp((int)n, obj.data(), pix.data(), cameras_[i].K().data(), cameras_[i].dist().data(), R.data(), tv.data())) continue;
+      // cv::Rodrigues(rvec, R) of the rvec solvePnP returns: the round trip re-orthonormalises R
+      Vec3 rv;
+      ptz::rodrigues_inv(R.data(), rv.data());
+      ptz::rodrigues_jac(rv.data(), R.data(), nullptr);
+      const double z0 = R[6] * obj[0] + R[7] * obj[1] + R[8] * obj[2] + tv[2];
+      const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+      if (z0 < 0 || det < 0.0) continue;  // .cc:582-587
+      // reprojection RMS of the float32 points without distortion (.cc:589-604)
+      const Mat33& K = cameras_[i].K();
+      double sq = 0;
+      for (size_t j = 0; j < n; ++j) {
+        const double X = (float)obj[3 * j], Y = (float)obj[3 * j + 1], Z = (float)obj[3 * j + 2];
+        const double xc = R[0] * X + R[1] * Y + R[2] * Z + tv[0], yc = R[3] * X + R[4] * Y + R[5] * Z + tv[1], zc = R[6] * X + R[7] * Y + R[8] * Z + tv[2];
+        const float pu = (float)(K[0] * (xc / zc) + K[2]), pv = (float)(K[4] * (yc / zc) + K[5]);
+        sq += (double)(pu - pix[2 * j]) * (pu - pix[2 * j]) + (double)(pv - pix[2 * j + 1]) * (pv - pix[2 * j + 1]);
+      }
+      if (std::sqrt(sq / n) > 300) continue;
+      // T_l_w = T_i_l^-1 T_i_w with T_i_l = [R_i | t_i] of the view (.cc:606-616): R_lw = R_i^T R, t_lw = R_i^T (t - t_i)
+      const Mat33& Ri = cameras_[i].R();
+      const Vec3& ti = cameras_[i].t();
+      Mat33 Rlw;
+      Vec3 tlw;
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) Rlw[3 * r + c] = Ri[r] * R[c] + Ri[3 + r] * R[3 + c] + Ri[6 + r] * R[6 + c];
+        tlw[r] = Ri[r] * (tv[0] - ti[0]) + Ri[3 + r] * (tv[1] - ti[1]) + Ri[6 + r] * (tv[2] - ti[2]);
+      }
+      Vec3 rlw;
+      ptz::rodrigues_inv(Rlw.data(), rlw.data());
+      tlw_param_ = {rlw[0], rlw[1], rlw[2], tlw[0], tlw[1], tlw[2]};
+      return true;
+    }
+    tlw_param_.assign(6, 0.0);
+    return false;
+  }
   static void T_l_w(const double* tlw, Mat33& R_l_w, Vec3& t_l_w) {                         // .cc:507-513
     ptz::rodrigues_jac(tlw, R_l_w.data(), nullptr);
     t_l_w = Vec3{{tlw[3], tlw[4], tlw[5]}};
   }
   const Tracks& tracks() const { return tracks_; }
+  const std::vector<double>& tlw_init() const { return tlw_param_; }  // T_l_w the solve started from
   int num_iterations() const { return num_iterations_; }
   int last_status() const { return last_status_; }
 
@@ -321,6 +372,7 @@ class PTZRayOptimizer {
   std::vector<long> shared_ic_ids_;
   FACTOR_TYPE type_;
   std::vector<double> tlw_param_ = std::vector<double>(6, 0.0);
+  bool tlw_given_ = false;
   Tracks tracks_;
   std::vector<int32_t> flat_id_, flat_img_, flat_feat_;  // tracks_ as ptztracks_result arrays
   std::vector<int64_t> flat_off_;

@@ -423,7 +423,36 @@ def make_lm_kat(seed=99):
     np.savez_compressed(os.path.join(HERE, "lm_kat.npz"), **out)
 
 
+def make_epnp_kat(seed=31, cases=48):
+    """cv2.solvePnP(SOLVEPNP_EPNP) on random non-planar point sets (double object points, float32 pixels as the reference's
+    cv::Point2f): the first half exact projections (EPnP is then independent of the SVD's sign conventions), the second half with
+    0.5 px noise.  Flat layout: n[c], K[c,9], dist[c,5], obj/pix concatenated with offsets, R[c,9], t[c,3], gt_R, gt_t."""
+    rng = np.random.default_rng(seed)
+    ns, Ks, ds, objs, pixs, Rs, ts, gR, gt, noise = [], [], [], [], [], [], [], [], [], []
+    for c in range(cases):
+        n = int(rng.integers(5, 40))
+        rvec = rng.normal(0, 0.8, 3)
+        R, _ = cv2.Rodrigues(rvec)
+        t = np.array([rng.normal(0, 2), rng.normal(0, 2), rng.uniform(20, 60)])
+        f = rng.uniform(1000, 3000)
+        K = np.array([[f, 0, 960], [0, f * rng.uniform(0.95, 1.05), 540], [0, 0, 1.0]])
+        dist = np.array([rng.normal(0, 0.05), rng.normal(0, 0.01), 0, 0, 0]) if c % 2 else np.zeros(5)
+        obj = rng.uniform(-10, 10, (n, 3))
+        sig = 0.0 if c < cases // 2 else 0.5
+        pix, _ = cv2.projectPoints(obj, rvec, t, K, dist)
+        pix = (pix.reshape(-1, 2) + rng.normal(0, sig, (n, 2))).astype(np.float32)
+        ok, rv, tv = cv2.solvePnP(obj, pix, K, dist, flags=cv2.SOLVEPNP_EPNP)
+        assert ok
+        Rcv, _ = cv2.Rodrigues(rv)
+        ns.append(n); Ks.append(K.ravel()); ds.append(dist); objs.append(obj); pixs.append(pix); Rs.append(Rcv.ravel()); ts.append(tv.ravel())
+        gR.append(R.ravel()); gt.append(t); noise.append(sig)
+    np.savez_compressed(os.path.join(HERE, "epnp_kat.npz"), n=np.array(ns, np.int32), K=np.array(Ks), dist=np.array(ds), obj=np.concatenate(objs),
+                        pix=np.concatenate(pixs), R=np.array(Rs), t=np.array(ts), gt_R=np.array(gR), gt_t=np.array(gt), noise=np.array(noise),
+                        cv2_version=np.array(cv2.__version__))
+
+
 if __name__ == "__main__":
+    make_epnp_kat()
     make_opencv_kat()
     make_functor_kat()
     make_lm_kat()

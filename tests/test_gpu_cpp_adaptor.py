@@ -25,6 +25,7 @@ def test_adaptor_compiles_without_gpu(tmp_path):
     """CPU: the adaptor header is valid C++17 against the C ABI and links to the library."""
     assert os.path.exists(build_exe(tmp_path))
     assert os.path.exists(build_exe(tmp_path, "iba_check"))
+    assert os.path.exists(build_exe(tmp_path, "georef_check"))
 
 
 @pytest.mark.gpu
@@ -106,3 +107,40 @@ def test_incremental_driver_registers_the_whole_scene(tmp_path, orc, both_direct
         rel_gt = gt["R"][b] @ gt["R"][a].T
         ang = np.arccos(np.clip((np.trace(rel_est @ rel_gt.T) - 1) / 2, -1, 1))
         assert ang < 2e-3, (a, b, ang)
+
+
+@pytest.mark.gpu
+def test_georeferencing_with_epnp_initialisation(tmp_path, orc):
+    """run_ptz_ba.cc:142-145: BA with annotated 2d-3d points; T_l_w comes from EPnP on the first annotated view inside Solve
+    (ptzray_optimizer.cc:562-633), the georeferencing BA refines it.  The EPnP start must sit at the ground truth up to the view's
+    own initial error, and the solve must end where the Python path ends when it is handed the same start."""
+    exe = build_exe(tmp_path, "georef_check")
+    p = synth.make_config(1, scale=0.5, num_pts3d=18, pts3d_views=3)
+    cams = np.zeros((p.V, 21))
+    for i in range(p.V):
+        cams[i, :4] = p.intr[i, :4]
+        cams[i, 4:13] = orc.rodrigues(p.ext[i, :3]).ravel()
+        cams[i, 13:16] = p.ext[i, 3:]
+        cams[i, 16:21] = p.intr[i, 4:9]
+    fin, fout = str(tmp_path / "g_in.bin"), str(tmp_path / "g_out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("5i", p.V, p.M, p.A, p.factor_type, 200))
+        for a in (cams, p.obs_view, p.obs_track, p.obs_uv, p.pt_view, p.pt_uv, p.pt_xyz):
+            f.write(np.ascontiguousarray(a).tobytes())
+    r = subprocess.run([exe, fin, fout], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = np.fromfile(fout, dtype=np.float64)
+    head, cw = out[:12], out[12:].reshape(p.V, 21)
+    assert head[0] == 1.0, r.stdout
+    tlw0, gt = head[6:12], p.gt["tlw"]
+    # rotation within ~2 degrees (0.5 deg initial error per axis of the view + focal error), translation within a few % of the range
+    assert np.abs(tlw0[:3] - gt[:3]).max() < 0.05, (tlw0, gt)
+    assert np.abs(tlw0[3:] - gt[3:]).max() < 0.1 * np.linalg.norm(gt[3:]) + 3.0, (tlw0, gt)
+    assert head[4] < 2.0  # final 2d-3d reprojection RMS [px]
+    q = synth.make_config(1, scale=0.5, num_pts3d=18, pts3d_views=3)
+    q.tlw0 = tlw0.copy()
+    want = ptz.ba_solve(q, max_num_iterations=200)
+    assert want.converged and int(head[1]) == want.num_iterations
+    assert abs(head[2] - want.final_reproj_error_all) <= 1e-7 * want.final_reproj_error_all
+    assert abs(head[4] - want.final_reproj_error_2d3d) <= 1e-6 * max(want.final_reproj_error_2d3d, 1e-3)
+    assert np.abs(cw - want.cams_world).max() <= 1e-5

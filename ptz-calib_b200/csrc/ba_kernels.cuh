@@ -438,8 +438,11 @@ __global__ void k_schur_diag(int V, const int* __restrict__ view_chunk_off, cons
 }
 
 // per upper off-diagonal block (one warp): S_rc = - sum over observation pairs What_o What_o'^T ; also writes S_cr = S_rc^T
+#ifndef PTZ_OD_MINB
+#define PTZ_OD_MINB 1
+#endif
 template <int NCL>
-__global__ void __launch_bounds__(256) k_schur_offdiag(int nub, const int64_t* __restrict__ pair_off, const int* __restrict__ pair_a,
+__global__ void __launch_bounds__(256, PTZ_OD_MINB) k_schur_offdiag(int nub, const int64_t* __restrict__ pair_off, const int* __restrict__ pair_a,
                                                        const int* __restrict__ pair_b, const double* __restrict__ What, const int* __restrict__ ub_pos,
                                                        const int* __restrict__ ub_pos_t, double* __restrict__ Sval) {
   typedef Dims<NCL> D;
@@ -449,9 +452,15 @@ __global__ void __launch_bounds__(256) k_schur_offdiag(int nub, const int64_t* _
   double acc[NCL * NCL];
 #pragma unroll
   for (int i = 0; i < NCL * NCL; ++i) acc[i] = 0.0;
-  for (int64_t k = pair_off[b] + lane; k < pair_off[b + 1]; k += 32) {
-    const double2* wa = reinterpret_cast<const double2*>(What + (size_t)pair_a[k] * D::WS);
-    const double2* wb = reinterpret_cast<const double2*>(What + (size_t)pair_b[k] * D::WS);
+  // the pair indices of the next round are fetched before the gathers of this one: one dependent latency less per round
+  const int64_t ke = pair_off[b + 1];
+  int64_t k = pair_off[b] + lane;
+  int ia = 0, ib = 0;
+  if (k < ke) { ia = pair_a[k]; ib = pair_b[k]; }
+  for (; k < ke; k += 32) {
+    const double2* wa = reinterpret_cast<const double2*>(What + (size_t)ia * D::WS);
+    const double2* wb = reinterpret_cast<const double2*>(What + (size_t)ib * D::WS);
+    if (k + 32 < ke) { ia = pair_a[k + 32]; ib = pair_b[k + 32]; }
     double x[D::WS], y[D::WS];
 #pragma unroll
     for (int i = 0; i < D::WS / 2; ++i) { const double2 t = wa[i]; x[2 * i] = t.x; x[2 * i + 1] = t.y; }

@@ -151,6 +151,43 @@ enum Slot {
   S_COUNT = 32
 };
 
+// Process-wide free lists of CUDA events and small pinned host blocks.  The many short-lived solver objects of one IBA run (and
+// bench.py's end-to-end leg) would otherwise call cudaEventCreate / cudaMallocHost / cudaFreeHost per solve: driver-lock calls that
+// were seen to stall for tens of milliseconds now and then (e.g. while nvidia-smi polls the device).
+struct HostCache {
+  static std::mutex& lock() { static std::mutex m; return m; }
+  static std::vector<cudaEvent_t>& events() { static std::vector<cudaEvent_t> v; return v; }
+  static std::vector<void*>& pinned() { static std::vector<void*> v; return v; }
+  static constexpr size_t kPinnedBytes = 512;
+  static cudaEvent_t get_event() {
+    {
+      std::lock_guard<std::mutex> g(lock());
+      if (!events().empty()) { cudaEvent_t e = events().back(); events().pop_back(); return e; }
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  static void put_events(const std::vector<cudaEvent_t>& ev) {
+    std::lock_guard<std::mutex> g(lock());
+    events().insert(events().end(), ev.begin(), ev.end());
+  }
+  static void* get_pinned() {
+    {
+      std::lock_guard<std::mutex> g(lock());
+      if (!pinned().empty()) { void* p = pinned().back(); pinned().pop_back(); return p; }
+    }
+    void* p = nullptr;
+    PTZ_CUDA(cudaMallocHost(&p, kPinnedBytes));
+    return p;
+  }
+  static void put_pinned(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(lock());
+    pinned().push_back(p);
+  }
+};
+
 struct StageClock {
   std::vector<cudaEvent_t> ev;
   std::vector<int> tag;  // kernel id of interval [2i, 2i+1]; -1 = a whole ptzba_run
@@ -162,7 +199,7 @@ struct StageClock {
   void init(cudaStream_t s) { stream = s; }
   void begin(int id) {
     if (used + 2 > ev.size()) {
-      for (int i = 0; i < 256; ++i) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+      for (int i = 0; i < 256; ++i) ev.push_back(HostCache::get_event());
     }
     cudaEventRecord(ev[used], stream);
     tag.push_back(id);
@@ -179,7 +216,7 @@ struct StageClock {
     tag.clear();
   }
   void reset() { collect(); for (int i = 0; i < PTZ_K_COUNT; ++i) { ms[i] = 0; launches[i] = 0; } ms_run = 0; }
-  ~StageClock() { for (auto e : ev) cudaEventDestroy(e); }
+  ~StageClock() { HostCache::put_events(ev); }  // (the owning solver synchronised its stream before this runs)
 };
 // time one kernel launch (or one collective) under its id
 #define PTZ_TIMED(id, ...) do { clk.begin(id); __VA_ARGS__; clk.end(); ++clk.launches[id]; } while (0)
@@ -458,8 +495,9 @@ struct BaSolver : BaSolverBase {
   }
 
   ~BaSolver() {
-    if (h_scalars) cudaFreeHost(h_scalars);
-    if (h_info) cudaFreeHost(h_info);
+    cudaStreamSynchronize(stream);
+    HostCache::put_pinned(h_scalars);
+    HostCache::put_pinned(h_info);
   }
 
   // every rank must hold the same block pattern of S: all-gather the local upper block keys, return their sorted union
@@ -603,8 +641,9 @@ struct BaSolver : BaSolverBase {
     d_cost_part.alloc(2 * (size_t)std::max(ds.nchunks, 1), stream); d_cost_part.zero(s);
     d_scalars.alloc(S_COUNT, stream); d_scalars.zero(s);
 
-    PTZ_CUDA(cudaMallocHost((void**)&h_scalars, S_COUNT * sizeof(double)));
-    PTZ_CUDA(cudaMallocHost((void**)&h_info, 4 * sizeof(int)));
+    static_assert(S_COUNT * sizeof(double) <= HostCache::kPinnedBytes, "pinned scratch block too small");
+    h_scalars = reinterpret_cast<double*>(HostCache::get_pinned());
+    h_info = reinterpret_cast<int*>(HostCache::get_pinned());
     reset();
   }
 

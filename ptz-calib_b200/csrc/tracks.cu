@@ -5,7 +5,7 @@
 // loop of AddConstraints2d2d (ptzray_optimizer.cc:801-848) that turns tracks into (uv, view, ray) rows.  SURVEY.md §8f row 1.
 //
 // Device algorithm (integer work, HBM/L2-bound; every step is a radix sort, a scan or a one-thread-per-item kernel):
-//   1. every match contributes two endpoint keys (image << 32 | feature); sort them carrying the endpoint number
+//   1. every match contributes two endpoint keys (image << fbits | feature, packed to the bits in use); sort them carrying the endpoint number
 //   2. heads of equal-key runs -> inclusive scan = flat node index of every endpoint.  Because the keys are sorted this IS
 //      the index the reference's flat_pair_map assigns (tracks.cc:35-43 iterates a std::set of pairs, i.e. ascending)
 //   3. lock-free union-find over the matches: roots are hooked larger-under-smaller with atomicCAS, so the final root of a
@@ -56,28 +56,41 @@ static inline unsigned grid_for(long long n, int b) { return (unsigned)std::max<
 static inline int bits_for(long long n) { int b = 1; while ((1ll << b) < n) ++b; return b; }
 
 // ---- 1. endpoint keys.  Endpoint e = 2*match + side.  The pair of a match: largest k with match_offset[k] <= match.
-__global__ void k_endpoint_keys(long long N, int npairs, const int* __restrict__ pair_src, const int* __restrict__ pair_dst,
-                                const long long* __restrict__ match_offset, const int* __restrict__ query_idx, const int* __restrict__ train_idx,
-                                unsigned long long* __restrict__ key, int* __restrict__ val, unsigned int* __restrict__ maxbits, int* __restrict__ bad) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned int hi = 0;
-  if (e < 2 * N) {
-    const long long m = e >> 1;
-    int lo = 0, up = npairs;  // invariant: match_offset[lo] <= m < match_offset[up]
-    while (up - lo > 1) {
-      const int mid = (lo + up) >> 1;
-      if (match_offset[mid] <= m) lo = mid; else up = mid;
-    }
-    const int img = (e & 1) ? pair_dst[lo] : pair_src[lo];
-    const int feat = (e & 1) ? train_idx[m] : query_idx[m];
-    if (img < 0 || feat < 0) *bad = 1;
-    key[e] = ((unsigned long long)(unsigned int)img << 32) | (unsigned int)feat;
-    val[e] = (int)e;
-    hi = (unsigned int)img;
+// Keys are packed as image << fbits | feature with fbits = bits of the largest feature index, so that the radix sort only
+// walks the bits in use (a 1000-image, 2000-keypoint problem sorts 21 bits instead of 42).
+__global__ void k_index_ranges(long long N, int npairs, const int* __restrict__ pair_src, const int* __restrict__ pair_dst, const int* __restrict__ query_idx,
+                               const int* __restrict__ train_idx, unsigned int* __restrict__ maxv /* [0] image, [1] feature */, int* __restrict__ bad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int f = 0, g = 0;
+  if (i < N) { const int q = query_idx[i], t = train_idx[i]; if (q < 0 || t < 0) *bad = 1; f = max(max(q, t), 0); }
+  if (i < npairs) { const int a = pair_src[i], c = pair_dst[i]; if (a < 0 || c < 0) *bad = 1; g = max(max(a, c), 0); }
+  const unsigned int fm = __reduce_max_sync(0xffffffffu, (unsigned int)f), gm = __reduce_max_sync(0xffffffffu, (unsigned int)g);
+  if ((threadIdx.x & 31) == 0) { if (fm) atomicMax(maxv + 1, fm); if (gm) atomicMax(maxv, gm); }
+}
+__device__ __forceinline__ int pair_of(const long long* __restrict__ match_offset, int npairs, long long m) {
+  int lo = 0, up = npairs;  // invariant: match_offset[lo] <= m < match_offset[up]
+  while (up - lo > 1) {
+    const int mid = (lo + up) >> 1;
+    if (match_offset[mid] <= m) lo = mid; else up = mid;
   }
-  // largest image index: bounds the radix-sort passes
-  hi = __reduce_max_sync(0xffffffffu, hi);
-  if ((threadIdx.x & 31) == 0 && hi) atomicMax(maxbits, hi);
+  return lo;
+}
+__global__ void k_endpoint_keys(long long N, int npairs, int fbits, const int* __restrict__ pair_src, const int* __restrict__ pair_dst,
+                                const long long* __restrict__ match_offset, const int* __restrict__ query_idx, const int* __restrict__ train_idx,
+                                unsigned long long* __restrict__ key, int* __restrict__ val) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long mc = m < N ? m : N - 1;
+  // consecutive matches mostly belong to the same image pair: the first and last lane search, the others only if those differ
+  const int lane = threadIdx.x & 31;
+  int pr = (lane == 0 || lane == 31) ? pair_of(match_offset, npairs, mc) : 0;
+  const int p0 = __shfl_sync(0xffffffffu, pr, 0), p1 = __shfl_sync(0xffffffffu, pr, 31);
+  if (p0 == p1) pr = p0;
+  else if (lane != 0 && lane != 31) pr = pair_of(match_offset, npairs, mc);
+  if (m >= N) return;
+  const unsigned long long a = ((unsigned long long)(unsigned int)pair_src[pr] << fbits) | (unsigned int)query_idx[m];
+  const unsigned long long c = ((unsigned long long)(unsigned int)pair_dst[pr] << fbits) | (unsigned int)train_idx[m];
+  reinterpret_cast<ulonglong2*>(key)[m] = make_ulonglong2(a, c);
+  reinterpret_cast<int2*>(val)[m] = make_int2((int)(2 * m), (int)(2 * m + 1));
 }
 
 // ---- 2. run heads of the sorted keys
@@ -125,13 +138,13 @@ __global__ void k_compress(int n, int* parent, int* __restrict__ root) {
 }
 
 // ---- 5. runs of equal root (nodes stably sorted by root): heads, image listed twice
-__global__ void k_run_heads(int K, const int* __restrict__ sroot, const int* __restrict__ snode, const unsigned long long* __restrict__ node_key,
+__global__ void k_run_heads(int K, int fbits, const int* __restrict__ sroot, const int* __restrict__ snode, const unsigned long long* __restrict__ node_key,
                             int* __restrict__ head, int* __restrict__ twice /* [K] by root, zeroed */) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K) return;
   const bool h = (i == 0 || sroot[i] != sroot[i - 1]);
   head[i] = h ? 1 : 0;
-  if (!h && (node_key[snode[i]] >> 32) == (node_key[snode[i - 1]] >> 32)) twice[sroot[i]] = 1;  // every writer stores the same value
+  if (!h && (node_key[snode[i]] >> fbits) == (node_key[snode[i - 1]] >> fbits)) twice[sroot[i]] = 1;  // every writer stores the same value
 }
 __global__ void k_run_starts(int K, const int* __restrict__ head, const int* __restrict__ incl, int* __restrict__ run_start) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -148,7 +161,7 @@ __global__ void k_run_valid(int C, int K, int min_len, const int* __restrict__ r
   valid[c] = ok ? 1 : 0;
   vlen[c] = ok ? len : 0;
 }
-__global__ void k_emit(int K, int C, const int* __restrict__ incl, const int* __restrict__ run_start, const int* __restrict__ valid,
+__global__ void k_emit(int K, int C, int fbits, const int* __restrict__ incl, const int* __restrict__ run_start, const int* __restrict__ valid,
                        const int* __restrict__ trank, const long long* __restrict__ eoff, const int* __restrict__ sroot, const int* __restrict__ snode,
                        const unsigned long long* __restrict__ node_key, long long cap_tracks, long long cap_elems, int* __restrict__ track_id,
                        long long* __restrict__ track_offset, int* __restrict__ elem_img, int* __restrict__ elem_feat) {
@@ -160,8 +173,8 @@ __global__ void k_emit(int K, int C, const int* __restrict__ incl, const int* __
   const long long pos = eoff[c] + (i - b);
   if (pos < cap_elems) {
     const unsigned long long k = node_key[snode[i]];
-    elem_img[pos] = (int)(k >> 32);
-    elem_feat[pos] = (int)(k & 0xffffffffull);
+    elem_img[pos] = (int)(k >> fbits);
+    elem_feat[pos] = (int)(k & ((1ull << fbits) - 1ull));
   }
   if (i == b && trank[c] < cap_tracks) { track_id[trank[c]] = sroot[i]; track_offset[trank[c]] = eoff[c]; }
 }
@@ -194,16 +207,18 @@ static DevCounts build_device(long long N, int npairs, const int* pair_src, cons
   const long long E = 2 * N;
   DevBuf<unsigned long long> key0, key1, node_key;
   DevBuf<int> val0, val1, head, incl, endpoint_node, d_bad;
-  DevBuf<unsigned int> d_maximg;
+  DevBuf<unsigned int> d_max;
   key0.alloc(E, s); key1.alloc(E, s); val0.alloc(E, s); val1.alloc(E, s); head.alloc(E, s); incl.alloc(E, s); endpoint_node.alloc(E, s);
-  d_bad.alloc(1, s); d_bad.zero(s); d_maximg.alloc(1, s); d_maximg.zero(s);
-  k_endpoint_keys<<<grid_for(E, 256), 256, 0, s>>>(N, npairs, pair_src, pair_dst, match_offset, query_idx, train_idx, key0.p, val0.p, d_maximg.p, d_bad.p);
-  unsigned int h_maximg = 0;
-  PTZ_CUDA(cudaMemcpyAsync(&h_maximg, d_maximg.p, 4, cudaMemcpyDeviceToHost, s));
+  d_bad.alloc(1, s); d_bad.zero(s); d_max.alloc(2, s); d_max.zero(s);
+  k_index_ranges<<<grid_for(std::max<long long>(N, npairs), 256), 256, 0, s>>>(N, npairs, pair_src, pair_dst, query_idx, train_idx, d_max.p, d_bad.p);
+  unsigned int h_max[2] = {0, 0};
+  PTZ_CUDA(cudaMemcpyAsync(h_max, d_max.p, 8, cudaMemcpyDeviceToHost, s));
   PTZ_CUDA(cudaMemcpyAsync(&out.bad, d_bad.p, 4, cudaMemcpyDeviceToHost, s));
   PTZ_CUDA(cudaStreamSynchronize(s));
   if (out.bad) return out;
-  sort_pairs(tmp, key0.p, key1.p, val0.p, val1.p, E, 32 + bits_for((long long)h_maximg + 1), s);
+  const int fbits = bits_for((long long)h_max[1] + 1), ibits = bits_for((long long)h_max[0] + 1);
+  k_endpoint_keys<<<grid_for(N, 256), 256, 0, s>>>(N, npairs, fbits, pair_src, pair_dst, match_offset, query_idx, train_idx, key0.p, val0.p);
+  sort_pairs(tmp, key0.p, key1.p, val0.p, val1.p, E, fbits + ibits, s);
   k_key_heads<<<grid_for(E, 256), 256, 0, s>>>(E, key1.p, head.p);
   inclusive_scan(tmp, head.p, incl.p, E, s);
   int K = 0;
@@ -223,7 +238,7 @@ static DevCounts build_device(long long N, int npairs, const int* pair_src, cons
   // components as runs
   sort_pairs(tmp, root.p, sroot.p, ids.p, snode.p, K, bits_for(K), s);
   twice.zero(s);
-  k_run_heads<<<grid_for(K, 256), 256, 0, s>>>(K, sroot.p, snode.p, node_key.p, head.p, twice.p);
+  k_run_heads<<<grid_for(K, 256), 256, 0, s>>>(K, fbits, sroot.p, snode.p, node_key.p, head.p, twice.p);
   inclusive_scan(tmp, head.p, incl.p, K, s);
   int Cn = 0;
   PTZ_CUDA(cudaMemcpyAsync(&Cn, incl.p + (K - 1), 4, cudaMemcpyDeviceToHost, s));
@@ -233,7 +248,7 @@ static DevCounts build_device(long long N, int npairs, const int* pair_src, cons
   k_run_valid<<<grid_for(Cn, 256), 256, 0, s>>>(Cn, K, min_len, run_start.p, sroot.p, twice.p, valid.p, vlen.p);
   exclusive_scan(tmp, valid.p, trank.p, Cn, s);
   exclusive_scan(tmp, vlen.p, eoff.p, Cn, s);
-  k_emit<<<grid_for(K, 256), 256, 0, s>>>(K, Cn, incl.p, run_start.p, valid.p, trank.p, eoff.p, sroot.p, snode.p, node_key.p, cap_tracks, cap_elems, track_id,
+  k_emit<<<grid_for(K, 256), 256, 0, s>>>(K, Cn, fbits, incl.p, run_start.p, valid.p, trank.p, eoff.p, sroot.p, snode.p, node_key.p, cap_tracks, cap_elems, track_id,
                                           track_offset, elem_img, elem_feat);
   k_finish<<<1, 1, 0, s>>>(Cn, valid.p, trank.p, vlen.p, eoff.p, cap_tracks, track_offset, d_counts.p);
   long long h_counts[4];
@@ -313,6 +328,7 @@ int ptztracks_build_dev(const ptztracks_matches* m, int64_t num_matches, ptztrac
   int rc = need_device();
   if (rc != PTZ_OK) return rc;
   return guarded_t([&]() {
+    enable_memory_pool();  // keep the scratch of repeated calls in the stream-ordered pool
     const DevCounts c = build_device(num_matches, m->num_pairs, m->pair_src, m->pair_dst, reinterpret_cast<const long long*>(m->match_offset), m->query_idx,
                                      m->train_idx, m->min_track_length, out->cap_tracks, out->cap_elems, out->track_id,
                                      reinterpret_cast<long long*>(out->track_offset), out->elem_img, out->elem_feat, (cudaStream_t)cuda_stream);

@@ -3,8 +3,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -79,6 +81,44 @@ inline void enable_memory_pool() {
 
 // Device buffer.  alloc(count, stream) with a non-null stream is stream-ordered (cudaMallocAsync / cudaFreeAsync on that
 // stream); without a stream it is a plain cudaMalloc.
+// Exact-size cache of device blocks in front of cudaMallocAsync, keyed by (stream, bytes).  A solve allocates ~80 buffers (1.3 GB at
+// cfg 4) and the next solve of an IBA run / of bench.py's end-to-end leg asks for the very same sizes; going back to the CUDA pool
+// each time was measured to stall now and then for tens to hundreds of milliseconds (the pool re-growing after fragmentation,
+// PTZ_SETUP_DEBUG).  A block is only ever handed back to work on the SAME stream it was released on, so reuse is stream-ordered
+// exactly like cudaFreeAsync / cudaMallocAsync.  Above the limit (PTZ_BLOCK_CACHE_MB, default 32 GB) everything cached is released.
+struct BlockCache {
+  typedef std::pair<cudaStream_t, size_t> Key;
+  static std::mutex& lock() { static std::mutex m; return m; }
+  static std::map<Key, std::vector<void*>>& blocks() { static std::map<Key, std::vector<void*>> b; return b; }
+  static size_t& cached() { static size_t c = 0; return c; }
+  static size_t limit() {
+    static size_t l = []() { const char* e = getenv("PTZ_BLOCK_CACHE_MB"); return (size_t)(e ? atoll(e) : 32768) << 20; }();
+    return l;
+  }
+  static size_t round(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+  static void* get(cudaStream_t s, size_t bytes) {
+    std::lock_guard<std::mutex> g(lock());
+    auto it = blocks().find(Key(s, bytes));
+    if (it == blocks().end() || it->second.empty()) return nullptr;
+    void* p = it->second.back();
+    it->second.pop_back();
+    cached() -= bytes;
+    return p;
+  }
+  static void put(cudaStream_t s, void* p, size_t bytes) {
+    std::lock_guard<std::mutex> g(lock());
+    if (cached() + bytes > limit()) {
+      for (auto& kv : blocks())
+        for (void* q : kv.second) cudaFreeAsync(q, kv.first.first);
+      blocks().clear();
+      cached() = 0;
+    }
+    if (bytes > limit()) { cudaFreeAsync(p, s); return; }
+    blocks()[Key(s, bytes)].push_back(p);
+    cached() += bytes;
+  }
+};
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -90,7 +130,7 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) { if (async) cudaFreeAsync(p, as); else cudaFree(p); }
+    if (p) { if (async) BlockCache::put(as, p, BlockCache::round(n * sizeof(T))); else cudaFree(p); }
     p = nullptr;
     n = 0;
   }
@@ -100,8 +140,13 @@ struct DevBuf {
     as = s;
     async = (s != nullptr);
     if (count) {
-      if (async) PTZ_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), s));
-      else PTZ_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+      if (async) {
+        const size_t bytes = BlockCache::round(count * sizeof(T));
+        p = reinterpret_cast<T*>(BlockCache::get(s, bytes));
+        if (!p) PTZ_CUDA(cudaMallocAsync((void**)&p, bytes, s));
+      } else {
+        PTZ_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+      }
     }
   }
   void zero(cudaStream_t s) {

@@ -365,7 +365,8 @@ def bench_tracks(args, prob):
     cr.cap_tracks, cr.cap_elems = N, 2 * N
     cr.track_id, cr.track_offset = C.cast(o_tid.data_ptr(), abi.ip), C.cast(o_off.data_ptr(), abi.lp)
     cr.elem_img, cr.elem_feat = C.cast(o_img.data_ptr(), abi.ip), C.cast(o_feat.data_ptr(), abi.ip)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real stream: the library's scratch is pooled per stream (the legacy default stream gets plain cudaMalloc)
+    torch.cuda.synchronize()
 
     def run():
         lib.check(L.ptztracks_build_dev(C.byref(cm), C.c_int64(N), C.byref(cr), C.c_void_p(stream.cuda_stream)), "tracks dev")

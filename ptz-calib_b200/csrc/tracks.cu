@@ -64,8 +64,14 @@ __global__ void k_index_ranges(long long N, int npairs, const int* __restrict__ 
   int f = 0, g = 0;
   if (i < N) { const int q = query_idx[i], t = train_idx[i]; if (q < 0 || t < 0) *bad = 1; f = max(max(q, t), 0); }
   if (i < npairs) { const int a = pair_src[i], c = pair_dst[i]; if (a < 0 || c < 0) *bad = 1; g = max(max(a, c), 0); }
+  // warp maximum -> block maximum in shared memory -> one global atomic per block
+  __shared__ unsigned int sm[2];
+  if (threadIdx.x < 2) sm[threadIdx.x] = 0;
+  __syncthreads();
   const unsigned int fm = __reduce_max_sync(0xffffffffu, (unsigned int)f), gm = __reduce_max_sync(0xffffffffu, (unsigned int)g);
-  if ((threadIdx.x & 31) == 0) { if (fm) atomicMax(maxv + 1, fm); if (gm) atomicMax(maxv, gm); }
+  if ((threadIdx.x & 31) == 0) { if (fm) atomicMax(&sm[1], fm); if (gm) atomicMax(&sm[0], gm); }
+  __syncthreads();
+  if (threadIdx.x < 2 && sm[threadIdx.x]) atomicMax(maxv + threadIdx.x, sm[threadIdx.x]);
 }
 __device__ __forceinline__ int pair_of(const long long* __restrict__ match_offset, int npairs, long long m) {
   int lo = 0, up = npairs;  // invariant: match_offset[lo] <= m < match_offset[up]

@@ -269,7 +269,8 @@ typedef struct ptztracks_result {
 
 /* PTZ_ERR_INVALID with the counts filled in when a capacity is too small, or for a negative image / feature index */
 int ptztracks_build(const ptztracks_matches* matches, ptztracks_result* out);
-/* all pointers (of both structs) are DEVICE pointers; counts come back in the struct (bench.py's kernel-only timing) */
+/* all pointers (of both structs) are DEVICE pointers; counts come back in the struct (bench.py's kernel-only timing).
+ * Scratch memory is cached per stream: pass a stream you created (with the legacy default stream, NULL, every call pays cudaMalloc). */
 int ptztracks_build_dev(const ptztracks_matches* dev_matches, int64_t num_matches, ptztracks_result* dev_out, void* cuda_stream);
 
 /* tracks -> observation rows of ptzba_problem, as the loop at ptzray_optimizer.cc:801-848 adds residual blocks: tracks in

@@ -165,6 +165,42 @@ class TracksBuilder {
   std::vector<int> parent_, rank_, size_;
 };
 
+// tracks.cc:120-136: total / longest / shortest track length
+inline void Length(const Tracks& tracks, int& total_length, int& max_length, int& min_length) {
+  total_length = 0; max_length = 0; min_length = std::numeric_limits<int>::max();
+  for (const auto& t : tracks) {
+    const int n = (int)t.second.size();
+    total_length += n; max_length = std::max(max_length, n); min_length = std::min(min_length, n);
+  }
+}
+// tracks.cc:150-202: the largest set of images connected through tracks.  The reference merges std::sets track by track; the result is
+// the largest connected component of the image graph, found here with a union-find over the images (ties: the component holding the
+// smallest image id).
+inline void FindMaxCoVisible(const Tracks& tracks, int num_images, std::set<int>& max_connect_imgs) {
+  std::vector<int> parent(std::max(num_images, 0));
+  std::iota(parent.begin(), parent.end(), 0);
+  std::vector<char> seen(parent.size(), 0);
+  auto find = [&](int i) { while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; } return i; };
+  for (const auto& t : tracks) {
+    int first = -1;
+    for (const auto& e : t.second) {
+      if (e.first < 0 || e.first >= num_images) continue;
+      seen[e.first] = 1;
+      if (first < 0) first = e.first; else parent[find(e.first)] = find(first);
+    }
+  }
+  std::map<int, std::vector<int>> comps;
+  for (int i = 0; i < num_images; ++i) if (seen[i]) comps[find(i)].push_back(i);
+  max_connect_imgs.clear();
+  size_t best = 0;
+  int best_min = std::numeric_limits<int>::max();
+  for (const auto& c : comps)
+    if (c.second.size() > best || (c.second.size() == best && c.second.front() < best_min)) {
+      best = c.second.size(); best_min = c.second.front();
+      max_connect_imgs = std::set<int>(c.second.begin(), c.second.end());
+    }
+}
+
 enum FACTOR_TYPE { PTZRay, PTZRayDist, PTZRayFxfyDist, PTZRayDistDisp };  // ptzray_optimizer.h:110
 
 class PTZRayOptimizer {

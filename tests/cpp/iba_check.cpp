@@ -1,6 +1,7 @@
 // Drives PtzIncrementalOptimizer (include/ptzcalib_b200.hpp, mirror of src/core/ptz_incremental_optimizer.h) the way
 // run_ptz_ba.cc does: features + a table of pairwise matches with homographies and confidences, cameras unknown.
 // Input: a synthetic scene (ground-truth cameras, observations by view/track); output: registered ids and refined cameras.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -68,18 +69,22 @@ int main(int argc, char** argv) {
 
   PtzIncrementalOptimizer iba(features, matches_info, cameras, max_iter);
   std::unordered_set<long> reg;
+  const auto t0 = std::chrono::steady_clock::now();
   const bool ok = iba.Solve(cameras, reg);
+  const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
   FILE* g = fopen(argv[2], "wb");
   if (!g) return 2;
   double head[8] = {(double)ok, (double)reg.size(), (double)iba.num_global_bundles(), (double)iba.num_reloc_batches(), (double)iba.num_reloc_queries(),
-                    iba.last_reproj_error(), (double)matches_info.size(), 0};
+                    iba.last_reproj_error(), (double)matches_info.size(), seconds};
   fwrite(head, sizeof(double), 8, g);
   std::vector<double> out(22 * (size_t)V);
   for (int i = 0; i < V; ++i) { out[22 * (size_t)i] = reg.count(i) ? 1.0 : 0.0; cameras[i].ToKrt21(&out[22 * (size_t)i + 1]); }
   fwrite(out.data(), sizeof(double), out.size(), g);
   fclose(g);
-  printf("iba ok=%d registered=%zu/%d global BAs=%d reloc batches=%d (%d queries) reproj=%.4f pairs=%zu\n", (int)ok, reg.size(), V, iba.num_global_bundles(),
-         iba.num_reloc_batches(), iba.num_reloc_queries(), iba.last_reproj_error(), matches_info.size());
+  size_t nm = 0;
+  for (auto& mi : matches_info) nm += mi.matches.size();
+  printf("iba ok=%d registered=%zu/%d global BAs=%d reloc batches=%d (%d queries) reproj=%.4f pairs=%zu matches=%zu  %.3f s\n", (int)ok, reg.size(), V,
+         iba.num_global_bundles(), iba.num_reloc_batches(), iba.num_reloc_queries(), iba.last_reproj_error(), matches_info.size(), nm, seconds);
   return 0;
 }

@@ -29,6 +29,14 @@ int main(int argc, char** argv) {
     for (int k = 0; k < 9; ++k) { worst = std::max(worst, std::fabs(cams[i].K()[k] - again[i].K()[k])); worst = std::max(worst, std::fabs(cams[i].R()[k] - again[i].R()[k])); }
     for (int k = 0; k < 5; ++k) worst = std::max(worst, std::fabs(cams[i].dist()[k] - again[i].dist()[k]));
   }
+  // Length / FindMaxCoVisible (tracks.cc:120-202): two components {0,1,2} and {5,6}; image 9 unseen
+  Tracks tr;
+  tr[0] = Track{{0, 1}, {1, 4}}; tr[3] = Track{{1, 2}, {2, 7}, {0, 3}}; tr[8] = Track{{5, 1}, {6, 1}};
+  int tot, mx, mn; Length(tr, tot, mx, mn);
+  std::set<int> co; FindMaxCoVisible(tr, 10, co);
+  printf("tracks %d %d %d covis", tot, mx, mn);
+  for (int i : co) printf(" %d", i);
+  printf("\n");
   std::vector<std::string> missing{"nope.jpg"};
   std::vector<Camera> none;
   printf("roundtrip %d %.3g missing %d pix0 %.9g %.9g size %d %d\n", (int)ok2, worst, (int)ReadCamFromJson(argv[4], missing, none), pix[0].empty() ? -1.0 : pix[0][0].x,

@@ -41,7 +41,8 @@ def test_text_formats_and_camera_json(tmp_path):
     assert np.allclose(got, kp, atol=1e-4)
     assert lines[1].startswith("pairs 2 | a.jpg b.jpg 3 0:3 1:2 4:4 | c.png a.jpg 1 7:9")
     assert lines[2] == "json 1 2"
-    rt = lines[3].split()
+    assert lines[3] == "tracks 7 3 2 covis 0 1 2"
+    rt = lines[4].split()
     assert rt[1] == "1" and float(rt[2]) == 0.0 and rt[4] == "0"  # round trip exact; a missing camera makes ReadCamFromJson fail
     assert abs(float(rt[6]) - 480.0) < 1e-4 and abs(float(rt[7]) - 540.0) < 1e-4 and rt[9:] == ["1920", "1080"]  # marker pixels scaled by the resolution
     out = json.load(open(jout))  # what SaveToJson wrote is valid JSON with the reference's fields

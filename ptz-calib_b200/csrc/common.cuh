@@ -109,7 +109,7 @@ struct BlockCache {
     std::lock_guard<std::mutex> g(lock());
     if (cached() + bytes > limit()) {
       for (auto& kv : blocks())
-        for (void* q : kv.second) cudaFreeAsync(q, kv.first.first);
+        for (void* q : kv.second) cudaFree(q);  // (rare; synchronising, and safe even if the caller's stream no longer exists)
       blocks().clear();
       cached() = 0;
     }

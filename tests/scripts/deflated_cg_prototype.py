@@ -270,3 +270,73 @@ def main3():
 
 if __name__ == "__main__" and os.environ.get("ANALYTIC") == "big":
     main3()
+
+
+def main4():
+    """init-CG: only the initial guess is projected (x0 = W G^-1 W^T b), the iteration itself is the plain one"""
+    V = int(sys.argv[1]) if len(sys.argv) > 1 else 150
+    P = int(sys.argv[2]) if len(sys.argv) > 2 else 12000
+    p = synth.make_ba_scene(V, P, "band", seed=1004)
+    A, b, sF, Linv = reduced_system_big(p, 1e4)
+    ev, evec = np.linalg.eigh(A)
+    xd = np.linalg.solve(A, b)
+    _, it = cg_single_reduction(A, b, 1e-13)
+    print(f"V={p.V}: none {it} it")
+    bases = [("analytic k=16", analytic_basis(p, (sF, Linv), "affine+f")), ("exact k=10", evec[:, :10]), ("exact k=16", evec[:, :16])]
+    for name, W in bases:
+        AW = A @ W
+        x0 = W @ np.linalg.solve(W.T @ AW, W.T @ b)
+        r0 = b - A @ x0
+        y, it = cg_single_reduction(A, r0, 1e-13 * np.linalg.norm(b) / np.linalg.norm(r0))
+        x = x0 + y
+        print(f"  init-CG {name}: {it} it, |r0|/|b| = {np.linalg.norm(r0) / np.linalg.norm(b):.2e} (err {np.abs(x - xd).max() / np.abs(xd).max():.1e})")
+
+
+if __name__ == "__main__" and os.environ.get("ANALYTIC") == "init":
+    main4()
+
+
+def lanczos_ritz_from_cg(A, b, k, tol=1e-13):
+    """plain CG on (A, b) keeping the normalised residuals; lowest k Ritz pairs of the Lanczos tridiagonal built from the CG coefficients"""
+    x = np.zeros_like(b); r = b.copy(); p = r.copy(); rr = r @ r; b2 = b @ b
+    Rm, alphas, betas = [], [], []
+    while np.sqrt(rr) > tol * np.sqrt(b2) and len(alphas) < 5000:
+        Rm.append(r / np.sqrt(rr))
+        Ap = A @ p; a = rr / (p @ Ap); x += a * p; r = r - a * Ap; rn = r @ r; be = rn / rr; p = r + be * p; rr = rn
+        alphas.append(a); betas.append(be)
+    m = len(alphas)
+    T = np.zeros((m, m))
+    for j in range(m):
+        T[j, j] = 1.0 / alphas[j] + (betas[j - 1] / alphas[j - 1] if j > 0 else 0.0)
+        if j + 1 < m:
+            T[j, j + 1] = T[j + 1, j] = -np.sqrt(betas[j]) / alphas[j]
+    th, Y = np.linalg.eigh(T)
+    W = np.stack(Rm, 1) @ Y[:, :k]
+    return th[:k], W, m
+
+
+def main5():
+    """recycling: Ritz vectors harvested from the CG run of ONE LM iterate, used as init-CG / deflation basis for ANOTHER iterate"""
+    V = int(sys.argv[1]) if len(sys.argv) > 1 else 150
+    P = int(sys.argv[2]) if len(sys.argv) > 2 else 12000
+    p = synth.make_ba_scene(V, P, "band", seed=1004)
+    q = synth.make_ba_scene(V, P, "band", seed=1004, rot_noise_deg=0.3, focal_noise=0.01)
+    A1, b1, _, _ = reduced_system_big(q, 3e2)      # "first LM iteration": harvest here
+    A, b, _, _ = reduced_system_big(p, 1e4)        # a later iterate: use there
+    xd = np.linalg.solve(A, b)
+    _, it = cg_single_reduction(A, b, 1e-13)
+    print(f"V={p.V}: none {it} it")
+    for k in (6, 10, 16):
+        th, W, m = lanczos_ritz_from_cg(A1, b1, k)
+        W, _ = np.linalg.qr(W)
+        AW = A @ W
+        x0 = W @ np.linalg.solve(W.T @ AW, W.T @ b)
+        r0 = b - A @ x0
+        y, it1 = cg_single_reduction(A, r0, 1e-13 * np.linalg.norm(b) / np.linalg.norm(r0))
+        x2, it2 = cg_single_reduction(A, b, 1e-13, W)
+        print(f"  Ritz vectors of the other iterate ({m} CG steps there), k={k:2d}: init-CG {it1} it (err {np.abs(x0 + y - xd).max() / np.abs(xd).max():.1e}), "
+              f"deflated CG {it2} it (err {np.abs(x2 - xd).max() / np.abs(xd).max():.1e}); lowest Ritz values {th[:3]}")
+
+
+if __name__ == "__main__" and os.environ.get("ANALYTIC") == "recycle":
+    main5()

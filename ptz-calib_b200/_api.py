@@ -23,11 +23,12 @@ def device_count() -> int:
 
 
 # --------------------------------------------------------------------------------------------- BA
-def ba_solve(prob: BAProblem, opt=None, **kw) -> BAResult:
-    """ptzba_solve: one PTZRayOptimizer::Solve worth of work (ptzray_optimizer.cc:454-489) with host buffers."""
+def ba_solve(prob: BAProblem, opt=None, alloc=None, **kw) -> BAResult:
+    """ptzba_solve: one PTZRayOptimizer::Solve worth of work (ptzray_optimizer.cc:454-489) with host buffers.
+    alloc(name, shape): optional provider of the output arrays (caller-owned, e.g. pinned and reused across calls)."""
     opt = opt or default_options(**kw)
     c = prob.to_c()
-    r, arrs, log = problem.alloc_ba_result(prob)
+    r, arrs, log = problem.alloc_ba_result(prob, alloc=alloc)
     rc = lib.load().ptzba_solve(C.byref(c), C.byref(opt), C.byref(r))
     lib.check(rc, "ptzba_solve")
     return problem.unpack_ba_result(prob, r, arrs, log)

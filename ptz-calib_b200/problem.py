@@ -177,10 +177,11 @@ class BAResult:
         return self.termination == abi.PTZ_CONVERGENCE
 
 
-def alloc_ba_result(prob: BAProblem, log_capacity=512):
+def alloc_ba_result(prob: BAProblem, log_capacity=512, alloc=None):
+    """alloc(name, shape) -> float64 array: lets a caller hand in its own (e.g. pinned, reused) output buffers"""
     V, P = prob.V, prob.P
-    arrs = dict(intr=np.zeros((V, 9)), ext=np.zeros((V, 6)), ray=np.zeros((max(P, 1), 3)), disp=np.zeros(3), tlw=np.zeros(6),
-                cams_world=np.zeros((V, 21)), rays_world=np.zeros((max(P, 1), 3)))
+    shapes = dict(intr=(V, 9), ext=(V, 6), ray=(max(P, 1), 3), disp=(3,), tlw=(6,), cams_world=(V, 21), rays_world=(max(P, 1), 3))
+    arrs = {k: (np.zeros(sh) if alloc is None else alloc(k, sh)) for k, sh in shapes.items()}
     log = (abi.IterLog * log_capacity)()
     r = abi.BAResultC()
     for k, a in arrs.items():

@@ -152,6 +152,34 @@ class PTZRayOptimizer:
         self.result = None
         self._err = (0.0, 0.0, 0.0)
 
+    @classmethod
+    def from_matches(cls, matches: Matches, views: Views, cams21, max_iter: int, factor_type=abi.PTZ_BA_PTZRAY, min_track_length=4,
+                     pt_uv=None, pt_xyz=None, pt_view=None, tlw0=None):
+        """The reference's constructor arguments (features = `views`, matches_info = `matches`, cameras = krt21 rows, cam_ids =
+        views.is_candidate): FindTracks (ptzray_optimizer.cc:537-552) and the residual-block loop (:801-848) run on the GPU through
+        ptztracks_build / ptztracks_flatten; the 2d-3d annotations are given per ORIGINAL image index (pt_view)."""
+        cams21 = f64(cams21).reshape(-1, 21)
+        tr = build_tracks(matches, min_track_length)
+        obs = flatten_tracks(tr, views)
+        cand = np.nonzero(views.is_candidate)[0]
+        dense = -np.ones(len(views.is_candidate), np.int64)
+        dense[cand] = np.arange(len(cand))
+        intr = np.concatenate([cams21[cand, 0:4], cams21[cand, 16:21]], axis=1)
+        ext = np.zeros((len(cand), 6))
+        from .synth import log_so3  # rvec of R (Camera::rvec, types.h:82-87)
+
+        ext[:, :3] = log_so3(cams21[cand, 4:13].reshape(-1, 3, 3))
+        ext[:, 3:] = cams21[cand, 13:16]
+        kw = {}
+        if pt_uv is not None and len(pt_uv):
+            keep = dense[np.asarray(pt_view)] >= 0
+            kw = dict(pt_uv=f32(pt_uv)[keep], pt_xyz=f64(pt_xyz)[keep], pt_view=dense[np.asarray(pt_view)][keep].astype(np.int32), tlw0=tlw0)
+        prob = BAProblem(factor_type=factor_type, intr=intr, ext=ext, obs_uv=obs.obs_uv, obs_view=obs.obs_view, obs_track=obs.obs_track,
+                         track_weight=obs.track_weight, **kw)
+        self = cls(prob, max_iter)
+        self.tracks, self.observations, self.view_of = tr, obs, cand
+        return self
+
     def CheckValid(self) -> bool:  # ptzray_optimizer.cc:515-535
         p = self.prob
         return p.V > 0 and self.max_iter > 0

@@ -115,3 +115,28 @@ def test_full_size_tracks_then_bundle_adjustment():
     r1, r2 = ptz.ba_solve(p, max_num_iterations=30), ptz.ba_solve(q, max_num_iterations=30)
     assert r1.termination == r2.termination == abi.PTZ_CONVERGENCE
     assert abs(r1.final_cost - r2.final_cost) <= 1e-9 * r1.final_cost
+
+
+def test_python_mirror_from_matches(orc):
+    """PTZRayOptimizer.from_matches: matches + keypoints + cameras in, refined cameras out, everything between on the GPU; a subset of
+    candidate views as in the incremental driver's global BAs."""
+    p = synth.make_config(1, scale=0.5)
+    m, v, _ = synth.make_matches_from_scene(p)
+    cams = np.zeros((p.V, 21))
+    for i in range(p.V):
+        cams[i, :4] = p.intr[i, :4]
+        cams[i, 4:13] = orc.rodrigues(p.ext[i, :3]).ravel()
+        cams[i, 16:21] = p.intr[i, 4:9]
+    ba = ptz.PTZRayOptimizer.from_matches(m, v, cams, max_iter=100)
+    ok, cw, rays = ba.Solve()
+    want = ptz.ba_solve(p, max_num_iterations=100)
+    assert ok and want.converged and ba.prob.M == p.M and ba.prob.P == p.P
+    assert abs(ba.final_reproj_error_all() - want.final_reproj_error_all) <= 1e-8 * want.final_reproj_error_all
+    assert np.abs(cw - want.cams_world).max() <= 1e-6
+    cand = (np.arange(p.V) < p.V // 2).astype(np.uint8)
+    ba2 = ptz.PTZRayOptimizer.from_matches(m, Views(cand, v.kp_offset, v.kp_uv), cams, max_iter=100)
+    ok2, cw2, _ = ba2.Solve()
+    assert ok2 and ba2.prob.V == p.V // 2 and ba2.prob.M == int(cand[p.obs_view].sum())
+    assert np.array_equal(ba2.view_of, np.arange(p.V // 2))
+    lens = np.diff(ba2.tracks.track_offset)
+    assert np.array_equal(ba2.prob.track_weight, lens[ba2.observations.row_track].astype(np.float64))  # weight counts every image of the track

@@ -170,7 +170,9 @@ enum {
   PTZ_K_TRACK_SOLVE, PTZ_K_SCHUR_DIAG, PTZ_K_SCHUR_OFFDIAG, PTZ_K_PRECOND,                     /* stage 2 */
   PTZ_K_PCG,                                                                                   /* stage 3 */
   PTZ_K_TRACK_BACKSUB, PTZ_K_CAM_UPDATE, PTZ_K_COST, PTZ_K_SCALARS,                            /* stage 4 */
-  PTZ_K_ALLREDUCE, PTZ_K_COUNT = 16
+  PTZ_K_ALLREDUCE,
+  PTZ_K_DEFLATE, /* stage 3: per-solve set-up of the deflated CG (basis scaling, S~W, S~S~W, Gram matrix, start vector) */
+  PTZ_K_COUNT = 16
 };
 typedef struct ptzba_stage_times {
   float ms_kernel[16];   /* summed device time per kernel id */

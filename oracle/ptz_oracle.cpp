@@ -562,9 +562,23 @@ bool solve_dense_qr(const std::vector<BlockJ>& B, int n, const double* D, double
 
 // SPARSE_SCHUR [ext]: eliminate the ray blocks (tangent range [rb,re), 3 columns each), solve the reduced system
 // exactly (dense Cholesky) or by block-Jacobi PCG to tight tolerance, back-substitute.
+//
+// Threading (Ceres runs its SchurEliminator on options.num_threads = 32 threads, ptzray_optimizer.cc:473): the rays are
+// eliminated in parallel (one track per task), and the reduced system is accumulated in parallel BY BLOCK ROW -- a task owns
+// the rows of one camera block and walks the tracks / residual blocks that touch it, so no two threads write the same entry
+// and every sum has a fixed order (results do not depend on the thread count).  The index structure is built once per solve.
 struct SchurWork {
   std::vector<std::vector<int>> track_blocks;  // residual blocks of each ray
   std::vector<int> cam_blocks;                 // residual blocks with no ray column
+  // per track: reduced camera columns it touches (grouped by camera block, ascending), and the block of each
+  std::vector<std::vector<int>> tcols;
+  // per block row: (track, first, count) -> tcols[track][first .. first+count) are the columns of this block
+  struct RowRef { int track, first, count; };
+  std::vector<std::vector<RowRef>> row_tracks;
+  std::vector<std::vector<int>> row_res;       // per block row: residual blocks with a column in this block
+  // block-sparse pattern (sparse mode): per block row the sorted block columns and the slot of each
+  std::vector<std::vector<int>> pat_col, pat_slot;
+  int nslots = 0;
   bool built = false;
 };
 bool solve_schur(const Problem& P, const std::vector<BlockJ>& B, const double* D, double* y, SchurWork& W, int linear_solver,
@@ -572,103 +586,166 @@ bool solve_schur(const Problem& P, const std::vector<BlockJ>& B, const double* D
   const int rb = P.ray_tan_begin, re = P.ray_tan_end, nt = P.num_tangent;
   const int nP = (re - rb) / 3;
   const int nC = nt - (re - rb);
+  const int nthreads = opt.num_threads > 0 ? opt.num_threads : 1;
+  (void)nthreads;
   auto cidx = [&](int t) { return t < rb ? t : t - (re - rb); };  // tangent -> reduced index
+  auto is_ray = [&](int t) { return t >= rb && t < re; };
+  // camera blocks own their rows; everything behind them is one border block.  (The dense solver keeps the same ownership
+  // for the accumulation; only the storage differs.)
+  const bool sparse = (linear_solver == 1);
+  const int bs = P.cam_block > 0 ? P.cam_block : 1, nvb = P.cam_block > 0 ? P.num_cam_blocks : 0, nblk = nvb + 1, bbs = nC - nvb * bs;
+  auto blk_of = [&](int c) { return c < nvb * bs ? c / bs : nvb; };
+  auto blk_off = [&](int c) { return c < nvb * bs ? c % bs : c - nvb * bs; };
+  auto blk_size = [&](int b) { return b < nvb ? bs : bbs; };
+  const int mbs = std::max(bs, bbs);
   if (!W.built) {
     W.track_blocks.assign(nP, std::vector<int>());
     W.cam_blocks.clear();
     for (int k = 0; k < (int)B.size(); ++k) {
       int p = -1;
       for (int c = 0; c < B[k].nc; ++c)
-        if (B[k].col[c] >= rb && B[k].col[c] < re) { p = (B[k].col[c] - rb) / 3; break; }
+        if (is_ray(B[k].col[c])) { p = (B[k].col[c] - rb) / 3; break; }
       if (p >= 0) W.track_blocks[p].push_back(k); else W.cam_blocks.push_back(k);
     }
+    W.tcols.assign(nP, std::vector<int>());
+    W.row_tracks.assign(nblk, std::vector<SchurWork::RowRef>());
+    W.row_res.assign(nblk, std::vector<int>());
+    std::vector<std::vector<int>> pat(nblk);
+    auto add_pairs = [&](const std::vector<int>& blocks) {
+      for (int a : blocks) for (int c : blocks) pat[a].push_back(c);
+    };
+    std::vector<int> blocks;
+    for (int p = 0; p < nP; ++p) {
+      std::vector<int>& tc = W.tcols[p];
+      for (int k : W.track_blocks[p])
+        for (int a = 0; a < B[k].nc; ++a)
+          if (!is_ray(B[k].col[a])) tc.push_back(cidx(B[k].col[a]));
+      std::sort(tc.begin(), tc.end());
+      tc.erase(std::unique(tc.begin(), tc.end()), tc.end());
+      blocks.clear();
+      for (size_t i = 0; i < tc.size();) {
+        const int b = blk_of(tc[i]);
+        size_t j = i;
+        while (j < tc.size() && blk_of(tc[j]) == b) ++j;
+        W.row_tracks[b].push_back({p, (int)i, (int)(j - i)});
+        blocks.push_back(b);
+        i = j;
+      }
+      if (sparse) add_pairs(blocks);
+    }
+    for (int k = 0; k < (int)B.size(); ++k) {
+      blocks.clear();
+      for (int a = 0; a < B[k].nc; ++a)
+        if (!is_ray(B[k].col[a])) blocks.push_back(blk_of(cidx(B[k].col[a])));
+      std::sort(blocks.begin(), blocks.end());
+      blocks.erase(std::unique(blocks.begin(), blocks.end()), blocks.end());
+      for (int b : blocks) W.row_res[b].push_back(k);
+      if (sparse) add_pairs(blocks);
+    }
+    W.pat_col.assign(nblk, std::vector<int>());
+    W.pat_slot.assign(nblk, std::vector<int>());
+    W.nslots = 0;
+    if (sparse)
+      for (int b = 0; b < nblk; ++b) {
+        pat[b].push_back(b);  // the diagonal block always exists (LM diagonal)
+        std::sort(pat[b].begin(), pat[b].end());
+        pat[b].erase(std::unique(pat[b].begin(), pat[b].end()), pat[b].end());
+        W.pat_col[b] = pat[b];
+        W.pat_slot[b].resize(pat[b].size());
+        for (size_t i = 0; i < pat[b].size(); ++i) W.pat_slot[b][i] = W.nslots++;
+      }
     W.built = true;
   }
-  // reduced system storage: dense (exact Cholesky, small problems) or block-sparse by view (PCG, large problems)
-  const bool sparse = (linear_solver == 1);
-  const int bs = P.cam_block > 0 ? P.cam_block : 1, nvb = sparse ? P.num_cam_blocks : 0, nblk = nvb + 1, bbs = nC - nvb * bs;  // border block size
-  auto blk_of = [&](int c) { return c < nvb * bs ? c / bs : nvb; };
-  auto blk_off = [&](int c) { return c < nvb * bs ? c % bs : c - nvb * bs; };
-  auto blk_size = [&](int b) { return b < nvb ? bs : bbs; };
-  const int mbs = std::max(bs, bbs);
   std::vector<double> S(sparse ? 0 : (size_t)nC * nC, 0.0), rhs(nC, 0.0);
-  std::vector<std::vector<std::pair<int, int>>> rows(sparse ? nblk : 0);  // per block row: (block col, slot)
-  std::vector<double> blocks;                                            // slot -> mbs*mbs values
+  std::vector<double> blocks(sparse ? (size_t)W.nslots * mbs * mbs : 0, 0.0);  // slot -> mbs*mbs values
   auto slot_of = [&](int bi, int bj) {
-    for (auto& e : rows[bi]) if (e.first == bj) return e.second;
-    int sl = (int)(blocks.size() / ((size_t)mbs * mbs));
-    blocks.resize(blocks.size() + (size_t)mbs * mbs, 0.0);
-    rows[bi].push_back(std::make_pair(bj, sl));
-    return sl;
+    const std::vector<int>& pc = W.pat_col[bi];
+    return W.pat_slot[bi][std::lower_bound(pc.begin(), pc.end(), bj) - pc.begin()];
   };
-  auto Sadd = [&](int i, int j, double v) {
-    if (!sparse) { S[(size_t)i * nC + j] += v; return; }
-    blocks[(size_t)slot_of(blk_of(i), blk_of(j)) * mbs * mbs + blk_off(i) * mbs + blk_off(j)] += v;
-  };
-  for (int t = 0; t < nt; ++t)
-    if (t < rb || t >= re) Sadd(cidx(t), cidx(t), D[t] * D[t]);
-  auto add_FtF = [&](const BlockJ& b) {
-    for (int a = 0; a < b.nc; ++a) {
-      if (b.col[a] >= rb && b.col[a] < re) continue;
-      int ia = cidx(b.col[a]);
-      rhs[ia] += b.J[0][a] * b.r[0] + b.J[1][a] * b.r[1];
-      for (int c = 0; c < b.nc; ++c) {
-        if (b.col[c] >= rb && b.col[c] < re) continue;
-        Sadd(ia, cidx(b.col[c]), b.J[0][a] * b.J[0][c] + b.J[1][a] * b.J[1][c]);
-      }
-    }
-  };
-  for (int k : W.cam_blocks) add_FtF(B[k]);
+  // ---- phase A: per track, V = E^T E + D^2 = L L^T, t = L^-1 h, What = (F^T E) L^-T for every camera column it touches
   std::vector<double> Lp((size_t)nP * 6), tp((size_t)nP * 3);
   std::vector<char> pok(nP, 0);
-  // per track: V = E^T E + D^2, h = E^T r, W = F^T E over the union of camera columns it touches
-  std::vector<int> cols;
-  std::vector<double> Wm;
+  std::vector<size_t> woff(nP + 1, 0);
+  for (int p = 0; p < nP; ++p) woff[p + 1] = woff[p] + W.tcols[p].size() * 3;
+  std::vector<double> What(woff[nP], 0.0);
+  int bad = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads) reduction(| : bad)
+#endif
   for (int p = 0; p < nP; ++p) {
     const std::vector<int>& tb = W.track_blocks[p];
     if (tb.empty()) continue;
+    const std::vector<int>& tc = W.tcols[p];
+    double* Wm = &What[woff[p]];
     double Vm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, h[3] = {0, 0, 0};
-    cols.clear();
-    for (int k : tb) {
-      add_FtF(B[k]);
-      for (int a = 0; a < B[k].nc; ++a)
-        if (!(B[k].col[a] >= rb && B[k].col[a] < re)) {
-          int ci = cidx(B[k].col[a]);
-          if (std::find(cols.begin(), cols.end(), ci) == cols.end()) cols.push_back(ci);
-        }
-    }
-    Wm.assign(cols.size() * 3, 0.0);
     for (int k : tb) {
       const BlockJ& b = B[k];
       double E[2][3] = {{0, 0, 0}, {0, 0, 0}};
       for (int a = 0; a < b.nc; ++a)
-        if (b.col[a] >= rb && b.col[a] < re) { int e = (b.col[a] - rb) % 3; E[0][e] = b.J[0][a]; E[1][e] = b.J[1][a]; }
+        if (is_ray(b.col[a])) { int e = (b.col[a] - rb) % 3; E[0][e] = b.J[0][a]; E[1][e] = b.J[1][a]; }
       for (int i = 0; i < 3; ++i) {
         h[i] += E[0][i] * b.r[0] + E[1][i] * b.r[1];
         for (int j = 0; j < 3; ++j) Vm[i][j] += E[0][i] * E[0][j] + E[1][i] * E[1][j];
       }
       for (int a = 0; a < b.nc; ++a)
-        if (!(b.col[a] >= rb && b.col[a] < re)) {
-          int li = (int)(std::find(cols.begin(), cols.end(), cidx(b.col[a])) - cols.begin());
+        if (!is_ray(b.col[a])) {
+          const int li = (int)(std::lower_bound(tc.begin(), tc.end(), cidx(b.col[a])) - tc.begin());
           for (int j = 0; j < 3; ++j) Wm[li * 3 + j] += b.J[0][a] * E[0][j] + b.J[1][a] * E[1][j];
         }
     }
     for (int i = 0; i < 3; ++i) Vm[i][i] += D[rb + 3 * p + i] * D[rb + 3 * p + i];
     double A6[6] = {Vm[0][0], Vm[1][0], Vm[1][1], Vm[2][0], Vm[2][1], Vm[2][2]};
-    if (!chol3(A6, &Lp[(size_t)p * 6])) return false;
+    if (!chol3(A6, &Lp[(size_t)p * 6])) { bad |= 1; continue; }
     pok[p] = 1;
     const double* L = &Lp[(size_t)p * 6];
-    // What = W L^-T  (rows of W solved against L), t = L^-1 h
     double t0 = h[0] / L[0], t1 = (h[1] - L[1] * t0) / L[2], t2 = (h[2] - L[3] * t0 - L[4] * t1) / L[5];
     tp[3 * p] = t0; tp[3 * p + 1] = t1; tp[3 * p + 2] = t2;
-    for (size_t a = 0; a < cols.size(); ++a) {
+    for (size_t a = 0; a < tc.size(); ++a) {
       double w0 = Wm[a * 3] / L[0], w1 = (Wm[a * 3 + 1] - L[1] * w0) / L[2], w2 = (Wm[a * 3 + 2] - L[3] * w0 - L[4] * w1) / L[5];
       Wm[a * 3] = w0; Wm[a * 3 + 1] = w1; Wm[a * 3 + 2] = w2;
     }
-    for (size_t a = 0; a < cols.size(); ++a) {
-      rhs[cols[a]] -= Wm[a * 3] * t0 + Wm[a * 3 + 1] * t1 + Wm[a * 3 + 2] * t2;
-      for (size_t c = 0; c < cols.size(); ++c)
-        Sadd(cols[a], cols[c], -(Wm[a * 3] * Wm[c * 3] + Wm[a * 3 + 1] * Wm[c * 3 + 1] + Wm[a * 3 + 2] * Wm[c * 3 + 2]));
+  }
+  if (bad) return false;
+  // ---- phase B: one task per block row: D^2, F^T F and F^T r of its residual blocks, minus the Schur terms of its tracks
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+#endif
+  for (int bi = 0; bi < nblk; ++bi) {
+    const int rows_n = blk_size(bi);
+    if (rows_n == 0) continue;
+    const int row0 = bi < nvb ? bi * bs : nvb * bs;
+    auto Sadd = [&](int i, int j, double v) {  // i is a reduced row of block bi
+      if (!sparse) { S[(size_t)i * nC + j] += v; return; }
+      blocks[(size_t)slot_of(bi, blk_of(j)) * mbs * mbs + blk_off(i) * mbs + blk_off(j)] += v;
+    };
+    for (int i = row0; i < row0 + rows_n; ++i) {
+      const int t = i < rb ? i : i + (re - rb);  // reduced -> tangent
+      Sadd(i, i, D[t] * D[t]);
+    }
+    for (int k : W.row_res[bi]) {
+      const BlockJ& b = B[k];
+      for (int a = 0; a < b.nc; ++a) {
+        if (is_ray(b.col[a])) continue;
+        const int ia = cidx(b.col[a]);
+        if (blk_of(ia) != bi) continue;
+        rhs[ia] += b.J[0][a] * b.r[0] + b.J[1][a] * b.r[1];
+        for (int c = 0; c < b.nc; ++c) {
+          if (is_ray(b.col[c])) continue;
+          Sadd(ia, cidx(b.col[c]), b.J[0][a] * b.J[0][c] + b.J[1][a] * b.J[1][c]);
+        }
+      }
+    }
+    for (const SchurWork::RowRef& rr : W.row_tracks[bi]) {
+      const int p = rr.track;
+      if (!pok[p]) continue;
+      const std::vector<int>& tc = W.tcols[p];
+      const double* Wm = &What[woff[p]];
+      const double t0 = tp[3 * p], t1 = tp[3 * p + 1], t2 = tp[3 * p + 2];
+      for (int a = rr.first; a < rr.first + rr.count; ++a) {
+        rhs[tc[a]] -= Wm[a * 3] * t0 + Wm[a * 3 + 1] * t1 + Wm[a * 3 + 2] * t2;
+        for (size_t c = 0; c < tc.size(); ++c)
+          Sadd(tc[a], tc[c], -(Wm[a * 3] * Wm[c * 3] + Wm[a * 3 + 1] * Wm[c * 3 + 1] + Wm[a * 3 + 2] * Wm[c * 3 + 2]));
+      }
     }
   }
   std::vector<double> yc(rhs);
@@ -681,13 +758,17 @@ bool solve_schur(const Problem& P, const std::vector<BlockJ>& B, const double* D
     // block-Jacobi preconditioned CG on the block-sparse reduced system, run to opt.pcg_rel_tolerance ("exact" stand-in
     // for the sparse Cholesky of SPARSE_SCHUR on problems where a dense factorisation would dominate the CPU baseline)
     std::vector<std::vector<double>> Minv(nblk);
+    int bad_block = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nthreads) reduction(| : bad_block)
+#endif
     for (int b = 0; b < nblk; ++b) {
       const int n = blk_size(b);
       if (n == 0) continue;
       std::vector<double> A((size_t)n * n);
       const double* Bd = &blocks[(size_t)slot_of(b, b) * mbs * mbs];
       for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) A[(size_t)i * n + j] = Bd[i * mbs + j];
-      if (!cholesky_inplace(A, n)) return false;
+      if (!cholesky_inplace(A, n)) { bad_block |= 1; continue; }
       Minv[b].assign((size_t)n * n, 0.0);
       for (int c = 0; c < n; ++c) {
         std::vector<double> e(n, 0.0);
@@ -696,8 +777,12 @@ bool solve_schur(const Problem& P, const std::vector<BlockJ>& B, const double* D
         for (int i = 0; i < n; ++i) Minv[b][(size_t)i * n + c] = e[i];
       }
     }
+    if (bad_block) return false;
     auto boff = [&](int b) { return b < nvb ? b * bs : nvb * bs; };
     auto apply_M = [&](const std::vector<double>& r, std::vector<double>& z) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+#endif
       for (int b = 0; b < nblk; ++b) {
         const int n = blk_size(b), o = boff(b);
         for (int i = 0; i < n; ++i) { double sacc = 0; for (int j = 0; j < n; ++j) sacc += Minv[b][(size_t)i * n + j] * r[o + j]; z[o + i] = sacc; }
@@ -705,14 +790,14 @@ bool solve_schur(const Problem& P, const std::vector<BlockJ>& B, const double* D
     };
     auto apply_S = [&](const std::vector<double>& x, std::vector<double>& out) {
 #ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 16)
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
 #endif
       for (int bi = 0; bi < nblk; ++bi) {
         const int ni = blk_size(bi), oi = boff(bi);
         for (int i = 0; i < ni; ++i) out[oi + i] = 0;
-        for (auto& e : rows[bi]) {
-          const int nj = blk_size(e.first), oj = boff(e.first);
-          const double* Bd = &blocks[(size_t)e.second * mbs * mbs];
+        for (size_t e = 0; e < W.pat_col[bi].size(); ++e) {
+          const int bj = W.pat_col[bi][e], nj = blk_size(bj), oj = boff(bj);
+          const double* Bd = &blocks[(size_t)W.pat_slot[bi][e] * mbs * mbs];
           for (int i = 0; i < ni; ++i) { double sacc = 0; for (int j = 0; j < nj; ++j) sacc += Bd[i * mbs + j] * x[oj + j]; out[oi + i] += sacc; }
         }
       }
@@ -748,6 +833,9 @@ bool solve_schur(const Problem& P, const std::vector<BlockJ>& B, const double* D
   for (int t = 0; t < nt; ++t)
     if (t < rb || t >= re) y[t] = yc[cidx(t)];
   // back-substitution: y_p = L^-T (t_p - What^T y_c)
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads)
+#endif
   for (int p = 0; p < nP; ++p) {
     if (!pok[p]) { y[rb + 3 * p] = y[rb + 3 * p + 1] = y[rb + 3 * p + 2] = 0; continue; }
     const double* L = &Lp[(size_t)p * 6];
@@ -756,7 +844,7 @@ bool solve_schur(const Problem& P, const std::vector<BlockJ>& B, const double* D
       const BlockJ& b = B[k];
       double E[2][3] = {{0, 0, 0}, {0, 0, 0}}, fy[2] = {0, 0};
       for (int a = 0; a < b.nc; ++a) {
-        if (b.col[a] >= rb && b.col[a] < re) { int e = (b.col[a] - rb) % 3; E[0][e] = b.J[0][a]; E[1][e] = b.J[1][a]; }
+        if (is_ray(b.col[a])) { int e = (b.col[a] - rb) % 3; E[0][e] = b.J[0][a]; E[1][e] = b.J[1][a]; }
         else { fy[0] += b.J[0][a] * y[b.col[a]]; fy[1] += b.J[1][a] * y[b.col[a]]; }
       }
       for (int j = 0; j < 3; ++j) acc[j] += E[0][j] * fy[0] + E[1][j] * fy[1];  // W^T y_c = E^T F y_c

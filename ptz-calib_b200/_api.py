@@ -72,7 +72,7 @@ class BAHandle:
         lib.check(lib.load().ptzba_get_stage_times(self._h, C.byref(t)), "ptzba_get_stage_times")
         out = dict(ms_run=t.ms_run, lm_iterations=t.lm_iterations, pcg_iterations=t.pcg_iterations, jacobian_evals=t.jacobian_evals,
                    cost_evals=t.cost_evals, kernels={})
-        for i, name in enumerate(abi.KERNEL_NAMES[:15]):
+        for i, name in enumerate(abi.KERNEL_NAMES[:16]):
             if t.launches[i]:
                 out["kernels"][name] = dict(ms=float(t.ms_kernel[i]), launches=int(t.launches[i]), stage=abi.KERNEL_STAGE[name])
         out["launches_total"] = sum(k["launches"] for k in out["kernels"].values())

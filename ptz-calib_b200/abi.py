@@ -118,9 +118,9 @@ class BAEvalOutC(C.Structure):
 
 
 KERNEL_NAMES = ["view_prep", "resjac", "view_finalize", "track_accum", "pts", "track_solve", "schur_diag", "schur_offdiag", "precond", "pcg",
-                "track_backsub", "cam_update", "cost", "scalars", "allreduce", "_"]
+                "track_backsub", "cam_update", "cost", "scalars", "allreduce", "deflate"]
 KERNEL_STAGE = {"view_prep": 1, "resjac": 1, "view_finalize": 1, "track_accum": 1, "pts": 1, "track_solve": 2, "schur_diag": 2, "schur_offdiag": 2,
-                "precond": 2, "pcg": 3, "track_backsub": 4, "cam_update": 4, "cost": 4, "scalars": 4, "allreduce": 2}
+                "precond": 2, "pcg": 3, "track_backsub": 4, "cam_update": 4, "cost": 4, "scalars": 4, "allreduce": 2, "deflate": 3}
 
 
 class StageTimesC(C.Structure):

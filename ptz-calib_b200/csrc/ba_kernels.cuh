@@ -500,7 +500,8 @@ __global__ void __launch_bounds__(256, PTZ_OD_MINB) k_schur_offdiag(int nub, con
 //
 // k_precond: Linv_c (explicit inverse of the Cholesky factor of every diagonal block)
 template <int NCL>
-__global__ void k_precond(int V, const int* __restrict__ diag_pos, const double* __restrict__ Sval, double* __restrict__ Linv, int* __restrict__ fail) {
+__global__ void k_precond(int V, const int* __restrict__ diag_pos, const double* __restrict__ Sval, double* __restrict__ Linv, int* __restrict__ fail,
+                          double* __restrict__ Lfac /* the factor itself (deflation basis scaling), or nullptr */) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
   double A[NCL * NCL];
@@ -511,7 +512,12 @@ __global__ void k_precond(int V, const int* __restrict__ diag_pos, const double*
   if (!chol_n(A, NCL, NCL)) {
     atomicExch(fail, 2);
     for (int i = 0; i < NCL * NCL; ++i) M[i] = (i / NCL == i % NCL) ? 1.0 : 0.0;
+    if (Lfac) for (int i = 0; i < NCL * NCL; ++i) Lfac[(size_t)v * NCL * NCL + i] = (i / NCL == i % NCL) ? 1.0 : 0.0;
     return;
+  }
+  if (Lfac) {
+#pragma unroll
+    for (int i = 0; i < NCL * NCL; ++i) Lfac[(size_t)v * NCL * NCL + i] = (i % NCL <= i / NCL) ? A[i] : 0.0;
   }
   // X = L^-1 by forward substitution, column by column (lower triangular)
   for (int c = 0; c < NCL; ++c) {
@@ -670,6 +676,20 @@ __global__ void k_unscale(int V, int nb, const double* __restrict__ Linv, const 
 // PTZ_CG_VRANKS=k (debug) runs the same protocol on ONE GPU with the grid split into k virtual ranks.
 // -------------------------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
+// Deflation (KD > 0): a small basis W (KD vectors: Ritz vectors harvested from the residual history of the first solve of a run)
+// is projected out of the Krylov space -- the handful of tiny eigenvalues of S~ (global gauge rotations and the smooth bending
+// modes of the view graph) are what the plain iteration spends most of its steps on.  Saad/Yeung/Erhel/Guyomarc'h's deflated
+// CG in the single-reduction form:
+//     mu = E^-1 (AW)^T r            E = W^T S~ W   (KD x KD, factored once per solve)
+//     p  = r + beta p - W mu ;  s = S~ p = w + beta s - (AW) mu ;  x += alpha p ;  r' = r - alpha s
+//     (p, S~ p) = delta - beta gamma / alpha_prev - mu^T nu         nu = (AW)^T r rides in the ONE fused reduction (KD + 2 values)
+// The single grid barrier per iteration survives: a neighbour's r' is still recomputed from its OLD (r, w, s) alone, and the
+// part of it that depends on mu is added by the owner of the row through Z = S~ (S~ W), precomputed once per solve:
+//     w'_i = sum_j B_ij [ r_j - alpha (w_j + beta s_j) ]  +  alpha (Z mu)_i
+// (validated statement for statement in tests/scripts/deflated_cg_kernel_model.py).
+constexpr int kDeflK = 16;
+constexpr int kCgMaxVals = 2 + kDeflK;
+constexpr int kCgMaxCtas = 192;  // CTAs per rank at most (one per SM): bounds the shared-memory copy of the reduction partials
 struct CgArgs {
   int V, nb, n;            // n = V*NCL + nb
   const int* rowptr; const int* col; const double* Sval;   // col: bit 31 set = the column is owned by another rank than the row
@@ -684,15 +704,24 @@ struct CgArgs {
   int slots_per_rank;
   double* p;               // search direction (every row has one owner)
   int smem_blocks;         // blocks of S (and their column indices) each warp keeps in shared memory for the whole solve
+  int smem_defl_rows;      // rows per warp whose deflation data (W, AW, Z entries) live in shared memory as well
   int debug;               // timing experiments only (PTZ_CG_DEBUG): 1 = skip the sparse product, 2 = skip the grid barrier
   int max_iter; double tol;
   int* out_info;           // [0] iterations, [1] status (0 converged, 1 hit cap, 2 breakdown, 3 peer timeout)
   double* out_res;         // [0] |r~| / |b~|
+  // deflation (KD > 0): W, AW = S~ W, Z = S~ AW as [n][KD]; Einv [KD*KD]; dscal = { |b~|^2, basis usable (1) or not (0) }
+  const double* dW; const double* dAW; const double* dZ; const double* dEinv; const double* dscal;
+  // residual history of an undeflated solve (harvested into the deflation basis by the host afterwards): hist [hist_cap][n],
+  // abg [.. ][3] = alpha, beta, gamma of every iteration.  nullptr = off
+  double* hist; int hist_cap; double* abg;
 };
 // arena control block (u64 words): [0] barrier arrival counter of the single-GPU path (never reset), [1] arrivals consumed by
 // the barriers passed so far, [2] next unused LL tag (the same on every rank; carried from solve to solve)
 constexpr size_t kArenaCtrlBytes = 256;
-constexpr size_t kSlotBytes = 32;
+// reduction slots: per-CTA partials [2][NV][G] doubles, then (multi-rank) LL rank totals [2][W][NV] x 16 bytes
+__host__ __device__ constexpr size_t cg_slot_region_bytes(int ctas) {
+  return 2 * (size_t)kCgMaxVals * ctas * sizeof(double) + 2 * (size_t)kMaxPeers * kCgMaxVals * 16;
+}
 constexpr long long kPeerTimeoutCycles = 40000000000ll;  // ~20 s
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -700,32 +729,65 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// single GPU: block partial -> slot, counter barrier, then every warp sums all slots in the same order
-__device__ __forceinline__ void grid_reduce2(const CgArgs& A, double& a, double& b, int parity, unsigned long long& arrived, double (*sred)[2]) {
+// CTA-level part of both reductions: v[0], v[1] may live in any lane, v[2..] only in the first 8 lanes of a warp (the lanes
+// that own a row entry).  Leaves the CTA totals of the NV values in sred[0..NV) (valid for warp 0 after its __syncwarp).
+template <int NV>
+__device__ __forceinline__ void cta_reduceN(double (&v)[NV], double* sred /* [nwarp][NV] */) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  a = warp_sum(a); b = warp_sum(b);
-  if (lane == 0) { sred[wid][0] = a; sred[wid][1] = b; }
-  __syncthreads();
-  double2* buf = reinterpret_cast<double2*>(A.arena[0] + A.off_partial) + (size_t)(parity & 1) * gridDim.x;
-  if (threadIdx.x == 0) {
-    double s0 = 0, s1 = 0;
-    for (int w = 0; w < nwarp; ++w) { s0 += sred[w][0]; s1 += sred[w][1]; }
-    __stcg(buf + blockIdx.x, make_double2(s0, s1));
-    // release-increment: orders this CTA's writes (published to thread 0 by the barrier above) before the arrival
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(A.arena[0]);
-    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" :: "l"(bar) : "memory");
-    const unsigned long long target = arrived + gridDim.x;
-    while (ld_acquire_u64(bar) < target) { }
+  const double a = warp_sum(v[0]), b = warp_sum(v[1]);
+  if (lane == 0) { sred[wid * NV] = a; sred[wid * NV + 1] = b; }
+  if constexpr (NV > 2) {
+    // reduce-scatter over the 8-lane group: 8 + 4 + 2 shuffles instead of 3 x 16; lane l ends up with elements e0, e0 + 1
+    constexpr int KD = NV - 2;
+    static_assert(KD == 16, "deflation width is 16");
+    double u[KD];
+#pragma unroll
+    for (int i = 0; i < KD; ++i) u[i] = v[2 + i];
+    WarpRS<KD, 4>::run(u, lane);
+    const int e0 = ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
+    if (lane < 8) { sred[wid * NV + 2 + e0] = u[0]; sred[wid * NV + 2 + e0 + 1] = u[1]; }
   }
   __syncthreads();
-  arrived += gridDim.x;
-  double s0 = 0, s1 = 0;
+  if (threadIdx.x < NV) {
+    double s = 0;
+    for (int w = 0; w < nwarp; ++w) s += sred[w * NV + threadIdx.x];
+    v[0] = s;  // thread c holds the CTA total of value c
+  }
+}
+// single GPU: CTA partials -> value-major slots, counter barrier; then ALL partials are fetched at once (one L2 round trip
+// for the whole CTA) into shared memory and the warps share the NV sums between them
+template <int NV>
+__device__ __forceinline__ void grid_reduceN(const CgArgs& A, double (&v)[NV], int parity, unsigned long long& arrived, double* sred, double* s_out,
+                                             double* s_flat /* [NV * G] */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5, G = gridDim.x;
+  cta_reduceN<NV>(v, sred);
+  double* buf = reinterpret_cast<double*>(A.arena[0] + A.off_partial) + (size_t)(parity & 1) * NV * G;
+  if (wid == 0) {
+    if (lane < NV) __stcg(buf + (size_t)lane * G + blockIdx.x, v[0]);
+    __syncwarp();  // the NV stores happen-before lane 0's release below
+    if (lane == 0) {
+      unsigned long long* bar = reinterpret_cast<unsigned long long*>(A.arena[0]);
+      asm volatile("red.release.gpu.global.add.u64 [%0], 1;" :: "l"(bar) : "memory");
+      const unsigned long long target = arrived + (unsigned long long)G;
+      while (ld_acquire_u64(bar) < target) { }
+    }
+  }
+  __syncthreads();
+  arrived += (unsigned long long)G;
   // every thread acquires: its later plain (L1-cached) loads must not be served from lines older than this barrier
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
-  for (int i = lane; i < (int)gridDim.x; i += 32) { const double2 v = __ldcg(buf + i); s0 += v.x; s1 += v.y; }
+  const int tot = NV * G;
+#pragma unroll 4
+  for (int e = threadIdx.x; e < tot; e += blockDim.x) s_flat[e] = __ldcg(buf + e);
+  __syncthreads();
+  for (int c = wid; c < NV; c += nwarp) {
+    double s = 0;
+    for (int i = lane; i < G; i += 32) s += s_flat[c * G + i];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
-  a = s0; b = s1;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_out[c] = s;
+  }
+  __syncthreads();
 }
 
 // ---- LL words
@@ -740,75 +802,83 @@ __device__ __forceinline__ bool ll_load(const ulonglong2* src, unsigned int tag,
   v = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
   return (unsigned int)(lo >> 32) == tag && (unsigned int)(hi >> 32) == tag;
 }
-// multi-rank reduction + barrier, two levels.  Inside a rank: plain partial + acq_rel arrival counter; the LAST CTA to arrive
-// sums the rank's partials in CTA order and pushes the rank total as LL words into the rank's slot on every rank (lane k ->
-// rank k).  Across ranks: every CTA polls the W local rank slots and adds them in rank order -- bit-identical totals on every
-// CTA of every rank.  sys_release: make this CTA's earlier PLAIN stores to peer memory visible first (end-of-solve push of
-// x).  Returns false on a peer timeout.
-__device__ __forceinline__ bool ll_reduce2(const CgArgs& A, double& a, double& b, int parity, unsigned int tag, int my_rank, int cta, int G, int W,
-                                           bool sys_release, unsigned long long& arrived, double (*sred)[2], double* s_tot) {
+// multi-rank reduction + barrier, two levels.  Inside a rank: plain partials + acq_rel arrival counter; the LAST CTA to arrive
+// fetches the rank's partials (all its threads, one L2 round trip), sums them in CTA order and pushes the NV rank totals as LL
+// words into the rank's slots on every rank.  Across ranks: the first W x NV threads of every CTA poll one local slot each; the
+// totals are added in rank order -- bit-identical on every CTA of every rank.  sys_release: make this CTA's earlier PLAIN stores
+// to peer memory visible first (end-of-solve push of x).  Totals in s_out[0..NV); returns false on a peer timeout.
+template <int NV>
+__device__ __forceinline__ bool ll_reduceN(const CgArgs& A, double (&v)[NV], int parity, unsigned int tag, int my_rank, int cta, int G, int W,
+                                           bool sys_release, unsigned long long& arrived, double* sred, double* s_out, double* s_part /* [kMaxPeers*NV] */,
+                                           double* s_flat /* [NV * G] */, int* s_flag) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  a = warp_sum(a); b = warp_sum(b);
-  if (lane == 0) { sred[wid][0] = a; sred[wid][1] = b; }
-  __syncthreads();
+  cta_reduceN<NV>(v, sred);
   char* const mine = A.arena[my_rank];
-  // slots region: [2][G] plain CTA partials (double2), then [2][W] LL rank totals (2 x 16 bytes each)
-  double2* lbuf = reinterpret_cast<double2*>(mine + A.off_partial) + (size_t)(parity & 1) * G;
-  const size_t roff = A.off_partial + 2 * (size_t)G * sizeof(double2) + (size_t)(parity & 1) * W * kSlotBytes;
+  double* lbuf = reinterpret_cast<double*>(mine + A.off_partial) + (size_t)(parity & 1) * NV * G;
+  const size_t roff = A.off_partial + 2 * (size_t)NV * G * sizeof(double) + (size_t)(parity & 1) * W * NV * 16;
   if (wid == 0) {
-    unsigned long long old = 0;
+    if (lane < NV) __stcg(lbuf + (size_t)lane * G + cta, v[0]);
+    __syncwarp();
     if (lane == 0) {
-      double s0 = 0, s1 = 0;
-      for (int w = 0; w < nwarp; ++w) { s0 += sred[w][0]; s1 += sred[w][1]; }
-      __stcg(lbuf + cta, make_double2(s0, s1));
+      unsigned long long old = 0;
       if (sys_release) asm volatile("fence.acq_rel.sys;" ::: "memory");
-      // arrival: releases this CTA's writes (published to this thread by the barrier above), acquires those of earlier arrivers
+      // arrival: releases this CTA's writes, acquires those of earlier arrivers
       asm volatile("atom.acq_rel.gpu.global.add.u64 %0, [%1], 1;" : "=l"(old) : "l"(reinterpret_cast<unsigned long long*>(mine)) : "memory");
+      s_flag[0] = (old + 1ull == arrived + (unsigned long long)G) ? 1 : 0;  // last CTA of this rank
+      s_flag[1] = 1;                                                        // no timeout so far
     }
-    old = __shfl_sync(0xffffffffu, old, 0);
-    if (old + 1ull == arrived + (unsigned long long)G) {  // last CTA of this rank
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      double t0 = 0, t1 = 0;
-      for (int i = lane; i < G; i += 32) { const double2 v = __ldcg(lbuf + i); t0 += v.x; t1 += v.y; }
+  }
+  __syncthreads();
+  if (s_flag[0]) {
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    const int tot = NV * G;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) s_flat[e] = __ldcg(lbuf + e);
+    __syncthreads();
+    for (int c = wid; c < NV; c += nwarp) {
+      double t = 0;
+      for (int i = lane; i < G; i += 32) t += s_flat[c * G + i];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { t0 += __shfl_xor_sync(0xffffffffu, t0, o); t1 += __shfl_xor_sync(0xffffffffu, t1, o); }
-      if (lane < W) {
-        ulonglong2* slot = reinterpret_cast<ulonglong2*>(A.arena[lane] + roff + (size_t)my_rank * kSlotBytes);
-        ll_store(slot, t0, tag);
-        ll_store(slot + 1, t1, tag);
-      }
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane < W) ll_store(reinterpret_cast<ulonglong2*>(A.arena[lane] + roff) + (size_t)my_rank * NV + c, t, tag);
     }
-    // all CTAs: wait for the W rank totals
-    double v0 = 0, v1 = 0;
-    int ok = 1;
-    if (lane < W) {
-      const ulonglong2* slot = reinterpret_cast<const ulonglong2*>(mine + roff + (size_t)lane * kSlotBytes);
-      const long long t_begin = clock64();
-      while (!(ll_load(slot, tag, v0) & ll_load(slot + 1, tag, v1))) {
-        if (clock64() - t_begin > kPeerTimeoutCycles) { ok = 0; break; }
-      }
+  }
+  // all CTAs: wait for the W x NV rank totals, one slot per thread
+  if ((int)threadIdx.x < W * NV) {
+    const ulonglong2* slot = reinterpret_cast<const ulonglong2*>(mine + roff) + threadIdx.x;
+    const long long t_begin = clock64();
+    double val = 0;
+    while (!ll_load(slot, tag, val)) {
+      if (clock64() - t_begin > kPeerTimeoutCycles) { s_flag[1] = 0; break; }
     }
-    ok = __all_sync(0xffffffffu, ok);
-    double s0 = 0, s1 = 0;
-    for (int k = 0; k < W; ++k) { s0 += __shfl_sync(0xffffffffu, v0, k); s1 += __shfl_sync(0xffffffffu, v1, k); }
-    if (lane == 0) { s_tot[0] = s0; s_tot[1] = s1; s_tot[2] = ok ? 1.0 : 0.0; }
+    s_part[threadIdx.x] = val;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < NV) {
+    double s = 0;
+    for (int k = 0; k < W; ++k) s += s_part[k * NV + threadIdx.x];
+    s_out[threadIdx.x] = s;
   }
   __syncthreads();
   arrived += (unsigned long long)G;
   // every thread acquires: its later plain (L1-cached) loads must not be served from lines older than this barrier
   if (sys_release) asm volatile("fence.acq_rel.sys;" ::: "memory");
   else asm volatile("fence.acq_rel.gpu;" ::: "memory");
-  a = s_tot[0]; b = s_tot[1];
-  return s_tot[2] != 0.0;
+  return s_flag[1] != 0;
 }
 
-// MAXT = CTA width (256 / 512 / 1024 threads): wide CTAs keep one row per warp on larger systems (one CTA per SM either way)
-template <int NCL, int MAXT, bool MULTI>
+// MAXT = CTA width (256 / 512 threads): wide CTAs keep one row per warp on larger systems (one CTA per SM either way; beyond
+// 16 rows per SM a warp walks several rows).  KD = 0: plain CG; KD = kDeflK: deflated.
+template <int NCL, int MAXT, bool MULTI, int KD>
 __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
-  constexpr int SLOTS = 32 / NCL, NB = NCL * NCL;
+  constexpr int SLOTS = 32 / NCL, NB = NCL * NCL, NV = 2 + KD;
   extern __shared__ double cg_smem[];
-  __shared__ double sred[MAXT / 32][2];
-  __shared__ double s_tot[3];
+  __shared__ double sred[(MAXT / 32) * NV];
+  __shared__ double s_out[NV + 1];
+  __shared__ double s_part[MULTI ? kMaxPeers * NV : 1];
+  __shared__ double s_einv[KD > 0 ? KD * KD : 1];
+  __shared__ double s_flat[NV * kCgMaxCtas];
+  __shared__ int s_flag[2];
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;
   const int la = lane % NCL, ls = lane / NCL;
   const bool lact = lane < SLOTS * NCL;
@@ -837,11 +907,35 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
     for (int e = lane; e < take; e += 32) cs[ncached + e] = A.col[b0 + e];
     ncached += take;
   }
+  bool defl = false;
+  // deflation data of the first `dcap` rows of every warp: [row][W | AW | Z][KD][NCL] (an entry's KD values at stride NCL:
+  // the NCL owner lanes read consecutive words)
+  const int dcap = KD > 0 ? A.smem_defl_rows : 0;
+  double* Ds = cg_smem + (((size_t)wpb * cap * (NB * sizeof(double) + sizeof(int)) + 15) / 16) * 2 + (size_t)wid * dcap * 3 * KD * NCL;
+  if (KD > 0) {
+    defl = A.dscal[1] != 0.0;  // the basis passed the Cholesky of E (else: plain CG from x = 0)
+    for (int e = threadIdx.x; e < KD * KD; e += blockDim.x) s_einv[e] = A.dEinv[e];
+    int ri = 0;
+    for (int sl = wid; sl < per && ri < dcap; sl += wpb, ++ri) {
+      const int slot = cta0 + sl;
+      if (slot >= min(V, slot1)) break;
+      const size_t g0 = (size_t)A.order[slot] * NCL * KD;
+      for (int e = lane; e < NCL * KD; e += 32) {
+        const int a = e / KD, dd = e % KD;
+        double* q = Ds + (size_t)ri * 3 * KD * NCL + dd * NCL + a;
+        q[0] = A.dW[g0 + e]; q[KD * NCL] = A.dAW[g0 + e]; q[2 * KD * NCL] = A.dZ[g0 + e];
+      }
+    }
+    __syncthreads();
+  }
   __syncwarp();
   unsigned long long* ctrl = reinterpret_cast<unsigned long long*>(mine);
   unsigned long long arrived = ctrl[1];             // single GPU: arrivals consumed so far on this arena
   const unsigned int tag0 = (unsigned int)ctrl[2];  // multi: first LL tag of this solve (same on every rank)
   double alpha = 0.0, beta = 0.0, gamma_old = 0.0, gamma0 = 0.0, gamma_last = 0.0;
+  double mus[KD > 0 ? KD : 1];  // mu, replicated in every lane
+#pragma unroll
+  for (int dd = 0; dd < (KD > 0 ? KD : 1); ++dd) mus[dd] = 0.0;
   size_t off_o = A.off_st0, off_n = A.off_st1;  // previous state (read by everyone) / next state (written by the owner only)
   double* const xl = reinterpret_cast<double*>(mine + A.off_x);
   int it = 0, status = 1;
@@ -854,26 +948,57 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
     const size_t off_lln = (it & 1) ? A.off_ll1 : A.off_ll0;
     const unsigned int tag_rd = tag0 + (unsigned int)it, tag_wr = tag_rd + 1u;
     const bool use_ll = MULTI && it > 0;  // iteration 0 reads the initial state, which every rank computed for all rows
-    double g = 0, d = 0;
+    double acc[NV];  // acc[0] = (r',r'), acc[1] = (w',r'), acc[2..] = (AW)^T r'
+#pragma unroll
+    for (int c = 0; c < NV; ++c) acc[c] = 0.0;
     int bi = 0;  // running index of this warp's blocks
+    int ri = -1; // running index of this warp's rows
     for (int sl = wid; sl < per; sl += wpb) {
       const int slot = cta0 + sl;
       if (slot >= slot1) break;
       const int row = slot < V ? A.order[slot] : V;
+      ++ri;
       if (row < V) {
-        double rn = 0, s_n = 0;
+        double rn = 0, s_n = 0, zm = 0;
         unsigned int pmask = 0;
         if (MULTI) pmask = A.peer_mask[row];
         if (lane < NCL) {
           const int i = row * NCL + lane;
           const double ro = __ldcg(so + (row * 3 + 0) * NCL + lane), wo = __ldcg(so + (row * 3 + 1) * NCL + lane), s_o = __ldcg(so + (row * 3 + 2) * NCL + lane);
-          const double pn = ro + beta * A.p[i];
+          double pn = ro + beta * A.p[i];
           s_n = wo + beta * s_o;
+          if (KD > 0) {
+            // deflation terms of this row entry: (W mu)_i, (AW mu)_i, (Z mu)_i
+            double wm = 0, awm = 0;
+            if (ri < dcap) {
+              const double* q = Ds + (size_t)ri * 3 * KD * NCL + lane;
+#pragma unroll
+              for (int dd = 0; dd < KD; ++dd) {
+                wm += q[dd * NCL] * mus[dd];
+                awm += q[(KD + dd) * NCL] * mus[dd];
+                zm += q[(2 * KD + dd) * NCL] * mus[dd];
+              }
+            } else {
+              const double2* Wi = reinterpret_cast<const double2*>(A.dW + (size_t)i * KD);
+              const double2* AWi = reinterpret_cast<const double2*>(A.dAW + (size_t)i * KD);
+              const double2* Zi = reinterpret_cast<const double2*>(A.dZ + (size_t)i * KD);
+#pragma unroll
+              for (int dd = 0; dd < KD / 2; ++dd) {
+                const double2 a = __ldg(Wi + dd), b = __ldg(AWi + dd), c = __ldg(Zi + dd);
+                wm += a.x * mus[2 * dd] + a.y * mus[2 * dd + 1];
+                awm += b.x * mus[2 * dd] + b.y * mus[2 * dd + 1];
+                zm += c.x * mus[2 * dd] + c.y * mus[2 * dd + 1];
+              }
+            }
+            pn -= wm;
+            s_n -= awm;
+          }
           A.p[i] = pn;
           xl[i] += alpha * pn;
           rn = ro - alpha * s_n;
           sn[(row * 3 + 0) * NCL + lane] = rn;
           sn[(row * 3 + 2) * NCL + lane] = s_n;
+          if (A.hist != nullptr && it < A.hist_cap) A.hist[(size_t)it * A.n + i] = rn;
           if (MULTI) {  // r and s leave now, so that the remote stores drain behind the sparse product
             for (int k = 0; k < W; ++k)
               if ((pmask >> k) & 1u) {
@@ -970,15 +1095,31 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
               for (int j = 0; j < nb; ++j) tot += strip[j] * (__ldcg(q + j) - alpha * (__ldcg(q + nb + j) + beta * __ldcg(q + 2 * nb + j)));
             }
           }
+          if (KD > 0) tot += alpha * zm;  // the neighbours' deflation terms, through Z = S~ (S~ W)
           sn[(row * 3 + 1) * NCL + lane] = tot;
           if (MULTI) {
             for (int k = 0; k < W; ++k)
               if ((pmask >> k) & 1u)
                 ll_store(reinterpret_cast<ulonglong2*>(A.arena[k] + off_lln) + (size_t)row * (3 * NCL) + NCL + lane, tot, tag_wr);
           }
-          g += rn * rn; d += tot * rn;
+          acc[0] += rn * rn; acc[1] += tot * rn;
+          if (KD > 0) {
+            if (ri < dcap) {
+              const double* q = Ds + (size_t)ri * 3 * KD * NCL + KD * NCL + lane;
+#pragma unroll
+              for (int dd = 0; dd < KD; ++dd) acc[2 + dd] += q[dd * NCL] * rn;
+            } else {
+              const double2* AWi = reinterpret_cast<const double2*>(A.dAW + (size_t)(row * NCL + lane) * KD);
+#pragma unroll
+              for (int dd = 0; dd < KD / 2; ++dd) {
+                const double2 b = __ldg(AWi + dd);
+                acc[2 + 2 * dd] += b.x * rn;
+                acc[2 + 2 * dd + 1] += b.y * rn;
+              }
+            }
+          }
         }
-      } else if (lane < nb) {  // dense border row (single rank only)
+      } else if (lane < nb) {  // dense border row (single rank only, never deflated)
         const int i = boff + lane;
         const double* q = so + 3 * (size_t)boff;
         const double ro = __ldcg(q + lane), wo = __ldcg(q + nb + lane), s_o = __ldcg(q + 2 * nb + lane);
@@ -996,29 +1137,48 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
             tot += A.C[((size_t)k * NCL + a) * nb + lane] * (__ldcg(qc + a) - alpha * (__ldcg(qc + NCL + a) + beta * __ldcg(qc + 2 * NCL + a)));
         }
         qn[nb + lane] = tot;
-        g += rn * rn; d += tot * rn;
+        acc[0] += rn * rn; acc[1] += tot * rn;
       }
     }
-    if (A.debug & 2) { g = 1.0 / (it + 1.0); d = 1.0; __syncthreads(); }
+    if (A.debug & 2) { s_out[0] = 1.0 / (it + 1.0); s_out[1] = 1.0; __syncthreads(); }
     else if (MULTI) {
-      if (!ll_reduce2(A, g, d, it, tag_wr, my_rank, cta, G, W, false, arrived, sred, s_tot)) peers_ok = false;
+      if (!ll_reduceN<NV>(A, acc, it, tag_wr, my_rank, cta, G, W, false, arrived, sred, s_out, s_part, s_flat, s_flag)) peers_ok = false;
       if (__syncthreads_or(peers_ok ? 0 : 1)) { status = 3; break; }
-    } else grid_reduce2(A, g, d, it, arrived, sred);
+    } else grid_reduceN<NV>(A, acc, it, arrived, sred, s_out, s_flat);
+    const double g = s_out[0], d = s_out[1];
+    // mu = E^-1 nu (lane c < KD computes mu_c, then every lane collects the vector) and mu^T nu, identically in every warp
+    double mu_nu = 0.0;
+    if (KD > 0) {
+      double mu_l = 0.0, prod = 0.0;
+      if (defl && lane < KD) {
+#pragma unroll
+        for (int dd = 0; dd < KD; ++dd) mu_l += s_einv[lane * KD + dd] * s_out[2 + dd];
+        prod = mu_l * s_out[2 + lane];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) prod += __shfl_xor_sync(0xffffffffu, prod, o);
+      mu_nu = prod;
+#pragma unroll
+      for (int dd = 0; dd < KD; ++dd) mus[dd] = __shfl_sync(0xffffffffu, mu_l, dd);
+    }
+    // (s_out is next written behind the barriers of the next reduction: no extra barrier needed here)
     gamma_last = g;
     if (it == 0) {
-      gamma0 = g;
+      gamma0 = (KD > 0) ? A.dscal[0] : g;  // deflated: x0 = W E^-1 W^T b~ already took part of b~ away; measure against |b~|
       if (!(g > 0)) { status = 0; break; }          // zero right-hand side: x = 0
-      if (!(d > 0) || !isfinite(d)) { status = 2; break; }
-      beta = 0.0; alpha = g / d;
+      const double den = d - mu_nu;
+      if (!(den > 0) || !isfinite(den)) { status = 2; break; }
+      beta = 0.0; alpha = g / den;
     } else {
       if (sqrt(g) <= A.tol * sqrt(gamma0)) { status = 0; break; }
       if (!isfinite(g) || !isfinite(d)) { status = 2; break; }
       if (it >= A.max_iter) { status = 1; break; }
       beta = g / gamma_old;
-      const double den = d - beta * g / alpha;
+      const double den = d - beta * g / alpha - mu_nu;
       if (!(den > 0)) { status = 2; break; }
       alpha = g / den;
     }
+    if (A.abg != nullptr && cta == 0 && threadIdx.x == 0 && it < A.hist_cap) { A.abg[3 * it] = alpha; A.abg[3 * it + 1] = beta; A.abg[3 * it + 2] = g; }
     gamma_old = g;
     const size_t t = off_o; off_o = off_n; off_n = t;
   }
@@ -1035,8 +1195,10 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
           if (k != my_rank) reinterpret_cast<double*>(A.arena[k] + A.off_x)[row * NCL + lane] = v;
       }
     }
-    double z0 = 0, z1 = 0;
-    if (!ll_reduce2(A, z0, z1, it + 1, tag0 + (unsigned int)it + 2u, my_rank, cta, G, W, true, arrived, sred, s_tot)) status = 3;
+    double z[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) z[c] = 0.0;
+    if (!ll_reduceN<NV>(A, z, it + 1, tag0 + (unsigned int)it + 2u, my_rank, cta, G, W, true, arrived, sred, s_out, s_part, s_flat, s_flag)) status = 3;
   }
   if (cta == 0 && threadIdx.x == 0) {
     ctrl[1] = arrived;
@@ -1046,6 +1208,207 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
       A.out_res[0] = gamma0 > 0 ? sqrt(gamma_last / gamma0) : 0.0;
     }
   }
+}
+
+// ---- deflation: the small kernels around k_cg<.., KD = kDeflK> (once per linear solve; the basis itself once per run) ---------
+// W~ = L^T W_y per view block: the basis is kept in the unscaled unknowns y and follows every solve's own block-Jacobi scaling
+// (y~ = L^T y).  trans_inv: W_y = Linv^T W~ instead (harvest time).  One thread per (view, column).
+template <int NCL>
+__global__ void k_defl_scale_basis(int V, const double* __restrict__ T /* L, or Linv */, const double* __restrict__ in, double* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = idx / kDeflK, c = idx % kDeflK;
+  if (v >= V) return;
+  const double* L = T + (size_t)v * NCL * NCL;
+  double x[NCL];
+#pragma unroll
+  for (int a = 0; a < NCL; ++a) x[a] = in[((size_t)v * NCL + a) * kDeflK + c];
+#pragma unroll
+  for (int a = 0; a < NCL; ++a) {
+    double s = 0;
+#pragma unroll
+    for (int q = a; q < NCL; ++q) s += L[q * NCL + a] * x[q];  // (T^T x)_a, T lower triangular
+    out[((size_t)v * NCL + a) * kDeflK + c] = s;
+  }
+}
+// Out = S~ In for the kDeflK columns at once.  One warp per row: lane = column + 16 * half, the two halves take alternate
+// blocks of the row, four blocks in flight per half (the walk is latency-bound: index -> gather).  Rows of other ranks (owner
+// != my_rank >= 0) are written as zeros: the caller sums the ranks' pieces.  Fixed summation order.
+template <int NCL>
+__global__ void __launch_bounds__(256) k_defl_spmm(int V, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ Sval,
+                                                   const double* __restrict__ in, double* __restrict__ out, const unsigned char* __restrict__ row_owner,
+                                                   int my_rank) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31, c = lane & (kDeflK - 1), h = lane >> 4;
+  static_assert(kDeflK == 16, "lane layout");
+  if (r >= V) return;
+  double acc[NCL];
+#pragma unroll
+  for (int a = 0; a < NCL; ++a) acc[a] = 0.0;
+  if (my_rank < 0 || row_owner[r] == my_rank) {
+    const int k1 = rowptr[r + 1];
+    for (int k = rowptr[r] + h; k < k1; k += 8) {
+      int j[4];
+      double x[4][NCL];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) j[u] = (k + 2 * u < k1) ? col[k + 2 * u] : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int b = 0; b < NCL; ++b) x[u][b] = j[u] >= 0 ? in[((size_t)j[u] * NCL + b) * kDeflK + c] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j[u] < 0) continue;
+        const double* B = Sval + (size_t)(k + 2 * u) * NCL * NCL;
+#pragma unroll
+        for (int a = 0; a < NCL; ++a)
+#pragma unroll
+          for (int b = 0; b < NCL; ++b) acc[a] += B[a * NCL + b] * x[u][b];
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NCL; ++a) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], 16);
+  if (h == 0) {
+#pragma unroll
+    for (int a = 0; a < NCL; ++a) out[((size_t)r * NCL + a) * kDeflK + c] = acc[a];
+  }
+}
+// E = W^T (AW), nu0 = W^T b~, |b~|^2 as per-CTA partial sums over chunks of 256 unknowns (b~ = the r component of the initial CG
+// state): partial[chunk][0..K*K) = E, [K*K..K*K+K) = nu0, [K*K+K] = |b~|^2.  Also keeps a copy of b~ for an undeflated retry.
+constexpr int kDeflGramVals = kDeflK * kDeflK + kDeflK + 1;
+constexpr int kDeflGramChunk = 128;  // unknowns per CTA (two 16 KB panels in shared memory)
+template <int NCL>
+__global__ void __launch_bounds__(256) k_defl_gram(int V, const double* __restrict__ Wm, const double* __restrict__ AW, const double* __restrict__ st0,
+                                                   double* __restrict__ partial, double* __restrict__ b_copy) {
+  __shared__ double sw[kDeflGramChunk * kDeflK], sa[kDeflGramChunk * kDeflK], sb[kDeflGramChunk];
+  const int n = V * NCL, i0 = blockIdx.x * kDeflGramChunk, cnt = min(kDeflGramChunk, n - i0), t = threadIdx.x;
+  for (int e = t; e < kDeflGramChunk * kDeflK; e += 256) {
+    const bool in = e < cnt * kDeflK;
+    sw[e] = in ? Wm[(size_t)i0 * kDeflK + e] : 0.0;
+    sa[e] = in ? AW[(size_t)i0 * kDeflK + e] : 0.0;
+  }
+  if (t < kDeflGramChunk) {
+    const int i = i0 + t;
+    const double bt = t < cnt ? st0[((size_t)(i / NCL) * 3) * NCL + (i % NCL)] : 0.0;
+    sb[t] = bt;
+    if (t < cnt) b_copy[i] = bt;
+  }
+  __syncthreads();
+  double* out = partial + (size_t)blockIdx.x * kDeflGramVals;
+  {
+    const int c = t / kDeflK, d = t % kDeflK;
+    double s = 0;
+    for (int i = 0; i < kDeflGramChunk; ++i) s += sw[i * kDeflK + c] * sa[i * kDeflK + d];
+    out[t] = s;
+  }
+  if (t < kDeflK) {
+    double s = 0;
+    for (int i = 0; i < kDeflGramChunk; ++i) s += sw[i * kDeflK + t] * sb[i];
+    out[kDeflK * kDeflK + t] = s;
+  } else if (t == 32) {
+    double s = 0;
+    for (int i = 0; i < kDeflGramChunk; ++i) s += sb[i] * sb[i];
+    out[kDeflK * kDeflK + kDeflK] = s;
+  }
+}
+// one warp: sums the chunk partials in chunk order, Cholesky of E (symmetrised), Einv, c0 = Einv nu0; dscal[0] = |b~|^2,
+// dscal[1] = 1 when every pivot is safely positive, else 0 (the solve then runs undeflated).  kd <= kDeflK columns are in use;
+// the rest of Einv is zero.
+__global__ void __launch_bounds__(32) k_defl_small(int kd, int nchunk, const double* __restrict__ partial, double* __restrict__ Einv,
+                                                   double* __restrict__ c0, double* __restrict__ dscal) {
+  __shared__ double A[kDeflK * kDeflK], Li[kDeflK * kDeflK], nu[kDeflK];
+  const int lane = threadIdx.x;
+  for (int e = lane; e < kDeflGramVals; e += 32) {
+    double s = 0;
+    for (int c = 0; c < nchunk; ++c) s += partial[(size_t)c * kDeflGramVals + e];
+    if (e < kDeflK * kDeflK) A[e] = s;
+    else if (e < kDeflK * kDeflK + kDeflK) nu[e - kDeflK * kDeflK] = s;
+    else dscal[0] = s;
+  }
+  __syncwarp();
+  for (int e = lane; e < kDeflK * kDeflK; e += 32) {  // symmetrise (lower triangle is what the factorisation reads)
+    const int i = e / kDeflK, j = e % kDeflK;
+    if (i > j) A[e] = 0.5 * (A[i * kDeflK + j] + A[j * kDeflK + i]);
+    Li[e] = 0.0;
+  }
+  __syncwarp();
+  double dmax = 0;
+  for (int j = 0; j < kd; ++j) dmax = fmax(dmax, A[j * kDeflK + j]);
+  int ok = kd > 0 ? 1 : 0;
+  for (int j = 0; j < kd && ok; ++j) {  // column j of L, row `lane`
+    double s = 0;
+    if (lane >= j && lane < kd) {
+      s = A[lane * kDeflK + j];
+      for (int k = 0; k < j; ++k) s -= A[lane * kDeflK + k] * A[j * kDeflK + k];
+    }
+    double dj = __shfl_sync(0xffffffffu, s, j);
+    if (!(dj > 1e-12 * dmax) || !isfinite(dj)) { ok = 0; break; }
+    dj = sqrt(dj);
+    __syncwarp();
+    if (lane == j) A[j * kDeflK + j] = dj;
+    else if (lane > j && lane < kd) A[lane * kDeflK + j] = s / dj;
+    __syncwarp();
+  }
+  // column c of L^-1 by forward substitution (lane c touches only its own column)
+  if (ok && lane < kd) {
+    const int c = lane;
+    for (int i = c; i < kd; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = c; k < i; ++k) s -= A[i * kDeflK + k] * Li[k * kDeflK + c];
+      Li[i * kDeflK + c] = s / A[i * kDeflK + i];
+    }
+  }
+  __syncwarp();
+  // Einv = L^-T L^-1 (into A, and out)
+  double ev[(kDeflK * kDeflK) / 32];
+#pragma unroll
+  for (int q = 0; q < (kDeflK * kDeflK) / 32; ++q) {
+    const int e = lane + 32 * q, i = e / kDeflK, j = e % kDeflK;
+    double s = 0;
+    if (ok) for (int k = max(i, j); k < kd; ++k) s += Li[k * kDeflK + i] * Li[k * kDeflK + j];
+    ev[q] = s;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < (kDeflK * kDeflK) / 32; ++q) { A[lane + 32 * q] = ev[q]; Einv[lane + 32 * q] = ev[q]; }
+  __syncwarp();
+  if (lane < kDeflK) {
+    double s = 0;
+    for (int j = 0; j < kDeflK; ++j) s += A[lane * kDeflK + j] * nu[j];
+    c0[lane] = ok ? s : 0.0;
+  }
+  if (lane == 0) dscal[1] = ok ? 1.0 : 0.0;
+}
+// x0 = W c0, r0 = b~ - (AW) c0 into the initial CG state (every rank, all rows); nothing to do when the basis was rejected
+template <int NCL>
+__global__ void k_defl_start(int V, const double* __restrict__ Wm, const double* __restrict__ AW, const double* __restrict__ c0, const double* __restrict__ dscal,
+                             double* __restrict__ st0, double* __restrict__ x) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V * NCL || dscal[1] == 0.0) return;
+  double xs = 0, rs = 0;
+#pragma unroll
+  for (int c = 0; c < kDeflK; ++c) { xs += Wm[(size_t)i * kDeflK + c] * c0[c]; rs += AW[(size_t)i * kDeflK + c] * c0[c]; }
+  x[i] = xs;
+  st0[((size_t)(i / NCL) * 3) * NCL + (i % NCL)] -= rs;
+}
+// back to the plain initial state (r = b~, w = s = 0, x = p = 0) for an undeflated retry after a breakdown
+template <int NCL>
+__global__ void k_cg_restart(int V, const double* __restrict__ b_copy, double* __restrict__ st0, double* __restrict__ x, double* __restrict__ p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V * NCL) return;
+  const size_t o = ((size_t)(i / NCL) * 3) * NCL + (i % NCL);
+  st0[o] = b_copy[i]; st0[o + NCL] = 0.0; st0[o + 2 * NCL] = 0.0;
+  x[i] = 0.0; p[i] = 0.0;
+}
+// harvest: W~[i][c] = sum_j Y[j][c] hist[j][i]  (Y already carries 1 / |r_j|); rows of other ranks -> 0 (summed by the caller)
+__global__ void k_defl_harvest(int n, int m, int kd, const double* __restrict__ hist, const double* __restrict__ Y /* [m][kDeflK] */,
+                               double* __restrict__ Wt, const unsigned char* __restrict__ row_owner, int ncl, int my_rank) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = idx / kDeflK, c = idx % kDeflK;
+  if (i >= n) return;
+  double s = 0;
+  if (c < kd && (my_rank < 0 || row_owner[i / ncl] == my_rank))
+    for (int j = 0; j < m; ++j) s += Y[(size_t)j * kDeflK + c] * hist[(size_t)j * n + i];
+  Wt[(size_t)i * kDeflK + c] = s;
 }
 
 // -------------------------------------------------------------------------------------------------------------

@@ -17,6 +17,7 @@
 #include "ba_kernels.cuh"
 #include "ba_setup.cuh"
 #include "ba_structure.hpp"
+#include "cg_ritz.hpp"
 
 namespace ptz {
 
@@ -287,11 +288,25 @@ struct BaSolver : BaSolverBase {
   DevBuf<unsigned char> d_cg_mask;      // per row: ranks that own one of its neighbours
   DevBuf<unsigned char> d_cg_owner;     // per row: owning rank
   double* arena_ptr(size_t off) const { return reinterpret_cast<double*>(g_arena.base[cgR] + off); }
-  const void* cg_kernel() const {
-    if (cgW > 1)
-      return cg_wpb == 8 ? (const void*)k_cg<NCL, 256, true> : cg_wpb == 16 ? (const void*)k_cg<NCL, 512, true> : (const void*)k_cg<NCL, 1024, true>;
-    return cg_wpb == 8 ? (const void*)k_cg<NCL, 256, false> : cg_wpb == 16 ? (const void*)k_cg<NCL, 512, false> : (const void*)k_cg<NCL, 1024, false>;
+  int cg_defl_rows = 0;  // rows per warp with their deflation data in shared memory
+  // dynamic shared memory of k_cg: S blocks + column indices (16-byte aligned), then the deflation rows
+  size_t cg_smem_bytes(bool deflated) const {
+    const size_t blocks = (((size_t)cg_wpb * cg_cap * (NCL * NCL * sizeof(double) + sizeof(int)) + 15) / 16) * 16;
+    return blocks + (deflated ? (size_t)cg_wpb * cg_defl_rows * 3 * NCL * kDeflK * sizeof(double) : 0) + 16;
   }
+  template <bool MULTI, int KD>
+  const void* cg_kernel_sel() const { return cg_wpb == 8 ? (const void*)k_cg<NCL, 256, MULTI, KD> : (const void*)k_cg<NCL, 512, MULTI, KD>; }
+  const void* cg_kernel(bool deflated) const {
+    if (cgW > 1) return deflated ? cg_kernel_sel<true, kDeflK>() : cg_kernel_sel<true, 0>();
+    return deflated ? cg_kernel_sel<false, kDeflK>() : cg_kernel_sel<false, 0>();
+  }
+  // ---- deflation of the CG (k_cg<.., KD = kDeflK>): basis harvested from the residual history of the first solve of a run
+  bool defl_enabled = false, have_W = false;
+  int defl_kd = 0, defl_solves = 0, defl_rejects = 0;
+  static constexpr int kHistCap = 320, kMinHarvest = 40;
+  DevBuf<double> d_hist, d_abg, d_Wy, d_Wt, d_AW, d_Z, d_gram, d_Einv, d_c0, d_dscal, d_bcopy, d_Lfac, d_Y;
+  std::vector<double> h_abg;
+  double h_dscal[2] = {0, 0};
 
   // LM state (names follow ceres::internal::TrustRegionMinimizer / LevenbergMarquardtStrategy)
   double radius = 0, decrease_factor = 2.0, x_cost = 0, x_norm = 0, min_cost = 0, initial_cost = 0, grad_max = 0;
@@ -390,7 +405,7 @@ struct BaSolver : BaSolverBase {
     }
     n = V * NCL + nb;
     {
-      // CG launch shape: one CTA per SM, as many warps per CTA (8/16/32) as it takes to give every warp at most one row
+      // CG launch shape: one CTA per SM, as many warps per CTA (8/16) as it takes to give every warp at most one row
       // where possible.  Rows are handed out in Cuthill-McKee order of the view graph, a contiguous run per CTA, so that the
       // rows of a CTA are neighbouring views whose gathers overlap (L1 hits).  Then: how many blocks of S fit 200 KB of smem.
       // Sharded problem: the rows are split across the ranks (a contiguous run of the ordering each), see k_cg.
@@ -406,7 +421,7 @@ struct BaSolver : BaSolverBase {
       cg_slots_per_rank = cdiv(nrows, W);
       const int my0 = R * cg_slots_per_rank, my1 = std::min(nrows, my0 + cg_slots_per_rank);
       const int need = cdiv(cg_slots_per_rank, sms_per_rank);
-      cg_wpb = need <= 8 ? 8 : (need <= 16 ? 16 : 32);
+      cg_wpb = need <= 8 ? 8 : 16;  // beyond 16 rows per SM a warp walks several rows
       cg_grid = std::min(sms_per_rank, cdiv(cg_slots_per_rank, cg_wpb));  // CTAs per rank
       std::vector<int> h_col(ds.nnzb);
       ds.s_col.download(h_col.data(), ds.nnzb, stream);
@@ -463,7 +478,7 @@ struct BaSolver : BaSolverBase {
         d_cg_owner.upload(own8, stream);
       }
       const size_t per_block = NCL * NCL * sizeof(double) + sizeof(int);
-      const int fit = (int)((160 * 1024) / (cg_wpb * per_block));  // leave >= 60 KB of the SM's 228 KB to the L1
+      const int fit = (int)((150 * 1024) / (cg_wpb * per_block));  // leave >= 60 KB of the SM's 228 KB to the L1 (the kernel has ~8 KB of static shared memory)
       cg_cap = std::max(1, std::min(worst, fit));
       if (g_nccl.world > 1) {  // every rank launches the same shape (the slot of a CTA's partial sums is rank * grid + cta)
         DevBuf<double> d_m;
@@ -474,12 +489,19 @@ struct BaSolver : BaSolverBase {
         PTZ_CUDA(cudaStreamSynchronize(stream));
         cg_cap = (int)m[0];
       }
-      const size_t cg_smem = (size_t)cg_wpb * cg_cap * per_block + 16;
-      PTZ_CUDA(cudaFuncSetAttribute(cg_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg_smem));
+      // deflation data of the first rows of every warp go to shared memory too (W, AW, Z entries: 3 * NCL * kDeflK doubles a row)
+      {
+        const size_t left = (size_t)190 * 1024 - std::min((size_t)190 * 1024, cg_smem_bytes(false));
+        const int rows_per_warp = cdiv(cdiv(cg_slots_per_rank, cg_grid), cg_wpb);
+        cg_defl_rows = std::min(rows_per_warp, (int)(left / ((size_t)cg_wpb * 3 * NCL * kDeflK * sizeof(double))));
+      }
+      if (cg_grid > kCgMaxCtas) throw CudaError(PTZ_ERR_UNSUPPORTED, "more SMs than the CG kernel's reduction buffer holds");
+      PTZ_CUDA(cudaFuncSetAttribute(cg_kernel(false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg_smem_bytes(false)));
+      PTZ_CUDA(cudaFuncSetAttribute(cg_kernel(true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg_smem_bytes(true)));
       // arena layout: ctrl | slots [2][W*grid] | st0 [3n] | st1 [3n] | x [n] | LL inboxes ll0, ll1 [V*3*NCL] 16-byte words
       auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
       ar_partial = kArenaCtrlBytes;
-      ar_st0 = al(ar_partial + 2 * (size_t)W * num_sms * kSlotBytes);
+      ar_st0 = al(ar_partial + cg_slot_region_bytes(num_sms));
       ar_st1 = al(ar_st0 + 3 * (size_t)n * sizeof(double));
       ar_x = al(ar_st1 + 3 * (size_t)n * sizeof(double));
       ar_ll0 = al(ar_x + (size_t)n * sizeof(double));
@@ -633,6 +655,22 @@ struct BaSolver : BaSolverBase {
     p_Sval = d_sys.p; p_rhs = p_Sval + (size_t)ds.nnzb * NCL * NCL;
     d_Linv.alloc((size_t)V * NCL * NCL, stream); d_Linv_b.alloc(kMaxBorder * kMaxBorder, stream); d_Sbb.alloc(kMaxBorder * kMaxBorder, stream);
     d_Cs.alloc((size_t)std::max(ncpl, 1) * NCL * std::max(nb, 1), stream);
+    {
+      // deflated CG (camera-only reduced systems of some size; PTZ_CG_DEFLATE=0 switches it off for A/B measurements)
+      const char* e = getenv("PTZ_CG_DEFLATE");
+      defl_enabled = (!e || atoi(e) != 0) && nb == 0 && V >= 64;
+      have_W = false;
+      if (defl_enabled) {
+        const size_t nk = (size_t)V * NCL * kDeflK;
+        d_hist.alloc((size_t)kHistCap * V * NCL, stream);
+        d_abg.alloc(3 * (size_t)kHistCap, stream); d_abg.zero(s);
+        d_Wy.alloc(nk, stream); d_Wt.alloc(nk, stream); d_AW.alloc(nk, stream); d_Z.alloc(nk, stream);
+        d_gram.alloc((size_t)cdiv(V * NCL, kDeflGramChunk) * kDeflGramVals, stream);
+        d_Einv.alloc(kDeflK * kDeflK, stream); d_c0.alloc(kDeflK, stream); d_dscal.alloc(2, stream); d_dscal.zero(s);
+        d_bcopy.alloc((size_t)V * NCL, stream); d_Lfac.alloc((size_t)V * NCL * NCL, stream); d_Y.alloc((size_t)kHistCap * kDeflK, stream);
+        h_abg.assign(3 * (size_t)kHistCap, 0.0);
+      }
+    }
     d_cgp.alloc((size_t)n, stream); d_cgp.zero(s);
     d_y.alloc(n, stream); d_y.zero(s);
     d_pcg_res.alloc(2, stream); d_pcg_info.alloc(2, stream); d_fail.alloc(1, stream); d_fail.zero(s);
@@ -664,6 +702,10 @@ struct BaSolver : BaSolverBase {
     radius = opt.initial_trust_region_radius; decrease_factor = 2.0; reuse_diagonal = false; last_successful = true;
     termination = PTZ_NO_CONVERGENCE;
     log.clear();
+    if (have_W || (defl_enabled && d_hist.n == 0)) {  // every solve harvests its own deflation basis: runs are bit-reproducible
+      have_W = false;
+      if (defl_enabled && d_hist.n == 0) d_hist.alloc((size_t)kHistCap * V * NCL, stream);
+    }
     // kernel timings keep accumulating across resets (bench.py times several solves); see ptzba_get_stage_times
   }
 
@@ -739,6 +781,10 @@ struct BaSolver : BaSolverBase {
     d_scalars.download(h_scalars, S_COUNT, stream);
     d_pcg_info.download(h_info, 2, stream);
     d_fail.download(h_info + 2, 1, stream);
+    if (defl_enabled) {
+      if (!have_W) d_abg.download(h_abg.data(), 3 * (size_t)kHistCap, stream);
+      else d_dscal.download(h_dscal, 2, stream);
+    }
     PTZ_CUDA(cudaStreamSynchronize(stream));
   }
 
@@ -770,7 +816,7 @@ struct BaSolver : BaSolverBase {
     PTZ_CUDA(cudaGetLastError());
     if (g_nccl.world > 1) PTZ_TIMED(PTZ_K_ALLREDUCE, allreduce_sum(d_sys.p, sys_n, s));
     PTZ_TIMED(PTZ_K_PRECOND, {
-      k_precond<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, ds.diag_pos.p, p_Sval, d_Linv.p, d_fail.p);
+      k_precond<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, ds.diag_pos.p, p_Sval, d_Linv.p, d_fail.p, defl_enabled ? d_Lfac.p : nullptr);
       if (nb > 0) k_precond_border<<<1, 32, 0, s>>>(nb, d_Sbb.p, d_Linv_b.p, d_fail.p);
       k_scale_system<NCL><<<cdiv(std::max(ds.nnzb, V), 128), 128, 0, s>>>(V, ds.nnzb, ds.blk_row.p, ds.s_col.p, d_Linv.p, p_Sval, p_rhs, arena_ptr(ar_st0),
                                                                             arena_ptr(ar_x), d_cgp.p, d_cg_owner.p,
@@ -779,7 +825,41 @@ struct BaSolver : BaSolverBase {
         k_scale_border<NCL><<<1, 128, 0, s>>>(V, nb, ncpl, d_cpl_view.p, d_Linv.p, d_Linv_b.p, kDisp ? d_Cw.p : p_C, d_Cs.p, p_rhs, arena_ptr(ar_st0), arena_ptr(ar_x),
                                               d_cgp.p);
     });
-    // ---- stage 3
+    // ---- stages 3 and 4
+    const bool deflate = defl_enabled && have_W;
+    const bool record = defl_enabled && !have_W;  // undeflated solve: keep its residual history for the deflation basis
+    linear_solve(deflate, record, false);
+    launch_stage4(mu);
+    read_scalars();
+    if (deflate) {
+      ++defl_solves;
+      if (h_dscal[1] == 0.0 || h_info[1] == 2) {
+        // the (stale) basis lost rank, or the deflated recurrences broke down: this handle goes back to the plain iteration
+        ++defl_rejects;
+        have_W = false; defl_enabled = false;
+        if (h_info[1] == 2) {
+          linear_solve(false, false, true);
+          launch_stage4(mu);
+          read_scalars();
+        }
+      }
+    } else if (record && h_info[1] == 0 && h_info[0] >= kMinHarvest) {
+      harvest_basis(h_info[0]);
+    }
+    ++cost_evals;
+    *lin_iters = h_info[0];
+    if (h_info[2] != 0) return false;          // a 3x3 / camera / border block was not positive definite
+    if (h_info[1] == 3) throw CudaError(PTZ_ERR_NCCL, "k_cg: a peer rank did not reach the cross-GPU barrier (timeout)");
+    if (h_info[1] == 2) return false;          // PCG breakdown (non-finite or non-positive curvature)
+    return true;
+  }
+
+  // stage 3: the deflation set-up (when a basis exists), ONE cooperative k_cg launch, back to the unscaled unknowns
+  void linear_solve(bool deflate, bool record, bool restart) {
+    cudaStream_t s = stream;
+    const int ncam = V * NCL;
+    const size_t nk = (size_t)ncam * kDeflK;
+    const int mr = (g_nccl.world > 1) ? cgR : -1;
     CgArgs a;
     a.V = V; a.nb = nb; a.n = n;
     a.rowptr = ds.s_rowptr.p; a.col = d_cg_col.p; a.Sval = p_Sval; a.peer_mask = d_cg_mask.p;
@@ -791,20 +871,59 @@ struct BaSolver : BaSolverBase {
     a.out_info = d_pcg_info.p; a.out_res = d_pcg_res.p;
     // shared-memory residency of S: every warp keeps up to cg_cap blocks (+ column indices) of its rows for the whole solve
     a.smem_blocks = cg_cap;
+    a.smem_defl_rows = deflate ? cg_defl_rows : 0;
     { const char* e = getenv("PTZ_CG_DEBUG"); a.debug = e ? atoi(e) : 0; }
-    const size_t cg_smem = (size_t)cg_wpb * cg_cap * (NCL * NCL * sizeof(double) + sizeof(int)) + 16;
+    a.dW = d_Wt.p; a.dAW = d_AW.p; a.dZ = d_Z.p; a.dEinv = d_Einv.p; a.dscal = d_dscal.p;
+    a.hist = record ? d_hist.p : nullptr; a.hist_cap = kHistCap; a.abg = record ? d_abg.p : nullptr;
+    const size_t cg_smem = cg_smem_bytes(deflate);
     void* args[] = {&a};
+    if (restart) k_cg_restart<NCL><<<cdiv(ncam, 256), 256, 0, s>>>(V, d_bcopy.p, arena_ptr(ar_st0), arena_ptr(ar_x), d_cgp.p);
+    if (deflate)
+      PTZ_TIMED(PTZ_K_DEFLATE, {
+        const int nchunk = cdiv(ncam, kDeflGramChunk);
+        k_defl_scale_basis<NCL><<<cdiv(V * kDeflK, 256), 256, 0, s>>>(V, d_Lfac.p, d_Wy.p, d_Wt.p);  // W~ = L^T W_y
+        k_defl_spmm<NCL><<<cdiv(V, 8), 256, 0, s>>>(V, ds.s_rowptr.p, ds.s_col.p, p_Sval, d_Wt.p, d_AW.p, d_cg_owner.p, mr);
+        allreduce_sum(d_AW.p, nk, s);  // sharded rows: every rank needs all of AW (for E and for the start vector)
+        k_defl_spmm<NCL><<<cdiv(V, 8), 256, 0, s>>>(V, ds.s_rowptr.p, ds.s_col.p, p_Sval, d_AW.p, d_Z.p, d_cg_owner.p, mr);
+        k_defl_gram<NCL><<<nchunk, 256, 0, s>>>(V, d_Wt.p, d_AW.p, arena_ptr(ar_st0), d_gram.p, d_bcopy.p);
+        k_defl_small<<<1, 32, 0, s>>>(defl_kd, nchunk, d_gram.p, d_Einv.p, d_c0.p, d_dscal.p);
+        k_defl_start<NCL><<<cdiv(ncam, 256), 256, 0, s>>>(V, d_Wt.p, d_AW.p, d_c0.p, d_dscal.p, arena_ptr(ar_st0), arena_ptr(ar_x));
+      });
     PTZ_TIMED(PTZ_K_PCG, {
       if (cg_vranks > 1) {  // debug: every virtual rank starts from the same initial state
         for (int k = 1; k < cg_vranks; ++k) {
           PTZ_CUDA(cudaMemcpyAsync(g_arena.base[k] + ar_st0, g_arena.base[0] + ar_st0, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
-          PTZ_CUDA(cudaMemsetAsync(g_arena.base[k] + ar_x, 0, (size_t)n * sizeof(double), s));
+          PTZ_CUDA(cudaMemcpyAsync(g_arena.base[k] + ar_x, g_arena.base[0] + ar_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
         }
       }
-      PTZ_CUDA(cudaLaunchCooperativeKernel(cg_kernel(), dim3(cg_grid * cg_vranks), dim3(32 * cg_wpb), args, cg_smem, s));
+      PTZ_CUDA(cudaLaunchCooperativeKernel(cg_kernel(deflate), dim3(cg_grid * cg_vranks), dim3(32 * cg_wpb), args, cg_smem, s));
       k_unscale<NCL><<<cdiv(V + nb, 128), 128, 0, s>>>(V, nb, d_Linv.p, d_Linv_b.p, arena_ptr(ar_x), d_y.p);
     });
-    // ---- stage 4
+    PTZ_CUDA(cudaGetLastError());
+  }
+
+  // after the first (undeflated, recorded) solve of a run: lowest Ritz vectors of its Lanczos tridiagonal -> deflation basis,
+  // stored in the unscaled unknowns (W_y = Linv^T W~) so that it can follow the block-Jacobi scaling of the later solves
+  void harvest_basis(int iterations) {
+    cudaStream_t s = stream;
+    const int m = std::min(iterations, (int)kHistCap), ncam = V * NCL;
+    std::vector<double> Y;
+    const int kd = lowest_ritz_vectors(h_abg.data(), m, kDeflK, kDeflK, Y);
+    if (kd < 4) return;
+    d_Y.upload(Y.data(), (size_t)m * kDeflK, s);
+    const int mr = (g_nccl.world > 1) ? cgR : -1;
+    k_defl_harvest<<<cdiv(ncam * kDeflK, 256), 256, 0, s>>>(ncam, m, kd, d_hist.p, d_Y.p, d_Wt.p, d_cg_owner.p, NCL, mr);
+    allreduce_sum(d_Wt.p, (size_t)ncam * kDeflK, s);
+    k_defl_scale_basis<NCL><<<cdiv(V * kDeflK, 256), 256, 0, s>>>(V, d_Linv.p, d_Wt.p, d_Wy.p);
+    PTZ_CUDA(cudaGetLastError());
+    have_W = true;
+    defl_kd = kd;
+    d_hist.release();  // (stream-ordered: goes back to the block cache behind the kernels above)
+    if (opt.verbose) printf("[ptzba] deflation basis: %d Ritz vectors from %d CG iterations\n", kd, m);
+  }
+
+  void launch_stage4(double mu) {
+    cudaStream_t s = stream;
     const int nxt = cur ^ 1;
     const double* y = d_y.p;
     if (P > 0)
@@ -818,13 +937,6 @@ struct BaSolver : BaSolverBase {
                                        d_tlw[nxt].p, d_intr[cur].p, d_intr[nxt].p, d_dispp[cur].p, d_dispp[nxt].p, d_part3_b.p);
     launch_cost(nxt);
     launch_step_scalars();
-    read_scalars();
-    ++cost_evals;
-    *lin_iters = h_info[0];
-    if (h_info[2] != 0) return false;          // a 3x3 / camera / border block was not positive definite
-    if (h_info[1] == 3) throw CudaError(PTZ_ERR_NCCL, "k_cg: a peer rank did not reach the cross-GPU barrier (timeout)");
-    if (h_info[1] == 2) return false;          // PCG breakdown (non-finite or non-positive curvature)
-    return true;
   }
 
   void launch_cost(int which) {

@@ -232,6 +232,16 @@ int ptzreloc_eval(int factor_type, int num_matches, const float* uv_ref, const f
                   const double* ref_cam21, const double* local_cam15,
                   double* residuals /*[2N]*/, double* jac /*[N][2][nfree]*/, double* cost, double* gradient);
 
+/* KRTOptimizer::Cal2d2dReprojError (krt_optimizer.cc:406-455) and Cal2d3dReprojError (:457-500): unweighted RMS of the functor
+ * residuals, sqrt(sum |r|^2 / count), at local_cam15 = cam_curr_local_param_ (the initial local parameters before Solve, the refined
+ * ones -- ptzreloc_result.local_cam15 -- after).  pt_xyz are WORLD points (moved to the reference-local frame as at :466-470).
+ * err_2d3d = -1 without points (:459-460); err_2d2d is NaN for an empty match list (0/0, as the reference). */
+/* cam_curr_local_param_ right after Add2d2dConstraints (krt_optimizer.cc:269-286): the initial camera moved to the frame of the
+ * reference camera and flattened by Camera::ToVector.  Plain host arithmetic (no device needed). */
+int ptzreloc_local_params(const double* ref_cam21, const double* init_cam21, double* local_cam15);
+int ptzreloc_reproj_error(int factor_type, const double* ref_cam21, const double* local_cam15, int num_matches, const float* uv_ref,
+                          const float* uv_cur, int num_pts, const float* pt_uv, const double* pt_xyz, double* err_2d2d, double* err_2d3d);
+
 /* device-resident variant used by bench.py's kernel-only timing: all pointers are DEVICE pointers */
 int ptzreloc_solve_batch_dev(const ptzreloc_batch* dev_batch, const ptz_solver_options* opt,
                              ptzreloc_result* dev_out, void* cuda_stream);

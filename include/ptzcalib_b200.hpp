@@ -432,6 +432,45 @@ class KRTOptimizer {
       uv1_.push_back(kpts_ref[m.queryIdx].pt.x); uv1_.push_back(kpts_ref[m.queryIdx].pt.y);
       uv2_.push_back(kpts_curr[m.trainIdx].pt.x); uv2_.push_back(kpts_curr[m.trainIdx].pt.y);
     }
+    double ref[21], init[21];
+    cam_ref_.ToKrt21(ref);
+    cam_curr_world_.ToKrt21(init);
+    ptzreloc_local_params(ref, init, cam_curr_local_param_);  // .cc:269-286
+  }
+  // .cc:406-455: RMS of the 2d-2d functor residuals at cam_curr_local_param_ (initial before Solve, refined after), for ANY match
+  // list against the camera passed to Add2d2dConstraints' frame
+  double Cal2d2dReprojError(const Camera& cam_ref, const std::vector<KeyPoint>& kpts_ref, const std::vector<KeyPoint>& kpts_curr,
+                            const std::vector<DMatch>& matches) {
+    std::vector<float> u1, u2;
+    for (const auto& m : matches) {
+      u1.push_back(kpts_ref[m.queryIdx].pt.x); u1.push_back(kpts_ref[m.queryIdx].pt.y);
+      u2.push_back(kpts_curr[m.trainIdx].pt.x); u2.push_back(kpts_curr[m.trainIdx].pt.y);
+    }
+    double ref[21], e22 = 0, e23 = 0;
+    Camera local = cam_ref;  // cam_ref_local: K and dist of the reference, R = I, t = 0 (.cc:409-413)
+    local.ToKrt21(ref);
+    for (int i = 0; i < 9; ++i) ref[4 + i] = (i % 4 == 0) ? 1.0 : 0.0;
+    ref[13] = ref[14] = ref[15] = 0.0;
+    if (ptzreloc_reproj_error(kMap()[(int)factor_type_], ref, cam_curr_local_param_, (int)matches.size(), u1.data(), u2.data(), 0, nullptr, nullptr, &e22,
+                              &e23) != PTZ_OK)
+      return -1;
+    return e22;
+  }
+  // .cc:457-500: world points go through R_local_world_, t_local_world_ = the reference camera's R, t
+  double Cal2d3dReprojError(const std::vector<Point2f>& pts2d, const std::vector<Point3d>& pts3d) {
+    if (pts2d.size() != pts3d.size() || pts2d.empty()) return -1;
+    std::vector<float> pu;
+    std::vector<double> px;
+    for (size_t i = 0; i < pts2d.size(); ++i) {
+      pu.push_back(pts2d[i].x); pu.push_back(pts2d[i].y);
+      px.push_back(pts3d[i].x); px.push_back(pts3d[i].y); px.push_back(pts3d[i].z);
+    }
+    double ref[21], e22 = 0, e23 = 0;
+    cam_ref_.ToKrt21(ref);
+    if (ptzreloc_reproj_error(kMap()[(int)factor_type_], ref, cam_curr_local_param_, 0, nullptr, nullptr, (int)pts2d.size(), pu.data(), px.data(), &e22, &e23) !=
+        PTZ_OK)
+      return -1;
+    return e23;
   }
   // .cc:350-383; the world->local transform of the points (.cc:357-362) is applied on the device with cam_ref's R, t
   void Add2d3dConstraints(const std::vector<Point2f>& pts2d, const std::vector<Point3d>& pts3d) {
@@ -446,19 +485,20 @@ class KRTOptimizer {
     cam_ref_.ToKrt21(ref);
     cam_curr_world_.ToKrt21(init);
     const int64_t off[2] = {0, (int64_t)(uv1_.size() / 2)};
-    static const int kMap[4] = {PTZ_KRT_F, PTZ_KRT_FDIST, PTZ_KRT_FXFY, PTZ_KRT_FXFYDIST};
     ptzreloc_batch b{};
-    b.factor_type = kMap[(int)factor_type_]; b.num_queries = 1; b.match_offset = off; b.uv_ref = uv1_.data(); b.uv_cur = uv2_.data();
+    b.factor_type = kMap()[(int)factor_type_]; b.num_queries = 1; b.match_offset = off; b.uv_ref = uv1_.data(); b.uv_cur = uv2_.data();
     b.ref_cam = ref; b.init_cam = init; b.max_iter = max_iter_; b.max_reproj_error = max_reproj_error_;
     const int64_t poff[2] = {0, (int64_t)(puv_.size() / 2)};
     if (!puv_.empty()) { b.pt_offset = poff; b.pt_uv = puv_.data(); b.pt_xyz = pxyz_.data(); }
     int32_t ok = 0, term = 0, nit = 0;
     ptzreloc_result r{};
-    r.cam = out; r.success = &ok; r.termination = &term; r.num_iter = &nit;
+    double local[15];
+    r.cam = out; r.success = &ok; r.termination = &term; r.num_iter = &nit; r.local_cam15 = local;
     ptz_solver_options o;
     ptz_solver_options_default(&o);
     if (ptzreloc_solve_batch(&b, &o, &r) != PTZ_OK) return false;
     num_iter_ = nit;
+    for (int j = 0; j < 15; ++j) cam_curr_local_param_[j] = local[j];  // Ceres refines the block in place, converged or not
     if (!ok) return false;  // CheckResults (.cc:504-533) ran on the device
     Camera c;
     c.FromKrt21(out);
@@ -469,6 +509,11 @@ class KRTOptimizer {
   int num_iter_ = 0;
 
  private:
+  static const int* kMap() {  // krt_optimizer.h:110 order -> the C enum
+    static const int m[4] = {PTZ_KRT_F, PTZ_KRT_FDIST, PTZ_KRT_FXFY, PTZ_KRT_FXFYDIST};
+    return m;
+  }
+  double cam_curr_local_param_[15] = {0};
   Camera cam_curr_world_, cam_ref_;
   std::vector<float> uv1_, uv2_, puv_;
   std::vector<double> pxyz_;

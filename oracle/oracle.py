@@ -111,6 +111,17 @@ def krt_to_local(ref21, init21):
     return out
 
 
+def reloc_reproj_error(ftype, ref21, local15, uv_ref=None, uv_cur=None, pt_uv=None, pt_xyz=None):
+    """(Cal2d2dReprojError, Cal2d3dReprojError) of KRTOptimizer at local15"""
+    e22, e23 = C.c_double(0), C.c_double(0)
+    n = 0 if uv_ref is None else len(uv_ref)
+    m = 0 if pt_uv is None else len(pt_uv)
+    a = [None if x is None else np.ascontiguousarray(x, dtype=dt) for x, dt in ((uv_ref, np.float32), (uv_cur, np.float32), (pt_uv, np.float32), (pt_xyz, np.float64))]
+    lib().orc_ptzreloc_reproj_error(C.c_int(ftype), as_ptr(f64(ref21), C.c_double), as_ptr(f64(local15), C.c_double), C.c_int(n), as_ptr(a[0], C.c_float),
+                                    as_ptr(a[1], C.c_float), C.c_int(m), as_ptr(a[2], C.c_float), as_ptr(a[3], C.c_double), C.byref(e22), C.byref(e23))
+    return e22.value, e23.value
+
+
 def krt_to_world(ftype, ref21, local15):
     out = np.zeros(21)
     lib().orc_krt_to_world(C.c_int(ftype), as_ptr(f64(ref21), C.c_double), as_ptr(f64(local15), C.c_double), as_ptr(out, C.c_double))

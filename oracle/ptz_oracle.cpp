@@ -44,6 +44,7 @@
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
+#include <cstdlib>
 #endif
 
 namespace {
@@ -461,6 +462,38 @@ double eval_all(const Problem& P, const double* x, int mode, std::vector<BlockJ>
   return cost;
 }
 
+// out[col] += f(block, c) over every (block, tangent column) pair, in parallel: thread-private accumulators over contiguous
+// ranges of blocks, merged in thread order (the result depends on the thread count only in the last bits)
+template <class F>
+void scatter_cols(const std::vector<BlockJ>& B, int nt, int nthreads, std::vector<double>& out, F f) {
+  std::fill(out.begin(), out.end(), 0.0);
+  const int nb = (int)B.size();
+  int T = std::max(1, std::min(nthreads, nb / 4096));
+  if (T == 1) {
+    for (const BlockJ& b : B)
+      for (int c = 0; c < b.nc; ++c) out[b.col[c]] += f(b, c);
+    return;
+  }
+  std::vector<double> priv((size_t)T * nt, 0.0);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+#endif
+  for (int t = 0; t < T; ++t) {
+    double* o = &priv[(size_t)t * nt];
+    const int k0 = (int)((long long)nb * t / T), k1 = (int)((long long)nb * (t + 1) / T);
+    for (int k = k0; k < k1; ++k)
+      for (int c = 0; c < B[k].nc; ++c) o[B[k].col[c]] += f(B[k], c);
+  }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(T)
+#endif
+  for (int j = 0; j < nt; ++j) {
+    double sacc = 0;
+    for (int t = 0; t < T; ++t) sacc += priv[(size_t)t * nt + j];
+    out[j] = sacc;
+  }
+}
+
 // ----------------------------------------------------------------------------------------------------
 // dense helpers
 // ----------------------------------------------------------------------------------------------------
@@ -870,6 +903,9 @@ struct LmSummary {
 
 void minimize(const Problem& P, std::vector<double>& x, const ptz_solver_options& o, bool use_schur, LmSummary& sum) {
   const int nt = P.num_tangent, na = P.num_ambient;
+  const bool timing = std::getenv("ORC_TIMING") != nullptr;  // where an iteration's time goes (stderr)
+  double t_eval = 0, t_grad = 0, t_lin = 0, t_model = 0, t_cost = 0;
+  auto now = []() { return omp_get_wtime(); };
   const int nthreads = o.num_threads > 0 ? o.num_threads : 1;
   std::vector<BlockJ> B;
   std::vector<double> scale(nt, 1.0), grad(nt), diag(nt), D(nt), ystep(nt), delta(nt), cand(x);
@@ -881,19 +917,24 @@ void minimize(const Problem& P, std::vector<double>& x, const ptz_solver_options
   double grad_max = 0;
   // EvaluateGradientAndJacobian
   auto eval_gj = [&]() {
+    double t0 = now();
     x_cost = eval_all(P, x.data(), o.jacobian_mode, &B, nthreads);
-    std::fill(grad.begin(), grad.end(), 0.0);
-    for (const BlockJ& b : B)
-      for (int c = 0; c < b.nc; ++c) grad[b.col[c]] += b.J[0][c] * b.r[0] + b.J[1][c] * b.r[1];  // unscaled J
+    t_eval += now() - t0; t0 = now();
+    scatter_cols(B, nt, nthreads, grad, [](const BlockJ& b, int c) { return b.J[0][c] * b.r[0] + b.J[1][c] * b.r[1]; });  // unscaled J
     if (o.jacobi_scaling) {
       if (iteration == 0) {
         std::vector<double> cn(nt, 0.0);
-        for (const BlockJ& b : B)
-          for (int c = 0; c < b.nc; ++c) cn[b.col[c]] += b.J[0][c] * b.J[0][c] + b.J[1][c] * b.J[1][c];
+        scatter_cols(B, nt, nthreads, cn, [](const BlockJ& b, int c) { return b.J[0][c] * b.J[0][c] + b.J[1][c] * b.J[1][c]; });
         for (int j = 0; j < nt; ++j) scale[j] = 1.0 / (1.0 + std::sqrt(cn[j]));
       }
-      for (BlockJ& b : B)
+      const int nbk = (int)B.size();
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+#endif
+      for (int k = 0; k < nbk; ++k) {
+        BlockJ& b = B[k];
         for (int c = 0; c < b.nc; ++c) { b.J[0][c] *= scale[b.col[c]]; b.J[1][c] *= scale[b.col[c]]; }
+      }
     }
     // |x - Plus(x, -g)|_inf
     grad_max = 0;
@@ -902,6 +943,7 @@ void minimize(const Problem& P, std::vector<double>& x, const ptz_solver_options
       double d = std::fabs(xv - (xv + (-grad[j])));
       if (d > grad_max) grad_max = d;
     }
+    t_grad += now() - t0;
   };
   auto push_log = [&](double cost, double cost_change, double step_norm, double rho, int lin, int ok) {
     ptz_iter_log l;
@@ -926,14 +968,14 @@ void minimize(const Problem& P, std::vector<double>& x, const ptz_solver_options
     ++iteration;
     // ComputeTrustRegionStep -> LevenbergMarquardtStrategy::ComputeStep
     if (!reuse_diagonal) {
-      std::fill(diag.begin(), diag.end(), 0.0);
-      for (const BlockJ& b : B)
-        for (int c = 0; c < b.nc; ++c) diag[b.col[c]] += b.J[0][c] * b.J[0][c] + b.J[1][c] * b.J[1][c];
+      scatter_cols(B, nt, nthreads, diag, [](const BlockJ& b, int c) { return b.J[0][c] * b.J[0][c] + b.J[1][c] * b.J[1][c]; });
       for (int j = 0; j < nt; ++j) diag[j] = std::min(std::max(diag[j], o.min_lm_diagonal), o.max_lm_diagonal);
     }
     for (int j = 0; j < nt; ++j) D[j] = std::sqrt(diag[j] / radius);
     int lin = 0;
+    double t0 = now();
     bool ok = use_schur ? solve_schur(P, B, D.data(), ystep.data(), SW, o.linear_solver, o, &lin) : solve_dense_qr(B, nt, D.data(), ystep.data());
+    t_lin += now() - t0; t0 = now();
     reuse_diagonal = true;
     sum.lin_iters += lin;
     if (ok)
@@ -942,13 +984,27 @@ void minimize(const Problem& P, std::vector<double>& x, const ptz_solver_options
     if (ok) {
       for (int j = 0; j < nt; ++j) ystep[j] = -ystep[j];
       // model_cost_change = -(J step)^T (r + J step / 2)
-      for (const BlockJ& b : B) {
-        double m0 = 0, m1 = 0;
-        for (int c = 0; c < b.nc; ++c) { m0 += b.J[0][c] * ystep[b.col[c]]; m1 += b.J[1][c] * ystep[b.col[c]]; }
-        model_cost_change -= m0 * (b.r[0] + m0 / 2.0) + m1 * (b.r[1] + m1 / 2.0);
+      {
+        const int nbk = (int)B.size(), Tm = std::max(1, std::min(nthreads, nbk / 4096));
+        std::vector<double> part(Tm, 0.0);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(Tm)
+#endif
+        for (int t = 0; t < Tm; ++t) {
+          double sacc = 0;
+          for (int k = (int)((long long)nbk * t / Tm); k < (int)((long long)nbk * (t + 1) / Tm); ++k) {
+            const BlockJ& b = B[k];
+            double m0 = 0, m1 = 0;
+            for (int c = 0; c < b.nc; ++c) { m0 += b.J[0][c] * ystep[b.col[c]]; m1 += b.J[1][c] * ystep[b.col[c]]; }
+            sacc += m0 * (b.r[0] + m0 / 2.0) + m1 * (b.r[1] + m1 / 2.0);
+          }
+          part[t] = sacc;
+        }
+        for (int t = 0; t < Tm; ++t) model_cost_change -= part[t];
       }
       ok = model_cost_change > 0.0;
     }
+    t_model += now() - t0;
     if (!ok) {
       // HandleInvalidStep
       ++num_consecutive_invalid;
@@ -964,7 +1020,9 @@ void minimize(const Problem& P, std::vector<double>& x, const ptz_solver_options
     // ComputeCandidatePointAndEvaluateCost
     cand = x;
     for (int j = 0; j < nt; ++j) cand[P.tan2amb[j]] = x[P.tan2amb[j]] + delta[j];
+    t0 = now();
     double cand_cost = eval_all(P, cand.data(), 0, nullptr, nthreads);
+    t_cost += now() - t0;
     if (!std::isfinite(cand_cost)) cand_cost = std::numeric_limits<double>::max();
     // ParameterToleranceReached
     double step_norm = 0;
@@ -1000,6 +1058,9 @@ void minimize(const Problem& P, std::vector<double>& x, const ptz_solver_options
       std::printf("[orc] it %3d cost %.10e change %.3e |g| %.3e |step| %.3e rho %.3e radius %.3e lin %d %s\n", iteration, sum.log.back().cost,
                   cost_change, grad_max, step_norm, rho, radius, lin, last_successful ? "ok" : "rej");
   }
+  if (timing)
+    std::fprintf(stderr, "[orc timing, %d threads] jacobian %.3f s  gradient/scaling %.3f s  linear solve %.3f s  model change %.3f s  cost %.3f s\n", nthreads,
+                 t_eval, t_grad, t_lin, t_model, t_cost);
   sum.num_iterations = (int)sum.log.size() - 1;
   sum.final_cost = min_cost;  // SetSummaryFinalCost: min over accepted iterates == cost at returned x
 }
@@ -1425,6 +1486,29 @@ int orc_ptzreloc_eval(int type, int N, const float* uv_ref, const float* uv_cur,
   return orc_ptzreloc_eval_mode(type, N, uv_ref, uv_cur, ref21, local15, residuals, jac, cost, gradient, 0);
 }
 void orc_krt_to_local(const double* ref21, const double* init21, double* local15) { krt_to_local(ref21, init21, local15); }
+// KRTOptimizer::Cal2d2dReprojError (krt_optimizer.cc:406-455) / Cal2d3dReprojError (:457-500) at local15
+int orc_ptzreloc_reproj_error(int type, const double* ref21, const double* local15, int N, const float* uv_ref, const float* uv_cur, int npts,
+                              const float* pt_uv, const double* pt_xyz, double* err_2d2d, double* err_2d3d) {
+  double s22 = 0, s23 = 0;
+  const double refK4[4] = {ref21[0], ref21[1], ref21[2], ref21[3]};
+  for (int i = 0; i < N; ++i) {
+    KrtPre pre;
+    krt_precompute(type, refK4, ref21 + 16, uv_ref + 2 * i, &pre);
+    double r[2];
+    krt_2d2d_factor<double>(type, local15, pre, uv_cur[2 * i], uv_cur[2 * i + 1], r);
+    s22 += r[0] * r[0] + r[1] * r[1];
+  }
+  for (int i = 0; i < npts; ++i) {
+    double P[3], r[2];
+    mul31(ref21 + 4, pt_xyz + 3 * i, P);
+    for (int a = 0; a < 3; ++a) P[a] += ref21[13 + a];
+    krt_2d3d_factor<double>(type, local15, P, pt_uv[2 * i], pt_uv[2 * i + 1], r);
+    s23 += r[0] * r[0] + r[1] * r[1];
+  }
+  if (err_2d2d) *err_2d2d = std::sqrt(s22 / (double)N);
+  if (err_2d3d) *err_2d3d = npts > 0 ? std::sqrt(s23 / (double)npts) : -1.0;
+  return PTZ_OK;
+}
 void orc_krt_to_world(int type, const double* ref21, const double* local15, double* out21) { krt_to_world(type, ref21, local15, out21); }
 
 int orc_ptzreloc_solve_batch(const ptzreloc_batch* b, const ptz_solver_options* opt, ptzreloc_result* out) {

@@ -227,6 +227,34 @@ class KRTOptimizer:
         matches = np.asarray(matches, dtype=np.int64).reshape(-1, 2)
         self._ref = f64(cam_ref21).reshape(21)
         self._uv = (f32(kpts_ref).reshape(-1, 2)[matches[:, 0]], f32(kpts_curr).reshape(-1, 2)[matches[:, 1]])
+        self._local15 = np.zeros(15)  # cam_curr_local_param_ (krt_optimizer.cc:269-286)
+        lib.check(lib.load().ptzreloc_local_params(as_ptr(self._ref, C.c_double), as_ptr(self._init, C.c_double), as_ptr(self._local15, C.c_double)),
+                  "ptzreloc_local_params")
+
+    def _reproj(self, ref21, uv1, uv2, pts2d, pts3d):
+        e22, e23 = C.c_double(0), C.c_double(0)
+        n, m = (0 if uv1 is None else len(uv1)), (0 if pts2d is None else len(pts2d))
+        rc = lib.load().ptzreloc_reproj_error(C.c_int(self.factor_type), as_ptr(f64(ref21), C.c_double), as_ptr(self._local15, C.c_double), C.c_int(n),
+                                              as_ptr(uv1, C.c_float), as_ptr(uv2, C.c_float), C.c_int(m), as_ptr(pts2d, C.c_float),
+                                              as_ptr(pts3d, C.c_double), C.byref(e22), C.byref(e23))
+        lib.check(rc, "ptzreloc_reproj_error")
+        return e22.value, e23.value
+
+    def Cal2d2dReprojError(self, cam_ref21, kpts_ref, kpts_curr, matches):  # krt_optimizer.cc:406-455
+        """RMS of the 2d-2d functor residuals at the current local parameters (initial before Solve, refined after)"""
+        matches = np.asarray(matches, dtype=np.int64).reshape(-1, 2)
+        ref = f64(cam_ref21).reshape(21).copy()
+        ref[4:13] = np.eye(3).reshape(9)  # cam_ref_local: K, dist of the reference; R = I, t = 0 (:409-413)
+        ref[13:16] = 0.0
+        uv1 = np.ascontiguousarray(f32(kpts_ref).reshape(-1, 2)[matches[:, 0]])
+        uv2 = np.ascontiguousarray(f32(kpts_curr).reshape(-1, 2)[matches[:, 1]])
+        return self._reproj(ref, uv1, uv2, None, None)[0]
+
+    def Cal2d3dReprojError(self, pts2d, pts3d):  # krt_optimizer.cc:457-500
+        pts2d, pts3d = np.ascontiguousarray(f32(pts2d).reshape(-1, 2)), np.ascontiguousarray(f64(pts3d).reshape(-1, 3))
+        if len(pts2d) != len(pts3d) or len(pts2d) == 0:
+            return -1.0
+        return self._reproj(self._ref, None, None, pts2d, pts3d)[1]
 
     def Add2d3dConstraints(self, pts2d, pts3d):  # krt_optimizer.cc:350-383
         """pts2d: [n,2] pixels of the current image; pts3d: [n,3] world points"""
@@ -245,6 +273,7 @@ class KRTOptimizer:
                            self.max_reproj_error, **pts)
         res = reloc_solve_batch(batch)
         self.num_iter_ = int(res.num_iter[0])
+        self._local15 = np.ascontiguousarray(res.local_cam15[0])  # Ceres refines cam_curr_local_param_ in place, converged or not
         if not res.success[0]:
             return False, None, None, None, None
         c = res.cam[0]

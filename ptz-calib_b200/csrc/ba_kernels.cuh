@@ -714,6 +714,7 @@ struct CgArgs {
   // residual history of an undeflated solve (harvested into the deflation basis by the host afterwards): hist [hist_cap][n],
   // abg [.. ][3] = alpha, beta, gamma of every iteration.  nullptr = off
   double* hist; int hist_cap; double* abg;
+  double* prof;            // PTZ_CG_DEBUG & 8: cycles of CTA 0 / thread 0 per phase of an iteration, summed over the solve
 };
 // arena control block (u64 words): [0] barrier arrival counter of the single-GPU path (never reset), [1] arrivals consumed by
 // the barriers passed so far, [2] next unused LL tag (the same on every rank; carried from solve to solve)
@@ -754,13 +755,44 @@ __device__ __forceinline__ void cta_reduceN(double (&v)[NV], double* sred /* [nw
     v[0] = s;  // thread c holds the CTA total of value c
   }
 }
-// single GPU: CTA partials -> value-major slots, counter barrier; then ALL partials are fetched at once (one L2 round trip
-// for the whole CTA) into shared memory and the warps share the NV sums between them
-template <int NV>
-__device__ __forceinline__ void grid_reduceN(const CgArgs& A, double (&v)[NV], int parity, unsigned long long& arrived, double* sred, double* s_out,
-                                             double* s_flat /* [NV * G] */) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5, G = gridDim.x;
+// Sums of the value-major partial array buf[NV][G] (G <= kCgMaxCtas): the NW warps of the CTA share the NV values between them
+// and every lane issues ALL its loads (<= ceil(NV/NW) * kCgMaxCtas/32) before the first one is consumed -- one L2 round trip
+// for the whole fetch.  Fixed order; the caller does something with (value index, total) in every lane of the owning warp.
+template <int NV, int NW, class F>
+__device__ __forceinline__ void sum_partials(const double* buf, int G, F&& emit) {
+  constexpr int VPW = (NV + NW - 1) / NW, LPV = kCgMaxCtas / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double t[VPW][LPV];
+#pragma unroll
+  for (int q = 0; q < VPW; ++q) {
+    const int c = wid + q * NW;
+#pragma unroll
+    for (int u = 0; u < LPV; ++u) {
+      const int i = lane + 32 * u;
+      t[q][u] = (c < NV && i < G) ? __ldcg(buf + (size_t)c * G + i) : 0.0;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < VPW; ++q) {
+    const int c = wid + q * NW;
+    double s = 0;
+#pragma unroll
+    for (int u = 0; u < LPV; ++u) s += t[q][u];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (c < NV) emit(c, s);
+  }
+}
+// single GPU: CTA partials -> value-major slots, counter barrier; then the warps share the NV sums between them (sum_partials)
+template <int NV, int NW>
+__device__ __forceinline__ void grid_reduceN(const CgArgs& A, double (&v)[NV], int parity, unsigned long long& arrived, double* sred, double* s_out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, G = gridDim.x;
+  const bool profiling = A.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  long long tprof = profiling ? clock64() : 0;
+#define PTZ_RED_PROF(slot)                                                       \
+  if (profiling) { const long long tn = clock64(); A.prof[slot] += (double)(tn - tprof); tprof = tn; }
   cta_reduceN<NV>(v, sred);
+  PTZ_RED_PROF(3)
   double* buf = reinterpret_cast<double*>(A.arena[0] + A.off_partial) + (size_t)(parity & 1) * NV * G;
   if (wid == 0) {
     if (lane < NV) __stcg(buf + (size_t)lane * G + blockIdx.x, v[0]);
@@ -773,21 +805,15 @@ __device__ __forceinline__ void grid_reduceN(const CgArgs& A, double (&v)[NV], i
     }
   }
   __syncthreads();
+  PTZ_RED_PROF(4)
   arrived += (unsigned long long)G;
   // every thread acquires: its later plain (L1-cached) loads must not be served from lines older than this barrier
   asm volatile("fence.acq_rel.gpu;" ::: "memory");
-  const int tot = NV * G;
-#pragma unroll 4
-  for (int e = threadIdx.x; e < tot; e += blockDim.x) s_flat[e] = __ldcg(buf + e);
+  sum_partials<NV, NW>(buf, G, [&](int c, double tot) { if (lane == 0) s_out[c] = tot; });
+  PTZ_RED_PROF(5)
   __syncthreads();
-  for (int c = wid; c < NV; c += nwarp) {
-    double s = 0;
-    for (int i = lane; i < G; i += 32) s += s_flat[c * G + i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) s_out[c] = s;
-  }
-  __syncthreads();
+  PTZ_RED_PROF(6)
+#undef PTZ_RED_PROF
 }
 
 // ---- LL words
@@ -803,15 +829,15 @@ __device__ __forceinline__ bool ll_load(const ulonglong2* src, unsigned int tag,
   return (unsigned int)(lo >> 32) == tag && (unsigned int)(hi >> 32) == tag;
 }
 // multi-rank reduction + barrier, two levels.  Inside a rank: plain partials + acq_rel arrival counter; the LAST CTA to arrive
-// fetches the rank's partials (all its threads, one L2 round trip), sums them in CTA order and pushes the NV rank totals as LL
+// fetches the rank's partials (all its warps, one L2 round trip), sums them in CTA order and pushes the NV rank totals as LL
 // words into the rank's slots on every rank.  Across ranks: the first W x NV threads of every CTA poll one local slot each; the
 // totals are added in rank order -- bit-identical on every CTA of every rank.  sys_release: make this CTA's earlier PLAIN stores
 // to peer memory visible first (end-of-solve push of x).  Totals in s_out[0..NV); returns false on a peer timeout.
-template <int NV>
+template <int NV, int NW>
 __device__ __forceinline__ bool ll_reduceN(const CgArgs& A, double (&v)[NV], int parity, unsigned int tag, int my_rank, int cta, int G, int W,
                                            bool sys_release, unsigned long long& arrived, double* sred, double* s_out, double* s_part /* [kMaxPeers*NV] */,
-                                           double* s_flat /* [NV * G] */, int* s_flag) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+                                           int* s_flag) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   cta_reduceN<NV>(v, sred);
   char* const mine = A.arena[my_rank];
   double* lbuf = reinterpret_cast<double*>(mine + A.off_partial) + (size_t)(parity & 1) * NV * G;
@@ -831,17 +857,9 @@ __device__ __forceinline__ bool ll_reduceN(const CgArgs& A, double (&v)[NV], int
   __syncthreads();
   if (s_flag[0]) {
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    const int tot = NV * G;
-#pragma unroll 4
-    for (int e = threadIdx.x; e < tot; e += blockDim.x) s_flat[e] = __ldcg(lbuf + e);
-    __syncthreads();
-    for (int c = wid; c < NV; c += nwarp) {
-      double t = 0;
-      for (int i = lane; i < G; i += 32) t += s_flat[c * G + i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane < W) ll_store(reinterpret_cast<ulonglong2*>(A.arena[lane] + roff) + (size_t)my_rank * NV + c, t, tag);
-    }
+    sum_partials<NV, NW>(lbuf, G, [&](int c, double tot) {
+      if (lane < W) ll_store(reinterpret_cast<ulonglong2*>(A.arena[lane] + roff) + (size_t)my_rank * NV + c, tot, tag);
+    });
   }
   // all CTAs: wait for the W x NV rank totals, one slot per thread
   if ((int)threadIdx.x < W * NV) {
@@ -877,7 +895,6 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
   __shared__ double s_out[NV + 1];
   __shared__ double s_part[MULTI ? kMaxPeers * NV : 1];
   __shared__ double s_einv[KD > 0 ? KD * KD : 1];
-  __shared__ double s_flat[NV * kCgMaxCtas];
   __shared__ int s_flag[2];
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, wid = threadIdx.x >> 5;
   const int la = lane % NCL, ls = lane / NCL;
@@ -940,7 +957,12 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
   double* const xl = reinterpret_cast<double*>(mine + A.off_x);
   int it = 0, status = 1;
   bool peers_ok = true;
+  const bool profiling = A.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  long long tprof = profiling ? clock64() : 0;
+#define PTZ_CG_PROF(slot)                                                        \
+  if (profiling) { const long long tn = clock64(); A.prof[slot] += (double)(tn - tprof); tprof = tn; }
   for (;; ++it) {
+    PTZ_CG_PROF(7)
     const double* so = reinterpret_cast<const double*>(mine + off_o);
     double* const sn = reinterpret_cast<double*>(mine + off_n);
     // LL inboxes: state(it-1) was pushed with tag0 + it into buffer (it-1)&1; state(it) goes out with tag0 + it + 1 into it&1
@@ -1140,11 +1162,13 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
         acc[0] += rn * rn; acc[1] += tot * rn;
       }
     }
+    PTZ_CG_PROF(0)  // rows: owner update + sparse product
     if (A.debug & 2) { s_out[0] = 1.0 / (it + 1.0); s_out[1] = 1.0; __syncthreads(); }
     else if (MULTI) {
-      if (!ll_reduceN<NV>(A, acc, it, tag_wr, my_rank, cta, G, W, false, arrived, sred, s_out, s_part, s_flat, s_flag)) peers_ok = false;
+      if (!ll_reduceN<NV, MAXT / 32>(A, acc, it, tag_wr, my_rank, cta, G, W, false, arrived, sred, s_out, s_part, s_flag)) peers_ok = false;
       if (__syncthreads_or(peers_ok ? 0 : 1)) { status = 3; break; }
-    } else grid_reduceN<NV>(A, acc, it, arrived, sred, s_out, s_flat);
+    } else grid_reduceN<NV, MAXT / 32>(A, acc, it, arrived, sred, s_out);
+    PTZ_CG_PROF(1)  // reduction + barrier
     const double g = s_out[0], d = s_out[1];
     // mu = E^-1 nu (lane c < KD computes mu_c, then every lane collects the vector) and mu^T nu, identically in every warp
     double mu_nu = 0.0;
@@ -1162,6 +1186,7 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
       for (int dd = 0; dd < KD; ++dd) mus[dd] = __shfl_sync(0xffffffffu, mu_l, dd);
     }
     // (s_out is next written behind the barriers of the next reduction: no extra barrier needed here)
+    PTZ_CG_PROF(2)  // mu
     gamma_last = g;
     if (it == 0) {
       gamma0 = (KD > 0) ? A.dscal[0] : g;  // deflated: x0 = W E^-1 W^T b~ already took part of b~ away; measure against |b~|
@@ -1182,6 +1207,7 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
     gamma_old = g;
     const size_t t = off_o; off_o = off_n; off_n = t;
   }
+#undef PTZ_CG_PROF
   if (MULTI && status != 3) {
     // every rank needs the whole solution: push the owned rows of x (plain stores) into the other replicas, then meet once
     // more -- this time behind a system-scope release -- so that nobody leaves before all pushes have landed
@@ -1198,7 +1224,7 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
     double z[NV];
 #pragma unroll
     for (int c = 0; c < NV; ++c) z[c] = 0.0;
-    if (!ll_reduceN<NV>(A, z, it + 1, tag0 + (unsigned int)it + 2u, my_rank, cta, G, W, true, arrived, sred, s_out, s_part, s_flat, s_flag)) status = 3;
+    if (!ll_reduceN<NV, MAXT / 32>(A, z, it + 1, tag0 + (unsigned int)it + 2u, my_rank, cta, G, W, true, arrived, sred, s_out, s_part, s_flag)) status = 3;
   }
   if (cta == 0 && threadIdx.x == 0) {
     ctrl[1] = arrived;
@@ -1230,26 +1256,27 @@ __global__ void k_defl_scale_basis(int V, const double* __restrict__ T /* L, or 
     out[((size_t)v * NCL + a) * kDeflK + c] = s;
   }
 }
-// Out = S~ In for the kDeflK columns at once.  One warp per row: lane = column + 16 * half, the two halves take alternate
-// blocks of the row, four blocks in flight per half (the walk is latency-bound: index -> gather).  Rows of other ranks (owner
-// != my_rank >= 0) are written as zeros: the caller sums the ranks' pieces.  Fixed summation order.
+// Out = S~ In for the kDeflK columns at once.  One CTA (4 warps) per row: lane = column + 16 * half; the 8 half-warps take
+// the blocks of the row round-robin, four blocks in flight each (the walk is latency-bound: index -> gather), and the partial
+// sums meet in shared memory in a fixed order.  Rows of other ranks (owner != my_rank >= 0) are written as zeros: the caller
+// sums the ranks' pieces.
 template <int NCL>
-__global__ void __launch_bounds__(256) k_defl_spmm(int V, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ Sval,
+__global__ void __launch_bounds__(128) k_defl_spmm(int V, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ Sval,
                                                    const double* __restrict__ in, double* __restrict__ out, const unsigned char* __restrict__ row_owner,
                                                    int my_rank) {
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31, c = lane & (kDeflK - 1), h = lane >> 4;
   static_assert(kDeflK == 16, "lane layout");
-  if (r >= V) return;
+  __shared__ double sacc[8][NCL][kDeflK];
+  const int r = blockIdx.x, t = threadIdx.x, c = t & (kDeflK - 1), hw = t >> 4;  // hw: half-warp 0..7
   double acc[NCL];
 #pragma unroll
   for (int a = 0; a < NCL; ++a) acc[a] = 0.0;
   if (my_rank < 0 || row_owner[r] == my_rank) {
     const int k1 = rowptr[r + 1];
-    for (int k = rowptr[r] + h; k < k1; k += 8) {
+    for (int k = rowptr[r] + hw; k < k1; k += 32) {
       int j[4];
       double x[4][NCL];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) j[u] = (k + 2 * u < k1) ? col[k + 2 * u] : -1;
+      for (int u = 0; u < 4; ++u) j[u] = (k + 8 * u < k1) ? col[k + 8 * u] : -1;
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -1257,7 +1284,7 @@ __global__ void __launch_bounds__(256) k_defl_spmm(int V, const int* __restrict_
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (j[u] < 0) continue;
-        const double* B = Sval + (size_t)(k + 2 * u) * NCL * NCL;
+        const double* B = Sval + (size_t)(k + 8 * u) * NCL * NCL;
 #pragma unroll
         for (int a = 0; a < NCL; ++a)
 #pragma unroll
@@ -1266,10 +1293,14 @@ __global__ void __launch_bounds__(256) k_defl_spmm(int V, const int* __restrict_
     }
   }
 #pragma unroll
-  for (int a = 0; a < NCL; ++a) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], 16);
-  if (h == 0) {
+  for (int a = 0; a < NCL; ++a) sacc[hw][a][c] = acc[a];
+  __syncthreads();
+  for (int e = t; e < NCL * kDeflK; e += 128) {
+    const int a = e / kDeflK, cc = e % kDeflK;
+    double s = 0;
 #pragma unroll
-    for (int a = 0; a < NCL; ++a) out[((size_t)r * NCL + a) * kDeflK + c] = acc[a];
+    for (int q = 0; q < 8; ++q) s += sacc[q][a][cc];
+    out[((size_t)r * NCL + a) * kDeflK + cc] = s;
   }
 }
 // E = W^T (AW), nu0 = W^T b~, |b~|^2 as per-CTA partial sums over chunks of 256 unknowns (b~ = the r component of the initial CG
@@ -1313,18 +1344,32 @@ __global__ void __launch_bounds__(256) k_defl_gram(int V, const double* __restri
 // one warp: sums the chunk partials in chunk order, Cholesky of E (symmetrised), Einv, c0 = Einv nu0; dscal[0] = |b~|^2,
 // dscal[1] = 1 when every pivot is safely positive, else 0 (the solve then runs undeflated).  kd <= kDeflK columns are in use;
 // the rest of Einv is zero.
-__global__ void __launch_bounds__(32) k_defl_small(int kd, int nchunk, const double* __restrict__ partial, double* __restrict__ Einv,
-                                                   double* __restrict__ c0, double* __restrict__ dscal) {
+constexpr int kDeflSmallThreads = 288;  // >= kDeflGramVals: one thread per reduced value, then warp 0 factors E
+__global__ void __launch_bounds__(kDeflSmallThreads) k_defl_small(int kd, int nchunk, const double* __restrict__ partial, double* __restrict__ Einv,
+                                                                  double* __restrict__ c0, double* __restrict__ dscal) {
   __shared__ double A[kDeflK * kDeflK], Li[kDeflK * kDeflK], nu[kDeflK];
-  const int lane = threadIdx.x;
-  for (int e = lane; e < kDeflGramVals; e += 32) {
-    double s = 0;
-    for (int c = 0; c < nchunk; ++c) s += partial[(size_t)c * kDeflGramVals + e];
-    if (e < kDeflK * kDeflK) A[e] = s;
-    else if (e < kDeflK * kDeflK + kDeflK) nu[e - kDeflK * kDeflK] = s;
-    else dscal[0] = s;
+  static_assert(kDeflSmallThreads >= kDeflGramVals, "one thread per value");
+  {
+    const int e = threadIdx.x;
+    if (e < kDeflGramVals) {
+      double s = 0;
+      int c = 0;
+      for (; c + 8 <= nchunk; c += 8) {  // eight loads in flight; summed in chunk order
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = partial[(size_t)(c + u) * kDeflGramVals + e];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+      }
+      for (; c < nchunk; ++c) s += partial[(size_t)c * kDeflGramVals + e];
+      if (e < kDeflK * kDeflK) A[e] = s;
+      else if (e < kDeflK * kDeflK + kDeflK) nu[e - kDeflK * kDeflK] = s;
+      else dscal[0] = s;
+    }
   }
-  __syncwarp();
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
   for (int e = lane; e < kDeflK * kDeflK; e += 32) {  // symmetrise (lower triangle is what the factorisation reads)
     const int i = e / kDeflK, j = e % kDeflK;
     if (i > j) A[e] = 0.5 * (A[i * kDeflK + j] + A[j * kDeflK + i]);

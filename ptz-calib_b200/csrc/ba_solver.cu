@@ -301,12 +301,13 @@ struct BaSolver : BaSolverBase {
     return deflated ? cg_kernel_sel<false, kDeflK>() : cg_kernel_sel<false, 0>();
   }
   // ---- deflation of the CG (k_cg<.., KD = kDeflK>): basis harvested from the residual history of the first solve of a run
-  bool defl_enabled = false, have_W = false;
-  int defl_kd = 0, defl_solves = 0, defl_rejects = 0;
-  static constexpr int kHistCap = 320, kMinHarvest = 40;
+  bool defl_enabled = false, have_W = false, defl_active = true;
+  int defl_kd = 0, defl_solves = 0, defl_rejects = 0, last_lin_iters = -1;
+  static constexpr int kHistCap = 320, kMinHarvest = 40, kDeflOffBelow = 12, kDeflOnAbove = 30;
   DevBuf<double> d_hist, d_abg, d_Wy, d_Wt, d_AW, d_Z, d_gram, d_Einv, d_c0, d_dscal, d_bcopy, d_Lfac, d_Y;
   std::vector<double> h_abg;
   double h_dscal[2] = {0, 0};
+  DevBuf<double> d_prof;
 
   // LM state (names follow ceres::internal::TrustRegionMinimizer / LevenbergMarquardtStrategy)
   double radius = 0, decrease_factor = 2.0, x_cost = 0, x_norm = 0, min_cost = 0, initial_cost = 0, grad_max = 0;
@@ -518,6 +519,15 @@ struct BaSolver : BaSolverBase {
 
   ~BaSolver() {
     cudaStreamSynchronize(stream);
+    if (d_prof.n) {
+      double pr[16];
+      cudaMemcpy(pr, d_prof.p, sizeof(pr), cudaMemcpyDeviceToHost);
+      const char* names[8] = {"rows (update + product)", "reduction + barrier (total)", "mu", "  cta reduce", "  store + arrive + spin", "  fetch partials", "  sum partials", "loop head"};
+      for (int k = 0; k < 2; ++k) {
+        fprintf(stderr, "[k_cg profile, %s] cycles of CTA 0 / thread 0 over all solves:\n", k ? "deflated" : "plain");
+        for (int i = 0; i < 8; ++i) fprintf(stderr, "   %-30s %14.0f\n", names[i], pr[8 * k + i]);
+      }
+    }
     HostCache::put_pinned(h_scalars);
     HostCache::put_pinned(h_info);
   }
@@ -704,6 +714,7 @@ struct BaSolver : BaSolverBase {
     log.clear();
     if (have_W || (defl_enabled && d_hist.n == 0)) {  // every solve harvests its own deflation basis: runs are bit-reproducible
       have_W = false;
+      defl_active = true; last_lin_iters = -1;
       if (defl_enabled && d_hist.n == 0) d_hist.alloc((size_t)kHistCap * V * NCL, stream);
     }
     // kernel timings keep accumulating across resets (bench.py times several solves); see ptzba_get_stage_times
@@ -826,7 +837,14 @@ struct BaSolver : BaSolverBase {
                                               d_cgp.p);
     });
     // ---- stages 3 and 4
-    const bool deflate = defl_enabled && have_W;
+    // Deflation pays when the plain iteration would sit on its plateau (hundreds of steps while the step is large); near
+    // convergence a solve takes a handful of iterations and the set-up of the deflated one (~0.1 ms) costs more than it saves.
+    // The previous solve's count decides: plain after a short deflated solve, deflated again after a long plain one.
+    if (have_W) {
+      if (defl_active && last_lin_iters >= 0 && last_lin_iters < kDeflOffBelow) defl_active = false;
+      else if (!defl_active && last_lin_iters > kDeflOnAbove) defl_active = true;
+    }
+    const bool deflate = defl_enabled && have_W && defl_active;
     const bool record = defl_enabled && !have_W;  // undeflated solve: keep its residual history for the deflation basis
     linear_solve(deflate, record, false);
     launch_stage4(mu);
@@ -848,6 +866,7 @@ struct BaSolver : BaSolverBase {
     }
     ++cost_evals;
     *lin_iters = h_info[0];
+    last_lin_iters = h_info[0];
     if (h_info[2] != 0) return false;          // a 3x3 / camera / border block was not positive definite
     if (h_info[1] == 3) throw CudaError(PTZ_ERR_NCCL, "k_cg: a peer rank did not reach the cross-GPU barrier (timeout)");
     if (h_info[1] == 2) return false;          // PCG breakdown (non-finite or non-positive curvature)
@@ -875,6 +894,11 @@ struct BaSolver : BaSolverBase {
     { const char* e = getenv("PTZ_CG_DEBUG"); a.debug = e ? atoi(e) : 0; }
     a.dW = d_Wt.p; a.dAW = d_AW.p; a.dZ = d_Z.p; a.dEinv = d_Einv.p; a.dscal = d_dscal.p;
     a.hist = record ? d_hist.p : nullptr; a.hist_cap = kHistCap; a.abg = record ? d_abg.p : nullptr;
+    a.prof = nullptr;
+    if (a.debug & 8) {  // per-phase cycle counters of CTA 0 (printed by the destructor)
+      if (d_prof.n == 0) { d_prof.alloc(16, s); d_prof.zero(s); }
+      a.prof = d_prof.p + (deflate ? 8 : 0);
+    }
     const size_t cg_smem = cg_smem_bytes(deflate);
     void* args[] = {&a};
     if (restart) k_cg_restart<NCL><<<cdiv(ncam, 256), 256, 0, s>>>(V, d_bcopy.p, arena_ptr(ar_st0), arena_ptr(ar_x), d_cgp.p);
@@ -882,11 +906,11 @@ struct BaSolver : BaSolverBase {
       PTZ_TIMED(PTZ_K_DEFLATE, {
         const int nchunk = cdiv(ncam, kDeflGramChunk);
         k_defl_scale_basis<NCL><<<cdiv(V * kDeflK, 256), 256, 0, s>>>(V, d_Lfac.p, d_Wy.p, d_Wt.p);  // W~ = L^T W_y
-        k_defl_spmm<NCL><<<cdiv(V, 8), 256, 0, s>>>(V, ds.s_rowptr.p, ds.s_col.p, p_Sval, d_Wt.p, d_AW.p, d_cg_owner.p, mr);
+        k_defl_spmm<NCL><<<V, 128, 0, s>>>(V, ds.s_rowptr.p, ds.s_col.p, p_Sval, d_Wt.p, d_AW.p, d_cg_owner.p, mr);
         allreduce_sum(d_AW.p, nk, s);  // sharded rows: every rank needs all of AW (for E and for the start vector)
-        k_defl_spmm<NCL><<<cdiv(V, 8), 256, 0, s>>>(V, ds.s_rowptr.p, ds.s_col.p, p_Sval, d_AW.p, d_Z.p, d_cg_owner.p, mr);
+        k_defl_spmm<NCL><<<V, 128, 0, s>>>(V, ds.s_rowptr.p, ds.s_col.p, p_Sval, d_AW.p, d_Z.p, d_cg_owner.p, mr);
         k_defl_gram<NCL><<<nchunk, 256, 0, s>>>(V, d_Wt.p, d_AW.p, arena_ptr(ar_st0), d_gram.p, d_bcopy.p);
-        k_defl_small<<<1, 32, 0, s>>>(defl_kd, nchunk, d_gram.p, d_Einv.p, d_c0.p, d_dscal.p);
+        k_defl_small<<<1, kDeflSmallThreads, 0, s>>>(defl_kd, nchunk, d_gram.p, d_Einv.p, d_c0.p, d_dscal.p);
         k_defl_start<NCL><<<cdiv(ncam, 256), 256, 0, s>>>(V, d_Wt.p, d_AW.p, d_c0.p, d_dscal.p, arena_ptr(ar_st0), arena_ptr(ar_x));
       });
     PTZ_TIMED(PTZ_K_PCG, {
@@ -917,6 +941,7 @@ struct BaSolver : BaSolverBase {
     k_defl_scale_basis<NCL><<<cdiv(V * kDeflK, 256), 256, 0, s>>>(V, d_Linv.p, d_Wt.p, d_Wy.p);
     PTZ_CUDA(cudaGetLastError());
     have_W = true;
+    defl_active = true;
     defl_kd = kd;
     d_hist.release();  // (stream-ordered: goes back to the block cache behind the kernels above)
     if (opt.verbose) printf("[ptzba] deflation basis: %d Ritz vectors from %d CG iterations\n", kd, m);

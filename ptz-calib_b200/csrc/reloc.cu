@@ -347,6 +347,36 @@ __global__ void k_reloc_eval(int N, const float2* uv_ref, const float2* uv_cur, 
   for (int j = 0; j < 2 * NF; ++j) jac[(size_t)i * 2 * NF + j] = J[j];
 }
 
+// KRTOptimizer::Cal2d2dReprojError / Cal2d3dReprojError (krt_optimizer.cc:406-500): sums of squared functor residuals at the
+// given local parameters, one CTA; out[0] = sum over the matches, out[1] = sum over the 2d-3d points
+template <int TYPE>
+__global__ void __launch_bounds__(256) k_reloc_reproj(int N, const float2* __restrict__ uv_ref, const float2* __restrict__ uv_cur, int npts,
+                                                      const float2* __restrict__ puv, const double* __restrict__ pxyz, const double* __restrict__ ref21,
+                                                      const double* __restrict__ local15, double* __restrict__ out) {
+  __shared__ double sred[2 * 8];
+  double refK4[4], refd[5], x[15];
+  for (int j = 0; j < 4; ++j) refK4[j] = ref21[j];
+  for (int j = 0; j < 5; ++j) refd[j] = ref21[16 + j];
+  for (int j = 0; j < 15; ++j) x[j] = local15[j];
+  KrtCam kc;
+  krt_make_cam<TYPE>(x, &kc, false);
+  double acc[2] = {0, 0};
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double n[3], r[2] = {0, 0};
+    if (krt_precompute(TYPE, refK4, refd, uv_ref[i].x, uv_ref[i].y, n)) krt_obs<TYPE, false>(kc, n, (double)uv_cur[i].x, (double)uv_cur[i].y, r, nullptr);
+    acc[0] += r[0] * r[0] + r[1] * r[1];
+  }
+  for (int i = threadIdx.x; i < npts; i += blockDim.x) {
+    const double* Rr = ref21 + 4;
+    double P[3], r[2];
+    for (int a = 0; a < 3; ++a) P[a] = Rr[3 * a] * pxyz[3 * i] + Rr[3 * a + 1] * pxyz[3 * i + 1] + Rr[3 * a + 2] * pxyz[3 * i + 2] + ref21[13 + a];
+    krt_obs3d<TYPE, false>(kc, x + 7, P, (double)puv[i].x, (double)puv[i].y, r, nullptr);
+    acc[1] += r[0] * r[0] + r[1] * r[1];
+  }
+  block_sum<2>(acc, sred);
+  if (threadIdx.x == 0) { out[0] = acc[0]; out[1] = acc[1]; }
+}
+
 static void launch_reloc(int type, const RelocArgs& a, int max_matches, cudaStream_t s) {
   // dynamic shared memory: 32 B per staged match, capped so that several CTAs still share an SM
   const int cap_matches = 2048;
@@ -504,6 +534,46 @@ int ptzreloc_eval(int type, int N, const float* uv_ref, const float* uv_cur, con
     if (jac) memcpy(jac, J.data(), J.size() * 8);
     if (cost) *cost = c;
     if (gradient) memcpy(gradient, g.data(), nf * 8);
+    return (int)PTZ_OK;
+  });
+}
+
+int ptzreloc_local_params(const double* ref21, const double* init21, double* local15) {
+  if (!ref21 || !init21 || !local15) return PTZ_ERR_INVALID;
+  krt_to_local(ref21, init21, local15);  // host instantiation of the routine the kernel runs per query
+  return PTZ_OK;
+}
+
+int ptzreloc_reproj_error(int type, const double* ref21, const double* local15, int N, const float* uv_ref, const float* uv_cur, int npts,
+                          const float* pt_uv, const double* pt_xyz, double* err_2d2d, double* err_2d3d) {
+  if (type < 0 || type > 3 || N < 0 || npts < 0 || !ref21 || !local15) return PTZ_ERR_INVALID;
+  if ((N > 0 && (!uv_ref || !uv_cur)) || (npts > 0 && (!pt_uv || !pt_xyz))) return PTZ_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_last_error("no CUDA device; this library has no CPU fallback"); return PTZ_ERR_NO_DEVICE; }
+  return guarded_r([&]() {
+    cudaStream_t s = 0;
+    DevBuf<float2> d_ur, d_uc, d_pu;
+    DevBuf<double> d_ref, d_x, d_px, d_out;
+    d_ur.upload(reinterpret_cast<const float2*>(uv_ref), N, s);
+    d_uc.upload(reinterpret_cast<const float2*>(uv_cur), N, s);
+    d_pu.upload(reinterpret_cast<const float2*>(pt_uv), npts, s);
+    d_px.upload(pt_xyz, 3 * (size_t)npts, s);
+    d_ref.upload(ref21, 21, s);
+    d_x.upload(local15, 15, s);
+    d_out.alloc(2);
+    switch (type) {
+      case KRT_F: k_reloc_reproj<KRT_F><<<1, 256, 0, s>>>(N, d_ur.p, d_uc.p, npts, d_pu.p, d_px.p, d_ref.p, d_x.p, d_out.p); break;
+      case KRT_FDIST: k_reloc_reproj<KRT_FDIST><<<1, 256, 0, s>>>(N, d_ur.p, d_uc.p, npts, d_pu.p, d_px.p, d_ref.p, d_x.p, d_out.p); break;
+      case KRT_FXFY: k_reloc_reproj<KRT_FXFY><<<1, 256, 0, s>>>(N, d_ur.p, d_uc.p, npts, d_pu.p, d_px.p, d_ref.p, d_x.p, d_out.p); break;
+      default: k_reloc_reproj<KRT_FXFYDIST><<<1, 256, 0, s>>>(N, d_ur.p, d_uc.p, npts, d_pu.p, d_px.p, d_ref.p, d_x.p, d_out.p); break;
+    }
+    PTZ_CUDA(cudaGetLastError());
+    double h[2] = {0, 0};
+    d_out.download(h, 2, s);
+    PTZ_CUDA(cudaStreamSynchronize(s));
+    // sqrt(sum / count): NaN for an empty match list, as the reference's 0/0; -1 without points (krt_optimizer.cc:459-460)
+    if (err_2d2d) *err_2d2d = sqrt(h[0] / (double)N);
+    if (err_2d3d) *err_2d3d = npts > 0 ? sqrt(h[1] / (double)npts) : -1.0;
     return (int)PTZ_OK;
   });
 }

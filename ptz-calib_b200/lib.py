@@ -11,7 +11,7 @@ EXPORTS = [
     "ptz_solver_options_default", "ptz_last_error", "ptz_device_count",
     "ptzba_solve", "ptzba_eval", "ptzba_create", "ptzba_reset", "ptzba_run", "ptzba_get_stage_times", "ptzba_destroy",
     "ptz_nccl_unique_id", "ptz_nccl_init", "ptz_nccl_finalize",
-    "ptzreloc_solve_batch", "ptzreloc_eval", "ptzreloc_solve_batch_dev",
+    "ptzreloc_solve_batch", "ptzreloc_eval", "ptzreloc_solve_batch_dev", "ptzreloc_reproj_error", "ptzreloc_local_params",
     "ptztracks_build", "ptztracks_build_dev", "ptztracks_flatten",
 ]
 
@@ -20,12 +20,30 @@ class PtzLibraryError(RuntimeError):
     pass
 
 
+def _preload_nccl():
+    """The library links libnccl.so.2.  PyTorch ships its own (newer) copy under site-packages/nvidia/nccl and needs ITS symbols: if
+    ours pulled the system copy in first, a later `import torch` in the same process would fail to resolve them.  Loading torch's
+    copy first (when there is one) makes both bind to the same library whatever the import order."""
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 def load():
     global _LIB
     if _LIB is None:
         if not os.path.exists(SO_PATH):
             raise PtzLibraryError(f"{SO_PATH} is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
                                   "(there is no CPU fallback for the solver path)")
+        _preload_nccl()
         L = C.CDLL(SO_PATH, mode=C.RTLD_GLOBAL)
         for name in EXPORTS:
             getattr(L, name).restype = C.c_int

@@ -54,10 +54,11 @@ def ptz_rotation(pan, tilt, roll):
     return Rz @ Rx @ Ry
 
 
-def project(R, f, c, k1, n):
-    """n [..,3] local directions/points -> pixels with the Brown k1 term; returns (uv, z)"""
+def project(R, f, c, k1, n, dz=0.0):
+    """n [..,3] local directions/points -> pixels with the Brown k1 term; returns (uv, z).  dz: displacement added to the depth
+    (the d0 + d1 f + d2 f^2 of PTZRayDistDispFactor / Reproj2d3dDispFactor, ptzray_optimizer.cc:231-232,368-369)"""
     X = np.einsum("...ij,...j->...i", R, n)
-    z = X[..., 2]
+    z = X[..., 2] + dz
     zz = np.where(np.abs(z) > 1e-12, z, 1e-12)
     x, y = X[..., 0] / zz, X[..., 1] / zz
     rad = 1.0 + k1 * (x * x + y * y)
@@ -94,7 +95,7 @@ def _views(cfg, rng, V, width, height):
 
 def make_ba_scene(V, P, layout="ring", factor_type=abi.PTZ_BA_PTZRAY, seed=1001, width=1920, height=1080, sigma=0.5, mean_extra_len=1.0,
                   max_len=None, rot_noise_deg=0.5, focal_noise=0.02, num_pts3d=0, pts3d_views=3, track_seed=None, k1_init_ratio=0.8,
-                  gt_init=False, neighbours=24):
+                  gt_init=False, neighbours=24, focal_range=None, disp_gt=None, k1_scale=-0.08):
     """One PTZ-BA problem: V views, ~P tracks (those with < 4 visible views are dropped, so the result has <= P).
 
     track_seed: tracks are drawn from an independent stream so that ranks of a multi-GPU run can each generate
@@ -102,10 +103,14 @@ def make_ba_scene(V, P, layout="ring", factor_type=abi.PTZ_BA_PTZRAY, seed=1001,
     """
     rng = np.random.default_rng(seed)
     R, f, c, k1 = _views(layout, rng, V, width, height)
+    if focal_range is not None:  # zoom sweep (drawn from its own stream: the other draws of the scene stay what they were)
+        f = np.exp(np.random.default_rng(seed + 77).uniform(np.log(focal_range[0]), np.log(focal_range[1]), V))
+    # true displacement of the projection centre along the optical axis, a polynomial of the focal length (DistDisp scenes)
+    dz = np.zeros(V) if disp_gt is None else disp_gt[0] + disp_gt[1] * f + disp_gt[2] * f * f
     if factor_type == abi.PTZ_BA_PTZRAY:
         k1 = np.zeros(V)
     elif layout != "broadcast":
-        k1 = -0.08 * (1500.0 / f)
+        k1 = k1_scale * (1500.0 / f)
     # initial guess (drawn before the tracks so it does not depend on track_seed)
     rvec_gt = log_so3(R)
     if gt_init:
@@ -131,7 +136,7 @@ def make_ba_scene(V, P, layout="ring", factor_type=abi.PTZ_BA_PTZRAY, seed=1001,
         ray = np.einsum("nji,nj->ni", R[anchor], d)  # R^T d
         _, nb = tree.query(ray, k=kq)
         nb = nb.reshape(n, kq)
-        uv, z = project(R[nb], f[nb], c[nb], k1[nb], ray[:, None, :])
+        uv, z = project(R[nb], f[nb], c[nb], k1[nb], ray[:, None, :], dz[nb])
         vis = (z > 0.1) & (uv[..., 0] >= 0) & (uv[..., 0] < width) & (uv[..., 1] >= 0) & (uv[..., 1] < height)
         want = 4 + trng.poisson(mean_extra_len, n)
         if max_len is not None:
@@ -165,7 +170,7 @@ def make_ba_scene(V, P, layout="ring", factor_type=abi.PTZ_BA_PTZRAY, seed=1001,
     intr[:, 0], intr[:, 1], intr[:, 2], intr[:, 3], intr[:, 4] = f0, f0, c[:, 0], c[:, 1], k10
     ext = np.zeros((V, 6))
     ext[:, :3] = log_so3(R0)
-    gt = dict(R=R, f=f, c=c, k1=k1, rvec=rvec_gt, rays=rays, width=width, height=height)
+    gt = dict(R=R, f=f, c=c, k1=k1, rvec=rvec_gt, rays=rays, width=width, height=height, disp=None if disp_gt is None else np.asarray(disp_gt, float))
 
     pt_uv = pt_xyz = pt_view = tlw0 = None
     if num_pts3d > 0:
@@ -181,7 +186,7 @@ def make_ba_scene(V, P, layout="ring", factor_type=abi.PTZ_BA_PTZRAY, seed=1001,
             dd = np.stack([(pxs[:, 0] - c[vi, 0]) / f[vi], (pxs[:, 1] - c[vi, 1]) / f[vi], np.ones(per)], -1)
             Xl = (R[vi].T @ dd.T).T * rng.uniform(30, 90, (per, 1))
             Xw = (Rlw.T @ (Xl - tlw).T).T
-            uvp, _ = project(R[vi], f[vi], c[vi], k1[vi], Xl)
+            uvp, _ = project(R[vi], f[vi], c[vi], k1[vi], Xl, dz[vi])
             pu.append((uvp + rng.normal(0, sigma, uvp.shape)).astype(np.float32))
             px3.append(Xw)
             pv.append(np.full(per, vi, np.int32))
@@ -212,6 +217,15 @@ def make_config(cfg, scale=1.0, factor_type=None, **kw):
         return make_ba_scene(max(8, int(10000 * s)), int(10000000 * s), "band", abi.PTZ_BA_PTZRAY if factor_type is None else factor_type,
                              seed=SEEDS[5], **kw)
     raise ValueError(cfg)
+
+
+def make_distdisp_scene(num_pts3d=0, V=12, P=3000, seed=1001, **kw):
+    """A scene on which PTZRayDistDispFactor's global disp[3] is OBSERVABLE: the data carry a true displacement polynomial
+    d0 + d1 f + d2 f^2 of the projection centre, the views sweep the zoom range (f log-uniform in [500, 2600] px, so that 1, f, f^2
+    separate and the wide end has enough perspective for the depth offset to differ from a focal change) and the distortion is
+    mild (Pix2Ray, the reference's ray initialisation, ignores it: ptzray_optimizer.cc:768-797).  Converges in tens of iterations."""
+    return make_ba_scene(V, P, "ring", abi.PTZ_BA_PTZRAY_DIST_DISP, seed=seed, neighbours=12, focal_range=(500.0, 2600.0),
+                         disp_gt=(0.03, -2e-5, 6e-9), k1_scale=-0.002, num_pts3d=num_pts3d, **kw)
 
 
 # ------------------------------------------------------------------------------------------ reloc batches

@@ -74,7 +74,10 @@ int main(int argc, char** argv) {
   for (int i = 0; i < N; ++i) { k1[i].pt.x = uv1[2 * i]; k1[i].pt.y = uv1[2 * i + 1]; k2[i].pt.x = uv2[2 * i]; k2[i].pt.y = uv2[2 * i + 1]; mm[i].queryIdx = i; mm[i].trainIdx = i; }
   krt.Add2d2dConstraints(cref, k1, k2, mm);
   Mat33 K, R; Vec3 t; Vec5 dist;
+  const double err_before = krt.Cal2d2dReprojError(cref, k1, k2, mm);  // krt_optimizer.cc:406-455, at the initial parameters
   const bool ok_krt = krt.Solve(K, R, t, dist);
+  const double err_after = krt.Cal2d2dReprojError(cref, k1, k2, mm);   // ... and at the refined ones
+  const double err_pts = krt.Cal2d3dReprojError(std::vector<Point2f>(), std::vector<Point3d>());  // -1 without points (:459-460)
 
   FILE* g = fopen(argv[2], "wb");
   double head[10] = {(double)ok, (double)ba.num_iterations(), ba.final_reproj_error_all(), ba.final_reproj_error_2d2d(), (double)ba.tracks().size(), (double)nrays,
@@ -83,6 +86,8 @@ int main(int argc, char** argv) {
   for (int i = 0; i < V; ++i) { double a[21]; cameras[i].ToKrt21(a); fwrite(a, sizeof(double), 21, g); }
   Camera out(K, R, t, dist);
   double a[21]; out.ToKrt21(a); fwrite(a, sizeof(double), 21, g);
+  double errs[3] = {err_before, err_after, err_pts};
+  fwrite(errs, sizeof(double), 3, g);
   fclose(g);
   printf("adaptor_check: ba ok=%d iters=%d err=%.6f tracks=%zu rays=%zu | capped ok=%d untouched=%d | krt ok=%d iters=%d fx=%.4f\n", (int)ok, ba.num_iterations(),
          ba.final_reproj_error_all(), ba.tracks().size(), nrays, (int)ok_capped, (int)same, (int)ok_krt, krt.num_iter_, K[0]);

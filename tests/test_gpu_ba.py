@@ -3,6 +3,8 @@
 Tolerances are the north star's: residuals and gradients 1e-9 relative, final cost 1e-6 relative, refined
 parameters 1e-6 rad / 1e-4 px focal (BASELINE.json).  The oracle's Jacobian here is the exact (dual-number) one;
 the Ceres-CENTRAL emulation is compared separately with its documented noise floor."""
+import os
+
 import numpy as np
 import pytest
 
@@ -230,28 +232,112 @@ def test_device_structure_builder_equals_host_builder():
 
 @pytest.mark.parametrize("npts", [0, 15])
 def test_distdisp_solve_matches_oracle(orc, npts):
-    """PTZRayDistDisp / Reproj2d3dDispFactor (ptzray_optimizer.cc:202-264,335-401): the global disp[3] block in the border.
-    The problem is ill-conditioned by construction (disp multiplies 1, f, f^2 in a pure-rotation scene), so a 150-iteration
-    trajectory amplifies rounding differences; the iteration table is compared row by row over the first iterations, where
-    it must agree to the usual tolerances, and the full solves must end at costs that agree to 1e-3 (1e-2 when both hit the cap)."""
-    t = abi.PTZ_BA_PTZRAY_DIST_DISP
-    p = synth.make_config(1, scale=0.3, factor_type=t, num_pts3d=npts)
-    got = ptz.ba_solve(p, max_num_iterations=8)
-    rc, want = orc.ba_solve(p, max_num_iterations=8)
-    assert rc == 0 and got.num_iterations == want.num_iterations == 8
+    """PTZRayDistDisp / Reproj2d3dDispFactor (ptzray_optimizer.cc:202-264,335-401): the global disp[3] block in the dense border,
+    coupled to every view and every ray.  On a scene where the displacement is observable (synth.make_distdisp_scene: zoom sweep,
+    true displacement in the data) the solve converges and is compared like every other factor type: same termination, iteration
+    count, accept/reject sequence, per-iteration cost 1e-7, final cost 1e-6, parameters 1e-6 rad / 1e-4 px."""
+    p = synth.make_distdisp_scene(num_pts3d=npts)
+    got = ptz.ba_solve(p, max_num_iterations=200)
+    rc, want = orc.ba_solve(p, max_num_iterations=200)
+    assert rc == 0 and want.termination == abi.PTZ_CONVERGENCE and want.num_iterations >= 8
+    check_solve(orc, p, got, want, f"distdisp{npts}")
+    assert got.converged
+    # the estimate means something: the displacement polynomial at a mid-range focal is the one in the data
+    f = np.array([1.0, 1500.0, 1500.0 ** 2])
+    assert abs(got.disp @ f - p.gt["disp"] @ f) < 0.02
+    assert 0.5 < got.final_reproj_error_2d2d < 0.9  # sigma = 0.5 px per axis
+    if npts:
+        assert abs(got.final_reproj_error_2d3d - want.final_reproj_error_2d3d) <= 1e-6 * want.final_reproj_error_2d3d
+        assert np.abs(got.tlw - want.tlw).max() <= 1e-5
+    # the ill-conditioned variant (pure rotation, no zoom sweep: disp is nearly a gauge) still follows the oracle over the first iterations
+    q = synth.make_config(1, scale=0.3, factor_type=abi.PTZ_BA_PTZRAY_DIST_DISP, num_pts3d=npts)
+    g8 = ptz.ba_solve(q, max_num_iterations=8)
+    rc, w8 = orc.ba_solve(q, max_num_iterations=8)
+    assert rc == 0 and g8.num_iterations == w8.num_iterations == 8
+    for lg, lw in zip(g8.log, w8.log):
+        assert lg["step_is_successful"] == lw["step_is_successful"]
+        assert abs(lg["cost"] - lw["cost"]) <= 1e-6 * lw["cost"]
+
+
+@pytest.mark.parametrize("cfg", [1, 2])
+def test_full_cfg1_cfg2_solve_matches_oracle(orc, cfg):
+    """BASELINE cfg 1 (Synthetic-shaped, V=36, PTZRay) and cfg 2 (WorldCup14-shaped, V=60, PTZRayDist) at their FULL size against
+    the oracle's exact path (dense Schur + Cholesky, exact Jacobian)."""
+    p = synth.make_config(cfg)
+    got = ptz.ba_solve(p, max_num_iterations=200)
+    rc, want = orc.ba_solve(p, max_num_iterations=200, num_threads=orc.num_threads())
+    assert rc == 0
+    check_solve(orc, p, got, want, f"cfg{cfg}")
+    assert got.converged
+    e, w = ptz.ba_eval(p), orc.ba_eval(p)
+    assert np.abs(e.residuals - w.residuals).max() <= 1e-9 * np.abs(w.residuals).max()
+    assert np.abs(e.gradient - w.gradient).max() <= 1e-9 * np.abs(w.gradient).max()
+
+
+def test_full_cfg1_georef_matches_oracle(orc):
+    """cfg 1 with its georeferencing stage (~10 annotated points in ~3 views, Reproj2d3dFactor, free T_l_w)"""
+    p = synth.make_config(1, num_pts3d=10)
+    got = ptz.ba_solve(p, max_num_iterations=200)
+    rc, want = orc.ba_solve(p, max_num_iterations=200, num_threads=orc.num_threads())
+    assert rc == 0
+    check_solve(orc, p, got, want, "cfg1-georef")
+    assert np.abs(got.tlw - want.tlw).max() <= 1e-5 and np.abs(got.cams_world - want.cams_world).max() <= 1e-4
+
+
+@pytest.mark.parametrize("scale", [0.25, 1.0])
+def test_cfg4_iterations_match_sparse_oracle(orc, scale):
+    """BASELINE cfg 4 (V=1000, 2e6 observations) at a quarter and at FULL size: the first LM iterations against the oracle's
+    block-sparse path (exact Jacobian, Schur + PCG at the same 1e-13): iteration table row by row, per-iteration cost 1e-7,
+    and the refined parameters after those iterations.  The second and third linear solves on the GPU are deflated ones."""
+    p = synth.make_config(4, scale=scale)
+    n_it = 3
+    got = ptz.ba_solve(p, max_num_iterations=n_it)
+    rc, want = orc.ba_solve(p, max_num_iterations=n_it, linear_solver=1, num_threads=orc.num_threads())
+    assert rc == 0 and got.num_iterations == want.num_iterations == n_it
     assert abs(got.initial_cost - want.initial_cost) <= 1e-11 * want.initial_cost
     for lg, lw in zip(got.log, want.log):
         assert lg["step_is_successful"] == lw["step_is_successful"]
-        assert abs(lg["cost"] - lw["cost"]) <= 1e-6 * lw["cost"]
-        assert abs(lg["trust_region_radius"] - lw["trust_region_radius"]) <= 1e-3 * lw["trust_region_radius"]
-    f = np.array([1.0, 1800.0, 1800.0 ** 2])
-    assert abs((got.disp - want.disp) @ f) <= 1e-5 * max(1.0, abs(want.disp @ f))
-    assert np.abs(got.intr[:, 0] - want.intr[:, 0]).max() <= 1e-3
-    assert np.abs(got.ext - want.ext).max() <= 1e-6
-    full = ptz.ba_solve(p, max_num_iterations=200)
-    rc, wfull = orc.ba_solve(p, max_num_iterations=200)
-    assert full.final_cost <= got.final_cost
-    # (with the annotated points neither run converges within 200 iterations; both stop at the cap a fraction of a percent apart)
-    assert full.termination == wfull.termination
-    assert abs(full.final_cost - wfull.final_cost) <= (1e-3 if full.converged else 1e-2) * wfull.final_cost
-    assert full.cams_world.shape == (p.V, 21) and np.isfinite(full.cams_world).all()
+        assert abs(lg["cost"] - lw["cost"]) <= 1e-7 * lw["cost"]
+        assert abs(lg["gradient_max_norm"] - lw["gradient_max_norm"]) <= 1e-6 * lw["gradient_max_norm"]
+        assert abs(lg["trust_region_radius"] - lw["trust_region_radius"]) <= 1e-4 * lw["trust_region_radius"]
+    assert abs(got.final_cost - want.final_cost) <= 1e-7 * want.final_cost
+    assert np.abs(got.intr[:, 0] - want.intr[:, 0]).max() <= 1e-4
+    assert np.abs(got.ext - want.ext).max() <= 1e-6 and np.abs(got.ray - want.ray).max() <= 1e-6
+    if scale < 1.0:  # (the evaluation hook returns every Jacobian block to the host: quarter size only)
+        e, w = ptz.ba_eval(p), orc.ba_eval(p)
+        assert np.abs(e.residuals - w.residuals).max() <= 1e-9 * np.abs(w.residuals).max()
+        assert np.abs(e.gradient - w.gradient).max() <= 1e-9 * np.abs(w.gradient).max()
+
+
+def test_deflated_cg_same_trajectory(monkeypatch):
+    """the deflated linear solver (Ritz vectors recycled from the first solve) and the plain one give the same LM trajectory, on
+    one GPU and with the rows split over virtual ranks (the multi-GPU kernel variant)"""
+    p = synth.make_config(4, scale=0.2)
+    monkeypatch.setenv("PTZ_CG_DEFLATE", "0")
+    plain = ptz.ba_solve(p, max_num_iterations=60)
+    monkeypatch.setenv("PTZ_CG_DEFLATE", "1")
+    defl = ptz.ba_solve(p, max_num_iterations=60)
+    monkeypatch.setenv("PTZ_CG_VRANKS", "4")
+    defl4 = ptz.ba_solve(p, max_num_iterations=60)
+    monkeypatch.delenv("PTZ_CG_VRANKS")
+    assert plain.converged and defl.linear_solver_iterations < 0.75 * plain.linear_solver_iterations
+    for r in (defl, defl4):
+        assert r.num_iterations == plain.num_iterations and r.termination == plain.termination
+        assert abs(r.final_cost - plain.final_cost) <= 1e-10 * plain.final_cost
+        assert np.abs(r.ext - plain.ext).max() <= 1e-9 and np.abs(r.intr[:, 0] - plain.intr[:, 0]).max() <= 1e-6
+        assert [l["step_is_successful"] for l in r.log] == [l["step_is_successful"] for l in plain.log]
+
+
+def test_multi_gpu_sharded_solve_matches_single_gpu():
+    """Real ranks (one process per GPU, NCCL + the peer-memory CG): the sharded solve reproduces the single-GPU one.  Runs
+    tests/scripts/multi_gpu_check.py under torchrun on 2 devices; skipped on a one-GPU box."""
+    import subprocess
+    import sys
+
+    if ptz.device_count() < 2:
+        pytest.skip("needs >= 2 CUDA devices")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29533",
+           os.path.join(root, "tests", "scripts", "multi_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "MULTI_GPU_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -59,7 +59,13 @@ def test_adaptor_matches_python_path(tmp_path, orc, t):
     assert head[6] == 0.0 and head[7] == 1.0  # capped solve: false, cameras untouched
     rr = ptz.reloc_solve_batch(b)
     assert head[8] == float(rr.success[0]) == 1.0 and int(head[9]) == int(rr.num_iter[0])
-    assert np.abs(krt - rr.cam[0]).max() <= 1e-9
+    assert np.abs(krt[:21] - rr.cam[0]).max() <= 1e-9
+    # Cal2d2dReprojError before / after Solve, Cal2d3dReprojError without points (krt_optimizer.cc:406-500)
+    ref_local = b.ref_cam[0].copy(); ref_local[4:13] = np.eye(3).ravel(); ref_local[13:16] = 0
+    e0, _ = orc.reloc_reproj_error(abi.PTZ_KRT_F, ref_local, orc.krt_to_local(b.ref_cam[0], b.init_cam[0]), b.uv_ref, b.uv_cur)
+    assert abs(krt[21] - e0) <= 1e-9 * e0
+    assert abs(krt[22] - rr.final_rms[0]) <= 1e-9 * rr.final_rms[0] and krt[22] < krt[21]
+    assert krt[23] == -1.0
 
 
 @pytest.mark.gpu

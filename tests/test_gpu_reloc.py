@@ -125,3 +125,36 @@ def test_batch_with_2d3d_constraints_matches_oracle(orc, t):
     assert ok == bool(got.success[q]) and k.num_iter_ == got.num_iter[q]
     if ok:
         assert K[0, 0] == got.cam[q, 0] and np.array_equal(R.reshape(9), got.cam[q, 4:13])
+
+
+@pytest.mark.parametrize("t", [abi.PTZ_KRT_F, abi.PTZ_KRT_FDIST, abi.PTZ_KRT_FXFY, abi.PTZ_KRT_FXFYDIST])
+def test_cal_reproj_errors_match_oracle(orc, t):
+    """KRTOptimizer::Cal2d2dReprojError / Cal2d3dReprojError (krt_optimizer.cc:406-500) through the class mirror: at the initial local
+    parameters (before Solve) and at the refined ones (after), against the oracle's restatement; and the identity
+    Cal2d2dReprojError == sqrt(2)*sqrt(2*final_cost/num_residuals) of CheckResults when there are no 2d-3d terms."""
+    b = synth.make_reloc_batch(6, factor_type=t, n_min=40, n_max=90, pts_per_query=5)
+    for q in range(b.B):
+        o0, o1 = int(b.match_offset[q]), int(b.match_offset[q + 1])
+        p0, p1 = int(b.pt_offset[q]), int(b.pt_offset[q + 1])
+        uv1, uv2 = b.uv_ref[o0:o1], b.uv_cur[o0:o1]
+        ref, init = b.ref_cam[q], b.init_cam[q]
+        k = ptz.KRTOptimizer(200, 100.0, t)
+        c = init
+        k.SetInitParams(np.array([[c[0], 0, c[2]], [0, c[1], c[3]], [0, 0, 1.0]]), c[4:13].reshape(3, 3), c[13:16], c[16:21])
+        m = np.stack([np.arange(o1 - o0), np.arange(o1 - o0)], 1)
+        k.Add2d2dConstraints(ref, uv1, uv2, m)
+        local0 = orc.krt_to_local(ref, init)
+        ref_local = ref.copy(); ref_local[4:13] = np.eye(3).reshape(9); ref_local[13:16] = 0
+        want22, _ = orc.reloc_reproj_error(t, ref_local, local0, uv1, uv2)
+        _, want23 = orc.reloc_reproj_error(t, ref, local0, None, None, b.pt_uv[p0:p1], b.pt_xyz[p0:p1])
+        assert abs(k.Cal2d2dReprojError(ref, uv1, uv2, m) - want22) <= 1e-9 * want22
+        assert abs(k.Cal2d3dReprojError(b.pt_uv[p0:p1], b.pt_xyz[p0:p1]) - want23) <= 1e-9 * want23
+        assert k.Cal2d3dReprojError(np.zeros((0, 2)), np.zeros((0, 3))) == -1.0
+        ok, K, R, tt, dist = k.Solve()
+        single = orc.reloc_solve_batch(b.slice(q, q + 1).__class__(t, [0, o1 - o0], uv1, uv2, ref[None], init[None], b.max_iter, b.max_reproj_error))
+        assert bool(ok) == bool(single.success[0])
+        after22, _ = orc.reloc_reproj_error(t, ref_local, single.local_cam15[0], uv1, uv2)
+        got22 = k.Cal2d2dReprojError(ref, uv1, uv2, m)
+        assert abs(got22 - after22) <= 1e-6 * after22
+        assert abs(got22 - single.final_rms[0]) <= 1e-6 * single.final_rms[0]
+        assert got22 < want22  # the refinement reduced the error

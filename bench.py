@@ -3,13 +3,21 @@
 
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA, through the C ABI)
   python bench.py --impl reference --gpus N --steps K ...  the reference-equivalent CPU path (oracle port), host cores
+  python bench.py --gpus N --config cfg5                   BASELINE cfg 5 at its named size (V = 10,000, 5e7 observations in total)
 
 Workload (config.workload): BASELINE cfg 4 "scaled synthetic PTZ-BA: 1,000 views x 2M observations, full LM with
 Schur + PCG" on one GPU.  With N > 1 the scene grows with N (V = 1000 N views, ~2M observations per rank, tracks
-sharded by observation, NCCL all-reduce of the camera blocks): weak scaling, cfg-5-shaped.
+sharded by observation, NCCL all-reduce of the camera blocks): weak scaling, cfg-5-shaped; --config cfg5 runs cfg 5 itself
+(fixed total size, sharded N ways).
 A STEP is one Levenberg-Marquardt iteration (stages 1-4).  Steps are drawn from complete solves run with the
 reference's own tolerances: when a solve converges the problem is reset and solved again until K steps are done.
-metric = observations x LM iterations per second (Mobs/s); lm_iters_per_sec and the batched-reloc figures ride along.
+metric = observations x LM iterations per second (Mobs/s); lm_iters_per_sec, the small configurations (cfg 1 / cfg 2, LM
+iterations per second), the batched-reloc and the track-building figures ride along.
+
+roofline: the kernel with the largest share of the step (stage 3, k_cg: L2-latency / grid-barrier bound, reported against the HBM
+peak all the same), then one entry per streaming kernel in `roofline_kernels`.  `traffic` comes from hardware counters read IN THIS
+RUN: after the timed region rank 0 runs a few LM iterations of the same scene under ncu (tests/scripts/ncu_counters.py; nothing
+timed there) and takes dram__bytes_read + dram__bytes_write per launch; null when ncu is not available.
 """
 import argparse
 import json
@@ -76,20 +84,81 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
 
 
-def ncu_traffic(factor_type, M):
-    """DRAM bytes per launch of k_resjac from the committed ncu --set full capture (profiles/r1_dram_traffic.json), scaled by
-    the observation count when the launch differs from the profiled one; None when no capture covers this factor type."""
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_dram_traffic.json")) as f:
-            rec = json.load(f).get(f"k_resjac<{factor_type}>")
-        return None if rec is None else int(rec["dram_bytes_per_launch"] * (M / rec["obs"]))
-    except Exception:
+NCU_METRICS = ("dram__bytes_read.sum,dram__bytes_write.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,"
+               "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum")
+NCU_KERNELS = "regex:k_cg|k_resjac|k_obs_what|k_track_factor|k_track_backsub|k_track_accum|k_schur_offdiag|k_schur_diag|k_cost|k_reloc"
+
+
+def hardware_counters(args):
+    """Per-launch DRAM bytes and fp64 operations of the hot kernels, from ncu, measured on this box in this run (side run, untimed):
+    {kernel: {launches, dram_bytes, fp64_flops}} or None when ncu is missing / fails."""
+    import csv
+    import shutil
+
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
         return None
+    log = os.path.join(ROOT, "gpurun_out", "bench_ncu_counters.csv")
+    os.makedirs(os.path.dirname(log), exist_ok=True)
+    cmd = [ncu, "--metrics", NCU_METRICS, "--clock-control", "none", "-k", NCU_KERNELS, "-c", "200", "--csv", "--log-file", log,
+           sys.executable, os.path.join(ROOT, "tests", "scripts", "ncu_counters.py"), str(args.scale), str(args.factor_type), str(min(args.reloc_queries, 20000))]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        subprocess.run(cmd, check=True, timeout=600, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env)
+        rows = [l for l in open(log) if not l.startswith("==")]
+        agg = {}
+        for r in csv.DictReader(rows):
+            name = r["Kernel Name"].split("(")[0].replace("void ", "").replace("ptz::", "").strip()
+            k = agg.setdefault(name, dict(ids=set(), dram=0.0, dfma=0.0, dadd=0.0, dmul=0.0))
+            k["ids"].add(r["ID"])
+            v = float(r["Metric Value"].replace(",", ""))
+            m = r["Metric Name"]
+            if m.startswith("dram__bytes"):
+                unit = r.get("Metric Unit", "byte").lower()
+                v *= {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+                k["dram"] += v
+            elif "dfma" in m:
+                k["dfma"] += v
+            elif "dadd" in m:
+                k["dadd"] += v
+            elif "dmul" in m:
+                k["dmul"] += v
+        out = {}
+        for name, k in agg.items():
+            n = max(len(k["ids"]), 1)
+            out[name] = dict(launches=n, dram_bytes=int(k["dram"] / n), fp64_flops=int((2 * k["dfma"] + k["dadd"] + k["dmul"]) / n))
+        return out
+    except Exception as e:  # noqa: BLE001
+        return dict(error=str(e)[:200])
+
+
+def counters_for(counters, prefix):
+    """the entry of the first kernel whose name starts with `prefix` (template arguments vary with the factor type)"""
+    if not counters or "error" in counters:
+        return None
+    for name, v in counters.items():
+        if name.startswith(prefix):
+            return v
+    return None
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def make_scene(args, rank, world):
     from ptz_calib_b200 import synth
 
+    if args.config == "cfg5":
+        # BASELINE cfg 5 at its named size: V = 10,000 views, 1e7 tracks / 5e7 observations IN TOTAL, every rank generates its own
+        # 1/world of the tracks over the same views
+        V, P = max(8, int(10000 * args.scale)), int(10000000 * args.scale / world)
+        return synth.make_ba_scene(V, P, "band", factor_type=args.factor_type, seed=synth.SEEDS[5], track_seed=950001 + rank)
     scale = args.scale
     V = max(8, int(1000 * scale)) * world
     P = int(400000 * scale)  # tracks generated per rank; >= 4 visible views survive
@@ -186,32 +255,76 @@ def run_ours(args):
     ms_per_step = dev_ms / max(done, 1)
     value = M_total * done / (dev_ms * 1e-3) / 1e6
     kernels = st["kernels"]
-    # roofline of the dominant kernel (largest share of the step) and of the streaming residual+Jacobian kernel
+    # ---- roofline: algorithmic bytes per launch / mean event-timed duration, against the measured HBM peak
     peak, peak_src = load_peaks()
-    alg_bytes = {
-        "resjac": RJ_BYTES_PER_OBS[args.factor_type] * prob.M,
-        "cost": 16 * prob.M,
-        "track_accum": 64 * prob.M,
-        "track_solve": (8 * (8 + 2 * (4 + (args.factor_type > 0) + (args.factor_type == 2))) + 8 * 3 * 4 + 8 * 4) * prob.M,
+    ncl = 4 + (args.factor_type > 0) + (args.factor_type == 2)
+    RS, WS = 8 + 2 * ncl, (3 * ncl + 1) & ~1
+    nnzb, npairs = st_b["nnz_blocks"], st_b["num_pairs"]
+    cg_its_per_launch = st["pcg_iterations"] / max(kernels.get("pcg", dict(launches=1))["launches"], 1)
+    alg = {
+        # stage 1: 16 B read + r 16 B + J
+        "resjac": ("hbm", RJ_BYTES_PER_OBS[args.factor_type] * prob.M, "k_resjac: 16 B in + 16 B r + %d B J per observation" % (RJ_BYTES_PER_OBS[args.factor_type] - 32)),
+        "track_accum": ("hbm", 64 * prob.M + 80 * prob.P, "k_track_accum: r + E (64 B) per observation gathered by track, 80 B per track out"),
+        # stage 2: record in, What out; Cholesky factor per track
+        "track_solve": ("hbm", 8 * (RS + WS) * prob.M + 160 * prob.P, "k_track_factor + k_obs_what: record %d B in + What %d B out per observation, 160 B per track" % (8 * RS, 8 * WS)),
+        "schur_offdiag": ("l2", 2 * 8 * WS * npairs, "k_schur_offdiag: two What records (%d B) per observation pair, L2-resident gathers" % (8 * WS)),
+        # stage 3: per CG iteration every block of S~ (NCL^2 doubles) and the (r, w, s) state of its column (3 NCL doubles)
+        "pcg": ("l2-latency + grid barrier", nnzb * (ncl * ncl + 3 * ncl) * 8 * cg_its_per_launch,
+                "k_cg: (NCL^2 + 3 NCL) x 8 B per block of S~ per CG iteration x %.1f iterations per launch; S~ lives in shared memory, the state in L2: "
+                "latency-bound, not bandwidth-bound" % cg_its_per_launch),
+        # stage 4
+        "track_backsub": ("hbm", 8 * WS * prob.M + 240 * prob.P, "k_track_backsub: What %d B per observation gathered by track, 240 B per track" % (8 * WS)),
+        "cost": ("hbm", 16 * prob.M, "k_cost: 16 B per observation (+ the L2-resident track gather)"),
     }
+    prefix = {"resjac": "k_resjac", "track_accum": "k_track_accum", "track_solve": "k_obs_what", "schur_offdiag": "k_schur_offdiag", "pcg": "k_cg",
+              "track_backsub": "k_track_backsub", "cost": "k_cost"}
     table = {}
     for name, k in kernels.items():
         avg_us = 1e3 * k["ms"] / k["launches"]
         row = dict(stage=k["stage"], launches=k["launches"], avg_us=round(avg_us, 2), share=round(k["ms"] / max(st["ms_kernels_total"], 1e-9), 4))
-        if name in alg_bytes:
-            row["alg_gbs"] = round(alg_bytes[name] / (avg_us * 1e-6) / 1e9, 1)
+        if name in alg:
+            row["alg_gbs"] = round(alg[name][1] / (avg_us * 1e-6) / 1e9, 1)
         table[name] = row
     dom = max(table, key=lambda n: table[n]["share"]) if table else None
     rj = table.get("resjac")
-    roof_kernel = "resjac"
-    roofline = None
-    if rj:
-        roofline = dict(kernel="k_resjac (stage 1: residual + analytic Jacobian)", bound="hbm", achieved=rj["alg_gbs"], peak=peak, unit="GB/s",
-                        frac=round(rj["alg_gbs"] / peak, 4), traffic=ncu_traffic(args.factor_type, prob.M), peak_source=peak_src,
-                        algorithmic_bytes_per_obs=RJ_BYTES_PER_OBS[args.factor_type], dominant_kernel_by_time=dom,
-                        dominant_kernel_share=table[dom]["share"] if dom else None)
     launches = st["launches_total"]
     h.close()
+    h = None
+
+    counters = None
+    if rank == 0 and world == 1 and not args.no_ncu:
+        counters = hardware_counters(args)
+
+    def roof_entry(name):
+        row = table[name]
+        bound, nbytes, what = alg[name]
+        c = counters_for(counters, prefix[name])
+        traffic = None
+        if c is not None:
+            traffic = c["dram_bytes"]
+            if name == "track_solve":  # two kernels share the id: add the small one
+                c2 = counters_for(counters, "k_track_factor")
+                traffic += c2["dram_bytes"] if c2 else 0
+        return dict(kernel=name, what=what, bound=bound if bound != "l2" else "l2", achieved=row["alg_gbs"], peak=peak, unit="GB/s",
+                    frac=round(row["alg_gbs"] / peak, 4), traffic=traffic, share_of_step=row["share"], avg_us=row["avg_us"],
+                    algorithmic_bytes_per_launch=int(nbytes))
+
+    roofs = [roof_entry(n) for n in sorted((n for n in table if n in alg), key=lambda n: -table[n]["share"])]
+    roofline = None
+    if dom in alg:
+        roofline = dict(roof_entry(dom))
+        # the contract's enumeration is hbm | tensor: the fraction is taken against the HBM peak; `limiter` says what really bounds it
+        roofline["limiter"] = roofline["bound"]
+        roofline["bound"] = "hbm"
+        roofline["peak_source"] = peak_src
+        roofline["traffic_source"] = ("ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, side run of this bench (first 3 LM iterations of the same scene)"
+                                      if roofline["traffic"] is not None else None)
+        if dom == "pcg":
+            roofline["us_per_cg_iteration"] = round(1e3 * kernels["pcg"]["ms"] / max(st["pcg_iterations"], 1), 3)
+            roofline["cg_iterations_per_lm_step"] = round(st["pcg_iterations"] / st["lm_iterations"], 1)
+            roofline["deflated_solves"] = st_b["deflated_solves"] - st_a["deflated_solves"]
+            roofline["deflation_vectors"] = st_b["deflation_vectors"]
+
 
     # ---------------- end to end through the C ABI with host buffers: complete ptzba_solve calls ----------------
     e2e = None
@@ -251,11 +364,15 @@ def run_ours(args):
     # ---------------- batched relocalisation (cfg 3), kernel-only with device-resident inputs and end to end ----------------
     reloc = None
     if not args.no_reloc:
-        reloc = bench_reloc(args, rank, world, barrier, allmax, allsum)
+        reloc = bench_reloc(args, rank, world, barrier, allmax, allsum, counters)
 
     tracks = None
     if rank == 0 and world == 1 and not args.no_tracks:
         tracks = bench_tracks(args, prob)
+
+    small = None
+    if rank == 0 and world == 1 and not args.no_small:
+        small = bench_small(args)
 
     clocks = sampler.stop() if rank == 0 else None
 
@@ -267,8 +384,8 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": "ptzba_lm_mobs_per_sec", "value": round(value, 3), "unit": "Mobs/s", "n_gpus": world, "steps": done, "warmup": W,
-            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"cfg4_scaled_ba per GPU (V={prob.V}, P={prob.P} local tracks, M={prob.M} local obs, M_total={int(M_total)}); "
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong" if args.config == "cfg5" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{'cfg5_sharded_ba' if args.config == 'cfg5' else 'cfg4_scaled_ba'} per GPU (V={prob.V}, P={prob.P} local tracks, M={prob.M} local obs, M_total={int(M_total)}); "
                                    f"factor {['PTZRay', 'PTZRayDist', 'PTZRayFxfyDist'][args.factor_type]}; LM iterations from complete solves at Ceres-default "
                                    f"tolerances, PCG tol {args.pcg_tol:g}; inputs larger than L2 (records {prob.M * 128 / 1e6:.0f} MB)",
                        "views": prob.V, "obs_per_gpu": prob.M, "parallelism": (f"tracks/observations sharded x{world} (NCCL all-reduce of camera blocks), rows of the reduced system sharded x{world} "
@@ -277,7 +394,8 @@ def run_ours(args):
             "pcg_iterations_per_step": round(st["pcg_iterations"] / st["lm_iterations"], 1),
             "us_per_pcg_iteration": round(1e3 * kernels["pcg"]["ms"] / max(st["pcg_iterations"], 1), 3) if "pcg" in kernels else None,
             "rj_mobs_per_sec": round(prob.M / (rj["avg_us"]) , 1) if rj else None,
-            "gpu_launches": launches, "kernels": table, "roofline": roofline, "e2e": e2e, "reloc": reloc, "tracks": tracks, "cpu_baseline": cpu, "clocks": clocks,
+            "gpu_launches": launches, "kernels": table, "roofline": roofline, "roofline_kernels": roofs, "e2e": e2e, "small_configs": small, "reloc": reloc,
+            "tracks": tracks, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -285,7 +403,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def bench_reloc(args, rank, world, barrier, allmax, allsum):
+def bench_reloc(args, rank, world, barrier, allmax, allsum, counters=None):
     import ctypes as C
 
     import torch
@@ -340,9 +458,64 @@ def bench_reloc(args, rank, world, barrier, allmax, allsum):
     r = ptz.reloc_solve_batch(b, opt)
     barrier()
     dt = allmax(time.perf_counter() - t0)
-    return dict(workload=f"cfg3: {B} queries, {int(allsum(float(b.N)))} matches, factor F, 5% displaced outliers", solves_per_sec=round(B / (ms * 1e-3), 1),
-                ms_per_batch=round(ms, 3), mean_lm_iterations=round(iters, 2), success_rate=round(succ, 4), e2e_solves_per_sec=round(B / dt, 1),
-                e2e_seconds=round(dt, 4), h2d_bytes=int(b.N * 16 + b.B * (42 * 8 + 8)), d2h_bytes=int(b.B * (21 + 15 + 3) * 8 + b.B * 16))
+    out = dict(workload=f"cfg3: {B} queries, {int(allsum(float(b.N)))} matches, factor F, 5% displaced outliers", solves_per_sec=round(B / (ms * 1e-3), 1),
+               ms_per_batch=round(ms, 3), mean_lm_iterations=round(iters, 2), success_rate=round(succ, 4), e2e_solves_per_sec=round(B / dt, 1),
+               e2e_seconds=round(dt, 4), h2d_bytes=int(b.N * 16 + b.B * (42 * 8 + 8)), d2h_bytes=int(b.B * (21 + 15 + 3) * 8 + b.B * 16))
+    # roofline of k_reloc: bound by the fp64 pipe, not by HBM (16 B per match read once).  fp64 operations per query come
+    # from the instruction counters of this run's side capture (2 x DFMA + DADD + DMUL), the peak from a DFMA micro-kernel on this device.
+    if rank == 0:
+        gf = C.c_double(0)
+        if L.ptz_measure_fp64_gflops(C.byref(gf)) == 0 and gf.value > 0:
+            out["fp64_peak_gflops_measured"] = round(gf.value, 1)
+        c = counters_for(counters, "k_reloc")
+        if c and c.get("fp64_flops"):
+            nq = min(args.reloc_queries, 20000)  # queries of the side run (same generator, a prefix-sized batch)
+            fl_q = c["fp64_flops"] / nq
+            out["fp64_flops_per_query"] = round(fl_q, 1)
+            out["fp64_flops_per_match_per_lm_iteration"] = round(fl_q / (b.N / max(b.B, 1)) / max(iters, 1e-9), 1)
+            ach = fl_q * b.B / (ms * 1e-3) / 1e9
+            out["roofline"] = dict(kernel="k_reloc<F>", bound="fp64 pipe", achieved=round(ach, 1), peak=out.get("fp64_peak_gflops_measured"), unit="GFLOP/s",
+                                   frac=round(ach / gf.value, 4) if gf.value > 0 else None,
+                                   hbm_gbs=round((b.N * 16 + b.B * (42 + 39) * 8) / (ms * 1e-3) / 1e9, 1),
+                                   traffic=c["dram_bytes"] * b.B // max(nq, 1))
+    return out
+
+
+def bench_small(args):
+    """BASELINE cfg 1 (Synthetic-shaped, V=36, PTZRay; with its georeferencing stage) and cfg 2 (WorldCup14-shaped, V=60, PTZRayDist) at full
+    size: latency-bound problems, reported as LM iterations per second -- device-resident (CUDA events over ptzba_run)
+    and end to end (ptzba_solve with host buffers)."""
+    import ptz_calib_b200 as ptz
+    from ptz_calib_b200 import synth
+
+    out = {}
+    for name, p in (("cfg1", synth.make_config(1)), ("cfg1_georef", synth.make_config(1, num_pts3d=10)), ("cfg2", synth.make_config(2))):
+        # these scenes converge in 2-3 iterations from the standard initial guess; a harder start (2 deg, 8 % focal error) gives the
+        # loop something to do, so both are reported
+        rows = {}
+        for tag, q in (("standard_init", p), ("hard_init", synth.make_config(int(name[3]), rot_noise_deg=2.0, focal_noise=0.08, **({"num_pts3d": 10} if "georef" in name else {})))):
+            h = ptz.BAHandle(q, max_num_iterations=200)
+            h.run(200); h.reset()
+            a = h.stage_times()
+            reps, its, conv = 20, 0, True
+            for _ in range(reps):
+                r = h.run(200)
+                its += r.num_iterations
+                conv = conv and r.converged
+                h.reset()
+            b = h.stage_times()
+            h.close()
+            ms = b["ms_run"] - a["ms_run"]
+            ptz.ba_solve(q, max_num_iterations=200)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                r = ptz.ba_solve(q, max_num_iterations=200)
+            dt = (time.perf_counter() - t0) / 5
+            rows[tag] = dict(lm_iterations_per_solve=round(its / reps, 1), lm_iters_per_sec=round(its / (ms * 1e-3), 1), us_per_lm_iteration=round(1e3 * ms / max(its, 1), 1),
+                             ms_per_solve_device=round(ms / reps, 3), ms_per_solve_e2e=round(1e3 * dt, 3), converged=bool(conv),
+                             kernel_launches_per_iteration=round((b["launches_total"] - a["launches_total"]) / max(its, 1), 1))
+        out[name] = dict(views=p.V, tracks=p.P, observations=p.M, annotated_points=p.A, **rows)
+    return out
 
 
 def bench_tracks(args, prob):
@@ -413,24 +586,41 @@ def bench_tracks(args, prob):
 
 
 def cpu_baseline(args, prob):
-    """The oracle port timed on the box's host cores: a bounded sample of the same workload (first tracks of the scene)."""
+    """The oracle port timed on the box's host cores: a bounded sample of the same workload (first tracks of the scene), all host threads
+    (passed explicitly: torchrun exports OMP_NUM_THREADS=1), plus its thread scaling and the Jacobian-only rate on a smaller sample."""
     from oracle import oracle as orc
 
-    threads = orc.num_threads()
-    T = min(prob.P, 5 * args.cpu_tracks)  # ~10-20 s of CPU work
-    sel = prob.obs_track < T
     import ptz_calib_b200 as ptz
 
-    sample = ptz.BAProblem(prob.factor_type, prob.intr, prob.ext, prob.obs_uv[sel], prob.obs_view[sel], prob.obs_track[sel], prob.track_weight[:T])
+    threads = host_threads()
+
+    def sample_of(T):
+        sel = prob.obs_track < T
+        return ptz.BAProblem(prob.factor_type, prob.intr, prob.ext, prob.obs_uv[sel], prob.obs_view[sel], prob.obs_track[sel], prob.track_weight[:T])
+
+    kw = dict(function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0, jacobian_mode=1, linear_solver=1, pcg_rel_tolerance=args.pcg_tol)
+    T = min(prob.P, 5 * args.cpu_tracks)  # ~10-20 s of CPU work
+    sample = sample_of(T)
     iters = args.cpu_iters
     t0 = time.perf_counter()
-    rc, r = orc.ba_solve(sample, max_num_iterations=iters, function_tolerance=0.0, parameter_tolerance=0.0, gradient_tolerance=0.0, jacobian_mode=1,
-                         linear_solver=1, num_threads=threads, pcg_rel_tolerance=args.pcg_tol)
+    rc, r = orc.ba_solve(sample, max_num_iterations=iters, num_threads=threads, **kw)
     dt = time.perf_counter() - t0
     its = max(r.num_iterations, 1)
+    # thread scaling on a fifth of that sample: 1 thread vs all
+    small = sample_of(max(1000, T // 5))
+    t0 = time.perf_counter()
+    orc.ba_solve(small, max_num_iterations=2, num_threads=1, **kw)
+    d1 = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    orc.ba_solve(small, max_num_iterations=2, num_threads=threads, **kw)
+    dn = time.perf_counter() - t0
+    tj = orc.ba_time_jacobian(small, 1, threads, 2)  # seconds per numeric-diff (Ceres CENTRAL) Jacobian evaluation
+    ta = orc.ba_time_jacobian(small, 0, threads, 2)  # ... and per exact (analytic-equivalent) one
     return dict(value=round(sample.M * its / dt / 1e6, 4), unit="Mobs/s", cores=threads, kind="port",
                 sample=f"first {T} tracks ({sample.M} obs) of the cfg-4 scene, all {prob.V} views, {its} LM iterations with Ceres-CENTRAL numeric "
-                       f"Jacobians (as the reference), block-sparse Schur + block-Jacobi PCG; {dt:.1f} s", lm_iters_per_sec=round(its / dt, 4))
+                       f"Jacobians (as the reference), block-sparse Schur + block-Jacobi PCG; {dt:.1f} s", lm_iters_per_sec=round(its / dt, 4),
+                thread_scaling=dict(threads=threads, speedup=round(d1 / dn, 2), sample_obs=small.M, seconds_1_thread=round(d1, 2), seconds_all_threads=round(dn, 2)),
+                jacobian_only_mobs_per_sec=dict(ceres_central_numeric=round(small.M / tj / 1e6, 3), exact=round(small.M / ta / 1e6, 3), threads=threads))
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -446,7 +636,7 @@ def run_reference(args):
 
     import ptz_calib_b200 as ptz
 
-    threads = orc.num_threads()
+    threads = host_threads()  # explicit: torchrun exports OMP_NUM_THREADS=1, which must not turn the arm into a 1-thread run
     prob = make_scene(args, 0, 1)
     T = min(prob.P, args.cpu_tracks)
     sel = prob.obs_track < T
@@ -476,7 +666,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink cfg 4 (tests / smoke only; the default is the named config)")
@@ -490,6 +680,9 @@ def main():
     ap.add_argument("--no-tracks", action="store_true")
     ap.add_argument("--no-reloc", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-small", action="store_true")
+    ap.add_argument("--no-ncu", action="store_true", help="skip the hardware-counter side run (roofline.traffic becomes null)")
+    ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg5"], help="cfg4: 2M observations per GPU (weak scaling); cfg5: 5e7 observations in total")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -149,6 +149,8 @@ typedef struct ptzba_eval_out {
 } ptzba_eval_out;
 
 void ptz_solver_options_default(ptz_solver_options* opt);
+/* measured fp64 FMA throughput of the current device in GFLOP/s (bench.py: denominator of the fp64-bound reloc kernel's roofline) */
+int ptz_measure_fp64_gflops(double* gflops);
 const char* ptz_last_error(void);
 int ptz_device_count(void);
 
@@ -179,6 +181,12 @@ typedef struct ptzba_stage_times {
   int launches[16];      /* launches per kernel id */
   float ms_run;          /* device span of the ptzba_run calls (first launch to last completion, host gaps included) */
   int lm_iterations, pcg_iterations, jacobian_evals, cost_evals;
+  /* structure of the reduced camera system (bench.py: algorithmic bytes of stage 3 and of the off-diagonal Schur kernel) */
+  int nnz_blocks;          /* blocks of S, both triangles + diagonal */
+  int deflated_solves;     /* linear solves that ran the deflated kernel */
+  int deflation_vectors;   /* size of the Ritz basis in use (0: none) */
+  int reserved_;
+  int64_t num_pairs;       /* observation pairs summed into the off-diagonal blocks */
 } ptzba_stage_times;
 int ptzba_get_stage_times(ptzba_handle* h, ptzba_stage_times* t);
 int ptzba_destroy(ptzba_handle* h);

@@ -6,13 +6,15 @@
 //   SaveToJson           data_io.cc:110-164  {"cameras": {<rootname>: {name,pos,res,K,R,t,dist,distType,marker{pix,pos},version}}}
 //   ReadFromJson         data_io.cc:180-247  (marker pixels are stored divided by the resolution)
 //   ReadCamFromJson      data_io.cc:249-292
-//   FindImgIndex         data_io.cc (by file name)
+//   FindImgIndex         data_io.cc:460-474 (by root name, extension ignored)
+//   FindBestMatch        run_ptz_reloc.cc:147-166 (reference image with the most matches for a query image)
 // JSON is read and written by a small parser here (the reference uses nlohmann::ordered_json, an un-vendored dependency).
 // Not built: LoadImgsAndFeatures (cv::imread on every image) and LoadMatchesInfo's cv::findHomography(RANSAC); callers that
 // already hold homographies fill MatchesInfo::H / has_H themselves (tests/cpp/iba_check.cpp does).
 #ifndef PTZCALIB_IO_HPP
 #define PTZCALIB_IO_HPP
 
+#include <algorithm>
 #include <cctype>
 #include <cstdio>
 #include <cstdlib>
@@ -76,9 +78,34 @@ inline void ReadColmapMatches(const std::string& filepath, std::vector<std::vect
   }
 }
 
+// root name: the file name without its extension (utils/os_path splitext: the last '.' of the last path component, not a leading one)
+inline std::string NameWithoutExt(const std::string& fname) {
+  const size_t slash = fname.find_last_of('/');
+  const size_t base = slash == std::string::npos ? 0 : slash + 1;
+  const size_t dot = fname.find_last_of('.');
+  if (dot == std::string::npos || dot <= base) return fname;
+  return fname.substr(0, dot);
+}
+// data_io.cc:460-474: images are matched by ROOT name -- JSON camera keys carry no extension, match files may name "a.png"
+// where the feature file was "a.jpg"
 inline long FindImgIndex(const std::vector<std::string>& fnames, const std::string& fname) {
-  for (size_t i = 0; i < fnames.size(); ++i) if (fnames[i] == fname) return (long)i;
+  const std::string want = NameWithoutExt(fname);
+  for (size_t i = 0; i < fnames.size(); ++i) if (NameWithoutExt(fnames[i]) == want) return (long)i;
   return -1;
+}
+
+// run_ptz_reloc.cc:147-166: among the pairs whose SECOND image is `fname`, the one with the most matches (first wins ties);
+// an empty name / list when there is none
+typedef std::pair<std::string, std::vector<DMatch>> BestMatchT;
+inline BestMatchT FindBestMatch(const std::string& fname, const std::vector<std::pair<std::string, std::string>>& img_pairs_name,
+                                const std::vector<std::vector<DMatch>>& pairs_matches) {
+  BestMatchT best;
+  if (img_pairs_name.size() != pairs_matches.size()) return best;
+  for (size_t i = 0; i < img_pairs_name.size(); ++i) {
+    if (img_pairs_name[i].second != fname) continue;
+    if (pairs_matches[i].size() > best.second.size()) best = {img_pairs_name[i].first, pairs_matches[i]};
+  }
+  return best;
 }
 
 // ---------------------------------------------------------------------------------------------------------- a small JSON value
@@ -223,7 +250,10 @@ inline bool ReadFromJson(const std::string& filepath, std::vector<Camera>& camer
   json::Value root;
   if (!detail::load_json(filepath, root)) return false;
   try {
-    for (const auto& el : root.at("cameras").obj) {
+    // the reference parses with nlohmann::json (std::map): cameras come out sorted by key, whatever the order in the file
+    std::vector<std::pair<std::string, json::Value>> sorted_cams = root.at("cameras").obj;
+    std::stable_sort(sorted_cams.begin(), sorted_cams.end(), [](const std::pair<std::string, json::Value>& a, const std::pair<std::string, json::Value>& b) { return a.first < b.first; });
+    for (const auto& el : sorted_cams) {
       Camera cam;
       detail::camera_from(el.second, cam);
       Size size;

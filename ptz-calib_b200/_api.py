@@ -15,7 +15,7 @@ from .problem import BAProblem, BAResult, RelocBatch, RelocResult, default_optio
 from .tracks import Matches, Tracks, Views, Observations, build_tracks, flatten_tracks
 
 __all__ = ["abi", "problem", "BAProblem", "BAResult", "RelocBatch", "RelocResult", "default_options", "ba_solve", "ba_eval", "BAHandle",
-           "reloc_solve_batch", "reloc_eval", "tracks", "Matches", "Tracks", "Views", "Observations", "build_tracks", "flatten_tracks", "PTZRayOptimizer", "KRTOptimizer", "device_count", "nccl_init_from_torch", "nccl_finalize"]
+           "reloc_solve_batch", "reloc_eval", "tracks", "Matches", "Tracks", "Views", "Observations", "build_tracks", "flatten_tracks", "PTZRayOptimizer", "KRTOptimizer", "find_best_match", "device_count", "nccl_init_from_torch", "nccl_finalize"]
 
 
 def device_count() -> int:
@@ -71,7 +71,8 @@ class BAHandle:
         t = abi.StageTimesC()
         lib.check(lib.load().ptzba_get_stage_times(self._h, C.byref(t)), "ptzba_get_stage_times")
         out = dict(ms_run=t.ms_run, lm_iterations=t.lm_iterations, pcg_iterations=t.pcg_iterations, jacobian_evals=t.jacobian_evals,
-                   cost_evals=t.cost_evals, kernels={})
+                   cost_evals=t.cost_evals, nnz_blocks=t.nnz_blocks, num_pairs=int(t.num_pairs), deflated_solves=t.deflated_solves,
+                   deflation_vectors=t.deflation_vectors, kernels={})
         for i, name in enumerate(abi.KERNEL_NAMES[:16]):
             if t.launches[i]:
                 out["kernels"][name] = dict(ms=float(t.ms_kernel[i]), launches=int(t.launches[i]), stage=abi.KERNEL_STAGE[name])
@@ -172,6 +173,13 @@ class PTZRayOptimizer:
         ext[:, 3:] = cams21[cand, 13:16]
         kw = {}
         if pt_uv is not None and len(pt_uv):
+            if len(pt_uv) != len(pt_xyz) or len(pt_uv) != len(pt_view):  # CheckValid, ptzray_optimizer.cc:524-532
+                raise ValueError("pt_uv, pt_xyz and pt_view must have one row per annotated point")
+            if tlw0 is None:
+                # The reference starts T_l_w from EPnP on the annotated view with the most points (SetInitTransLocalToWorld, :562-633);
+                # that initialisation lives in the C++ adaptor (include/ptzcalib_epnp.hpp).  Starting from T_l_w = 0 here would solve a
+                # different (possibly non-convergent) problem, so the Python mirror asks for the estimate instead of guessing.
+                raise ValueError("from_matches: annotated points need tlw0 (the EPnP initialisation of T_l_w lives in the C++ adaptor)")
             keep = dense[np.asarray(pt_view)] >= 0
             kw = dict(pt_uv=f32(pt_uv)[keep], pt_xyz=f64(pt_xyz)[keep], pt_view=dense[np.asarray(pt_view)][keep].astype(np.int32), tlw0=tlw0)
         prob = BAProblem(factor_type=factor_type, intr=intr, ext=ext, obs_uv=obs.obs_uv, obs_view=obs.obs_view, obs_track=obs.obs_track,
@@ -203,6 +211,18 @@ class PTZRayOptimizer:
 
     def final_reproj_error_2d3d(self):
         return self._err[2]
+
+
+def find_best_match(fname, img_pairs_name, pairs_matches):
+    """FindBestMatch (run_ptz_reloc.cc:147-166): among the pairs whose SECOND image is `fname`, the one with the most matches (the
+    first wins ties).  Returns (reference image name, matches) or ("", []) when there is none."""
+    best = ("", [])
+    if len(img_pairs_name) != len(pairs_matches):
+        return best
+    for (first, second), m in zip(img_pairs_name, pairs_matches):
+        if second == fname and len(m) > len(best[1]):
+            best = (first, m)
+    return best
 
 
 class KRTOptimizer:

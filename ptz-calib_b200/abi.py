@@ -132,6 +132,11 @@ class StageTimesC(C.Structure):
         ("pcg_iterations", C.c_int),
         ("jacobian_evals", C.c_int),
         ("cost_evals", C.c_int),
+        ("nnz_blocks", C.c_int),
+        ("deflated_solves", C.c_int),
+        ("deflation_vectors", C.c_int),
+        ("reserved_", C.c_int),
+        ("num_pairs", C.c_int64),
     ]
 
 

@@ -1272,6 +1272,7 @@ struct BaSolver : BaSolverBase {
     for (int i = 0; i < PTZ_K_COUNT; ++i) { t->ms_kernel[i] = clk.ms[i]; t->launches[i] = clk.launches[i]; }
     t->ms_run = clk.ms_run;
     t->lm_iterations = (int)life_lm; t->pcg_iterations = (int)life_pcg; t->jacobian_evals = jac_evals; t->cost_evals = cost_evals;
+    t->nnz_blocks = ds.nnzb; t->deflated_solves = defl_solves; t->deflation_vectors = have_W ? defl_kd : 0; t->reserved_ = 0; t->num_pairs = ds.npairs;
   }
 };
 

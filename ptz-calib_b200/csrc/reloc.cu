@@ -396,6 +396,23 @@ static void launch_reloc(int type, const RelocArgs& a, int max_matches, cudaStre
   }
 }
 
+// fp64 FMA throughput of the device, measured: the denominator of the reloc kernel's roofline (it is bound by the fp64 pipe,
+// not by HBM).  8 independent chains per thread, every SM full.
+__global__ void __launch_bounds__(256) k_fp64_peak(int iters, double seed, double* __restrict__ out) {
+  double a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = seed + i + threadIdx.x;
+  const double m = 1.0000001, c = 1e-9;
+  for (int k = 0; k < iters; ++k) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = fma(a[i], m, c);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 12345.678) out[0] = s;  // never true: keeps the chains alive
+}
+
 template <class F>
 static int guarded_r(F&& f) {
   try {
@@ -534,6 +551,38 @@ int ptzreloc_eval(int type, int N, const float* uv_ref, const float* uv_cur, con
     if (jac) memcpy(jac, J.data(), J.size() * 8);
     if (cost) *cost = c;
     if (gradient) memcpy(gradient, g.data(), nf * 8);
+    return (int)PTZ_OK;
+  });
+}
+
+int ptz_measure_fp64_gflops(double* gflops) {
+  if (!gflops) return PTZ_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { set_last_error("no CUDA device"); return PTZ_ERR_NO_DEVICE; }
+  return guarded_r([&]() {
+    int dev = 0, sms = 0;
+    PTZ_CUDA(cudaGetDevice(&dev));
+    PTZ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DevBuf<double> d;
+    d.alloc(1);
+    cudaEvent_t e0, e1;
+    PTZ_CUDA(cudaEventCreate(&e0));
+    PTZ_CUDA(cudaEventCreate(&e1));
+    const int iters = 1 << 14, grid = sms * 8;
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+      PTZ_CUDA(cudaEventRecord(e0, 0));
+      k_fp64_peak<<<grid, 256>>>(iters, 1.0, d.p);
+      PTZ_CUDA(cudaEventRecord(e1, 0));
+      PTZ_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      PTZ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      const double gf = 2.0 * 8.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e9;
+      if (rep > 0 && gf > best) best = gf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *gflops = best;
     return (int)PTZ_OK;
   });
 }

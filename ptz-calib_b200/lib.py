@@ -8,7 +8,7 @@ SO_PATH = os.path.join(_HERE, "csrc", "libptzcalib_b200.so")
 _LIB = None
 
 EXPORTS = [
-    "ptz_solver_options_default", "ptz_last_error", "ptz_device_count",
+    "ptz_solver_options_default", "ptz_last_error", "ptz_device_count", "ptz_measure_fp64_gflops",
     "ptzba_solve", "ptzba_eval", "ptzba_create", "ptzba_reset", "ptzba_run", "ptzba_get_stage_times", "ptzba_destroy",
     "ptz_nccl_unique_id", "ptz_nccl_init", "ptz_nccl_finalize",
     "ptzreloc_solve_batch", "ptzreloc_eval", "ptzreloc_solve_batch_dev", "ptzreloc_reproj_error", "ptzreloc_local_params",

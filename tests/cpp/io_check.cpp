@@ -37,6 +37,14 @@ int main(int argc, char** argv) {
   printf("tracks %d %d %d covis", tot, mx, mn);
   for (int i : co) printf(" %d", i);
   printf("\n");
+  // FindImgIndex compares root names (data_io.cc:460-474); FindBestMatch takes the pair with the most matches whose second image is the query
+  std::vector<std::string> fn{"img001.jpg", "dir.v2/img002.png", "img003"};
+  printf("find %ld %ld %ld %ld %ld\n", FindImgIndex(fn, "img001"), FindImgIndex(fn, "img001.png"), FindImgIndex(fn, "dir.v2/img002"), FindImgIndex(fn, "img003.jpg"),
+         FindImgIndex(fn, "img004.jpg"));
+  BestMatchT bm = FindBestMatch("a.jpg", names, pm), none_bm = FindBestMatch("zzz.jpg", names, pm);
+  printf("best %s %zu | %s %zu | order", bm.first.c_str(), bm.second.size(), none_bm.first.c_str(), none_bm.second.size());
+  for (auto& n : cn) printf(" %s", n.c_str());
+  printf("\n");
   std::vector<std::string> missing{"nope.jpg"};
   std::vector<Camera> none;
   printf("roundtrip %d %.3g missing %d pix0 %.9g %.9g size %d %d\n", (int)ok2, worst, (int)ReadCamFromJson(argv[4], missing, none), pix[0].empty() ? -1.0 : pix[0][0].x,

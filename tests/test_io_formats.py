@@ -24,7 +24,7 @@ def test_text_formats_and_camera_json(tmp_path):
     with open(matches, "w") as f:
         f.write("a.jpg b.jpg\n0 3\n1 2\n4 4\n\nb.jpg c.png\n\nc.png a.jpg\n7 9\n\n")  # the middle block has no matches: dropped
     cams = {}
-    for name in ("a", "b"):
+    for name in ("b", "a"):  # written out of order: the reference reads through std::map, i.e. sorted by key
         R = np.linalg.qr(rng.normal(size=(3, 3)))[0]
         R *= np.sign(np.linalg.det(R))
         cams[name] = dict(name=name, pos=[0, 0, 0], res=[1920, 1080], K=[1500.0, 0, 960, 0, 1510.0, 540, 0, 0, 1], R=R.ravel().tolist(),
@@ -42,7 +42,9 @@ def test_text_formats_and_camera_json(tmp_path):
     assert lines[1].startswith("pairs 2 | a.jpg b.jpg 3 0:3 1:2 4:4 | c.png a.jpg 1 7:9")
     assert lines[2] == "json 1 2"
     assert lines[3] == "tracks 7 3 2 covis 0 1 2"
-    rt = lines[4].split()
+    assert lines[4] == "find 0 0 1 2 -1"
+    assert lines[5] == "best c.png 1 |  0 | order a b"
+    rt = lines[6].split()
     assert rt[1] == "1" and float(rt[2]) == 0.0 and rt[4] == "0"  # round trip exact; a missing camera makes ReadCamFromJson fail
     assert abs(float(rt[6]) - 480.0) < 1e-4 and abs(float(rt[7]) - 540.0) < 1e-4 and rt[9:] == ["1920", "1080"]  # marker pixels scaled by the resolution
     out = json.load(open(jout))  # what SaveToJson wrote is valid JSON with the reference's fields

@@ -548,13 +548,17 @@ class PtzIncrementalOptimizer {
     for (int trial = 0; trial < kInitNumTrials; ++trial) {
       long id1, id2;
       if (!FindInitialImagePair(id1, id2)) return false;
-      if (!RegisterInitialImagePair(id1, id2)) continue;
+      Trace(kTraceSeedPair, id1, id2);
+      const bool init_ok = RegisterInitialImagePair(id1, id2);
+      Trace(kTraceInitResult, init_ok ? 1 : 0, last_ba_iterations_);
+      if (!init_ok) continue;
       AdjustGlobalBundle();
       size_t ba_prev = reg_image_ids_.size();
       bool reg_next = true;
       while (reg_next) {
         reg_next = false;
         const std::vector<long> next = FindNextImages();
+        Trace(kTraceNextList, (long)next.size(), next.empty() ? -1 : next[0]);
         if (next.empty()) break;
         for (size_t reg_trial = 0; reg_trial < next.size(); ++reg_trial) {
           const long image_id = next[reg_trial];
@@ -562,6 +566,7 @@ class PtzIncrementalOptimizer {
           if (reg_next && reg_image_ids_.size() >= kBaGlobalImagesRatio() * ba_prev) {
             if (AdjustGlobalBundle()) { ba_prev = reg_image_ids_.size(); break; }
             reg_image_ids_.erase(image_id);
+            Trace(kTraceUnregister, image_id, 0);
             reg_next = false;
           }
           if (!reg_next) {
@@ -580,6 +585,12 @@ class PtzIncrementalOptimizer {
   }
 
   // bookkeeping a caller may want to look at (not in the reference's public interface)
+  // the decisions of Solve in the order they were taken, as (kind, a, b): seed pair (a, b); result of the two-view BA (ok, LM
+  // iterations); list FindNextImages returned (length, first id); RegisterNextImage (image, registered neighbour it succeeded
+  // from or -1); global BA (ok, registered images); image erased again after a failed global BA.  tests/ compare this log with
+  // the CPU restatement of the reference's driver (oracle/iba_oracle.cpp), which numbers the kinds the same way.
+  enum { kTraceSeedPair = 1, kTraceInitResult = 2, kTraceGlobalBa = 3, kTraceRegister = 4, kTraceUnregister = 5, kTraceNextList = 6 };
+  const std::vector<std::array<long, 3>>& trace() const { return trace_; }
   int num_global_bundles() const { return num_global_bundles_; }
   int num_reloc_batches() const { return num_reloc_batches_; }
   int num_reloc_queries() const { return num_reloc_queries_; }
@@ -587,6 +598,7 @@ class PtzIncrementalOptimizer {
 
  private:
   bool isReg(long id) const { return reg_image_ids_.find(id) != reg_image_ids_.end(); }
+  void Trace(long kind, long a, long b) { trace_.push_back(std::array<long, 3>{{kind, a, b}}); }
   static std::vector<long> RankedIds(const std::vector<float>& rank) {  // descending confidence, images without any dropped
     std::vector<long> idx(rank.size());
     std::iota(idx.begin(), idx.end(), 0);
@@ -615,7 +627,8 @@ class PtzIncrementalOptimizer {
   }
   std::vector<long> FindFirstInitialImage() const {  // .cc:179-206
     std::vector<float> rank(features_.size(), 0.0f);
-    for (const auto& mi : matches_info_) { rank[mi.src_img_idx] += (float)mi.confidence; rank[mi.dst_img_idx] += (float)mi.confidence; }
+    // (float += double, as the reference: the sum is formed in double and rounded back)
+    for (const auto& mi : matches_info_) { rank[mi.src_img_idx] += mi.confidence; rank[mi.dst_img_idx] += mi.confidence; }
     return RankedIds(rank);
   }
   std::vector<long> FindSecondInitialImage(long id1) const {  // .cc:208-247
@@ -625,7 +638,7 @@ class PtzIncrementalOptimizer {
       const long s = mi.src_img_idx, d = mi.dst_img_idx;
       if (mi.matches.empty() || (id1 != s && id1 != d) || (id1 == s && id1 == d)) continue;
       if (CalPixelDiff(s, d, mi.matches) < kMinPixelDiff) continue;
-      rank[id1 == s ? d : s] += (float)mi.confidence;
+      rank[id1 == s ? d : s] += mi.confidence;
     }
     return RankedIds(rank);
   }
@@ -638,7 +651,7 @@ class PtzIncrementalOptimizer {
       if (s == d || !mi.has_H || tired(s) || tired(d)) continue;
       const bool rs = isReg(s), rd = isReg(d);
       if (rs == rd) continue;  // both registered already, or neither a neighbour of the model
-      rank[rs ? d : s] += (float)mi.confidence;
+      rank[rs ? d : s] += mi.confidence;
     }
     return RankedIds(rank);
   }
@@ -646,7 +659,8 @@ class PtzIncrementalOptimizer {
     float total = 0.0f;
     for (const DMatch& m : matches) {
       const Point2f a = features_[id1].keypoints[m.queryIdx].pt, b = features_[id2].keypoints[m.trainIdx].pt;
-      total += (float)std::sqrt((double)(a.x - b.x) * (a.x - b.x) + (double)(a.y - b.y) * (a.y - b.y));
+      const float dx = a.x - b.x, dy = a.y - b.y;  // Point2f difference, then cv::norm in double, added into the float total
+      total += std::sqrt((double)dx * dx + (double)dy * dy);
     }
     return total * 1.0f / matches.size();
   }
@@ -679,6 +693,7 @@ class PtzIncrementalOptimizer {
     SetInitialImagePairParameters(id1, id2);
     PTZRayOptimizer optimizer(features_, matches_info_, cameras_, std::unordered_set<long>{id1, id2}, max_iter_, PTZRay);
     const bool ok = optimizer.Solve(cameras_);
+    last_ba_iterations_ = optimizer.num_iterations();
     if (ok) { reg_image_ids_.insert(id1); reg_image_ids_.insert(id2); }
     return ok;
   }
@@ -688,7 +703,7 @@ class PtzIncrementalOptimizer {
     std::vector<const MatchesInfo*> cand;
     for (const auto& mi : matches_info_)
       if (mi.has_H && isReg(mi.src_img_idx) && mi.dst_img_idx == j) cand.push_back(&mi);
-    if (cand.empty()) return false;
+    if (cand.empty()) { Trace(kTraceRegister, j, -1); return false; }
     const int B = (int)cand.size();
     std::vector<int64_t> off(1, 0);
     std::vector<float> uv1, uv2;
@@ -719,7 +734,7 @@ class PtzIncrementalOptimizer {
     ptz_solver_options o;
     ptz_solver_options_default(&o);
     ++num_reloc_batches_; num_reloc_queries_ += B;
-    if (ptzreloc_solve_batch(&b, &o, &r) != PTZ_OK) return false;
+    if (ptzreloc_solve_batch(&b, &o, &r) != PTZ_OK) { Trace(kTraceRegister, j, -1); return false; }
     for (int q = 0; q < B; ++q)
       if (ok[q]) {
         Camera c;
@@ -727,8 +742,10 @@ class PtzIncrementalOptimizer {
         cameras_[j].K() = c.K();
         cameras_[j].R() = c.R();
         reg_image_ids_.insert(j);
+        Trace(kTraceRegister, j, cand[q]->src_img_idx);
         return true;
       }
+    Trace(kTraceRegister, j, -1);
     // every trial failed: the reference leaves the last trial's initial K, R in cameras_[j]
     cameras_[j].K() = init_cam[B - 1].K();
     cameras_[j].R() = init_cam[B - 1].R();
@@ -739,6 +756,7 @@ class PtzIncrementalOptimizer {
     const bool ok = optimizer.Solve(cameras_);
     last_reproj_error_ = optimizer.final_reproj_error_all();
     ++num_global_bundles_;
+    Trace(kTraceGlobalBa, ok ? 1 : 0, (long)reg_image_ids_.size());
     return ok;
   }
 
@@ -751,8 +769,9 @@ class PtzIncrementalOptimizer {
   std::unordered_map<long, size_t> num_reg_trials_;      // registration attempts per image (bounded by kMaxRegTrials)
   std::unordered_set<long> reg_image_ids_;
   std::vector<long> seed_image_ids_;
-  int num_global_bundles_ = 0, num_reloc_batches_ = 0, num_reloc_queries_ = 0;
+  int num_global_bundles_ = 0, num_reloc_batches_ = 0, num_reloc_queries_ = 0, last_ba_iterations_ = 0;
   double last_reproj_error_ = 0;
+  std::vector<std::array<long, 3>> trace_;
 };
 
 }  // namespace ptzcalib

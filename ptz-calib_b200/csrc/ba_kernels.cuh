@@ -1624,6 +1624,29 @@ __global__ void __launch_bounds__(1024) k_scalars(ScalarJobs J, double* __restri
   }
 }
 
+// What the host reads once per step attempt, in ONE pinned, device-mapped block: the kernel writes it over PCIe and raises
+// `seq` behind a system-scope fence; the host spins on `seq` (no copy engine, no stream synchronise on the critical path).
+struct PublishBlock {
+  double sc[32];          // the scalar slots
+  double dscal[2];        // deflation: |b~|^2, basis usable
+  int info[4];            // pcg iterations, pcg status, factorisation failure flag
+  unsigned long long seq;
+};
+__global__ void __launch_bounds__(64) k_publish(const double* __restrict__ scalars, const int* __restrict__ pcg_info, const int* __restrict__ fail,
+                                               const double* __restrict__ dscal /* or nullptr */, PublishBlock* host, unsigned long long seq) {
+  const int t = threadIdx.x;
+  if (t < 32) host->sc[t] = scalars[t];
+  else if (t < 34) host->info[t - 32] = pcg_info[t - 32];
+  else if (t == 34) host->info[2] = fail[0];
+  else if (t < 37 && dscal) host->dscal[t - 35] = dscal[t - 35];
+  __threadfence_system();
+  __syncthreads();
+  if (t == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&host->seq) = seq;
+  }
+}
+
 // |x|^2 of the current point over the coordinates that are in the Ceres problem: partial sums per CTA
 __global__ void k_xnorm2(int V, int P, const int* __restrict__ view_active, const double* __restrict__ intr, const double* __restrict__ ext,
                          const int* __restrict__ t_off, const double* __restrict__ trk, double* __restrict__ part2) {

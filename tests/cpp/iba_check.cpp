@@ -1,13 +1,17 @@
 // Drives PtzIncrementalOptimizer (include/ptzcalib_b200.hpp, mirror of src/core/ptz_incremental_optimizer.h) the way
 // run_ptz_ba.cc does: features + a table of pairwise matches with homographies and confidences, cameras unknown.
 // Input: a synthetic scene (ground-truth cameras, observations by view/track); output: registered ids and refined cameras.
+#include <dlfcn.h>
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <vector>
 
 #include "../../include/ptzcalib_b200.hpp"
+#include "../../oracle/iba_oracle.h"  // (tests may use the oracle; the product never does)
 
 using namespace ptzcalib;
 
@@ -70,7 +74,8 @@ int main(int argc, char** argv) {
   PtzIncrementalOptimizer iba(features, matches_info, cameras, max_iter);
   std::unordered_set<long> reg;
   const auto t0 = std::chrono::steady_clock::now();
-  const bool ok = iba.Solve(cameras, reg);
+  const bool only_oracle = argc > 4;  // CPU-only check of the oracle's driver (no device needed)
+  const bool ok = only_oracle ? false : iba.Solve(cameras, reg);
   const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
   FILE* g = fopen(argv[2], "wb");
@@ -81,6 +86,58 @@ int main(int argc, char** argv) {
   std::vector<double> out(22 * (size_t)V);
   for (int i = 0; i < V; ++i) { out[22 * (size_t)i] = reg.count(i) ? 1.0 : 0.0; cameras[i].ToKrt21(&out[22 * (size_t)i + 1]); }
   fwrite(out.data(), sizeof(double), out.size(), g);
+  // the driver's decisions, then (argv[3] = path of the oracle library) the same run through the CPU restatement of the
+  // reference's sequential driver on the very same tables
+  {
+    std::vector<double> tr(1 + 3 * iba.trace().size());
+    tr[0] = (double)iba.trace().size();
+    for (size_t k = 0; k < iba.trace().size(); ++k) for (int c = 0; c < 3; ++c) tr[1 + 3 * k + c] = (double)iba.trace()[k][c];
+    fwrite(tr.data(), sizeof(double), tr.size(), g);
+  }
+  if (argc > 3) {
+    void* so = dlopen(argv[3], RTLD_NOW | RTLD_LOCAL);
+    if (!so) { fprintf(stderr, "dlopen %s: %s\n", argv[3], dlerror()); return 3; }
+    typedef int (*solve_fn)(const orc_iba_input*, orc_iba_output*);
+    solve_fn orc_solve = (solve_fn)dlsym(so, "orc_iba_solve");
+    if (!orc_solve) { fprintf(stderr, "orc_iba_solve missing\n"); return 3; }
+    std::vector<int32_t> iw(V, 1920), ih(V, 1080), src, dst, qi, ti;
+    std::vector<int64_t> kpo(V + 1, 0), mo(1, 0);
+    std::vector<float> kpuv;
+    std::vector<double> H, conf, c0(21 * (size_t)V);
+    std::vector<uint8_t> hasH;
+    for (int i = 0; i < V; ++i) {
+      kpo[i + 1] = kpo[i] + (int64_t)features[i].keypoints.size();
+      for (const auto& k : features[i].keypoints) { kpuv.push_back(k.pt.x); kpuv.push_back(k.pt.y); }
+      Camera().ToKrt21(&c0[21 * (size_t)i]);
+    }
+    for (const auto& mi : matches_info) {
+      src.push_back((int32_t)mi.src_img_idx); dst.push_back((int32_t)mi.dst_img_idx);
+      for (const auto& m : mi.matches) { qi.push_back(m.queryIdx); ti.push_back(m.trainIdx); }
+      mo.push_back((int64_t)qi.size());
+      for (int e = 0; e < 9; ++e) H.push_back(mi.H[e]);
+      hasH.push_back(mi.has_H ? 1 : 0);
+      conf.push_back(mi.confidence);
+    }
+    orc_iba_input in{};
+    in.num_images = V; in.img_w = iw.data(); in.img_h = ih.data(); in.kp_offset = kpo.data(); in.kp_uv = kpuv.data();
+    in.num_pairs = (int32_t)src.size(); in.pair_src = src.data(); in.pair_dst = dst.data(); in.match_offset = mo.data(); in.query_idx = qi.data();
+    in.train_idx = ti.data(); in.H = H.data(); in.has_H = hasH.data(); in.confidence = conf.data(); in.cams21 = c0.data(); in.max_iter = max_iter;
+    std::vector<uint8_t> oreg(V, 0);
+    std::vector<double> ocam(21 * (size_t)V);
+    std::vector<int64_t> ev(3 * 65536);
+    orc_iba_output o{};
+    o.registered = oreg.data(); o.cams21 = ocam.data(); o.events = ev.data(); o.cap_events = 65536;
+    const auto t1 = std::chrono::steady_clock::now();
+    const int rc = orc_solve(&in, &o);
+    const double osec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+    const int ne = std::min(o.num_events, o.cap_events);
+    std::vector<double> od(5 + 3 * (size_t)ne + 22 * (size_t)V);
+    od[0] = (double)rc; od[1] = (double)o.ok; od[2] = (double)o.num_registered; od[3] = o.last_reproj_error; od[4] = (double)ne;
+    for (int k = 0; k < 3 * ne; ++k) od[5 + k] = (double)ev[k];
+    for (int i = 0; i < V; ++i) { od[5 + 3 * (size_t)ne + 22 * (size_t)i] = oreg[i]; std::memcpy(&od[5 + 3 * (size_t)ne + 22 * (size_t)i + 1], &ocam[21 * (size_t)i], 21 * sizeof(double)); }
+    fwrite(od.data(), sizeof(double), od.size(), g);
+    printf("oracle driver: ok=%d registered=%d events=%d reproj=%.4f  %.3f s\n", o.ok, o.num_registered, o.num_events, o.last_reproj_error, osec);
+  }
   fclose(g);
   size_t nm = 0;
   for (auto& mi : matches_info) nm += mi.matches.size();

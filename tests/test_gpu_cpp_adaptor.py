@@ -17,8 +17,64 @@ def build_exe(tmp_path, name="adaptor_check"):
     exe = str(tmp_path / name)
     so_dir = os.path.dirname(lib.SO_PATH)
     subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe, "-L" + so_dir, "-lptzcalib_b200",
-                    "-Wl,-rpath," + so_dir], check=True)
+                    "-ldl", "-Wl,-rpath," + so_dir], check=True)
     return exe
+
+
+ORACLE_SO = os.path.join(ROOT, "oracle", "libptz_oracle.so")
+
+
+def write_iba_input(path, p, max_iter, both_directions):
+    gt, V = p.gt, p.V
+    cams = np.zeros((V, 21))
+    for i in range(V):
+        cams[i, 0] = cams[i, 1] = gt["f"][i]
+        cams[i, 2:4] = gt["c"][i]
+        cams[i, 4:13] = gt["R"][i].ravel()
+    with open(path, "wb") as f:
+        f.write(struct.pack("4i", V, p.M, max_iter, both_directions))
+        for a in (cams, p.obs_view, p.obs_track, p.obs_uv):
+            f.write(np.ascontiguousarray(a).tobytes())
+
+
+def parse_iba_output(path, V):
+    """head(8) | V x (registered, krt21) | n, n x (kind, a, b) of the GPU driver | oracle: (rc, ok, registered, reproj, n), events, V x 22"""
+    out = np.fromfile(path, dtype=np.float64)
+    head, rows = out[:8], out[8 : 8 + 22 * V].reshape(V, 22)
+    pos = 8 + 22 * V
+    nt = int(out[pos])
+    trace = out[pos + 1 : pos + 1 + 3 * nt].reshape(nt, 3).astype(np.int64)
+    pos += 1 + 3 * nt
+    if pos >= out.size:
+        return head, rows, trace, None, None, None
+    oh = out[pos : pos + 5]
+    ne = int(oh[4])
+    otrace = out[pos + 5 : pos + 5 + 3 * ne].reshape(ne, 3).astype(np.int64)
+    orows = out[pos + 5 + 3 * ne :].reshape(V, 22)
+    return head, rows, trace, oh, otrace, orows
+
+
+def test_iba_oracle_driver_on_cpu(tmp_path):
+    """CPU: the restated reference driver (oracle/iba_oracle.cpp) with the oracle's own BA / KRT / tracks registers a synthetic ring
+    from unknown cameras and lands on the ground truth -- the checker is itself checked before the GPU driver is compared with it."""
+    exe = build_exe(tmp_path, "iba_check")
+    p = synth.make_config(1, scale=0.4)
+    fin, fout = str(tmp_path / "iba_in.bin"), str(tmp_path / "iba_out.bin")
+    write_iba_input(fin, p, 100, 1)
+    r = subprocess.run([exe, fin, fout, ORACLE_SO, "oracle-only"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    _, _, trace, oh, otrace, orows = parse_iba_output(fout, p.V)
+    assert trace.size == 0 and oh[0] == 0.0 and oh[1] == 1.0 and int(oh[2]) == p.V, r.stdout
+    kinds = otrace[:, 0].tolist()
+    assert kinds[0] == 1 and kinds[1] == 2 and otrace[1, 1] == 1 and kinds[2] == 3 and kinds[-1] == 3
+    registered_in_order = [int(a) for k, a, b in otrace if k == 4 and b >= 0]
+    assert len(set(registered_in_order)) == len(registered_in_order) == p.V - 2
+    gt = p.gt
+    assert np.abs(orows[:, 1] / gt["f"] - 1).max() < 5e-3
+    R = orows[:, 5:14].reshape(p.V, 3, 3)
+    for b in range(1, p.V):
+        rel_est, rel_gt = R[b] @ R[0].T, gt["R"][b] @ gt["R"][0].T
+        assert np.arccos(np.clip((np.trace(rel_est @ rel_gt.T) - 1) / 2, -1, 1)) < 2e-3
 
 
 def test_adaptor_compiles_without_gpu(tmp_path):
@@ -79,21 +135,22 @@ def test_incremental_driver_registers_the_whole_scene(tmp_path, orc, both_direct
     p = synth.make_config(1, scale=0.5)
     gt = p.gt
     V = p.V
-    cams = np.zeros((V, 21))
-    for i in range(V):
-        cams[i, 0] = cams[i, 1] = gt["f"][i]
-        cams[i, 2:4] = gt["c"][i]
-        cams[i, 4:13] = gt["R"][i].ravel()
     fin, fout = str(tmp_path / "iba_in.bin"), str(tmp_path / "iba_out.bin")
-    with open(fin, "wb") as f:
-        f.write(struct.pack("4i", V, p.M, 100, both_directions))
-        for a in (cams, p.obs_view, p.obs_track, p.obs_uv):
-            f.write(np.ascontiguousarray(a).tobytes())
-    r = subprocess.run([exe, fin, fout], capture_output=True, text=True, timeout=300)
+    write_iba_input(fin, p, 100, both_directions)
+    r = subprocess.run([exe, fin, fout, ORACLE_SO], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
-    out = np.fromfile(fout, dtype=np.float64)
-    head, rows = out[:8], out[8:].reshape(V, 22)
+    head, rows, trace, orc_head, orc_trace, orc_rows = parse_iba_output(fout, V)
     assert head[0] == 1.0, r.stdout
+    # decision-for-decision against the CPU restatement of the reference's SEQUENTIAL driver (oracle/iba_oracle.cpp) on the same
+    # tables: seed pair, LM iterations of the two-view BA, every FindNextImages list (length, head), every registration attempt and
+    # the registered neighbour it succeeded from, every global BA (outcome, model size), un-register events -- in the same order
+    assert orc_head[0] == 0.0 and orc_head[1] == 1.0, r.stdout
+    assert trace.shape == orc_trace.shape and (trace == orc_trace).all(), (trace.tolist(), orc_trace.tolist())
+    assert (rows[:, 0] == orc_rows[:, 0]).all()
+    both = rows[:, 0] == 1.0
+    assert np.abs(rows[both, 1] - orc_rows[both, 1]).max() <= 1e-4                 # focal [px]
+    assert np.abs(rows[both, 5:14] - orc_rows[both, 5:14]).max() <= 1e-6           # R entries
+    assert abs(head[5] - orc_head[3]) <= 1e-6 * orc_head[3]                        # reprojection error of the last global BA
     reg = rows[:, 0] == 1.0
     if both_directions:
         assert reg.all(), r.stdout

@@ -189,10 +189,14 @@ typedef struct ptzba_stage_times {
   int64_t num_pairs;       /* observation pairs summed into the off-diagonal blocks */
 } ptzba_stage_times;
 int ptzba_get_stage_times(ptzba_handle* h, ptzba_stage_times* t);
+/* per_kernel = 0: stop bracketing every kernel with CUDA events (ms_kernel[] stops accumulating; launches[] and ms_run keep counting).
+ * The events cost two cudaEventRecord per launch; bench.py times its headline with them off and the per-kernel table in a second pass. */
+int ptzba_set_stage_timing(ptzba_handle* h, int per_kernel);
 int ptzba_destroy(ptzba_handle* h);
 
 /* multi-GPU: the caller shards tracks (hence observations) across ranks and hands every rank the same
- * views; the library all-reduces camera blocks over its own NCCL communicator.  id_bytes is the 128-byte
+ * views AND the same annotated 2d-3d points (they are evaluated on rank 0 and reach the other ranks inside
+ * the all-reduce); the library all-reduces camera blocks over its own NCCL communicator.  id_bytes is the 128-byte
  * ncclUniqueId made on rank 0 by ptz_nccl_unique_id and broadcast by the caller (torch.distributed). */
 int ptz_nccl_unique_id(void* id_bytes128);
 int ptz_nccl_init(const void* id_bytes128, int rank, int world_size);

@@ -67,6 +67,10 @@ class BAHandle:
         lib.check(rc, "ptzba_run")
         return problem.unpack_ba_result(self.prob, r, arrs, log)
 
+    def set_stage_timing(self, per_kernel: bool):
+        """per-kernel CUDA events on/off (ptzba_set_stage_timing); the span of the runs is always timed"""
+        lib.check(lib.load().ptzba_set_stage_timing(self._h, C.c_int(1 if per_kernel else 0)), "ptzba_set_stage_timing")
+
     def stage_times(self) -> dict:
         t = abi.StageTimesC()
         lib.check(lib.load().ptzba_get_stage_times(self._h, C.byref(t)), "ptzba_get_stage_times")

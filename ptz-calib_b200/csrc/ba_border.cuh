@@ -1,37 +1,41 @@
 // ba_border.cuh — the georeferencing terms of PTZ-BA: annotated 2d-3d points (AddConstraints2d3d,
-// ptzray_optimizer.cc:887-958; Reproj2d3dFactor :268-326).  There are only tens of them, in a handful of views, so they
-// are handled by ONE CTA with fixed-order loops (deterministic, no atomics).  They couple the annotated views to a
-// small dense BORDER of the reduced system:
-//     border = [ tlw(6) | fy of each annotated view (factor types that tie fy:=fx in the ray terms) ]
-// (fy is identically-zero-column in the ray factors of those types and is driven only by these terms: SURVEY.md A6.)
+// ptzray_optimizer.cc:887-958; Reproj2d3dFactor :268-326).  They are few next to the ray observations, so ONE CTA handles
+// them with fixed-order loops (deterministic, no atomics).  They bring two kinds of unknowns besides the cameras:
+//     border  = [ tlw(6) | disp(3) ]                 <= 9 unknowns, a dense row/column of the reduced system (k_cg's border row)
+//     fy_k    = fy of annotated view k               (factor types that tie fy := fx in the ray terms: the column is identically
+//                                                     zero there and is driven only by these terms)
+// fy_k touches nothing but its own view's points, i.e. the camera block of view k and the border: it is ELIMINATED like a ray
+// (1x1 Schur complement, k_border_system / k_fy_eliminate / back-substitution in k_border_update), so any number of views may be
+// annotated.  Vectors over [border | fy] (scales, LM diagonal, gradient) are stored with the fy part behind the nb border entries.
 #pragma once
 #include "ba_kernels.cuh"
 
 namespace ptz {
 
 struct PtsArgs {
-  int A, nav, nb, fy_in_border;     // fy_in_border = 1 for the factor types that tie fy := fx in the ray terms
-  int bo_tlw, bo_fy, bo_disp;       // first border column of tlw(6) / fy(nav) / disp(3), or -1
+  int A, nav, nb, nf;               // nf = nav when fy lives outside the camera block (fy := fx factor types), else 0
+  int bo_tlw, bo_disp;              // first border column of tlw(6) / disp(3), or -1
   const int* ann_strip;             // strip row of annotated view k inside C (k itself, or the view id when every view has a strip)
   const double* disp;               // current disp[3] (PTZRayDistDisp) or nullptr
   const float2* uv; const double* xyz; const int* view;   // sorted by view
   const int* ann_view; const int* ann_off;                // [nav], [nav+1]
   const ViewTab* vt; const double* tlw;                   // current parameters
-  const double* scale_cam; const double* scale_b;
-  double* scratch;                  // [A][2 + 2*NCL + 2*nb] scaled rows
+  const double* scale_cam; const double* scale_b;         // scale_b: [nb + nf]
+  double* scratch;                  // [A][2 + 2*NCL + 2*nb + 2] scaled rows: r, Fc, B (border columns), bf (fy column)
   double* raw;                      // optional [A][2 + 12 + 12 + 6]: r, Jc(2x6), Jt(2x6), Jd(2x3) unscaled (ptzba_eval), or nullptr
   // outputs
   double* U; double* g; double* gabs;   // += on the annotated views
-  double* C;                        // [nav][NCL][nb]
-  double* Hbb; double* gb;          // [nb*nb], [nb]
+  double* C;                        // [strips][NCL][nb]
+  double* Hbb; double* gb;          // [nb*nb], [nb + nf]
+  double* Cf; double* Hrf; double* Hff;  // fy_k: coupling to its camera block [nf][NCL], to the border [nf][nb], own diagonal [nf]
   double* cost_pts;                 // [2]: 1/2 sum r^2, sum r^2
-  double* gabs_b;                   // [nb]
+  double* gabs_b;                   // [nb + nf]
 };
 
 template <int TYPE>
 __global__ void __launch_bounds__(128) k_pts(PtsArgs a) {
   constexpr int NCL = ba_ncl(TYPE);
-  const int nb = a.nb, RW = 2 + 2 * NCL + 2 * nb;
+  const int nb = a.nb, RW = 2 + 2 * NCL + 2 * nb + 2;
   __shared__ double sR[9], sdR[9], st[3];
   if (threadIdx.x == 0) {
     double w[3] = {a.tlw[0], a.tlw[1], a.tlw[2]};
@@ -46,7 +50,11 @@ __global__ void __launch_bounds__(128) k_pts(PtsArgs a) {
   for (int i = threadIdx.x; i < a.A; i += blockDim.x) {
     const int v = a.view[i];
     int k = 0;
-    while (a.ann_view[k] != v) ++k;
+    {  // annotated-view index of v (ann_view is ascending)
+      int lo = 0, hi = a.nav - 1;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (a.ann_view[mid] < v) lo = mid + 1; else hi = mid; }
+      k = lo;
+    }
     const ViewTab vt = a.vt[v];
     const double Xw[3] = {a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2]};
     double r[2], Jc[12], Jt[12], Jd[6] = {0, 0, 0, 0, 0, 0};
@@ -67,6 +75,7 @@ __global__ void __launch_bounds__(128) k_pts(PtsArgs a) {
     row[0] = r[0]; row[1] = r[1];
     double* Fc = row + 2;            // [2][NCL]
     double* Bj = row + 2 + 2 * NCL;  // [2][nb]
+    double* bf = Bj + 2 * nb;        // [2]
     for (int j = 0; j < 2 * nb; ++j) Bj[j] = 0.0;
     for (int rr = 0; rr < 2; ++rr) {
       const double* jc = Jc + 6 * rr;
@@ -77,26 +86,34 @@ __global__ void __launch_bounds__(128) k_pts(PtsArgs a) {
       else { live[n++] = jc[0]; live[n++] = jc[2]; live[n++] = jc[3]; live[n++] = jc[4]; live[n++] = jc[5]; }
       for (int c = 0; c < NCL; ++c) Fc[rr * NCL + c] = live[c] * a.scale_cam[v * NCL + c];
       for (int j = 0; j < 6; ++j) Bj[rr * nb + a.bo_tlw + j] = Jt[6 * rr + j] * a.scale_b[a.bo_tlw + j];
-      if (a.fy_in_border) Bj[rr * nb + a.bo_fy + k] = jc[1] * a.scale_b[a.bo_fy + k];
+      bf[rr] = a.nf > 0 ? jc[1] * a.scale_b[nb + k] : 0.0;
       if (TYPE == BA_PTZRAY_DIST_DISP) for (int j = 0; j < 3; ++j) Bj[rr * nb + a.bo_disp + j] = Jd[3 * rr + j] * a.scale_b[a.bo_disp + j];
     }
   }
   __syncthreads();
-  // phase 2a: per annotated view, camera block / gradient / coupling strip (fixed order over its points)
+  // phase 2a: per annotated view, camera block / gradient / coupling strip and the fy terms (fixed order over its points)
   for (int k = threadIdx.x; k < a.nav; k += blockDim.x) {
     const int v = a.ann_view[k];
-    double Uadd[NCL * NCL], gadd[NCL];
+    double Uadd[NCL * NCL], gadd[NCL], cf[NCL], hff = 0, gf = 0;
     for (int i = 0; i < NCL * NCL; ++i) Uadd[i] = 0;
-    for (int i = 0; i < NCL; ++i) gadd[i] = 0;
+    for (int i = 0; i < NCL; ++i) { gadd[i] = 0; cf[i] = 0; }
     double* Ck = a.C + (size_t)a.ann_strip[k] * NCL * nb;  // zeroed by the caller; the disp kernels add to it as well
+    double* Hk = a.nf > 0 ? a.Hrf + (size_t)k * nb : nullptr;  // zeroed by the caller
     for (int i = a.ann_off[k]; i < a.ann_off[k + 1]; ++i) {
       const double* row = a.scratch + (size_t)i * RW;
       const double* Fc = row + 2;
       const double* Bj = row + 2 + 2 * NCL;
+      const double* bf = Bj + 2 * nb;
       for (int c = 0; c < NCL; ++c) {
         gadd[c] += Fc[c] * row[0] + Fc[NCL + c] * row[1];
         for (int d = 0; d < NCL; ++d) Uadd[c * NCL + d] += Fc[c] * Fc[d] + Fc[NCL + c] * Fc[NCL + d];
         for (int j = 0; j < nb; ++j) Ck[c * nb + j] += Fc[c] * Bj[j] + Fc[NCL + c] * Bj[nb + j];
+        cf[c] += Fc[c] * bf[0] + Fc[NCL + c] * bf[1];
+      }
+      if (a.nf > 0) {
+        for (int j = 0; j < nb; ++j) Hk[j] += bf[0] * Bj[j] + bf[1] * Bj[nb + j];
+        hff += bf[0] * bf[0] + bf[1] * bf[1];
+        gf += bf[0] * row[0] + bf[1] * row[1];
       }
     }
     for (int i = 0; i < NCL * NCL; ++i) a.U[(size_t)v * NCL * NCL + i] += Uadd[i];
@@ -104,6 +121,12 @@ __global__ void __launch_bounds__(128) k_pts(PtsArgs a) {
       const double gv = a.g[v * NCL + c] + gadd[c];
       a.g[v * NCL + c] = gv;
       a.gabs[v * NCL + c] = fabs(gv / a.scale_cam[v * NCL + c]);
+    }
+    if (a.nf > 0) {
+      for (int c = 0; c < NCL; ++c) a.Cf[(size_t)k * NCL + c] = cf[c];
+      a.Hff[k] = hff;
+      a.gb[nb + k] = gf;
+      a.gabs_b[nb + k] = fabs(gf / a.scale_b[nb + k]);
     }
   }
   // phase 2b: border block and gradient
@@ -164,15 +187,36 @@ __global__ void k_pts_cost(int A, const float2* __restrict__ uv, const double* _
   if (threadIdx.x == 0) { out2[0] = 0.5 * s; out2[1] = s; }
 }
 
-// Jacobi scaling of the border columns at iteration 0
-__global__ void k_border_scales(int nb, const double* __restrict__ Hbb, double* __restrict__ scale_b) {
-  const int i = threadIdx.x;
+// Jacobi scaling of the border and fy columns at iteration 0
+__global__ void k_border_scales(int nb, int nf, const double* __restrict__ Hbb, const double* __restrict__ Hff, double* __restrict__ scale_b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nb) scale_b[i] = 1.0 / (1.0 + sqrt(Hbb[i * nb + i]));
+  else if (i < nb + nf) scale_b[i] = 1.0 / (1.0 + sqrt(Hff[i - nb]));
+}
+// |g_j / s_j| of every camera, border and fy column from the (all-reduced) gradient: the sharded problem's replacement for the
+// values k_view_finalize / k_pts wrote from rank-local sums
+__global__ void k_grad_abs(int ncam, const double* __restrict__ g, const double* __restrict__ scale_cam, double* __restrict__ gabs, int nbt,
+                           const double* __restrict__ gb, const double* __restrict__ scale_b, double* __restrict__ gabs_b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ncam) gabs[i] = fabs(g[i] / scale_cam[i]);
+  else if (i < ncam + nbt) gabs_b[i - ncam] = fabs(gb[i - ncam] / scale_b[i - ncam]);
 }
 
-// S_bb = H_bb + D_b^2, rhs_b = g_b  (D_b^2 = clamp(diag H_bb)/mu, refreshed after accepted steps only)
-__global__ void k_border_system(int nb, const double* __restrict__ Hbb, const double* __restrict__ gb, double mu, int refresh_diag, double min_diag,
-                                double max_diag, double* __restrict__ diag_b, double* __restrict__ Sbb, double* __restrict__ rhs_b) {
+// Border system of one linear solve, with the fy unknowns eliminated:
+//   h_k = Hff_k + D_k^2          S_bb = H_bb + D_b^2 - sum_k Hrf_k Hrf_k^T / h_k          rhs_b = g_b - sum_k Hrf_k gf_k / h_k
+// (D^2 = clamp(diag)/mu, refreshed after accepted steps only; sums over k in ascending order).  One CTA.
+__global__ void __launch_bounds__(128) k_border_system(int nb, int nf, const double* __restrict__ Hbb, const double* __restrict__ Hrf,
+                                                       const double* __restrict__ Hff, const double* __restrict__ gb, double mu, int refresh_diag,
+                                                       double min_diag, double max_diag, int own /* sharded problem: rank 0 contributes, the others write zeros */,
+                                                       double* __restrict__ diag_b, double* __restrict__ hinv, double* __restrict__ Sbb,
+                                                       double* __restrict__ rhs_b) {
+  for (int k = threadIdx.x; k < nf; k += blockDim.x) {
+    double d;
+    if (refresh_diag) { d = fmin(fmax(Hff[k], min_diag), max_diag); diag_b[nb + k] = d; }
+    else d = diag_b[nb + k];
+    hinv[k] = 1.0 / (Hff[k] + d / mu);
+  }
+  __syncthreads();
   for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
     const int i = e / nb, j = e % nb;
     double s = Hbb[e];
@@ -181,43 +225,84 @@ __global__ void k_border_system(int nb, const double* __restrict__ Hbb, const do
       if (refresh_diag) { d = fmin(fmax(Hbb[e], min_diag), max_diag); diag_b[i] = d; }
       else d = diag_b[i];
       s += d / mu;
-      rhs_b[i] = gb[i];
+      double r = gb[i];
+      for (int k = 0; k < nf; ++k) r -= Hrf[(size_t)k * nb + i] * gb[nb + k] * hinv[k];
+      rhs_b[i] = own ? r : 0.0;
     }
-    Sbb[e] = s;
+    for (int k = 0; k < nf; ++k) s -= Hrf[(size_t)k * nb + i] * Hrf[(size_t)k * nb + j] * hinv[k];
+    Sbb[e] = own ? s : 0.0;
   }
 }
+// camera side of the fy elimination (one thread per annotated view k, view v):
+//   S_vv -= Cf_k Cf_k^T / h_k      rhs_v -= Cf_k gf_k / h_k      strip_k = C_k - Cf_k Hrf_k^T / h_k   (into the working strips Cw)
+template <int NCL>
+__global__ void k_fy_eliminate(int nf, int nb, const int* __restrict__ ann_view, const int* __restrict__ ann_strip, const double* __restrict__ Cf,
+                               const double* __restrict__ Hrf, const double* __restrict__ gf, const double* __restrict__ hinv,
+                               const double* __restrict__ Csrc, double* __restrict__ Cw, const int* __restrict__ diag_pos, double* __restrict__ Sval,
+                               double* __restrict__ rhs) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nf) return;
+  const int v = ann_view[k];
+  const double hi = hinv[k];
+  double cf[NCL];
+#pragma unroll
+  for (int a = 0; a < NCL; ++a) cf[a] = Cf[(size_t)k * NCL + a];
+  double* S = Sval + (size_t)diag_pos[v] * NCL * NCL;
+#pragma unroll
+  for (int a = 0; a < NCL; ++a) {
+#pragma unroll
+    for (int b = 0; b < NCL; ++b) S[a * NCL + b] -= cf[a] * cf[b] * hi;
+    rhs[v * NCL + a] -= cf[a] * gf[k] * hi;
+  }
+  const size_t so = (size_t)ann_strip[k] * NCL * nb;
+  for (int a = 0; a < NCL; ++a)
+    for (int j = 0; j < nb; ++j) Cw[so + a * nb + j] = Csrc[so + a * nb + j] - cf[a] * Hrf[(size_t)k * nb + j] * hi;
+}
 
-// candidate border parameters; part3 = {model cost change, |step|^2, |x_cand|^2} contributions (fy corrections included)
-__global__ void k_border_update(int nb, int nav, int bo_tlw, int bo_fy, int bo_disp, const int* __restrict__ ann_view, const double* __restrict__ yb,
-                                const double* __restrict__ scale_b, const double* __restrict__ gb, const double* __restrict__ diag_b, double mu,
-                                const double* __restrict__ tlw, double* __restrict__ tlw_c, const double* __restrict__ intr, double* __restrict__ intr_c,
-                                const double* __restrict__ disp, double* __restrict__ disp_c, double* __restrict__ part3) {
-  if (threadIdx.x != 0) return;
+// candidate border parameters and the back-substituted fy steps  y_fk = (gf_k - Cf_k^T y_v - Hrf_k^T y_b) / h_k;
+// part3 = {model cost change, |step|^2, |x_cand|^2} contributions.  One warp, lanes stride the annotated views.
+template <int NCL>
+__global__ void __launch_bounds__(32) k_border_update(int nb, int nf, int bo_tlw, int bo_disp, const int* __restrict__ ann_view, const double* __restrict__ y,
+                                                      int ncam, const double* __restrict__ scale_b, const double* __restrict__ gb,
+                                                      const double* __restrict__ diag_b, double mu, const double* __restrict__ Cf,
+                                                      const double* __restrict__ Hrf, const double* __restrict__ hinv, const double* __restrict__ tlw,
+                                                      double* __restrict__ tlw_c, const double* __restrict__ intr, double* __restrict__ intr_c,
+                                                      const double* __restrict__ disp, double* __restrict__ disp_c, double* __restrict__ part3) {
+  const int lane = threadIdx.x;
+  const double* yb = y + ncam;
   double dm = 0, st = 0, xn = 0;
-  for (int j = 0; j < nb; ++j) dm += 0.5 * yb[j] * (gb[j] + diag_b[j] / mu * yb[j]);
-  if (bo_tlw >= 0)
-    for (int j = 0; j < 6; ++j) {
-      const double c = tlw[j] + (-scale_b[bo_tlw + j] * yb[bo_tlw + j]);
-      tlw_c[j] = c;
-      st += (tlw[j] - c) * (tlw[j] - c);
-      xn += c * c;
-    }
-  if (bo_fy >= 0)
-    for (int k = 0; k < nav; ++k) {
-      const int v = ann_view[k];
-      const double x = intr[9 * v + 1], c = x + (-scale_b[bo_fy + k] * yb[bo_fy + k]);
-      intr_c[9 * v + 1] = c;
-      st += (x - c) * (x - c);
-      xn += c * c - x * x;  // k_cam_update counted the unchanged fy
-    }
-  if (bo_disp >= 0)
-    for (int j = 0; j < 3; ++j) {
-      const double c = disp[j] + (-scale_b[bo_disp + j] * yb[bo_disp + j]);
-      disp_c[j] = c;
-      st += (disp[j] - c) * (disp[j] - c);
-      xn += c * c;
-    }
-  part3[0] = dm; part3[1] = st; part3[2] = xn;
+  if (lane == 0) {
+    for (int j = 0; j < nb; ++j) dm += 0.5 * yb[j] * (gb[j] + diag_b[j] / mu * yb[j]);
+    if (bo_tlw >= 0)
+      for (int j = 0; j < 6; ++j) {
+        const double c = tlw[j] + (-scale_b[bo_tlw + j] * yb[bo_tlw + j]);
+        tlw_c[j] = c;
+        st += (tlw[j] - c) * (tlw[j] - c);
+        xn += c * c;
+      }
+    if (bo_disp >= 0)
+      for (int j = 0; j < 3; ++j) {
+        const double c = disp[j] + (-scale_b[bo_disp + j] * yb[bo_disp + j]);
+        disp_c[j] = c;
+        st += (disp[j] - c) * (disp[j] - c);
+        xn += c * c;
+      }
+  }
+  for (int k = lane; k < nf; k += 32) {
+    const int v = ann_view[k];
+    double t = gb[nb + k];
+#pragma unroll
+    for (int a = 0; a < NCL; ++a) t -= Cf[(size_t)k * NCL + a] * y[v * NCL + a];
+    for (int j = 0; j < nb; ++j) t -= Hrf[(size_t)k * nb + j] * yb[j];
+    const double yf = t * hinv[k];
+    dm += 0.5 * yf * (gb[nb + k] + diag_b[nb + k] / mu * yf);
+    const double x = intr[9 * v + 1], c = x + (-scale_b[nb + k] * yf);
+    intr_c[9 * v + 1] = c;
+    st += (x - c) * (x - c);
+    xn += c * c - x * x;  // k_cam_update counted the unchanged fy
+  }
+  dm = warp_sum(dm); st = warp_sum(st); xn = warp_sum(xn);
+  if (lane == 0) { part3[0] = dm; part3[1] = st; part3[2] = xn; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -297,7 +382,7 @@ __global__ void k_disp_track(int P, const int* __restrict__ t_off, const int* __
 // of the working copy Cw (= C at the last Jacobian evaluation)
 template <int NCL>
 __global__ void k_disp_schur_view(int V, const int* __restrict__ view_off, const int* __restrict__ o_track, const double* __restrict__ What,
-                                  const double* __restrict__ Wdh, int nb, int bo_disp, const double* __restrict__ C, double* __restrict__ Cw) {
+                                  const double* __restrict__ Wdh, int nb, int bo_disp, int own, const double* __restrict__ C, double* __restrict__ Cw) {
   typedef Dims<NCL> D;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
@@ -311,7 +396,7 @@ __global__ void k_disp_schur_view(int V, const int* __restrict__ view_off, const
   }
   for (int a = 0; a < NCL; ++a)
     for (int j = 0; j < nb; ++j) {
-      double val = C[((size_t)v * NCL + a) * nb + j];
+      double val = own ? C[((size_t)v * NCL + a) * nb + j] : 0.0;  // (sharded problem: the ranks' pieces are summed by the all-reduce)
       if (j >= bo_disp && j < bo_disp + 3) val -= c[a * 3 + (j - bo_disp)];
       Cw[((size_t)v * NCL + a) * nb + j] = val;
     }

@@ -18,7 +18,8 @@ namespace ptz {
 namespace cg = cooperative_groups;
 
 constexpr int kChunk = 128;      // observations per CTA in the streaming passes; chunks never straddle a view
-constexpr int kMaxBorder = 32;   // dense border (tlw + per-annotated-view fy): one warp owns it in the PCG
+constexpr int kMaxBorder = 9;    // dense border of the reduced system: tlw(6) + disp(3); one warp owns its row in the CG (the fy of
+                                 // annotated views are eliminated before the CG, ba_border.cuh)
 
 template <int NCL>
 struct Dims {
@@ -1141,25 +1142,44 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
             }
           }
         }
-      } else if (lane < nb) {  // dense border row (single rank only, never deflated)
-        const int i = boff + lane;
+      } else if (KD == 0) {  // dense border row (never deflated, never sharded): the lanes split the coupled views
         const double* q = so + 3 * (size_t)boff;
-        const double ro = __ldcg(q + lane), wo = __ldcg(q + nb + lane), s_o = __ldcg(q + 2 * nb + lane);
-        const double pn = ro + beta * A.p[i];
-        const double s_n = wo + beta * s_o;
-        A.p[i] = pn;
-        xl[i] += alpha * pn;
-        const double rn = ro - alpha * s_n;
-        double* qn = sn + 3 * (size_t)boff;
-        qn[lane] = rn; qn[2 * nb + lane] = s_n;
-        double tot = rn;  // unit diagonal block
-        for (int k = 0; k < A.nav; ++k) {
+        double part[kMaxBorder];
+#pragma unroll
+        for (int j = 0; j < kMaxBorder; ++j) part[j] = 0.0;
+        for (int k = lane; k < A.nav; k += 32) {
           const double* qc = so + (size_t)A.ann_view[k] * 3 * NCL;
-          for (int a = 0; a < NCL; ++a)
-            tot += A.C[((size_t)k * NCL + a) * nb + lane] * (__ldcg(qc + a) - alpha * (__ldcg(qc + NCL + a) + beta * __ldcg(qc + 2 * NCL + a)));
+#pragma unroll
+          for (int a = 0; a < NCL; ++a) {
+            const double rk = __ldcg(qc + a) - alpha * (__ldcg(qc + NCL + a) + beta * __ldcg(qc + 2 * NCL + a));
+            const double* crow = A.C + ((size_t)k * NCL + a) * nb;
+#pragma unroll
+            for (int j = 0; j < kMaxBorder; ++j)
+              if (j < nb) part[j] += crow[j] * rk;
+          }
         }
-        qn[nb + lane] = tot;
-        acc[0] += rn * rn; acc[1] += tot * rn;
+        double mine_part = 0.0;
+#pragma unroll
+        for (int j = 0; j < kMaxBorder; ++j) {
+          double t = part[j];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == j) mine_part = t;
+        }
+        if (lane < nb) {
+          const int i = boff + lane;
+          const double ro = __ldcg(q + lane), wo = __ldcg(q + nb + lane), s_o = __ldcg(q + 2 * nb + lane);
+          const double pn = ro + beta * A.p[i];
+          const double s_n = wo + beta * s_o;
+          A.p[i] = pn;
+          xl[i] += alpha * pn;
+          const double rn = ro - alpha * s_n;
+          double* qn = sn + 3 * (size_t)boff;
+          qn[lane] = rn; qn[2 * nb + lane] = s_n;
+          const double tot = rn + mine_part;  // unit diagonal block
+          qn[nb + lane] = tot;
+          acc[0] += rn * rn; acc[1] += tot * rn;
+        }
       }
     }
     PTZ_CG_PROF(0)  // rows: owner update + sparse product

@@ -198,7 +198,10 @@ struct StageClock {
   int launches[PTZ_K_COUNT] = {0};
   float ms_run = 0;
   cudaStream_t stream = nullptr;
-  void init(cudaStream_t s) { stream = s; }
+  // per-kernel events: two cudaEventRecord per launch, which open small gaps between dependent kernels on the device (measured
+  // below).  On by default (ptzba_get_stage_times reports them); ptzba_set_stage_timing(h, 0) keeps only the span of the runs.
+  bool per_kernel = true;
+  void init(cudaStream_t s) { stream = s; const char* e = getenv("PTZ_STAGE_TIMES"); if (e) per_kernel = atoi(e) != 0; }
   void begin(int id) {
     if (used + 2 > ev.size()) {
       for (int i = 0; i < 256; ++i) ev.push_back(HostCache::get_event());
@@ -221,7 +224,7 @@ struct StageClock {
   ~StageClock() { HostCache::put_events(ev); }  // (the owning solver synchronised its stream before this runs)
 };
 // time one kernel launch (or one collective) under its id
-#define PTZ_TIMED(id, ...) do { clk.begin(id); __VA_ARGS__; clk.end(); ++clk.launches[id]; } while (0)
+#define PTZ_TIMED(id, ...) do { if (clk.per_kernel) { clk.begin(id); __VA_ARGS__; clk.end(); } else { __VA_ARGS__; } ++clk.launches[id]; } while (0)
 
 // --------------------------------------------------------------------------------------------------------------
 // the solver, specialised on the factor type
@@ -232,6 +235,7 @@ struct BaSolverBase {
   virtual void run(int max_new_iterations, ptzba_result* out) = 0;
   virtual void eval(const double* disp, ptzba_eval_out* out) = 0;
   virtual void stage_times(ptzba_stage_times* t) = 0;
+  virtual void set_stage_timing(bool on) = 0;
 };
 
 template <int TYPE>
@@ -243,7 +247,9 @@ struct BaSolver : BaSolverBase {
 
   StreamHolder sh;       // first member: destroyed last, after every buffer allocated on its stream
   int V, P, M, A, nb = 0, nav = 0, n = 0;
-  int bo_tlw = -1, bo_fy = -1, bo_disp = -1;  // first border column of tlw(6) / fy(nav) / disp(3)
+  int nf = 0, nbt = 0;                 // fy unknowns of annotated views (eliminated before the CG, ba_border.cuh); nbt = nb + nf
+  int bo_tlw = -1, bo_disp = -1;       // first border column of tlw(6) / disp(3)
+  bool rows_sharded = false;           // the CG's rows are split across the ranks (camera-only systems); else every rank solves it all
   int ncpl = 0;                               // views with a coupling strip to the border (annotated ones, or all of them with disp)
   std::vector<int> h_cpl_view, h_cpl_idx, h_ann_strip;
   ptz_solver_options opt;
@@ -266,18 +272,18 @@ struct BaSolver : BaSolverBase {
   // device: work
   DevBuf<ViewTab> d_vt;
   DevBuf<double> d_scale_cam, d_scale_b, d_rec, d_part, d_viewred, d_Vh, d_gmax_part, d_diag_ray, d_diag_cam, d_diag_b, d_Lt, d_What, d_q, d_sys, d_Linv,
-      d_Linv_b, d_Sbb, d_Cs, d_cgp, d_y, d_pcg_res, d_part3_ray, d_part3_cam, d_part3_b, d_cost_part, d_scalars, d_RiKi, d_pts_scratch, d_pts_raw,
+      d_Linv_b, d_Cs, d_cgp, d_y, d_pcg_res, d_part3_ray, d_part3_cam, d_part3_b, d_cost_part, d_scalars, d_RiKi, d_pts_scratch, d_pts_raw,
       d_pts_xyz;
   DevBuf<float2> d_pts_uv;
   DevBuf<int> d_pts_view, d_ann_view, d_ann_off, d_ann_idx, d_fail, d_pcg_info, d_cpl_view, d_cpl_idx, d_ann_strip;
-  DevBuf<double> d_recd, d_dpart, d_Wdh, d_Cw, d_dispp[2], d_disp_init;
+  DevBuf<double> d_recd, d_dpart, d_Wdh, d_Cw, d_hinv, d_dispp[2], d_disp_init;
   DevBuf<int> d_cg_order;
   // views into d_viewred (all-reduced once per Jacobian evaluation): U | g | cost_view | C | Hbb | gb | cost_pts(2)
-  double *p_U, *p_g, *p_cost_view, *p_C, *p_Hbb, *p_gb, *p_cost_pts, *p_gabs, *p_gabs_b;
+  double *p_U, *p_g, *p_cost_view, *p_C, *p_Hbb, *p_gb, *p_cost_pts, *p_gabs, *p_gabs_b, *p_Cf, *p_Hrf, *p_Hff;
   DevBuf<double> d_gabs;
   size_t viewred_n = 0;
   // views into d_sys (all-reduced once per linear solve): Sval | rhs(n)
-  double *p_Sval, *p_rhs;
+  double *p_Sval, *p_rhs, *p_Sbb, *p_Cw;
   size_t sys_n = 0;
   // what the host reads once per step attempt.  The block is pinned AND device-mapped: k_publish writes it straight over PCIe and
   // raises `seq` behind a system-scope fence; the host spins on `seq` instead of paying three cudaMemcpyAsync + a stream
@@ -394,11 +400,11 @@ struct BaSolver : BaSolverBase {
       h_ann_off.push_back(A);
       nav = (int)h_ann_view.size();
       bo_tlw = 0; nb = 6;
-      if (kFyBorder) { bo_fy = nb; nb += nav; }
+      if (kFyBorder) nf = nav;
     }
     if (kDisp) { bo_disp = nb; nb += 3; }
-    if (nb > kMaxBorder) throw CudaError(PTZ_ERR_UNSUPPORTED, "border larger than 32 unknowns (too many annotated views)");
-    if (g_nccl.world > 1 && nb > 0) throw CudaError(PTZ_ERR_UNSUPPORTED, "2d-3d terms / disp block with a sharded problem");
+    nbt = nb + nf;
+    static_assert(kMaxBorder >= 9, "tlw(6) + disp(3)");
     h_ann_strip.resize(nav);
     if (kDisp) {
       ncpl = V;
@@ -418,18 +424,22 @@ struct BaSolver : BaSolverBase {
       // rows of a CTA are neighbouring views whose gathers overlap (L1 hits).  Then: how many blocks of S fit 200 KB of smem.
       // Sharded problem: the rows are split across the ranks (a contiguous run of the ordering each), see k_cg.
       const int nrows = V + (nb > 0 ? 1 : 0);
-      cgW = g_nccl.world; cgR = g_nccl.rank; cg_vranks = 1;
-      if (cgW == 1 && nb == 0) {
+      // a system with a border row is solved replicated (every rank runs the single-GPU kernel on the all-reduced system): the
+      // border row would sit on one rank and serialise the others behind an NVLink hop per iteration
+      cgW = (nb > 0) ? 1 : g_nccl.world; cgR = g_nccl.rank; cg_vranks = 1;
+      rows_sharded = cgW > 1;
+      if (g_nccl.world == 1 && nb == 0) {
         const char* e = getenv("PTZ_CG_VRANKS");
         const int vr = e ? atoi(e) : 1;
         if (vr > 1 && vr <= kMaxPeers && V >= 2 * vr) { cg_vranks = vr; cgW = vr; }
       }
-      const int W = cgW, R = cgR;
+      const int W = cgW, R = rows_sharded ? cgR : 0;
       const int sms_per_rank = cg_vranks > 1 ? num_sms / cg_vranks : num_sms;
       cg_slots_per_rank = cdiv(nrows, W);
       const int my0 = R * cg_slots_per_rank, my1 = std::min(nrows, my0 + cg_slots_per_rank);
       const int need = cdiv(cg_slots_per_rank, sms_per_rank);
       cg_wpb = need <= 8 ? 8 : 16;  // beyond 16 rows per SM a warp walks several rows
+      if (const char* e = getenv("PTZ_CG_WPB")) { const int w = atoi(e); if (w == 8 || w == 16) cg_wpb = w; }  // tuning hook
       cg_grid = std::min(sms_per_rank, cdiv(cg_slots_per_rank, cg_wpb));  // CTAs per rank
       std::vector<int> h_col(ds.nnzb);
       ds.s_col.download(h_col.data(), ds.nnzb, stream);
@@ -488,7 +498,7 @@ struct BaSolver : BaSolverBase {
       const size_t per_block = NCL * NCL * sizeof(double) + sizeof(int);
       const int fit = (int)((150 * 1024) / (cg_wpb * per_block));  // leave >= 60 KB of the SM's 228 KB to the L1 (the kernel has ~8 KB of static shared memory)
       cg_cap = std::max(1, std::min(worst, fit));
-      if (g_nccl.world > 1) {  // every rank launches the same shape (the slot of a CTA's partial sums is rank * grid + cta)
+      if (rows_sharded) {  // every rank launches the same shape (the slot of a CTA's partial sums is rank * grid + cta)
         DevBuf<double> d_m;
         double m[2] = {(double)cg_cap, 0.0};
         d_m.upload(m, 2, stream);
@@ -615,7 +625,7 @@ struct BaSolver : BaSolverBase {
       d_pts_uv.upload(reinterpret_cast<const float2*>(puv.data()), A, s);
       d_pts_xyz.upload(pxyz, s); d_pts_view.upload(pview, s);
       d_ann_view.upload(h_ann_view, s); d_ann_off.upload(h_ann_off, s);
-      d_pts_scratch.alloc((size_t)A * (2 + 2 * NCL + 2 * nb), stream);
+      d_pts_scratch.alloc((size_t)A * (2 + 2 * NCL + 2 * nb + 2), stream);
       d_pts_raw.alloc((size_t)A * 32, stream);
     }
     d_ann_idx.upload(h_ann_idx, s);
@@ -629,10 +639,11 @@ struct BaSolver : BaSolverBase {
     }
     if (kDisp) {
       d_recd.alloc((size_t)std::max(M, 1) * 6, s); d_dpart.alloc((size_t)V * 9, s); d_Wdh.alloc((size_t)std::max(P, 1) * 12, s);
-      d_Cw.alloc((size_t)V * NCL * nb, s);
     }
+    if (!kDisp && nf > 0) d_Cw.alloc((size_t)std::max(ncpl, 1) * NCL * nb, s);  // working copy of the coupling strips of one linear solve
+    d_hinv.alloc(std::max(nf, 1), s);
     // work buffers
-    d_scale_cam.alloc((size_t)V * NCL, stream); d_scale_b.alloc(kMaxBorder, stream);
+    d_scale_cam.alloc((size_t)V * NCL, stream); d_scale_b.alloc(std::max(nbt, 1), stream);
     d_rec.alloc((size_t)std::max(M, 1) * D::RS, stream);
     {
       // k_resjac runs persistent CTAs, one resident wave, each over a contiguous run of chunks (<= kResjacMaxPer of them)
@@ -651,25 +662,29 @@ struct BaSolver : BaSolverBase {
       ow_grid = std::max(1, cdiv(ds.nchunks, ow_per));
     }
     d_part.alloc((size_t)std::max(ds.nchunks, 1) * D::NPART, stream);
-    viewred_n = (size_t)V * NCL * NCL + (size_t)V * NCL + V + (size_t)ncpl * NCL * nb + (size_t)nb * nb + nb + 2;
+    viewred_n = (size_t)V * NCL * NCL + (size_t)V * NCL + V + (size_t)ncpl * NCL * nb + (size_t)nb * nb + nbt + 2 + (size_t)nf * (NCL + nb + 1);
     d_viewred.alloc(viewred_n, stream);
     d_viewred.zero(s);
     p_U = d_viewred.p; p_g = p_U + (size_t)V * NCL * NCL; p_cost_view = p_g + (size_t)V * NCL; p_C = p_cost_view + V;
-    p_Hbb = p_C + (size_t)ncpl * NCL * nb; p_gb = p_Hbb + (size_t)nb * nb; p_cost_pts = p_gb + nb;
-    d_gabs.alloc((size_t)V * NCL + kMaxBorder, stream);
+    p_Hbb = p_C + (size_t)ncpl * NCL * nb; p_gb = p_Hbb + (size_t)nb * nb; p_cost_pts = p_gb + nbt;
+    p_Cf = p_cost_pts + 2; p_Hrf = p_Cf + (size_t)nf * NCL; p_Hff = p_Hrf + (size_t)nf * nb;
+    d_gabs.alloc((size_t)V * NCL + std::max(nbt, 1), stream);
     d_gabs.zero(s);
     p_gabs = d_gabs.p; p_gabs_b = d_gabs.p + (size_t)V * NCL;
     d_Vh.alloc((size_t)std::max(P, 1) * 10, stream);
     nblk_ray = std::max(cdiv(P, 128), 1); nblk_cam = std::max(cdiv(V, 128), 1);
     d_gmax_part.alloc(nblk_ray, stream); d_gmax_part.zero(s);
-    d_diag_ray.alloc(3 * (size_t)std::max(P, 1), stream); d_diag_cam.alloc((size_t)V * NCL, stream); d_diag_b.alloc(kMaxBorder, stream);
+    d_diag_ray.alloc(3 * (size_t)std::max(P, 1), stream); d_diag_cam.alloc((size_t)V * NCL, stream); d_diag_b.alloc(std::max(nbt, 1), stream);
     d_Lt.alloc((size_t)std::max(P, 1) * 10, stream);
     d_What.alloc((size_t)std::max(M, 1) * D::WS, stream); d_What.zero(s);
     d_q.alloc((size_t)std::max(ds.nchunks, 1) * (D::NU + NCL), stream);  // chunk partials of sum What What^T, sum q
-    sys_n = (size_t)ds.nnzb * NCL * NCL + n;
+    // d_sys (all-reduced once per linear solve): Sval | rhs(n) | Sbb(nb^2) | PTZRayDistDisp: the working strips Cw (they carry
+    // rank-local Schur terms of the rays)
+    sys_n = (size_t)ds.nnzb * NCL * NCL + n + (size_t)nb * nb + (kDisp ? (size_t)ncpl * NCL * nb : 0);
     d_sys.alloc(sys_n, stream);
-    p_Sval = d_sys.p; p_rhs = p_Sval + (size_t)ds.nnzb * NCL * NCL;
-    d_Linv.alloc((size_t)V * NCL * NCL, stream); d_Linv_b.alloc(kMaxBorder * kMaxBorder, stream); d_Sbb.alloc(kMaxBorder * kMaxBorder, stream);
+    p_Sval = d_sys.p; p_rhs = p_Sval + (size_t)ds.nnzb * NCL * NCL; p_Sbb = p_rhs + n;
+    p_Cw = kDisp ? p_Sbb + (size_t)nb * nb : d_Cw.p;
+    d_Linv.alloc((size_t)V * NCL * NCL, stream); d_Linv_b.alloc(kMaxBorder * kMaxBorder, stream);
     d_Cs.alloc((size_t)std::max(ncpl, 1) * NCL * std::max(nb, 1), stream);
     {
       // deflated CG (camera-only reduced systems of some size; PTZ_CG_DEFLATE=0 switches it off for A/B measurements)
@@ -745,20 +760,27 @@ struct BaSolver : BaSolverBase {
       PTZ_TIMED(PTZ_K_TRACK_ACCUM, k_track_accum<<<nblk_ray, 128, 0, s>>>(P, D::RS, ds.t_off.p, ds.t_obs.p, d_rec.p, d_trk[cur].p, d_Vh.p, d_gmax_part.p));
     if (A > 0) {
       PtsArgs a;
-      a.A = A; a.nav = nav; a.nb = nb; a.fy_in_border = kFyBorder ? 1 : 0;
-      a.bo_tlw = bo_tlw; a.bo_fy = bo_fy; a.bo_disp = bo_disp; a.ann_strip = d_ann_strip.p; a.disp = d_dispp[cur].p;
+      a.A = A; a.nav = nav; a.nb = nb; a.nf = nf;
+      a.bo_tlw = bo_tlw; a.bo_disp = bo_disp; a.ann_strip = d_ann_strip.p; a.disp = d_dispp[cur].p;
       a.uv = d_pts_uv.p; a.xyz = d_pts_xyz.p; a.view = d_pts_view.p; a.ann_view = d_ann_view.p; a.ann_off = d_ann_off.p;
       a.vt = d_vt.p; a.tlw = d_tlw[cur].p; a.scale_cam = d_scale_cam.p; a.scale_b = d_scale_b.p; a.scratch = d_pts_scratch.p;
       a.raw = weighted ? nullptr : d_pts_raw.p;
       a.U = p_U; a.g = p_g; a.gabs = p_gabs; a.C = p_C; a.Hbb = p_Hbb; a.gb = p_gb; a.cost_pts = p_cost_pts; a.gabs_b = p_gabs_b;
-      PTZ_TIMED(PTZ_K_PTS, k_pts<TYPE><<<1, 128, 0, s>>>(a));
+      a.Cf = p_Cf; a.Hrf = p_Hrf; a.Hff = p_Hff;
+      // sharded problem: the annotated points belong to rank 0 and reach the others through the all-reduce below
+      if (g_nccl.rank == 0) PTZ_TIMED(PTZ_K_PTS, k_pts<TYPE><<<1, 128, 0, s>>>(a));
     }
     if (kDisp) {
       k_disp_view<NCL><<<cdiv(V, 64), 64, 0, s>>>(V, ds.view_off.p, d_rec.p, d_recd.p, nb, bo_disp, p_C, d_dpart.p);
       k_disp_total<<<1, 32, 0, s>>>(V, d_dpart.p, nb, bo_disp, d_scale_b.p, p_Hbb, p_gb, p_gabs_b);
     }
     PTZ_CUDA(cudaGetLastError());
-    if (g_nccl.world > 1) PTZ_TIMED(PTZ_K_ALLREDUCE, allreduce_sum(d_viewred.p, viewred_n, s));
+    if (g_nccl.world > 1) {
+      PTZ_TIMED(PTZ_K_ALLREDUCE, allreduce_sum(d_viewred.p, viewred_n, s));
+      // |g/s| was formed from rank-local sums: redo it from the reduced gradient
+      k_grad_abs<<<cdiv(V * NCL + nbt, 256), 256, 0, s>>>(V * NCL, p_g, d_scale_cam.p, p_gabs, nbt, p_gb, d_scale_b.p, p_gabs_b);
+      PTZ_CUDA(cudaGetLastError());
+    }
   }
 
   void fill_ones(double* p, size_t count) {
@@ -771,11 +793,11 @@ struct BaSolver : BaSolverBase {
   void evaluate_jacobian(bool first) {
     if (first) {
       fill_ones(d_scale_cam.p, (size_t)V * NCL);
-      fill_ones(d_scale_b.p, kMaxBorder);
+      fill_ones(d_scale_b.p, std::max(nbt, 1));
       if (opt.jacobi_scaling) {
         launch_resjac(1);
         k_make_scales<NCL><<<cdiv(std::max(V * NCL, P), 256), 256, 0, stream>>>(V, P, p_U, d_Vh.p, d_scale_cam.p, d_trk[0].p, d_trk[1].p);
-        if (nb > 0) k_border_scales<<<1, 32, 0, stream>>>(nb, p_Hbb, d_scale_b.p);
+        if (nbt > 0) k_border_scales<<<cdiv(nbt, 128), 128, 0, stream>>>(nb, nf, p_Hbb, p_Hff, d_scale_b.p);
       }
     }
     launch_resjac(1);
@@ -789,7 +811,7 @@ struct BaSolver : BaSolverBase {
     add_sum(p_cost_pts + 1, A > 0 ? 1 : 0, 1, S_RAWPTS_X);
     add_max(p_gabs, V * NCL, S_GMAX_CAM);
     add_max(d_gmax_part.p, P > 0 ? nblk_ray : 0, S_GMAX_RAY);
-    add_max(p_gabs_b, nb, S_GMAX_B);
+    add_max(p_gabs_b, nbt, S_GMAX_B);
     PTZ_TIMED(PTZ_K_SCALARS, k_scalars<<<J.nsum + J.nmax, 1024, 0, stream>>>(J, d_scalars.p));
     PTZ_CUDA(cudaGetLastError());
     allreduce_max(d_scalars.p + S_GMAX_RAY, S_MAX_END - S_GMAX_RAY, stream);
@@ -849,21 +871,30 @@ struct BaSolver : BaSolverBase {
     if (ds.nub > 0)
       PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, k_schur_offdiag<NCL><<<cdiv(ds.nub, 8), 256, 0, s>>>(ds.nub, ds.pair_off.p, ds.pair_a.p, ds.pair_b.p, d_What.p,
                                                                                             ds.ub_pos.p, ds.ub_pos_t.p, p_Sval));
-    if (nb > 0) k_border_system<<<1, 128, 0, s>>>(nb, p_Hbb, p_gb, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_b.p, d_Sbb.p, p_rhs + (size_t)V * NCL);
+    if (nb > 0)
+      k_border_system<<<1, 128, 0, s>>>(nb, nf, p_Hbb, p_Hrf, p_Hff, p_gb, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, own, d_diag_b.p, d_hinv.p,
+                                        p_Sbb, p_rhs + (size_t)V * NCL);
     if (kDisp) {
-      k_disp_schur_view<NCL><<<cdiv(V, 64), 64, 0, s>>>(V, ds.view_off.p, ds.o_track.p, d_What.p, d_Wdh.p, nb, bo_disp, p_C, d_Cw.p);
-      k_disp_schur_border<<<1, 32, 0, s>>>(P, ds.t_off.p, d_Wdh.p, nb, bo_disp, d_Sbb.p, p_rhs + (size_t)V * NCL);
+      k_disp_schur_view<NCL><<<cdiv(V, 64), 64, 0, s>>>(V, ds.view_off.p, ds.o_track.p, d_What.p, d_Wdh.p, nb, bo_disp, own, p_C, p_Cw);
+      k_disp_schur_border<<<1, 32, 0, s>>>(P, ds.t_off.p, d_Wdh.p, nb, bo_disp, p_Sbb, p_rhs + (size_t)V * NCL);
     }
     PTZ_CUDA(cudaGetLastError());
-    if (g_nccl.world > 1) PTZ_TIMED(PTZ_K_ALLREDUCE, allreduce_sum(d_sys.p, sys_n, s));
+    if (g_nccl.world > 1) {
+      PTZ_TIMED(PTZ_K_ALLREDUCE, allreduce_sum(d_sys.p, sys_n, s));
+    }
+    if (nf > 0) {  // fy elimination, camera side (replicated: after the reduce)
+      k_fy_eliminate<NCL><<<cdiv(nf, 64), 64, 0, s>>>(nf, nb, d_ann_view.p, d_ann_strip.p, p_Cf, p_Hrf, p_gb + nb, d_hinv.p, kDisp ? p_Cw : p_C, p_Cw,
+                                                     ds.diag_pos.p, p_Sval, p_rhs);
+      PTZ_CUDA(cudaGetLastError());
+    }
     PTZ_TIMED(PTZ_K_PRECOND, {
       k_precond<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, ds.diag_pos.p, p_Sval, d_Linv.p, d_fail.p, defl_enabled ? d_Lfac.p : nullptr);
-      if (nb > 0) k_precond_border<<<1, 32, 0, s>>>(nb, d_Sbb.p, d_Linv_b.p, d_fail.p);
+      if (nb > 0) k_precond_border<<<1, 32, 0, s>>>(nb, p_Sbb, d_Linv_b.p, d_fail.p);
       k_scale_system<NCL><<<cdiv(std::max(ds.nnzb, V), 128), 128, 0, s>>>(V, ds.nnzb, ds.blk_row.p, ds.s_col.p, d_Linv.p, p_Sval, p_rhs, arena_ptr(ar_st0),
                                                                             arena_ptr(ar_x), d_cgp.p, d_cg_owner.p,
-                                                                            (g_nccl.world > 1) ? cgR : -1);
+                                                                            rows_sharded && g_nccl.world > 1 ? cgR : -1);
       if (nb > 0)
-        k_scale_border<NCL><<<1, 128, 0, s>>>(V, nb, ncpl, d_cpl_view.p, d_Linv.p, d_Linv_b.p, kDisp ? d_Cw.p : p_C, d_Cs.p, p_rhs, arena_ptr(ar_st0), arena_ptr(ar_x),
+        k_scale_border<NCL><<<1, 128, 0, s>>>(V, nb, ncpl, d_cpl_view.p, d_Linv.p, d_Linv_b.p, (kDisp || nf > 0) ? p_Cw : p_C, d_Cs.p, p_rhs, arena_ptr(ar_st0), arena_ptr(ar_x),
                                               d_cgp.p);
     });
     // ---- stages 3 and 4
@@ -908,14 +939,15 @@ struct BaSolver : BaSolverBase {
     cudaStream_t s = stream;
     const int ncam = V * NCL;
     const size_t nk = (size_t)ncam * kDeflK;
-    const int mr = (g_nccl.world > 1) ? cgR : -1;
+    const int mr = (rows_sharded && g_nccl.world > 1) ? cgR : -1;
     CgArgs a;
     a.V = V; a.nb = nb; a.n = n;
     a.rowptr = ds.s_rowptr.p; a.col = d_cg_col.p; a.Sval = p_Sval; a.peer_mask = d_cg_mask.p;
     a.nav = ncpl; a.ann_view = d_cpl_view.p; a.ann_idx = d_cpl_idx.p; a.C = d_Cs.p; a.order = d_cg_order.p;
     for (int k = 0; k < kMaxPeers; ++k) a.arena[k] = g_arena.base[k];
+    if (!rows_sharded && cg_vranks == 1) a.arena[0] = g_arena.base[cgR];  // the single-rank kernel works in arena[0]: this rank's own block
     a.off_partial = ar_partial; a.off_st0 = ar_st0; a.off_st1 = ar_st1; a.off_x = ar_x; a.off_ll0 = ar_ll0; a.off_ll1 = ar_ll1;
-    a.W = cgW; a.rank = cgR; a.vranks = cg_vranks; a.slots_per_rank = cg_slots_per_rank; a.p = d_cgp.p;
+    a.W = cgW; a.rank = rows_sharded ? cgR : 0; a.vranks = cg_vranks; a.slots_per_rank = cg_slots_per_rank; a.p = d_cgp.p;
     a.max_iter = opt.pcg_max_iterations; a.tol = opt.pcg_rel_tolerance;
     a.out_info = d_pcg_info.p; a.out_res = d_pcg_res.p;
     // shared-memory residency of S: every warp keeps up to cg_cap blocks (+ column indices) of its rows for the whole solve
@@ -967,7 +999,7 @@ struct BaSolver : BaSolverBase {
     const int kd = lowest_ritz_vectors(h_abg.data(), m, kDeflK, kDeflK, Y);
     if (kd < 4) return;
     d_Y.upload(Y.data(), (size_t)m * kDeflK, s);
-    const int mr = (g_nccl.world > 1) ? cgR : -1;
+    const int mr = (rows_sharded && g_nccl.world > 1) ? cgR : -1;
     k_defl_harvest<<<cdiv(ncam * kDeflK, 256), 256, 0, s>>>(ncam, m, kd, d_hist.p, d_Y.p, d_Wt.p, d_cg_owner.p, NCL, mr);
     allreduce_sum(d_Wt.p, (size_t)ncam * kDeflK, s);
     k_defl_scale_basis<NCL><<<cdiv(V * kDeflK, 256), 256, 0, s>>>(V, d_Linv.p, d_Wt.p, d_Wy.p);
@@ -990,7 +1022,7 @@ struct BaSolver : BaSolverBase {
     PTZ_TIMED(PTZ_K_CAM_UPDATE, k_cam_update<TYPE><<<nblk_cam, 128, 0, s>>>(V, y, d_scale_cam.p, p_g, d_diag_cam.p, mu, ds.view_active.p, d_intr[cur].p,
                                                                             d_ext[cur].p, d_intr[nxt].p, d_ext[nxt].p, d_part3_cam.p));
     if (nb > 0)
-      k_border_update<<<1, 32, 0, s>>>(nb, nav, bo_tlw, bo_fy, bo_disp, d_ann_view.p, y + (size_t)V * NCL, d_scale_b.p, p_gb, d_diag_b.p, mu, d_tlw[cur].p,
+      k_border_update<NCL><<<1, 32, 0, s>>>(nb, nf, bo_tlw, bo_disp, d_ann_view.p, y, V * NCL, d_scale_b.p, p_gb, d_diag_b.p, mu, p_Cf, p_Hrf, d_hinv.p, d_tlw[cur].p,
                                        d_tlw[nxt].p, d_intr[cur].p, d_intr[nxt].p, d_dispp[cur].p, d_dispp[nxt].p, d_part3_b.p);
     launch_cost(nxt);
     launch_step_scalars();
@@ -1226,7 +1258,7 @@ struct BaSolver : BaSolverBase {
     const int dd = kDisp ? 3 : 0;
     const int wo = ncv + 3 + dd, wp = ncv + 6 + dd;
     fill_ones(d_scale_cam.p, (size_t)V * NCL);
-    fill_ones(d_scale_b.p, kMaxBorder);
+    fill_ones(d_scale_b.p, std::max(nbt, 1));
     if (kDisp && disp) { PTZ_CUDA(cudaMemcpyAsync(d_dispp[cur].p, disp, 24, cudaMemcpyHostToDevice, stream)); PTZ_CUDA(cudaStreamSynchronize(stream)); }
     // pass 1: unweighted, unscaled records
     launch_resjac(0);
@@ -1275,11 +1307,11 @@ struct BaSolver : BaSolverBase {
     }
     // pass 2: weighted (still unscaled) -> cost and gradient
     launch_resjac(1);
-    std::vector<double> g((size_t)V * NCL), Vh((size_t)std::max(P, 1) * 10), gb(std::max(nb, 1)), cv(V), cp(2, 0.0);
+    std::vector<double> g((size_t)V * NCL), Vh((size_t)std::max(P, 1) * 10), gb(std::max(nbt, 1)), cv(V), cp(2, 0.0);
     PTZ_CUDA(cudaMemcpyAsync(g.data(), p_g, g.size() * 8, cudaMemcpyDeviceToHost, stream));
     PTZ_CUDA(cudaMemcpyAsync(cv.data(), p_cost_view, cv.size() * 8, cudaMemcpyDeviceToHost, stream));
     if (P > 0) d_Vh.download(Vh.data(), (size_t)P * 10, stream);
-    if (nb > 0) PTZ_CUDA(cudaMemcpyAsync(gb.data(), p_gb, nb * 8, cudaMemcpyDeviceToHost, stream));
+    if (nbt > 0) PTZ_CUDA(cudaMemcpyAsync(gb.data(), p_gb, nbt * 8, cudaMemcpyDeviceToHost, stream));
     if (A > 0) PTZ_CUDA(cudaMemcpyAsync(cp.data(), p_cost_pts, 16, cudaMemcpyDeviceToHost, stream));
     PTZ_CUDA(cudaStreamSynchronize(stream));
     double cost = cp[0];
@@ -1295,11 +1327,12 @@ struct BaSolver : BaSolverBase {
       for (int j = 0; j < dd; ++j) out->gradient[(size_t)V * ncv + 3 * (size_t)P + j] = gb[bo_disp + j];
       if (A > 0) {
         for (int j = 0; j < 6; ++j) out->gradient[(size_t)V * ncv + 3 * (size_t)P + dd + j] = gb[bo_tlw + j];
-        if (kFyBorder) for (int k = 0; k < nav; ++k) out->gradient[(size_t)h_ann_view[k] * ncv + 1] = gb[bo_fy + k];
+        for (int k = 0; k < nf; ++k) out->gradient[(size_t)h_ann_view[k] * ncv + 1] = gb[nb + k];
       }
     }
   }
 
+  void set_stage_timing(bool on) override { clk.per_kernel = on; }
   void stage_times(ptzba_stage_times* t) override {
     for (int i = 0; i < PTZ_K_COUNT; ++i) { t->ms_kernel[i] = clk.ms[i]; t->launches[i] = clk.launches[i]; }
     t->ms_run = clk.ms_run;
@@ -1430,6 +1463,12 @@ int ptzba_get_stage_times(ptzba_handle* h, ptzba_stage_times* t) {
   return PTZ_OK;
 }
 
+int ptzba_set_stage_timing(ptzba_handle* h, int per_kernel) {
+  if (!h || !h->s) return PTZ_ERR_INVALID;
+  h->s->set_stage_timing(per_kernel != 0);
+  return PTZ_OK;
+}
+
 int ptzba_destroy(ptzba_handle* h) {
   delete h;
   return PTZ_OK;
@@ -1444,6 +1483,7 @@ int ptzba_solve(const ptzba_problem* prob, const ptz_solver_options* opt, ptzba_
   const auto t0 = now();
   int rc = ptzba_create(prob, opt, &h);
   if (rc != PTZ_OK) return rc;
+  if (!getenv("PTZ_STAGE_TIMES")) h->s->set_stage_timing(false);  // nobody can read the per-kernel times of a one-shot solve
   const auto t1 = now();
   rc = ptzba_run(h, opt->max_num_iterations + 1, out);
   const auto t2 = now();

@@ -9,7 +9,7 @@ _LIB = None
 
 EXPORTS = [
     "ptz_solver_options_default", "ptz_last_error", "ptz_device_count", "ptz_measure_fp64_gflops",
-    "ptzba_solve", "ptzba_eval", "ptzba_create", "ptzba_reset", "ptzba_run", "ptzba_get_stage_times", "ptzba_destroy",
+    "ptzba_solve", "ptzba_eval", "ptzba_create", "ptzba_reset", "ptzba_run", "ptzba_get_stage_times", "ptzba_set_stage_timing", "ptzba_destroy",
     "ptz_nccl_unique_id", "ptz_nccl_init", "ptz_nccl_finalize",
     "ptzreloc_solve_batch", "ptzreloc_eval", "ptzreloc_solve_batch_dev", "ptzreloc_reproj_error", "ptzreloc_local_params",
     "ptztracks_build", "ptztracks_build_dev", "ptztracks_flatten",

@@ -143,8 +143,9 @@ class BAProblem:
         return BAProblem(
             factor_type=self.factor_type, intr=self.intr, ext=self.ext, obs_uv=self.obs_uv[sel], obs_view=self.obs_view[sel],
             obs_track=self.obs_track[sel] - lo, track_weight=self.track_weight[lo:hi], ray0=None if self.ray0 is None else self.ray0[lo:hi],
-            pt_uv=self.pt_uv if rank == 0 else None, pt_xyz=self.pt_xyz if rank == 0 else None, pt_view=self.pt_view if rank == 0 else None,
-            tlw0=self.tlw0, gt=self.gt)
+            # the annotated 2d-3d points are NOT sharded: every rank passes all of them (the library evaluates them on rank 0 and the
+            # all-reduce of the camera blocks carries them to the others)
+            pt_uv=self.pt_uv, pt_xyz=self.pt_xyz, pt_view=self.pt_view, tlw0=self.tlw0, gt=self.gt)
 
 
 @dataclass

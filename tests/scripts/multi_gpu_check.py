@@ -20,8 +20,12 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for t, cfg, scale in ((abi.PTZ_BA_PTZRAY, 1, 0.5), (abi.PTZ_BA_PTZRAY_DIST, 2, 0.3), (abi.PTZ_BA_PTZRAY, 4, 0.1)):
-        full = synth.make_config(cfg, scale=scale, factor_type=t)
+    cases = [(abi.PTZ_BA_PTZRAY, 1, 0.5, {}), (abi.PTZ_BA_PTZRAY_DIST, 2, 0.3, {}), (abi.PTZ_BA_PTZRAY, 4, 0.1, {}),
+             # georeferencing on a sharded problem: 2d-3d terms on rank 0, inside the all-reduce; every view annotated
+             (abi.PTZ_BA_PTZRAY, 1, 0.5, dict(num_pts3d=54, pts3d_views=18)), (abi.PTZ_BA_PTZRAY_DIST, 4, 0.1, dict(num_pts3d=40, pts3d_views=8)),
+             (abi.PTZ_BA_PTZRAY_DIST_DISP, 0, 1.0, dict(num_pts3d=12))]
+    for t, cfg, scale, kw in cases:
+        full = synth.make_distdisp_scene(**kw) if cfg == 0 else synth.make_config(cfg, scale=scale, factor_type=t, **kw)
         single = ptz.ba_solve(full, max_num_iterations=100)  # before the communicator exists: plain single-GPU solve
         ptz.nccl_init_from_torch()
         shard = full.shard_tracks(rank, world)
@@ -31,12 +35,17 @@ def main():
                 and abs(got.final_cost - single.final_cost) <= 1e-9 * single.final_cost and got.num_residuals == single.num_residuals
                 and np.abs(got.intr - single.intr).max() <= 1e-6 and np.abs(got.ext - single.ext).max() <= 1e-8
                 and abs(got.final_reproj_error_2d2d - single.final_reproj_error_2d2d) <= 1e-9)
+        if full.A > 0:
+            good = (good and np.abs(got.tlw - single.tlw).max() <= 1e-8 and np.abs(got.cams_world - single.cams_world).max() <= 1e-7
+                    and abs(got.final_reproj_error_2d3d - single.final_reproj_error_2d3d) <= 1e-9)
+        if t == abi.PTZ_BA_PTZRAY_DIST_DISP:
+            good = good and np.abs(got.disp - single.disp).max() <= 1e-6 * max(1.0, np.abs(single.disp).max())
         # rays stay on their owner rank: compare this rank's slice
         counts = np.bincount(full.obs_track, minlength=full.P)
         cum = np.cumsum(counts)
         lo = np.searchsorted(cum, cum[-1] * rank / world, side="left") if rank > 0 else 0
         good = good and np.abs(got.ray - single.ray[lo : lo + shard.P]).max() <= 1e-8
-        print(f"[rank {rank}] cfg{cfg} type{t}: V={full.V} M={full.M} shard M={shard.M} iters {got.num_iterations}/{single.num_iterations} "
+        print(f"[rank {rank}] cfg{cfg} type{t} A={full.A}: V={full.V} M={full.M} shard M={shard.M} iters {got.num_iterations}/{single.num_iterations} "
               f"cost {got.final_cost:.10e}/{single.final_cost:.10e} -> {'OK' if good else 'MISMATCH'}", flush=True)
         ok = ok and good
     # reloc: contiguous shards, no collective

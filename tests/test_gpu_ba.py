@@ -284,6 +284,26 @@ def test_full_cfg1_georef_matches_oracle(orc):
     assert np.abs(got.tlw - want.tlw).max() <= 1e-5 and np.abs(got.cams_world - want.cams_world).max() <= 1e-4
 
 
+@pytest.mark.parametrize("cfg,scale,t", [(1, 1.0, abi.PTZ_BA_PTZRAY), (4, 0.12, abi.PTZ_BA_PTZRAY), (2, 1.0, abi.PTZ_BA_PTZRAY_DIST)])
+def test_georef_with_every_view_annotated(orc, cfg, scale, t):
+    """RunGeoreferencing annotates whatever images the annotation file lists (run_ptz_ba.cc:131-145) -- possibly all of them.  The fy
+    of an annotated view is driven by its 2d-3d terms alone; it is eliminated like a ray before the CG, so the number of
+    annotated views is unbounded: 36, 60 and 120 annotated views here, four points each, against the oracle."""
+    V = {1: 36, 2: 60, 4: 120}[cfg]
+    p = synth.make_config(cfg, scale=scale, factor_type=t, num_pts3d=4 * V, pts3d_views=V)
+    assert p.V == V and len(set(p.pt_view.tolist())) == V
+    got = ptz.ba_solve(p, max_num_iterations=200)
+    rc, want = orc.ba_solve(p, max_num_iterations=200, num_threads=orc.num_threads())
+    assert rc == 0
+    check_solve(orc, p, got, want, f"georef-all-{cfg}")
+    assert abs(got.final_reproj_error_2d3d - want.final_reproj_error_2d3d) <= 1e-6 * want.final_reproj_error_2d3d
+    assert np.abs(got.tlw - want.tlw).max() <= 1e-5
+    assert np.abs(got.intr[:, 1] - want.intr[:, 1]).max() <= 1e-4
+    assert np.abs(got.cams_world - want.cams_world).max() <= 1e-4
+    e, w = ptz.ba_eval(p), orc.ba_eval(p)
+    assert np.abs(e.gradient - w.gradient).max() <= 1e-9 * np.abs(w.gradient).max()
+
+
 @pytest.mark.parametrize("scale", [0.25, 1.0])
 def test_cfg4_iterations_match_sparse_oracle(orc, scale):
     """BASELINE cfg 4 (V=1000, 2e6 observations) at a quarter and at FULL size: the first LM iterations against the oracle's

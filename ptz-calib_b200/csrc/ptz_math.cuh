@@ -28,10 +28,11 @@ struct ViewTab {
   double Jl[9];     // left Jacobian of SO(3) at rvec, row-major: d(R n)/dw_k = (Jl e_k) x (R n)
   double fx, fy, cx, cy;
   double k1, k2, k3, p1, p2;  // hand-written factors read dist as (k1,k2,k3,p1,p2): ptzray_optimizer.cc:108-109
-  double pad[5];
+  double sc[6];     // Jacobi scales of the view's live camera columns (k_resjac takes the whole table in ONE bulk copy)
+  double pad[7];
 };
-constexpr int kViewTabDoubles = 32;
-static_assert(sizeof(ViewTab) == kViewTabDoubles * 8, "ViewTab is 32 doubles");
+constexpr int kViewTabDoubles = 40;
+static_assert(sizeof(ViewTab) == kViewTabDoubles * 8 && sizeof(ViewTab) % 16 == 0, "ViewTab is 40 doubles");
 
 // R(w) = I + a[w]x + b[w]x^2 and its derivatives.  a = sin t/t, b = (1-cos t)/t^2; da = a'(t)/t, db = b'(t)/t.
 // Series below t^2 = 1e-2 (truncation < 3e-18), closed forms above.  Same function as cv::Rodrigues; OpenCV
@@ -110,7 +111,8 @@ PTZ_HD void make_view_tab(const double intr[9], const double ext[6], ViewTab* vt
   (void)with_jac;
   vt->fx = intr[0]; vt->fy = intr[1]; vt->cx = intr[2]; vt->cy = intr[3];
   vt->k1 = intr[4]; vt->k2 = intr[5]; vt->k3 = intr[6]; vt->p1 = intr[7]; vt->p2 = intr[8];
-  for (int i = 0; i < 5; ++i) vt->pad[i] = 0.0;
+  for (int i = 0; i < 6; ++i) vt->sc[i] = 1.0;
+  for (int i = 0; i < 7; ++i) vt->pad[i] = 0.0;
 }
 
 // Brown model of the hand-written factors and its 2x2 Jacobian

@@ -266,7 +266,8 @@ int ptzreloc_solve_batch_dev(const ptzreloc_batch* dev_batch, const ptz_solver_o
  * On the device: radix sort + unique of the (image, feature) nodes, lock-free union-find over the matches, one more sort
  * by component, scans.  Integer work, results identical to the reference's as SETS; the reference's track ids are the
  * union-by-rank roots of its sequential UnionFind (union_find.h:66-92), which only order the tracks — here a track's id is
- * canonical: the flat index of its smallest (image, feature) node, and tracks come in ascending id.
+ * canonical: the flat index of its smallest (image, feature) node, and tracks come in ascending id.  ptztracks_reference_ids
+ * (below) turns them into the reference's ids and order; the C++ adaptor does so by default.
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct ptztracks_matches {
   int32_t num_pairs;            /* matches_info.size() (struct MatchesInfo, types.h:24-35) */
@@ -296,6 +297,12 @@ int ptztracks_build(const ptztracks_matches* matches, ptztracks_result* out);
 /* all pointers (of both structs) are DEVICE pointers; counts come back in the struct (bench.py's kernel-only timing).
  * Scratch memory is cached per stream: pass a stream you created (with the legacy default stream, NULL, every call pays cudaMalloc). */
 int ptztracks_build_dev(const ptztracks_matches* dev_matches, int64_t num_matches, ptztracks_result* dev_out, void* cuda_stream);
+
+/* Reference-id mode: relabels the tracks of ptztracks_build with the ids the reference's sequential union-by-rank forest gives them
+ * (union_find.h:66-92 replayed over the matches in order, on the host) and re-sorts them in ascending id, i.e. into the iteration
+ * order of the reference's Tracks map.  After this call track ids, track order and therefore Ray::id_ and the order of the residual
+ * blocks are the reference's, not only the tracks as sets.  Host code: O(N log N) for N matches, no device needed. */
+int ptztracks_reference_ids(const ptztracks_matches* matches, ptztracks_result* tracks);
 
 /* tracks -> observation rows of ptzba_problem, as the loop at ptzray_optimizer.cc:801-848 adds residual blocks: tracks in
  * ascending id, inside a track ascending image id, candidate views only (isCandidate, :554-560); a track without any

@@ -296,6 +296,8 @@ class PTZRayOptimizer {
     if (shared_ic_ids.size() != cameras_.size()) return;  // .cc:499-502
     shared_ic_ids_ = shared_ic_ids;
   }
+  // false: keep the device's canonical track ids (skips the host pass over the matches; the tracks are the same sets)
+  void SetReferenceTrackIds(bool on) { reference_track_ids_ = on; }
   void SetInitTransLocalToWorld(const double tlw[6]) { tlw_param_.assign(tlw, tlw + 6); tlw_given_ = true; }  // see the header comment
   // .cc:562-633: T_l_w from EPnP on the first annotated candidate view that passes the gates; zeros and false when none does
   bool SetInitTransLocalToWorld() {
@@ -370,7 +372,8 @@ class PTZRayOptimizer {
     return true;
   }
   // .cc:537-552: TracksBuilder::Build / Filter(4) / ExportToSTL, on the device (ptztracks_build); the class above stays as the
-  // host-side mirror of the reference's TracksBuilder API.  Track ids are canonical (smallest node), see ptzcalib_b200.h.
+  // host-side mirror of the reference's TracksBuilder API.  By default the device's canonical ids (smallest node) are turned into
+  // the reference's union-by-rank root ids, so tracks(), Ray::id_ and the order of the residual blocks are the reference's.
   bool FindTracks() {
     std::vector<int32_t> src, dst, q, t;
     std::vector<int64_t> off(1, 0);
@@ -388,6 +391,10 @@ class PTZRayOptimizer {
     tr.track_id = flat_id_.data(); tr.track_offset = flat_off_.data(); tr.elem_img = flat_img_.data(); tr.elem_feat = flat_feat_.data();
     last_status_ = ptztracks_build(&mm, &tr);
     if (last_status_ != PTZ_OK) return false;
+    if (reference_track_ids_) {  // ids and order of the reference's sequential UnionFind (host pass over the matches)
+      last_status_ = ptztracks_reference_ids(&mm, &tr);
+      if (last_status_ != PTZ_OK) return false;
+    }
     flat_id_.resize(tr.num_tracks); flat_off_.resize((size_t)tr.num_tracks + 1); flat_img_.resize(tr.num_elems); flat_feat_.resize(tr.num_elems);
     tracks_.clear();
     for (int32_t k = 0; k < tr.num_tracks; ++k) {
@@ -408,7 +415,7 @@ class PTZRayOptimizer {
   std::vector<long> shared_ic_ids_;
   FACTOR_TYPE type_;
   std::vector<double> tlw_param_ = std::vector<double>(6, 0.0);
-  bool tlw_given_ = false;
+  bool tlw_given_ = false, reference_track_ids_ = true;
   Tracks tracks_;
   std::vector<int32_t> flat_id_, flat_img_, flat_feat_;  // tracks_ as ptztracks_result arrays
   std::vector<int64_t> flat_off_;

@@ -385,6 +385,64 @@ int ptztracks_build(const ptztracks_matches* m, ptztracks_result* out) {
   });
 }
 
+// Reference track ids.  The device build labels a track by the flat index of its smallest (image, feature) node; the reference's id
+// is the root its SEQUENTIAL union-by-rank forest ends up with (union_find.h:66-92: equal ranks keep the first argument's root,
+// i.e. the source node of the match), which depends on the order of the matches and cannot be formed in parallel.  It only orders
+// the tracks (std::map<int, Track>, tracks.h:32) and fills Ray::id_ (types.h:35), which nothing in the reference reads -- but a
+// drop-in should hand back the same numbers, so this host pass replays the unions in match order (one sort of the 2N nodes, then
+// near-linear time), relabels the tracks and re-sorts them by the reference id.  Plain host code: no device needed.
+int ptztracks_reference_ids(const ptztracks_matches* m, ptztracks_result* tr) {
+  if (!m || !tr || m->num_pairs < 0 || tr->num_tracks < 0) return PTZ_ERR_INVALID;
+  if (tr->num_tracks == 0) return PTZ_OK;
+  if (!m->pair_src || !m->pair_dst || !m->match_offset || !tr->track_id || !tr->track_offset || !tr->elem_img || !tr->elem_feat) return PTZ_ERR_INVALID;
+  const int64_t N = m->match_offset[m->num_pairs];
+  if (N > 0 && (!m->query_idx || !m->train_idx)) return PTZ_ERR_INVALID;
+  auto key = [](int img, int feat) { return ((uint64_t)(uint32_t)img << 32) | (uint32_t)feat; };
+  std::vector<uint64_t> nodes;
+  nodes.reserve(2 * (size_t)N);
+  for (int k = 0; k < m->num_pairs; ++k)
+    for (int64_t i = m->match_offset[k]; i < m->match_offset[k + 1]; ++i) {
+      nodes.push_back(key(m->pair_src[k], m->query_idx[i]));
+      nodes.push_back(key(m->pair_dst[k], m->train_idx[i]));
+    }
+  std::sort(nodes.begin(), nodes.end());
+  nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());  // flat index = position (flat_pair_map, tracks.cc:35-43)
+  auto index_of = [&](uint64_t kx) { return (int)(std::lower_bound(nodes.begin(), nodes.end(), kx) - nodes.begin()); };
+  std::vector<int> parent(nodes.size()), rank(nodes.size(), 0);
+  for (size_t i = 0; i < parent.size(); ++i) parent[i] = (int)i;
+  auto find = [&](int i) { while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; } return i; };
+  for (int k = 0; k < m->num_pairs; ++k)
+    for (int64_t i = m->match_offset[k]; i < m->match_offset[k + 1]; ++i) {
+      const int a = find(index_of(key(m->pair_src[k], m->query_idx[i]))), b = find(index_of(key(m->pair_dst[k], m->train_idx[i])));
+      if (a == b) continue;
+      if (rank[a] < rank[b]) parent[a] = b;
+      else { parent[b] = a; if (rank[a] == rank[b]) ++rank[a]; }
+    }
+  const int T = tr->num_tracks;
+  std::vector<int> ref(T), perm(T);
+  for (int t = 0; t < T; ++t) {
+    const int64_t o = tr->track_offset[t];
+    const uint64_t kx = key(tr->elem_img[o], tr->elem_feat[o]);
+    const int idx = index_of(kx);
+    if (idx >= (int)nodes.size() || nodes[idx] != kx) { ptz::set_last_error("track %d does not come from these matches", t); return PTZ_ERR_INVALID; }
+    ref[t] = find(idx);
+    perm[t] = t;
+  }
+  std::sort(perm.begin(), perm.end(), [&](int a, int b) { return ref[a] < ref[b]; });
+  const int64_t E = tr->track_offset[T];
+  std::vector<int32_t> img(tr->elem_img, tr->elem_img + E), feat(tr->elem_feat, tr->elem_feat + E);
+  std::vector<int64_t> off(tr->track_offset, tr->track_offset + T + 1);
+  int64_t pos = 0;
+  for (int q = 0; q < T; ++q) {
+    const int t = perm[q];
+    tr->track_id[q] = ref[t];
+    tr->track_offset[q] = pos;
+    for (int64_t i = off[t]; i < off[t + 1]; ++i, ++pos) { tr->elem_img[pos] = img[i]; tr->elem_feat[pos] = feat[i]; }
+  }
+  tr->track_offset[T] = pos;
+  return PTZ_OK;
+}
+
 int ptztracks_flatten(const ptztracks_result* tr, const ptztracks_views* v, ptztracks_obs* out) {
   if (!tr || !v || !out || tr->num_tracks < 0 || tr->num_elems < 0 || v->num_images < 0 || out->cap_rows < 0 || out->cap_obs < 0) return PTZ_ERR_INVALID;
   if (tr->num_tracks > 0 && (!tr->track_offset || !tr->elem_img || !tr->elem_feat || !v->is_candidate || !v->kp_offset || !v->kp_uv)) return PTZ_ERR_INVALID;

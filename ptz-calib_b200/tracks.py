@@ -153,12 +153,21 @@ def call_flatten(fn, tracks: Tracks, views: Views):
     return 0, Observations(rt[:R].copy(), w[:R].copy(), uv[:M].copy(), ov[:M].copy(), ot[:M].copy())
 
 
-def build_tracks(matches: Matches, min_track_length=4) -> Tracks:
-    """TracksBuilder::Build + Filter(min_track_length) + ExportToSTL on the GPU (FindTracks uses 4, ptzray_optimizer.cc:541)"""
+def reference_ids(matches: Matches, tracks: Tracks, min_track_length=4) -> Tracks:
+    """ptztracks_reference_ids: the tracks relabelled with, and sorted by, the reference's union-by-rank root ids (host pass)"""
+    t = Tracks(tracks.num_nodes, tracks.num_components, tracks.track_id.copy(), tracks.track_offset.copy(), tracks.elem_img.copy(), tracks.elem_feat.copy())
+    cm, ct = matches.to_c(min_track_length), t.to_c()
+    lib.check(lib.load().ptztracks_reference_ids(C.byref(cm), C.byref(ct)), "ptztracks_reference_ids")
+    return t
+
+
+def build_tracks(matches: Matches, min_track_length=4, reference_track_ids=False) -> Tracks:
+    """TracksBuilder::Build + Filter(min_track_length) + ExportToSTL on the GPU (FindTracks uses 4, ptzray_optimizer.cc:541).
+    reference_track_ids: ids and order of the reference's sequential UnionFind instead of the canonical smallest-node ids."""
     L = lib.load()
     rc, t = call_build(L.ptztracks_build, matches, min_track_length, "ptztracks_build")
     lib.check(rc, "ptztracks_build")
-    return t
+    return reference_ids(matches, t, min_track_length) if reference_track_ids else t
 
 
 def flatten_tracks(tracks: Tracks, views: Views) -> Observations:

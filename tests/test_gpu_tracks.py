@@ -10,7 +10,7 @@ import ptz_calib_b200 as ptz
 from ptz_calib_b200 import abi, lib, synth
 from ptz_calib_b200.tracks import Matches, Tracks, Views
 
-from test_tracks_oracle import random_match_graph
+from test_tracks_oracle import flip_every_other_pair, random_match_graph
 
 pytestmark = pytest.mark.gpu
 
@@ -42,6 +42,18 @@ def test_random_graphs_match_oracle(orc, seed, min_len):
     m = random_match_graph(100 + seed, num_images=20, feats=60, num_pairs=80, per_pair=10 + 10 * (seed % 3))
     got = ptz.build_tracks(m, min_len)
     assert_same(got, canonical(orc.tracks_build(m, min_len), m))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_reference_track_ids_equal_the_oracle_exactly(orc, seed):
+    """reference-id mode: ids, order and every array equal the restated TracksBuilder's WITHOUT any relabelling (the ids are the
+    union-by-rank roots of the sequential forest, union_find.h:66-92)"""
+    m = flip_every_other_pair(random_match_graph(seed, num_images=20, feats=80, num_pairs=90, per_pair=40))
+    for min_len in (2, 4):
+        assert_same(ptz.build_tracks(m, min_len, reference_track_ids=True), orc.tracks_build(m, min_len))
+    p = synth.make_config(1, scale=0.5)
+    m, v, _ = synth.make_matches_from_scene(p, n_collisions=7, n_short=9, extra_keypoints=3)
+    assert_same(ptz.build_tracks(m, 4, reference_track_ids=True), orc.tracks_build(m, 4))
 
 
 @pytest.mark.parametrize("cfg,scale", [(1, 1.0), (2, 0.5)])

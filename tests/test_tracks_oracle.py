@@ -10,7 +10,7 @@ from scipy.sparse.csgraph import connected_components
 
 import ptz_calib_b200 as ptz
 from ptz_calib_b200 import abi, lib, synth
-from ptz_calib_b200.tracks import Matches, Views
+from ptz_calib_b200.tracks import Matches, Tracks, Views
 
 
 def random_match_graph(seed, num_images=12, feats=40, num_pairs=30, per_pair=25):
@@ -153,3 +153,35 @@ def test_tracks_entry_points_need_a_gpu_and_validate_arguments():
         t = oracle.tracks_build(mm, 4)
         with pytest.raises(lib.PtzLibraryError, match="-5"):
             ptz.flatten_tracks(t, v)
+
+
+def flip_every_other_pair(m: Matches) -> Matches:
+    """every other pair stored the other way round (dst -> src), so that union-by-rank roots are not simply the smallest nodes"""
+    flip = np.arange(len(m.pair_src)) % 2 == 1
+    rows = np.repeat(flip, np.diff(m.match_offset))
+    return Matches(np.where(flip, m.pair_dst, m.pair_src), np.where(flip, m.pair_src, m.pair_dst), m.match_offset,
+                   np.where(rows, m.train_idx, m.query_idx), np.where(rows, m.query_idx, m.train_idx))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_reference_id_pass_restores_the_oracle_ids(orc, seed):
+    """CPU: ptztracks_reference_ids is host code.  The oracle's tracks, re-labelled canonically (smallest node) and re-sorted the way
+    the device build emits them, come back with the reference's ids and order."""
+    from ptz_calib_b200 import tracks as T
+
+    m = flip_every_other_pair(random_match_graph(seed, num_images=16, feats=60, num_pairs=70, per_pair=30))
+    want = orc.tracks_build(m, 2)
+    src = np.repeat(m.pair_src, np.diff(m.match_offset)).astype(np.int64)
+    dst = np.repeat(m.pair_dst, np.diff(m.match_offset)).astype(np.int64)
+    nodes = np.unique(np.concatenate([src << 32 | m.query_idx, dst << 32 | m.train_idx]))
+    first = want.track_offset[:-1]
+    ids = np.searchsorted(nodes, want.elem_img[first].astype(np.int64) << 32 | want.elem_feat[first]).astype(np.int32)
+    order = np.argsort(ids, kind="stable")
+    lens = np.diff(want.track_offset)
+    off = np.concatenate([[0], np.cumsum(lens[order])]).astype(np.int64)
+    gather = np.concatenate([np.arange(want.track_offset[k], want.track_offset[k + 1]) for k in order])
+    canon = Tracks(want.num_nodes, want.num_components, ids[order], off, want.elem_img[gather], want.elem_feat[gather])
+    assert not np.array_equal(canon.track_id, want.track_id)  # (the two labellings do differ)
+    got = T.reference_ids(m, canon, 2)
+    for name in ("track_id", "track_offset", "elem_img", "elem_feat"):
+        assert np.array_equal(getattr(got, name), getattr(want, name)), name

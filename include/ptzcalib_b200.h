@@ -102,7 +102,10 @@ typedef struct ptzba_problem {
   const double* pt_xyz;       /* [A*3]  annotated world point */
   const int32_t* pt_view;     /* [A] */
   const double* tlw0;         /* [6]    initial T_l_w (:562-633) or NULL = zeros */
-  const int32_t* shared_ic_id;/* [V]    SetSharedIntrinsics (:497-505); NULL = identity (the only mode built) */
+  const int32_t* shared_ic_id;/* [V]    SetSharedIntrinsics (:497-505): views with equal ids use ONE intrinsics block, that of the
+                                        first such view (:640-650); NULL = every view its own.  Groups of >= 2 views put
+                                        their 1-3 free intrinsics into the dense border of the reduced system: at most 16
+                                        such unknowns in total (minus 3 for PTZRayDistDisp); not together with 2d-3d points */
 } ptzba_problem;
 
 typedef struct ptzba_result {

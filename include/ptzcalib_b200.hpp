@@ -267,6 +267,11 @@ class PTZRayOptimizer {
     p.num_views = (int)view_of.size(); p.num_tracks = (int)track_ids.size(); p.num_obs = (int)oview.size(); p.num_pts3d = (int)pview.size();
     p.intr = intr.data(); p.ext = ext.data(); p.obs_uv = uv.data(); p.obs_view = oview.data(); p.obs_track = otrack.data(); p.track_weight = weight.data();
     p.pt_uv = puv.data(); p.pt_xyz = pxyz.data(); p.pt_view = pview.data(); p.tlw0 = tlw_param_.data();
+    std::vector<int32_t> shared;  // SetSharedIntrinsics: the ids of the candidate views, in their dense order
+    for (long id : view_of) shared.push_back((int32_t)shared_ic_ids_[id]);
+    bool identity = true;
+    for (size_t k = 0; k < view_of.size(); ++k) if (shared_ic_ids_[view_of[k]] != view_of[k]) identity = false;
+    if (!identity) p.shared_ic_id = shared.data();
     ptz_solver_options o;
     ptz_solver_options_default(&o);
     o.max_num_iterations = max_iter_;

@@ -41,6 +41,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -1074,10 +1075,24 @@ struct BaProblem : Problem {
   int off_ext, off_ray, off_disp, off_tlw;  // ambient offsets: intr V*9 | ext V*6 | ray P*3 | disp 3 | tlw 6
   int nci, ncv;
   bool use_disp, use_tlw;
+  // SetSharedIntrinsics (ptzray_optimizer.cc:497-505): views with the same shared_ic_id use ONE intrinsics block, the one of the
+  // first such view (SetUpInitialCameraParams :640-650 inserts the block at the first candidate of the id).  rep[v] = that view.
+  std::vector<int> rep;
   BaProblem(const ptzba_problem* pp) : p(pp) {
     type = p->factor_type; V = p->num_views; Pn = p->num_tracks; M = p->num_obs; A = p->num_pts3d;
     off_ext = V * 9; off_ray = off_ext + V * 6; off_disp = off_ray + Pn * 3; off_tlw = off_disp + 3;
-    num_ambient = off_tlw + 6;
+    num_ambient = off_tlw + 6 + 1;  // (+1: a scratch coordinate that tangent slots without a parameter point to)
+    rep.resize(V);
+    {
+      std::map<int, int> first;
+      for (int i = 0; i < V; ++i) {
+        const int id = p->shared_ic_id ? p->shared_ic_id[i] : i;
+        auto it = first.find(id);
+        if (it == first.end()) { first[id] = i; rep[i] = i; } else rep[i] = it->second;
+      }
+    }
+    std::vector<int> gsize(V, 0);
+    for (int i = 0; i < V; ++i) ++gsize[rep[i]];
     num_blocks = M + A;
     use_disp = (type == PTZ_BA_PTZRAY_DIST_DISP);
     use_tlw = A > 0;
@@ -1103,16 +1118,31 @@ struct BaProblem : Problem {
     ray_tan_end = t;
     if (use_disp) for (int j = 0; j < 3; ++j) { amb2tan[off_disp + j] = t++; amb_active[off_disp + j] = 1; }
     if (use_tlw) for (int j = 0; j < 6; ++j) { amb2tan[off_tlw + j] = t++; amb_active[off_tlw + j] = 1; }
+    // shared intrinsics blocks: their free coordinates (fx, fy, (k1)) sit behind everything else, in the border of the reduced
+    // system; the per-view slots of the representative keep their place in the camera block but point to no parameter (zero
+    // columns, zero step), those of the other members point to their own, unused, intrinsics
+    std::vector<int> orphan;
+    for (int i = 0; i < V; ++i) {
+      if (rep[i] != i || gsize[i] < 2) continue;
+      bool used = false;
+      for (int v = 0; v < V; ++v) if (rep[v] == i && view_used[v]) used = true;
+      const int idx[3] = {0, 1, 4};
+      for (int c = 0; c < nci; ++c) { orphan.push_back(amb2tan[i * 9 + idx[c]]); amb2tan[i * 9 + idx[c]] = t++; }
+      for (int j = 0; j < 9; ++j) amb_active[i * 9 + j] = used ? 1 : 0;
+    }
+    for (int i = 0; i < V; ++i)
+      if (rep[i] != i) for (int j = 0; j < 9; ++j) amb_active[i * 9 + j] = 0;  // not parameter blocks of the problem
     num_tangent = t;
-    tan2amb.assign(t, 0);
+    tan2amb.assign(t, num_ambient - 1);
     for (int i = 0; i < num_ambient; ++i) if (amb2tan[i] >= 0) tan2amb[amb2tan[i]] = i;
+    for (int o : orphan) tan2amb[o] = num_ambient - 1;
     cam_block = ncv; num_cam_blocks = V;
   }
   // functor argument order: 2d-2d: intr(9) [disp(3)] ext(6) ray(3); 2d-3d: intr(9) [disp(3)] ext(6) tlw(6)
   int block_params(int k, int* amb) const override {
     int n = 0;
     int view = k < M ? p->obs_view[k] : p->pt_view[k - M];
-    for (int j = 0; j < 9; ++j) amb[n++] = view * 9 + j;
+    for (int j = 0; j < 9; ++j) amb[n++] = rep[view] * 9 + j;  // intrinsics_param_.at(ic_id), :821-848
     if (use_disp) for (int j = 0; j < 3; ++j) amb[n++] = off_disp + j;
     for (int j = 0; j < 6; ++j) amb[n++] = off_ext + view * 6 + j;
     if (k < M) for (int j = 0; j < 3; ++j) amb[n++] = off_ray + p->obs_track[k] * 3 + j;
@@ -1182,7 +1212,7 @@ int ba_check(const ptzba_problem* p) {
     if (p->obs_view[k] < 0 || p->obs_view[k] >= p->num_views || p->obs_track[k] < 0 || p->obs_track[k] >= p->num_tracks) return PTZ_ERR_INVALID;
   for (int k = 0; k < p->num_pts3d; ++k)
     if (p->pt_view[k] < 0 || p->pt_view[k] >= p->num_views) return PTZ_ERR_INVALID;
-  if (p->shared_ic_id)
+  if (p->shared_ic_id && p->num_pts3d > 0)  // (not restated: shared blocks together with 2d-3d terms)
     for (int i = 0; i < p->num_views; ++i) if (p->shared_ic_id[i] != i) return PTZ_ERR_UNSUPPORTED;
   return PTZ_OK;
 }
@@ -1195,7 +1225,7 @@ void ba_world_outputs(const BaProblem& bp, const std::vector<double>& x, ptzba_r
   const double* d = &x[bp.off_disp];
   if (out->cams_world) {
     for (int i = 0; i < bp.V; ++i) {
-      const double* in = &x[i * 9];
+      const double* in = &x[bp.rep[i] * 9];  // intrinsics_param_.at(ic_id), :679-727
       const double* ex = &x[bp.off_ext + i * 6];
       double* c = out->cams_world + 21 * i;
       double fx = in[0];
@@ -1447,7 +1477,7 @@ int orc_ptzba_solve(const ptzba_problem* prob, const ptz_solver_options* opt, pt
   }
   out->final_reproj_error_2d2d = std::sqrt(s2 / bp.M);
   out->final_reproj_error_2d3d = std::sqrt(s3 / bp.A);
-  if (out->intr) std::memcpy(out->intr, &x[0], sizeof(double) * 9 * bp.V);
+  if (out->intr) for (int i = 0; i < bp.V; ++i) std::memcpy(out->intr + 9 * i, &x[bp.rep[i] * 9], sizeof(double) * 9);
   if (out->ext) std::memcpy(out->ext, &x[bp.off_ext], sizeof(double) * 6 * bp.V);
   if (out->ray) std::memcpy(out->ray, &x[bp.off_ray], sizeof(double) * 3 * bp.Pn);
   if (out->disp) std::memcpy(out->disp, &x[bp.off_disp], sizeof(double) * 3);

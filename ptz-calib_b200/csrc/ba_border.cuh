@@ -188,9 +188,11 @@ __global__ void k_pts_cost(int A, const float2* __restrict__ uv, const double* _
 }
 
 // Jacobi scaling of the border and fy columns at iteration 0
-__global__ void k_border_scales(int nb, int nf, const double* __restrict__ Hbb, const double* __restrict__ Hff, double* __restrict__ scale_b) {
+__global__ void k_border_scales(int nb, int nf, const double* __restrict__ Hbb, const double* __restrict__ Hff, double* __restrict__ scale_b,
+                                int nb_plain, const double* __restrict__ sh_h /* column norms^2 of the shared intrinsics unknowns */) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nb) scale_b[i] = 1.0 / (1.0 + sqrt(Hbb[i * nb + i]));
+  if (i < nb_plain) scale_b[i] = 1.0 / (1.0 + sqrt(Hbb[i * nb + i]));
+  else if (i < nb) scale_b[i] = 1.0 / (1.0 + sqrt(sh_h[i - nb_plain]));
   else if (i < nb + nf) scale_b[i] = 1.0 / (1.0 + sqrt(Hff[i - nb]));
 }
 // |g_j / s_j| of every camera, border and fy column from the (all-reduced) gradient: the sharded problem's replacement for the
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(128) k_border_system(int nb, int nf, const dou
                                                        const double* __restrict__ Hff, const double* __restrict__ gb, double mu, int refresh_diag,
                                                        double min_diag, double max_diag, int own /* sharded problem: rank 0 contributes, the others write zeros */,
                                                        double* __restrict__ diag_b, double* __restrict__ hinv, double* __restrict__ Sbb,
-                                                       double* __restrict__ rhs_b) {
+                                                       double* __restrict__ rhs_b, int nb_plain /* entries behind it: shared intrinsics, k_shared_border */) {
   for (int k = threadIdx.x; k < nf; k += blockDim.x) {
     double d;
     if (refresh_diag) { d = fmin(fmax(Hff[k], min_diag), max_diag); diag_b[nb + k] = d; }
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(128) k_border_system(int nb, int nf, const dou
   for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
     const int i = e / nb, j = e % nb;
     double s = Hbb[e];
+    if (i >= nb_plain || j >= nb_plain) { Sbb[e] = 0.0; if (i == j) rhs_b[i] = 0.0; continue; }
     if (i == j) {
       double d;
       if (refresh_diag) { d = fmin(fmax(Hbb[e], min_diag), max_diag); diag_b[i] = d; }
@@ -267,12 +270,14 @@ __global__ void __launch_bounds__(32) k_border_update(int nb, int nf, int bo_tlw
                                                       const double* __restrict__ diag_b, double mu, const double* __restrict__ Cf,
                                                       const double* __restrict__ Hrf, const double* __restrict__ hinv, const double* __restrict__ tlw,
                                                       double* __restrict__ tlw_c, const double* __restrict__ intr, double* __restrict__ intr_c,
-                                                      const double* __restrict__ disp, double* __restrict__ disp_c, double* __restrict__ part3) {
+                                                      const double* __restrict__ disp, double* __restrict__ disp_c, double* __restrict__ part3, int nb_plain) {
   const int lane = threadIdx.x;
   const double* yb = y + ncam;
   double dm = 0, st = 0, xn = 0;
   if (lane == 0) {
-    for (int j = 0; j < nb; ++j) dm += 0.5 * yb[j] * (gb[j] + diag_b[j] / mu * yb[j]);
+    for (int j = 0; j < nb_plain; ++j) dm += 0.5 * yb[j] * (gb[j] + diag_b[j] / mu * yb[j]);
+    // shared intrinsics unknowns: k_cam_update already summed 1/2 y g over the views of the group; the damping term is theirs once
+    for (int j = nb_plain; j < nb; ++j) dm += 0.5 * yb[j] * (diag_b[j] / mu * yb[j]);
     if (bo_tlw >= 0)
       for (int j = 0; j < 6; ++j) {
         const double c = tlw[j] + (-scale_b[bo_tlw + j] * yb[bo_tlw + j]);
@@ -303,6 +308,146 @@ __global__ void __launch_bounds__(32) k_border_update(int nb, int nf, int bo_tlw
   }
   dm = warp_sum(dm); st = warp_sum(st); xn = warp_sum(xn);
   if (lane == 0) { part3[0] = dm; part3[1] = st; part3[2] = xn; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SetSharedIntrinsics (ptzray_optimizer.cc:497-505; wiring :640-650, :821-848): the views of a group use ONE intrinsics block.
+// Everything up to the reduced camera system is formed per view as if the blocks were independent (records, U, g, What, S); the
+// constraint "the intrinsics columns of all views of group G are the same unknown" is then applied to the reduced system itself,
+// S' = T^T S T: the nI = NCL - 3 intrinsics unknowns of every group of two or more views move into the dense border
+//     border = [ tlw | disp | group 0: fx (k1) (fy) | group 1: ... ]
+// and the rows / columns they had in the camera blocks are deactivated (unit diagonal, zero right-hand side).  Exact: rays are
+// eliminated per observation, and T only adds camera columns.  Jacobi scale, LM diagonal and gradient of a shared column come from
+// the sums over the group (k_shared_grad); the step is copied back into the per-view slots (k_shared_expand), so the per-view
+// update kernels run unchanged and the views of a group stay bit-identical.
+// ---------------------------------------------------------------------------------------------------------------------
+// after every Jacobian evaluation (and all-reduce): gradient and squared column norm of each shared unknown j = (group, column)
+template <int NCL>
+__global__ void k_shared_grad(int ns, const int* __restrict__ grp_off, const int* __restrict__ grp_view, const double* __restrict__ U,
+                              const double* __restrict__ g, const double* __restrict__ scale_b, int bo_sh, double* __restrict__ gb,
+                              double* __restrict__ gabs_b, double* __restrict__ sh_h, double* __restrict__ gabs) {
+  constexpr int NI = NCL - 3;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ns) return;
+  const int grp = j / NI, c = j % NI;
+  double gs = 0, hs = 0;
+  for (int k = grp_off[grp]; k < grp_off[grp + 1]; ++k) {
+    const int v = grp_view[k];
+    gs += g[v * NCL + c];
+    hs += U[(size_t)v * NCL * NCL + c * NCL + c];
+    gabs[v * NCL + c] = 0.0;  // not a column of its own
+  }
+  gb[bo_sh + j] = gs;
+  gabs_b[bo_sh + j] = fabs(gs / scale_b[bo_sh + j]);
+  sh_h[j] = hs;
+}
+// iteration 0: every view of a group takes the group's Jacobi scale
+template <int NCL>
+__global__ void k_shared_scales(int V, const int* __restrict__ grp_of, const double* __restrict__ scale_b, int bo_sh, double* __restrict__ scale_cam) {
+  constexpr int NI = NCL - 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = i / NI, c = i % NI;
+  if (v >= V || grp_of[v] < 0) return;
+  scale_cam[v * NCL + c] = scale_b[bo_sh + grp_of[v] * NI + c];
+}
+// per linear solve, one thread per block row w of S: the shared columns of every block (w, v) are summed into the strip of row w
+// and zeroed; if w is itself in a group its intrinsics rows move to `rowpart` (summed over the group by k_shared_border) and are
+// deactivated.  Every entry of S is touched by the thread of its row only.
+template <int NCL>
+__global__ void k_shared_fold(int V, int nb, int nb_plain, const int* __restrict__ grp_of, const int* __restrict__ rowptr, const int* __restrict__ col,
+                              double* __restrict__ Sval, double* __restrict__ rhs, const double* __restrict__ Csrc /* strips so far, or nullptr */,
+                              double* __restrict__ Cw, double* __restrict__ rowpart /* [V][NI][nb + 1] */) {
+  constexpr int NI = NCL - 3, NB = NCL * NCL;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= V) return;
+  double strip[NCL][kMaxBorder];
+#pragma unroll
+  for (int a = 0; a < NCL; ++a)
+#pragma unroll
+    for (int j = 0; j < kMaxBorder; ++j) strip[a][j] = (Csrc != nullptr && j < nb_plain) ? Csrc[((size_t)w * NCL + a) * nb + j] : 0.0;
+  const int gw = grp_of[w];
+  for (int k = rowptr[w]; k < rowptr[w + 1]; ++k) {
+    const int v = col[k], gv = grp_of[v];
+    double* B = Sval + (size_t)k * NB;
+    if (gv >= 0) {
+#pragma unroll
+      for (int c = 0; c < NI; ++c) {
+        const int j = nb_plain + gv * NI + c;
+#pragma unroll
+        for (int a = 0; a < NCL; ++a) {
+#pragma unroll
+          for (int jj = 0; jj < kMaxBorder; ++jj)
+            if (jj == j) strip[a][jj] += B[a * NCL + c];
+          B[a * NCL + c] = (v == w && a == c) ? 1.0 : 0.0;
+        }
+      }
+    }
+    if (gw >= 0) {
+#pragma unroll
+      for (int a = 0; a < NI; ++a)
+#pragma unroll
+        for (int c = 0; c < NCL; ++c) B[a * NCL + c] = (v == w && a == c) ? 1.0 : 0.0;  // (its content went into strip[a][.] / the other rows' strips)
+    }
+  }
+  // NOTE: the intrinsics rows of a grouped w were zeroed above AFTER their shared columns were taken into strip[a][.]; their
+  // non-shared columns (the coupling to the rotation unknowns of the neighbours) are the transposes of what the neighbours' threads
+  // put into THEIR strips, so nothing is lost.
+  if (gw >= 0) {
+#pragma unroll
+    for (int a = 0; a < NI; ++a) {
+      double* rp = rowpart + ((size_t)w * NI + a) * (nb + 1);
+#pragma unroll
+      for (int j = 0; j < kMaxBorder; ++j)
+        if (j < nb) { rp[j] = strip[a][j]; strip[a][j] = 0.0; }
+      rp[nb] = rhs[w * NCL + a];
+      rhs[w * NCL + a] = 0.0;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NCL; ++a)
+#pragma unroll
+    for (int j = 0; j < kMaxBorder; ++j)
+      if (j < nb) Cw[((size_t)w * NCL + a) * nb + j] = strip[a][j];
+}
+// one thread per shared unknown (row of the border): sum its group's row parts in member order, add the LM diagonal
+template <int NCL>
+__global__ void k_shared_border(int ns, int nb, int nb_plain, const int* __restrict__ grp_off, const int* __restrict__ grp_view,
+                                const double* __restrict__ rowpart, const double* __restrict__ sh_h, double mu, int refresh_diag, double min_diag,
+                                double max_diag, double* __restrict__ diag_b, double* __restrict__ Sbb, double* __restrict__ rhs_b) {
+  constexpr int NI = NCL - 3;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ns) return;
+  const int grp = j / NI, a = j % NI, row = nb_plain + j;
+  double acc[kMaxBorder + 1];
+#pragma unroll
+  for (int q = 0; q <= kMaxBorder; ++q) acc[q] = 0.0;
+  for (int k = grp_off[grp]; k < grp_off[grp + 1]; ++k) {
+    const double* rp = rowpart + ((size_t)grp_view[k] * NI + a) * (nb + 1);
+#pragma unroll
+    for (int q = 0; q < kMaxBorder; ++q)
+      if (q < nb) acc[q] += rp[q];
+    acc[kMaxBorder] += rp[nb];
+  }
+  double d;
+  if (refresh_diag) { d = fmin(fmax(sh_h[j], min_diag), max_diag); diag_b[row] = d; }
+  else d = diag_b[row];
+#pragma unroll
+  for (int q = 0; q < kMaxBorder; ++q) {
+    if (q >= nb) continue;
+    const double val = acc[q] + (q == row ? d / mu : 0.0);
+    Sbb[row * nb + q] = val;
+    if (q < nb_plain) Sbb[q * nb + row] = val;
+  }
+  rhs_b[row] = acc[kMaxBorder];
+}
+// the solved step of every shared unknown back into the per-view slots of its group
+template <int NCL>
+__global__ void k_shared_expand(int V, const int* __restrict__ grp_of, int ncam, int bo_sh, double* __restrict__ y) {
+  constexpr int NI = NCL - 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = i / NI, c = i % NI;
+  if (v >= V || grp_of[v] < 0) return;
+  y[v * NCL + c] = y[ncam + bo_sh + grp_of[v] * NI + c];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

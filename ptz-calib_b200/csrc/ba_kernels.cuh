@@ -18,8 +18,8 @@ namespace ptz {
 namespace cg = cooperative_groups;
 
 constexpr int kChunk = 128;      // observations per CTA in the streaming passes; chunks never straddle a view
-constexpr int kMaxBorder = 9;    // dense border of the reduced system: tlw(6) + disp(3); one warp owns its row in the CG (the fy of
-                                 // annotated views are eliminated before the CG, ba_border.cuh)
+constexpr int kMaxBorder = 16;   // dense border of the reduced system: tlw(6) + disp(3) + shared intrinsics unknowns; one warp owns its
+                                 // row in the CG (the fy of annotated views are eliminated before the CG, ba_border.cuh)
 
 template <int NCL>
 struct Dims {
@@ -452,7 +452,8 @@ __global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, i
 template <int NCL>
 __global__ void k_schur_diag(int V, const int* __restrict__ view_chunk_off, const double* __restrict__ wpart, const double* __restrict__ U,
                              const double* __restrict__ g, double mu, int refresh_diag, double min_diag, double max_diag, int add_own,
-                             double* __restrict__ diag_cam, const int* __restrict__ diag_pos, double* __restrict__ Sval, double* __restrict__ rhs) {
+                             double* __restrict__ diag_cam, const int* __restrict__ diag_pos, double* __restrict__ Sval, double* __restrict__ rhs,
+                             const int* __restrict__ grp_of /* shared intrinsics: group of the view or -1; nullptr = none */) {
   typedef Dims<NCL> D;
   constexpr int NV = D::NU + NCL;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -475,7 +476,8 @@ __global__ void k_schur_diag(int V, const int* __restrict__ view_chunk_off, cons
       if (add_own) sacc += Uv[a * NCL + b];
       if (a == b) {
         double d;
-        if (refresh_diag) { d = fmin(fmax(Uv[a * NCL + a], min_diag), max_diag); diag_cam[v * NCL + a] = d; }
+        if (grp_of != nullptr && a < NCL - 3 && grp_of[v] >= 0) { d = 0.0; diag_cam[v * NCL + a] = 0.0; }  // damped once, in the border (k_shared_border)
+        else if (refresh_diag) { d = fmin(fmax(Uv[a * NCL + a], min_diag), max_diag); diag_cam[v * NCL + a] = d; }
         else d = diag_cam[v * NCL + a];
         if (add_own) sacc += d / mu;
       }
@@ -1604,7 +1606,8 @@ __host__ __device__ constexpr int live_col_slot(int a) {
 template <int TYPE>
 __global__ void k_cam_update(int V, const double* __restrict__ y, const double* __restrict__ scale_cam, const double* __restrict__ g,
                              const double* __restrict__ diag_cam, double mu, const int* __restrict__ view_active, const double* __restrict__ intr,
-                             const double* __restrict__ ext, double* __restrict__ intr_c, double* __restrict__ ext_c, double* __restrict__ part3) {
+                             const double* __restrict__ ext, double* __restrict__ intr_c, double* __restrict__ ext_c, double* __restrict__ part3,
+                             const int* __restrict__ intr_counted /* shared intrinsics: 0 = the block belongs to another view; nullptr = all own */) {
   constexpr int NCL = ba_ncl(TYPE);
   __shared__ double sred[3 * 8];
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1623,7 +1626,8 @@ __global__ void k_cam_update(int V, const double* __restrict__ y, const double* 
     for (int j = 0; j < 9; ++j) intr_c[9 * v + j] = c[j];
     for (int j = 0; j < 6; ++j) ext_c[6 * v + j] = c[9 + j];
     if (view_active[v]) {
-      for (int j = 0; j < 15; ++j) { acc[1] += (x[j] - c[j]) * (x[j] - c[j]); acc[2] += c[j] * c[j]; }
+      const int j0 = (intr_counted != nullptr && !intr_counted[v]) ? 9 : 0;  // a shared intrinsics block counts once, at its first view
+      for (int j = j0; j < 15; ++j) { acc[1] += (x[j] - c[j]) * (x[j] - c[j]); acc[2] += c[j] * c[j]; }
     }
   }
   block_sum<3>(acc, sred);
@@ -1716,12 +1720,14 @@ __global__ void __launch_bounds__(64) k_publish(const double* __restrict__ scala
 
 // |x|^2 of the current point over the coordinates that are in the Ceres problem: partial sums per CTA
 __global__ void k_xnorm2(int V, int P, const int* __restrict__ view_active, const double* __restrict__ intr, const double* __restrict__ ext,
-                         const int* __restrict__ t_off, const double* __restrict__ trk, double* __restrict__ part2) {
+                         const int* __restrict__ t_off, const double* __restrict__ trk, double* __restrict__ part2,
+                         const int* __restrict__ intr_counted) {
   __shared__ double sred[2 * 8];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[2] = {0, 0};
   if (i < V && view_active[i]) {
-    for (int j = 0; j < 9; ++j) acc[0] += intr[9 * i + j] * intr[9 * i + j];
+    if (intr_counted == nullptr || intr_counted[i])
+      for (int j = 0; j < 9; ++j) acc[0] += intr[9 * i + j] * intr[9 * i + j];
     for (int j = 0; j < 6; ++j) acc[0] += ext[6 * i + j] * ext[6 * i + j];
   }
   if (i < P && t_off[i + 1] > t_off[i]) {

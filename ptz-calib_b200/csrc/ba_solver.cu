@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <map>
 #include <chrono>
 #include <memory>
 
@@ -250,6 +251,11 @@ struct BaSolver : BaSolverBase {
   int nf = 0, nbt = 0;                 // fy unknowns of annotated views (eliminated before the CG, ba_border.cuh); nbt = nb + nf
   int bo_tlw = -1, bo_disp = -1;       // first border column of tlw(6) / disp(3)
   bool rows_sharded = false;           // the CG's rows are split across the ranks (camera-only systems); else every rank solves it all
+  // SetSharedIntrinsics: groups of >= 2 views with one intrinsics block (ba_border.cuh).  ns = G * (NCL - 3) unknowns in the border
+  int ngrp = 0, ns = 0, bo_sh = 0, nb_plain = 0;
+  std::vector<int> h_rep, h_grp_of, h_grp_off, h_grp_view, h_intr_counted;
+  DevBuf<int> d_grp_of, d_grp_off, d_grp_view, d_intr_counted;
+  DevBuf<double> d_sh_h, d_rowpart;
   int ncpl = 0;                               // views with a coupling strip to the border (annotated ones, or all of them with disp)
   std::vector<int> h_cpl_view, h_cpl_idx, h_ann_strip;
   ptz_solver_options opt;
@@ -403,10 +409,39 @@ struct BaSolver : BaSolverBase {
       if (kFyBorder) nf = nav;
     }
     if (kDisp) { bo_disp = nb; nb += 3; }
+    nb_plain = nb;
+    // shared intrinsics blocks (SetSharedIntrinsics): the block of an id is the one of its first view (ptzray_optimizer.cc:640-650)
+    h_rep.resize(V); h_grp_of.assign(V, -1); h_intr_counted.assign(V, 1);
+    {
+      std::map<int, int> first;
+      std::vector<int> gsize(V, 0);
+      for (int i = 0; i < V; ++i) {
+        const int id = prob->shared_ic_id ? prob->shared_ic_id[i] : i;
+        auto it = first.find(id);
+        if (it == first.end()) { first[id] = i; h_rep[i] = i; } else h_rep[i] = it->second;
+        ++gsize[h_rep[i]];
+      }
+      std::vector<int> gidx(V, -1);
+      for (int i = 0; i < V; ++i) if (h_rep[i] == i && gsize[i] >= 2) gidx[i] = ngrp++;
+      h_grp_off.assign(ngrp + 1, 0);
+      for (int i = 0; i < V; ++i) {
+        h_grp_of[i] = gidx[h_rep[i]];
+        if (h_grp_of[i] >= 0) { ++h_grp_off[h_grp_of[i] + 1]; if (h_rep[i] != i) h_intr_counted[i] = 0; }
+      }
+      for (int q = 0; q < ngrp; ++q) h_grp_off[q + 1] += h_grp_off[q];
+      h_grp_view.resize(h_grp_off[ngrp]);
+      std::vector<int> fill(h_grp_off.begin(), h_grp_off.end() - 1);
+      for (int i = 0; i < V; ++i) if (h_grp_of[i] >= 0) h_grp_view[fill[h_grp_of[i]]++] = i;
+    }
+    ns = ngrp * (NCL - 3);
+    if (ns > 0 && A > 0) throw CudaError(PTZ_ERR_UNSUPPORTED, "shared intrinsics together with 2d-3d terms");
+    bo_sh = nb; nb += ns;
+    if (nb > kMaxBorder)
+      throw CudaError(PTZ_ERR_UNSUPPORTED, "more shared intrinsics unknowns than the dense border holds (16 minus tlw / disp): too many groups");
     nbt = nb + nf;
     static_assert(kMaxBorder >= 9, "tlw(6) + disp(3)");
     h_ann_strip.resize(nav);
-    if (kDisp) {
+    if (kDisp || ns > 0) {
       ncpl = V;
       h_cpl_view.resize(V); std::iota(h_cpl_view.begin(), h_cpl_view.end(), 0);
       h_cpl_idx = h_cpl_view;
@@ -591,6 +626,7 @@ struct BaSolver : BaSolverBase {
     if (prob->tlw0) h_tlw0.assign(prob->tlw0, prob->tlw0 + 6);
     have_ray0 = prob->ray0 != nullptr;
     d_intr_init.upload(h_intr0, s); d_ext_init.upload(h_ext0, s); d_tlw_init.upload(h_tlw0, s);
+    if (ns > 0) { PTZ_CUDA(cudaStreamSynchronize(s)); for (int i = 0; i < V; ++i) for (int j = 0; j < 9; ++j) h_intr0[9 * (size_t)i + j] = prob->intr[9 * (size_t)h_rep[i] + j]; }
     // track records [ray(3), sqrt(weight), Jacobi scale(3), pad] are laid out on the device from the caller's arrays
     const size_t trk_n = (size_t)std::max(P, 1) * kTrk;
     d_trk_init.alloc(trk_n, s);
@@ -610,6 +646,14 @@ struct BaSolver : BaSolverBase {
       k_rikI<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr_init.p, d_ext_init.p, d_RiKi.p);
       k_init_rays<<<cdiv(P, 128), 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, ds.o_view.p, ds.o_uv.p, d_RiKi.p, d_trk_init.p);
       PTZ_CUDA(cudaGetLastError());
+    }
+    if (ns > 0) {
+      // (Pix2Ray above used every view's own K, as the reference does: :768-797 read cameras_.)  The solve starts from the block of
+      // the group's first view
+      d_intr_init.upload(h_intr0, s);
+      d_grp_of.upload(h_grp_of, s); d_grp_off.upload(h_grp_off, s); d_grp_view.upload(h_grp_view, s); d_intr_counted.upload(h_intr_counted, s);
+      d_sh_h.alloc(ns, s); d_sh_h.zero(s);
+      d_rowpart.alloc((size_t)V * (NCL - 3) * (nb + 1), s); d_rowpart.zero(s);
     }
     // annotated points
     if (A > 0) {
@@ -640,7 +684,7 @@ struct BaSolver : BaSolverBase {
     if (kDisp) {
       d_recd.alloc((size_t)std::max(M, 1) * 6, s); d_dpart.alloc((size_t)V * 9, s); d_Wdh.alloc((size_t)std::max(P, 1) * 12, s);
     }
-    if (!kDisp && nf > 0) d_Cw.alloc((size_t)std::max(ncpl, 1) * NCL * nb, s);  // working copy of the coupling strips of one linear solve
+    if (!kDisp && (nf > 0 || ns > 0)) d_Cw.alloc((size_t)std::max(ncpl, 1) * NCL * nb, s);  // working copy of the coupling strips of one linear solve
     d_hinv.alloc(std::max(nf, 1), s);
     // work buffers
     d_scale_cam.alloc((size_t)V * NCL, stream); d_scale_b.alloc(std::max(nbt, 1), stream);
@@ -783,6 +827,10 @@ struct BaSolver : BaSolverBase {
       k_grad_abs<<<cdiv(V * NCL + nbt, 256), 256, 0, s>>>(V * NCL, p_g, d_scale_cam.p, p_gabs, nbt, p_gb, d_scale_b.p, p_gabs_b);
       PTZ_CUDA(cudaGetLastError());
     }
+    if (ns > 0) {
+      k_shared_grad<NCL><<<cdiv(ns, 32), 32, 0, s>>>(ns, d_grp_off.p, d_grp_view.p, p_U, p_g, d_scale_b.p, bo_sh, p_gb, p_gabs_b, d_sh_h.p, p_gabs);
+      PTZ_CUDA(cudaGetLastError());
+    }
   }
 
   void fill_ones(double* p, size_t count) {
@@ -799,7 +847,8 @@ struct BaSolver : BaSolverBase {
       if (opt.jacobi_scaling) {
         launch_resjac(1);
         k_make_scales<NCL><<<cdiv(std::max(V * NCL, P), 256), 256, 0, stream>>>(V, P, p_U, d_Vh.p, d_scale_cam.p, d_trk[0].p, d_trk[1].p);
-        if (nbt > 0) k_border_scales<<<cdiv(nbt, 128), 128, 0, stream>>>(nb, nf, p_Hbb, p_Hff, d_scale_b.p);
+        if (nbt > 0) k_border_scales<<<cdiv(nbt, 128), 128, 0, stream>>>(nb, nf, p_Hbb, p_Hff, d_scale_b.p, nb_plain, d_sh_h.p);
+        if (ns > 0) k_shared_scales<NCL><<<cdiv(V * (NCL - 3), 128), 128, 0, stream>>>(V, d_grp_of.p, d_scale_b.p, bo_sh, d_scale_cam.p);
       }
     }
     launch_resjac(1);
@@ -869,13 +918,13 @@ struct BaSolver : BaSolverBase {
         if (kDisp) k_disp_track<NCL><<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_recA.p, d_recd.p, d_Lt.p, d_Wdh.p);
       });
     PTZ_TIMED(PTZ_K_SCHUR_DIAG, k_schur_diag<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, ds.view_chunk_off.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal,
-                                                                               opt.max_lm_diagonal, own, d_diag_cam.p, ds.diag_pos.p, p_Sval, p_rhs));
+                                                                               opt.max_lm_diagonal, own, d_diag_cam.p, ds.diag_pos.p, p_Sval, p_rhs, ns > 0 ? d_grp_of.p : nullptr));
     if (ds.nub > 0)
       PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, k_schur_offdiag<NCL><<<cdiv(ds.nub, 8), 256, 0, s>>>(ds.nub, ds.pair_off.p, ds.pair_a.p, ds.pair_b.p, d_What.p,
                                                                                             ds.ub_pos.p, ds.ub_pos_t.p, p_Sval));
     if (nb > 0)
       k_border_system<<<1, 128, 0, s>>>(nb, nf, p_Hbb, p_Hrf, p_Hff, p_gb, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, own, d_diag_b.p, d_hinv.p,
-                                        p_Sbb, p_rhs + (size_t)V * NCL);
+                                        p_Sbb, p_rhs + (size_t)V * NCL, nb_plain);
     if (kDisp) {
       k_disp_schur_view<NCL><<<cdiv(V, 64), 64, 0, s>>>(V, ds.view_off.p, ds.o_track.p, d_What.p, d_Wdh.p, nb, bo_disp, own, p_C, p_Cw);
       k_disp_schur_border<<<1, 32, 0, s>>>(P, ds.t_off.p, d_Wdh.p, nb, bo_disp, p_Sbb, p_rhs + (size_t)V * NCL);
@@ -889,6 +938,13 @@ struct BaSolver : BaSolverBase {
                                                      ds.diag_pos.p, p_Sval, p_rhs);
       PTZ_CUDA(cudaGetLastError());
     }
+    if (ns > 0) {  // shared intrinsics: fold their columns of S into the border (replicated: after the reduce)
+      k_shared_fold<NCL><<<cdiv(V, 64), 64, 0, s>>>(V, nb, nb_plain, d_grp_of.p, ds.s_rowptr.p, ds.s_col.p, p_Sval, p_rhs, kDisp ? p_Cw : nullptr, p_Cw,
+                                                    d_rowpart.p);
+      k_shared_border<NCL><<<cdiv(ns, 32), 32, 0, s>>>(ns, nb, nb_plain, d_grp_off.p, d_grp_view.p, d_rowpart.p, d_sh_h.p, mu, refresh, opt.min_lm_diagonal,
+                                                       opt.max_lm_diagonal, d_diag_b.p, p_Sbb, p_rhs + (size_t)V * NCL);
+      PTZ_CUDA(cudaGetLastError());
+    }
     PTZ_TIMED(PTZ_K_PRECOND, {
       k_precond<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, ds.diag_pos.p, p_Sval, d_Linv.p, d_fail.p, defl_enabled ? d_Lfac.p : nullptr);
       if (nb > 0) k_precond_border<<<1, 32, 0, s>>>(nb, p_Sbb, d_Linv_b.p, d_fail.p);
@@ -896,7 +952,7 @@ struct BaSolver : BaSolverBase {
                                                                             arena_ptr(ar_x), d_cgp.p, d_cg_owner.p,
                                                                             rows_sharded && g_nccl.world > 1 ? cgR : -1);
       if (nb > 0)
-        k_scale_border<NCL><<<1, 128, 0, s>>>(V, nb, ncpl, d_cpl_view.p, d_Linv.p, d_Linv_b.p, (kDisp || nf > 0) ? p_Cw : p_C, d_Cs.p, p_rhs, arena_ptr(ar_st0), arena_ptr(ar_x),
+        k_scale_border<NCL><<<1, 128, 0, s>>>(V, nb, ncpl, d_cpl_view.p, d_Linv.p, d_Linv_b.p, (kDisp || nf > 0 || ns > 0) ? p_Cw : p_C, d_Cs.p, p_rhs, arena_ptr(ar_st0), arena_ptr(ar_x),
                                               d_cgp.p);
     });
     // ---- stages 3 and 4
@@ -986,6 +1042,7 @@ struct BaSolver : BaSolverBase {
       }
       PTZ_CUDA(cudaLaunchCooperativeKernel(cg_kernel(deflate), dim3(cg_grid * cg_vranks), dim3(32 * cg_wpb), args, cg_smem, s));
       k_unscale<NCL><<<cdiv(V + nb, 128), 128, 0, s>>>(V, nb, d_Linv.p, d_Linv_b.p, arena_ptr(ar_x), d_y.p);
+      if (ns > 0) k_shared_expand<NCL><<<cdiv(V * (NCL - 3), 128), 128, 0, s>>>(V, d_grp_of.p, V * NCL, bo_sh, d_y.p);
     });
     PTZ_CUDA(cudaGetLastError());
   }
@@ -1022,10 +1079,10 @@ struct BaSolver : BaSolverBase {
                                                                                    mu, d_trk[cur].p, d_trk[nxt].p, d_part3_ray.p, kDisp ? d_Wdh.p : nullptr,
                                                                                    y + (size_t)V * NCL + (kDisp ? bo_disp : 0)));
     PTZ_TIMED(PTZ_K_CAM_UPDATE, k_cam_update<TYPE><<<nblk_cam, 128, 0, s>>>(V, y, d_scale_cam.p, p_g, d_diag_cam.p, mu, ds.view_active.p, d_intr[cur].p,
-                                                                            d_ext[cur].p, d_intr[nxt].p, d_ext[nxt].p, d_part3_cam.p));
+                                                                            d_ext[cur].p, d_intr[nxt].p, d_ext[nxt].p, d_part3_cam.p, ns > 0 ? d_intr_counted.p : nullptr));
     if (nb > 0)
       k_border_update<NCL><<<1, 32, 0, s>>>(nb, nf, bo_tlw, bo_disp, d_ann_view.p, y, V * NCL, d_scale_b.p, p_gb, d_diag_b.p, mu, p_Cf, p_Hrf, d_hinv.p, d_tlw[cur].p,
-                                       d_tlw[nxt].p, d_intr[cur].p, d_intr[nxt].p, d_dispp[cur].p, d_dispp[nxt].p, d_part3_b.p);
+                                       d_tlw[nxt].p, d_intr[cur].p, d_intr[nxt].p, d_dispp[cur].p, d_dispp[nxt].p, d_part3_b.p, nb_plain);
     launch_cost(nxt);
     launch_step_scalars();
   }
@@ -1067,7 +1124,7 @@ struct BaSolver : BaSolverBase {
     const int nblk = std::max(cdiv(std::max(V, P), 256), 1);
     DevBuf<double> part;
     part.alloc(2 * (size_t)nblk, stream);
-    k_xnorm2<<<nblk, 256, 0, stream>>>(V, P, ds.view_active.p, d_intr[cur].p, d_ext[cur].p, ds.t_off.p, d_trk[cur].p, part.p);
+    k_xnorm2<<<nblk, 256, 0, stream>>>(V, P, ds.view_active.p, d_intr[cur].p, d_ext[cur].p, ds.t_off.p, d_trk[cur].p, part.p, ns > 0 ? d_intr_counted.p : nullptr);
     ScalarJobs J;
     J.nsum = 2; J.nmax = 0;
     J.sum_ptr[0] = part.p; J.sum_n[0] = nblk; J.sum_stride[0] = 2; J.sum_slot[0] = S_XN2_CAM;
@@ -1256,6 +1313,7 @@ struct BaSolver : BaSolverBase {
 
   // ptzba_eval: raw residuals + analytic Jacobian in the caller's observation order, weighted cost and gradient
   void eval(const double* disp, ptzba_eval_out* out) override {
+    if (ns > 0) throw CudaError(PTZ_ERR_UNSUPPORTED, "ptzba_eval reports per-view columns: not defined with shared intrinsics");
     const int ncv = (TYPE == BA_PTZRAY) ? 5 : 6;
     const int dd = kDisp ? 3 : 0;
     const int wo = ncv + 3 + dd, wp = ncv + 6 + dd;
@@ -1363,9 +1421,6 @@ static int check_problem(const ptzba_problem* p) {
     if (p->obs_view[k] < 0 || p->obs_view[k] >= p->num_views || p->obs_track[k] < 0 || p->obs_track[k] >= p->num_tracks) return PTZ_ERR_INVALID;
   for (int k = 0; k < p->num_pts3d; ++k)
     if (p->pt_view[k] < 0 || p->pt_view[k] >= p->num_views) return PTZ_ERR_INVALID;
-  if (p->shared_ic_id)
-    for (int i = 0; i < p->num_views; ++i)
-      if (p->shared_ic_id[i] != i) { set_last_error("shared intrinsics (SetSharedIntrinsics) are not built"); return PTZ_ERR_UNSUPPORTED; }
   return PTZ_OK;
 }
 

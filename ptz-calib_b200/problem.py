@@ -54,6 +54,7 @@ class BAProblem:
     pt_xyz: Optional[np.ndarray] = None  # [A,3]
     pt_view: Optional[np.ndarray] = None  # [A]
     tlw0: Optional[np.ndarray] = None  # [6]
+    shared_ic_id: Optional[np.ndarray] = None  # [V] int32: SetSharedIntrinsics (views with equal ids share one intrinsics block)
     gt: dict = field(default_factory=dict)  # ground truth of a synthetic scene (not part of the ABI)
 
     def __post_init__(self):
@@ -113,7 +114,9 @@ class BAProblem:
         c.pt_xyz = as_ptr(self.pt_xyz, C.c_double)
         c.pt_view = as_ptr(self.pt_view, C.c_int32)
         c.tlw0 = as_ptr(self.tlw0, C.c_double)
-        c.shared_ic_id = as_ptr(None, C.c_int32)
+        if self.shared_ic_id is not None:
+            self.shared_ic_id = i32(self.shared_ic_id).reshape(-1)
+        c.shared_ic_id = as_ptr(self.shared_ic_id, C.c_int32)
         return c
 
     def with_params(self, intr=None, ext=None, ray=None, tlw=None):
@@ -145,7 +148,7 @@ class BAProblem:
             obs_track=self.obs_track[sel] - lo, track_weight=self.track_weight[lo:hi], ray0=None if self.ray0 is None else self.ray0[lo:hi],
             # the annotated 2d-3d points are NOT sharded: every rank passes all of them (the library evaluates them on rank 0 and the
             # all-reduce of the camera blocks carries them to the others)
-            pt_uv=self.pt_uv, pt_xyz=self.pt_xyz, pt_view=self.pt_view, tlw0=self.tlw0, gt=self.gt)
+            pt_uv=self.pt_uv, pt_xyz=self.pt_xyz, pt_view=self.pt_view, tlw0=self.tlw0, shared_ic_id=self.shared_ic_id, gt=self.gt)
 
 
 @dataclass

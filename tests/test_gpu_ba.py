@@ -304,6 +304,41 @@ def test_georef_with_every_view_annotated(orc, cfg, scale, t):
     assert np.abs(e.gradient - w.gradient).max() <= 1e-9 * np.abs(w.gradient).max()
 
 
+@pytest.mark.parametrize("t,groups", [(abi.PTZ_BA_PTZRAY, "all"), (abi.PTZ_BA_PTZRAY, "mixed"), (abi.PTZ_BA_PTZRAY_DIST, "all"), (abi.PTZ_BA_PTZRAY_DIST, "mixed"),
+                                      (abi.PTZ_BA_PTZRAY_FXFY_DIST, "all")])
+def test_shared_intrinsics_match_oracle(orc, t, groups):
+    """PTZRayOptimizer::SetSharedIntrinsics (ptzray_optimizer.cc:497-505, wiring :640-650, :821-848): views with one id share ONE
+    intrinsics block -- the one of the first view, fixed cx, cy, dist included.  A fixed-zoom scene (one true focal length); either
+    every view in one group, or three groups of different sizes next to views that keep their own block.  Same iteration table,
+    costs and parameters as the oracle, and the views of a group come out bit-identical."""
+    def scene():
+        if t == abi.PTZ_BA_PTZRAY:
+            return synth.make_config(1, scale=0.7, factor_type=t, focal_range=(1800.0, 1800.0001))
+        return synth.make_config(2, scale=0.4, factor_type=t, focal_range=(2500.0, 2500.0001))
+
+    p = scene()
+    V = p.V
+    if groups == "all":
+        ids = np.full(V, 7, np.int32)
+    else:
+        ids = np.arange(V, dtype=np.int32) + 100
+        ids[[2, 9, 17]] = 5            # three views far apart
+        ids[[3, 4]] = 3                # two neighbours
+        ids[10:16] = 42                # six in a row
+    p.shared_ic_id = ids
+    got = ptz.ba_solve(p, max_num_iterations=200)
+    rc, want = orc.ba_solve(p, max_num_iterations=200)
+    assert rc == 0 and want.termination == abi.PTZ_CONVERGENCE
+    check_solve(orc, p, got, want, f"shared-{t}-{groups}")
+    for g in set(ids.tolist()):
+        members = np.nonzero(ids == g)[0]
+        assert (got.intr[members] == got.intr[members[0]]).all()
+        assert np.array_equal(got.intr[members[0], 2:4], p.intr[members[0], 2:4])  # cx, cy of the group's first view
+    # the shared model really is a different problem from the independent one
+    free = ptz.ba_solve(scene(), max_num_iterations=200)
+    assert free.final_cost < got.final_cost and np.ptp(free.intr[:, 0]) > 1e-3
+
+
 @pytest.mark.parametrize("scale", [0.25, 1.0])
 def test_cfg4_iterations_match_sparse_oracle(orc, scale):
     """BASELINE cfg 4 (V=1000, 2e6 observations) at a quarter and at FULL size: the first LM iterations against the oracle's

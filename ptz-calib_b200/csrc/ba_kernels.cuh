@@ -446,9 +446,9 @@ __global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, i
   }
 }
 
-// per view (one thread): S_cc = [U + D^2] - sum_chunks(partial What What^T), rhs_c = [g] - sum_chunks(partial q), chunk order fixed.
-// The bracketed terms are added by the rank that owns the camera blocks (add_own); D^2 = clamp(diag U)/mu, refreshed after
-// accepted steps only.
+// per (view, value) one thread: S_cc = [U + D^2] - sum_chunks(partial What What^T), rhs_c = [g] - sum_chunks(partial q), chunk order
+// fixed.  The bracketed terms are added by the rank that owns the camera blocks (add_own); D^2 = clamp(diag U)/mu, refreshed after
+// accepted steps only.  (Round 1 ran one thread per VIEW, 14-27 dependent sums each: 31 us for 1000 views.)
 template <int NCL>
 __global__ void k_schur_diag(int V, const int* __restrict__ view_chunk_off, const double* __restrict__ wpart, const double* __restrict__ U,
                              const double* __restrict__ g, double mu, int refresh_diag, double min_diag, double max_diag, int add_own,
@@ -456,36 +456,38 @@ __global__ void k_schur_diag(int V, const int* __restrict__ view_chunk_off, cons
                              const int* __restrict__ grp_of /* shared intrinsics: group of the view or -1; nullptr = none */) {
   typedef Dims<NCL> D;
   constexpr int NV = D::NU + NCL;
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = idx / NV, e = idx % NV;
   if (v >= V) return;
-  double acc[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
-  for (int c = view_chunk_off[v]; c < view_chunk_off[v + 1]; ++c) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] += wpart[(size_t)c * NV + i];
+  double acc = 0.0;
+  const int c1 = view_chunk_off[v + 1];
+  int c = view_chunk_off[v];
+  for (; c + 4 <= c1; c += 4) {  // four loads in flight, summed in chunk order
+    const double a0 = wpart[(size_t)c * NV + e], a1 = wpart[(size_t)(c + 1) * NV + e], a2 = wpart[(size_t)(c + 2) * NV + e], a3 = wpart[(size_t)(c + 3) * NV + e];
+    acc += a0; acc += a1; acc += a2; acc += a3;
   }
+  for (; c < c1; ++c) acc += wpart[(size_t)c * NV + e];
+  if (e >= D::NU) {
+    const int a = e - D::NU;
+    rhs[v * NCL + a] = (add_own ? g[v * NCL + a] : 0.0) - acc;
+    return;
+  }
+  int a = 0, rem = e;
+  while (rem >= NCL - a) { rem -= NCL - a; ++a; }
+  const int b = a + rem;
   const double* Uv = U + (size_t)v * NCL * NCL;
   double* S = Sval + (size_t)diag_pos[v] * NCL * NCL;
-  int k = 0;
-#pragma unroll
-  for (int a = 0; a < NCL; ++a)
-#pragma unroll
-    for (int b = a; b < NCL; ++b) {
-      double sacc = -acc[k++];
-      if (add_own) sacc += Uv[a * NCL + b];
-      if (a == b) {
-        double d;
-        if (grp_of != nullptr && a < NCL - 3 && grp_of[v] >= 0) { d = 0.0; diag_cam[v * NCL + a] = 0.0; }  // damped once, in the border (k_shared_border)
-        else if (refresh_diag) { d = fmin(fmax(Uv[a * NCL + a], min_diag), max_diag); diag_cam[v * NCL + a] = d; }
-        else d = diag_cam[v * NCL + a];
-        if (add_own) sacc += d / mu;
-      }
-      S[a * NCL + b] = sacc;
-      S[b * NCL + a] = sacc;
-    }
-#pragma unroll
-  for (int a = 0; a < NCL; ++a) rhs[v * NCL + a] = (add_own ? g[v * NCL + a] : 0.0) - acc[D::NU + a];
+  double sacc = -acc;
+  if (add_own) sacc += Uv[a * NCL + b];
+  if (a == b) {
+    double d;
+    if (grp_of != nullptr && a < NCL - 3 && grp_of[v] >= 0) { d = 0.0; diag_cam[v * NCL + a] = 0.0; }  // damped once, in the border (k_shared_border)
+    else if (refresh_diag) { d = fmin(fmax(Uv[a * NCL + a], min_diag), max_diag); diag_cam[v * NCL + a] = d; }
+    else d = diag_cam[v * NCL + a];
+    if (add_own) sacc += d / mu;
+  }
+  S[a * NCL + b] = sacc;
+  S[b * NCL + a] = sacc;
 }
 
 // per upper off-diagonal block (one warp): S_rc = - sum over observation pairs What_o What_o'^T ; also writes S_cr = S_rc^T
@@ -1087,7 +1089,10 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
           // Every lane of a slot fetches ONE entry of the neighbour's (r, w, s) -- 3 loads, each 32-byte sector requested once --
           // forms its entry of r' and the NCL lanes of the slot exchange by shuffle.  Branch-free: lanes without a block read
           // their own row (valid memory) and discard; the raw loads of CH steps are issued before any is consumed.
-          constexpr int CH = 4;
+#ifndef PTZ_CG_CH
+#define PTZ_CG_CH 6
+#endif
+          constexpr int CH = PTZ_CG_CH;
           const int nsteps = (A.debug & 1) ? 0 : (nblk + SLOTS - 1) / SLOTS;
           const int lim = lact ? nblk : 0;
           const int base = ls * NCL;

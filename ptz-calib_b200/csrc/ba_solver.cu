@@ -275,6 +275,8 @@ struct BaSolver : BaSolverBase {
   // device: parameters (two copies: current / candidate)
   DevBuf<double> d_intr[2], d_ext[2], d_trk[2], d_tlw[2], d_intr_init, d_ext_init, d_trk_init, d_tlw_init;
   int cur = 0;
+  int vt_for = -1;         // parameter copy (0/1) the view table d_vt was built from, -1 = stale
+  bool vt_scaled = false;  // ... with the final Jacobi scales in it
   // device: work
   DevBuf<ViewTab> d_vt;
   DevBuf<double> d_scale_cam, d_scale_b, d_recA, d_recF, d_part, d_viewred, d_Vh, d_gmax_part, d_diag_ray, d_diag_cam, d_diag_b, d_Lt, d_What, d_q, d_sys, d_Linv,
@@ -777,6 +779,7 @@ struct BaSolver : BaSolverBase {
     }
     for (int i = 0; i < 2; ++i) PTZ_CUDA(cudaMemcpyAsync(d_trk[i].p, d_trk_init.p, d_trk_init.n * 8, cudaMemcpyDeviceToDevice, s));
     cur = 0;
+    vt_for = -1; vt_scaled = false;
     started = finished = false;
     iteration = 0; num_consecutive_invalid = 0; num_successful = num_unsuccessful = lin_iters_total = jac_evals = cost_evals = 0;
     radius = opt.initial_trust_region_radius; decrease_factor = 2.0; reuse_diagonal = false; last_successful = true;
@@ -793,7 +796,10 @@ struct BaSolver : BaSolverBase {
   // ---- stage 1 at the current point.  scale arrays must be valid (all ones on the very first pass).
   void launch_resjac(int weighted) {
     cudaStream_t s = stream;
-    PTZ_TIMED(PTZ_K_VIEW_PREP, k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[cur].p, d_ext[cur].p, d_vt.p, 1, d_scale_cam.p, NCL));
+    // (after an accepted step the table is already the one of the new point: the cost pass built it for the candidate)
+    if (vt_for != cur || !vt_scaled)
+      PTZ_TIMED(PTZ_K_VIEW_PREP, k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[cur].p, d_ext[cur].p, d_vt.p, 1, d_scale_cam.p, NCL));
+    vt_for = cur; vt_scaled = true;
     if (nb > 0) PTZ_CUDA(cudaMemsetAsync(p_C, 0, (viewred_n - (size_t)(p_C - d_viewred.p)) * sizeof(double), s));  // C | Hbb | gb | cost_pts accumulate
     if (ds.nchunks > 0)
       PTZ_TIMED(PTZ_K_RESJAC, k_resjac<TYPE><<<rj_grid, kChunk, ResjacSmem<NCL>::kBytes, s>>>(ds.nchunks, rj_per, ds.chunk_view.p, ds.chunk_begin.p, ds.chunk_cnt.p,
@@ -850,6 +856,7 @@ struct BaSolver : BaSolverBase {
         if (nbt > 0) k_border_scales<<<cdiv(nbt, 128), 128, 0, stream>>>(nb, nf, p_Hbb, p_Hff, d_scale_b.p, nb_plain, d_sh_h.p);
         if (ns > 0) k_shared_scales<NCL><<<cdiv(V * (NCL - 3), 128), 128, 0, stream>>>(V, d_grp_of.p, d_scale_b.p, bo_sh, d_scale_cam.p);
       }
+      vt_scaled = false;  // the table carries the scales: rebuild it with the final ones
     }
     launch_resjac(1);
     ++jac_evals;
@@ -917,7 +924,7 @@ struct BaSolver : BaSolverBase {
                                                                           d_What.p, d_q.p);
         if (kDisp) k_disp_track<NCL><<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_recA.p, d_recd.p, d_Lt.p, d_Wdh.p);
       });
-    PTZ_TIMED(PTZ_K_SCHUR_DIAG, k_schur_diag<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, ds.view_chunk_off.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal,
+    PTZ_TIMED(PTZ_K_SCHUR_DIAG, k_schur_diag<NCL><<<cdiv(V * (D::NU + NCL), 128), 128, 0, s>>>(V, ds.view_chunk_off.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal,
                                                                                opt.max_lm_diagonal, own, d_diag_cam.p, ds.diag_pos.p, p_Sval, p_rhs, ns > 0 ? d_grp_of.p : nullptr));
     if (ds.nub > 0)
       PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, k_schur_offdiag<NCL><<<cdiv(ds.nub, 8), 256, 0, s>>>(ds.nub, ds.pair_off.p, ds.pair_a.p, ds.pair_b.p, d_What.p,
@@ -1090,6 +1097,7 @@ struct BaSolver : BaSolverBase {
   void launch_cost(int which) {
     cudaStream_t s = stream;
     PTZ_TIMED(PTZ_K_VIEW_PREP, k_view_prep<<<cdiv(V, 128), 128, 0, s>>>(V, d_intr[which].p, d_ext[which].p, d_vt.p, 0, d_scale_cam.p, NCL));
+    vt_for = which;
     if (ds.nchunks > 0)
       PTZ_TIMED(PTZ_K_COST, k_cost<TYPE><<<ds.nchunks, kChunk, 0, s>>>(ds.chunk_view.p, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_uv.p, ds.o_track.p, d_vt.p,
                                                                          d_trk[which].p, d_dispp[which].p, d_cost_part.p));

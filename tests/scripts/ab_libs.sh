@@ -4,7 +4,7 @@ cd "$(dirname "$0")/../.."
 for so in ptz-calib_b200/csrc/ab/*.so; do
   cp "$so" ptz-calib_b200/csrc/libptzcalib_b200.so
   echo "== $so"
-  timeout 200 python bench.py --steps 40 --warmup 3 --no-e2e --no-cpu --no-tracks $AB_FLAGS 2>/dev/null | python -c "
+  timeout 200 python bench.py --steps 120 --warmup 3 --no-e2e --no-cpu --no-tracks $AB_FLAGS 2>/dev/null | python -c "
 import sys, json
 for line in sys.stdin:
     line=line.strip()

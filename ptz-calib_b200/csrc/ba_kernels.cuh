@@ -708,6 +708,215 @@ __global__ void k_unscale(int V, int nb, const double* __restrict__ Linv, const 
 }
 
 // -------------------------------------------------------------------------------------------------------------
+// stage 3 for SMALL reduced systems (n = V*NCL + nb <= kDenseMaxN: BASELINE cfg 1 / cfg 2, every BA of an IBA run): a dense
+// Cholesky factorisation in ONE CTA instead of the CG.  At this size the CG is pure latency -- ~100 iterations of a grid-wide
+// barrier each, 400 us per solve at V = 36 -- while the whole matrix fits the shared memory of one SM (n <= 160).  It is also
+// what SPARSE_SCHUR does in the reference: an exact factorisation of the reduced camera system (ptzray_optimizer.cc:471).
+//   k_dense_assemble: lower triangle of S (blocks, border strips, border block) and the right-hand side as row n of A[(n+1) x n]
+//   k_dense_chol    : the matrix is copied into shared memory once (odd row pitch: no bank conflicts) and factored there by a
+//                     blocked right-looking Cholesky, NB = 16: diagonal block factored by one warp in registers, panel rows (one
+//                     thread each, registers) X = A L^-T written in place, trailing update straight from the panel columns (a warp
+//                     = 4 rows, a lane = 4 columns: 8 LDS per 16 FMA).  A first version kept the matrix in global memory: the
+//                     read-modify-write latency of the trailing update made it 4x slower (161 us at n = 144, no gain at n = 300).  Carrying b as an extra ROW makes z = L^-1 b fall out of the panel
+//                     steps; L^T y = z is then solved block by block from the bottom.  Fixed order: bit-reproducible.
+// -------------------------------------------------------------------------------------------------------------
+constexpr int kDenseMaxN = 160;  // (n + 1) x (n | 1) doubles of shared memory: 207 KB at n = 160
+template <int NCL>
+__global__ void k_dense_assemble(int V, int nb, int nnzb, const int* __restrict__ blk_row, const int* __restrict__ col, const double* __restrict__ Sval,
+                                 const double* __restrict__ rhs, int ncpl, const int* __restrict__ cpl_view, const double* __restrict__ C,
+                                 const double* __restrict__ Sbb, double* __restrict__ A) {
+  const int n = V * NCL + nb, ld = n;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nnzb) {
+    const int r = blk_row[k], c = col[k];
+    if (c <= r) {
+      const double* B = Sval + (size_t)k * NCL * NCL;
+#pragma unroll
+      for (int i = 0; i < NCL; ++i)
+#pragma unroll
+        for (int j = 0; j < NCL; ++j) A[(size_t)(r * NCL + i) * ld + c * NCL + j] = B[i * NCL + j];
+    }
+    return;
+  }
+  int e = k - nnzb;
+  if (e < ncpl * NCL * nb) {  // border rows x camera columns: transposed strips
+    const int q = e / (NCL * nb), a = (e / nb) % NCL, j = e % nb;
+    A[(size_t)(V * NCL + j) * ld + cpl_view[q] * NCL + a] = C[e];
+    return;
+  }
+  e -= ncpl * NCL * nb;
+  if (e < nb * nb) { A[(size_t)(V * NCL + e / nb) * ld + V * NCL + e % nb] = Sbb[e]; return; }
+  e -= nb * nb;
+  if (e < n) A[(size_t)n * ld + e] = rhs[e];
+}
+#ifndef PTZ_DENSE_THREADS
+#define PTZ_DENSE_THREADS 256
+#endif
+constexpr int kDenseThreads = PTZ_DENSE_THREADS;
+constexpr int kDenseNB = 16, kDenseLd = kDenseNB + 1;  // block size: the serial chains (diagonal factor, row substitution) grow with NB^2
+__global__ void __launch_bounds__(kDenseThreads) k_dense_chol(int n, const double* __restrict__ Ag, double* __restrict__ y, int* __restrict__ info,
+                                                              int* __restrict__ fail) {
+  constexpr int NB = kDenseNB, LD = kDenseLd;
+  extern __shared__ double dsm_chol[];
+  const int ldp = n | 1;                        // odd pitch: the rows a warp reads side by side fall into different banks
+  double* Ld = dsm_chol;                        // [NB][LD] diagonal block (identity-padded)
+  double* red = Ld + NB * LD;                   // [<= 32 warps][NB]
+  double* yv = red + 32 * NB;                   // [n]
+  double* rdiag = yv + ((n + 3) & ~3);          // [n] 1 / L[i][i]: the substitutions multiply instead of paying a dependent divide per step
+  double* A = rdiag + ((n + 3) & ~3);           // [(n + 1)][ldp]: lower triangle of S, the right-hand side as row n
+  __shared__ int s_ok;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5, nw = blockDim.x >> 5;
+  if (t == 0) s_ok = 1;
+  for (int r = wid; r <= n; r += nw) {  // a row per warp, coalesced, four loads in flight
+    const double* src = Ag + (size_t)r * n;
+    double* dst = A + r * ldp;
+    int c = lane;
+    for (; c + 96 < n; c += 128) {
+      const double v0 = src[c], v1 = src[c + 32], v2 = src[c + 64], v3 = src[c + 96];
+      dst[c] = v0; dst[c + 32] = v1; dst[c + 64] = v2; dst[c + 96] = v3;
+    }
+    for (; c < n; c += 32) dst[c] = src[c];
+  }
+  __syncthreads();
+  for (int j0 = 0; j0 < n; j0 += NB) {
+    const int bs = min(NB, n - j0);
+    if (wid == 0) {
+      // the NB x NB block in registers, one row per lane (lanes >= NB idle); column c of L leaves by shuffles: no shared-memory
+      // round trips in the chain.  Constant loop bounds + predicates so that everything unrolls and a[] stays in registers.
+      const int row = lane < bs ? lane : -1;
+      double a[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) a[c] = (row >= 0 && c < bs) ? (c <= row ? A[(j0 + row) * ldp + j0 + c] : 0.0) : (lane == c ? 1.0 : 0.0);
+      bool ok = true;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        const double dcc = __shfl_sync(0xffffffffu, a[c], c);
+        const bool good = dcc > 0.0 && isfinite(dcc);  // (uniform)
+        ok = ok && good;
+        const double dinv = good ? rsqrt(dcc) : 1.0, d = good ? dcc * dinv : 1.0;
+        const double l = lane > c ? a[c] * dinv : (lane == c ? d : 0.0);
+        a[c] = l;
+        if (lane == c && c < bs) rdiag[j0 + c] = dinv;
+#pragma unroll
+        for (int cc = 0; cc < NB; ++cc) {
+          if (cc > c) {
+            const double lcc = __shfl_sync(0xffffffffu, l, cc);  // L[cc][c]
+            if (lane >= cc) a[cc] -= l * lcc;
+          }
+        }
+      }
+      if (!ok && lane == 0) s_ok = 0;
+      if (lane < NB) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+          Ld[lane * LD + c] = a[c];
+          if (lane < bs && c <= lane) A[(j0 + lane) * ldp + j0 + c] = a[c];
+        }
+      }
+    }
+    __syncthreads();
+    if (!s_ok) break;
+    // panel: rows below the block, the right-hand side row (row n) last: X = A L^-T in place, one thread per row
+    const int m = n - j0 - bs;
+    for (int pr = t; pr <= m; pr += blockDim.x) {
+      double* arow = A + (j0 + bs + pr) * ldp + j0;
+      double x[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) x[c] = c < bs ? arow[c] : 0.0;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        double s0 = x[c], s1 = 0.0;  // two chains
+#pragma unroll
+        for (int q = 0; q < NB; q += 2) {
+          if (q < c) s0 -= x[q] * Ld[c * LD + q];
+          if (q + 1 < c) s1 -= x[q + 1] * Ld[c * LD + q + 1];
+        }
+        x[c] = (s0 + s1) * (c < bs ? rdiag[j0 + c] : 1.0);
+      }
+#pragma unroll
+      for (int c = 0; c < NB; ++c) if (c < bs) arow[c] = x[c];
+    }
+    __syncthreads();
+    // trailing update: A[r][c] -= X_r . X_c for c <= r < m, and the right-hand side row (r == m) for all c < m.
+    // A warp = 4 rows, a lane = 4 columns (c0 + lane + 32 b): 8 LDS per 16 FMA
+    const double* X = A + (j0 + bs) * ldp + j0;  // panel: X[row * ldp + c], c < bs
+    double* T = A + (j0 + bs) * ldp + j0 + bs;   // trailing matrix
+    for (int r0 = wid * 4; r0 <= m; r0 += nw * 4) {
+      const int rmax = min(r0 + 3, m);
+      const int cend = rmax == m ? m : rmax + 1;  // columns [0, cend)
+      for (int c0 = 0; c0 < cend; c0 += 128) {
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        int pc[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) pc[b] = min(c0 + lane + 32 * b, m);  // (clamped lanes read a valid row and discard)
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+          if (c < bs) {
+            double pv[4], qv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) pv[a] = X[min(r0 + a, m) * ldp + c];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) qv[b] = X[pc[b] * ldp + c];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) acc[a][b] += pv[a] * qv[b];
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int r = r0 + a;
+          if (r > m) continue;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int c = c0 + lane + 32 * b;
+            if (c < m && (c <= r || r == m)) T[r * ldp + c] -= acc[a][b];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (!s_ok) {
+    for (int i = t; i < n; i += blockDim.x) y[i] = 0.0;
+    if (t == 0) { atomicExch(fail, 2); info[0] = 0; info[1] = 0; }
+    return;
+  }
+  // L^T y = z, z = row n of A; blocks from the bottom
+  const int last = ((n - 1) / NB) * NB;
+  for (int j0 = last; j0 >= 0; j0 -= NB) {
+    const int bs = min(NB, n - j0);
+    double part = 0.0;
+    if (lane < bs)
+      for (int i = j0 + bs + wid; i < n; i += nw) part += A[i * ldp + j0 + lane] * yv[i];
+    if (lane < NB) red[wid * NB + lane] = part;
+    __syncthreads();
+    if (wid == 0) {
+      double tc = 0.0;
+      if (lane < bs) {
+        tc = A[n * ldp + j0 + lane];
+        for (int w = 0; w < nw; ++w) tc -= red[w * NB + lane];
+      }
+#pragma unroll
+      for (int r = NB - 1; r >= 0; --r) {
+        if (r < bs) {
+          const double yr = __shfl_sync(0xffffffffu, tc, r) * rdiag[j0 + r];
+          if (lane == r) tc = yr;
+          else if (lane < r) tc -= A[(j0 + r) * ldp + j0 + lane] * yr;
+        }
+      }
+      if (lane < bs) { yv[j0 + lane] = tc; y[j0 + lane] = tc; }
+    }
+    __syncthreads();
+  }
+  if (t == 0) { info[0] = 1; info[1] = 0; }
+}
+
+// -------------------------------------------------------------------------------------------------------------
 // stage 3: conjugate gradients on the scaled reduced system, ONE cooperative launch per linear solve and ONE grid-wide
 // barrier per iteration.  Chronopoulos-Gear recurrences (single fused reduction of (r,r) and (S~r, r)):
 //     p = r + beta p ; s = w + beta s ; x += alpha p ; r' = r - alpha s ; w' = S~ r' ; gamma' = (r',r') ; delta = (w',r')

@@ -275,6 +275,9 @@ struct BaSolver : BaSolverBase {
   // device: parameters (two copies: current / candidate)
   DevBuf<double> d_intr[2], d_ext[2], d_trk[2], d_tlw[2], d_intr_init, d_ext_init, d_trk_init, d_tlw_init;
   int cur = 0;
+  bool use_dense = false;  // n <= kDenseMaxN: stage 3 is a dense Cholesky in one CTA (k_dense_chol) instead of the CG
+  DevBuf<double> d_dense;  // [(n + 1) x n]
+  size_t dense_smem_bytes() const { return (size_t)(kDenseNB * kDenseLd + 32 * kDenseNB + 2 * ((n + 3) & ~3) + (n + 1) * (n | 1)) * sizeof(double); }
   int vt_for = -1;         // parameter copy (0/1) the view table d_vt was built from, -1 = stale
   bool vt_scaled = false;  // ... with the final Jacobi scales in it
   // device: work
@@ -749,6 +752,16 @@ struct BaSolver : BaSolverBase {
         h_abg.assign(3 * (size_t)kHistCap, 0.0);
       }
     }
+    {
+      const char* e = getenv("PTZ_DENSE_MAX_N");  // (0 switches the dense path off: A/B measurements, tests of the CG on small scenes)
+      const int cap = e ? atoi(e) : kDenseMaxN;
+      use_dense = n <= std::min(cap, (int)kDenseMaxN) && cg_vranks == 1;
+      if (use_dense) {
+        d_dense.alloc((size_t)(n + 1) * n, stream);
+        PTZ_CUDA(cudaFuncSetAttribute(k_dense_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense_smem_bytes()));
+        defl_enabled = false;
+      }
+    }
     d_cgp.alloc((size_t)n, stream); d_cgp.zero(s);
     d_y.alloc(n, stream); d_y.zero(s);
     d_pcg_res.alloc(2, stream); d_pcg_info.alloc(2, stream); d_fail.alloc(1, stream); d_fail.zero(s);
@@ -951,6 +964,24 @@ struct BaSolver : BaSolverBase {
       k_shared_border<NCL><<<cdiv(ns, 32), 32, 0, s>>>(ns, nb, nb_plain, d_grp_off.p, d_grp_view.p, d_rowpart.p, d_sh_h.p, mu, refresh, opt.min_lm_diagonal,
                                                        opt.max_lm_diagonal, d_diag_b.p, p_Sbb, p_rhs + (size_t)V * NCL);
       PTZ_CUDA(cudaGetLastError());
+    }
+    if (use_dense) {
+      // small system: exact dense Cholesky in one CTA instead of the CG (k_dense_chol)
+      PTZ_TIMED(PTZ_K_PCG, {
+        PTZ_CUDA(cudaMemsetAsync(d_dense.p, 0, d_dense.n * sizeof(double), s));
+        const int nthreads = ds.nnzb + ncpl * NCL * nb + nb * nb + n;
+        k_dense_assemble<NCL><<<cdiv(nthreads, 128), 128, 0, s>>>(V, nb, ds.nnzb, ds.blk_row.p, ds.s_col.p, p_Sval, p_rhs, ncpl, d_cpl_view.p,
+                                                                  (kDisp || nf > 0 || ns > 0) ? p_Cw : p_C, p_Sbb, d_dense.p);
+        k_dense_chol<<<1, kDenseThreads, dense_smem_bytes(), s>>>(n, d_dense.p, d_y.p, d_pcg_info.p, d_fail.p);
+        if (ns > 0) k_shared_expand<NCL><<<cdiv(V * (NCL - 3), 128), 128, 0, s>>>(V, d_grp_of.p, V * NCL, bo_sh, d_y.p);
+      });
+      PTZ_CUDA(cudaGetLastError());
+      launch_stage4(mu);
+      read_scalars();
+      ++cost_evals;
+      *lin_iters = h_info[0];
+      last_lin_iters = h_info[0];
+      return h_info[2] == 0;
     }
     PTZ_TIMED(PTZ_K_PRECOND, {
       k_precond<NCL><<<cdiv(V, 128), 128, 0, s>>>(V, ds.diag_pos.p, p_Sval, d_Linv.p, d_fail.p, defl_enabled ? d_Lfac.p : nullptr);

@@ -364,6 +364,26 @@ def test_cfg4_iterations_match_sparse_oracle(orc, scale):
         assert np.abs(e.gradient - w.gradient).max() <= 1e-9 * np.abs(w.gradient).max()
 
 
+@pytest.mark.parametrize("cfg,kw", [(1, {}), (1, dict(num_pts3d=40, pts3d_views=10)), (0, dict(num_pts3d=12))])
+def test_dense_direct_solve_equals_the_cg(monkeypatch, cfg, kw):
+    """small reduced systems (n <= 160: cfg 1, the BAs of an IBA run) are factored by a dense Cholesky in one CTA (k_dense_chol) instead of the CG: same LM
+    trajectory, cost and parameters as the CG path at its 1e-13 tolerance -- camera-only systems, with the tlw border, with disp"""
+    def scene():
+        return synth.make_distdisp_scene(**kw) if cfg == 0 else synth.make_config(cfg, **kw)
+
+    dense = ptz.ba_solve(scene(), max_num_iterations=200)
+    monkeypatch.setenv("PTZ_DENSE_MAX_N", "0")
+    cg = ptz.ba_solve(scene(), max_num_iterations=200)
+    monkeypatch.delenv("PTZ_DENSE_MAX_N")
+    assert dense.converged and dense.linear_solver_iterations < cg.linear_solver_iterations  # (one 'iteration' per direct solve)
+    assert dense.num_iterations == cg.num_iterations and dense.termination == cg.termination
+    assert [l["step_is_successful"] for l in dense.log] == [l["step_is_successful"] for l in cg.log]
+    loose = 1e3 if cfg == 0 else 1.0
+    assert abs(dense.final_cost - cg.final_cost) <= 1e-9 * cg.final_cost
+    assert np.abs(dense.ext - cg.ext).max() <= 1e-8 * loose and np.abs(dense.intr[:, 0] - cg.intr[:, 0]).max() <= 1e-6 * loose
+    assert np.abs(dense.ray - cg.ray).max() <= 1e-8 * loose
+
+
 def test_deflated_cg_same_trajectory(monkeypatch):
     """the deflated linear solver (Ritz vectors recycled from the first solve) and the plain one give the same LM trajectory, on
     one GPU and with the rows split over virtual ranks (the multi-GPU kernel variant)"""

@@ -484,19 +484,56 @@ int ptzreloc_solve_batch(const ptzreloc_batch* b, const ptz_solver_options* opt,
     DevBuf<double> d_ref, d_init, d_cam, d_ic, d_fc, d_rms, d_loc;
     DevBuf<int> d_succ, d_term, d_ni, d_it;
     d_off.upload(b->match_offset, B + 1, s);
-    d_ur.upload(reinterpret_cast<const float2*>(b->uv_ref), N, s);
-    d_uc.upload(reinterpret_cast<const float2*>(b->uv_cur), N, s);
-    d_ref.upload(b->ref_cam, 21 * (size_t)B, s);
-    d_init.upload(b->init_cam, 21 * (size_t)B, s);
+    d_ur.alloc(N, s); d_uc.alloc(N, s); d_ref.alloc(21 * (size_t)B, s); d_init.alloc(21 * (size_t)B, s);
     d_cam.alloc(21 * (size_t)B, s); d_ic.alloc(B, s); d_fc.alloc(B, s); d_rms.alloc(B, s); d_loc.alloc(15 * (size_t)B, s);
     d_succ.alloc(B, s); d_term.alloc(B, s); d_ni.alloc(B, s); d_it.alloc(B, s);
-    RelocArgs a;
-    a.B = B; a.off = d_off.p; a.uv_ref = d_ur.p; a.uv_cur = d_uc.p; a.ref_cam = d_ref.p; a.init_cam = d_init.p;
-    a.max_iter = b->max_iter; a.max_reproj_error = b->max_reproj_error; a.opt = *opt;
-    a.pt_off = has_pts ? d_poff.p : nullptr; a.pt_uv = d_puv.p; a.pt_xyz = d_pxyz.p;
-    a.cam = d_cam.p; a.success = d_succ.p; a.termination = d_term.p; a.num_iter = d_ni.p; a.iterations = d_it.p;
-    a.initial_cost = d_ic.p; a.final_cost = d_fc.p; a.final_rms = d_rms.p; a.local15 = d_loc.p;
-    launch_reloc(b->factor_type, a, max_matches, s);
+    // The batch is PCIe-bound end to end (16 B per match in, the kernel reads them once): cut it into slices of ~1 M matches and
+    // rotate them over three streams, so that the copy-in of slice k+1 and the copy-out of slice k-1 run under the kernel of slice k
+    // (the copies only overlap when the caller's buffers are pinned; with pageable memory this degrades to the serial order).
+    const int64_t kSliceMatches = 1 << 20;
+    const int nslices = (int)std::max<int64_t>(1, std::min<int64_t>(64, N / kSliceMatches));
+    StreamHolder extra[2];
+    cudaStream_t st[3] = {s, s, s};
+    cudaEvent_t ready = nullptr, done[2] = {nullptr, nullptr};
+    if (nslices > 1) {
+      extra[0].create(); extra[1].create();
+      st[1] = extra[0].s; st[2] = extra[1].s;
+      PTZ_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+      PTZ_CUDA(cudaEventRecord(ready, s));  // allocations and the offsets are stream-ordered on s
+      for (int k = 0; k < 2; ++k) { PTZ_CUDA(cudaStreamWaitEvent(st[k + 1], ready, 0)); PTZ_CUDA(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming)); }
+    }
+    int q0 = 0;
+    for (int k = 0; k < nslices; ++k) {
+      int q1 = B;
+      if (k + 1 < nslices) {  // first query whose matches start at or behind the slice's share
+        const int64_t target = N * (int64_t)(k + 1) / nslices;
+        q1 = (int)(std::lower_bound(b->match_offset + q0, b->match_offset + B, target) - b->match_offset);
+        q1 = std::max(q1, q0);
+      }
+      const int nq = q1 - q0;
+      if (nq == 0) continue;
+      cudaStream_t cs = st[k % 3];
+      const int64_t m0 = b->match_offset[q0], m1 = b->match_offset[q1];
+      if (m1 > m0) {
+        PTZ_CUDA(cudaMemcpyAsync(d_ur.p + m0, reinterpret_cast<const float2*>(b->uv_ref) + m0, (size_t)(m1 - m0) * sizeof(float2), cudaMemcpyHostToDevice, cs));
+        PTZ_CUDA(cudaMemcpyAsync(d_uc.p + m0, reinterpret_cast<const float2*>(b->uv_cur) + m0, (size_t)(m1 - m0) * sizeof(float2), cudaMemcpyHostToDevice, cs));
+      }
+      PTZ_CUDA(cudaMemcpyAsync(d_ref.p + 21 * (size_t)q0, b->ref_cam + 21 * (size_t)q0, 21 * (size_t)nq * 8, cudaMemcpyHostToDevice, cs));
+      PTZ_CUDA(cudaMemcpyAsync(d_init.p + 21 * (size_t)q0, b->init_cam + 21 * (size_t)q0, 21 * (size_t)nq * 8, cudaMemcpyHostToDevice, cs));
+      RelocArgs a;
+      a.B = nq; a.off = d_off.p + q0; a.uv_ref = d_ur.p; a.uv_cur = d_uc.p; a.ref_cam = d_ref.p + 21 * (size_t)q0; a.init_cam = d_init.p + 21 * (size_t)q0;
+      a.max_iter = b->max_iter; a.max_reproj_error = b->max_reproj_error; a.opt = *opt;
+      a.pt_off = has_pts ? d_poff.p + q0 : nullptr; a.pt_uv = d_puv.p; a.pt_xyz = d_pxyz.p;
+      a.cam = d_cam.p + 21 * (size_t)q0; a.success = d_succ.p + q0; a.termination = d_term.p + q0; a.num_iter = d_ni.p + q0; a.iterations = d_it.p + q0;
+      a.initial_cost = d_ic.p + q0; a.final_cost = d_fc.p + q0; a.final_rms = d_rms.p + q0; a.local15 = d_loc.p + 15 * (size_t)q0;
+      launch_reloc(b->factor_type, a, max_matches, cs);
+      q0 = q1;
+    }
+    if (nslices > 1) {  // the main stream (on which the buffers are released) waits for the other two
+      for (int k = 0; k < 2; ++k) { PTZ_CUDA(cudaEventRecord(done[k], st[k + 1])); PTZ_CUDA(cudaStreamWaitEvent(s, done[k], 0)); }
+    }
+    // results (small next to the matches) leave at the end: a copy into PAGEABLE caller memory blocks the host until it is done, and
+    // issued per slice it would stall the loop above behind every kernel
     d_cam.download(out->cam, 21 * (size_t)B, s);
     d_succ.download(out->success, B, s);
     d_term.download(out->termination, B, s);
@@ -507,9 +544,12 @@ int ptzreloc_solve_batch(const ptzreloc_batch* b, const ptz_solver_options* opt,
     if (out->final_rms) d_rms.download(out->final_rms, B, s);
     if (out->local_cam15) d_loc.download(out->local_cam15, 15 * (size_t)B, s);
     PTZ_CUDA(cudaStreamSynchronize(s));
+    if (ready) cudaEventDestroy(ready);
+    for (int k = 0; k < 2; ++k) if (done[k]) cudaEventDestroy(done[k]);
     return (int)PTZ_OK;
   });
 }
+
 
 int ptzreloc_eval(int type, int N, const float* uv_ref, const float* uv_cur, const double* ref21, const double* local15, double* residuals, double* jac,
                   double* cost, double* gradient) {

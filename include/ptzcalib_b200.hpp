@@ -203,6 +203,15 @@ inline void FindMaxCoVisible(const Tracks& tracks, int num_images, std::set<int>
 
 enum FACTOR_TYPE { PTZRay, PTZRayDist, PTZRayFxfyDist, PTZRayDistDisp };  // ptzray_optimizer.h:110
 
+// What FindTracks produces.  It depends on the match table alone (ptzray_optimizer.cc:537-552 builds the tracks from ALL of
+// matches_info_, whatever the candidate set), so a caller that solves many BAs over one table -- the incremental driver -- builds it
+// once and hands it to every optimizer (PTZRayOptimizer::SetTrackCache) instead of re-running the build per BA as the reference does.
+struct TrackCache {
+  Tracks tracks;
+  std::vector<int32_t> flat_id, flat_img, flat_feat;
+  std::vector<int64_t> flat_off;
+};
+
 class PTZRayOptimizer {
  public:
   PTZRayOptimizer(const std::vector<ImageFeatures>& features, const std::vector<MatchesInfo>& matches_info, const std::vector<Camera>& cameras,
@@ -301,6 +310,8 @@ class PTZRayOptimizer {
     if (shared_ic_ids.size() != cameras_.size()) return;  // .cc:499-502
     shared_ic_ids_ = shared_ic_ids;
   }
+  // filled by the first Solve that sees it empty, reused by every later optimizer it is given to (same match table!)
+  void SetTrackCache(TrackCache* cache) { track_cache_ = cache; }
   // false: keep the device's canonical track ids (skips the host pass over the matches; the tracks are the same sets)
   void SetReferenceTrackIds(bool on) { reference_track_ids_ = on; }
   void SetInitTransLocalToWorld(const double tlw[6]) { tlw_param_.assign(tlw, tlw + 6); tlw_given_ = true; }  // see the header comment
@@ -380,6 +391,11 @@ class PTZRayOptimizer {
   // host-side mirror of the reference's TracksBuilder API.  By default the device's canonical ids (smallest node) are turned into
   // the reference's union-by-rank root ids, so tracks(), Ray::id_ and the order of the residual blocks are the reference's.
   bool FindTracks() {
+    if (track_cache_ && !track_cache_->flat_off.empty()) {  // built by an earlier optimizer over the same match table
+      tracks_ = track_cache_->tracks; flat_id_ = track_cache_->flat_id; flat_off_ = track_cache_->flat_off;
+      flat_img_ = track_cache_->flat_img; flat_feat_ = track_cache_->flat_feat;
+      return true;
+    }
     std::vector<int32_t> src, dst, q, t;
     std::vector<int64_t> off(1, 0);
     for (const auto& mi : matches_info_) {
@@ -406,6 +422,10 @@ class PTZRayOptimizer {
       Track& trk = tracks_[flat_id_[k]];
       for (int64_t i = flat_off_[k]; i < flat_off_[k + 1]; ++i) trk.emplace_hint(trk.end(), flat_img_[i], flat_feat_[i]);
     }
+    if (track_cache_) {
+      track_cache_->tracks = tracks_; track_cache_->flat_id = flat_id_; track_cache_->flat_off = flat_off_;
+      track_cache_->flat_img = flat_img_; track_cache_->flat_feat = flat_feat_;
+    }
     return true;
   }
   bool isCandidate(long id) const { return cam_ids_.find(id) != cam_ids_.end(); }
@@ -421,6 +441,7 @@ class PTZRayOptimizer {
   FACTOR_TYPE type_;
   std::vector<double> tlw_param_ = std::vector<double>(6, 0.0);
   bool tlw_given_ = false, reference_track_ids_ = true;
+  TrackCache* track_cache_ = nullptr;
   Tracks tracks_;
   std::vector<int32_t> flat_id_, flat_img_, flat_feat_;  // tracks_ as ptztracks_result arrays
   std::vector<int64_t> flat_off_;
@@ -536,8 +557,9 @@ class KRTOptimizer {
 };
 
 // ptz_incremental_optimizer.h:24-124, .cc:39-441 — PTZ-IBA: greedy incremental registration around global bundle adjustments.
-// Same control flow, thresholds and state as the reference; the numerical work goes to the GPU: every global BA is one
-// ptztracks_build + ptztracks_flatten + ptzba_solve (through PTZRayOptimizer above), and RegisterNextImage solves ALL the
+// Same control flow, thresholds and state as the reference; the numerical work goes to the GPU: the tracks are built ONCE per run
+// (ptztracks_build; they depend on the match table alone, the reference rebuilds them for each of its ~20-40 BAs), every global BA
+// is then one ptztracks_flatten + ptzba_solve (through PTZRayOptimizer above), and RegisterNextImage solves ALL the
 // candidate (registered neighbour, new image) KRT problems of one image in ONE ptzreloc_solve_batch call — one CTA each —
 // then takes the first success in matches_info order, which is what the reference's sequential loop (.cc:384-415) returns.
 class PtzIncrementalOptimizer {
@@ -704,6 +726,7 @@ class PtzIncrementalOptimizer {
     init_image_pairs_.insert(PairId(id1, id2));
     SetInitialImagePairParameters(id1, id2);
     PTZRayOptimizer optimizer(features_, matches_info_, cameras_, std::unordered_set<long>{id1, id2}, max_iter_, PTZRay);
+    optimizer.SetTrackCache(&track_cache_);
     const bool ok = optimizer.Solve(cameras_);
     last_ba_iterations_ = optimizer.num_iterations();
     if (ok) { reg_image_ids_.insert(id1); reg_image_ids_.insert(id2); }
@@ -765,6 +788,7 @@ class PtzIncrementalOptimizer {
   }
   bool AdjustGlobalBundle() {  // .cc:421-439
     PTZRayOptimizer optimizer(features_, matches_info_, cameras_, reg_image_ids_, max_iter_, PTZRay);
+    optimizer.SetTrackCache(&track_cache_);  // the tracks are a function of the match table: built by the first BA of the run only
     const bool ok = optimizer.Solve(cameras_);
     last_reproj_error_ = optimizer.final_reproj_error_all();
     ++num_global_bundles_;
@@ -784,6 +808,7 @@ class PtzIncrementalOptimizer {
   int num_global_bundles_ = 0, num_reloc_batches_ = 0, num_reloc_queries_ = 0, last_ba_iterations_ = 0;
   double last_reproj_error_ = 0;
   std::vector<std::array<long, 3>> trace_;
+  TrackCache track_cache_;
 };
 
 }  // namespace ptzcalib

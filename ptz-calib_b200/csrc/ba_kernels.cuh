@@ -495,13 +495,16 @@ __global__ void k_schur_diag(int V, const int* __restrict__ view_chunk_off, cons
 #define PTZ_OD_MINB 1
 #endif
 template <int NCL>
-__global__ void __launch_bounds__(256, PTZ_OD_MINB) k_schur_offdiag(int nub, const int64_t* __restrict__ pair_off, const int* __restrict__ pair_a,
-                                                       const int* __restrict__ pair_b, const double* __restrict__ What, const int* __restrict__ ub_pos,
-                                                       const int* __restrict__ ub_pos_t, double* __restrict__ Sval) {
+__global__ void __launch_bounds__(256, PTZ_OD_MINB) k_schur_offdiag(int nlist, const int* __restrict__ ub_list, const int64_t* __restrict__ pair_off,
+                                                       const int* __restrict__ pair_a, const int* __restrict__ pair_b, const double* __restrict__ What,
+                                                       const int* __restrict__ ub_pos, const int* __restrict__ ub_pos_t, double* __restrict__ Sval) {
   typedef Dims<NCL> D;
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int li = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (b >= nub) return;
+  if (li >= nlist) return;
+  // sharded problem: the block pattern is the union over the ranks, this rank has pairs in ~1/W of the blocks; ub_list names those (the
+  // others were zeroed by a memset), nullptr = every block
+  const int b = ub_list != nullptr ? ub_list[li] : li;
   double acc[NCL * NCL];
 #pragma unroll
   for (int i = 0; i < NCL * NCL; ++i) acc[i] = 0.0;
@@ -544,6 +547,55 @@ __global__ void __launch_bounds__(256, PTZ_OD_MINB) k_schur_offdiag(int nub, con
     const double tot = warp_reduce_scatter<RP>(v, lane);
     const int e = 32 + lane / (32 / RP);
     if (lane % (32 / RP) == 0 && e < NN) { S[e] = -tot; St[(e % NCL) * NCL + e / NCL] = -tot; }
+  }
+}
+
+// A SUB-warp per block (GROUP = 16 or 8 lanes: two or four blocks per warp).  More blocks in flight per SM hide the gather latency
+// better than a whole warp per block even at ~100 pairs per block (cfg 4 on one GPU: 155 -> 145 us with half-warps), and on sharded
+// problems the pairs of a block are spread over the ranks (~25 per block and rank at 4 ranks, ~12 at 8), where a whole warp leaves most
+// lanes idle.  NCL = 4 only (16 entries: one or two per lane).
+template <int NCL, int GROUP>
+__global__ void __launch_bounds__(256, PTZ_OD_MINB) k_schur_offdiag_sub(int nlist, const int* __restrict__ ub_list, const int64_t* __restrict__ pair_off,
+                                                           const int* __restrict__ pair_a, const int* __restrict__ pair_b,
+                                                           const double* __restrict__ What, const int* __restrict__ ub_pos,
+                                                           const int* __restrict__ ub_pos_t, double* __restrict__ Sval) {
+  static_assert(NCL == 4 && (GROUP == 16 || GROUP == 8), "16 block entries over a half or a quarter warp");
+  typedef Dims<NCL> D;
+  const int li = blockIdx.x * (blockDim.x / GROUP) + (threadIdx.x / GROUP);
+  const int lane = threadIdx.x & 31, gl = lane & (GROUP - 1);
+  const bool active = li < nlist;  // (no early return: all groups of a warp take part in the shuffles below)
+  const int b = active ? (ub_list != nullptr ? ub_list[li] : li) : 0;
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+  const int64_t ke = active ? pair_off[b + 1] : 0;
+  int64_t k = active ? pair_off[b] + gl : 0;
+  int ia = 0, ib = 0;
+  if (k < ke) { ia = pair_a[k]; ib = pair_b[k]; }
+  for (; k < ke; k += GROUP) {
+    const double* wa = What + (size_t)ia * D::WS;
+    const double* wb = What + (size_t)ib * D::WS;
+    if (k + GROUP < ke) { ia = pair_a[k + GROUP]; ib = pair_b[k + GROUP]; }
+    double x[D::WS], y[D::WS];
+#pragma unroll
+    for (int i = 0; i < D::WS / 4; ++i) ld256(wa + 4 * i, x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+#pragma unroll
+    for (int i = 0; i < D::WS / 4; ++i) ld256(wb + 4 * i, y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+#pragma unroll
+    for (int a = 0; a < NCL; ++a)
+#pragma unroll
+      for (int c = 0; c < NCL; ++c) acc[a * NCL + c] += x[3 * a] * y[3 * c] + x[3 * a + 1] * y[3 * c + 1] + x[3 * a + 2] * y[3 * c + 2];
+  }
+  // reduce-scatter inside each group: lane gl ends up with the totals of entries [gl * 16/GROUP, (gl + 1) * 16/GROUP)
+  WarpRS<16, GROUP / 2>::run(acc, lane);
+  if (active) {
+    constexpr int PER = 16 / GROUP;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int e = gl * PER + u;
+      Sval[(size_t)ub_pos[b] * 16 + e] = -acc[u];
+      Sval[(size_t)ub_pos_t[b] * 16 + (e % NCL) * NCL + e / NCL] = -acc[u];
+    }
   }
 }
 

@@ -275,6 +275,9 @@ struct BaSolver : BaSolverBase {
   // device: parameters (two copies: current / candidate)
   DevBuf<double> d_intr[2], d_ext[2], d_trk[2], d_tlw[2], d_intr_init, d_ext_init, d_trk_init, d_tlw_init;
   int cur = 0;
+  int od_group = 32;       // lanes per block in the off-diagonal Schur kernel: 32 (k_schur_offdiag), 16 or 8 (k_schur_offdiag_sub, NCL = 4)
+  int nub_local = 0;       // upper blocks of S with observation pairs on THIS rank (sharded problem: ~1/W of the union pattern)
+  DevBuf<int> d_ub_list;   // their indices; empty = all blocks
   bool use_dense = false;  // n <= kDenseMaxN: stage 3 is a dense Cholesky in one CTA (k_dense_chol) instead of the CG
   DevBuf<double> d_dense;  // [(n + 1) x n]
   size_t dense_smem_bytes() const { return (size_t)(kDenseNB * kDenseLd + 32 * kDenseNB + 2 * ((n + 3) & ~3) + (n + 1) * (n | 1)) * sizeof(double); }
@@ -396,6 +399,20 @@ struct BaSolver : BaSolverBase {
       } else {
         build_structure_device_blocks(ds, nullptr, stream);
       }
+    }
+    nub_local = ds.nub;
+    if (g_nccl.world > 1 && ds.nub > 0) {
+      std::vector<int64_t> poff((size_t)ds.nub + 1);
+      ds.pair_off.download(poff.data(), poff.size(), stream);
+      PTZ_CUDA(cudaStreamSynchronize(stream));
+      std::vector<int> list;
+      for (int b = 0; b < ds.nub; ++b) if (poff[b + 1] > poff[b]) list.push_back(b);
+      if ((int)list.size() < ds.nub) { nub_local = (int)list.size(); if (list.empty()) list.push_back(0); d_ub_list.upload(list, stream); }
+    }
+    {
+      const char* e = getenv("PTZ_OD_GROUP");  // tuning hook: 32 / 16 / 8 force the variant
+      od_group = e ? atoi(e) : (ds.npairs < 40ll * std::max(nub_local, 1) ? 8 : 16);
+      if (NCL != 4 || (od_group != 16 && od_group != 8)) od_group = 32;
     }
     phase("block pattern + pair lists");
     // annotated points: sort by view, list annotated views
@@ -937,11 +954,26 @@ struct BaSolver : BaSolverBase {
                                                                           d_What.p, d_q.p);
         if (kDisp) k_disp_track<NCL><<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_recA.p, d_recd.p, d_Lt.p, d_Wdh.p);
       });
+    if (d_ub_list.n) PTZ_CUDA(cudaMemsetAsync(p_Sval, 0, (size_t)ds.nnzb * NCL * NCL * sizeof(double), s));  // blocks without local pairs stay zero
     PTZ_TIMED(PTZ_K_SCHUR_DIAG, k_schur_diag<NCL><<<cdiv(V * (D::NU + NCL), 128), 128, 0, s>>>(V, ds.view_chunk_off.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal,
                                                                                opt.max_lm_diagonal, own, d_diag_cam.p, ds.diag_pos.p, p_Sval, p_rhs, ns > 0 ? d_grp_of.p : nullptr));
-    if (ds.nub > 0)
-      PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, k_schur_offdiag<NCL><<<cdiv(ds.nub, 8), 256, 0, s>>>(ds.nub, ds.pair_off.p, ds.pair_a.p, ds.pair_b.p, d_What.p,
-                                                                                            ds.ub_pos.p, ds.ub_pos_t.p, p_Sval));
+    if (ds.nub > 0) {
+      bool half = false;
+      if constexpr (NCL == 4) {
+        half = od_group != 32;
+        const int* list = d_ub_list.n ? d_ub_list.p : nullptr;
+        if (od_group == 16)
+          PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, (k_schur_offdiag_sub<NCL, 16><<<cdiv(std::max(nub_local, 1), 16), 256, 0, s>>>(
+                                             nub_local, list, ds.pair_off.p, ds.pair_a.p, ds.pair_b.p, d_What.p, ds.ub_pos.p, ds.ub_pos_t.p, p_Sval)));
+        else if (od_group == 8)
+          PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, (k_schur_offdiag_sub<NCL, 8><<<cdiv(std::max(nub_local, 1), 32), 256, 0, s>>>(
+                                             nub_local, list, ds.pair_off.p, ds.pair_a.p, ds.pair_b.p, d_What.p, ds.ub_pos.p, ds.ub_pos_t.p, p_Sval)));
+      }
+      if (!half)
+        PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, k_schur_offdiag<NCL><<<cdiv(std::max(nub_local, 1), 8), 256, 0, s>>>(nub_local, d_ub_list.n ? d_ub_list.p : nullptr, ds.pair_off.p,
+                                                                                                            ds.pair_a.p, ds.pair_b.p, d_What.p, ds.ub_pos.p,
+                                                                                                            ds.ub_pos_t.p, p_Sval));
+    }
     if (nb > 0)
       k_border_system<<<1, 128, 0, s>>>(nb, nf, p_Hbb, p_Hrf, p_Hff, p_gb, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, own, d_diag_b.p, d_hinv.p,
                                         p_Sbb, p_rhs + (size_t)V * NCL, nb_plain);

@@ -268,7 +268,9 @@ def run_ours(args):
     st["ms_kernels_total"] = st_k["ms_kernels_total"]
     st["ms_run_instrumented"] = st_k["ms_run"]
     st["deflated_solves"] = st_k["deflated_solves"]
-    assert done_k == done and st_k["launches_total"] == st["launches_total"], "the two passes must run the same launches"
+    # single GPU: bit-reproducible, both passes are the same launches.  Sharded: the order of the NCCL sums may differ from run to run,
+    # an LM trajectory may then take one linear solve more or less; the line says so instead of failing
+    passes_identical = bool(done_k == done and st_k["launches_total"] == st["launches_total"])
     # (the clock sampler keeps running through the e2e and reloc legs: the BA region alone lasts ~0.3 s)
     dev_ms = allmax(st["ms_run"])  # CUDA events on the solver's stream, max over ranks
     dev_ms_instrumented = allmax(st["ms_run_instrumented"])  # (collectives are called by EVERY rank, never inside `if rank == 0`)
@@ -411,8 +413,8 @@ def run_ours(args):
                        "views": prob.V, "obs_per_gpu": prob.M, "parallelism": (f"tracks/observations sharded x{world} (NCCL all-reduce of camera blocks), rows of the reduced system sharded x{world} "
                                                                                        "(in-kernel NVLink peer exchange)") if world > 1 else "single GPU"},
             "lm_iters_per_sec": round(done / (dev_ms * 1e-3), 2), "solves_in_timed_region": solves, "wall_seconds": round(wall, 4),
-            "ms_per_step_with_per_kernel_events": round(dev_ms_instrumented / max(done, 1), 4),
-            "ms_per_step_kernels_only": round(st["ms_kernels_total"] / max(done, 1), 4),
+            "ms_per_step_with_per_kernel_events": round(dev_ms_instrumented / max(done_k, 1), 4),
+            "ms_per_step_kernels_only": round(st["ms_kernels_total"] / max(done_k, 1), 4), "timed_and_instrumented_pass_identical": passes_identical,
             "pcg_iterations_per_step": round(st["pcg_iterations"] / st["lm_iterations"], 1),
             "us_per_pcg_iteration": round(1e3 * kernels["pcg"]["ms"] / max(st["pcg_iterations"], 1), 3) if "pcg" in kernels else None,
             "rj_mobs_per_sec": round(prob.M / (rj["avg_us"]) , 1) if rj else None,

@@ -328,8 +328,8 @@ struct BaSolver : BaSolverBase {
     return deflated ? cg_kernel_sel<false, kDeflK>() : cg_kernel_sel<false, 0>();
   }
   // ---- deflation of the CG (k_cg<.., KD = kDeflK>): basis harvested from the residual history of the first solve of a run
-  bool defl_enabled = false, have_W = false, defl_active = true;
-  int defl_kd = 0, defl_solves = 0, defl_rejects = 0, last_lin_iters = -1;
+  bool defl_enabled = false, defl_allowed = false, have_W = false, defl_active = true;
+  int defl_kd = 0, defl_solves = 0, defl_rejects = 0, last_lin_iters = -1, defl_ref_iters = 0;
   static constexpr int kHistCap = 320, kMinHarvest = 40, kDeflOffBelow = 12, kDeflOnAbove = 30;
   DevBuf<double> d_hist, d_abg, d_Wy, d_Wt, d_AW, d_Z, d_gram, d_Einv, d_c0, d_dscal, d_bcopy, d_Lfac, d_Y;
   std::vector<double> h_abg;
@@ -411,7 +411,7 @@ struct BaSolver : BaSolverBase {
     }
     {
       const char* e = getenv("PTZ_OD_GROUP");  // tuning hook: 32 / 16 / 8 force the variant
-      od_group = e ? atoi(e) : (ds.npairs < 40ll * std::max(nub_local, 1) ? 8 : 16);
+      od_group = e ? atoi(e) : (ds.npairs < 64ll * std::max(nub_local, 1) ? 8 : 16);
       if (NCL != 4 || (od_group != 16 && od_group != 8)) od_group = 32;
     }
     phase("block pattern + pair lists");
@@ -779,6 +779,7 @@ struct BaSolver : BaSolverBase {
         defl_enabled = false;
       }
     }
+    defl_allowed = defl_enabled;
     d_cgp.alloc((size_t)n, stream); d_cgp.zero(s);
     d_y.alloc(n, stream); d_y.zero(s);
     d_pcg_res.alloc(2, stream); d_pcg_info.alloc(2, stream); d_fail.alloc(1, stream); d_fail.zero(s);
@@ -815,6 +816,7 @@ struct BaSolver : BaSolverBase {
     radius = opt.initial_trust_region_radius; decrease_factor = 2.0; reuse_diagonal = false; last_successful = true;
     termination = PTZ_NO_CONVERGENCE;
     log.clear();
+    defl_enabled = defl_allowed; defl_rejects = 0;   // (a run that gave deflation up does not decide for the next one)
     if (have_W || (defl_enabled && d_hist.n == 0)) {  // every solve harvests its own deflation basis: runs are bit-reproducible
       have_W = false;
       defl_active = true; last_lin_iters = -1;
@@ -1040,14 +1042,25 @@ struct BaSolver : BaSolverBase {
     read_scalars();
     if (deflate) {
       ++defl_solves;
+      const bool stalled = h_info[1] == 1 && h_info[0] < opt.pcg_max_iterations;  // hit the deflated solve's own cap
+      if (stalled) h_info[1] = 2;
       if (h_dscal[1] == 0.0 || h_info[1] == 2) {
-        // the (stale) basis lost rank, or the deflated recurrences broke down: this handle goes back to the plain iteration
+        // the (stale) basis lost rank, or the deflated single-reduction recurrences stagnated above the tolerance and broke down (seen
+        // on sharded problems with V = 4000): drop the basis, redo this solve with the plain iteration and harvest a FRESH basis from
+        // it; after three such rejections in one run the handle stays with the plain iteration
         ++defl_rejects;
-        have_W = false; defl_enabled = false;
+        if (opt.verbose || getenv("PTZ_DEFL_DEBUG"))
+          fprintf(stderr, "[ptzba rank %d] deflated solve rejected at LM iteration %d: basis usable %g, pcg status %d after %d iterations (%d rejections)\n",
+                  g_nccl.rank, iteration, h_dscal[1], h_info[1], h_info[0], defl_rejects);
+        have_W = false;
+        if (defl_rejects >= 3) defl_enabled = false;
+        if (defl_enabled && d_hist.n == 0) d_hist.alloc((size_t)kHistCap * V * NCL, stream);
         if (h_info[1] == 2) {
-          linear_solve(false, false, true);
+          const bool rec = defl_enabled;
+          linear_solve(false, rec, true);
           launch_stage4(mu);
           read_scalars();
+          if (rec && h_info[1] == 0 && h_info[0] >= kMinHarvest) harvest_basis(h_info[0]);
         }
       }
     } else if (record && h_info[1] == 0 && h_info[0] >= kMinHarvest) {
@@ -1076,7 +1089,9 @@ struct BaSolver : BaSolverBase {
     if (!rows_sharded && cg_vranks == 1) a.arena[0] = g_arena.base[cgR];  // the single-rank kernel works in arena[0]: this rank's own block
     a.off_partial = ar_partial; a.off_st0 = ar_st0; a.off_st1 = ar_st1; a.off_x = ar_x; a.off_ll0 = ar_ll0; a.off_ll1 = ar_ll1;
     a.W = cgW; a.rank = rows_sharded ? cgR : 0; a.vranks = cg_vranks; a.slots_per_rank = cg_slots_per_rank; a.p = d_cgp.p;
-    a.max_iter = opt.pcg_max_iterations; a.tol = opt.pcg_rel_tolerance;
+    // a deflated solve that needs more iterations than the plain solve its basis came from has stagnated: stop it there (-> rejected)
+    a.max_iter = deflate ? std::min(opt.pcg_max_iterations, std::max(60, defl_ref_iters)) : opt.pcg_max_iterations;
+    a.tol = opt.pcg_rel_tolerance;
     a.out_info = d_pcg_info.p; a.out_res = d_pcg_res.p;
     // shared-memory residency of S: every warp keeps up to cg_cap blocks (+ column indices) of its rows for the whole solve
     a.smem_blocks = cg_cap;
@@ -1136,6 +1151,7 @@ struct BaSolver : BaSolverBase {
     have_W = true;
     defl_active = true;
     defl_kd = kd;
+    defl_ref_iters = iterations;
     d_hist.release();  // (stream-ordered: goes back to the block cache behind the kernels above)
     if (opt.verbose) printf("[ptzba] deflation basis: %d Ritz vectors from %d CG iterations\n", kd, m);
   }

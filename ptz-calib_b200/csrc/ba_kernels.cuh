@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(kChunk, PTZ_RJ_MINB) k_resjac(int nchunks, int
       bulk_store(recF + (size_t)begin * D::RF, sF, (unsigned)(cnt * D::RF * 8));
       bulk_commit();
     }
+    // (one reduction per CHUNK here: keeping the 15 partial sums in registers across the chunks of a view, as k_obs_what does, costs
+    // k_resjac its fifth resident CTA or 176 bytes of spills -- measured 88 -> 98 / 117 us)
     block_sum_sm<D::NPART, kChunk>(acc, sred);
     if (t == 0) {
 #pragma unroll
@@ -335,7 +337,8 @@ struct ObsWhatSmem {
   static constexpr int kBytes = 2 * kRecBytes + (kWBytes > kRedBytes ? kWBytes : kRedBytes);
 };
 template <int NCL>
-__global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, int per, const int* __restrict__ chunk_begin, const int* __restrict__ chunk_cnt,
+__global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, int per, const int* __restrict__ chunk_view, const int* __restrict__ chunk_begin,
+                                                                  const int* __restrict__ chunk_cnt,
                                                                   const int* __restrict__ o_track, const double* __restrict__ recA,
                                                                   const double* __restrict__ recF, const double* __restrict__ Lt,
                                                                   double* __restrict__ What, double* __restrict__ wpart) {
@@ -343,13 +346,13 @@ __global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, i
   typedef ObsWhatSmem<NCL> SM;
   constexpr int NV = SM::NV, RC = SM::RC, WC = SM::WC;
   extern __shared__ __align__(16) unsigned char dsm[];
-  __shared__ int s_begin[kResjacMaxPer], s_cnt[kResjacMaxPer];
+  __shared__ int s_begin[kResjacMaxPer], s_cnt[kResjacMaxPer], s_view[kResjacMaxPer];
   double2* sw = reinterpret_cast<double2*>(dsm + 2 * SM::kRecBytes);
   double* sred = reinterpret_cast<double*>(dsm + 2 * SM::kRecBytes);  // reused after the staged What has been written out
   const int t = threadIdx.x;
   const int c0 = blockIdx.x * per, n = min(per, nchunks - c0);
   if (n <= 0) return;
-  if (t < n) { s_begin[t] = chunk_begin[c0 + t]; s_cnt[t] = chunk_cnt[c0 + t]; }
+  if (t < n) { s_begin[t] = chunk_begin[c0 + t]; s_cnt[t] = chunk_cnt[c0 + t]; s_view[t] = chunk_view[c0 + t]; }
   __syncthreads();
   auto stage_rec = [&](int k) {  // the chunk's records are two contiguous blocks: coalesced 16-byte copies into (swizzled) shared memory
     double2* dst = reinterpret_cast<double2*>(dsm + (k & 1) * SM::kRecBytes);
@@ -368,6 +371,9 @@ __global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, i
   };
   double2 l01 = make_double2(1, 0), l23 = make_double2(1, 0), l45 = make_double2(0, 1), l67 = make_double2(0, 0), l89 = make_double2(0, 0);
   int p_b = -1, p_c = -1;
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
   stage_rec(0);
   if (t < s_cnt[0]) {
     const double2* lp = reinterpret_cast<const double2*>(Lt + (size_t)o_track[s_begin[0] + t] * 10);
@@ -380,9 +386,6 @@ __global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, i
     __syncthreads();
     const double2* srec = reinterpret_cast<const double2*>(dsm + (k & 1) * SM::kRecBytes);
     const int chunk = c0 + k, begin = s_begin[k], cnt = s_cnt[k];
-    double acc[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) acc[i] = 0.0;
     if (t < cnt) {
       const double L1 = l01.y, L3 = l23.y, L4 = l45.x, t0 = l67.x, t1 = l67.y, t2 = l89.x;
       const double i00 = 1.0 / l01.x, i11 = 1.0 / l23.x, i22 = 1.0 / l45.y;
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, i
         const double w0 = f0 * a0 + f1 * b0, w1 = f0 * a1 + f1 * b1, w2 = f0 * a2 + f1 * b2;  // row a of F^T E
         const double x0 = w0 * i00, x1 = (w1 - L1 * x0) * i11, x2 = (w2 - L3 * x0 - L4 * x1) * i22;
         w[3 * a] = x0; w[3 * a + 1] = x1; w[3 * a + 2] = x2;
-        acc[D::NU + a] = x0 * t0 + x1 * t1 + x2 * t2;  // q_a
+        acc[D::NU + a] += x0 * t0 + x1 * t1 + x2 * t2;  // q_a
       }
 #pragma unroll
       for (int i = 3 * NCL; i < D::WS; ++i) w[i] = 0.0;
@@ -408,7 +411,7 @@ __global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, i
 #pragma unroll
       for (int a = 0; a < NCL; ++a)
 #pragma unroll
-        for (int bb = a; bb < NCL; ++bb) acc[kk++] = w[3 * a] * w[3 * bb] + w[3 * a + 1] * w[3 * bb + 1] + w[3 * a + 2] * w[3 * bb + 2];
+        for (int bb = a; bb < NCL; ++bb) acc[kk++] += w[3 * a] * w[3 * bb] + w[3 * a + 1] * w[3 * bb + 1] + w[3 * a + 2] * w[3 * bb + 2];
     }
     // gathers for the next two chunks: in flight during the write-out and the reduction below
     if (p_b >= 0) {
@@ -437,10 +440,14 @@ __global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, i
       }
     }
     __syncthreads();
-    block_sum_sm<NV, kChunk>(acc, sred);
-    if (t == 0) {
+    if (k + 1 == n || s_view[k + 1] != s_view[k]) {  // one block reduction per view of the CTA's run (as k_resjac): the other slots stay zero
+      block_sum_sm<NV, kChunk>(acc, sred);
+      if (t == 0) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) wpart[(size_t)chunk * NV + i] = acc[i];
+        for (int i = 0; i < NV; ++i) wpart[(size_t)chunk * NV + i] = acc[i];
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] = 0.0;
     }
     p_b = p_c;
   }
@@ -476,7 +483,7 @@ __global__ void k_schur_diag(int V, const int* __restrict__ view_chunk_off, cons
   while (rem >= NCL - a) { rem -= NCL - a; ++a; }
   const int b = a + rem;
   const double* Uv = U + (size_t)v * NCL * NCL;
-  double* S = Sval + (size_t)diag_pos[v] * NCL * NCL;
+  double* S = Sval + (size_t)(diag_pos != nullptr ? diag_pos[v] : v) * NCL * NCL;  // (nullptr: packed layout of the sharded problem)
   double sacc = -acc;
   if (add_own) sacc += Uv[a * NCL + b];
   if (a == b) {
@@ -529,15 +536,17 @@ __global__ void __launch_bounds__(256, PTZ_OD_MINB) k_schur_offdiag(int nlist, c
   }
   // reduce-scatter over the warp: element e of the block ends up in lane e * (32 / NP); those lanes store it (and its transpose)
   constexpr int NN = NCL * NCL, NP = NN <= 16 ? 16 : 32, REST = NN > 32 ? NN - 32 : 0;
-  double* S = Sval + (size_t)ub_pos[b] * NN;
-  double* St = Sval + (size_t)ub_pos_t[b] * NN;
+  // packed layout (sharded problem, ub_pos == nullptr): block b itself, no transpose -- k_unpack_S mirrors after the all-reduce
+  const bool packed = ub_pos == nullptr;
+  double* S = Sval + (size_t)(packed ? b : ub_pos[b]) * NN;
+  double* St = packed ? S : Sval + (size_t)ub_pos_t[b] * NN;
   {
     double v[NP];
 #pragma unroll
     for (int i = 0; i < NP; ++i) v[i] = i < NN ? acc[i] : 0.0;
     const double tot = warp_reduce_scatter<NP>(v, lane);
     const int e = lane / (32 / NP);
-    if (lane % (32 / NP) == 0 && e < NN) { S[e] = -tot; St[(e % NCL) * NCL + e / NCL] = -tot; }
+    if (lane % (32 / NP) == 0 && e < NN) { S[e] = -tot; if (!packed) St[(e % NCL) * NCL + e / NCL] = -tot; }
   }
   if (REST > 0) {  // NCL = 6: elements 32..35
     constexpr int RP = 4;
@@ -546,7 +555,7 @@ __global__ void __launch_bounds__(256, PTZ_OD_MINB) k_schur_offdiag(int nlist, c
     for (int i = 0; i < RP; ++i) v[i] = (REST > 0 && 32 + i < NN) ? acc[(32 + i) < NN ? 32 + i : 0] : 0.0;
     const double tot = warp_reduce_scatter<RP>(v, lane);
     const int e = 32 + lane / (32 / RP);
-    if (lane % (32 / RP) == 0 && e < NN) { S[e] = -tot; St[(e % NCL) * NCL + e / NCL] = -tot; }
+    if (lane % (32 / RP) == 0 && e < NN) { S[e] = -tot; if (!packed) St[(e % NCL) * NCL + e / NCL] = -tot; }
   }
 }
 
@@ -593,10 +602,29 @@ __global__ void __launch_bounds__(256, PTZ_OD_MINB) k_schur_offdiag_sub(int nlis
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
       const int e = gl * PER + u;
+      if (ub_pos == nullptr) { Sval[(size_t)b * 16 + e] = -acc[u]; continue; }  // packed layout: mirrored after the all-reduce
       Sval[(size_t)ub_pos[b] * 16 + e] = -acc[u];
       Sval[(size_t)ub_pos_t[b] * 16 + (e % NCL) * NCL + e / NCL] = -acc[u];
     }
   }
+}
+
+// Sharded problem: the ranks' pieces of S travel through the all-reduce PACKED -- diagonal blocks, then the upper blocks once --
+// instead of in the block-CSR layout that stores both triangles: half the bytes on the wire (92 -> 46 MB at 8 ranks).  One thread
+// per entry puts them (and the transposes) into place afterwards.
+template <int NCL>
+__global__ void k_unpack_S(int V, int nub, const double* __restrict__ pack, const int* __restrict__ diag_pos, const int* __restrict__ ub_pos,
+                           const int* __restrict__ ub_pos_t, double* __restrict__ Sval) {
+  constexpr int NB = NCL * NCL;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t blk = idx / NB;
+  const int e = (int)(idx % NB);
+  if (blk >= (size_t)(V + nub)) return;
+  const double v = pack[idx];
+  if (blk < (size_t)V) { Sval[(size_t)diag_pos[blk] * NB + e] = v; return; }
+  const int b = (int)(blk - V);
+  Sval[(size_t)ub_pos[b] * NB + e] = v;
+  Sval[(size_t)ub_pos_t[b] * NB + (e % NCL) * NCL + e / NCL] = v;
 }
 
 // ---- block-Jacobi preconditioning applied as a SYMMETRIC SCALING of the reduced system --------------------------------

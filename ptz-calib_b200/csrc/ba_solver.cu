@@ -297,7 +297,9 @@ struct BaSolver : BaSolverBase {
   DevBuf<double> d_gabs;
   size_t viewred_n = 0;
   // views into d_sys (all-reduced once per linear solve): Sval | rhs(n)
-  double *p_Sval, *p_rhs, *p_Sbb, *p_Cw;
+  double *p_Sval, *p_rhs, *p_Sbb, *p_Cw, *p_Spack;
+  bool s_packed = false;
+  DevBuf<double> d_Sfull;
   size_t sys_n = 0;
   // what the host reads once per step attempt.  The block is pinned AND device-mapped: k_publish writes it straight over PCIe and
   // raises `seq` behind a system-scope fence; the host spins on `seq` instead of paying three cudaMemcpyAsync + a stream
@@ -728,7 +730,7 @@ struct BaSolver : BaSolverBase {
       if (const char* e = getenv("PTZ_OW_PER")) ow_per = std::min(kResjacMaxPer, std::max(1, atoi(e)));
       ow_grid = std::max(1, cdiv(ds.nchunks, ow_per));
     }
-    d_part.alloc((size_t)std::max(ds.nchunks, 1) * D::NPART, stream);
+    d_part.alloc((size_t)std::max(ds.nchunks, 1) * D::NPART, stream); d_part.zero(s);  // (only the last chunk of a view-run is ever written)
     viewred_n = (size_t)V * NCL * NCL + (size_t)V * NCL + V + (size_t)ncpl * NCL * nb + (size_t)nb * nb + nbt + 2 + (size_t)nf * (NCL + nb + 1);
     d_viewred.alloc(viewred_n, stream);
     d_viewred.zero(s);
@@ -744,19 +746,24 @@ struct BaSolver : BaSolverBase {
     d_diag_ray.alloc(3 * (size_t)std::max(P, 1), stream); d_diag_cam.alloc((size_t)V * NCL, stream); d_diag_b.alloc(std::max(nbt, 1), stream);
     d_Lt.alloc((size_t)std::max(P, 1) * 10, stream);
     d_What.alloc((size_t)std::max(M, 1) * D::WS, stream); d_What.zero(s);
-    d_q.alloc((size_t)std::max(ds.nchunks, 1) * (D::NU + NCL), stream);  // chunk partials of sum What What^T, sum q
+    d_q.alloc((size_t)std::max(ds.nchunks, 1) * (D::NU + NCL), stream); d_q.zero(s);  // chunk partials of sum What What^T, sum q (likewise)
     // d_sys (all-reduced once per linear solve): Sval | rhs(n) | Sbb(nb^2) | PTZRayDistDisp: the working strips Cw (they carry
     // rank-local Schur terms of the rays)
-    sys_n = (size_t)ds.nnzb * NCL * NCL + n + (size_t)nb * nb + (kDisp ? (size_t)ncpl * NCL * nb : 0);
+    // Sharded problem: S goes through the all-reduce packed (diagonal blocks + upper blocks once, k_unpack_S), the block-CSR copy
+    // the later kernels work on is a buffer of its own
+    s_packed = g_nccl.world > 1;
+    const size_t s_reduced = s_packed ? (size_t)(V + ds.nub) * NCL * NCL : (size_t)ds.nnzb * NCL * NCL;
+    sys_n = s_reduced + n + (size_t)nb * nb + (kDisp ? (size_t)ncpl * NCL * nb : 0);
     d_sys.alloc(sys_n, stream);
-    p_Sval = d_sys.p; p_rhs = p_Sval + (size_t)ds.nnzb * NCL * NCL; p_Sbb = p_rhs + n;
+    if (s_packed) { d_Sfull.alloc((size_t)ds.nnzb * NCL * NCL, stream); p_Sval = d_Sfull.p; } else p_Sval = d_sys.p;
+    p_Spack = d_sys.p; p_rhs = d_sys.p + s_reduced; p_Sbb = p_rhs + n;
     p_Cw = kDisp ? p_Sbb + (size_t)nb * nb : d_Cw.p;
     d_Linv.alloc((size_t)V * NCL * NCL, stream); d_Linv_b.alloc(kMaxBorder * kMaxBorder, stream);
     d_Cs.alloc((size_t)std::max(ncpl, 1) * NCL * std::max(nb, 1), stream);
     {
       // deflated CG (camera-only reduced systems of some size; PTZ_CG_DEFLATE=0 switches it off for A/B measurements)
       const char* e = getenv("PTZ_CG_DEFLATE");
-      defl_enabled = (!e || atoi(e) != 0) && nb == 0 && V >= 64;
+      defl_enabled = (!e || atoi(e) != 0) && nb == 0 && V >= 64;  // (tried V >= 48 for cfg 2, V = 60: the deflated solves get rejected and redone there, 965 -> 1480 us per LM iteration)
       have_W = false;
       if (defl_enabled) {
         const size_t nk = (size_t)V * NCL * kDeflK;
@@ -952,13 +959,19 @@ struct BaSolver : BaSolverBase {
       PTZ_TIMED(PTZ_K_TRACK_SOLVE, {
         k_track_factor<<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, d_Vh.p, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_ray.p, d_Lt.p, d_fail.p);
         if (ds.nchunks > 0)
-          k_obs_what<NCL><<<ow_grid, kChunk, ObsWhatSmem<NCL>::kBytes, s>>>(ds.nchunks, ow_per, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_track.p, d_recA.p, d_recF.p, d_Lt.p,
+          k_obs_what<NCL><<<ow_grid, kChunk, ObsWhatSmem<NCL>::kBytes, s>>>(ds.nchunks, ow_per, ds.chunk_view.p, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_track.p, d_recA.p, d_recF.p, d_Lt.p,
                                                                           d_What.p, d_q.p);
         if (kDisp) k_disp_track<NCL><<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_recA.p, d_recd.p, d_Lt.p, d_Wdh.p);
       });
-    if (d_ub_list.n) PTZ_CUDA(cudaMemsetAsync(p_Sval, 0, (size_t)ds.nnzb * NCL * NCL * sizeof(double), s));  // blocks without local pairs stay zero
+    if (d_ub_list.n) PTZ_CUDA(cudaMemsetAsync(s_packed ? p_Spack : p_Sval, 0, (size_t)(s_packed ? V + ds.nub : ds.nnzb) * NCL * NCL * sizeof(double), s));  // blocks without local pairs stay zero
+    // stage-2 targets: the block-CSR S, or (sharded) the packed buffer the all-reduce carries
+    const int* t_diag = s_packed ? nullptr : ds.diag_pos.p;
+    const int* t_ub = s_packed ? nullptr : ds.ub_pos.p;
+    const int* t_ubt = s_packed ? nullptr : ds.ub_pos_t.p;
+    double* t_Sd = s_packed ? p_Spack : p_Sval;
+    double* t_So = s_packed ? p_Spack + (size_t)V * NCL * NCL : p_Sval;
     PTZ_TIMED(PTZ_K_SCHUR_DIAG, k_schur_diag<NCL><<<cdiv(V * (D::NU + NCL), 128), 128, 0, s>>>(V, ds.view_chunk_off.p, d_q.p, p_U, p_g, mu, refresh, opt.min_lm_diagonal,
-                                                                               opt.max_lm_diagonal, own, d_diag_cam.p, ds.diag_pos.p, p_Sval, p_rhs, ns > 0 ? d_grp_of.p : nullptr));
+                                                                               opt.max_lm_diagonal, own, d_diag_cam.p, t_diag, t_Sd, p_rhs, ns > 0 ? d_grp_of.p : nullptr));
     if (ds.nub > 0) {
       bool half = false;
       if constexpr (NCL == 4) {
@@ -966,15 +979,15 @@ struct BaSolver : BaSolverBase {
         const int* list = d_ub_list.n ? d_ub_list.p : nullptr;
         if (od_group == 16)
           PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, (k_schur_offdiag_sub<NCL, 16><<<cdiv(std::max(nub_local, 1), 16), 256, 0, s>>>(
-                                             nub_local, list, ds.pair_off.p, ds.pair_a.p, ds.pair_b.p, d_What.p, ds.ub_pos.p, ds.ub_pos_t.p, p_Sval)));
+                                             nub_local, list, ds.pair_off.p, ds.pair_a.p, ds.pair_b.p, d_What.p, t_ub, t_ubt, t_So)));
         else if (od_group == 8)
           PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, (k_schur_offdiag_sub<NCL, 8><<<cdiv(std::max(nub_local, 1), 32), 256, 0, s>>>(
-                                             nub_local, list, ds.pair_off.p, ds.pair_a.p, ds.pair_b.p, d_What.p, ds.ub_pos.p, ds.ub_pos_t.p, p_Sval)));
+                                             nub_local, list, ds.pair_off.p, ds.pair_a.p, ds.pair_b.p, d_What.p, t_ub, t_ubt, t_So)));
       }
       if (!half)
         PTZ_TIMED(PTZ_K_SCHUR_OFFDIAG, k_schur_offdiag<NCL><<<cdiv(std::max(nub_local, 1), 8), 256, 0, s>>>(nub_local, d_ub_list.n ? d_ub_list.p : nullptr, ds.pair_off.p,
-                                                                                                            ds.pair_a.p, ds.pair_b.p, d_What.p, ds.ub_pos.p,
-                                                                                                            ds.ub_pos_t.p, p_Sval));
+                                                                                                            ds.pair_a.p, ds.pair_b.p, d_What.p, t_ub,
+                                                                                                            t_ubt, t_So));
     }
     if (nb > 0)
       k_border_system<<<1, 128, 0, s>>>(nb, nf, p_Hbb, p_Hrf, p_Hff, p_gb, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, own, d_diag_b.p, d_hinv.p,
@@ -986,6 +999,8 @@ struct BaSolver : BaSolverBase {
     PTZ_CUDA(cudaGetLastError());
     if (g_nccl.world > 1) {
       PTZ_TIMED(PTZ_K_ALLREDUCE, allreduce_sum(d_sys.p, sys_n, s));
+      k_unpack_S<NCL><<<cdiv((int)((size_t)(V + ds.nub) * NCL * NCL), 256), 256, 0, s>>>(V, ds.nub, p_Spack, ds.diag_pos.p, ds.ub_pos.p, ds.ub_pos_t.p, p_Sval);
+      PTZ_CUDA(cudaGetLastError());
     }
     if (nf > 0) {  // fy elimination, camera side (replicated: after the reduce)
       k_fy_eliminate<NCL><<<cdiv(nf, 64), 64, 0, s>>>(nf, nb, d_ann_view.p, d_ann_strip.p, p_Cf, p_Hrf, p_gb + nb, d_hinv.p, kDisp ? p_Cw : p_C, p_Cw,

@@ -540,7 +540,50 @@ def bench_small(args):
                              ms_per_solve_device=round(ms / reps, 3), ms_per_solve_e2e=round(1e3 * dt, 3), converged=bool(conv),
                              kernel_launches_per_iteration=round((b["launches_total"] - a["launches_total"]) / max(its, 1), 1))
         out[name] = dict(views=p.V, tracks=p.P, observations=p.M, annotated_points=p.A, **rows)
+    try:
+        out["iba_flow"] = bench_iba()
+    except Exception as e:  # noqa: BLE001  (no compiler on the box, ...: the line still goes out)
+        out["iba_flow"] = dict(error=str(e)[:200])
     return out
+
+
+def bench_iba():
+    """The whole incremental flow (run_ptzba_synthetic.sh: PtzIncrementalOptimizer from unknown cameras -- seed pair, batched KRT
+    registrations, a global BA whenever the model grew by 10 %) through the C++ adaptor, on cfg-1-shaped rings with exhaustive pairwise
+    matches.  One process per size: an untimed run first (CUDA start-up), then the timed one."""
+    import re
+    import struct
+    import tempfile
+
+    from ptz_calib_b200 import lib, synth
+
+    d = tempfile.mkdtemp()
+    exe = os.path.join(d, "iba_check")
+    so_dir = os.path.dirname(lib.SO_PATH)
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", os.path.join(ROOT, "tests", "cpp", "iba_check.cpp"), "-o", exe, "-L" + so_dir, "-lptzcalib_b200", "-ldl",
+                    "-Wl,-rpath," + so_dir], check=True, capture_output=True)
+    rows = []
+    for scale in (1.0, 2.0):
+        p = synth.make_config(1, scale=scale)
+        cams = np.zeros((p.V, 21))
+        cams[:, 0] = cams[:, 1] = p.gt["f"]
+        cams[:, 2:4] = p.gt["c"]
+        cams[:, 4:13] = p.gt["R"].reshape(p.V, 9)
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        with open(fin, "wb") as f:
+            f.write(struct.pack("4i", p.V, p.M, 100, 1))
+            for a in (cams, p.obs_view, p.obs_track, p.obs_uv):
+                f.write(np.ascontiguousarray(a).tobytes())
+        r = subprocess.run([exe, fin, fout], capture_output=True, text=True, timeout=600, env=dict(os.environ, IBA_WARMUP="1"))
+        m = re.search(r"iba ok=(\d) registered=(\d+)/(\d+) global BAs=(\d+) reloc batches=(\d+) \((\d+) queries\) reproj=([0-9.]+) pairs=(\d+) matches=(\d+)\s+([0-9.]+) s", r.stdout)
+        c = re.search(r"cold run[^:]*: ([0-9.]+) s", r.stdout)
+        if not m:
+            rows.append(dict(views=p.V, error=(r.stdout + r.stderr)[-200:]))
+            continue
+        rows.append(dict(views=p.V, matches=int(m.group(9)), image_pairs=int(m.group(8)), ok=bool(int(m.group(1))), registered=int(m.group(2)),
+                         global_bundle_adjustments=int(m.group(4)), registration_batches=int(m.group(5)), krt_solves=int(m.group(6)),
+                         final_reproj_error_px=float(m.group(7)), seconds=float(m.group(10)), seconds_cold_process=float(c.group(1)) if c else None))
+    return rows
 
 
 def bench_tracks(args, prob):

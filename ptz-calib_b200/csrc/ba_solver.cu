@@ -291,7 +291,7 @@ struct BaSolver : BaSolverBase {
   DevBuf<float2> d_pts_uv;
   DevBuf<int> d_pts_view, d_ann_view, d_ann_off, d_ann_idx, d_fail, d_pcg_info, d_cpl_view, d_cpl_idx, d_ann_strip;
   DevBuf<double> d_recd, d_dpart, d_Wdh, d_Cw, d_hinv, d_dispp[2], d_disp_init;
-  DevBuf<int> d_cg_order;
+  DevBuf<int> d_cg_order, d_t_view;
   // views into d_viewred (all-reduced once per Jacobian evaluation): U | g | cost_view | C | Hbb | gb | cost_pts(2)
   double *p_U, *p_g, *p_cost_view, *p_C, *p_Hbb, *p_gb, *p_cost_pts, *p_gabs, *p_gabs_b, *p_Cf, *p_Hrf, *p_Hff;
   DevBuf<double> d_gabs;
@@ -741,6 +741,8 @@ struct BaSolver : BaSolverBase {
     d_gabs.zero(s);
     p_gabs = d_gabs.p; p_gabs_b = d_gabs.p + (size_t)V * NCL;
     d_Vh.alloc((size_t)std::max(P, 1) * 10, stream);
+    d_t_view.alloc(std::max(M, 1), stream);
+    if (M > 0) k_gather_int<<<cdiv(M, 256), 256, 0, s>>>(M, ds.t_obs.p, ds.o_view.p, d_t_view.p);
     nblk_ray = std::max(cdiv(P, 128), 1); nblk_cam = std::max(cdiv(V, 128), 1);
     d_gmax_part.alloc(nblk_ray, stream); d_gmax_part.zero(s);
     d_diag_ray.alloc(3 * (size_t)std::max(P, 1), stream); d_diag_cam.alloc((size_t)V * NCL, stream); d_diag_b.alloc(std::max(nbt, 1), stream);
@@ -1176,7 +1178,7 @@ struct BaSolver : BaSolverBase {
     const int nxt = cur ^ 1;
     const double* y = d_y.p;
     if (P > 0)
-      PTZ_TIMED(PTZ_K_TRACK_BACKSUB, k_track_backsub<NCL><<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, ds.o_view.p, d_What.p, y, d_Lt.p, d_Vh.p, d_diag_ray.p,
+      PTZ_TIMED(PTZ_K_TRACK_BACKSUB, k_track_backsub<NCL><<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_t_view.p, d_What.p, y, d_Lt.p, d_Vh.p, d_diag_ray.p,
                                                                                    mu, d_trk[cur].p, d_trk[nxt].p, d_part3_ray.p, kDisp ? d_Wdh.p : nullptr,
                                                                                    y + (size_t)V * NCL + (kDisp ? bo_disp : 0)));
     PTZ_TIMED(PTZ_K_CAM_UPDATE, k_cam_update<TYPE><<<nblk_cam, 128, 0, s>>>(V, y, d_scale_cam.p, p_g, d_diag_cam.p, mu, ds.view_active.p, d_intr[cur].p,

@@ -1525,6 +1525,11 @@ static int check_problem(const ptzba_problem* p) {
     if (p->obs_view[k] < 0 || p->obs_view[k] >= p->num_views || p->obs_track[k] < 0 || p->obs_track[k] >= p->num_tracks) return PTZ_ERR_INVALID;
   for (int k = 0; k < p->num_pts3d; ++k)
     if (p->pt_view[k] < 0 || p->pt_view[k] >= p->num_views) return PTZ_ERR_INVALID;
+  if (p->shared_ic_id && p->num_pts3d > 0) {  // shared intrinsics blocks are built for the 2d-2d terms only (ba_border.cuh)
+    for (int i = 0; i < p->num_views; ++i)
+      for (int j = 0; j < i; ++j)
+        if (p->shared_ic_id[i] == p->shared_ic_id[j]) { set_last_error("shared intrinsics together with 2d-3d terms are not built"); return PTZ_ERR_UNSUPPORTED; }
+  }
   return PTZ_OK;
 }
 

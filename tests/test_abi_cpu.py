@@ -60,9 +60,16 @@ def test_invalid_arguments_are_rejected_without_touching_the_gpu():
     c.obs_view = bad.ctypes.data_as(C.POINTER(C.c_int32))
     assert L.ptzba_solve(C.byref(c), C.byref(o), C.byref(r)) == abi.PTZ_ERR_INVALID
     c = p.to_c()
-    ids = np.arange(p.V, dtype=np.int32)[::-1].copy()  # SetSharedIntrinsics with a non-identity map is not built
+    # SetSharedIntrinsics: a permutation of distinct ids shares nothing and is accepted (then fails for lack of a device here);
+    # shared blocks together with 2d-3d points are the one combination that is not built
+    ids = np.arange(p.V, dtype=np.int32)[::-1].copy()
     c.shared_ic_id = ids.ctypes.data_as(C.POINTER(C.c_int32))
-    assert L.ptzba_solve(C.byref(c), C.byref(o), C.byref(r)) == abi.PTZ_ERR_UNSUPPORTED
+    assert L.ptzba_solve(C.byref(c), C.byref(o), C.byref(r)) == abi.PTZ_ERR_NO_DEVICE
+    q = synth.make_config(1, scale=0.2, num_pts3d=6)
+    q.shared_ic_id = np.zeros(q.V, np.int32)
+    cq = q.to_c()
+    rq, _, _ = ptz.problem.alloc_ba_result(q)
+    assert L.ptzba_solve(C.byref(cq), C.byref(o), C.byref(rq)) == abi.PTZ_ERR_UNSUPPORTED
     c.factor_type = 7
     assert L.ptzba_solve(C.byref(c), C.byref(o), C.byref(r)) == abi.PTZ_ERR_INVALID
 

@@ -494,14 +494,14 @@ def bench_reloc(args, rank, world, barrier, allmax, allsum, counters=None):
         c = counters_for(counters, "k_reloc")
         if c and c.get("fp64_flops"):
             nq = min(args.reloc_queries, 20000)  # queries of the side run (same generator, a prefix-sized batch)
-            fl_q = c["fp64_flops"] / nq
+            fl_q = c["fp64_flops"] * c["launches"] / nq  # (the batch runs as several slices = launches: sum them)
             out["fp64_flops_per_query"] = round(fl_q, 1)
             out["fp64_flops_per_match_per_lm_iteration"] = round(fl_q / (b.N / max(b.B, 1)) / max(iters, 1e-9), 1)
             ach = fl_q * b.B / (ms * 1e-3) / 1e9
             out["roofline"] = dict(kernel="k_reloc<F>", bound="fp64 pipe", achieved=round(ach, 1), peak=out.get("fp64_peak_gflops_measured"), unit="GFLOP/s",
                                    frac=round(ach / gf.value, 4) if gf.value > 0 else None,
                                    hbm_gbs=round((b.N * 16 + b.B * (42 + 39) * 8) / (ms * 1e-3) / 1e9, 1),
-                                   traffic=c["dram_bytes"] * b.B // max(nq, 1))
+                                   traffic=c["dram_bytes"] * c["launches"] * b.B // max(nq, 1))
     return out
 
 

@@ -107,6 +107,9 @@ __global__ void __launch_bounds__(kChunk, PTZ_RJ_MINB) k_resjac(int nchunks, int
   if (n <= 0) return;
   if (t < n) { s_view[t] = chunk_view[c0 + t]; s_begin[t] = chunk_begin[c0 + t]; s_cnt[t] = chunk_cnt[c0 + t]; }
   if (t == 0) { mbar_init(&vbar[0], 1); mbar_init(&vbar[1], 1); mbar_init_fence(); }
+#ifdef PTZ_L2_HINTS
+  const unsigned long long pol_stream = l2_evict_first_policy();
+#endif
   __syncthreads();
   auto stage_view = [&](int k) {  // bulk copy of chunk k's view table into buffer k & 1 (thread 0 only)
     const int b = k & 1;
@@ -192,8 +195,13 @@ __global__ void __launch_bounds__(kChunk, PTZ_RJ_MINB) k_resjac(int nchunks, int
     bulk_store_fence();  // this thread's shared-memory writes become visible to the TMA engine ...
     __syncthreads();     // ... and all of them are done
     if (t == 0) {        // the chunk's records are contiguous in both arrays: two bulk stores
+#ifdef PTZ_L2_HINTS
+      bulk_store_hint(recA + (size_t)begin * D::RA, sA, (unsigned)(cnt * D::RA * 8), pol_stream);
+      bulk_store_hint(recF + (size_t)begin * D::RF, sF, (unsigned)(cnt * D::RF * 8), pol_stream);
+#else
       bulk_store(recA + (size_t)begin * D::RA, sA, (unsigned)(cnt * D::RA * 8));
       bulk_store(recF + (size_t)begin * D::RF, sF, (unsigned)(cnt * D::RF * 8));
+#endif
       bulk_commit();
     }
     // (one reduction per CHUNK here: keeping the 15 partial sums in registers across the chunks of a view, as k_obs_what does, costs
@@ -359,14 +367,21 @@ __global__ void __launch_bounds__(kChunk, PTZ_OW_MINB) k_obs_what(int nchunks, i
     const double2* ga = reinterpret_cast<const double2*>(recA + (size_t)s_begin[k] * D::RA);
     const double2* gf = reinterpret_cast<const double2*>(recF + (size_t)s_begin[k] * D::RF);
     const int cnt = s_cnt[k];
+#ifdef PTZ_L2_HINTS
+    const unsigned long long pol_stream = l2_evict_first_policy();
+#define PTZ_OW_CP(d, g) cp_async16_hint(d, g, pol_stream)
+#else
+#define PTZ_OW_CP(d, g) cp_async16(d, g)
+#endif
     for (int gch = t; gch < cnt * 4; gch += kChunk) {
       const int tt = gch >> 2, pch = gch & 3;
-      cp_async16(&dst[tt * RC + chunk_swz<RC>(tt, pch)], ga + gch);
+      PTZ_OW_CP(&dst[tt * RC + chunk_swz<RC>(tt, pch)], ga + gch);
     }
     for (int gch = t; gch < cnt * NCL; gch += kChunk) {
       const int tt = gch / NCL, pch = 4 + gch % NCL;
-      cp_async16(&dst[tt * RC + chunk_swz<RC>(tt, pch)], gf + gch);
+      PTZ_OW_CP(&dst[tt * RC + chunk_swz<RC>(tt, pch)], gf + gch);
     }
+#undef PTZ_OW_CP
     cp_async_commit();
   };
   double2 l01 = make_double2(1, 0), l23 = make_double2(1, 0), l45 = make_double2(0, 1), l67 = make_double2(0, 0), l89 = make_double2(0, 0);

@@ -272,6 +272,21 @@ __device__ __forceinline__ void bulk_load(void* smem, const void* gmem, unsigned
 __device__ __forceinline__ void bulk_store(void* gmem, const void* smem, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem), "r"(smem_u32(smem)), "r"(bytes) : "memory");
 }
+// L2 residency: data that is streamed once (record blocks) is marked evict-first, so that it does not push the small gathered
+// arrays of the same kernel (track records, per-track Cholesky factors: 25-32 MB) out of the 126 MB L2
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_store_hint(void* gmem, const void* smem, unsigned bytes, unsigned long long pol) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem), "r"(smem_u32(smem)), "r"(bytes), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16_hint(void* smem, const void* gmem, unsigned long long pol) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void bulk_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }  // sources may be reused

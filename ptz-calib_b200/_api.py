@@ -159,12 +159,13 @@ class PTZRayOptimizer:
 
     @classmethod
     def from_matches(cls, matches: Matches, views: Views, cams21, max_iter: int, factor_type=abi.PTZ_BA_PTZRAY, min_track_length=4,
-                     pt_uv=None, pt_xyz=None, pt_view=None, tlw0=None):
+                     pt_uv=None, pt_xyz=None, pt_view=None, tlw0=None, shared_ic_ids=None, reference_track_ids=True):
         """The reference's constructor arguments (features = `views`, matches_info = `matches`, cameras = krt21 rows, cam_ids =
         views.is_candidate): FindTracks (ptzray_optimizer.cc:537-552) and the residual-block loop (:801-848) run on the GPU through
         ptztracks_build / ptztracks_flatten; the 2d-3d annotations are given per ORIGINAL image index (pt_view)."""
         cams21 = f64(cams21).reshape(-1, 21)
-        tr = build_tracks(matches, min_track_length)
+        # reference_track_ids: ids and order of the reference's sequential UnionFind (as the C++ adaptor), else the canonical device ids
+        tr = build_tracks(matches, min_track_length, reference_track_ids=reference_track_ids)
         obs = flatten_tracks(tr, views)
         cand = np.nonzero(views.is_candidate)[0]
         dense = -np.ones(len(views.is_candidate), np.int64)
@@ -186,11 +187,18 @@ class PTZRayOptimizer:
                 raise ValueError("from_matches: annotated points need tlw0 (the EPnP initialisation of T_l_w lives in the C++ adaptor)")
             keep = dense[np.asarray(pt_view)] >= 0
             kw = dict(pt_uv=f32(pt_uv)[keep], pt_xyz=f64(pt_xyz)[keep], pt_view=dense[np.asarray(pt_view)][keep].astype(np.int32), tlw0=tlw0)
+        if shared_ic_ids is not None:  # SetSharedIntrinsics (:497-505): one id per ORIGINAL image; a wrong length is ignored as there
+            if len(shared_ic_ids) == len(views.is_candidate):
+                kw["shared_ic_id"] = np.asarray(shared_ic_ids, dtype=np.int64)[cand].astype(np.int32)
         prob = BAProblem(factor_type=factor_type, intr=intr, ext=ext, obs_uv=obs.obs_uv, obs_view=obs.obs_view, obs_track=obs.obs_track,
                          track_weight=obs.track_weight, **kw)
         self = cls(prob, max_iter)
         self.tracks, self.observations, self.view_of = tr, obs, cand
         return self
+
+    def SetSharedIntrinsics(self, shared_ic_ids):  # ptzray_optimizer.cc:497-505: one id per view of the problem; a wrong length is ignored
+        if len(shared_ic_ids) == self.prob.V:
+            self.prob.shared_ic_id = np.asarray(shared_ic_ids, dtype=np.int32)
 
     def CheckValid(self) -> bool:  # ptzray_optimizer.cc:515-535
         p = self.prob

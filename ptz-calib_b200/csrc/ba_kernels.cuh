@@ -283,6 +283,175 @@ __global__ void k_track_accum(int P, const int* __restrict__ t_off, const int* _
   }
 }
 
+// ---- by-track passes with ONE LANE PER (track, observation) ENTRY (opt-in experiment, PTZ_BYTRACK_WARP=1: see ba_solver.cu) ----
+// The by-track list (t_off / t_obs) is cut into groups: group g = the tracks whose first entry lies in [32 g, 32 g + 32).  A warp takes a
+// group: every lane gathers ONE record (all loads of a round independent: 32 gathers in flight per warp instead of 4 per thread), the
+// per-track sums are formed by a segmented shuffle reduction (entries of a track are neighbours; fixed tree order: bit-reproducible),
+// and the lane at the head of each segment finishes the track.  A group has at most 32 + (longest track - 1) entries: the tail
+// of its last track is a second round whose partial sums are carried.  The default kernels run one THREAD per track, four records in
+// flight: k_track_accum 62 us, k_track_backsub 87 us against 36 / 55 us for a plain random gather of the same records.  This
+// version measured 110 / 131 us: too little work per warp for the length of its dependent chain.
+constexpr int kNoGroup = 0x7f7f7f7f;  // (what cudaMemset(0x7f) leaves: larger than any entry index)
+__global__ void k_entry_tracks(int P, const int* __restrict__ t_off, int* __restrict__ t_trk, int* __restrict__ grp_e0) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int b = t_off[p], e = t_off[p + 1];
+  for (int i = b; i < e; ++i) t_trk[i] = p;
+  // first entry of the first non-empty track that starts in group b / 32 (entries ascend with p: the minimum wins)
+  if (e > b) atomicMin(grp_e0 + (b >> 5), b);
+}
+// reduce NV values over runs of equal `key` among neighbouring lanes; afterwards the first lane of a run holds the run's sum
+template <int NV>
+__device__ __forceinline__ void seg_reduce(double (&v)[NV], int key, int lane) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int k2 = __shfl_down_sync(0xffffffffu, key, off);
+    const bool take = lane + off < 32 && k2 == key;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const double t = __shfl_down_sync(0xffffffffu, v[j], off);
+      if (take) v[j] += t;
+    }
+  }
+}
+// V = sum E^T E (lower 6), h = sum E^T r per track; gradient max-norm partial per warp
+__global__ void __launch_bounds__(256) k_track_accum_w(int G, int M, const int* __restrict__ grp_e0, const int* __restrict__ t_trk, const int* __restrict__ t_obs,
+                                                       const double* __restrict__ recA, const double* __restrict__ trk, double* __restrict__ Vh,
+                                                       double* __restrict__ gmax_part) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (g >= G) return;
+  double gm = 0.0;
+  const int e0 = grp_e0[g];
+  if (e0 != kNoGroup) {
+    int gg = g + 1;
+    while (gg < G && grp_e0[gg] == kNoGroup) ++gg;
+    const int e1 = gg < G ? grp_e0[gg] : M;
+    double carry[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) carry[j] = 0.0;
+    int carry_trk = -1;
+    for (int base = e0; base < e1; base += 32) {
+      const int e = base + lane;
+      const bool valid = e < e1;
+      const int key = valid ? t_trk[e] : -2 - lane;
+      double v[9];
+#pragma unroll
+      for (int j = 0; j < 9; ++j) v[j] = 0.0;
+      if (valid) {
+        const double* q = recA + (size_t)t_obs[e] * 8;
+        double r0, r1, a0, a1, a2, b0, b1, b2;
+        ld256(q, r0, r1, a0, a1);
+        ld256(q + 4, a2, b0, b1, b2);
+        v[0] = a0 * a0 + b0 * b0; v[1] = a1 * a0 + b1 * b0; v[2] = a1 * a1 + b1 * b1;
+        v[3] = a2 * a0 + b2 * b0; v[4] = a2 * a1 + b2 * b1; v[5] = a2 * a2 + b2 * b2;
+        v[6] = a0 * r0 + b0 * r1; v[7] = a1 * r0 + b1 * r1; v[8] = a2 * r0 + b2 * r1;
+      }
+      seg_reduce<9>(v, key, lane);
+      const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+      const bool head = valid && (lane == 0 || prev != key);
+      if (head && lane == 0 && key == carry_trk) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) v[j] += carry[j];
+      }
+      // does the last track of this round go on in the next one?
+      const int last_key = __shfl_sync(0xffffffffu, key, 31);
+      const bool goes_on = base + 32 < e1 && last_key >= 0 && t_trk[base + 32] == last_key;
+      // the head of that track hands its sum to the next round instead of writing it
+      const bool is_carry = head && goes_on && key == last_key;
+      const unsigned cm = __ballot_sync(0xffffffffu, is_carry);
+      if (cm) {
+        const int src = __ffs(cm) - 1;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) carry[j] = __shfl_sync(0xffffffffu, v[j], src);
+        carry_trk = last_key;
+      }
+      if (head && !is_carry) {
+        double* o = Vh + (size_t)key * 10;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) o[j] = v[j];
+        o[9] = 0.0;
+        const double* t = trk + (size_t)key * kTrk;
+        gm = fmax(gm, fmax(fabs(v[6] / t[4]), fmax(fabs(v[7] / t[5]), fabs(v[8] / t[6]))));
+      }
+    }
+  }
+  gm = warp_max(gm);
+  if (lane == 0) gmax_part[g] = gm;
+}
+// back-substitution of the rays, same scheme: per entry  c = What_o^T y_view(o), summed per track; the head lane solves
+// L^T y_p = t - c, writes the candidate ray; partial sums (model cost change, |step|^2, |x_cand|^2) per warp
+template <int NCL>
+__global__ void __launch_bounds__(256) k_track_backsub_w(int G, int M, const int* __restrict__ grp_e0, const int* __restrict__ t_trk, const int* __restrict__ t_obs,
+                                                         const int* __restrict__ t_view, const double* __restrict__ What, const double* __restrict__ y,
+                                                         const double* __restrict__ Lt, const double* __restrict__ Vh, const double* __restrict__ diag_ray,
+                                                         double mu, const double* __restrict__ trk, double* __restrict__ trk_cand,
+                                                         double* __restrict__ part3, const double* __restrict__ Wdh /* or nullptr */,
+                                                         const double* __restrict__ ydisp) {
+  typedef Dims<NCL> D;
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (g >= G) return;
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+  const int e0 = grp_e0[g];
+  if (e0 != kNoGroup) {
+    int gg = g + 1;
+    while (gg < G && grp_e0[gg] == kNoGroup) ++gg;
+    const int e1 = gg < G ? grp_e0[gg] : M;
+    double carry[3] = {0.0, 0.0, 0.0};
+    int carry_trk = -1;
+    for (int base = e0; base < e1; base += 32) {
+      const int e = base + lane;
+      const bool valid = e < e1;
+      const int key = valid ? t_trk[e] : -2 - lane;
+      double v[3] = {0.0, 0.0, 0.0};
+      if (valid) {
+        const double* w4 = What + (size_t)t_obs[e] * D::WS;
+        const double* yv = y + (size_t)t_view[e] * NCL;
+        double w[D::WS];
+#pragma unroll
+        for (int k = 0; k < D::WS / 4; ++k) ld256(w4 + 4 * k, w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+#pragma unroll
+        for (int a = 0; a < NCL; ++a) { const double ya = yv[a]; v[0] += w[3 * a] * ya; v[1] += w[3 * a + 1] * ya; v[2] += w[3 * a + 2] * ya; }
+      }
+      seg_reduce<3>(v, key, lane);
+      const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+      const bool head = valid && (lane == 0 || prev != key);
+      if (head && lane == 0 && key == carry_trk) { v[0] += carry[0]; v[1] += carry[1]; v[2] += carry[2]; }
+      const int last_key = __shfl_sync(0xffffffffu, key, 31);
+      const bool goes_on = base + 32 < e1 && last_key >= 0 && t_trk[base + 32] == last_key;
+      const bool is_carry = head && goes_on && key == last_key;
+      const unsigned cm = __ballot_sync(0xffffffffu, is_carry);
+      if (cm) {
+        const int src = __ffs(cm) - 1;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) carry[j] = __shfl_sync(0xffffffffu, v[j], src);
+        carry_trk = last_key;
+      }
+      if (head && !is_carry) {
+        const int p = key;
+        const double* lt = Lt + (size_t)p * 10;
+        const double* t = trk + (size_t)p * kTrk;
+        double b0 = lt[6] - v[0], b1 = lt[7] - v[1], b2 = lt[8] - v[2];
+        if (Wdh) {  // PTZRayDistDisp: - Wdh^T y_disp
+          const double* wd = Wdh + (size_t)p * 12;
+#pragma unroll
+          for (int a = 0; a < 3; ++a) { const double ya = ydisp[a]; b0 -= wd[3 * a] * ya; b1 -= wd[3 * a + 1] * ya; b2 -= wd[3 * a + 2] * ya; }
+        }
+        const double y2 = b2 / lt[5], y1 = (b1 - lt[4] * y2) / lt[2], y0 = (b0 - lt[1] * y1 - lt[3] * y2) / lt[0];
+        const double* vh = Vh + (size_t)p * 10;
+        const double* dg = diag_ray + 3 * (size_t)p;
+        acc0 += 0.5 * (y0 * (vh[6] + dg[0] / mu * y0) + y1 * (vh[7] + dg[1] / mu * y1) + y2 * (vh[8] + dg[2] / mu * y2));
+        const double c0 = t[0] + (-t[4] * y0), c1 = t[1] + (-t[5] * y1), c2 = t[2] + (-t[6] * y2);
+        double* tc = trk_cand + (size_t)p * kTrk;
+        tc[0] = c0; tc[1] = c1; tc[2] = c2;
+        acc1 += (t[0] - c0) * (t[0] - c0) + (t[1] - c1) * (t[1] - c1) + (t[2] - c2) * (t[2] - c2);
+        acc2 += c0 * c0 + c1 * c1 + c2 * c2;
+      }
+    }
+  }
+  acc0 = warp_sum(acc0); acc1 = warp_sum(acc1); acc2 = warp_sum(acc2);
+  if (lane == 0) { part3[3 * (size_t)g] = acc0; part3[3 * (size_t)g + 1] = acc1; part3[3 * (size_t)g + 2] = acc2; }
+}
+
 // Jacobi scaling, once at iteration 0: s = 1 / (1 + sqrt(column norm^2))      (TrustRegionMinimizer::EvaluateGradientAndJacobian)
 template <int NCL>
 __global__ void k_make_scales(int V, int P, const double* __restrict__ U, const double* __restrict__ Vh, double* __restrict__ scale_cam,

@@ -291,7 +291,8 @@ struct BaSolver : BaSolverBase {
   DevBuf<float2> d_pts_uv;
   DevBuf<int> d_pts_view, d_ann_view, d_ann_off, d_ann_idx, d_fail, d_pcg_info, d_cpl_view, d_cpl_idx, d_ann_strip;
   DevBuf<double> d_recd, d_dpart, d_Wdh, d_Cw, d_hinv, d_dispp[2], d_disp_init;
-  DevBuf<int> d_cg_order, d_t_view;
+  DevBuf<int> d_cg_order, d_t_view, d_t_trk, d_grp_e0;
+  int track_groups = 0, nray_parts = 1;  // groups of 32 by-track entries (0: thread-per-track kernels); per-warp / per-CTA partial counts
   // views into d_viewred (all-reduced once per Jacobian evaluation): U | g | cost_view | C | Hbb | gb | cost_pts(2)
   double *p_U, *p_g, *p_cost_view, *p_C, *p_Hbb, *p_gb, *p_cost_pts, *p_gabs, *p_gabs_b, *p_Cf, *p_Hrf, *p_Hff;
   DevBuf<double> d_gabs;
@@ -740,11 +741,27 @@ struct BaSolver : BaSolverBase {
     d_gabs.alloc((size_t)V * NCL + std::max(nbt, 1), stream);
     d_gabs.zero(s);
     p_gabs = d_gabs.p; p_gabs_b = d_gabs.p + (size_t)V * NCL;
-    d_Vh.alloc((size_t)std::max(P, 1) * 10, stream);
+    d_Vh.alloc((size_t)std::max(P, 1) * 10, stream); d_Vh.zero(s);  // (tracks without observations are never written)
     d_t_view.alloc(std::max(M, 1), stream);
     if (M > 0) k_gather_int<<<cdiv(M, 256), 256, 0, s>>>(M, ds.t_obs.p, ds.o_view.p, d_t_view.p);
     nblk_ray = std::max(cdiv(P, 128), 1); nblk_cam = std::max(cdiv(V, 128), 1);
-    d_gmax_part.alloc(nblk_ray, stream); d_gmax_part.zero(s);
+    {
+      // by-track passes: a lane per (track, observation) entry, a warp per group of 32 entries (k_track_accum_w / k_track_backsub_w)
+      // OPT-IN (PTZ_BYTRACK_WARP=1): measured SLOWER than one thread per track at cfg 4 (k_track_accum 62 -> 110 us, k_track_backsub
+      // 87 -> 131 us, the 62 k per-warp partials cost k_scalars 25 us more): a warp that handles only 32 records pays the dependent chain
+      // group -> indices -> records -> head epilogue five times as often as a warp of 32 tracks.  Kept for the record and for a
+      // persistent, pipelined version; parity-tested (pytest with the variable set).
+      const char* e = getenv("PTZ_BYTRACK_WARP");
+      track_groups = (M > 0 && P > 0 && e && atoi(e) != 0) ? cdiv(M, 32) : 0;
+      if (track_groups > 0) {
+        d_t_trk.alloc(M, s); d_grp_e0.alloc(track_groups, s);
+        PTZ_CUDA(cudaMemsetAsync(d_grp_e0.p, 0x7f, (size_t)track_groups * sizeof(int), s));
+        k_entry_tracks<<<cdiv(P, 256), 256, 0, s>>>(P, ds.t_off.p, d_t_trk.p, d_grp_e0.p);
+        PTZ_CUDA(cudaGetLastError());
+      }
+      nray_parts = track_groups > 0 ? track_groups : nblk_ray;
+    }
+    d_gmax_part.alloc(nray_parts, stream); d_gmax_part.zero(s);
     d_diag_ray.alloc(3 * (size_t)std::max(P, 1), stream); d_diag_cam.alloc((size_t)V * NCL, stream); d_diag_b.alloc(std::max(nbt, 1), stream);
     d_Lt.alloc((size_t)std::max(P, 1) * 10, stream);
     d_What.alloc((size_t)std::max(M, 1) * D::WS, stream); d_What.zero(s);
@@ -792,7 +809,7 @@ struct BaSolver : BaSolverBase {
     d_cgp.alloc((size_t)n, stream); d_cgp.zero(s);
     d_y.alloc(n, stream); d_y.zero(s);
     d_pcg_res.alloc(2, stream); d_pcg_info.alloc(2, stream); d_fail.alloc(1, stream); d_fail.zero(s);
-    d_part3_ray.alloc(3 * (size_t)nblk_ray, stream); d_part3_ray.zero(s);
+    d_part3_ray.alloc(3 * (size_t)nray_parts, stream); d_part3_ray.zero(s);
     d_part3_cam.alloc(3 * (size_t)nblk_cam, stream); d_part3_b.alloc(3, stream); d_part3_b.zero(s);
     d_cost_part.alloc(2 * (size_t)std::max(ds.nchunks, 1), stream); d_cost_part.zero(s);
     d_scalars.alloc(S_COUNT, stream); d_scalars.zero(s);
@@ -850,7 +867,13 @@ struct BaSolver : BaSolverBase {
     PTZ_TIMED(PTZ_K_VIEW_FINALIZE,
               k_view_finalize<NCL><<<cdiv(V * D::NPART, 256), 256, 0, s>>>(V, ds.view_chunk_off.p, d_part.p, d_scale_cam.p, p_U, p_g, p_cost_view, p_gabs));
     if (P > 0)
-      PTZ_TIMED(PTZ_K_TRACK_ACCUM, k_track_accum<<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_recA.p, d_trk[cur].p, d_Vh.p, d_gmax_part.p));
+    {
+      if (track_groups > 0)
+        PTZ_TIMED(PTZ_K_TRACK_ACCUM, k_track_accum_w<<<cdiv(track_groups, 8), 256, 0, s>>>(track_groups, M, d_grp_e0.p, d_t_trk.p, ds.t_obs.p, d_recA.p, d_trk[cur].p,
+                                                                                            d_Vh.p, d_gmax_part.p));
+      else
+        PTZ_TIMED(PTZ_K_TRACK_ACCUM, k_track_accum<<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_recA.p, d_trk[cur].p, d_Vh.p, d_gmax_part.p));
+    }
     if (A > 0) {
       PtsArgs a;
       a.A = A; a.nav = nav; a.nb = nb; a.nf = nf;
@@ -909,7 +932,7 @@ struct BaSolver : BaSolverBase {
     add_sum(p_cost_pts, A > 0 ? 1 : 0, 1, S_COSTPTS_X);
     add_sum(p_cost_pts + 1, A > 0 ? 1 : 0, 1, S_RAWPTS_X);
     add_max(p_gabs, V * NCL, S_GMAX_CAM);
-    add_max(d_gmax_part.p, P > 0 ? nblk_ray : 0, S_GMAX_RAY);
+    add_max(d_gmax_part.p, P > 0 ? nray_parts : 0, S_GMAX_RAY);
     add_max(p_gabs_b, nbt, S_GMAX_B);
     PTZ_TIMED(PTZ_K_SCALARS, k_scalars<<<J.nsum + J.nmax, 1024, 0, stream>>>(J, d_scalars.p));
     PTZ_CUDA(cudaGetLastError());
@@ -1178,7 +1201,11 @@ struct BaSolver : BaSolverBase {
     cudaStream_t s = stream;
     const int nxt = cur ^ 1;
     const double* y = d_y.p;
-    if (P > 0)
+    if (P > 0 && track_groups > 0)
+      PTZ_TIMED(PTZ_K_TRACK_BACKSUB, k_track_backsub_w<NCL><<<cdiv(track_groups, 8), 256, 0, s>>>(
+                                         track_groups, M, d_grp_e0.p, d_t_trk.p, ds.t_obs.p, d_t_view.p, d_What.p, y, d_Lt.p, d_Vh.p, d_diag_ray.p, mu, d_trk[cur].p,
+                                         d_trk[nxt].p, d_part3_ray.p, kDisp ? d_Wdh.p : nullptr, y + (size_t)V * NCL + (kDisp ? bo_disp : 0)));
+    else if (P > 0)
       PTZ_TIMED(PTZ_K_TRACK_BACKSUB, k_track_backsub<NCL><<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_t_view.p, d_What.p, y, d_Lt.p, d_Vh.p, d_diag_ray.p,
                                                                                    mu, d_trk[cur].p, d_trk[nxt].p, d_part3_ray.p, kDisp ? d_Wdh.p : nullptr,
                                                                                    y + (size_t)V * NCL + (kDisp ? bo_disp : 0)));
@@ -1210,9 +1237,9 @@ struct BaSolver : BaSolverBase {
     auto add_sum = [&](const double* p, int cnt, int stride, int slot) { J.sum_ptr[J.nsum] = p; J.sum_n[J.nsum] = cnt; J.sum_stride[J.nsum] = stride; J.sum_slot[J.nsum] = slot; ++J.nsum; };
     add_sum(d_cost_part.p, ds.nchunks, 2, S_COST_CAND);
     add_sum(d_cost_part.p + 1, ds.nchunks, 2, S_RAW2_CAND);
-    add_sum(d_part3_ray.p, P > 0 ? nblk_ray : 0, 3, S_DM_RAY);
-    add_sum(d_part3_ray.p + 1, P > 0 ? nblk_ray : 0, 3, S_STEP2_RAY);
-    add_sum(d_part3_ray.p + 2, P > 0 ? nblk_ray : 0, 3, S_XN2_RAY);
+    add_sum(d_part3_ray.p, P > 0 ? nray_parts : 0, 3, S_DM_RAY);
+    add_sum(d_part3_ray.p + 1, P > 0 ? nray_parts : 0, 3, S_STEP2_RAY);
+    add_sum(d_part3_ray.p + 2, P > 0 ? nray_parts : 0, 3, S_XN2_RAY);
     add_sum(d_part3_cam.p, nblk_cam, 3, S_DM_CAM);
     add_sum(d_part3_cam.p + 1, nblk_cam, 3, S_STEP2_CAM);
     add_sum(d_part3_cam.p + 2, nblk_cam, 3, S_XN2_CAM);

@@ -250,17 +250,21 @@ __global__ void k_track_accum(int P, const int* __restrict__ t_off, const int* _
   if (p < P) {
     double v00 = 0, v10 = 0, v11 = 0, v20 = 0, v21 = 0, v22 = 0, h0 = 0, h1 = 0, h2 = 0;
     const int tb = t_off[p], te = t_off[p + 1];
-    for (int i = tb; i < te; i += 4) {
-      // four records in flight (indices clamped, extra ones weighted 0)
-      double2 rr[4], ea[4], eb[4], ec[4];
+#ifndef PTZ_TA_U
+#define PTZ_TA_U 6
+#endif
+    constexpr int U = PTZ_TA_U;
+    for (int i = tb; i < te; i += U) {
+      // U records in flight (indices clamped, extra ones weighted 0)
+      double2 rr[U], ea[U], eb[U], ec[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {  // a 64-byte record = two 256-bit loads
+      for (int u = 0; u < U; ++u) {  // a 64-byte record = two 256-bit loads
         const double* q = recA + (size_t)t_obs[min(i + u, te - 1)] * 8;
         ld256(q, rr[u].x, rr[u].y, ea[u].x, ea[u].y);
         ld256(q + 4, eb[u].x, eb[u].y, ec[u].x, ec[u].y);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         if (i + u >= te) break;
         const double a0 = ea[u].x, a1 = ea[u].y, a2 = eb[u].x, b0 = eb[u].y, b1 = ec[u].x, b2 = ec[u].y;
         v00 += a0 * a0 + b0 * b0; v10 += a1 * a0 + b1 * b0; v11 += a1 * a1 + b1 * b1;

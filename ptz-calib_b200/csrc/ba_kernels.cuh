@@ -1237,7 +1237,8 @@ struct CgArgs {
   int smem_defl_rows;      // rows per warp whose deflation data (W, AW, Z entries) live in shared memory as well
   int debug;               // timing experiments only (PTZ_CG_DEBUG): 1 = skip the sparse product, 2 = skip the grid barrier
   int max_iter; double tol;
-  int* out_info;           // [0] iterations, [1] status (0 converged, 1 hit cap, 2 breakdown, 3 peer timeout)
+  int* out_info;           // [0] iterations, [1] status (0 converged, 1 hit cap, 2 breakdown, 3 peer timeout, 4 deflated solve stagnated in the endgame)
+  const double* gamma0_ptr;  // plain kernel warm-started from a deflated solve's x: |b~|^2 to measure the residual against (else nullptr)
   double* out_res;         // [0] |r~| / |b~|
   // deflation (KD > 0): W, AW = S~ W, Z = S~ AW as [n][KD]; Einv [KD*KD]; dscal = { |b~|^2, basis usable (1) or not (0) }
   const double* dW; const double* dAW; const double* dZ; const double* dEinv; const double* dscal;
@@ -1479,7 +1480,8 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
   unsigned long long* ctrl = reinterpret_cast<unsigned long long*>(mine);
   unsigned long long arrived = ctrl[1];             // single GPU: arrivals consumed so far on this arena
   const unsigned int tag0 = (unsigned int)ctrl[2];  // multi: first LL tag of this solve (same on every rank)
-  double alpha = 0.0, beta = 0.0, gamma_old = 0.0, gamma0 = 0.0, gamma_last = 0.0;
+  double alpha = 0.0, beta = 0.0, gamma_old = 0.0, gamma0 = 0.0, gamma_last = 0.0, g_best = 1.7976931348623157e308;
+  int it_best = 0;
   double mus[KD > 0 ? KD : 1];  // mu, replicated in every lane
 #pragma unroll
   for (int dd = 0; dd < (KD > 0 ? KD : 1); ++dd) mus[dd] = 0.0;
@@ -1741,7 +1743,8 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
     PTZ_CG_PROF(2)  // mu
     gamma_last = g;
     if (it == 0) {
-      gamma0 = (KD > 0) ? A.dscal[0] : g;  // deflated: x0 = W E^-1 W^T b~ already took part of b~ away; measure against |b~|
+      // deflated: x0 = W E^-1 W^T b~ already took part of b~ away; measure against |b~| (warm start of the plain kernel likewise)
+      gamma0 = (KD > 0) ? A.dscal[0] : (A.gamma0_ptr != nullptr ? A.gamma0_ptr[0] : g);
       if (!(g > 0)) { status = 0; break; }          // zero right-hand side: x = 0
       const double den = d - mu_nu;
       if (!(den > 0) || !isfinite(den)) { status = 2; break; }
@@ -1749,7 +1752,16 @@ __global__ void __launch_bounds__(MAXT) k_cg(CgArgs A) {
     } else {
       if (sqrt(g) <= A.tol * sqrt(gamma0)) { status = 0; break; }
       if (!isfinite(g) || !isfinite(d)) { status = 2; break; }
-      if (it >= A.max_iter) { status = 1; break; }
+      if (it >= A.max_iter) { status = (KD > 0 && g < 1e-18 * gamma0) ? 4 : 1; break; }  // (a deflated solve at its cap but nearly done: polish)
+      if (KD > 0) {
+        // The recurrence residual of the deflated single-reduction iteration can level off a digit or two above the tolerance on
+        // ill-conditioned systems (V >= 4000: 1e-12 relative for a tolerance of 1e-13).  Below 1e-10 relative, forty iterations
+        // without a new minimum (by 10 %) are that plateau: leave, the host polishes with the plain iteration from this x.  (Twenty
+        // iterations below 1e-9 fired on solves that were still converging, V = 8000, and the polish is not cheap: the restarted
+        // plain iteration has lost the Krylov space.)
+        if (g < 0.9 * g_best) { g_best = g; it_best = it; }
+        else if (it - it_best >= 40 && g < 1e-20 * gamma0) { status = 4; break; }
+      }
       beta = g / gamma_old;
       const double den = d - beta * g / alpha - mu_nu;
       if (!(den > 0)) { status = 2; break; }
@@ -1995,6 +2007,44 @@ __global__ void k_cg_restart(int V, const double* __restrict__ b_copy, double* _
   const size_t o = ((size_t)(i / NCL) * 3) * NCL + (i % NCL);
   st0[o] = b_copy[i]; st0[o + NCL] = 0.0; st0[o + 2 * NCL] = 0.0;
   x[i] = 0.0; p[i] = 0.0;
+}
+// warm start of the plain iteration from a given x~ (a deflated solve that stagnated just above the tolerance): the TRUE residual
+// r = b~ - S~ x~ into the CG state (w = s = 0, p = 0); one warp per row, lanes over the row's blocks, fixed order.  Rows of other
+// ranks are written as zeros (the caller sums the ranks' pieces).
+template <int NCL>
+__global__ void __launch_bounds__(256) k_cg_residual(int V, const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ Sval,
+                                                     const double* __restrict__ x, const double* __restrict__ b_copy, double* __restrict__ st0,
+                                                     double* __restrict__ p, const unsigned char* __restrict__ row_owner, int my_rank) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= V) return;
+  double acc[NCL];
+#pragma unroll
+  for (int a = 0; a < NCL; ++a) acc[a] = 0.0;
+  const bool mine = my_rank < 0 || row_owner[r] == my_rank;
+  if (mine) {
+    for (int k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) {
+      const int c = col[k] & 0x7fffffff;
+      const double* B = Sval + (size_t)k * NCL * NCL;
+      double xc[NCL];
+#pragma unroll
+      for (int b = 0; b < NCL; ++b) xc[b] = x[c * NCL + b];
+#pragma unroll
+      for (int a = 0; a < NCL; ++a)
+#pragma unroll
+        for (int b = 0; b < NCL; ++b) acc[a] += B[a * NCL + b] * xc[b];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NCL; ++a) acc[a] = warp_sum(acc[a]);
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < NCL; ++a) {
+      st0[(r * 3 + 0) * NCL + a] = mine ? b_copy[r * NCL + a] - acc[a] : 0.0;
+      st0[(r * 3 + 1) * NCL + a] = 0.0;
+      st0[(r * 3 + 2) * NCL + a] = 0.0;
+      p[r * NCL + a] = 0.0;
+    }
+  }
 }
 // harvest: W~[i][c] = sum_j Y[j][c] hist[j][i]  (Y already carries 1 / |r_j|); rows of other ranks -> 0 (summed by the caller)
 __global__ void k_defl_harvest(int n, int m, int kd, const double* __restrict__ hist, const double* __restrict__ Y /* [m][kDeflK] */,

@@ -332,7 +332,7 @@ struct BaSolver : BaSolverBase {
   }
   // ---- deflation of the CG (k_cg<.., KD = kDeflK>): basis harvested from the residual history of the first solve of a run
   bool defl_enabled = false, defl_allowed = false, have_W = false, defl_active = true;
-  int defl_kd = 0, defl_solves = 0, defl_rejects = 0, last_lin_iters = -1, defl_ref_iters = 0;
+  int defl_kd = 0, defl_solves = 0, defl_rejects = 0, defl_polishes = 0, last_lin_iters = -1, defl_ref_iters = 0;
   static constexpr int kHistCap = 320, kMinHarvest = 40, kDeflOffBelow = 12, kDeflOnAbove = 30;
   DevBuf<double> d_hist, d_abg, d_Wy, d_Wt, d_AW, d_Z, d_gram, d_Einv, d_c0, d_dscal, d_bcopy, d_Lfac, d_Y;
   std::vector<double> h_abg;
@@ -1080,6 +1080,18 @@ struct BaSolver : BaSolverBase {
     linear_solve(deflate, record, false);
     launch_stage4(mu);
     read_scalars();
+    if (deflate && h_info[1] == 4) {
+      // the deflated solve levelled off just above the tolerance (k_cg, status 4): polish with the plain iteration from its x
+      ++defl_polishes;
+      const int it1 = h_info[0];
+      linear_solve(false, false, false, true);
+      launch_stage4(mu);
+      read_scalars();
+      if (opt.verbose || getenv("PTZ_DEFL_DEBUG"))
+        fprintf(stderr, "[ptzba rank %d] LM iteration %d: deflated solve stagnated after %d iterations, polished with %d plain ones (status %d)\n", g_nccl.rank,
+                iteration, it1, h_info[0], h_info[1]);
+      h_info[0] += it1;
+    }
     if (deflate) {
       ++defl_solves;
       const bool stalled = h_info[1] == 1 && h_info[0] < opt.pcg_max_iterations;  // hit the deflated solve's own cap
@@ -1089,9 +1101,13 @@ struct BaSolver : BaSolverBase {
         // on sharded problems with V = 4000): drop the basis, redo this solve with the plain iteration and harvest a FRESH basis from
         // it; after three such rejections in one run the handle stays with the plain iteration
         ++defl_rejects;
-        if (opt.verbose || getenv("PTZ_DEFL_DEBUG"))
-          fprintf(stderr, "[ptzba rank %d] deflated solve rejected at LM iteration %d: basis usable %g, pcg status %d after %d iterations (%d rejections)\n",
-                  g_nccl.rank, iteration, h_dscal[1], h_info[1], h_info[0], defl_rejects);
+        if (opt.verbose || getenv("PTZ_DEFL_DEBUG")) {
+          double res = 0;
+          d_pcg_res.download(&res, 1, stream);
+          PTZ_CUDA(cudaStreamSynchronize(stream));
+          fprintf(stderr, "[ptzba rank %d] deflated solve rejected at LM iteration %d: basis usable %g, pcg status %d%s after %d iterations, |r|/|b| = %.3e (%d rejections)\n",
+                  g_nccl.rank, iteration, h_dscal[1], h_info[1], stalled ? " (stalled at its cap)" : "", h_info[0], res, defl_rejects);
+        }
         have_W = false;
         if (defl_rejects >= 3) defl_enabled = false;
         if (defl_enabled && d_hist.n == 0) d_hist.alloc((size_t)kHistCap * V * NCL, stream);
@@ -1116,7 +1132,7 @@ struct BaSolver : BaSolverBase {
   }
 
   // stage 3: the deflation set-up (when a basis exists), ONE cooperative k_cg launch, back to the unscaled unknowns
-  void linear_solve(bool deflate, bool record, bool restart) {
+  void linear_solve(bool deflate, bool record, bool restart, bool warm = false) {
     cudaStream_t s = stream;
     const int ncam = V * NCL;
     const size_t nk = (size_t)ncam * kDeflK;
@@ -1141,6 +1157,7 @@ struct BaSolver : BaSolverBase {
     a.dW = d_Wt.p; a.dAW = d_AW.p; a.dZ = d_Z.p; a.dEinv = d_Einv.p; a.dscal = d_dscal.p;
     a.hist = record ? d_hist.p : nullptr; a.hist_cap = kHistCap; a.abg = record ? d_abg.p : nullptr;
     a.prof = nullptr;
+    a.gamma0_ptr = warm ? d_dscal.p : nullptr;
     if (a.debug & 8) {  // per-phase cycle counters of CTA 0 (printed by the destructor)
       if (d_prof.n == 0) { d_prof.alloc(16, s); d_prof.zero(s); }
       a.prof = d_prof.p + (deflate ? 8 : 0);
@@ -1148,6 +1165,10 @@ struct BaSolver : BaSolverBase {
     const size_t cg_smem = cg_smem_bytes(deflate);
     void* args[] = {&a};
     if (restart) k_cg_restart<NCL><<<cdiv(ncam, 256), 256, 0, s>>>(V, d_bcopy.p, arena_ptr(ar_st0), arena_ptr(ar_x), d_cgp.p);
+    if (warm) {  // plain iteration from the x~ a stagnated deflated solve left behind: true residual into the state
+      k_cg_residual<NCL><<<cdiv(V, 8), 256, 0, s>>>(V, ds.s_rowptr.p, ds.s_col.p, p_Sval, arena_ptr(ar_x), d_bcopy.p, arena_ptr(ar_st0), d_cgp.p, d_cg_owner.p, mr);
+      allreduce_sum(arena_ptr(ar_st0), 3 * (size_t)ncam, s);  // sharded rows: every rank needs the whole initial state (no-op on one GPU)
+    }
     if (deflate)
       PTZ_TIMED(PTZ_K_DEFLATE, {
         const int nchunk = cdiv(ncam, kDeflGramChunk);

@@ -646,8 +646,13 @@ def bench_tracks(args, prob):
     t0 = time.perf_counter()
     orc.tracks_build(ms_, 4)
     dc = time.perf_counter() - t0
-    # algorithmic bytes: 16 B/match in (two indices + the pair's images), 8 B/track element out
-    return dict(workload=f"matches of the bench scene: {N} matches in {len(m.pair_src)} image pairs -> {t.num_tracks} tracks, {len(t.elem_img)} elements",
+    # algorithmic bytes: 16 B/match in (two indices + the pair's images), 8 B/track element + 12 B/track out; the build is a chain of
+    # radix sorts and scans over 24-32 B per match, so its real DRAM traffic is ~10x that: the fraction says so
+    peak, peak_src = load_peaks()
+    alg = 16 * N + 8 * len(t.elem_img) + 12 * t.num_tracks
+    roof = dict(kernel="ptztracks_build_dev (28 launches: CUB radix sorts / scans + union-find)", bound="hbm", achieved=round(alg / (ms * 1e-3) / 1e9, 1), peak=peak,
+                unit="GB/s", frac=round(alg / (ms * 1e-3) / 1e9 / peak, 4), algorithmic_bytes_per_launch=int(alg), peak_source=peak_src, traffic=None)
+    return dict(roofline=roof, workload=f"matches of the bench scene: {N} matches in {len(m.pair_src)} image pairs -> {t.num_tracks} tracks, {len(t.elem_img)} elements",
                 matches_per_sec=round(N / (ms * 1e-3), 1), ms_per_build=round(ms, 3), tracks_as_scene=bool(ok),
                 e2e_matches_per_sec=round(N / dt, 1), e2e_seconds=round(dt, 4), h2d_bytes=int(8 * N + 16 * len(m.pair_src)), d2h_bytes=int(8 * len(t.elem_img) + 12 * t.num_tracks),
                 cpu_matches_per_sec=round(ms_.num_matches / dc, 1), cpu_sample=f"first {kp} pairs ({ms_.num_matches} matches), 1 thread, {dc:.1f} s")

@@ -851,7 +851,7 @@ __global__ void k_precond(int V, const int* __restrict__ diag_pos, const double*
     for (int i = 0; i < NCL; ++i) M[i * NCL + c] = x[i];
   }
 }
-// border block (nb <= 32): Cholesky in shared memory, one lane per column of L^-1
+// border block (nb <= kMaxBorder = 16): Cholesky in shared memory, one lane per column of L^-1
 __global__ void __launch_bounds__(32) k_precond_border(int nb, const double* __restrict__ Sbb, double* __restrict__ Linv_b, int* __restrict__ fail) {
   __shared__ double A[kMaxBorder * kMaxBorder];
   __shared__ int ok;

@@ -241,9 +241,33 @@ __global__ void k_view_finalize(int V, const int* __restrict__ view_chunk_off, c
   }
 }
 
+// damp and factor one ray block: (V + D^2) = L L^T, t = L^-1 h (D^2 = clamp(diag V)/mu, refreshed after accepted steps only)
+__device__ __forceinline__ void track_factor_one(int p, bool empty, const double (&vh)[9], double mu, int refresh_diag, double min_diag, double max_diag,
+                                                 double* __restrict__ diag_ray, double* __restrict__ Lt, int* __restrict__ fail) {
+  double d0, d1, d2;
+  if (refresh_diag) {
+    d0 = fmin(fmax(vh[0], min_diag), max_diag); d1 = fmin(fmax(vh[2], min_diag), max_diag); d2 = fmin(fmax(vh[5], min_diag), max_diag);
+    diag_ray[3 * (size_t)p] = d0; diag_ray[3 * (size_t)p + 1] = d1; diag_ray[3 * (size_t)p + 2] = d2;
+  } else {
+    d0 = diag_ray[3 * (size_t)p]; d1 = diag_ray[3 * (size_t)p + 1]; d2 = diag_ray[3 * (size_t)p + 2];
+  }
+  const double A6[6] = {vh[0] + d0 / mu, vh[1], vh[2] + d1 / mu, vh[3], vh[4], vh[5] + d2 / mu};
+  double L[6] = {1, 0, 1, 0, 0, 1};
+  double* lt = Lt + (size_t)p * 10;
+  if (!empty && !chol3(A6, L)) {
+    atomicExch(fail, 1);
+    L[0] = L[2] = L[5] = 1.0; L[1] = L[3] = L[4] = 0.0;
+  }
+  const double t0 = vh[6] / L[0], t1 = (vh[7] - L[1] * t0) / L[2], t2 = (vh[8] - L[3] * t0 - L[4] * t1) / L[5];
+  lt[0] = L[0]; lt[1] = L[1]; lt[2] = L[2]; lt[3] = L[3]; lt[4] = L[4]; lt[5] = L[5];
+  lt[6] = empty ? 0.0 : t0; lt[7] = empty ? 0.0 : t1; lt[8] = empty ? 0.0 : t2; lt[9] = 0;
+}
 // per track: V = sum E^T E (lower 6), h = sum E^T r.  Once per Jacobian evaluation (gradient, column norms, LM diagonal).
+// factor_mu > 0: the damped Cholesky factor of the NEXT linear solve is formed right here from the sums still in registers (after an
+// accepted step the new radius is known before the Jacobian is evaluated), which saves that solve its k_track_factor launch.
 __global__ void k_track_accum(int P, const int* __restrict__ t_off, const int* __restrict__ t_obs, const double* __restrict__ recA,
-                              const double* __restrict__ trk, double* __restrict__ Vh, double* __restrict__ gmax_part) {
+                              const double* __restrict__ trk, double* __restrict__ Vh, double* __restrict__ gmax_part, double factor_mu, double min_diag,
+                              double max_diag, double* __restrict__ diag_ray, double* __restrict__ Lt, int* __restrict__ fail) {
   __shared__ double sm[8];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   double gm = 0;
@@ -274,6 +298,10 @@ __global__ void k_track_accum(int P, const int* __restrict__ t_off, const int* _
     }
     double* o = Vh + (size_t)p * 10;
     o[0] = v00; o[1] = v10; o[2] = v11; o[3] = v20; o[4] = v21; o[5] = v22; o[6] = h0; o[7] = h1; o[8] = h2; o[9] = 0;
+    if (factor_mu > 0.0) {
+      const double vh[9] = {v00, v10, v11, v20, v21, v22, h0, h1, h2};
+      track_factor_one(p, tb == te, vh, factor_mu, 1, min_diag, max_diag, diag_ray, Lt, fail);
+    }
     const double* t = trk + (size_t)p * kTrk;
     gm = fmax(fabs(h0 / t[4]), fmax(fabs(h1 / t[5]), fabs(h2 / t[6])));
   }
@@ -481,25 +509,9 @@ __global__ void k_track_factor(int P, const int* __restrict__ t_off, const doubl
                                double max_diag, double* __restrict__ diag_ray, double* __restrict__ Lt, int* __restrict__ fail) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  const double* vh = Vh + (size_t)p * 10;
-  double d0, d1, d2;
-  if (refresh_diag) {
-    d0 = fmin(fmax(vh[0], min_diag), max_diag); d1 = fmin(fmax(vh[2], min_diag), max_diag); d2 = fmin(fmax(vh[5], min_diag), max_diag);
-    diag_ray[3 * (size_t)p] = d0; diag_ray[3 * (size_t)p + 1] = d1; diag_ray[3 * (size_t)p + 2] = d2;
-  } else {
-    d0 = diag_ray[3 * (size_t)p]; d1 = diag_ray[3 * (size_t)p + 1]; d2 = diag_ray[3 * (size_t)p + 2];
-  }
-  const double A6[6] = {vh[0] + d0 / mu, vh[1], vh[2] + d1 / mu, vh[3], vh[4], vh[5] + d2 / mu};
-  double L[6] = {1, 0, 1, 0, 0, 1};
-  double* lt = Lt + (size_t)p * 10;
-  const bool empty = t_off[p] == t_off[p + 1];  // track without observations: not in the problem
-  if (!empty && !chol3(A6, L)) {
-    atomicExch(fail, 1);
-    L[0] = L[2] = L[5] = 1.0; L[1] = L[3] = L[4] = 0.0;
-  }
-  const double t0 = vh[6] / L[0], t1 = (vh[7] - L[1] * t0) / L[2], t2 = (vh[8] - L[3] * t0 - L[4] * t1) / L[5];
-  lt[0] = L[0]; lt[1] = L[1]; lt[2] = L[2]; lt[3] = L[3]; lt[4] = L[4]; lt[5] = L[5];
-  lt[6] = empty ? 0.0 : t0; lt[7] = empty ? 0.0 : t1; lt[8] = empty ? 0.0 : t2; lt[9] = 0;
+  const double* q = Vh + (size_t)p * 10;
+  const double vh[9] = {q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], q[8]};
+  track_factor_one(p, t_off[p] == t_off[p + 1], vh, mu, refresh_diag, min_diag, max_diag, diag_ray, Lt, fail);
 }
 // per observation (one thread each; a chunk of one view per step, so records stream and the view's Schur terms reduce in the
 // CTA): What = (F^T E) L^-T, q = What t; chunk partials of sum What What^T (upper) and sum q for k_schur_diag.

@@ -281,6 +281,8 @@ struct BaSolver : BaSolverBase {
   bool use_dense = false;  // n <= kDenseMaxN: stage 3 is a dense Cholesky in one CTA (k_dense_chol) instead of the CG
   DevBuf<double> d_dense;  // [(n + 1) x n]
   size_t dense_smem_bytes() const { return (size_t)(kDenseNB * kDenseLd + 32 * kDenseNB + 2 * ((n + 3) & ~3) + (n + 1) * (n | 1)) * sizeof(double); }
+  double fuse_factor_mu = 0.0;  // > 0: the next k_track_accum also factors the ray blocks for this radius
+  double lt_mu = 0.0;           // radius d_Lt was factored for inside k_track_accum (0: k_track_factor has to run)
   int vt_for = -1;         // parameter copy (0/1) the view table d_vt was built from, -1 = stale
   bool vt_scaled = false;  // ... with the final Jacobi scales in it
   // device: work
@@ -837,6 +839,7 @@ struct BaSolver : BaSolverBase {
     for (int i = 0; i < 2; ++i) PTZ_CUDA(cudaMemcpyAsync(d_trk[i].p, d_trk_init.p, d_trk_init.n * 8, cudaMemcpyDeviceToDevice, s));
     cur = 0;
     vt_for = -1; vt_scaled = false;
+    fuse_factor_mu = 0.0; lt_mu = 0.0;
     started = finished = false;
     iteration = 0; num_consecutive_invalid = 0; num_successful = num_unsuccessful = lin_iters_total = jac_evals = cost_evals = 0;
     radius = opt.initial_trust_region_radius; decrease_factor = 2.0; reuse_diagonal = false; last_successful = true;
@@ -872,7 +875,10 @@ struct BaSolver : BaSolverBase {
         PTZ_TIMED(PTZ_K_TRACK_ACCUM, k_track_accum_w<<<cdiv(track_groups, 8), 256, 0, s>>>(track_groups, M, d_grp_e0.p, d_t_trk.p, ds.t_obs.p, d_recA.p, d_trk[cur].p,
                                                                                             d_Vh.p, d_gmax_part.p));
       else
-        PTZ_TIMED(PTZ_K_TRACK_ACCUM, k_track_accum<<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_recA.p, d_trk[cur].p, d_Vh.p, d_gmax_part.p));
+        PTZ_TIMED(PTZ_K_TRACK_ACCUM, k_track_accum<<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, ds.t_obs.p, d_recA.p, d_trk[cur].p, d_Vh.p, d_gmax_part.p, fuse_factor_mu,
+                                                                            opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_ray.p, d_Lt.p, d_fail.p));
+      lt_mu = (track_groups > 0) ? 0.0 : fuse_factor_mu;  // d_Lt now holds the factor for this radius (fresh diagonal), or nothing
+      fuse_factor_mu = 0.0;
     }
     if (A > 0) {
       PtsArgs a;
@@ -979,10 +985,15 @@ struct BaSolver : BaSolverBase {
     const double mu = radius;
     const int refresh = reuse_diagonal ? 0 : 1;
     const int own = (g_nccl.rank == 0) ? 1 : 0;
-    PTZ_CUDA(cudaMemsetAsync(d_fail.p, 0, sizeof(int), s));
+    // (after an accepted step the ray blocks were already damped and factored for this radius inside k_track_accum: their failure flag,
+    // if any, is in d_fail and must survive)
+    const bool lt_ready = P > 0 && refresh && lt_mu == mu;
+    lt_mu = 0.0;
+    if (!lt_ready) PTZ_CUDA(cudaMemsetAsync(d_fail.p, 0, sizeof(int), s));
     if (P > 0)
       PTZ_TIMED(PTZ_K_TRACK_SOLVE, {
-        k_track_factor<<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, d_Vh.p, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_ray.p, d_Lt.p, d_fail.p);
+        if (!lt_ready)
+          k_track_factor<<<nblk_ray, 128, 0, s>>>(P, ds.t_off.p, d_Vh.p, mu, refresh, opt.min_lm_diagonal, opt.max_lm_diagonal, d_diag_ray.p, d_Lt.p, d_fail.p);
         if (ds.nchunks > 0)
           k_obs_what<NCL><<<ow_grid, kChunk, ObsWhatSmem<NCL>::kBytes, s>>>(ds.nchunks, ow_per, ds.chunk_view.p, ds.chunk_begin.p, ds.chunk_cnt.p, ds.o_track.p, d_recA.p, d_recF.p, d_Lt.p,
                                                                           d_What.p, d_q.p);
@@ -1362,9 +1373,10 @@ struct BaSolver : BaSolverBase {
         // HandleSuccessfulStep
         cur ^= 1;
         x_norm = cand_norm;
-        evaluate_jacobian(false);
-        radius = radius / std::max(1.0 / 3.0, 1.0 - pow(2.0 * rho - 1.0, 3));
+        radius = radius / std::max(1.0 / 3.0, 1.0 - pow(2.0 * rho - 1.0, 3));  // (does not depend on the new Jacobian: known before it)
         radius = std::min(opt.max_trust_region_radius, radius);
+        if (num_consecutive_invalid == 0) { PTZ_CUDA(cudaMemsetAsync(d_fail.p, 0, sizeof(int), stream)); fuse_factor_mu = radius; }
+        evaluate_jacobian(false);
         decrease_factor = 2.0;
         reuse_diagonal = false;
         last_successful = true;

@@ -280,15 +280,21 @@ def run_ours(args):
     # ---- roofline: algorithmic bytes per launch / mean event-timed duration, against the measured HBM peak
     peak, peak_src = load_peaks()
     ncl = 4 + (args.factor_type > 0) + (args.factor_type == 2)
-    RS, WS = 8 + 2 * ncl, (3 * ncl + 1) & ~1
+    RS, WS = 8 + 2 * ncl, (3 * ncl + 3) & ~3  # record and What sizes in doubles (Dims<NCL> of ba_kernels.cuh)
     nnzb, npairs = st_b["nnz_blocks"], st_b["num_pairs"]
     cg_its_per_launch = st["pcg_iterations"] / max(kernels.get("pcg", dict(launches=1))["launches"], 1)
+    # after an accepted step the ray blocks are damped and factored inside k_track_accum (160 B/track: Vh in registers, Lt + diagonal out),
+    # k_track_factor then only runs for the solves that follow a rejected step: split its bytes between the two entries accordingly
+    n_acc = kernels.get("track_accum", dict(launches=0))["launches"]
+    n_sol = max(kernels.get("track_solve", dict(launches=1))["launches"], 1)
+    f_fused = min(1.0, n_acc / n_sol)
     alg = {
         # stage 1: 16 B read + r 16 B + J
         "resjac": ("hbm", RJ_BYTES_PER_OBS[args.factor_type] * prob.M, "k_resjac: 16 B in + 16 B r + %d B J per observation" % (RJ_BYTES_PER_OBS[args.factor_type] - 32)),
-        "track_accum": ("hbm", 64 * prob.M + 80 * prob.P, "k_track_accum: r + E (64 B) per observation gathered by track, 80 B per track out"),
+        "track_accum": ("hbm", 64 * prob.M + (80 + 104) * prob.P, "k_track_accum: r + E (64 B) per observation gathered by track, 80 B per track out, + the damped Cholesky factor of the next solve (104 B per track)"),
         # stage 2: record in, What out; Cholesky factor per track
-        "track_solve": ("hbm", 8 * (RS + WS) * prob.M + 160 * prob.P, "k_track_factor + k_obs_what: record %d B in + What %d B out per observation, 160 B per track" % (8 * RS, 8 * WS)),
+        "track_solve": ("hbm", 8 * (RS + WS) * prob.M + 160 * prob.P * (1.0 - f_fused),
+                        "k_obs_what (+ k_track_factor after rejected steps, %.0f %% of the solves): record %d B in + What %d B out per observation, 160 B per track when the factor runs" % (100 * (1 - f_fused), 8 * RS, 8 * WS)),
         "schur_offdiag": ("l2", 2 * 8 * WS * npairs, "k_schur_offdiag: two What records (%d B) per observation pair, L2-resident gathers" % (8 * WS)),
         # stage 3: per CG iteration every block of S~ (NCL^2 doubles) and the (r, w, s) state of its column (3 NCL doubles)
         "pcg": ("l2-latency + grid barrier", nnzb * (ncl * ncl + 3 * ncl) * 8 * cg_its_per_launch,

@@ -451,9 +451,52 @@ def make_epnp_kat(seed=31, cases=48):
                         cv2_version=np.array(cv2.__version__))
 
 
+def make_shared_kat():
+    """SetSharedIntrinsics (ptzray_optimizer.cc:497-505, :640-650, :821-848): the tiny BA scenes of lm_kat.npz again, now with (a) ALL views and
+    (b) views {1, 3, 4} sharing ONE intrinsics block -- the block of the group's first view, its fixed cx, cy, dist included -- minimised
+    by scipy with the cv2 functors.  Pins the oracle's restatement of shared blocks (cost, shared focal, relative rotations)."""
+    k = np.load(os.path.join(HERE, "lm_kat.npz"))
+    out = {}
+    for t in (0, 1):
+        intr0, ext0, uv, oview, otrack, w, ray0 = (k[f"ba{t}_{n}"] for n in ("intr", "ext", "obs_uv", "obs_view", "obs_track", "track_weight", "ray0"))
+        V, P, M = len(intr0), len(ray0), len(uv)
+        for name, ids in (("all", np.zeros(V, np.int32)), ("some", np.array([10, 7, 11, 7, 7, 12][:V], np.int32))):
+            rep = np.array([int(np.nonzero(ids == ids[i])[0][0]) for i in range(V)])
+            groups = sorted(set(rep.tolist()))           # one intrinsics block per group, at its first view
+            gi = {g: n for n, g in enumerate(groups)}
+            G = len(groups)
+
+            def unpack(z):
+                intr = intr0[rep].copy()                 # every view reads its group's block: fixed cx, cy, dist of the first view too
+                intr[:, 0] = np.array([z[gi[rep[i]]] for i in range(V)])
+                o = G
+                if t == 1:
+                    intr[:, 4] = np.array([z[o + gi[rep[i]]] for i in range(V)])
+                    o += G
+                ext = ext0.copy()
+                ext[:, :3] = z[o : o + 3 * V].reshape(V, 3)
+                return intr, ext, z[o + 3 * V :].reshape(P, 3)
+
+            def fun(z):
+                intr, ext, ray = unpack(z)
+                return np.concatenate([np.sqrt(w[otrack[q]]) * ba_ray_cv(t, intr[oview[q]], ext[oview[q]], ray[otrack[q]], np.zeros(3), uv[q]) for q in range(M)])
+
+            z0 = np.concatenate([intr0[groups, 0]] + ([intr0[groups, 4]] if t == 1 else []) + [ext0[:, :3].ravel(), ray0.ravel()])
+            s = least_squares(fun, z0, method="trf", xtol=1e-15, ftol=1e-15, gtol=1e-13, x_scale="jac", max_nfev=600)
+            intr, ext, ray = unpack(s.x)
+            key = f"ba{t}_{name}"
+            out[f"{key}_ids"], out[f"{key}_sol_intr"], out[f"{key}_sol_ext"], out[f"{key}_cost"] = ids, intr, ext, s.cost
+            print("shared", key, s.cost, s.status, s.nfev, flush=True)
+    np.savez_compressed(os.path.join(HERE, "shared_kat.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--shared-only" in sys.argv:
+        make_shared_kat()
+        sys.exit(0)
     make_epnp_kat()
     make_opencv_kat()
     make_functor_kat()
     make_lm_kat()
+    make_shared_kat()
     print("golden vectors written to", HERE)

@@ -1,6 +1,8 @@
 """The oracle against the golden vectors (OpenCV-python, mpmath, scipy): this is what pins the checker.
 CPU only.  Tolerances: values 1e-9 px absolute (cv2 and the oracle round differently at the 1e-12 level on
 pixel magnitudes of 1e3); exact Jacobians 1e-9 relative to the row scale."""
+import os
+
 import numpy as np
 import pytest
 
@@ -193,3 +195,31 @@ def test_ba_minimum_matches_scipy(orc, lm_kat):
         rel_a = Ra @ Ra[0].T
         rel_b = Rb @ Rb[0].T
         assert np.abs(rel_a - rel_b).max() < 1e-5
+
+
+@pytest.mark.parametrize("t,name", [(0, "some"), (1, "all"), (1, "some"), (0, "all")])
+def test_shared_intrinsics_minimum_matches_scipy(orc, lm_kat, t, name):
+    """SetSharedIntrinsics pinned independently of the oracle: the tiny BA scenes again with all views, or views {1, 3, 4}, on ONE
+    intrinsics block, minimised by scipy with the cv2 functors (tests/golden/make_golden.py: make_shared_kat).  Free gauge: cost, the
+    shared focal lengths and the relative rotations are compared."""
+    k = lm_kat
+    sk = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "shared_kat.npz"))
+    key = f"ba{t}_{name}"
+    p = problem.BAProblem(factor_type=t, intr=k[f"ba{t}_intr"], ext=k[f"ba{t}_ext"], obs_uv=k[f"ba{t}_obs_uv"], obs_view=k[f"ba{t}_obs_view"],
+                          obs_track=k[f"ba{t}_obs_track"], track_weight=k[f"ba{t}_track_weight"], shared_ic_id=sk[f"{key}_ids"])
+    rc, r = orc.ba_solve(p, function_tolerance=1e-16, parameter_tolerance=1e-15, gradient_tolerance=1e-12, max_num_iterations=500)
+    assert rc == 0
+    want = float(sk[f"{key}_cost"])
+    if (t, name) == (0, "all"):  # scipy stopped at its evaluation cap there: the oracle must be at least as low
+        assert r.final_cost <= want * (1 + 1e-6)
+        return
+    assert abs(r.final_cost - want) / want < 1e-7
+    ids = sk[f"{key}_ids"]
+    for g in set(ids.tolist()):
+        m = np.nonzero(ids == g)[0]
+        assert (r.intr[m] == r.intr[m[0]]).all()                      # one block per group, the first view's fixed entries included
+        assert np.array_equal(r.intr[m[0], 2:4], p.intr[m[0], 2:4])
+    assert np.abs(r.intr[:, 0] - sk[f"{key}_sol_intr"][:, 0]).max() < 5e-2 * max(1.0, want ** 0.0)
+    Ra = np.array([orc.rodrigues(e[:3]) for e in r.ext])
+    Rb = np.array([orc.rodrigues(e[:3]) for e in sk[f"{key}_sol_ext"]])
+    assert np.abs(Ra @ Ra[0].T - Rb @ Rb[0].T).max() < 1e-4

@@ -490,7 +490,59 @@ def make_shared_kat():
     np.savez_compressed(os.path.join(HERE, "shared_kat.npz"), **out)
 
 
+def make_georef_kat(seed=123):
+    """RunGeoreferencing (run_ptz_ba.cc:131-145): ray terms + annotated 2d-3d points with a free T_l_w, EVERY view annotated (two points
+    each), minimised by scipy with the cv2 functors.  fy of an annotated view is driven by its 2d-3d terms only.  The gauge
+    of the local frame is free, so the test compares the cost, T-invariant world-frame rotations R_i R_lw and the focal lengths."""
+    out = {}
+    for t in (0, 1):
+        p = synth.make_ba_scene(6, 60, "ring", factor_type=t, seed=seed + t, neighbours=6, num_pts3d=12, pts3d_views=6)
+        V, P, M, A = p.V, p.P, p.M, p.A
+        ray0 = np.zeros((P, 3))
+        cnt = np.zeros(P)
+        for k in range(M):  # Pix2Ray
+            i = p.obs_view[k]
+            K = np.array([[p.intr[i, 0], 0, p.intr[i, 2]], [0, p.intr[i, 1], p.intr[i, 3]], [0, 0, 1.0]])
+            v = np.linalg.inv(np_rod(p.ext[i, :3])) @ np.linalg.inv(K) @ np.array([p.obs_uv[k, 0], p.obs_uv[k, 1], 1.0], np.float64)
+            ray0[p.obs_track[k]] += v / np.linalg.norm(v)
+            cnt[p.obs_track[k]] += 1
+        ray0 /= cnt[:, None]
+        ray0 /= np.linalg.norm(ray0, axis=1, keepdims=True)
+
+        def unpack(z):
+            intr, ext = p.intr.copy(), p.ext.copy()
+            intr[:, 0] = z[:V]
+            intr[:, 1] = z[V : 2 * V]          # fy: only the 2d-3d terms read it (the ray factors tie fy := fx)
+            o = 2 * V
+            if t == 1:
+                intr[:, 4] = z[o : o + V]
+                o += V
+            ext[:, :3] = z[o : o + 3 * V].reshape(V, 3)
+            o += 3 * V
+            return intr, ext, z[o : o + 3 * P].reshape(P, 3), z[o + 3 * P :]
+
+        def fun(z):
+            intr, ext, ray, tlw = unpack(z)
+            r = [np.sqrt(p.track_weight[p.obs_track[k]]) * ba_ray_cv(t, intr[p.obs_view[k]], ext[p.obs_view[k]], ray[p.obs_track[k]], np.zeros(3), p.obs_uv[k])
+                 for k in range(M)]
+            r += [ba_pt_cv(t, intr[p.pt_view[a]], ext[p.pt_view[a]], tlw, np.zeros(3), p.pt_uv[a], p.pt_xyz[a]) for a in range(A)]
+            return np.concatenate(r)
+
+        z0 = np.concatenate([p.intr[:, 0], p.intr[:, 1]] + ([p.intr[:, 4]] if t == 1 else []) + [p.ext[:, :3].ravel(), ray0.ravel(), p.tlw0])
+        s = least_squares(fun, z0, method="trf", xtol=1e-15, ftol=1e-15, gtol=1e-13, x_scale="jac", max_nfev=400)
+        intr, ext, ray, tlw = unpack(s.x)
+        key = f"geo{t}"
+        for nm in ("intr", "ext", "obs_uv", "obs_view", "obs_track", "track_weight", "pt_uv", "pt_xyz", "pt_view", "tlw0"):
+            out[f"{key}_{nm}"] = getattr(p, nm)
+        out[f"{key}_sol_intr"], out[f"{key}_sol_ext"], out[f"{key}_sol_tlw"], out[f"{key}_cost"] = intr, ext, tlw, s.cost
+        print("georef", key, s.cost, s.status, s.nfev, flush=True)
+    np.savez_compressed(os.path.join(HERE, "georef_kat.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--georef-only" in sys.argv:
+        make_georef_kat()
+        sys.exit(0)
     if "--shared-only" in sys.argv:
         make_shared_kat()
         sys.exit(0)
@@ -499,4 +551,5 @@ if __name__ == "__main__":
     make_functor_kat()
     make_lm_kat()
     make_shared_kat()
+    make_georef_kat()
     print("golden vectors written to", HERE)

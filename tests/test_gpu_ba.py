@@ -416,3 +416,31 @@ def test_multi_gpu_sharded_solve_matches_single_gpu():
            os.path.join(root, "tests", "scripts", "multi_gpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "MULTI_GPU_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("t", [0, 1])
+def test_golden_scipy_minima_reproduced_on_the_gpu(orc, t):
+    """the scipy / cv2 golden minima (tests/golden: georeferencing with every view annotated, shared intrinsics) straight against the
+    CUDA path -- no oracle in between: cost to 1e-7, gauge-invariant rotations to 1e-5 / 1e-4"""
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    k = np.load(os.path.join(gdir, "georef_kat.npz"))
+    g = f"geo{t}"
+    p = ptz.BAProblem(factor_type=t, intr=k[f"{g}_intr"], ext=k[f"{g}_ext"], obs_uv=k[f"{g}_obs_uv"], obs_view=k[f"{g}_obs_view"], obs_track=k[f"{g}_obs_track"],
+                          track_weight=k[f"{g}_track_weight"], pt_uv=k[f"{g}_pt_uv"], pt_xyz=k[f"{g}_pt_xyz"], pt_view=k[f"{g}_pt_view"], tlw0=k[f"{g}_tlw0"])
+    r = ptz.ba_solve(p, function_tolerance=1e-16, parameter_tolerance=1e-15, gradient_tolerance=1e-12, max_num_iterations=500)
+    want = float(k[f"{g}_cost"])
+    assert abs(r.final_cost - want) / want < 1e-7
+    Ra = np.array([orc.rodrigues(e[:3]) @ orc.rodrigues(r.tlw[:3]) for e in r.ext])
+    Rb = np.array([orc.rodrigues(e[:3]) @ orc.rodrigues(k[f"{g}_sol_tlw"][:3]) for e in k[f"{g}_sol_ext"]])
+    assert np.abs(Ra - Rb).max() < 1e-5
+    lk, sk = np.load(os.path.join(gdir, "lm_kat.npz")), np.load(os.path.join(gdir, "shared_kat.npz"))
+    for name in ("some", "all") if t == 1 else ("some",):
+        key = f"ba{t}_{name}"
+        q = ptz.BAProblem(factor_type=t, intr=lk[f"ba{t}_intr"], ext=lk[f"ba{t}_ext"], obs_uv=lk[f"ba{t}_obs_uv"], obs_view=lk[f"ba{t}_obs_view"],
+                              obs_track=lk[f"ba{t}_obs_track"], track_weight=lk[f"ba{t}_track_weight"], shared_ic_id=sk[f"{key}_ids"])
+        rs = ptz.ba_solve(q, function_tolerance=1e-16, parameter_tolerance=1e-15, gradient_tolerance=1e-12, max_num_iterations=500)
+        ws = float(sk[f"{key}_cost"])
+        assert abs(rs.final_cost - ws) / ws < 1e-7, (key, rs.final_cost, ws)
+        Rc = np.array([orc.rodrigues(e[:3]) for e in rs.ext])
+        Rd = np.array([orc.rodrigues(e[:3]) for e in sk[f"{key}_sol_ext"]])
+        assert np.abs(Rc @ Rc[0].T - Rd @ Rd[0].T).max() < 1e-4

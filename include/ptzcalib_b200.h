@@ -331,6 +331,18 @@ typedef struct ptztracks_obs {
 
 int ptztracks_flatten(const ptztracks_result* tracks, const ptztracks_views* views, ptztracks_obs* out);
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Initial local->world transform of a georeferencing BA: PTZRayOptimizer::SetInitTransLocalToWorld
+ * (ptzray_optimizer.cc:562-633).  For each view in order that has annotated points: cv::solvePnP(SOLVEPNP_EPNP) (:572, restated
+ * in ptzcalib_epnp.hpp), the gates of :582-604, and T_l_w = T_i_l^-1 T_i_w (:606-616); the first view that passes gives tlw =
+ * [rvec | t] (what ptzba_problem.tlw0 takes) and *view_used; when none passes tlw = 0, *view_used = -1 (the reference then
+ * starts from zeros too).  Host code, a few tens of points: no device needed.  cams21 holds the CANDIDATE views only, in the
+ * order of ptzba_problem's views, in the krt21 layout of ptzreloc_* (fx fy cx cy | R row-major | t | k1 k2 p1 p2 k3).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int ptzgeo_init_tlw(int32_t num_views, const double* cams21, const int64_t* pt_offset /* [num_views+1] */,
+                    const float* pt_uv /* [.. * 2] */, const double* pt_xyz /* [.. * 3] */, double tlw[6], int32_t* view_used);
+
 #ifdef __cplusplus
 }
 #endif

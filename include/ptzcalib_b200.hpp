@@ -326,38 +326,11 @@ class PTZRayOptimizer {
         obj[3 * j] = pts3d_[i][j].x; obj[3 * j + 1] = pts3d_[i][j].y; obj[3 * j + 2] = pts3d_[i][j].z;
         pix[2 * j] = pixels_[i][j].x; pix[2 * j + 1] = pixels_[i][j].y;
       }
-      Mat33 R;
-      Vec3 tv;
-      if (!epnp::solve_pnp_epnp((int)n, obj.data(), pix.data(), cameras_[i].K().data(), cameras_[i].dist().data(), R.data(), tv.data())) continue;
-      // cv::Rodrigues(rvec, R) of the rvec solvePnP returns: the round trip re-orthonormalises R
-      Vec3 rv;
-      ptz::rodrigues_inv(R.data(), rv.data());
-      ptz::rodrigues_jac(rv.data(), R.data(), nullptr);
-      const double z0 = R[6] * obj[0] + R[7] * obj[1] + R[8] * obj[2] + tv[2];
-      const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
-      if (z0 < 0 || det < 0.0) continue;  // .cc:582-587
-      // reprojection RMS of the float32 points without distortion (.cc:589-604)
-      const Mat33& K = cameras_[i].K();
-      double sq = 0;
-      for (size_t j = 0; j < n; ++j) {
-        const double X = (float)obj[3 * j], Y = (float)obj[3 * j + 1], Z = (float)obj[3 * j + 2];
-        const double xc = R[0] * X + R[1] * Y + R[2] * Z + tv[0], yc = R[3] * X + R[4] * Y + R[5] * Z + tv[1], zc = R[6] * X + R[7] * Y + R[8] * Z + tv[2];
-        const float pu = (float)(K[0] * (xc / zc) + K[2]), pv = (float)(K[4] * (yc / zc) + K[5]);
-        sq += (double)(pu - pix[2 * j]) * (pu - pix[2 * j]) + (double)(pv - pix[2 * j + 1]) * (pv - pix[2 * j + 1]);
-      }
-      if (std::sqrt(sq / n) > 300) continue;
-      // T_l_w = T_i_l^-1 T_i_w with T_i_l = [R_i | t_i] of the view (.cc:606-616): R_lw = R_i^T R, t_lw = R_i^T (t - t_i)
-      const Mat33& Ri = cameras_[i].R();
-      const Vec3& ti = cameras_[i].t();
-      Mat33 Rlw;
-      Vec3 tlw;
-      for (int r = 0; r < 3; ++r) {
-        for (int c = 0; c < 3; ++c) Rlw[3 * r + c] = Ri[r] * R[c] + Ri[3 + r] * R[3 + c] + Ri[6 + r] * R[6 + c];
-        tlw[r] = Ri[r] * (tv[0] - ti[0]) + Ri[3 + r] * (tv[1] - ti[1]) + Ri[6 + r] * (tv[2] - ti[2]);
-      }
-      Vec3 rlw;
-      ptz::rodrigues_inv(Rlw.data(), rlw.data());
-      tlw_param_ = {rlw[0], rlw[1], rlw[2], tlw[0], tlw[1], tlw[2]};
+      double tlw[6];  // EPnP, the gates of .cc:582-604 and T_l_w = T_i_l^-1 T_i_w: epnp::init_tlw_from_view (shared with ptzgeo_init_tlw)
+      if (!epnp::init_tlw_from_view((int)n, obj.data(), pix.data(), cameras_[i].K().data(), cameras_[i].dist().data(), cameras_[i].R().data(),
+                                    cameras_[i].t().data(), tlw))
+        continue;
+      tlw_param_.assign(tlw, tlw + 6);
       return true;
     }
     tlw_param_.assign(6, 0.0);

@@ -16,6 +16,8 @@
 #include <cmath>
 #include <vector>
 
+#include "../ptz-calib_b200/csrc/ptz_math.cuh"  // rodrigues_jac / rodrigues_inv (plain C++ when not compiled by nvcc)
+
 namespace ptzcalib {
 namespace epnp {
 
@@ -402,6 +404,36 @@ inline bool solve_pnp_epnp(int n, const double* object_pts, const float* pixels,
   s.compute_pose(n, object_pts, us.data(), R, t);
   for (int i = 0; i < 9; ++i) if (!std::isfinite(R[i])) return false;
   return std::isfinite(t[0]) && std::isfinite(t[1]) && std::isfinite(t[2]);
+}
+
+// One view's attempt of PTZRayOptimizer::SetInitTransLocalToWorld (ptzray_optimizer.cc:566-616): EPnP pose of the annotated view, the
+// gates of :582-604 (first point in front, det R >= 0, reprojection RMS of the float32 points <= 300 px without distortion) and
+// T_l_w = T_i_l^-1 T_i_w (:606-616) as [rvec | t].  Ri, ti: the view's rotation (row-major) and translation in the local frame.
+inline bool init_tlw_from_view(int n, const double* obj, const float* pix, const double K[9], const double dist[5], const double Ri[9], const double ti[3],
+                               double tlw[6]) {
+  double R[9], tv[3], rv[3];
+  if (n <= 0 || !solve_pnp_epnp(n, obj, pix, K, dist, R, tv)) return false;
+  // cv::Rodrigues(rvec, R) of the rvec solvePnP returns: the round trip re-orthonormalises R
+  ptz::rodrigues_inv(R, rv);
+  ptz::rodrigues_jac(rv, R, nullptr);
+  const double z0 = R[6] * obj[0] + R[7] * obj[1] + R[8] * obj[2] + tv[2];
+  const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+  if (z0 < 0 || det < 0.0) return false;  // .cc:582-587
+  double sq = 0;  // .cc:589-604
+  for (int j = 0; j < n; ++j) {
+    const double X = (float)obj[3 * j], Y = (float)obj[3 * j + 1], Z = (float)obj[3 * j + 2];
+    const double xc = R[0] * X + R[1] * Y + R[2] * Z + tv[0], yc = R[3] * X + R[4] * Y + R[5] * Z + tv[1], zc = R[6] * X + R[7] * Y + R[8] * Z + tv[2];
+    const float pu = (float)(K[0] * (xc / zc) + K[2]), pv = (float)(K[4] * (yc / zc) + K[5]);
+    sq += (double)(pu - pix[2 * j]) * (pu - pix[2 * j]) + (double)(pv - pix[2 * j + 1]) * (pv - pix[2 * j + 1]);
+  }
+  if (std::sqrt(sq / n) > 300) return false;
+  double Rlw[9];  // R_lw = R_i^T R, t_lw = R_i^T (t - t_i)
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) Rlw[3 * r + c] = Ri[r] * R[c] + Ri[3 + r] * R[3 + c] + Ri[6 + r] * R[6 + c];
+    tlw[3 + r] = Ri[r] * (tv[0] - ti[0]) + Ri[3 + r] * (tv[1] - ti[1]) + Ri[6 + r] * (tv[2] - ti[2]);
+  }
+  ptz::rodrigues_inv(Rlw, tlw);
+  return true;
 }
 
 }  // namespace epnp

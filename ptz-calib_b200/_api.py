@@ -15,7 +15,7 @@ from .problem import BAProblem, BAResult, RelocBatch, RelocResult, default_optio
 from .tracks import Matches, Tracks, Views, Observations, build_tracks, flatten_tracks
 
 __all__ = ["abi", "problem", "BAProblem", "BAResult", "RelocBatch", "RelocResult", "default_options", "ba_solve", "ba_eval", "BAHandle",
-           "reloc_solve_batch", "reloc_eval", "tracks", "Matches", "Tracks", "Views", "Observations", "build_tracks", "flatten_tracks", "PTZRayOptimizer", "KRTOptimizer", "find_best_match", "device_count", "nccl_init_from_torch", "nccl_finalize"]
+           "reloc_solve_batch", "reloc_eval", "tracks", "Matches", "Tracks", "Views", "Observations", "build_tracks", "flatten_tracks", "PTZRayOptimizer", "KRTOptimizer", "find_best_match", "init_trans_local_to_world", "device_count", "nccl_init_from_torch", "nccl_finalize"]
 
 
 def device_count() -> int:
@@ -143,6 +143,28 @@ def nccl_finalize():
     lib.check(lib.load().ptz_nccl_finalize(), "ptz_nccl_finalize")
 
 
+def init_trans_local_to_world(cams21, pt_uv, pt_xyz, pt_view):
+    """PTZRayOptimizer::SetInitTransLocalToWorld (ptzray_optimizer.cc:562-633) through ptzgeo_init_tlw: cams21 [V,21] are the problem's
+    views, pt_view the view index of every annotated point.  -> (tlw [6] = rvec | t, index of the view the estimate came from or -1).
+    Host code (EPnP on a few tens of points): works without a device."""
+    cams21 = f64(cams21).reshape(-1, 21)
+    pt_view = np.asarray(pt_view, dtype=np.int64).reshape(-1)
+    V = len(cams21)
+    if len(pt_view) and (pt_view.min() < 0 or pt_view.max() >= V):
+        raise ValueError("pt_view out of range")
+    order = np.argsort(pt_view, kind="stable")  # per view, in the order given (pixels_[i][j], pts3d_[i][j])
+    uv = np.ascontiguousarray(f32(pt_uv).reshape(-1, 2)[order])
+    xyz = np.ascontiguousarray(f64(pt_xyz).reshape(-1, 3)[order])
+    off = np.zeros(V + 1, np.int64)
+    np.cumsum(np.bincount(pt_view, minlength=V), out=off[1:])
+    tlw = np.zeros(6)
+    used = C.c_int32(-1)
+    L = lib.load()
+    lib.check(L.ptzgeo_init_tlw(C.c_int32(V), cams21.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), uv.ctypes.data_as(C.c_void_p),
+                                xyz.ctypes.data_as(C.c_void_p), tlw.ctypes.data_as(C.c_void_p), C.byref(used)), "ptzgeo_init_tlw")
+    return tlw, int(used.value)
+
+
 # --------------------------------------------------------------------------------------------- class mirrors
 class PTZRayOptimizer:
     """Mirror of ptzcalib::PTZRayOptimizer (ptzray_optimizer.h:112-177) on flattened inputs.
@@ -180,12 +202,11 @@ class PTZRayOptimizer:
         if pt_uv is not None and len(pt_uv):
             if len(pt_uv) != len(pt_xyz) or len(pt_uv) != len(pt_view):  # CheckValid, ptzray_optimizer.cc:524-532
                 raise ValueError("pt_uv, pt_xyz and pt_view must have one row per annotated point")
-            if tlw0 is None:
-                # The reference starts T_l_w from EPnP on the annotated view with the most points (SetInitTransLocalToWorld, :562-633);
-                # that initialisation lives in the C++ adaptor (include/ptzcalib_epnp.hpp).  Starting from T_l_w = 0 here would solve a
-                # different (possibly non-convergent) problem, so the Python mirror asks for the estimate instead of guessing.
-                raise ValueError("from_matches: annotated points need tlw0 (the EPnP initialisation of T_l_w lives in the C++ adaptor)")
             keep = dense[np.asarray(pt_view)] >= 0
+            if tlw0 is None:
+                # SetInitTransLocalToWorld (:562-633), as the C++ adaptor's Solve does when no T_l_w was given: EPnP on the first
+                # annotated candidate view that passes the gates, zeros when none does
+                tlw0, _ = init_trans_local_to_world(cams21[cand], f32(pt_uv)[keep], f64(pt_xyz)[keep], dense[np.asarray(pt_view)][keep])
             kw = dict(pt_uv=f32(pt_uv)[keep], pt_xyz=f64(pt_xyz)[keep], pt_view=dense[np.asarray(pt_view)][keep].astype(np.int32), tlw0=tlw0)
         if shared_ic_ids is not None:  # SetSharedIntrinsics (:497-505): one id per ORIGINAL image; a wrong length is ignored as there
             if len(shared_ic_ids) == len(views.is_candidate):

@@ -12,7 +12,7 @@ EXPORTS = [
     "ptzba_solve", "ptzba_eval", "ptzba_create", "ptzba_reset", "ptzba_run", "ptzba_get_stage_times", "ptzba_set_stage_timing", "ptzba_destroy",
     "ptz_nccl_unique_id", "ptz_nccl_init", "ptz_nccl_finalize",
     "ptzreloc_solve_batch", "ptzreloc_eval", "ptzreloc_solve_batch_dev", "ptzreloc_reproj_error", "ptzreloc_local_params",
-    "ptztracks_build", "ptztracks_build_dev", "ptztracks_flatten", "ptztracks_reference_ids",
+    "ptztracks_build", "ptztracks_build_dev", "ptztracks_flatten", "ptztracks_reference_ids", "ptzgeo_init_tlw",
 ]
 
 

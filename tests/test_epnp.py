@@ -81,3 +81,53 @@ def test_degenerate_inputs():
     # (EPnP without its planar variant is unreliable on coplanar points — cv2 4.13 returns mirrored poses on such inputs too; the
     # caller's gates, ptzray_optimizer.cc:582-604, are what reject a bad initialisation.  Here: no NaN, no crash.)
     assert out[1, 0, 0] == 1.0 and np.isfinite(out[1, 0]).all()
+
+
+def _rodrigues(r):
+    th = np.linalg.norm(r)
+    if th < 1e-12:
+        return np.eye(3)
+    k = r / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+
+
+def test_init_trans_local_to_world_through_the_c_abi():
+    """ptzgeo_init_tlw (PTZRayOptimizer::SetInitTransLocalToWorld, ptzray_optimizer.cc:562-633) is host code behind the C ABI: runs here
+    without a device.  Exact projections of world points through T_i_l T_l_w must give T_l_w back; a view without points, one with fewer
+    than 4 and one whose pixels no pose explains are passed over in order (:566-604)."""
+    import ptz_calib_b200 as ptz
+
+    rng = np.random.default_rng(5)
+    Rlw, tlw = _rodrigues(np.array([0.3, -0.2, 0.5])), np.array([4.0, -3.0, 60.0])
+    V = 5
+    cams = np.zeros((V, 21))
+    uv, xyz, view = [], [], []
+    for i in range(V):
+        Ri = _rodrigues(rng.normal(size=3) * 0.2)
+        ti = np.zeros(3)                                          # a PTZ camera: no translation in the local frame
+        fx = 1500.0 + 100 * i
+        cams[i] = np.concatenate([[fx, fx * 1.01, 960, 540], Ri.ravel(), ti, [-0.05, 0.01, 0, 0, 0]])
+        n = [0, 3, 8, 10, 12][i]
+        # world points whose local-frame image falls inside the view: pick camera-frame points, pull them back to the world
+        xc = np.stack([rng.uniform(-0.4, 0.4, n), rng.uniform(-0.25, 0.25, n), np.ones(n)], 1) * rng.uniform(40, 90, (n, 1))
+        X = (Rlw.T @ ((Ri.T @ (xc - ti).T).T - tlw).T).T
+        x, y = xc[:, 0] / xc[:, 2], xc[:, 1] / xc[:, 2]
+        r2 = x * x + y * y
+        d = 1 + cams[i, 16] * r2 + cams[i, 17] * r2 * r2
+        uv.append(np.stack([fx * x * d + 960, fx * 1.01 * y * d + 540], 1))
+        if i == 2:                                                # pixels unrelated to the points: no pose reprojects them within 300 px RMS
+            uv[-1] = np.stack([rng.uniform(0, 1920, n), rng.uniform(0, 1080, n)], 1)
+        xyz.append(X)
+        view.append(np.full(n, i))
+    uv, xyz, view = np.concatenate(uv), np.concatenate(xyz), np.concatenate(view)
+    sh = rng.permutation(len(view))                               # any order of the rows: grouped by view inside
+    got, used = ptz.init_trans_local_to_world(cams, uv[sh], xyz[sh], view[sh])
+    assert used == 3
+    assert np.abs(_rodrigues(got[:3]) - Rlw).max() < 1e-5
+    assert np.abs(got[3:] - tlw).max() < 2e-3
+    # no annotated view passes -> zeros, -1 (the reference leaves tlw_param_ at zero, :628-632)
+    z, u0 = ptz.init_trans_local_to_world(cams[:2], uv[view < 2], xyz[view < 2], view[view < 2])
+    assert u0 == -1 and not z.any()
+    z, u0 = ptz.init_trans_local_to_world(cams, np.zeros((0, 2)), np.zeros((0, 3)), np.zeros(0, int))
+    assert u0 == -1 and not z.any()

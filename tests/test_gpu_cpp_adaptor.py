@@ -200,6 +200,9 @@ def test_georeferencing_with_epnp_initialisation(tmp_path, orc):
     assert np.abs(tlw0[:3] - gt[:3]).max() < 0.05, (tlw0, gt)
     assert np.abs(tlw0[3:] - gt[3:]).max() < 0.1 * np.linalg.norm(gt[3:]) + 3.0, (tlw0, gt)
     assert head[4] < 2.0  # final 2d-3d reprojection RMS [px]
+    # the same initialisation through the C ABI (ptzgeo_init_tlw), as the Python mirror's from_matches uses it
+    t_abi, used = ptz.init_trans_local_to_world(cams, p.pt_uv, p.pt_xyz, p.pt_view)
+    assert used >= 0 and np.abs(t_abi - tlw0).max() <= 1e-9 * (1 + np.abs(tlw0).max())
     q = synth.make_config(1, scale=0.5, num_pts3d=18, pts3d_views=3)
     q.tlw0 = tlw0.copy()
     want = ptz.ba_solve(q, max_num_iterations=200)

@@ -72,6 +72,14 @@ def test_invalid_arguments_are_rejected_without_touching_the_gpu():
     assert L.ptzba_solve(C.byref(cq), C.byref(o), C.byref(rq)) == abi.PTZ_ERR_UNSUPPORTED
     c.factor_type = 7
     assert L.ptzba_solve(C.byref(c), C.byref(o), C.byref(r)) == abi.PTZ_ERR_INVALID
+    # ptzgeo_init_tlw: null output, negative count, decreasing offsets
+    tlw, used, off = np.zeros(6), C.c_int32(7), np.array([0, 4, 2], np.int64)
+    cams, uv, xyz = np.zeros((2, 21)), np.zeros((4, 2), np.float32), np.zeros((4, 3))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.ptzgeo_init_tlw(C.c_int32(2), vp(cams), vp(off), vp(uv), vp(xyz), None, C.byref(used)) == abi.PTZ_ERR_INVALID
+    assert L.ptzgeo_init_tlw(C.c_int32(-1), vp(cams), vp(off), vp(uv), vp(xyz), vp(tlw), C.byref(used)) == abi.PTZ_ERR_INVALID
+    assert L.ptzgeo_init_tlw(C.c_int32(2), vp(cams), vp(off), vp(uv), vp(xyz), vp(tlw), C.byref(used)) == abi.PTZ_ERR_INVALID
+    assert L.ptzgeo_init_tlw(C.c_int32(0), None, None, None, None, vp(tlw), C.byref(used)) == 0 and used.value == -1
 
 
 def test_no_cpu_fallback():

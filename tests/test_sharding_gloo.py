@@ -38,6 +38,26 @@ def _worker(rank, world, port, out):
     ok = ok and abs(cam[-3].item() - ref.cost) <= 1e-12 * ref.cost and int(cam[-2].item()) == full.M and int(cam[-1].item()) == full.P
     ray_g = e.gradient[full.V * ncv :].reshape(-1, 3)
     ok = ok and np.abs(ray_g - ref.gradient[full.V * ncv :].reshape(-1, 3)[lo : lo + shard.P]).max() <= 1e-9 * np.abs(ref.gradient).max()
+    # georeferencing on a sharded problem ("2d-3d terms computed on rank 0 and included in the all-reduce"): every rank holds
+    # all annotated points (shard_tracks keeps them), rank 0 alone evaluates them; camera blocks, cost and the T_l_w gradient then sum
+    # to the unsharded evaluation
+    import dataclasses
+
+    geo = synth.make_config(1, scale=0.3, num_pts3d=12, pts3d_views=3)
+    geo = geo.with_params(ray=orc.ba_init_rays(geo))
+    gs = geo.shard_tracks(rank, world)
+    ok = ok and gs.A == geo.A and np.array_equal(gs.pt_view, geo.pt_view)
+    mine = gs if rank == 0 else dataclasses.replace(gs, pt_uv=None, pt_xyz=None, pt_view=None, tlw0=None)
+    eg = orc.ba_eval(mine)
+    nv = geo.V * geo.ncv
+    tl = eg.gradient[-6:] if rank == 0 else np.zeros(6)
+    red = torch.from_numpy(np.concatenate([eg.gradient[:nv], tl, [eg.cost]]))
+    dist.all_reduce(red)
+    rg = orc.ba_eval(geo)
+    gmax = np.abs(rg.gradient).max()
+    ok = ok and np.abs(red[:nv].numpy() - rg.gradient[:nv]).max() <= 1e-9 * gmax
+    ok = ok and np.abs(red[nv : nv + 6].numpy() - rg.gradient[-6:]).max() <= 1e-9 * gmax and np.abs(rg.gradient[-6:]).max() > 0
+    ok = ok and abs(red[-1].item() - rg.cost) <= 1e-12 * rg.cost
     # reloc batch: contiguous shards balanced by matches, no exchange
     b = synth.make_reloc_batch(200, n_min=8, n_max=64)
     mine = b.shard(rank, world)

@@ -539,7 +539,51 @@ def make_georef_kat(seed=123):
     np.savez_compressed(os.path.join(HERE, "georef_kat.npz"), **out)
 
 
+def make_distdisp_kat(seed=77):
+    """PTZRayDistDispFactor (ptzray_optimizer.cc:202-264): the global displacement polynomial disp[3] shared by every residual block, on a
+    small scene where it is observable (synth.make_distdisp_scene: zoom sweep, true displacement in the data), minimised by scipy with the
+    cv2 functors.  Free gauge: the test compares the cost, relative rotations and the displacement at a mid-range focal length."""
+    t = 3
+    p = synth.make_distdisp_scene(V=8, P=90, seed=seed)
+    V, P, M = p.V, p.P, p.M
+    ray0 = np.zeros((P, 3))
+    cnt = np.zeros(P)
+    for k in range(M):  # Pix2Ray
+        i = p.obs_view[k]
+        K = np.array([[p.intr[i, 0], 0, p.intr[i, 2]], [0, p.intr[i, 1], p.intr[i, 3]], [0, 0, 1.0]])
+        v = np.linalg.inv(np_rod(p.ext[i, :3])) @ np.linalg.inv(K) @ np.array([p.obs_uv[k, 0], p.obs_uv[k, 1], 1.0], np.float64)
+        ray0[p.obs_track[k]] += v / np.linalg.norm(v)
+        cnt[p.obs_track[k]] += 1
+    ray0 /= cnt[:, None]
+    ray0 /= np.linalg.norm(ray0, axis=1, keepdims=True)
+
+    def unpack(z):
+        intr, ext = p.intr.copy(), p.ext.copy()
+        intr[:, 0] = z[:V]
+        intr[:, 4] = z[V : 2 * V]
+        ext[:, :3] = z[2 * V : 5 * V].reshape(V, 3)
+        return intr, ext, z[5 * V : 5 * V + 3 * P].reshape(P, 3), z[5 * V + 3 * P :]
+
+    def fun(z):
+        intr, ext, ray, disp = unpack(z)
+        return np.concatenate([np.sqrt(p.track_weight[p.obs_track[k]]) * ba_ray_cv(t, intr[p.obs_view[k]], ext[p.obs_view[k]], ray[p.obs_track[k]], disp, p.obs_uv[k])
+                               for k in range(M)])
+
+    z0 = np.concatenate([p.intr[:, 0], p.intr[:, 4], p.ext[:, :3].ravel(), ray0.ravel(), np.zeros(3)])
+    s = least_squares(fun, z0, method="trf", xtol=1e-15, ftol=1e-15, gtol=1e-13, x_scale="jac", max_nfev=600)
+    intr, ext, ray, disp = unpack(s.x)
+    out = {}
+    for nm in ("intr", "ext", "obs_uv", "obs_view", "obs_track", "track_weight"):
+        out[f"dd_{nm}"] = getattr(p, nm)
+    out["dd_sol_intr"], out["dd_sol_ext"], out["dd_sol_disp"], out["dd_cost"], out["dd_status"], out["dd_nfev"] = intr, ext, disp, s.cost, s.status, s.nfev
+    print("distdisp", s.cost, s.status, s.nfev, disp, flush=True)
+    np.savez_compressed(os.path.join(HERE, "distdisp_kat.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--distdisp-only" in sys.argv:
+        make_distdisp_kat()
+        sys.exit(0)
     if "--georef-only" in sys.argv:
         make_georef_kat()
         sys.exit(0)
@@ -552,4 +596,5 @@ if __name__ == "__main__":
     make_lm_kat()
     make_shared_kat()
     make_georef_kat()
+    make_distdisp_kat()
     print("golden vectors written to", HERE)
